@@ -1,0 +1,133 @@
+/*
+ * pr_oracle.h — CPU oracle for the plane-RANSAC hot path.  TEST INFRASTRUCTURE ONLY.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load
+ * this library.  The product (dialog_b200/, include/) never links, imports or calls it.
+ *
+ * PARITY UNPINNED: the path named by BASELINE.json (pcl::SACSegmentation<PointXYZ> with
+ * SACMODEL_PLANE / SAC_RANSAC, iterated with pcl::ExtractIndices) is PCL 1.8 library behaviour.
+ * PCL is an un-vendored dependency of the reference (Dialog/PropertySheet-success.props:6,11 pins
+ * "pcl-1.8" only), it is absent from /root/reference and from this image, and the reference holds no
+ * tests, golden vectors or recorded outputs for it.  This file restates the
+ * published PCL 1.8 algorithm; every function names the PCL source it follows.  What IS pinned:
+ * the mt19937 stream (C++11 [rand.predef] 10000th-value check and numpy's MT19937), analytic
+ * known-answer cases, and the reference's only fixture for this path (Dialog/double_shadow.pcd).
+ *
+ * Reference-side sites that compute the same quantities (for parity reading):
+ *   point-to-plane threshold test  Dialog/PlaneDetect.h:1442-1448, 2019-2023, 1902
+ *   peel / order-preserving compaction  Dialog/PlaneDetect.h:1560-1566
+ *   least-squares plane refit (pcl::computePointNormal)  Dialog/PlaneDetect.h:1084,1130,1386,1485
+ *   parameters T_dist_point_plane / T_num_of_single_plane  Dialog/config.txt:29,20
+ */
+#ifndef PR_ORACLE_H
+#define PR_ORACLE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* == pcl::PointXYZ (16 bytes; Dialog/HeaderFile.h:53-54).  w is padding and is treated as 1. */
+typedef struct { float x, y, z, w; } orc_point;
+
+/* Order in which the 4-term FP32 dot product coeff·(x,y,z,1) is evaluated.
+ *   ORC_DOT_PCL_SSE2: (a*x + c*z) + (b*y + d), every product and sum rounded separately — Eigen's
+ *                     4-wide SSE2 packet product + predux (movehl/add, shuffle/add) as PCL 1.8 built
+ *                     with MSVC v140 executes it.
+ *   ORC_DOT_FMA:      fma(a, x, fma(b, y, fma(c, z, d))) — three fused multiply-adds, the order the
+ *                     CUDA scoring kernel uses in its default mode. */
+enum { ORC_DOT_PCL_SSE2 = 0, ORC_DOT_FMA = 1 };
+
+/* How optimizeModelCoefficients accumulates the moments.
+ *   ORC_REFIT_PCL_FLOAT: PCL 1.8 computeMeanAndCovarianceMatrix — nine float accumulators summed
+ *                        sequentially, cov = E[ab] - E[a]E[b], float eigen33.
+ *   ORC_REFIT_FIXED:     order-independent exact integer moments of the coordinates quantised to a
+ *                        2^-30 grid of the cloud extent about a pivot, eigen33 in double.  This is
+ *                        the arithmetic a parallel device can reproduce bit for bit. */
+enum { ORC_REFIT_PCL_FLOAT = 0, ORC_REFIT_FIXED = 1 };
+
+typedef struct {
+  double distance_threshold;  /* SACSegmentation::setDistanceThreshold(double)              */
+  int max_iterations;         /* SACSegmentation::setMaxIterations (PCL default 50)           */
+  int min_plane_size;         /* peel stop rule; reference analogue T_num_of_single_plane    */
+  double probability;         /* SACSegmentation::setProbability (default 0.99); 1.0 = no early exit */
+  int optimize_coefficients;  /* SACSegmentation::setOptimizeCoefficients (default true)      */
+  unsigned seed;              /* 12345u == PCL's non-random model seed                        */
+  int max_planes;             /* peel loop bound                                              */
+  int dot_order;              /* ORC_DOT_*                                                    */
+  int refit_mode;             /* ORC_REFIT_*                                                  */
+} orc_params;
+
+/* Everything segment() decided, for parity tests. */
+typedef struct {
+  int ok;                /* computeModel returned true                                   */
+  int iterations;        /* RandomSampleConsensus::iterations_ at exit                   */
+  int draws;             /* drawIndexSample calls made (good + rejected)                 */
+  int skipped;           /* skipped_count                                                */
+  int best_sample[3];    /* model_                                                       */
+  int best_count;        /* n_best_inliers_count                                         */
+  float raw_coeff[4];    /* model_coefficients_ before optimizeModelCoefficients         */
+  int n_inliers_raw;     /* |selectWithinDistance(raw_coeff)|                            */
+  int n_inliers;         /* final inlier count                                           */
+  int scale_exp;         /* ORC_REFIT_FIXED: s (grid = 2^-s)                             */
+} orc_trace;
+
+/* ---- mt19937 (boost::mt19937 == std::mt19937) ------------------------------------------- */
+typedef struct { uint32_t mt[624]; int idx; } orc_mt19937;
+void orc_mt_seed(orc_mt19937* g, uint32_t seed);
+uint32_t orc_mt_next(orc_mt19937* g);
+
+/* ---- SampleConsensusModel sampling (sac_model.h: getSamples / drawIndexSample / rnd) ----- */
+typedef struct { orc_mt19937 rng; int32_t* shuffled; size_t n; } orc_sampler;
+int orc_sampler_init(orc_sampler* s, size_t n, uint32_t seed);
+void orc_sampler_free(orc_sampler* s);
+void orc_sampler_draw(orc_sampler* s, int32_t idx[3]);
+/* Convenience for tests: the first n_draws raw draws for a cloud of n points. */
+int orc_draw_sequence(size_t n, uint32_t seed, int n_draws, int32_t* triples /* 3*n_draws */);
+
+/* ---- SampleConsensusModelPlane (sac_model_plane.hpp) ------------------------------------- */
+int orc_is_sample_good(const orc_point* cloud, const int32_t idx[3]);
+int orc_compute_model(const orc_point* cloud, const int32_t idx[3], float coeff[4]);
+float orc_signed_distance(const float coeff[4], const orc_point* p, int dot_order);
+void orc_residuals(const orc_point* cloud, size_t n, const float coeff[4], int dot_order, float* out);
+int64_t orc_count_within(const orc_point* cloud, size_t n, const float coeff[4], double t, int dot_order);
+/* Same loop, OpenMP-parallel over points (NOT how PCL 1.8 runs; used by the multi-thread CPU arm). */
+int64_t orc_count_within_mt(const orc_point* cloud, size_t n, const float coeff[4], double t, int dot_order);
+size_t orc_select_within(const orc_point* cloud, size_t n, const float coeff[4], double t, int dot_order,
+                         int32_t* out);
+/* counts[k] for K models, scalar PCL loop per model; threads > 1 uses orc_count_within_mt. */
+void orc_count_batch(const orc_point* cloud, size_t n, const float* coeffs /* 4*K */, int K, double t,
+                     int dot_order, int threads, int32_t* counts);
+
+/* ---- optimizeModelCoefficients ------------------------------------------------------------ */
+int orc_refit_pcl_float(const orc_point* cloud, const int32_t* idx, size_t n_idx, const float coeff_in[4],
+                        float coeff_out[4]);
+/* Extent exponent of a cloud: s such that |x - pivot| * 2^s < 2^30 for every finite point. */
+int orc_fixed_scale_exp(const orc_point* cloud, size_t n);
+/* moments_out (optional, 19 x int64): n, Sx,Sy,Sz, then (hi,lo-as-int64) pairs... see .c */
+int orc_refit_fixed(const orc_point* cloud, const int32_t* idx, size_t n_idx, const float pivot[3],
+                    int scale_exp, const float coeff_in[4], float coeff_out[4], int64_t* moments_out);
+/* The host half of the fixed refit alone: integer moments -> plane.  Exposed so tests can feed it
+ * the device's moments.  m = {n, Sx, Sy, Sz, Sxx_hi, Sxx_lo, Sxy_hi, Sxy_lo, ... Szz_hi, Szz_lo}
+ * with S_ab = hi * 2^32 + lo. */
+int orc_plane_from_moments(const int64_t m[16], const float pivot[3], int scale_exp, float coeff_out[4]);
+
+/* ---- RandomSampleConsensus::computeModel + SACSegmentation::segment ----------------------- */
+int orc_segment(const orc_point* cloud, size_t n, const orc_params* prm, int scale_exp_or_min,
+                float coeff[4], int32_t* inliers /* cap n */, size_t* n_inliers, orc_trace* trace);
+
+/* ---- segment + ExtractIndices peel loop ---------------------------------------------------
+ * coeffs: 4*max_planes; inlier_cur: indices into the cloud of that round (what PCL's loop yields);
+ * inlier_orig: the same points as indices into the input cloud; plane_offsets: max_planes+1;
+ * remaining (optional): cap n points; traces (optional): max_planes+1 entries (the last, rejected,
+ * segment call is traced too). */
+int orc_extract_planes(const orc_point* cloud, size_t n, const orc_params* prm, float* coeffs,
+                       int32_t* inlier_cur, int32_t* inlier_orig, size_t idx_cap, size_t* plane_offsets,
+                       int* n_planes, orc_point* remaining, size_t* n_remaining, orc_trace* traces);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
