@@ -1,0 +1,4 @@
+"""dialog_b200 — B200 (sm_100a) backend for czh55/Dialog's plane-detection path (RANSAC + peel)."""
+from .plane_detect import (DOT_FMA, DOT_PCL_SSE2, Extraction, Plane, PlaneRansac, PlaneRansacError,  # noqa: F401
+                           detect_planes, host_draw_triples, host_plane_from_moments, host_replay,
+                           host_shard_range, make_params)

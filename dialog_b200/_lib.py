@@ -1,0 +1,128 @@
+"""ctypes binding of libplane_ransac.so (include/plane_ransac.h).
+
+The library is the product: if it is missing this module raises — there is no Python or CPU
+implementation of the kernels to fall back to.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libplane_ransac.so")
+
+UNIQUE_ID_BYTES = 128
+DOT_PCL_SSE2 = 0
+DOT_FMA = 1
+
+# every symbol include/plane_ransac.h declares (checked by tests/test_abi.py)
+SYMBOLS = [
+    "plane_ransac_abi_version", "plane_ransac_last_error", "plane_ransac_default_params",
+    "plane_ransac_create", "plane_ransac_destroy", "plane_ransac_set_cloud", "plane_ransac_set_cloud_device",
+    "plane_ransac_cloud_size", "plane_ransac_score", "plane_ransac_segment_one", "plane_ransac_extract_planes",
+    "plane_ransac_remaining", "plane_ransac_set_cloud_batch", "plane_ransac_segment_batch",
+    "plane_ransac_comm_unique_id", "plane_ransac_comm_init", "plane_ransac_shard_info",
+    "plane_ransac_profile_enable", "plane_ransac_profile_reset", "plane_ransac_profile_get",
+    "plane_ransac_measure_ffma_peak", "plane_ransac_measure_copy_bw", "plane_ransac_flush_l2",
+    "plane_ransac_host_draw_triples", "plane_ransac_host_replay", "plane_ransac_host_shard_range",
+    "plane_ransac_host_plane_from_moments",
+]
+
+
+class PrParams(C.Structure):
+    _fields_ = [
+        ("distance_threshold", C.c_double),
+        ("max_iterations", C.c_int),
+        ("min_plane_size", C.c_int),
+        ("probability", C.c_double),
+        ("optimize_coefficients", C.c_int),
+        ("seed", C.c_uint),
+        ("max_planes", C.c_int),
+        ("dot_order", C.c_int),
+    ]
+
+
+class PrSegmentInfo(C.Structure):
+    _fields_ = [
+        ("ok", C.c_int),
+        ("iterations", C.c_int),
+        ("draws", C.c_int),
+        ("skipped", C.c_int),
+        ("best_sample", C.c_int * 3),
+        ("best_count", C.c_int),
+        ("raw_coeff", C.c_float * 4),
+        ("n_inliers_raw", C.c_int),
+        ("n_inliers", C.c_int),
+        ("scale_exp", C.c_int),
+        ("n_scored", C.c_int),
+        ("n_cloud", C.c_longlong),
+    ]
+
+
+class PrProfile(C.Structure):
+    _fields_ = [(n, C.c_double) for n in ("ms_stage", "ms_models", "ms_score", "ms_refit", "ms_compact", "ms_other")] + \
+               [(n, C.c_longlong) for n in ("launches_stage", "launches_models", "launches_score", "launches_refit",
+                                            "launches_compact", "launches_other", "pairs_scored", "points_refit",
+                                            "points_compact", "bytes_compact", "bytes_refit")]
+
+
+class PlaneRansacError(RuntimeError):
+    def __init__(self, code: int, message: str):
+        super().__init__(f"plane_ransac error {code}: {message}")
+        self.code = code
+
+
+_lib = None
+
+
+def load():
+    """Load the shared library, building nothing: a missing library is a hard error."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -m dialog_b200.build` "
+            "(there is no CPU or PyTorch fallback for the CUDA kernels)")
+    L = C.CDLL(LIB_PATH)
+    vp, sz = C.c_void_p, C.c_size_t
+    L.plane_ransac_abi_version.restype = C.c_int
+    L.plane_ransac_last_error.restype = C.c_char_p
+    L.plane_ransac_default_params.argtypes = [C.POINTER(PrParams)]
+    L.plane_ransac_default_params.restype = None
+    L.plane_ransac_create.argtypes = [C.POINTER(vp), C.c_int]
+    L.plane_ransac_destroy.argtypes = [vp]
+    L.plane_ransac_destroy.restype = None
+    L.plane_ransac_set_cloud.argtypes = [vp, vp, sz]
+    L.plane_ransac_set_cloud_device.argtypes = [vp, vp, sz]
+    L.plane_ransac_cloud_size.argtypes = [vp, C.POINTER(sz), C.POINTER(sz)]
+    L.plane_ransac_score.argtypes = [vp, vp, C.c_int, C.c_double, C.c_int, vp, vp, vp]
+    L.plane_ransac_segment_one.argtypes = [vp, C.POINTER(PrParams), vp, vp, sz, C.POINTER(sz), C.POINTER(PrSegmentInfo)]
+    L.plane_ransac_extract_planes.argtypes = [vp, C.POINTER(PrParams), vp, vp, vp, sz, vp, C.POINTER(C.c_int), vp]
+    L.plane_ransac_remaining.argtypes = [vp, vp, sz, C.POINTER(sz)]
+    L.plane_ransac_set_cloud_batch.argtypes = [vp, vp, sz, sz]
+    L.plane_ransac_segment_batch.argtypes = [vp, C.POINTER(PrParams), vp, vp, vp]
+    L.plane_ransac_comm_unique_id.argtypes = [vp]
+    L.plane_ransac_comm_init.argtypes = [vp, C.c_int, C.c_int, vp]
+    L.plane_ransac_shard_info.argtypes = [vp] + [C.POINTER(C.c_longlong)] * 4
+    L.plane_ransac_profile_enable.argtypes = [vp, C.c_int]
+    L.plane_ransac_profile_reset.argtypes = [vp]
+    L.plane_ransac_profile_get.argtypes = [vp, C.POINTER(PrProfile)]
+    L.plane_ransac_measure_ffma_peak.argtypes = [vp, C.POINTER(C.c_double)]
+    L.plane_ransac_measure_copy_bw.argtypes = [vp, sz, C.POINTER(C.c_double)]
+    L.plane_ransac_flush_l2.argtypes = [vp]
+    L.plane_ransac_host_draw_triples.argtypes = [sz, C.c_uint, C.c_int, vp]
+    L.plane_ransac_host_replay.argtypes = [vp, vp, C.c_int, C.c_longlong, C.c_int, C.c_double] + [C.POINTER(C.c_int)] * 5
+    L.plane_ransac_host_shard_range.argtypes = [C.c_longlong, C.c_int, C.c_int, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]
+    L.plane_ransac_host_plane_from_moments.argtypes = [vp, vp, C.c_int, vp]
+    for name in SYMBOLS:
+        fn = getattr(L, name)
+        if fn.restype is C.c_int and name not in ("plane_ransac_abi_version",):
+            fn.restype = C.c_int
+    _lib = L
+    return L
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        raise PlaneRansacError(rc, load().plane_ransac_last_error().decode("utf-8", "replace"))

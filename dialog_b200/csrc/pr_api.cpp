@@ -1,0 +1,937 @@
+// pr_api.cpp — the extern "C" boundary (include/plane_ransac.h) and the per-call orchestration:
+// host draws PCL's sample stream, the device scores it, the host replays PCL's sequential decisions,
+// the device refits and peels.  NCCL (loaded at run time) sums counts and moments when the cloud is
+// sharded over ranks.  There is no CPU implementation of the device work in this file or anywhere
+// in the product: without a CUDA device every entry point that needs one fails.
+#include "../../include/plane_ransac.h"
+
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <algorithm>
+#include <climits>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "pr_host.hpp"
+#include "pr_kernels.h"
+
+namespace {
+
+thread_local std::string g_error;
+
+int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_error = buf;
+  return code;
+}
+
+#define PR_CUDA(expr)                                                                                   \
+  do {                                                                                                  \
+    cudaError_t e__ = (expr);                                                                           \
+    if (e__ != cudaSuccess) return fail(PR_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+  } while (0)
+
+#define PR_TRY(expr)              \
+  do {                            \
+    int rc__ = (expr);            \
+    if (rc__ != PR_OK) return rc__; \
+  } while (0)
+
+// ---- NCCL, resolved at run time so the library loads on hosts without it ------------------------
+struct NcclApi {
+  void* handle = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+
+NcclApi g_nccl;
+
+int load_nccl() {
+  if (g_nccl.handle) return PR_OK;
+  void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) return fail(PR_ERR_COMM, "cannot load libnccl.so.2: %s", dlerror());
+  NcclApi a;
+  a.handle = h;
+#define PR_SYM(field, name)                                                        \
+  *(void**)(&a.field) = dlsym(h, name);                                             \
+  if (!a.field) return fail(PR_ERR_COMM, "libnccl is missing symbol %s", name)
+  PR_SYM(GetUniqueId, "ncclGetUniqueId");
+  PR_SYM(CommInitRank, "ncclCommInitRank");
+  PR_SYM(CommDestroy, "ncclCommDestroy");
+  PR_SYM(AllReduce, "ncclAllReduce");
+  PR_SYM(AllGather, "ncclAllGather");
+  PR_SYM(GetErrorString, "ncclGetErrorString");
+#undef PR_SYM
+  g_nccl = a;
+  return PR_OK;
+}
+
+#define PR_NCCL(expr)                                                                                  \
+  do {                                                                                                 \
+    ncclResult_t r__ = (expr);                                                                         \
+    if (r__ != ncclSuccess) return fail(PR_ERR_COMM, "%s failed: %s", #expr, g_nccl.GetErrorString(r__)); \
+  } while (0)
+
+enum KClass { KC_STAGE = 0, KC_MODELS, KC_SCORE, KC_REFIT, KC_COMPACT, KC_OTHER, KC_COUNT };
+
+struct TimedSpan {
+  cudaEvent_t a, b;
+  int cls;
+};
+
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t cap = 0;  // elements
+};
+
+template <typename T>
+struct PinBuf {
+  T* p = nullptr;
+  size_t cap = 0;
+};
+
+}  // namespace
+
+struct plane_ransac_ctx {
+  int device = 0;
+  int num_sms = 148;
+  cudaStream_t stream = nullptr;
+
+  // staged cloud (immutable) and the two peel buffers
+  pr::CloudView staged, work[2];
+  DevBuf<float> staged_mem, work_mem[2];
+  DevBuf<int32_t> work_orig[2];
+  size_t n_staged = 0;
+  bool have_cloud = false;
+  pr::CloudView current;
+  size_t n_current = 0;
+  int scale_exp = 0;
+  uint32_t bbox_keys[6] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0, 0, 0};
+
+  DevBuf<float4> aos;        // AoS staging (upload / download)
+  DevBuf<uint32_t> d_bbox;   // 6 keys
+  // per-call hypothesis state (capacity in draws)
+  size_t draw_cap = 0;
+  DevBuf<int32_t> d_triples, d_counts, d_good;
+  DevBuf<int4> d_sample_pts;
+  DevBuf<float4> d_hyps;
+  PinBuf<int32_t> h_triples, h_counts, h_good;
+  DevBuf<pr::RefitOut> d_refit;
+  PinBuf<pr::RefitOut> h_refit;
+  DevBuf<long long> d_totals;     // [0..2) local totals, [2 .. 2 + 2*ranks) gathered
+  PinBuf<long long> h_totals;
+  DevBuf<unsigned char> d_scratch;
+  DevBuf<int32_t> d_inl_cur, d_inl_orig;
+  PinBuf<float4> h_small;  // raw coefficient read-back
+  DevBuf<float4> d_flush;
+
+  // batch of small clouds
+  size_t batch_clouds = 0, batch_n = 0, batch_stride = 0;
+  DevBuf<float> batch_mem;
+  pr::CloudView batch_view;
+
+  // sharding
+  ncclComm_t comm = nullptr;
+  int n_ranks = 1, rank = 0;
+  long long n_global_staged = 0, first_staged = 0, n_global_current = 0, first_current = 0;
+  bool global_valid = false;
+
+  // measurement
+  bool profiling = false;
+  std::vector<TimedSpan> spans;
+  pr_profile prof;
+};
+
+namespace {
+
+template <typename T>
+int dev_reserve(DevBuf<T>& b, size_t n, bool keep = false, cudaStream_t s = nullptr) {
+  if (n <= b.cap && b.p) return PR_OK;
+  size_t want = std::max(n, (size_t)16);
+  T* np = nullptr;
+  if (cudaMalloc(&np, want * sizeof(T)) != cudaSuccess) {
+    cudaGetLastError();
+    return fail(PR_ERR_OOM, "cudaMalloc of %zu bytes failed", want * sizeof(T));
+  }
+  if (b.p) {
+    if (keep && b.cap) {
+      if (cudaMemcpyAsync(np, b.p, b.cap * sizeof(T), cudaMemcpyDeviceToDevice, s) != cudaSuccess ||
+          cudaStreamSynchronize(s) != cudaSuccess)
+        return fail(PR_ERR_CUDA, "device buffer grow copy failed");
+    }
+    cudaFree(b.p);
+  }
+  b.p = np;
+  b.cap = want;
+  return PR_OK;
+}
+
+template <typename T>
+void dev_free(DevBuf<T>& b) {
+  if (b.p) cudaFree(b.p);
+  b.p = nullptr;
+  b.cap = 0;
+}
+
+template <typename T>
+int pin_reserve(PinBuf<T>& b, size_t n, bool keep = false) {
+  if (n <= b.cap && b.p) return PR_OK;
+  size_t want = std::max(n, (size_t)16);
+  T* np = nullptr;
+  if (cudaMallocHost(&np, want * sizeof(T)) != cudaSuccess) {
+    cudaGetLastError();
+    return fail(PR_ERR_OOM, "cudaMallocHost of %zu bytes failed", want * sizeof(T));
+  }
+  if (b.p) {
+    if (keep && b.cap) std::memcpy(np, b.p, b.cap * sizeof(T));
+    cudaFreeHost(b.p);
+  }
+  b.p = np;
+  b.cap = want;
+  return PR_OK;
+}
+
+template <typename T>
+void pin_free(PinBuf<T>& b) {
+  if (b.p) cudaFreeHost(b.p);
+  b.p = nullptr;
+  b.cap = 0;
+}
+
+// RAII span: records CUDA events around a kernel class when profiling, and counts launches.
+struct Span {
+  plane_ransac_ctx* c;
+  int cls;
+  cudaEvent_t a = nullptr, b = nullptr;
+  Span(plane_ransac_ctx* ctx, int k, int launches) : c(ctx), cls(k) {
+    long long* lc[KC_COUNT] = {&c->prof.launches_stage, &c->prof.launches_models, &c->prof.launches_score,
+                               &c->prof.launches_refit, &c->prof.launches_compact, &c->prof.launches_other};
+    *lc[k] += launches;
+    if (c->profiling) {
+      cudaEventCreate(&a);
+      cudaEventCreate(&b);
+      cudaEventRecord(a, c->stream);
+    }
+  }
+  ~Span() {
+    if (c->profiling) {
+      cudaEventRecord(b, c->stream);
+      c->spans.push_back({a, b, cls});
+    }
+  }
+};
+
+void collect_spans(plane_ransac_ctx* c) {
+  if (c->spans.empty()) return;
+  cudaStreamSynchronize(c->stream);
+  double* ms[KC_COUNT] = {&c->prof.ms_stage, &c->prof.ms_models, &c->prof.ms_score,
+                          &c->prof.ms_refit, &c->prof.ms_compact, &c->prof.ms_other};
+  for (auto& s : c->spans) {
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, s.a, s.b) == cudaSuccess) *ms[s.cls] += t;
+    cudaEventDestroy(s.a);
+    cudaEventDestroy(s.b);
+  }
+  c->spans.clear();
+}
+
+int check_ctx(plane_ransac_ctx* c) {
+  if (!c) return fail(PR_ERR_INVALID, "null context");
+  PR_CUDA(cudaSetDevice(c->device));
+  return PR_OK;
+}
+
+int check_params(const pr_params* p) {
+  if (!p) return fail(PR_ERR_INVALID, "null params");
+  if (!(p->distance_threshold > 0.0) || !std::isfinite(p->distance_threshold))
+    return fail(PR_ERR_INVALID, "distance_threshold must be finite and > 0");
+  if (p->max_iterations < 0) return fail(PR_ERR_INVALID, "max_iterations must be >= 0");
+  if (!(p->probability > 0.0) || p->probability > 1.0) return fail(PR_ERR_INVALID, "probability must be in (0, 1]");
+  if (p->dot_order != PR_DOT_PCL_SSE2 && p->dot_order != PR_DOT_FMA) return fail(PR_ERR_INVALID, "unknown dot_order");
+  if (p->max_planes < 0) return fail(PR_ERR_INVALID, "max_planes must be >= 0");
+  return PR_OK;
+}
+
+pr::CloudView planes_view(float* base, int32_t* orig, size_t cap) {
+  pr::CloudView v;
+  v.x = base;
+  v.y = base + cap;
+  v.z = base + 2 * cap;
+  v.orig = orig;
+  v.cap = cap;
+  return v;
+}
+
+int reserve_draws(plane_ransac_ctx* c, size_t need, bool keep) {
+  if (need <= c->draw_cap) return PR_OK;
+  size_t cap = std::max(need, c->draw_cap * 2);
+  PR_TRY(dev_reserve(c->d_triples, 3 * cap, keep, c->stream));
+  PR_TRY(dev_reserve(c->d_sample_pts, 3 * cap, keep, c->stream));
+  PR_TRY(dev_reserve(c->d_hyps, cap, keep, c->stream));
+  PR_TRY(dev_reserve(c->d_counts, cap, keep, c->stream));
+  PR_TRY(dev_reserve(c->d_good, cap, keep, c->stream));
+  PR_TRY(pin_reserve(c->h_triples, 3 * cap, keep));
+  PR_TRY(pin_reserve(c->h_counts, cap, keep));
+  PR_TRY(pin_reserve(c->h_good, cap, keep));
+  c->draw_cap = cap;
+  return PR_OK;
+}
+
+int reserve_small(plane_ransac_ctx* c) {
+  PR_TRY(dev_reserve(c->d_refit, 1));
+  PR_TRY(pin_reserve(c->h_refit, 1));
+  PR_TRY(dev_reserve(c->d_totals, 2 + 2 * (size_t)std::max(1, c->n_ranks)));
+  PR_TRY(pin_reserve(c->h_totals, 2 + 2 * (size_t)std::max(1, c->n_ranks)));
+  PR_TRY(pin_reserve(c->h_small, 4));
+  PR_TRY(dev_reserve(c->d_bbox, 8));
+  return PR_OK;
+}
+
+// Global size / offset / bounding box of a sharded staged cloud.
+int refresh_global(plane_ransac_ctx* c) {
+  if (!c->have_cloud) return PR_OK;
+  if (!c->comm) {
+    c->n_global_staged = (long long)c->n_staged;
+    c->first_staged = 0;
+    c->scale_exp = pr::scale_exp_from_bbox_keys(c->bbox_keys);
+    c->global_valid = true;
+    return PR_OK;
+  }
+  PR_TRY(reserve_small(c));
+  // allgather of local sizes
+  long long* d = c->d_totals.p;
+  c->h_totals.p[0] = (long long)c->n_staged;
+  PR_CUDA(cudaMemcpyAsync(d, c->h_totals.p, sizeof(long long), cudaMemcpyHostToDevice, c->stream));
+  PR_NCCL(g_nccl.AllGather(d, d + 2, 1, ncclInt64, c->comm, c->stream));
+  // bounding box: min over keys[0..3), max over keys[3..6)
+  PR_CUDA(cudaMemcpyAsync(c->d_bbox.p, c->bbox_keys, 6 * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+  PR_NCCL(g_nccl.AllReduce(c->d_bbox.p, c->d_bbox.p, 3, ncclUint32, ncclMin, c->comm, c->stream));
+  PR_NCCL(g_nccl.AllReduce(c->d_bbox.p + 3, c->d_bbox.p + 3, 3, ncclUint32, ncclMax, c->comm, c->stream));
+  uint32_t keys[6];
+  PR_CUDA(cudaMemcpyAsync(c->h_totals.p + 2, d + 2, c->n_ranks * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
+  PR_CUDA(cudaMemcpyAsync(keys, c->d_bbox.p, sizeof(keys), cudaMemcpyDeviceToHost, c->stream));
+  PR_CUDA(cudaStreamSynchronize(c->stream));
+  long long first = 0, total = 0;
+  for (int r = 0; r < c->n_ranks; ++r) {
+    if (r == c->rank) first = total;
+    total += c->h_totals.p[2 + r];
+  }
+  c->n_global_staged = total;
+  c->first_staged = first;
+  c->scale_exp = pr::scale_exp_from_bbox_keys(keys);
+  c->global_valid = true;
+  return PR_OK;
+}
+
+int stage_from_device(plane_ransac_ctx* c, const float4* d_aos, size_t n) {
+  const size_t cap = pr::padded_capacity(n);
+  PR_TRY(dev_reserve(c->staged_mem, 3 * cap));
+  PR_TRY(reserve_small(c));
+  c->staged = planes_view(c->staged_mem.p, nullptr, cap);
+  {
+    Span sp(c, KC_STAGE, 2);
+    pr::launch_bbox_init(c->d_bbox.p, c->stream);
+    pr::launch_stage(d_aos, n, c->staged, c->d_bbox.p, c->stream);
+  }
+  PR_CUDA(cudaGetLastError());
+  PR_CUDA(cudaMemcpyAsync(c->bbox_keys, c->d_bbox.p, 6 * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+  PR_CUDA(cudaStreamSynchronize(c->stream));
+  c->n_staged = n;
+  c->have_cloud = true;
+  c->current = c->staged;
+  c->n_current = n;
+  c->global_valid = false;
+  PR_TRY(refresh_global(c));
+  c->n_global_current = c->n_global_staged;
+  c->first_current = c->first_staged;
+  return PR_OK;
+}
+
+struct SegmentOut {
+  float coeff[4] = {0, 0, 0, 0};
+  long long n_inl_local = 0, n_rem_local = 0;
+  long long n_inl_global = 0;
+  std::vector<long long> rem_per_rank;  // sharded: remaining points per rank after this round
+};
+
+// One pcl::SACSegmentation::segment() on the cloud `src` (n_local points here, n_global overall,
+// this rank's first global index `first`).  Inlier positions / original indices go to d_inl_*; with
+// write_remaining the non-inliers are compacted into dst.
+int segment_core(plane_ransac_ctx* c, const pr_params* prm, pr::CloudView src, size_t n_local, long long n_global,
+                 long long first, bool write_remaining, pr::CloudView dst, int32_t* d_inl_cur, int32_t* d_inl_orig,
+                 pr_segment_info* info, SegmentOut* out) {
+  pr_segment_info inf;
+  std::memset(&inf, 0, sizeof(inf));
+  inf.n_cloud = n_global;
+  inf.scale_exp = c->scale_exp;
+  *out = SegmentOut();
+  out->n_rem_local = (long long)n_local;
+  const float t = pr::threshold_up(prm->distance_threshold);
+  PR_TRY(reserve_small(c));
+
+  pr::RansacReplay replay(std::max(1ll, n_global), prm->max_iterations, prm->probability);
+  int total_draws = 0;
+  if (n_global >= 3 && !replay.done()) {
+    pr::IndexSampler sampler((size_t)n_global, prm->seed);
+    int prev_batch = 0;
+    while (!replay.done()) {
+      const long long trials_left = (long long)prm->max_iterations + 1 - replay.iterations();
+      long long B;
+      if (prm->probability >= 1.0) {
+        B = trials_left;
+      } else if (prev_batch == 0) {
+        B = std::min<long long>(trials_left, 256);
+      } else {
+        B = std::min<long long>(trials_left, std::max<long long>(std::min(replay.draws_wanted(), 8192), 2 * prev_batch));
+      }
+      if (B < 1) B = 1;
+      if ((long long)total_draws + B > (long long)INT_MAX / 4) return fail(PR_ERR_INVALID, "too many draws");
+      PR_TRY(reserve_draws(c, (size_t)total_draws + (size_t)B, total_draws > 0));
+      int32_t* ht = c->h_triples.p + 3 * (size_t)total_draws;
+      for (long long j = 0; j < B; ++j) sampler.draw(ht + 3 * j);
+      int32_t* dt = c->d_triples.p + 3 * (size_t)total_draws;
+      int4* dsp = c->d_sample_pts.p + 3 * (size_t)total_draws;
+      float4* dh = c->d_hyps.p + total_draws;
+      int32_t* dc = c->d_counts.p + total_draws;
+      int32_t* dg = c->d_good.p + total_draws;
+      PR_CUDA(cudaMemcpyAsync(dt, ht, 3 * B * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+      {
+        Span sp(c, KC_MODELS, 2);
+        pr::launch_gather_samples(src, first, n_local, dt, (int)(3 * B), dsp, 1, 0, c->stream);
+        if (c->comm) PR_NCCL(g_nccl.AllReduce(dsp, dsp, (size_t)(3 * B) * 4, ncclInt32, ncclSum, c->comm, c->stream));
+        pr::launch_models(dsp, (int)B, dh, dg, c->stream);
+      }
+      PR_CUDA(cudaMemsetAsync(dc, 0, B * sizeof(int32_t), c->stream));
+      {
+        Span sp(c, KC_SCORE, 1);
+        pr::launch_score(src, n_local, 1, 0, dh, (int)B, t, prm->dot_order, dc, c->num_sms, c->stream);
+        c->prof.pairs_scored += (long long)n_local * B;
+      }
+      if (c->comm) PR_NCCL(g_nccl.AllReduce(dc, dc, (size_t)B, ncclInt32, ncclSum, c->comm, c->stream));
+      PR_CUDA(cudaGetLastError());
+      PR_CUDA(cudaMemcpyAsync(c->h_counts.p + total_draws, dc, B * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+      PR_CUDA(cudaMemcpyAsync(c->h_good.p + total_draws, dg, B * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+      PR_CUDA(cudaStreamSynchronize(c->stream));
+      std::vector<uint8_t> good8((size_t)B);
+      for (long long j = 0; j < B; ++j) good8[j] = c->h_good.p[total_draws + j] ? 1 : 0;
+      replay.feed(c->h_counts.p + total_draws, good8.data(), (int)B);
+      total_draws += (int)B;
+      prev_batch = (int)B;
+    }
+  }
+  inf.n_scored = total_draws;
+  inf.iterations = replay.iterations();
+  inf.draws = replay.draws_used();
+  inf.skipped = replay.skipped();
+  const int best = replay.best_draw();
+  if (best < 0) {
+    if (info) *info = inf;
+    return PR_OK;  // "No solution found": outputs cleared
+  }
+  inf.ok = 1;
+  inf.best_count = replay.best_count();
+  inf.n_inliers_raw = inf.best_count;
+  for (int i = 0; i < 3; ++i) inf.best_sample[i] = c->h_triples.p[3 * (size_t)best + i];
+
+  float refined[4];
+  if (prm->optimize_coefficients) {
+    PR_CUDA(cudaMemsetAsync(c->d_refit.p, 0, sizeof(pr::RefitOut), c->stream));
+    {
+      Span sp(c, KC_REFIT, 1);
+      pr::launch_refit(src, n_local, c->d_hyps.p, c->d_sample_pts.p, best, t, prm->dot_order, c->scale_exp,
+                       c->d_refit.p, c->num_sms, c->stream);
+      c->prof.points_refit += (long long)n_local;
+      c->prof.bytes_refit += 12ll * (long long)n_local;
+    }
+    if (c->comm) PR_NCCL(g_nccl.AllReduce(c->d_refit.p, c->d_refit.p, 16, ncclInt64, ncclSum, c->comm, c->stream));
+    PR_CUDA(cudaMemcpyAsync(c->h_refit.p, c->d_refit.p, sizeof(pr::RefitOut), cudaMemcpyDeviceToHost, c->stream));
+  }
+  PR_CUDA(cudaMemcpyAsync(c->h_small.p, c->d_hyps.p + best, sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
+  PR_CUDA(cudaStreamSynchronize(c->stream));
+  std::memcpy(inf.raw_coeff, c->h_small.p, 4 * sizeof(float));
+  std::memcpy(refined, inf.raw_coeff, sizeof(refined));
+  if (prm->optimize_coefficients) {
+    int64_t m[16];
+    for (int i = 0; i < 16; ++i) m[i] = (int64_t)c->h_refit.p->m[i];
+    // sharded: every rank wrote the same pivot; the all-reduce summed only m[]
+    float pivot[3] = {c->h_refit.p->pivot[0], c->h_refit.p->pivot[1], c->h_refit.p->pivot[2]};
+    pr::plane_from_moments(m, pivot, c->scale_exp, refined);  // < 4 inliers: keeps the raw model
+  }
+
+  // final selection with the (refined) coefficients; peel
+  PR_TRY(dev_reserve(c->d_scratch, pr::compact_scratch_bytes(n_local) + 64));
+  {
+    Span sp(c, KC_COMPACT, n_local ? 1 : 0);
+    pr::Plane4 pl = {refined[0], refined[1], refined[2], refined[3]};
+    pr::launch_compact(src, n_local, pl, t, prm->dot_order, dst, write_remaining, d_inl_cur, d_inl_orig,
+                       c->d_scratch.p, c->d_totals.p, c->stream);
+    c->prof.points_compact += (long long)n_local;
+  }
+  PR_CUDA(cudaGetLastError());
+  if (c->comm) PR_NCCL(g_nccl.AllGather(c->d_totals.p, c->d_totals.p + 2, 2, ncclInt64, c->comm, c->stream));
+  PR_CUDA(cudaMemcpyAsync(c->h_totals.p, c->d_totals.p, (2 + (c->comm ? 2 * c->n_ranks : 0)) * sizeof(long long),
+                          cudaMemcpyDeviceToHost, c->stream));
+  PR_CUDA(cudaStreamSynchronize(c->stream));
+  out->n_rem_local = c->h_totals.p[0];
+  out->n_inl_local = c->h_totals.p[1];
+  out->n_inl_global = out->n_inl_local;
+  if (c->comm) {
+    out->n_inl_global = 0;
+    out->rem_per_rank.resize(c->n_ranks);
+    for (int r = 0; r < c->n_ranks; ++r) {
+      out->rem_per_rank[r] = c->h_totals.p[2 + 2 * r];
+      out->n_inl_global += c->h_totals.p[2 + 2 * r + 1];
+    }
+  }
+  c->prof.bytes_compact += 16ll * (long long)n_local + (write_remaining ? 16ll * out->n_rem_local : 0) +
+                           ((d_inl_cur ? 4ll : 0) + (d_inl_orig ? 4ll : 0)) * out->n_inl_local;
+  std::memcpy(out->coeff, refined, sizeof(refined));
+  inf.n_inliers = (int)out->n_inl_global;
+  if (info) *info = inf;
+  return PR_OK;
+}
+
+int reserve_work(plane_ransac_ctx* c) {
+  const size_t cap = c->staged.cap;
+  for (int i = 0; i < 2; ++i) {
+    PR_TRY(dev_reserve(c->work_mem[i], 3 * cap));
+    PR_TRY(dev_reserve(c->work_orig[i], cap));
+    c->work[i] = planes_view(c->work_mem[i].p, c->work_orig[i].p, cap);
+  }
+  PR_TRY(dev_reserve(c->d_inl_cur, std::max<size_t>(c->n_staged, 1)));
+  PR_TRY(dev_reserve(c->d_inl_orig, std::max<size_t>(c->n_staged, 1)));
+  return PR_OK;
+}
+
+}  // namespace
+
+// =================================================================================================
+// extern "C"
+// =================================================================================================
+extern "C" {
+
+int plane_ransac_abi_version(void) { return PLANE_RANSAC_ABI_VERSION; }
+
+const char* plane_ransac_last_error(void) { return g_error.c_str(); }
+
+void plane_ransac_default_params(pr_params* p) {
+  if (!p) return;
+  p->distance_threshold = 0.1;  // Dialog/config.txt:29 T_dist_point_plane
+  p->max_iterations = 50;       // pcl::SACSegmentation default
+  p->min_plane_size = 500;      // Dialog/config.txt:20 T_num_of_single_plane
+  p->probability = 0.99;
+  p->optimize_coefficients = 1;
+  p->seed = 12345u;
+  p->max_planes = 64;
+  p->dot_order = PR_DOT_FMA;
+}
+
+int plane_ransac_create(plane_ransac_ctx** out, int device_id) {
+  if (!out) return fail(PR_ERR_INVALID, "null output pointer");
+  *out = nullptr;
+  int n_dev = 0;
+  cudaError_t e = cudaGetDeviceCount(&n_dev);
+  if (e != cudaSuccess || n_dev == 0) {
+    cudaGetLastError();
+    return fail(PR_ERR_CUDA, "no CUDA device available (%s); this backend has no CPU fallback",
+                e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+  }
+  if (device_id < 0 || device_id >= n_dev) return fail(PR_ERR_INVALID, "device_id %d out of range (0..%d)", device_id, n_dev - 1);
+  PR_CUDA(cudaSetDevice(device_id));
+  cudaDeviceProp prop;
+  PR_CUDA(cudaGetDeviceProperties(&prop, device_id));
+  if (prop.major < 10) return fail(PR_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device_id, prop.major, prop.minor);
+  plane_ransac_ctx* c = new (std::nothrow) plane_ransac_ctx();
+  if (!c) return fail(PR_ERR_OOM, "out of host memory");
+  c->device = device_id;
+  c->num_sms = prop.multiProcessorCount;
+  std::memset(&c->prof, 0, sizeof(c->prof));
+  if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete c;
+    return fail(PR_ERR_CUDA, "cudaStreamCreate failed");
+  }
+  *out = c;
+  return PR_OK;
+}
+
+void plane_ransac_destroy(plane_ransac_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  collect_spans(c);
+  if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+  dev_free(c->staged_mem);
+  for (int i = 0; i < 2; ++i) { dev_free(c->work_mem[i]); dev_free(c->work_orig[i]); }
+  dev_free(c->aos); dev_free(c->d_bbox); dev_free(c->d_triples); dev_free(c->d_counts); dev_free(c->d_good);
+  dev_free(c->d_sample_pts); dev_free(c->d_hyps); dev_free(c->d_refit); dev_free(c->d_totals);
+  dev_free(c->d_scratch); dev_free(c->d_inl_cur); dev_free(c->d_inl_orig); dev_free(c->d_flush); dev_free(c->batch_mem);
+  pin_free(c->h_triples); pin_free(c->h_counts); pin_free(c->h_good); pin_free(c->h_refit);
+  pin_free(c->h_totals); pin_free(c->h_small);
+  cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+int plane_ransac_set_cloud(plane_ransac_ctx* c, const pr_point* pts, size_t n) {
+  PR_TRY(check_ctx(c));
+  if (!pts && n) return fail(PR_ERR_INVALID, "null cloud");
+  if (n > (size_t)INT_MAX - 4096) return fail(PR_ERR_INVALID, "cloud too large for 32-bit indices");
+  PR_TRY(dev_reserve(c->aos, std::max<size_t>(n, 1)));
+  if (n) PR_CUDA(cudaMemcpyAsync(c->aos.p, pts, n * sizeof(pr_point), cudaMemcpyHostToDevice, c->stream));
+  return stage_from_device(c, c->aos.p, n);
+}
+
+int plane_ransac_set_cloud_device(plane_ransac_ctx* c, const pr_point* dev_pts, size_t n) {
+  PR_TRY(check_ctx(c));
+  if (!dev_pts && n) return fail(PR_ERR_INVALID, "null cloud");
+  if (n > (size_t)INT_MAX - 4096) return fail(PR_ERR_INVALID, "cloud too large for 32-bit indices");
+  cudaPointerAttributes attr;
+  if (n && (cudaPointerGetAttributes(&attr, dev_pts) != cudaSuccess || attr.type != cudaMemoryTypeDevice)) {
+    cudaGetLastError();
+    return fail(PR_ERR_INVALID, "set_cloud_device needs a device pointer");
+  }
+  return stage_from_device(c, reinterpret_cast<const float4*>(dev_pts), n);
+}
+
+int plane_ransac_cloud_size(plane_ransac_ctx* c, size_t* n_staged, size_t* n_current) {
+  if (!c) return fail(PR_ERR_INVALID, "null context");
+  if (!c->have_cloud) return fail(PR_ERR_NO_CLOUD, "no cloud staged");
+  if (n_staged) *n_staged = c->n_staged;
+  if (n_current) *n_current = c->n_current;
+  return PR_OK;
+}
+
+int plane_ransac_score(plane_ransac_ctx* c, const int32_t* triples, int K, double t, int dot_order, int32_t* counts,
+                       float* coeffs, uint8_t* good) {
+  PR_TRY(check_ctx(c));
+  if (!c->have_cloud) return fail(PR_ERR_NO_CLOUD, "no cloud staged");
+  if (K < 0 || (K && (!triples || !counts))) return fail(PR_ERR_INVALID, "bad triples/counts");
+  if (!(t > 0.0)) return fail(PR_ERR_INVALID, "threshold must be > 0");
+  if (dot_order != PR_DOT_PCL_SSE2 && dot_order != PR_DOT_FMA) return fail(PR_ERR_INVALID, "unknown dot_order");
+  if (K == 0) return PR_OK;
+  for (int i = 0; i < 3 * K; ++i)
+    if (triples[i] < 0 || (long long)triples[i] >= c->n_global_staged) return fail(PR_ERR_INVALID, "triple index %d out of range", triples[i]);
+  PR_TRY(reserve_draws(c, (size_t)K, false));
+  std::memcpy(c->h_triples.p, triples, 3 * (size_t)K * sizeof(int32_t));
+  PR_CUDA(cudaMemcpyAsync(c->d_triples.p, c->h_triples.p, 3 * (size_t)K * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+  {
+    Span sp(c, KC_MODELS, 2);
+    pr::launch_gather_samples(c->staged, c->first_staged, c->n_staged, c->d_triples.p, 3 * K, c->d_sample_pts.p, 1, 0, c->stream);
+    if (c->comm) PR_NCCL(g_nccl.AllReduce(c->d_sample_pts.p, c->d_sample_pts.p, (size_t)(3 * K) * 4, ncclInt32, ncclSum, c->comm, c->stream));
+    pr::launch_models(c->d_sample_pts.p, K, c->d_hyps.p, c->d_good.p, c->stream);
+  }
+  PR_CUDA(cudaMemsetAsync(c->d_counts.p, 0, (size_t)K * sizeof(int32_t), c->stream));
+  {
+    Span sp(c, KC_SCORE, 1);
+    pr::launch_score(c->staged, c->n_staged, 1, 0, c->d_hyps.p, K, pr::threshold_up(t), dot_order, c->d_counts.p, c->num_sms, c->stream);
+    c->prof.pairs_scored += (long long)c->n_staged * K;
+  }
+  if (c->comm) PR_NCCL(g_nccl.AllReduce(c->d_counts.p, c->d_counts.p, (size_t)K, ncclInt32, ncclSum, c->comm, c->stream));
+  PR_CUDA(cudaGetLastError());
+  PR_CUDA(cudaMemcpyAsync(c->h_counts.p, c->d_counts.p, (size_t)K * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+  PR_CUDA(cudaMemcpyAsync(c->h_good.p, c->d_good.p, (size_t)K * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+  if (coeffs) PR_CUDA(cudaMemcpyAsync(coeffs, c->d_hyps.p, (size_t)K * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
+  PR_CUDA(cudaStreamSynchronize(c->stream));
+  std::memcpy(counts, c->h_counts.p, (size_t)K * sizeof(int32_t));
+  if (good)
+    for (int k = 0; k < K; ++k) good[k] = c->h_good.p[k] ? 1 : 0;
+  return PR_OK;
+}
+
+int plane_ransac_segment_one(plane_ransac_ctx* c, const pr_params* prm, float coeff[4], int32_t* inliers, size_t cap,
+                             size_t* n_inliers, pr_segment_info* info) {
+  PR_TRY(check_ctx(c));
+  PR_TRY(check_params(prm));
+  if (!c->have_cloud) return fail(PR_ERR_NO_CLOUD, "no cloud staged");
+  if (!coeff || !n_inliers) return fail(PR_ERR_INVALID, "null output");
+  PR_TRY(dev_reserve(c->d_inl_cur, std::max<size_t>(c->n_staged, 1)));
+  SegmentOut so;
+  pr::CloudView none;
+  PR_TRY(segment_core(c, prm, c->staged, c->n_staged, c->n_global_staged, c->first_staged, false, none, c->d_inl_cur.p,
+                      nullptr, info, &so));
+  std::memcpy(coeff, so.coeff, 4 * sizeof(float));
+  *n_inliers = (size_t)so.n_inl_local;
+  if (inliers) {
+    if ((size_t)so.n_inl_local > cap) return fail(PR_ERR_CAPACITY, "inlier buffer holds %zu, need %lld", cap, so.n_inl_local);
+    if (so.n_inl_local) {
+      PR_CUDA(cudaMemcpyAsync(inliers, c->d_inl_cur.p, (size_t)so.n_inl_local * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+      PR_CUDA(cudaStreamSynchronize(c->stream));
+    }
+  }
+  return PR_OK;
+}
+
+int plane_ransac_extract_planes(plane_ransac_ctx* c, const pr_params* prm, float* coeffs, int32_t* inlier_cur,
+                                int32_t* inlier_orig, size_t idx_cap, size_t* plane_offsets, int* n_planes,
+                                pr_segment_info* infos) {
+  PR_TRY(check_ctx(c));
+  PR_TRY(check_params(prm));
+  if (!c->have_cloud) return fail(PR_ERR_NO_CLOUD, "no cloud staged");
+  if (!coeffs || !plane_offsets || !n_planes) return fail(PR_ERR_INVALID, "null output");
+  PR_TRY(reserve_work(c));
+  pr::CloudView src = c->staged;
+  size_t n_local = c->n_staged;
+  long long n_global = c->n_global_staged, first = c->first_staged;
+  int planes = 0;
+  size_t off = 0;
+  plane_offsets[0] = 0;
+  *n_planes = 0;
+  const bool want_lists = inlier_cur || inlier_orig;
+  while (planes < prm->max_planes) {
+    pr::CloudView dst = c->work[planes & 1];
+    SegmentOut so;
+    pr_segment_info inf;
+    PR_TRY(segment_core(c, prm, src, n_local, n_global, first, true, dst, c->d_inl_cur.p + off, c->d_inl_orig.p + off,
+                        &inf, &so));
+    if (infos) infos[planes] = inf;
+    const long long m = so.n_inl_global;
+    if (m == 0 || m < (long long)std::max(0, prm->min_plane_size)) break;
+    if (want_lists && off + (size_t)so.n_inl_local > idx_cap)
+      return fail(PR_ERR_CAPACITY, "inlier index buffers hold %zu entries, need at least %zu", idx_cap, off + (size_t)so.n_inl_local);
+    std::memcpy(coeffs + 4 * planes, so.coeff, 4 * sizeof(float));
+    off += (size_t)so.n_inl_local;
+    plane_offsets[planes + 1] = off;
+    ++planes;
+    src = dst;
+    n_local = (size_t)so.n_rem_local;
+    if (c->comm) {
+      long long tot = 0, f = 0;
+      for (int r = 0; r < c->n_ranks; ++r) {
+        if (r == c->rank) f = tot;
+        tot += so.rem_per_rank[r];
+      }
+      n_global = tot;
+      first = f;
+    } else {
+      n_global = (long long)n_local;
+      first = 0;
+    }
+  }
+  *n_planes = planes;
+  c->current = src;
+  c->n_current = n_local;
+  c->n_global_current = n_global;
+  c->first_current = first;
+  if (off && inlier_cur) PR_CUDA(cudaMemcpyAsync(inlier_cur, c->d_inl_cur.p, off * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+  if (off && inlier_orig) PR_CUDA(cudaMemcpyAsync(inlier_orig, c->d_inl_orig.p, off * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+  PR_CUDA(cudaStreamSynchronize(c->stream));
+  return PR_OK;
+}
+
+int plane_ransac_remaining(plane_ransac_ctx* c, pr_point* out, size_t cap, size_t* n) {
+  PR_TRY(check_ctx(c));
+  if (!c->have_cloud) return fail(PR_ERR_NO_CLOUD, "no cloud staged");
+  if (n) *n = c->n_current;
+  if (!out) return PR_OK;
+  if (c->n_current > cap) return fail(PR_ERR_CAPACITY, "output holds %zu points, need %zu", cap, c->n_current);
+  if (c->n_current == 0) return PR_OK;
+  PR_TRY(dev_reserve(c->aos, c->n_current));
+  {
+    Span sp(c, KC_STAGE, 1);
+    pr::launch_unstage(c->current, c->n_current, c->aos.p, c->stream);
+  }
+  PR_CUDA(cudaGetLastError());
+  PR_CUDA(cudaMemcpyAsync(out, c->aos.p, c->n_current * sizeof(pr_point), cudaMemcpyDeviceToHost, c->stream));
+  PR_CUDA(cudaStreamSynchronize(c->stream));
+  return PR_OK;
+}
+
+// ---- batch of small clouds --------------------------------------------------------------------
+int plane_ransac_set_cloud_batch(plane_ransac_ctx* c, const pr_point* pts, size_t n_clouds, size_t n_per_cloud) {
+  PR_TRY(check_ctx(c));
+  (void)pts; (void)n_clouds; (void)n_per_cloud;
+  return fail(PR_ERR_INVALID, "batch staging is not built yet");
+}
+
+int plane_ransac_segment_batch(plane_ransac_ctx* c, const pr_params* prm, float* coeffs, int32_t* n_inliers,
+                               pr_segment_info* infos) {
+  PR_TRY(check_ctx(c));
+  (void)prm; (void)coeffs; (void)n_inliers; (void)infos;
+  return fail(PR_ERR_INVALID, "batch segmentation is not built yet");
+}
+
+// ---- sharding -----------------------------------------------------------------------------------
+int plane_ransac_comm_unique_id(void* out128) {
+  if (!out128) return fail(PR_ERR_INVALID, "null output");
+  PR_TRY(load_nccl());
+  ncclUniqueId id;
+  PR_NCCL(g_nccl.GetUniqueId(&id));
+  static_assert(sizeof(ncclUniqueId) == PLANE_RANSAC_UNIQUE_ID_BYTES, "ncclUniqueId size");
+  std::memcpy(out128, &id, sizeof(id));
+  return PR_OK;
+}
+
+int plane_ransac_comm_init(plane_ransac_ctx* c, int n_ranks, int rank, const void* unique_id128) {
+  PR_TRY(check_ctx(c));
+  if (n_ranks < 1 || rank < 0 || rank >= n_ranks || !unique_id128) return fail(PR_ERR_INVALID, "bad rank/n_ranks/id");
+  if (c->comm) return fail(PR_ERR_INVALID, "communicator already initialised");
+  PR_TRY(load_nccl());
+  ncclUniqueId id;
+  std::memcpy(&id, unique_id128, sizeof(id));
+  PR_NCCL(g_nccl.CommInitRank(&c->comm, n_ranks, id, rank));
+  c->n_ranks = n_ranks;
+  c->rank = rank;
+  PR_TRY(reserve_small(c));
+  if (c->have_cloud) {
+    PR_TRY(refresh_global(c));
+    c->n_global_current = c->n_global_staged;
+    c->first_current = c->first_staged;
+  }
+  return PR_OK;
+}
+
+int plane_ransac_shard_info(plane_ransac_ctx* c, long long* n_global_staged, long long* first_staged,
+                            long long* n_global_current, long long* first_current) {
+  if (!c) return fail(PR_ERR_INVALID, "null context");
+  if (!c->have_cloud) return fail(PR_ERR_NO_CLOUD, "no cloud staged");
+  if (n_global_staged) *n_global_staged = c->n_global_staged;
+  if (first_staged) *first_staged = c->first_staged;
+  if (n_global_current) *n_global_current = c->n_global_current;
+  if (first_current) *first_current = c->first_current;
+  return PR_OK;
+}
+
+// ---- measurement ----------------------------------------------------------------------------------
+int plane_ransac_profile_enable(plane_ransac_ctx* c, int on) {
+  PR_TRY(check_ctx(c));
+  collect_spans(c);
+  c->profiling = on != 0;
+  return PR_OK;
+}
+
+int plane_ransac_profile_reset(plane_ransac_ctx* c) {
+  PR_TRY(check_ctx(c));
+  collect_spans(c);
+  std::memset(&c->prof, 0, sizeof(c->prof));
+  return PR_OK;
+}
+
+int plane_ransac_profile_get(plane_ransac_ctx* c, pr_profile* out) {
+  PR_TRY(check_ctx(c));
+  if (!out) return fail(PR_ERR_INVALID, "null output");
+  collect_spans(c);
+  *out = c->prof;
+  return PR_OK;
+}
+
+int plane_ransac_measure_ffma_peak(plane_ransac_ctx* c, double* tflops) {
+  PR_TRY(check_ctx(c));
+  if (!tflops) return fail(PR_ERR_INVALID, "null output");
+  const int grid = c->num_sms * 8, iters = 4096;
+  DevBuf<float> out;
+  PR_TRY(dev_reserve(out, (size_t)grid * 256));
+  cudaEvent_t a, b;
+  PR_CUDA(cudaEventCreate(&a));
+  PR_CUDA(cudaEventCreate(&b));
+  double best = 0.0;
+  for (int rep = 0; rep < 4; ++rep) {
+    PR_CUDA(cudaEventRecord(a, c->stream));
+    pr::launch_ffma_peak(out.p, iters, grid, c->stream);
+    PR_CUDA(cudaEventRecord(b, c->stream));
+    PR_CUDA(cudaEventSynchronize(b));
+    float ms = 0.f;
+    PR_CUDA(cudaEventElapsedTime(&ms, a, b));
+    // 8 chains x 8 unrolled FFMA2 per iteration, 2 FMA each, 2 FLOP per FMA
+    const double flop = (double)grid * 256.0 * iters * 64.0 * 4.0;
+    if (rep > 0) best = std::max(best, flop / (ms * 1e-3) / 1e12);
+  }
+  c->prof.launches_other += 4;
+  cudaEventDestroy(a);
+  cudaEventDestroy(b);
+  dev_free(out);
+  *tflops = best;
+  return PR_OK;
+}
+
+int plane_ransac_measure_copy_bw(plane_ransac_ctx* c, size_t bytes, double* gbs) {
+  PR_TRY(check_ctx(c));
+  if (!gbs) return fail(PR_ERR_INVALID, "null output");
+  const size_t nvec = std::max<size_t>(bytes / 16, 1 << 20);
+  DevBuf<float4> src, dst;
+  PR_TRY(dev_reserve(src, nvec));
+  PR_TRY(dev_reserve(dst, nvec));
+  pr::launch_fill(src.p, nvec, 1.0f, c->num_sms, c->stream);
+  cudaEvent_t a, b;
+  PR_CUDA(cudaEventCreate(&a));
+  PR_CUDA(cudaEventCreate(&b));
+  double best = 0.0;
+  for (int rep = 0; rep < 6; ++rep) {
+    PR_CUDA(cudaEventRecord(a, c->stream));
+    pr::launch_copy(src.p, dst.p, nvec, c->num_sms, c->stream);
+    PR_CUDA(cudaEventRecord(b, c->stream));
+    PR_CUDA(cudaEventSynchronize(b));
+    float ms = 0.f;
+    PR_CUDA(cudaEventElapsedTime(&ms, a, b));
+    if (rep > 0) best = std::max(best, 2.0 * nvec * 16.0 / (ms * 1e-3) / 1e9);
+  }
+  c->prof.launches_other += 7;
+  cudaEventDestroy(a);
+  cudaEventDestroy(b);
+  dev_free(src);
+  dev_free(dst);
+  *gbs = best;
+  return PR_OK;
+}
+
+int plane_ransac_flush_l2(plane_ransac_ctx* c) {
+  PR_TRY(check_ctx(c));
+  const size_t nvec = (256u << 20) / 16;  // 256 MiB > 126 MB L2
+  PR_TRY(dev_reserve(c->d_flush, nvec));
+  pr::launch_fill(c->d_flush.p, nvec, 0.0f, c->num_sms, c->stream);
+  c->prof.launches_other += 1;
+  PR_CUDA(cudaStreamSynchronize(c->stream));
+  return PR_OK;
+}
+
+// ---- host-side logic ------------------------------------------------------------------------------
+int plane_ransac_host_draw_triples(size_t n_points, unsigned seed, int n_draws, int32_t* triples) {
+  if (n_points < 3) return fail(PR_ERR_INVALID, "need at least 3 points to sample");
+  if (n_draws < 0 || (n_draws && !triples)) return fail(PR_ERR_INVALID, "bad n_draws/triples");
+  pr::IndexSampler s(n_points, seed);
+  for (int k = 0; k < n_draws; ++k) s.draw(triples + 3 * (size_t)k);
+  return PR_OK;
+}
+
+int plane_ransac_host_replay(const int32_t* counts, const uint8_t* good, int n_draws, long long n_points,
+                             int max_iterations, double probability, int* best_draw, int* iterations, int* draws_used,
+                             int* skipped, int* exhausted) {
+  if (n_draws < 0 || (n_draws && (!counts || !good)) || n_points < 1 || max_iterations < 0)
+    return fail(PR_ERR_INVALID, "bad replay arguments");
+  pr::RansacReplay r(n_points, max_iterations, probability);
+  const bool done = r.done() || r.feed(counts, good, n_draws);
+  if (best_draw) *best_draw = r.best_draw();
+  if (iterations) *iterations = r.iterations();
+  if (draws_used) *draws_used = r.draws_used();
+  if (skipped) *skipped = r.skipped();
+  if (exhausted) *exhausted = done ? 0 : 1;
+  return PR_OK;
+}
+
+int plane_ransac_host_shard_range(long long n_points, int n_ranks, int rank, long long* first, long long* count) {
+  if (n_points < 0 || n_ranks < 1 || rank < 0 || rank >= n_ranks || !first || !count)
+    return fail(PR_ERR_INVALID, "bad shard arguments");
+  pr::shard_range(n_points, n_ranks, rank, first, count);
+  return PR_OK;
+}
+
+int plane_ransac_host_plane_from_moments(const int64_t m[16], const float pivot[3], int scale_exp, float coeff[4]) {
+  if (!m || !pivot || !coeff) return fail(PR_ERR_INVALID, "null argument");
+  return pr::plane_from_moments(m, pivot, scale_exp, coeff) ? PR_OK : fail(PR_ERR_INVALID, "fewer than 4 points in the moments");
+}
+
+}  // extern "C"

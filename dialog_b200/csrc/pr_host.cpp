@@ -1,0 +1,239 @@
+// pr_host.cpp — see pr_host.hpp.  Restates PCL 1.8 host-side behaviour (sac_model.h, ransac.hpp,
+// common/impl/eigen.hpp); PCL itself is not part of the reference tree.
+#include "pr_host.hpp"
+
+#include <cfloat>
+#include <climits>
+#include <cmath>
+#include <cstring>
+
+namespace pr {
+
+void Mt19937::seed_with(uint32_t seed) {
+  mt_[0] = seed;
+  for (int i = 1; i < 624; ++i) mt_[i] = 1812433253u * (mt_[i - 1] ^ (mt_[i - 1] >> 30)) + (uint32_t)i;
+  idx_ = 624;
+}
+
+uint32_t Mt19937::next() {
+  if (idx_ >= 624) {
+    for (int i = 0; i < 624; ++i) {
+      uint32_t y = (mt_[i] & 0x80000000u) | (mt_[(i + 1) % 624] & 0x7fffffffu);
+      uint32_t v = mt_[(i + 397) % 624] ^ (y >> 1);
+      if (y & 1u) v ^= 0x9908b0dfu;
+      mt_[i] = v;
+    }
+    idx_ = 0;
+  }
+  uint32_t y = mt_[idx_++];
+  y ^= y >> 11;
+  y ^= (y << 7) & 0x9d2c5680u;
+  y ^= (y << 15) & 0xefc60000u;
+  y ^= y >> 18;
+  return y;
+}
+
+int32_t IndexSampler::get(size_t i) const {
+  auto it = moved_.find(i);
+  return it == moved_.end() ? (int32_t)i : it->second;
+}
+
+void IndexSampler::draw(int32_t out[3]) {
+  for (size_t i = 0; i < 3; ++i) {
+    // rnd() = boost::uniform_int<>(0, INT_MAX) over mt19937 == rng() >> 1
+    const uint32_t r = rng_.next() >> 1;
+    const size_t j = i + (size_t)r % (n_ - i);
+    const int32_t vi = get(i), vj = get(j);
+    moved_[i] = vj;
+    moved_[j] = vi;
+  }
+  out[0] = get(0);
+  out[1] = get(1);
+  out[2] = get(2);
+}
+
+RansacReplay::RansacReplay(long long n_points, int max_iterations, double probability)
+    : one_over_n_(1.0 / (double)n_points),
+      log_probability_(std::log(1.0 - probability)),
+      max_iterations_(max_iterations),
+      n_best_(-INT_MAX),
+      max_skip_((unsigned)max_iterations * 10u) {
+  done_ = !loop_condition();
+}
+
+bool RansacReplay::loop_condition() const { return (double)iterations_ < k_ && skipped_ < max_skip_; }
+
+int RansacReplay::draws_wanted() const {
+  if (done_) return 0;
+  // at most (max_iterations + 1) trials are ever scored; k may cut that short
+  long long left = (long long)max_iterations_ + 1 - iterations_;
+  if (k_ < (double)left + iterations_) {
+    double kk = std::ceil(k_) - iterations_;
+    if (kk < (double)left) left = (long long)kk;
+  }
+  if (left < 1) left = 1;
+  return (int)left;
+}
+
+bool RansacReplay::feed(const int32_t* counts, const uint8_t* good, int n) {
+  for (int j = 0; j < n && !done_; ++j) {
+    ++draws_used_;
+    if (!good[j]) {
+      // getSamples: redraw; after max_sample_checks_ (1000) failures the selection is empty and
+      // computeModel breaks out of its loop.
+      if (++bad_run_ >= 1000) done_ = true;
+      continue;
+    }
+    bad_run_ = 0;
+    // computeModelCoefficients cannot fail on a sample isSampleGood accepted (same test), so
+    // skipped_count stays 0 for the plane model; kept for fidelity with the loop condition.
+    const int c = counts[j];
+    if (c > n_best_) {
+      n_best_ = c;
+      best_draw_ = draws_used_ - 1;
+      const double w = (double)n_best_ * one_over_n_;
+      double p_no_outliers = 1.0 - std::pow(w, 3.0);
+      if (p_no_outliers < DBL_EPSILON) p_no_outliers = DBL_EPSILON;
+      if (p_no_outliers > 1.0 - DBL_EPSILON) p_no_outliers = 1.0 - DBL_EPSILON;
+      k_ = log_probability_ / std::log(p_no_outliers);
+    }
+    ++iterations_;
+    if (iterations_ > max_iterations_) done_ = true;
+    if (!loop_condition()) done_ = true;
+  }
+  return done_;
+}
+
+static float key_to_float(uint32_t k) {
+  uint32_t b = (k & 0x80000000u) ? (k ^ 0x80000000u) : ~k;
+  float f;
+  std::memcpy(&f, &b, 4);
+  return f;
+}
+
+int scale_exp_from_bbox_keys(const uint32_t keys[6]) {
+  double r = 0.0;
+  for (int a = 0; a < 3; ++a) {
+    if (keys[a] > keys[3 + a]) continue;  // no finite point
+    const double e = (double)key_to_float(keys[3 + a]) - (double)key_to_float(keys[a]);
+    if (e > r) r = e;
+  }
+  if (!(r > 0.0)) return 0;
+  int e;
+  (void)std::frexp(r, &e);
+  return 30 - e;
+}
+
+// --- pcl::eigen33 / computeRoots / computeRoots2 (common/impl/eigen.hpp) in double ---------------
+static void roots2(double b, double c, double roots[3]) {
+  roots[0] = 0.0;
+  double d = b * b - 4.0 * c;
+  if (d < 0.0) d = 0.0;
+  const double sd = std::sqrt(d);
+  roots[2] = 0.5 * (b + sd);
+  roots[1] = 0.5 * (b - sd);
+}
+
+static void roots3(const double m[9], double roots[3]) {
+  const double c0 = m[0] * m[4] * m[8] + 2.0 * m[1] * m[2] * m[5] - m[0] * m[5] * m[5] - m[4] * m[2] * m[2] -
+                    m[8] * m[1] * m[1];
+  const double c1 = m[0] * m[4] - m[1] * m[1] + m[0] * m[8] - m[2] * m[2] + m[4] * m[8] - m[5] * m[5];
+  const double c2 = m[0] + m[4] + m[8];
+  if (std::fabs(c0) < DBL_EPSILON) {
+    roots2(c2, c1, roots);
+    return;
+  }
+  const double s_inv3 = 1.0 / 3.0;
+  const double s_sqrt3 = std::sqrt(3.0);
+  const double c2_over_3 = c2 * s_inv3;
+  double a_over_3 = (c1 - c2 * c2_over_3) * s_inv3;
+  if (a_over_3 > 0.0) a_over_3 = 0.0;
+  const double half_b = 0.5 * (c0 + c2_over_3 * (2.0 * c2_over_3 * c2_over_3 - c1));
+  double q = half_b * half_b + a_over_3 * a_over_3 * a_over_3;
+  if (q > 0.0) q = 0.0;
+  const double rho = std::sqrt(-a_over_3);
+  const double theta = std::atan2(std::sqrt(-q), half_b) * s_inv3;
+  const double cos_theta = std::cos(theta);
+  const double sin_theta = std::sin(theta);
+  roots[0] = c2_over_3 + 2.0 * rho * cos_theta;
+  roots[1] = c2_over_3 - rho * (cos_theta + s_sqrt3 * sin_theta);
+  roots[2] = c2_over_3 - rho * (cos_theta - s_sqrt3 * sin_theta);
+  double tmp;
+  if (roots[0] >= roots[1]) { tmp = roots[0]; roots[0] = roots[1]; roots[1] = tmp; }
+  if (roots[1] >= roots[2]) {
+    tmp = roots[1]; roots[1] = roots[2]; roots[2] = tmp;
+    if (roots[0] >= roots[1]) { tmp = roots[0]; roots[0] = roots[1]; roots[1] = tmp; }
+  }
+  if (roots[0] <= 0) roots2(c2, c1, roots);
+}
+
+static void smallest_eigenvector(const double mat[9], double vec[3]) {
+  double scale = 0.0;
+  for (int i = 0; i < 9; ++i) {
+    const double a = std::fabs(mat[i]);
+    if (a > scale) scale = a;
+  }
+  if (scale <= DBL_MIN) scale = 1.0;
+  double s[9];
+  for (int i = 0; i < 9; ++i) s[i] = mat[i] / scale;
+  double ev[3];
+  roots3(s, ev);
+  s[0] -= ev[0];
+  s[4] -= ev[0];
+  s[8] -= ev[0];
+  const double *r0 = s, *r1 = s + 3, *r2 = s + 6;
+  const double v1[3] = {r0[1] * r1[2] - r0[2] * r1[1], r0[2] * r1[0] - r0[0] * r1[2], r0[0] * r1[1] - r0[1] * r1[0]};
+  const double v2[3] = {r0[1] * r2[2] - r0[2] * r2[1], r0[2] * r2[0] - r0[0] * r2[2], r0[0] * r2[1] - r0[1] * r2[0]};
+  const double v3[3] = {r1[1] * r2[2] - r1[2] * r2[1], r1[2] * r2[0] - r1[0] * r2[2], r1[0] * r2[1] - r1[1] * r2[0]};
+  const double len1 = v1[0] * v1[0] + v1[1] * v1[1] + v1[2] * v1[2];
+  const double len2 = v2[0] * v2[0] + v2[1] * v2[1] + v2[2] * v2[2];
+  const double len3 = v3[0] * v3[0] + v3[1] * v3[1] + v3[2] * v3[2];
+  const double* best;
+  double len;
+  if (len1 >= len2 && len1 >= len3) { best = v1; len = len1; }
+  else if (len2 >= len1 && len2 >= len3) { best = v2; len = len2; }
+  else { best = v3; len = len3; }
+  const double nrm = std::sqrt(len);
+  vec[0] = best[0] / nrm;
+  vec[1] = best[1] / nrm;
+  vec[2] = best[2] / nrm;
+}
+
+bool plane_from_moments(const int64_t m[16], const float pivot[3], int scale_exp, float coeff[4]) {
+  typedef __int128 i128;
+  const int64_t n = m[0];
+  if (n < 4) return false;
+  const i128 S[3] = {m[1], m[2], m[3]};
+  i128 Sab[6];
+  for (int k = 0; k < 6; ++k) Sab[k] = (i128)m[4 + 2 * k] * ((i128)1 << 32) + (i128)m[5 + 2 * k];
+  static const int A[6] = {0, 0, 0, 1, 1, 2}, B[6] = {0, 1, 2, 1, 2, 2};
+  double C[6];
+  for (int k = 0; k < 6; ++k) C[k] = (double)((i128)n * Sab[k] - S[A[k]] * S[B[k]]);
+  const double cov[9] = {C[0], C[1], C[2], C[1], C[3], C[4], C[2], C[4], C[5]};
+  double v[3];
+  smallest_eigenvector(cov, v);
+  const double inv = std::ldexp(1.0, -scale_exp);
+  const double cx = (double)pivot[0] + ((double)m[1] / (double)n) * inv;
+  const double cy = (double)pivot[1] + ((double)m[2] / (double)n) * inv;
+  const double cz = (double)pivot[2] + ((double)m[3] / (double)n) * inv;
+  const double d = -((v[0] * cx + v[1] * cy) + v[2] * cz);
+  coeff[0] = (float)v[0];
+  coeff[1] = (float)v[1];
+  coeff[2] = (float)v[2];
+  coeff[3] = (float)d;
+  return true;
+}
+
+float threshold_up(double t) {
+  float f = (float)t;  // round to nearest
+  if ((double)f < t) f = std::nextafterf(f, INFINITY);
+  return f;
+}
+
+void shard_range(long long n_points, int n_ranks, int rank, long long* first, long long* count) {
+  const long long base = n_points / n_ranks, rem = n_points % n_ranks;
+  *first = base * rank + (rank < rem ? rank : rem);
+  *count = base + (rank < rem ? 1 : 0);
+}
+
+}  // namespace pr

@@ -1,0 +1,80 @@
+// pr_host.hpp — host-side logic of the plane-RANSAC backend: PCL's sampling stream, the sequential
+// RANSAC decision loop replayed over batched device counts, and the closed-form plane from integer
+// moments.  Pure C++ (no CUDA), compiled with -ffp-contract=off.
+#pragma once
+
+#include <cstddef>
+#include <cstdint>
+#include <unordered_map>
+#include <vector>
+
+namespace pr {
+
+// boost::mt19937 / std::mt19937 (PCL sac_model.h: rng_alg_).
+class Mt19937 {
+ public:
+  explicit Mt19937(uint32_t seed = 5489u) { seed_with(seed); }
+  void seed_with(uint32_t seed);
+  uint32_t next();
+
+ private:
+  uint32_t mt_[624];
+  int idx_ = 624;
+};
+
+// SampleConsensusModel::drawIndexSample for a 3-point model (PCL 1.8 sac_model.h).  The permutation
+// shuffled_indices_ starts as the identity over n indices and persists across draws; only the
+// entries touched so far are stored, so a 10^8-point cloud costs nothing to (re)initialise.
+class IndexSampler {
+ public:
+  IndexSampler(size_t n, uint32_t seed) : rng_(seed), n_(n) {}
+  void draw(int32_t out[3]);
+  size_t size() const { return n_; }
+
+ private:
+  int32_t get(size_t i) const;
+  Mt19937 rng_;
+  size_t n_;
+  std::unordered_map<size_t, int32_t> moved_;
+};
+
+// RandomSampleConsensus::computeModel's while-loop (PCL 1.8 ransac.hpp), fed one draw at a time.
+// The draw stream does not depend on the scores, so the device scores a batch of draws and this
+// object replays PCL's sequential decisions (strict '>' first-best, adaptive k, iteration cap,
+// getSamples' 1000-redraw limit) over them.
+class RansacReplay {
+ public:
+  RansacReplay(long long n_points, int max_iterations, double probability);
+  // Consumes draws [0, n); returns true when the loop has terminated (no more draws needed).
+  bool feed(const int32_t* counts, const uint8_t* good, int n);
+  bool done() const { return done_; }
+  // Upper bound on the draws the loop can still consume if every one of them is good.
+  int draws_wanted() const;
+  int best_draw() const { return best_draw_; }  // global draw index, -1 if none
+  int best_count() const { return n_best_; }
+  int iterations() const { return iterations_; }
+  int draws_used() const { return draws_used_; }
+  int skipped() const { return (int)skipped_; }
+
+ private:
+  bool loop_condition() const;
+  double one_over_n_, log_probability_, k_ = 1.0;
+  int max_iterations_, iterations_ = 0, n_best_, best_draw_ = -1, draws_used_ = 0, bad_run_ = 0;
+  unsigned skipped_ = 0, max_skip_;
+  bool done_ = false;
+};
+
+// Extent exponent s: |x - pivot| * 2^s < 2^30 for all finite points of a cloud with the given
+// bounding box (ordered-float keys as written by the staging kernel: min x,y,z then max x,y,z).
+int scale_exp_from_bbox_keys(const uint32_t keys[6]);
+
+// Least-squares plane from exact integer moments (DESIGN.md "refit").  Returns false (coeff
+// untouched) when fewer than 4 points contributed.
+bool plane_from_moments(const int64_t m[16], const float pivot[3], int scale_exp, float coeff[4]);
+
+// Smallest float >= t: the FP32 threshold equivalent to PCL's float-vs-double strict compare.
+float threshold_up(double t);
+
+void shard_range(long long n_points, int n_ranks, int rank, long long* first, long long* count);
+
+}  // namespace pr

@@ -1,0 +1,745 @@
+// pr_kernels.cu — sm_100a kernels of the plane-RANSAC backend (see DESIGN.md for the rooflines).
+//
+//   K0 stage_kernel     AoS pcl::PointXYZ -> x[] y[] z[] planes, NaN padding, bounding box
+//   K1 gather/models    sample triples -> plane hypotheses, PCL op order, no contraction
+//   K2 score_kernel     N x K threshold tests; FP32-FMA bound; TMA bulk copies into a smem ring
+//   K3 refit_kernel     inlier predicate + exact integer moments; HBM bound
+//   K5 compact_kernel   stable partition (decoupled look-back scan); HBM bound
+//
+// Reference arithmetic restated here: the point-to-plane threshold test of
+// Dialog/PlaneDetect.h:1442-1448,1902,2019-2023 (PCL countWithinDistance), the order-preserving
+// rebuild of source_cloud at Dialog/PlaneDetect.h:1560-1566 (PCL ExtractIndices), and the
+// covariance accumulation behind pcl::computePointNormal at Dialog/PlaneDetect.h:1485.
+//
+// Built with -fmad=false: every multiply-add that is fused is written as an explicit fma intrinsic,
+// so the FP32 results are a function of the source text only.
+#include "pr_kernels.h"
+
+#include <math_constants.h>
+
+namespace pr {
+
+// ------------------------------------------------------------------------------------------------
+// small device helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t addr = smem_u32(bar), done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+
+// TMA 1-D bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP).
+__device__ __forceinline__ void tma_bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// coeff . (x, y, z, 1) in the two documented orders (include/plane_ransac.h PR_DOT_*).
+template <int DOT>
+__device__ __forceinline__ float plane_dot(float a, float b, float c, float d, float x, float y, float z) {
+  if (DOT == 1) return __fmaf_rn(a, x, __fmaf_rn(b, y, __fmaf_rn(c, z, d)));
+  return __fadd_rn(__fadd_rn(__fmul_rn(a, x), __fmul_rn(c, z)), __fadd_rn(__fmul_rn(b, y), d));
+}
+
+template <int DOT>
+__device__ __forceinline__ float2 plane_dot2(float a, float b, float c, float d, float2 x, float2 y, float2 z) {
+  if (DOT == 1) {
+    const float2 A = make_float2(a, a), B = make_float2(b, b), C = make_float2(c, c), D = make_float2(d, d);
+    return __ffma2_rn(A, x, __ffma2_rn(B, y, __ffma2_rn(C, z, D)));
+  }
+  // Separately rounded products and sums must stay scalar: ptxas 12.9 contracts mul.rn.f32x2 +
+  // add.rn.f32x2 into FFMA2 even though both carry an explicit rounding mode (seen in SASS and as
+  // +-1 count differences against the oracle); scalar FMUL/FADD with .rn are never fused.
+  return make_float2(plane_dot<0>(a, b, c, d, x.x, y.x, z.x), plane_dot<0>(a, b, c, d, x.y, y.y, z.y));
+}
+
+__device__ __forceinline__ uint32_t float_order_key(float f) {
+  uint32_t b = __float_as_uint(f);
+  return b ^ ((b >> 31) ? 0xFFFFFFFFu : 0x80000000u);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K0: staging
+// ------------------------------------------------------------------------------------------------
+__global__ void bbox_init_kernel(uint32_t* bbox) {
+  if (threadIdx.x < 3) bbox[threadIdx.x] = 0xFFFFFFFFu;
+  else if (threadIdx.x < 6) bbox[threadIdx.x] = 0u;
+}
+
+__global__ void __launch_bounds__(256) stage_kernel(const float4* __restrict__ aos, size_t n, float* __restrict__ x,
+                                                    float* __restrict__ y, float* __restrict__ z, size_t cap,
+                                                    uint32_t* __restrict__ bbox) {
+  uint32_t lo[3] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu}, hi[3] = {0u, 0u, 0u};
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += stride) {
+    if (i < n) {
+      float4 p = __ldg(&aos[i]);
+      x[i] = p.x;
+      y[i] = p.y;
+      z[i] = p.z;
+      if (isfinite(p.x) && isfinite(p.y) && isfinite(p.z)) {
+        const float c[3] = {p.x, p.y, p.z};
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+          uint32_t k = float_order_key(c[a]);
+          lo[a] = min(lo[a], k);
+          hi[a] = max(hi[a], k);
+        }
+      }
+    } else {
+      x[i] = CUDART_NAN_F;
+      y[i] = CUDART_NAN_F;
+      z[i] = CUDART_NAN_F;
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    uint32_t l = __reduce_min_sync(0xFFFFFFFFu, lo[a]);
+    uint32_t h = __reduce_max_sync(0xFFFFFFFFu, hi[a]);
+    if ((threadIdx.x & 31) == 0) {
+      if (l != 0xFFFFFFFFu) atomicMin(&bbox[a], l);
+      if (h != 0u) atomicMax(&bbox[3 + a], h);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) unstage_kernel(const float* __restrict__ x, const float* __restrict__ y,
+                                                      const float* __restrict__ z, size_t n, float4* __restrict__ aos) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    aos[i] = make_float4(x[i], y[i], z[i], 1.0f);
+}
+
+void launch_bbox_init(uint32_t* bbox, cudaStream_t s) { bbox_init_kernel<<<1, 32, 0, s>>>(bbox); }
+
+void launch_stage(const float4* aos, size_t n, CloudView dst, uint32_t* bbox, cudaStream_t s) {
+  size_t blocks = (dst.cap + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  stage_kernel<<<(unsigned)blocks, 256, 0, s>>>(aos, n, dst.x, dst.y, dst.z, dst.cap, bbox);
+}
+
+void launch_unstage(CloudView src, size_t n, float4* aos, cudaStream_t s) {
+  if (n == 0) return;
+  size_t blocks = (n + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  unstage_kernel<<<(unsigned)blocks, 256, 0, s>>>(src.x, src.y, src.z, n, aos);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1: hypotheses from sample triples
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gather_samples_kernel(const float* __restrict__ x, const float* __restrict__ y,
+                                                             const float* __restrict__ z, long long first, size_t n,
+                                                             const int32_t* __restrict__ triples, int n_samples,
+                                                             int4* __restrict__ out, int n_clouds, size_t cloud_stride) {
+  const long long total = (long long)n_samples * n_clouds;
+  for (long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x; s < total; s += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(s / n_samples);
+    int j = (int)(s - (long long)c * n_samples);
+    long long local = (long long)triples[j] - first;
+    int4 v = make_int4(0, 0, 0, 0);
+    if (local >= 0 && local < (long long)n) {
+      size_t o = (size_t)c * cloud_stride + (size_t)local;
+      v = make_int4(__float_as_int(x[o]), __float_as_int(y[o]), __float_as_int(z[o]), 0x3F800000);
+    }
+    out[s] = v;
+  }
+}
+
+// PCL SampleConsensusModelPlane::isSampleGood + computeModelCoefficients (sac_model_plane.hpp), FP32,
+// every operation rounded on its own; reductions in Eigen's SSE2 order (e0 + e2) + (e1 + e3).
+__global__ void __launch_bounds__(128) models_kernel(const int4* __restrict__ sample_pts, int n_models,
+                                                     float4* __restrict__ hyps, int32_t* __restrict__ good) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n_models) return;
+  int4 q0 = sample_pts[3 * k], q1 = sample_pts[3 * k + 1], q2 = sample_pts[3 * k + 2];
+  float p0x = __int_as_float(q0.x), p0y = __int_as_float(q0.y), p0z = __int_as_float(q0.z);
+  float ux = __fsub_rn(__int_as_float(q1.x), p0x), uy = __fsub_rn(__int_as_float(q1.y), p0y),
+        uz = __fsub_rn(__int_as_float(q1.z), p0z);
+  float vx = __fsub_rn(__int_as_float(q2.x), p0x), vy = __fsub_rn(__int_as_float(q2.y), p0y),
+        vz = __fsub_rn(__int_as_float(q2.z), p0z);
+  float r0 = __fdiv_rn(ux, vx), r1 = __fdiv_rn(uy, vy), r2 = __fdiv_rn(uz, vz);
+  bool ok = (r0 != r1) || (r2 != r1);
+  float4 h = make_float4(CUDART_NAN_F, CUDART_NAN_F, CUDART_NAN_F, CUDART_NAN_F);
+  if (ok) {
+    float nx = __fsub_rn(__fmul_rn(uy, vz), __fmul_rn(uz, vy));
+    float ny = __fsub_rn(__fmul_rn(uz, vx), __fmul_rn(ux, vz));
+    float nz = __fsub_rn(__fmul_rn(ux, vy), __fmul_rn(uy, vx));
+    float sq = __fadd_rn(__fadd_rn(__fmul_rn(nx, nx), __fmul_rn(nz, nz)), __fadd_rn(__fmul_rn(ny, ny), 0.0f));
+    float nrm = __fsqrt_rn(sq);
+    nx = __fdiv_rn(nx, nrm);
+    ny = __fdiv_rn(ny, nrm);
+    nz = __fdiv_rn(nz, nrm);
+    float dot = __fadd_rn(__fadd_rn(__fmul_rn(nx, p0x), __fmul_rn(nz, p0z)), __fadd_rn(__fmul_rn(ny, p0y), 0.0f));
+    h = make_float4(nx, ny, nz, __fmul_rn(-1.0f, dot));
+  }
+  hyps[k] = h;
+  good[k] = ok ? 1 : 0;
+}
+
+void launch_gather_samples(CloudView cloud, long long first, size_t n, const int32_t* triples, int n_samples,
+                           int4* sample_pts, int n_clouds, size_t cloud_stride, cudaStream_t s) {
+  long long total = (long long)n_samples * n_clouds;
+  if (total <= 0) return;
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  gather_samples_kernel<<<(unsigned)blocks, 256, 0, s>>>(cloud.x, cloud.y, cloud.z, first, n, triples, n_samples,
+                                                         sample_pts, n_clouds, cloud_stride);
+}
+
+void launch_models(const int4* sample_pts, int n_models_total, float4* hyps, int32_t* good, cudaStream_t s) {
+  if (n_models_total <= 0) return;
+  models_kernel<<<(n_models_total + 127) / 128, 128, 0, s>>>(sample_pts, n_models_total, hyps, good);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2: hypothesis scoring
+//
+// Layout: hypothesis-per-lane, point broadcast.  Each lane keeps H hypotheses (a,b,c,d) in registers
+// for the whole kernel; a warp walks a tile of points held in shared memory, reading four points per
+// step with three broadcast LDS.128 (x[4], y[4], z[4]); every lane evaluates its H hypotheses on the
+// four points with packed FP32 FMAs (FFMA2: two points per instruction, the hypothesis operand
+// broadcast), tests |r| < t with FSET.BF and adds the 1.0f/0.0f bit patterns two at a time with one
+// IADD3.  Counts stay lane-private until the end: no shuffles, no shared-memory atomics.
+//
+// The 1.0f pattern is 0x3F800000 = 127 * 2^23, so after c increments the accumulator holds
+// (127 c mod 512) << 23; c < 512 is recovered as ((acc >> 23) * 383) & 511 (127 * 383 = 1 mod 512) and
+// folded into a plain counter every <= 64 steps (<= 256 increments).
+//
+// Tiles arrive through a kStages-deep ring of TMA bulk copies (one producer lane, full/empty
+// mbarriers).  The work list is (cloud, tile) items so that a batch of small clouds runs in one launch.
+// ------------------------------------------------------------------------------------------------
+constexpr int kScoreConsumerWarps = 8;
+constexpr int kScoreThreads = (kScoreConsumerWarps + 1) * 32;
+constexpr int kScoreStages = 3;
+
+template <int H, int DOT>
+__global__ void __launch_bounds__(kScoreThreads, 2)
+    score_kernel(const float* __restrict__ X, const float* __restrict__ Y, const float* __restrict__ Z,
+                 size_t cloud_stride, int tiles_per_cloud, int total_items, int items_per_cta,
+                 const float4* __restrict__ hyps, int K, float t, int32_t* __restrict__ counts, int warps_h) {
+  __shared__ __align__(128) float s_pts[kScoreStages][3][kTilePoints];
+  __shared__ __align__(8) uint64_t s_full[kScoreStages];
+  __shared__ __align__(8) uint64_t s_empty[kScoreStages];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int item_begin = blockIdx.x * items_per_cta;
+  const int n_items = min(total_items, item_begin + items_per_cta) - item_begin;
+  if (n_items <= 0) return;
+
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int s = 0; s < kScoreStages; ++s) {
+      mbar_init(&s_full[s], 1);
+      mbar_init(&s_empty[s], kScoreConsumerWarps);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  if (warp == kScoreConsumerWarps) {
+    // ---- producer: one lane feeds the ring ----
+    if (lane == 0) {
+      for (int it = 0; it < n_items; ++it) {
+        const int s = it % kScoreStages;
+        if (it >= kScoreStages) mbar_wait(&s_empty[s], ((it / kScoreStages) - 1) & 1);
+        const int item = item_begin + it;
+        const int c = item / tiles_per_cloud, tl = item - c * tiles_per_cloud;
+        const size_t off = (size_t)c * cloud_stride + (size_t)tl * kTilePoints;
+        mbar_expect_tx(&s_full[s], 3u * kTilePoints * sizeof(float));
+        tma_bulk_g2s(&s_pts[s][0][0], X + off, kTilePoints * sizeof(float), &s_full[s]);
+        tma_bulk_g2s(&s_pts[s][1][0], Y + off, kTilePoints * sizeof(float), &s_full[s]);
+        tma_bulk_g2s(&s_pts[s][2][0], Z + off, kTilePoints * sizeof(float), &s_full[s]);
+      }
+    }
+    return;
+  }
+
+  // ---- consumers ----
+  const int wh = warp % warps_h, wp = warp / warps_h;
+  const int pts_per_warp = kTilePoints / (kScoreConsumerWarps / warps_h);
+  const int p_begin = wp * pts_per_warp;
+  const int steps_per_flush = min(64, pts_per_warp / 4);
+  const int k_stride = 32 * warps_h;
+  const int k0 = blockIdx.y * (k_stride * H) + wh * 32 + lane;
+
+  float ha[H], hb[H], hc[H], hd[H];
+  int cnt[H];
+  unsigned acc[H];
+  int cur_cloud = -1;
+
+  for (int it = 0; it < n_items; ++it) {
+    const int s = it % kScoreStages;
+    const int item = item_begin + it;
+    const int c = item / tiles_per_cloud;
+    if (c != cur_cloud) {
+      if (cur_cloud >= 0) {
+#pragma unroll
+        for (int j = 0; j < H; ++j) {
+          const int k = k0 + j * k_stride;
+          if (k < K && cnt[j] != 0) atomicAdd(&counts[(size_t)cur_cloud * K + k], cnt[j]);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < H; ++j) {
+        const int k = k0 + j * k_stride;
+        float4 h = make_float4(CUDART_NAN_F, CUDART_NAN_F, CUDART_NAN_F, CUDART_NAN_F);
+        if (k < K) h = __ldg(&hyps[(size_t)c * K + k]);
+        ha[j] = h.x; hb[j] = h.y; hc[j] = h.z; hd[j] = h.w;
+        cnt[j] = 0;
+        acc[j] = 0u;
+      }
+      cur_cloud = c;
+    }
+
+    mbar_wait(&s_full[s], (it / kScoreStages) & 1);
+    const float* sx = &s_pts[s][0][p_begin];
+    const float* sy = &s_pts[s][1][p_begin];
+    const float* sz = &s_pts[s][2][p_begin];
+
+    for (int p = 0; p < pts_per_warp; p += 4 * steps_per_flush) {
+#pragma unroll 2
+      for (int q = 0; q < steps_per_flush; ++q) {
+        const float4 x4 = *reinterpret_cast<const float4*>(sx + p + 4 * q);
+        const float4 y4 = *reinterpret_cast<const float4*>(sy + p + 4 * q);
+        const float4 z4 = *reinterpret_cast<const float4*>(sz + p + 4 * q);
+        const float2 xa = make_float2(x4.x, x4.y), xb = make_float2(x4.z, x4.w);
+        const float2 ya = make_float2(y4.x, y4.y), yb = make_float2(y4.z, y4.w);
+        const float2 za = make_float2(z4.x, z4.y), zb = make_float2(z4.z, z4.w);
+#pragma unroll
+        for (int j = 0; j < H; ++j) {
+          const float2 ra = plane_dot2<DOT>(ha[j], hb[j], hc[j], hd[j], xa, ya, za);
+          const float2 rb = plane_dot2<DOT>(ha[j], hb[j], hc[j], hd[j], xb, yb, zb);
+          float f0, f1, f2, f3;
+          asm("set.lt.f32.f32 %0, %1, %2;" : "=f"(f0) : "f"(fabsf(ra.x)), "f"(t));
+          asm("set.lt.f32.f32 %0, %1, %2;" : "=f"(f1) : "f"(fabsf(ra.y)), "f"(t));
+          asm("set.lt.f32.f32 %0, %1, %2;" : "=f"(f2) : "f"(fabsf(rb.x)), "f"(t));
+          asm("set.lt.f32.f32 %0, %1, %2;" : "=f"(f3) : "f"(fabsf(rb.y)), "f"(t));
+          unsigned a = acc[j];
+          a = a + __float_as_uint(f0) + __float_as_uint(f1);
+          a = a + __float_as_uint(f2) + __float_as_uint(f3);
+          acc[j] = a;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < H; ++j) {
+        cnt[j] += (int)(((acc[j] >> 23) * 383u) & 511u);
+        acc[j] = 0u;
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&s_empty[s]);
+  }
+#pragma unroll
+  for (int j = 0; j < H; ++j) {
+    const int k = k0 + j * k_stride;
+    if (k < K && cnt[j] != 0) atomicAdd(&counts[(size_t)cur_cloud * K + k], cnt[j]);
+  }
+}
+
+static int next_pow2(int v) {
+  int p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+template <int H>
+static void launch_score_h(const float* X, const float* Y, const float* Z, size_t cloud_stride, int tiles_per_cloud,
+                           int n_clouds, const float4* hyps, int K, float t, int dot_order, int32_t* counts, int num_sms,
+                           cudaStream_t s) {
+  int warps_h = next_pow2((K + 32 * H - 1) / (32 * H));
+  if (warps_h > kScoreConsumerWarps) warps_h = kScoreConsumerWarps;
+  const int chunk = 32 * H * warps_h;
+  const int n_chunks = (K + chunk - 1) / chunk;
+  const long long total_items_ll = (long long)tiles_per_cloud * n_clouds;
+  const int total_items = (int)total_items_ll;
+  int gx = (2 * num_sms) / n_chunks;
+  if (gx < 1) gx = 1;
+  if (gx > total_items) gx = total_items;
+  const int items_per_cta = (total_items + gx - 1) / gx;
+  gx = (total_items + items_per_cta - 1) / items_per_cta;
+  dim3 grid(gx, n_chunks);
+  if (dot_order == 1)
+    score_kernel<H, 1><<<grid, kScoreThreads, 0, s>>>(X, Y, Z, cloud_stride, tiles_per_cloud, total_items, items_per_cta,
+                                                      hyps, K, t, counts, warps_h);
+  else
+    score_kernel<H, 0><<<grid, kScoreThreads, 0, s>>>(X, Y, Z, cloud_stride, tiles_per_cloud, total_items, items_per_cta,
+                                                      hyps, K, t, counts, warps_h);
+}
+
+void launch_score(CloudView cloud, size_t n_per_cloud, int n_clouds, size_t cloud_stride, const float4* hyps, int K,
+                  float t, int dot_order, int32_t* counts, int num_sms, cudaStream_t s) {
+  if (K <= 0 || n_per_cloud == 0 || n_clouds <= 0) return;
+  const int tiles_per_cloud = (int)((n_per_cloud + kTilePoints - 1) / kTilePoints);
+  int H = next_pow2((K + 31) / 32);
+  if (H > 8) H = 8;
+  switch (H) {
+    case 1: launch_score_h<1>(cloud.x, cloud.y, cloud.z, cloud_stride, tiles_per_cloud, n_clouds, hyps, K, t, dot_order, counts, num_sms, s); break;
+    case 2: launch_score_h<2>(cloud.x, cloud.y, cloud.z, cloud_stride, tiles_per_cloud, n_clouds, hyps, K, t, dot_order, counts, num_sms, s); break;
+    case 4: launch_score_h<4>(cloud.x, cloud.y, cloud.z, cloud_stride, tiles_per_cloud, n_clouds, hyps, K, t, dot_order, counts, num_sms, s); break;
+    default: launch_score_h<8>(cloud.x, cloud.y, cloud.z, cloud_stride, tiles_per_cloud, n_clouds, hyps, K, t, dot_order, counts, num_sms, s); break;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3: refit moments.  One predicated pass over the cloud; inliers are quantised to a 2^-s grid about
+// the pivot and their first and second moments summed as exact integers (second moments split into
+// hi * 2^32 + lo so that 64-bit accumulators cannot overflow).  Integer sums commute, so the result
+// does not depend on the thread, block or GPU count.
+// ------------------------------------------------------------------------------------------------
+template <int DOT>
+__global__ void __launch_bounds__(256) refit_kernel(const float* __restrict__ X, const float* __restrict__ Y,
+                                                    const float* __restrict__ Z, size_t n,
+                                                    const float4* __restrict__ hyps, const int4* __restrict__ sample_pts,
+                                                    int model_index, float t, double scale, RefitOut* __restrict__ out) {
+  const float4 h = hyps[model_index];
+  const int4 pv = sample_pts[3 * model_index];
+  const double px = (double)__int_as_float(pv.x), py = (double)__int_as_float(pv.y), pz = (double)__int_as_float(pv.z);
+  long long acc[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) acc[i] = 0;
+
+  const size_t nvec = (n + 3) / 4;  // the tail of the last vector is NaN padding: never an inlier
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += stride) {
+    const float4 x4 = __ldg(reinterpret_cast<const float4*>(X) + v);
+    const float4 y4 = __ldg(reinterpret_cast<const float4*>(Y) + v);
+    const float4 z4 = __ldg(reinterpret_cast<const float4*>(Z) + v);
+    const float xs[4] = {x4.x, x4.y, x4.z, x4.w}, ys[4] = {y4.x, y4.y, y4.z, y4.w}, zs[4] = {z4.x, z4.y, z4.z, z4.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float r = plane_dot<DOT>(h.x, h.y, h.z, h.w, xs[e], ys[e], zs[e]);
+      if (fabsf(r) < t) {
+        const long long qx = __double2ll_rn(((double)xs[e] - px) * scale);
+        const long long qy = __double2ll_rn(((double)ys[e] - py) * scale);
+        const long long qz = __double2ll_rn(((double)zs[e] - pz) * scale);
+        acc[0] += 1;
+        acc[1] += qx;
+        acc[2] += qy;
+        acc[3] += qz;
+        const long long pr[6] = {qx * qx, qx * qy, qx * qz, qy * qy, qy * qz, qz * qz};
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+          acc[4 + 2 * k] += pr[k] >> 32;
+          acc[5 + 2 * k] += pr[k] & 0xFFFFFFFFll;
+        }
+      }
+    }
+  }
+  __shared__ long long s_part[8][16];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    long long v = acc[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xFFFFFFFFu, v, o);
+    if (lane == 0) s_part[warp][i] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 16) {
+    long long v = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) v += s_part[w][threadIdx.x];
+    if (v != 0) atomicAdd(reinterpret_cast<unsigned long long*>(&out->m[threadIdx.x]), (unsigned long long)v);
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    out->pivot[0] = __int_as_float(pv.x);
+    out->pivot[1] = __int_as_float(pv.y);
+    out->pivot[2] = __int_as_float(pv.z);
+    out->pivot[3] = 0.0f;
+  }
+}
+
+void launch_refit(CloudView cloud, size_t n, const float4* hyps, const int4* sample_pts, int model_index, float t,
+                  int dot_order, int scale_exp, RefitOut* out, int num_sms, cudaStream_t s) {
+  const double scale = ldexp(1.0, scale_exp);
+  size_t nvec = (n + 3) / 4;
+  size_t blocks = (nvec + 255) / 256;
+  if (blocks > (size_t)num_sms * 4) blocks = (size_t)num_sms * 4;
+  if (blocks < 1) blocks = 1;
+  if (dot_order == 1)
+    refit_kernel<1><<<(unsigned)blocks, 256, 0, s>>>(cloud.x, cloud.y, cloud.z, n, hyps, sample_pts, model_index, t, scale, out);
+  else
+    refit_kernel<0><<<(unsigned)blocks, 256, 0, s>>>(cloud.x, cloud.y, cloud.z, n, hyps, sample_pts, model_index, t, scale, out);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K5: stable partition with a single-pass decoupled look-back scan.
+// Tile = 2048 points (256 threads x 2 rounds x 4 consecutive points, 128-bit loads).  The scan runs
+// on the number of KEPT points; the inlier rank of a point is its position minus the kept points
+// before it, so one scan serves both outputs.  Both outputs are staged in shared memory (kept points
+// from the front, inliers from the back of the same arrays) and written out contiguously.
+// ------------------------------------------------------------------------------------------------
+constexpr int kCompactThreads = 256;
+constexpr unsigned long long kTileAggregate = 1ull << 62;
+constexpr unsigned long long kTileInclusive = 2ull << 62;
+constexpr unsigned long long kTileValueMask = (1ull << 62) - 1;
+
+template <int DOT, bool WRITE_REM>
+__global__ void __launch_bounds__(kCompactThreads)
+    compact_kernel(const float* __restrict__ X, const float* __restrict__ Y, const float* __restrict__ Z,
+                   const int32_t* __restrict__ O, size_t n, Plane4 pl, float t, float* __restrict__ DX,
+                   float* __restrict__ DY, float* __restrict__ DZ, int32_t* __restrict__ DO, size_t dst_cap,
+                   int32_t* __restrict__ inl_cur, int32_t* __restrict__ inl_orig, unsigned long long* tile_state,
+                   unsigned* ticket, long long* __restrict__ totals, unsigned n_tiles) {
+  __shared__ __align__(16) float s_x[kCompactTile];
+  __shared__ __align__(16) float s_y[kCompactTile];
+  __shared__ __align__(16) float s_z[kCompactTile];
+  __shared__ __align__(16) int s_o[kCompactTile];
+  __shared__ int s_warp[2][8];
+  __shared__ unsigned s_tile;
+  __shared__ long long s_excl;
+
+  if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+  __syncthreads();
+  const unsigned tile = s_tile;
+  const size_t base = (size_t)tile * kCompactTile;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  float xs[2][4], ys[2][4], zs[2][4];
+  int os[2][4];
+  unsigned keep[2], inl[2];
+  int kc[2];
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    const size_t i0 = base + (size_t)u * 1024 + 4 * threadIdx.x;
+    const float4 x4 = __ldg(reinterpret_cast<const float4*>(X + i0));
+    const float4 y4 = __ldg(reinterpret_cast<const float4*>(Y + i0));
+    const float4 z4 = __ldg(reinterpret_cast<const float4*>(Z + i0));
+    xs[u][0] = x4.x; xs[u][1] = x4.y; xs[u][2] = x4.z; xs[u][3] = x4.w;
+    ys[u][0] = y4.x; ys[u][1] = y4.y; ys[u][2] = y4.z; ys[u][3] = y4.w;
+    zs[u][0] = z4.x; zs[u][1] = z4.y; zs[u][2] = z4.z; zs[u][3] = z4.w;
+    if (O != nullptr) {
+      const int4 o4 = __ldg(reinterpret_cast<const int4*>(O + i0));
+      os[u][0] = o4.x; os[u][1] = o4.y; os[u][2] = o4.z; os[u][3] = o4.w;
+    } else {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) os[u][e] = (int)(i0 + e);
+    }
+    keep[u] = 0u;
+    inl[u] = 0u;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const bool valid = (i0 + e) < n;
+      const float r = plane_dot<DOT>(pl.a, pl.b, pl.c, pl.d, xs[u][e], ys[u][e], zs[u][e]);
+      const bool in = fabsf(r) < t;
+      if (valid && !in) keep[u] |= 1u << e;
+      if (valid && in) inl[u] |= 1u << e;
+    }
+    kc[u] = __popc(keep[u]);
+  }
+
+  // block-wide exclusive scan of the kept counts, per round
+  int lane_excl[2], round_total[2];
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    int v = kc[u];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int y = __shfl_up_sync(0xFFFFFFFFu, v, o);
+      if (lane >= o) v += y;
+    }
+    lane_excl[u] = v - kc[u];
+    if (lane == 31) s_warp[u][warp] = v;
+  }
+  __syncthreads();
+  int warp_excl[2];
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    int run = 0, mine = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      if (w == warp) mine = run;
+      run += s_warp[u][w];
+    }
+    warp_excl[u] = mine;
+    round_total[u] = run;
+  }
+  const int keep_total = round_total[0] + round_total[1];
+  const size_t remaining_pts = n - base;
+  const int valid_in_tile = remaining_pts < (size_t)kCompactTile ? (int)remaining_pts : kCompactTile;
+  const int inl_total = valid_in_tile - keep_total;
+
+  // decoupled look-back (warp 0)
+  if (warp == 0) {
+    long long excl = 0;
+    if (tile == 0) {
+      if (lane == 0) atomicExch(&tile_state[0], kTileInclusive | (unsigned long long)keep_total);
+    } else {
+      if (lane == 0) atomicExch(&tile_state[tile], kTileAggregate | (unsigned long long)keep_total);
+      long long look = (long long)tile - 1;
+      while (true) {
+        const long long idx = look - lane;
+        unsigned long long st = kTileInclusive;  // lanes before tile 0 contribute an inclusive 0
+        if (idx >= 0) {
+          do {
+            st = *reinterpret_cast<volatile unsigned long long*>(&tile_state[idx]);
+          } while ((st >> 62) == 0ull);
+        }
+        const unsigned incl_mask = __ballot_sync(0xFFFFFFFFu, (st >> 62) == 2ull);
+        const int first_incl = incl_mask ? (__ffs(incl_mask) - 1) : 32;
+        long long val = (lane <= first_incl) ? (long long)(st & kTileValueMask) : 0ll;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) val += __shfl_down_sync(0xFFFFFFFFu, val, o);
+        excl += __shfl_sync(0xFFFFFFFFu, val, 0);
+        if (incl_mask) break;
+        look -= 32;
+      }
+      if (lane == 0) atomicExch(&tile_state[tile], kTileInclusive | (unsigned long long)(excl + keep_total));
+    }
+    if (lane == 0) s_excl = excl;
+  }
+
+  // stage both partitions in shared memory
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    int kr = (u ? round_total[0] : 0) + warp_excl[u] + lane_excl[u];  // kept rank within the tile
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int lp = u * 1024 + 4 * threadIdx.x + e;  // local position
+      if (keep[u] & (1u << e)) {
+        if (WRITE_REM) {
+          s_x[kr] = xs[u][e];
+          s_y[kr] = ys[u][e];
+          s_z[kr] = zs[u][e];
+          s_o[kr] = os[u][e];
+        }
+        ++kr;
+      } else if (inl[u] & (1u << e)) {
+        const int ir = lp - kr;  // inlier rank within the tile
+        s_x[kCompactTile - 1 - ir] = __int_as_float(lp);
+        s_o[kCompactTile - 1 - ir] = os[u][e];
+      }
+    }
+  }
+  __syncthreads();
+  const long long excl = s_excl;
+  const long long inl_excl = (long long)base - excl;
+
+  if (WRITE_REM) {
+    for (int j = threadIdx.x; j < keep_total; j += kCompactThreads) {
+      DX[excl + j] = s_x[j];
+      DY[excl + j] = s_y[j];
+      DZ[excl + j] = s_z[j];
+      DO[excl + j] = s_o[j];
+    }
+  }
+  for (int j = threadIdx.x; j < inl_total; j += kCompactThreads) {
+    const int lp = __float_as_int(s_x[kCompactTile - 1 - j]);
+    if (inl_cur) inl_cur[inl_excl + j] = (int32_t)(base + lp);
+    if (inl_orig) inl_orig[inl_excl + j] = s_o[kCompactTile - 1 - j];
+  }
+
+  if (tile == n_tiles - 1) {
+    const long long total_keep = excl + keep_total;
+    if (threadIdx.x == 0) {
+      totals[0] = total_keep;
+      totals[1] = (long long)n - total_keep;
+    }
+    if (WRITE_REM) {
+      size_t pad_end = ((size_t)total_keep + kTilePoints - 1) / kTilePoints * kTilePoints + kTilePoints;
+      if (pad_end > dst_cap) pad_end = dst_cap;
+      for (size_t j = (size_t)total_keep + threadIdx.x; j < pad_end; j += kCompactThreads) {
+        DX[j] = CUDART_NAN_F;
+        DY[j] = CUDART_NAN_F;
+        DZ[j] = CUDART_NAN_F;
+      }
+    }
+  }
+}
+
+size_t compact_scratch_bytes(size_t n) {
+  size_t n_tiles = (n + kCompactTile - 1) / kCompactTile;
+  return (n_tiles + 2) * sizeof(unsigned long long);
+}
+
+void launch_compact(CloudView src, size_t n, Plane4 plane, float t, int dot_order, CloudView dst, bool write_remaining,
+                    int32_t* inl_cur, int32_t* inl_orig, void* scratch, long long* totals, cudaStream_t s) {
+  if (n == 0) {
+    cudaMemsetAsync(totals, 0, 2 * sizeof(long long), s);
+    return;
+  }
+  const unsigned n_tiles = (unsigned)((n + kCompactTile - 1) / kCompactTile);
+  cudaMemsetAsync(scratch, 0, compact_scratch_bytes(n), s);
+  unsigned long long* tile_state = reinterpret_cast<unsigned long long*>(scratch);
+  unsigned* ticket = reinterpret_cast<unsigned*>(tile_state + n_tiles);
+#define PR_COMPACT(D, W)                                                                                              \
+  compact_kernel<D, W><<<n_tiles, kCompactThreads, 0, s>>>(src.x, src.y, src.z, src.orig, n, plane, t, dst.x, dst.y,  \
+                                                           dst.z, dst.orig, dst.cap, inl_cur, inl_orig, tile_state,   \
+                                                           ticket, totals, n_tiles)
+  if (dot_order == 1) {
+    if (write_remaining) PR_COMPACT(1, true); else PR_COMPACT(1, false);
+  } else {
+    if (write_remaining) PR_COMPACT(0, true); else PR_COMPACT(0, false);
+  }
+#undef PR_COMPACT
+}
+
+// ------------------------------------------------------------------------------------------------
+// measurement helpers
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) ffma_peak_kernel(float* out, int iters, float a, float b) {
+  float2 r[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) r[i] = make_float2(threadIdx.x * 0.001f + i, (float)i);
+  const float2 A = make_float2(a, a), B = make_float2(b, b);
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) r[i] = __ffma2_rn(r[i], A, B);
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += r[i].x + r[i].y;
+  out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+void launch_ffma_peak(float* out, int iters, int grid, cudaStream_t s) {
+  ffma_peak_kernel<<<grid, 256, 0, s>>>(out, iters, 1.0001f, 0.5f);
+}
+
+__global__ void __launch_bounds__(256) copy_kernel(const float4* __restrict__ src, float4* __restrict__ dst, size_t n) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = __ldg(&src[i]);
+}
+
+__global__ void __launch_bounds__(256) fill_kernel(float4* __restrict__ dst, size_t n, float v) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = make_float4(v, v, v, v);
+}
+
+void launch_copy(const float4* src, float4* dst, size_t n_vec, int num_sms, cudaStream_t s) {
+  copy_kernel<<<num_sms * 8, 256, 0, s>>>(src, dst, n_vec);
+}
+
+void launch_fill(float4* dst, size_t n_vec, float v, int num_sms, cudaStream_t s) {
+  fill_kernel<<<num_sms * 8, 256, 0, s>>>(dst, n_vec, v);
+}
+
+}  // namespace pr

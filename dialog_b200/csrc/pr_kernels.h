@@ -1,0 +1,75 @@
+// pr_kernels.h — launch wrappers of the sm_100a kernels behind plane_ransac.h.
+// Host-callable C++ (no CUDA syntax) so the orchestration in pr_api.cpp compiles with plain g++.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+namespace pr {
+
+// Points per scoring tile; every cloud plane is padded with NaN to a multiple of this, plus one
+// spare tile, so tile loads never need a bounds check (NaN is never an inlier).
+constexpr int kTilePoints = 1024;
+// Points per compaction tile (one CTA).
+constexpr int kCompactTile = 2048;
+
+inline size_t padded_capacity(size_t n) {
+  return (n + kTilePoints - 1) / kTilePoints * kTilePoints + kTilePoints;
+}
+
+// A cloud in HBM: three coordinate planes (+ optional original-index plane), each `cap` elements.
+struct CloudView {
+  float* x = nullptr;
+  float* y = nullptr;
+  float* z = nullptr;
+  int32_t* orig = nullptr;  // nullptr == identity (the staged cloud)
+  size_t cap = 0;
+};
+
+struct Plane4 { float a, b, c, d; };
+
+// moments[16]: n, Sx, Sy, Sz, then (hi, lo) of Sxx, Sxy, Sxz, Syy, Syz, Szz; pivot in moments_pivot[3].
+struct RefitOut {
+  long long m[16];
+  float pivot[4];
+};
+
+// K0: AoS pr_point[n] -> planes (NaN padded to cap) + bounding box of the finite points.
+// bbox: 6 x uint32 ordered-float encodings {min x,y,z, max x,y,z}; must be initialised by bbox_init.
+void launch_bbox_init(uint32_t* bbox, cudaStream_t s);
+void launch_stage(const float4* aos, size_t n, CloudView dst, uint32_t* bbox, cudaStream_t s);
+// planes -> AoS (w = 1)
+void launch_unstage(CloudView src, size_t n, float4* aos, cudaStream_t s);
+
+// K1a: sample_pts[s] = bits of point triples[s] if this rank owns it (first <= idx < first + n), else 0.
+// clouds > 1: batch mode, the same triples are gathered from every cloud (cloud_stride elements apart).
+void launch_gather_samples(CloudView cloud, long long first, size_t n, const int32_t* triples, int n_samples,
+                           int4* sample_pts, int n_clouds, size_t cloud_stride, cudaStream_t s);
+// K1b: plane through each sample triple, PCL op order, no contraction; NaN plane + good = 0 when degenerate.
+void launch_models(const int4* sample_pts, int n_models_total, float4* hyps, int32_t* good, cudaStream_t s);
+
+// K2: counts[c * K + k] += |{ i in cloud c : |hyp[c*K+k] . (p_i, 1)| < t }|.  counts must be zeroed.
+void launch_score(CloudView cloud, size_t n_per_cloud, int n_clouds, size_t cloud_stride, const float4* hyps,
+                  int K, float t, int dot_order, int32_t* counts, int num_sms, cudaStream_t s);
+
+// K3: inlier predicate with hyps[model_index] + exact integer moments about the model's first sample point.
+// out must be zeroed.  sample_pts supplies the pivot (sample_pts[3 * model_index]).
+void launch_refit(CloudView cloud, size_t n, const float4* hyps, const int4* sample_pts, int model_index, float t,
+                  int dot_order, int scale_exp, RefitOut* out, int num_sms, cudaStream_t s);
+
+// K5: stable partition by the inlier predicate of `plane`: remaining points -> dst (NaN re-padded),
+// inlier positions -> inl_cur, their original indices -> inl_orig.  totals[0] = remaining, totals[1] = inliers.
+// scratch: tile_state (n_tiles x uint64) + ticket, zeroed by the wrapper.
+size_t compact_scratch_bytes(size_t n);
+void launch_compact(CloudView src, size_t n, Plane4 plane, float t, int dot_order, CloudView dst, bool write_remaining,
+                    int32_t* inl_cur, int32_t* inl_orig, void* scratch, long long* totals, cudaStream_t s);
+
+// Batch: per-cloud inlier count of per-cloud planes is K2 with K = 1; nothing else needed.
+
+// Measurement helpers.
+void launch_ffma_peak(float* out, int iters, int grid, cudaStream_t s);
+void launch_copy(const float4* src, float4* dst, size_t n_vec, int num_sms, cudaStream_t s);
+void launch_fill(float4* dst, size_t n_vec, float v, int num_sms, cudaStream_t s);
+
+}  // namespace pr

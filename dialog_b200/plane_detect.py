@@ -1,0 +1,247 @@
+"""Host-side mirror of the PlaneDetect call surface for the RANSAC backend.
+
+The reference drives plane detection as a stage between estimateNormal() and polyPlanes()
+(Dialog/PCLViewer.cpp:1183-1226): input is the global PointCloudT::Ptr source_cloud
+(Dialog/PlaneDetect.h:104), output is one Plane{coeff, points_set} per plane appended to
+plane_clouds_final (Dialog/HeaderFile.h:81-98) and source_cloud rebuilt from the unclaimed points
+(Dialog/PlaneDetect.h:1560-1566).  `detect_planes` has that shape; `PlaneRansac` is the thin object
+over the C ABI (include/plane_ransac.h) that the tests and the bench harness drive.  The C++ shim with
+the same surface is include/PlaneDetectRansac.h.
+
+All device work happens in libplane_ransac.so; nothing here computes on the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import _lib
+from ._lib import DOT_FMA, DOT_PCL_SSE2, PlaneRansacError, PrParams, PrProfile, PrSegmentInfo  # noqa: F401
+
+
+def make_params(distance_threshold: float = 0.1, max_iterations: int = 50, min_plane_size: int = 500,
+                probability: float = 0.99, optimize_coefficients: bool = True, seed: int = 12345,
+                max_planes: int = 64, dot_order: int = DOT_FMA) -> PrParams:
+    """Defaults: T_dist_point_plane / T_num_of_single_plane from Dialog/config.txt:29,20 and PCL's
+    SACSegmentation defaults for the knobs config.txt has no key for."""
+    return PrParams(float(distance_threshold), int(max_iterations), int(min_plane_size), float(probability),
+                    int(bool(optimize_coefficients)), int(seed), int(max_planes), int(dot_order))
+
+
+def as_cloud(points: np.ndarray) -> np.ndarray:
+    """(N,4) float32 C-contiguous rows laid out like pcl::PointXYZ (x, y, z, 1)."""
+    a = np.asarray(points)
+    if a.ndim != 2 or a.shape[1] not in (3, 4):
+        raise ValueError("cloud must have shape (N,3) or (N,4)")
+    if a.shape[1] == 3:
+        b = np.ones((a.shape[0], 4), np.float32)
+        b[:, :3] = a
+        return b
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+@dataclass
+class Plane:
+    """== struct Plane (Dialog/HeaderFile.h:81-88) restricted to what this path fills."""
+    coeff: np.ndarray                 # (4,) a, b, c, d
+    inliers_cur: np.ndarray           # indices into the cloud of the round that found it
+    inliers_orig: np.ndarray          # indices into the staged cloud (== points_set)
+    info: PrSegmentInfo = None
+
+
+@dataclass
+class Extraction:
+    planes: list = field(default_factory=list)
+    infos: list = field(default_factory=list)   # one per segment call, the final rejected one included
+
+    @property
+    def coeffs(self) -> np.ndarray:
+        return np.array([p.coeff for p in self.planes], np.float32).reshape(-1, 4)
+
+
+class PlaneRansac:
+    """One CUDA device + stream behind the C ABI.  Not thread-safe (like the reference's GUI-thread path)."""
+
+    def __init__(self, device: int = 0):
+        self._L = _lib.load()
+        h = C.c_void_p()
+        _lib.check(self._L.plane_ransac_create(C.byref(h), device))
+        self._h = h
+        self._keep = None
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.plane_ransac_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # ---- staging ----
+    def set_cloud(self, points: np.ndarray) -> int:
+        a = as_cloud(points)
+        _lib.check(self._L.plane_ransac_set_cloud(self._h, a.ctypes.data_as(C.c_void_p), a.shape[0]))
+        return a.shape[0]
+
+    def set_cloud_ptr(self, host_ptr: int, n: int) -> None:
+        """Stage from a raw host address (e.g. a pinned torch tensor's data_ptr())."""
+        _lib.check(self._L.plane_ransac_set_cloud(self._h, C.c_void_p(host_ptr), n))
+
+    def set_cloud_device_ptr(self, dev_ptr: int, n: int) -> None:
+        _lib.check(self._L.plane_ransac_set_cloud_device(self._h, C.c_void_p(dev_ptr), n))
+
+    def cloud_size(self):
+        a, b = C.c_size_t(0), C.c_size_t(0)
+        _lib.check(self._L.plane_ransac_cloud_size(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    # ---- scoring hook ----
+    def score(self, triples: np.ndarray, distance_threshold: float, dot_order: int = DOT_FMA, want_models: bool = False):
+        t = np.ascontiguousarray(triples, np.int32).reshape(-1, 3)
+        K = t.shape[0]
+        counts = np.zeros(K, np.int32)
+        coeffs = np.zeros((K, 4), np.float32) if want_models else None
+        good = np.zeros(K, np.uint8) if want_models else None
+        _lib.check(self._L.plane_ransac_score(
+            self._h, t.ctypes.data_as(C.c_void_p), K, float(distance_threshold), dot_order,
+            counts.ctypes.data_as(C.c_void_p),
+            coeffs.ctypes.data_as(C.c_void_p) if want_models else None,
+            good.ctypes.data_as(C.c_void_p) if want_models else None))
+        return (counts, coeffs, good.astype(bool)) if want_models else counts
+
+    # ---- segment / extract ----
+    def segment_one(self, params: PrParams):
+        n_staged, _ = self.cloud_size()
+        coeff = np.zeros(4, np.float32)
+        inl = np.empty(max(n_staged, 1), np.int32)
+        n = C.c_size_t(0)
+        info = PrSegmentInfo()
+        _lib.check(self._L.plane_ransac_segment_one(self._h, C.byref(params), coeff.ctypes.data_as(C.c_void_p),
+                                                    inl.ctypes.data_as(C.c_void_p), inl.size, C.byref(n), C.byref(info)))
+        return coeff, inl[: n.value].copy(), info
+
+    def extract_planes(self, params: PrParams, want_indices: bool = True) -> Extraction:
+        n_staged, _ = self.cloud_size()
+        mp = params.max_planes
+        coeffs = np.zeros((max(mp, 1), 4), np.float32)
+        offs = np.zeros(mp + 1, np.uintp)
+        npl = C.c_int(0)
+        infos = (PrSegmentInfo * (mp + 1))()
+        cur = np.empty(max(n_staged, 1), np.int32) if want_indices else None
+        orig = np.empty(max(n_staged, 1), np.int32) if want_indices else None
+        _lib.check(self._L.plane_ransac_extract_planes(
+            self._h, C.byref(params), coeffs.ctypes.data_as(C.c_void_p),
+            cur.ctypes.data_as(C.c_void_p) if want_indices else None,
+            orig.ctypes.data_as(C.c_void_p) if want_indices else None,
+            n_staged if want_indices else 0, offs.ctypes.data_as(C.c_void_p), C.byref(npl), infos))
+        P = npl.value
+        o = [int(v) for v in offs[: P + 1]]
+        ex = Extraction()
+        for k in range(P):
+            ex.planes.append(Plane(coeffs[k].copy(),
+                                   cur[o[k]: o[k + 1]].copy() if want_indices else None,
+                                   orig[o[k]: o[k + 1]].copy() if want_indices else None, infos[k]))
+        ex.infos = [infos[k] for k in range(min(P + 1, mp))]
+        return ex
+
+    def remaining(self) -> np.ndarray:
+        _, n_cur = self.cloud_size()
+        out = np.empty((max(n_cur, 1), 4), np.float32)
+        n = C.c_size_t(0)
+        _lib.check(self._L.plane_ransac_remaining(self._h, out.ctypes.data_as(C.c_void_p), out.shape[0], C.byref(n)))
+        return out[: n.value]
+
+    # ---- sharding ----
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        buf = C.create_string_buffer(_lib.UNIQUE_ID_BYTES)
+        _lib.check(_lib.load().plane_ransac_comm_unique_id(buf))
+        return buf.raw
+
+    def comm_init(self, n_ranks: int, rank: int, unique_id: bytes) -> None:
+        buf = C.create_string_buffer(unique_id, _lib.UNIQUE_ID_BYTES)
+        _lib.check(self._L.plane_ransac_comm_init(self._h, n_ranks, rank, buf))
+
+    def shard_info(self):
+        v = [C.c_longlong(0) for _ in range(4)]
+        _lib.check(self._L.plane_ransac_shard_info(self._h, *[C.byref(x) for x in v]))
+        return tuple(x.value for x in v)
+
+    # ---- measurement ----
+    def profile_enable(self, on: bool = True):
+        _lib.check(self._L.plane_ransac_profile_enable(self._h, int(on)))
+
+    def profile_reset(self):
+        _lib.check(self._L.plane_ransac_profile_reset(self._h))
+
+    def profile(self) -> PrProfile:
+        p = PrProfile()
+        _lib.check(self._L.plane_ransac_profile_get(self._h, C.byref(p)))
+        return p
+
+    def measure_ffma_peak(self) -> float:
+        v = C.c_double(0)
+        _lib.check(self._L.plane_ransac_measure_ffma_peak(self._h, C.byref(v)))
+        return v.value
+
+    def measure_copy_bw(self, nbytes: int = 1 << 30) -> float:
+        v = C.c_double(0)
+        _lib.check(self._L.plane_ransac_measure_copy_bw(self._h, nbytes, C.byref(v)))
+        return v.value
+
+    def flush_l2(self):
+        _lib.check(self._L.plane_ransac_flush_l2(self._h))
+
+
+# ---- host-side logic exported by the library (no device needed) ---------------------------------
+def host_draw_triples(n_points: int, n_draws: int, seed: int = 12345) -> np.ndarray:
+    out = np.empty((n_draws, 3), np.int32)
+    _lib.check(_lib.load().plane_ransac_host_draw_triples(n_points, seed, n_draws, out.ctypes.data_as(C.c_void_p)))
+    return out
+
+
+def host_replay(counts, good, n_points: int, max_iterations: int, probability: float):
+    c = np.ascontiguousarray(counts, np.int32)
+    g = np.ascontiguousarray(good, np.uint8)
+    v = [C.c_int(0) for _ in range(5)]
+    _lib.check(_lib.load().plane_ransac_host_replay(c.ctypes.data_as(C.c_void_p), g.ctypes.data_as(C.c_void_p), c.size,
+                                                    n_points, max_iterations, probability, *[C.byref(x) for x in v]))
+    return dict(best_draw=v[0].value, iterations=v[1].value, draws_used=v[2].value, skipped=v[3].value,
+                exhausted=bool(v[4].value))
+
+
+def host_shard_range(n_points: int, n_ranks: int, rank: int):
+    a, b = C.c_longlong(0), C.c_longlong(0)
+    _lib.check(_lib.load().plane_ransac_host_shard_range(n_points, n_ranks, rank, C.byref(a), C.byref(b)))
+    return a.value, b.value
+
+
+def host_plane_from_moments(moments, pivot, scale_exp: int) -> np.ndarray:
+    m = np.ascontiguousarray(moments, np.int64)
+    p = np.ascontiguousarray(pivot, np.float32)
+    out = np.zeros(4, np.float32)
+    _lib.check(_lib.load().plane_ransac_host_plane_from_moments(m.ctypes.data_as(C.c_void_p), p.ctypes.data_as(C.c_void_p),
+                                                                scale_exp, out.ctypes.data_as(C.c_void_p)))
+    return out
+
+
+def detect_planes(source_cloud: np.ndarray, distance_threshold: float = 0.1, max_iterations: int = 50,
+                  min_plane_size: int = 500, device: int = 0, **kw):
+    """PlaneDetect-style entry: cloud + (threshold, max iterations, minimum plane size) ->
+    (list of Plane, remaining cloud).  The remaining cloud is what the reference leaves in
+    source_cloud after postProcessPlanes (Dialog/PlaneDetect.h:1560-1566)."""
+    with PlaneRansac(device) as pr:
+        pr.set_cloud(source_cloud)
+        ex = pr.extract_planes(make_params(distance_threshold, max_iterations, min_plane_size, **kw))
+        return ex.planes, pr.remaining().copy()

@@ -1,0 +1,191 @@
+/*
+ * plane_ransac.h — C ABI of the B200 (sm_100a) plane-detection backend.
+ *
+ * Drop-in boundary for ONE path of czh55/Dialog: multi-plane extraction from a
+ * pcl::PointCloud<pcl::PointXYZ> by RANSAC plane segmentation with iterative inlier peeling
+ * (PCL 1.8 SACSegmentation<PointXYZ>(SACMODEL_PLANE, SAC_RANSAC) + ExtractIndices semantics).
+ * The reference has no FFI layer of its own; every entry point below names the
+ * reference (or PCL 1.8) interface it stands in for.
+ *
+ *   pr_point                       pcl::PointXYZ / PointT            Dialog/HeaderFile.h:53-54
+ *   pr_params.distance_threshold   T_dist_point_plane                Dialog/PlaneDetect.h:88, config.txt:29
+ *   pr_params.min_plane_size       T_num_of_single_plane             Dialog/PlaneDetect.h:70, config.txt:20
+ *   pr_params.max_iterations       SACSegmentation::setMaxIterations (no counterpart in config.txt)
+ *   plane coefficients (a,b,c,d)   Plane::coeff.values               Dialog/HeaderFile.h:81-88, PlaneDetect.h:1493-1497
+ *   inlier indices                 Plane::points_set                 Dialog/HeaderFile.h:85
+ *   remaining cloud                rebuilt source_cloud              Dialog/PlaneDetect.h:1560-1566
+ *
+ * All types are POD; no C++ types or exceptions cross the boundary.  Every call returns 0 on
+ * success or a negative pr_status; plane_ransac_last_error() holds the message of the calling
+ * thread's last failure.  One context owns one CUDA device + stream and is not thread-safe (the
+ * reference drives this path from the GUI thread only, Dialog/PCLViewer.cpp:1180-1235).
+ * There is no CPU fallback: without a CUDA device plane_ransac_create fails.
+ */
+#ifndef PLANE_RANSAC_H
+#define PLANE_RANSAC_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PLANE_RANSAC_ABI_VERSION 1
+
+typedef struct plane_ransac_ctx plane_ransac_ctx;
+
+/* == pcl::PointXYZ: 16 bytes, w is padding (treated as 1). */
+typedef struct { float x, y, z, w; } pr_point;
+
+typedef enum {
+  PR_OK = 0,
+  PR_ERR_INVALID = -1,   /* bad argument                                              */
+  PR_ERR_CUDA = -2,      /* CUDA runtime / driver error                               */
+  PR_ERR_NO_CLOUD = -3,  /* no cloud staged                                           */
+  PR_ERR_CAPACITY = -4,  /* caller buffer too small                                   */
+  PR_ERR_COMM = -5,      /* NCCL error or NCCL not loadable                           */
+  PR_ERR_OOM = -6        /* host or device allocation failed                          */
+} pr_status;
+
+/* Order of the FP32 dot product coeff·(x,y,z,1) in the distance test.
+ *   PR_DOT_PCL_SSE2  (a*x + c*z) + (b*y + d), products and sums rounded separately: Eigen's SSE2
+ *                    packet reduction as PCL 1.8 / MSVC v140 runs it.  6 FP32 ops per point-hypothesis.
+ *   PR_DOT_FMA       fma(a,x, fma(b,y, fma(c,z,d))): 3 FFMA per point-hypothesis (default).
+ * The two differ only for points whose residual is within rounding of the threshold. */
+enum { PR_DOT_PCL_SSE2 = 0, PR_DOT_FMA = 1 };
+
+/* pcl::SACSegmentation knobs + the peel stop rule. */
+typedef struct {
+  double distance_threshold;  /* setDistanceThreshold(double); inlier iff |n·p + d| <  t (strict) */
+  int max_iterations;         /* setMaxIterations; up to max_iterations + 1 trials are scored    */
+  int min_plane_size;         /* stop peeling when a plane has fewer inliers                     */
+  double probability;         /* setProbability; 0.99 = PCL default; 1.0 = score every trial     */
+  int optimize_coefficients;  /* setOptimizeCoefficients: least-squares refit + re-selection     */
+  unsigned seed;              /* 12345u = PCL's non-random SampleConsensusModel seed             */
+  int max_planes;             /* bound on planes returned by plane_ransac_extract_planes         */
+  int dot_order;              /* PR_DOT_*                                                         */
+} pr_params;
+
+/* What one segment() call decided (mirrors RandomSampleConsensus state; used by parity tests). */
+typedef struct {
+  int ok;               /* a model was found                                                    */
+  int iterations;       /* RandomSampleConsensus::iterations_                                   */
+  int draws;            /* drawIndexSample calls consumed                                       */
+  int skipped;          /* skipped_count                                                        */
+  int best_sample[3];   /* model_ (indices into the cloud of this round, global when sharded)   */
+  int best_count;       /* inliers of the raw model                                             */
+  float raw_coeff[4];   /* model_coefficients_ before the refit                                 */
+  int n_inliers_raw;    /* == best_count                                                        */
+  int n_inliers;        /* final inlier count (after refit + re-selection), global when sharded */
+  int scale_exp;        /* refit grid exponent s (grid = 2^-s)                                  */
+  int n_scored;         /* hypotheses scored on the device for this call                        */
+  long long n_cloud;    /* points in the cloud of this round (global when sharded)              */
+} pr_segment_info;
+
+/* Device time per kernel class, accumulated while profiling is enabled (CUDA events on the
+ * context's stream), and launch counts since the last plane_ransac_profile_reset. */
+typedef struct {
+  double ms_stage, ms_models, ms_score, ms_refit, ms_compact, ms_other;
+  long long launches_stage, launches_models, launches_score, launches_refit, launches_compact,
+      launches_other;
+  long long pairs_scored;    /* sum of points x hypotheses over score launches (this rank)      */
+  long long points_refit;    /* points streamed by refit launches                               */
+  long long points_compact;  /* points streamed by compaction launches                          */
+  long long bytes_compact;   /* algorithmic bytes of compaction launches (read + written)       */
+  long long bytes_refit;     /* algorithmic bytes of refit launches                             */
+} pr_profile;
+
+/* ---- lifetime ---------------------------------------------------------------------------- */
+int plane_ransac_abi_version(void);
+const char* plane_ransac_last_error(void);
+void plane_ransac_default_params(pr_params* p); /* t=0.1, it=50, min=500, p=0.99, refit, 12345, 64, FMA */
+int plane_ransac_create(plane_ransac_ctx** ctx, int device_id);
+void plane_ransac_destroy(plane_ransac_ctx* ctx);
+
+/* ---- staging: replaces preProcess's copy of source_cloud (Dialog/PlaneDetect.h:449-455) ----
+ * Uploads the AoS cloud and transposes it to x[] y[] z[] planes in HBM (128-bit aligned, padded
+ * with NaN to a tile multiple).  The staged cloud is immutable; extract/segment calls start from it
+ * (plane_ransac_extract_planes may be called repeatedly).  pts may be pageable or pinned host memory. */
+int plane_ransac_set_cloud(plane_ransac_ctx* ctx, const pr_point* pts, size_t n);
+/* Same, from a device pointer (AoS pr_point[] already in HBM on the context's device). */
+int plane_ransac_set_cloud_device(plane_ransac_ctx* ctx, const pr_point* dev_pts, size_t n);
+/* n_staged: points given to set_cloud; n_current: points left after the last extract call. */
+int plane_ransac_cloud_size(plane_ransac_ctx* ctx, size_t* n_staged, size_t* n_current);
+
+/* ---- countWithinDistance for K models (bench + parity hook) --------------------------------
+ * triples: 3*K indices into the staged cloud (as drawn by SampleConsensusModel::drawIndexSample).
+ * counts[k] = |{ i : |coeff_k · (p_i,1)| < t }|; coeffs (optional, 4*K) and good (optional, K)
+ * receive computeModelCoefficients' output and isSampleGood's verdict; bad samples count 0. */
+int plane_ransac_score(plane_ransac_ctx* ctx, const int32_t* triples, int K, double t, int dot_order,
+                       int32_t* counts, float* coeffs, uint8_t* good);
+
+/* ---- pcl::SACSegmentation<PointXYZ>::segment(inliers, coefficients) on the staged cloud -----
+ * inliers: ascending indices, capacity cap.  On "no model" n_inliers = 0 and coeff is zeroed. */
+int plane_ransac_segment_one(plane_ransac_ctx* ctx, const pr_params* prm, float coeff[4], int32_t* inliers,
+                             size_t cap, size_t* n_inliers, pr_segment_info* info);
+
+/* ---- segment + ExtractIndices(negative) peel loop -------------------------------------------
+ * coeffs: 4*max_planes floats.  inlier_cur (optional): per plane, indices into the cloud of that
+ * round (what PCL's loop yields); inlier_orig (optional): the same points as indices into the staged
+ * cloud; both have capacity idx_cap entries in total and are delimited by plane_offsets
+ * (max_planes + 1 entries).  infos (optional): max_planes + 1 entries, the last rejected segment
+ * call included.  When sharded, indices are local to this rank's shard. */
+int plane_ransac_extract_planes(plane_ransac_ctx* ctx, const pr_params* prm, float* coeffs,
+                                int32_t* inlier_cur, int32_t* inlier_orig, size_t idx_cap,
+                                size_t* plane_offsets, int* n_planes, pr_segment_info* infos);
+/* Points left after the last extract call, original order (== the rebuilt source_cloud). */
+int plane_ransac_remaining(plane_ransac_ctx* ctx, pr_point* out, size_t cap, size_t* n);
+
+/* ---- batch of equal-sized small clouds (per-scan tiles), one best plane each, no peel --------
+ * pts: n_clouds * n_per_cloud points.  Every cloud runs segment() with the same parameters (and,
+ * having the same size and seed, the same index triples).  coeffs: 4*n_clouds; n_inliers: n_clouds. */
+int plane_ransac_set_cloud_batch(plane_ransac_ctx* ctx, const pr_point* pts, size_t n_clouds,
+                                 size_t n_per_cloud);
+int plane_ransac_segment_batch(plane_ransac_ctx* ctx, const pr_params* prm, float* coeffs,
+                               int32_t* n_inliers, pr_segment_info* infos /* optional, n_clouds */);
+
+/* ---- point-sharded multi-GPU (one process per GPU; NCCL over NVLink) -------------------------
+ * Rank r stages its contiguous index range of the global cloud with plane_ransac_set_cloud; after
+ * comm_init every segment/extract/score call is collective: per-hypothesis counts and refit moments
+ * are summed with ncclAllReduce (integers, so the result is bit-identical to one GPU). */
+#define PLANE_RANSAC_UNIQUE_ID_BYTES 128
+int plane_ransac_comm_unique_id(void* out128);
+int plane_ransac_comm_init(plane_ransac_ctx* ctx, int n_ranks, int rank, const void* unique_id128);
+/* Global size and this rank's first global index for the staged / current cloud. */
+int plane_ransac_shard_info(plane_ransac_ctx* ctx, long long* n_global_staged, long long* first_staged,
+                            long long* n_global_current, long long* first_current);
+
+/* ---- measurement ------------------------------------------------------------------------- */
+int plane_ransac_profile_enable(plane_ransac_ctx* ctx, int on);
+int plane_ransac_profile_reset(plane_ransac_ctx* ctx);
+int plane_ransac_profile_get(plane_ransac_ctx* ctx, pr_profile* out);
+/* FP32 FMA peak of this device measured with an FFMA-only kernel (TFLOP/s), for the scoring roofline. */
+int plane_ransac_measure_ffma_peak(plane_ransac_ctx* ctx, double* tflops);
+/* Streaming copy bandwidth of this device (GB/s, read + write bytes), for the HBM rooflines. */
+int plane_ransac_measure_copy_bw(plane_ransac_ctx* ctx, size_t bytes, double* gbs);
+/* Writes a buffer larger than L2 (between timed iterations). */
+int plane_ransac_flush_l2(plane_ransac_ctx* ctx);
+
+/* ---- host-side logic, exported for tests and multi-process drivers (no device work) -----------
+ * The first n_draws triples SampleConsensusModel::drawIndexSample yields for n points. */
+int plane_ransac_host_draw_triples(size_t n_points, unsigned seed, int n_draws, int32_t* triples);
+/* RandomSampleConsensus::computeModel's loop replayed over per-draw results: counts[j] is the
+ * inlier count of draw j, good[j] isSampleGood's verdict.  Returns the index of the winning draw in
+ * *best_draw (-1: none), fills iterations/draws_used/skipped, and sets *exhausted when the loop
+ * would have needed more than n_draws draws. */
+int plane_ransac_host_replay(const int32_t* counts, const uint8_t* good, int n_draws, long long n_points,
+                             int max_iterations, double probability, int* best_draw, int* iterations,
+                             int* draws_used, int* skipped, int* exhausted);
+/* Contiguous shard [first, first + count) of rank r among n_ranks for n points. */
+int plane_ransac_host_shard_range(long long n_points, int n_ranks, int rank, long long* first,
+                                  long long* count);
+/* Least-squares plane from exact integer moments (see DESIGN.md "refit"): m = {n, Sx, Sy, Sz,
+ * Sxx_hi, Sxx_lo, ... Szz_hi, Szz_lo}, S_ab = hi * 2^32 + lo. */
+int plane_ransac_host_plane_from_moments(const int64_t m[16], const float pivot[3], int scale_exp,
+                                         float coeff[4]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PLANE_RANSAC_H */

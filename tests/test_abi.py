@@ -1,0 +1,66 @@
+"""CPU checks of the drop-in boundary: the C-ABI library builds, loads without a GPU and exports every
+symbol include/plane_ransac.h declares; the product never reaches into oracle/."""
+import ctypes
+import os
+import re
+import subprocess
+
+import pytest
+
+from conftest import ROOT
+
+
+def _declared_symbols():
+    hdr = open(os.path.join(ROOT, "include", "plane_ransac.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    return sorted(set(re.findall(r"\b(plane_ransac_[a-z0-9_]+)\s*\(", hdr)))
+
+
+def test_header_symbols_are_exported(lib_built):
+    names = _declared_symbols()
+    assert len(names) >= 25
+    L = ctypes.CDLL(lib_built)
+    missing = [n for n in names if not hasattr(L, n)]
+    assert not missing, missing
+    from dialog_b200 import _lib
+    assert sorted(_lib.SYMBOLS) == names
+
+
+def test_abi_version_and_defaults(lib_built):
+    from dialog_b200 import _lib
+    L = _lib.load()
+    assert L.plane_ransac_abi_version() == 1
+    p = _lib.PrParams()
+    L.plane_ransac_default_params(ctypes.byref(p))
+    # Dialog/config.txt:29 T_dist_point_plane, :20 T_num_of_single_plane; PCL SACSegmentation defaults
+    assert (p.distance_threshold, p.max_iterations, p.min_plane_size, p.probability) == (0.1, 50, 500, 0.99)
+    assert (p.optimize_coefficients, p.seed, p.dot_order) == (1, 12345, _lib.DOT_FMA)
+
+
+def test_library_does_not_link_the_oracle_or_need_nccl_at_load(lib_built):
+    out = subprocess.run(["ldd", lib_built], capture_output=True, text=True).stdout
+    assert "oracle" not in out and "nccl" not in out
+    syms = subprocess.run(["nm", "-D", lib_built], capture_output=True, text=True).stdout
+    assert "orc_" not in syms
+
+
+def test_product_sources_never_reference_the_oracle():
+    bad = []
+    for base in ("dialog_b200", "include"):
+        for dp, _, fs in os.walk(os.path.join(ROOT, base)):
+            for f in fs:
+                if f.endswith((".py", ".cu", ".cpp", ".h", ".hpp", ".cuh")):
+                    txt = open(os.path.join(dp, f), errors="replace").read()
+                    if re.search(r"\boracle\b|pr_oracle|orc_", txt):
+                        bad.append(os.path.join(dp, f))
+    assert not bad, bad
+
+
+def test_create_without_gpu_fails_loudly(lib_built):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from dialog_b200 import PlaneRansac, PlaneRansacError
+    with pytest.raises(PlaneRansacError) as e:
+        PlaneRansac(0)
+    assert "no CPU fallback" in str(e.value)

@@ -1,0 +1,260 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same inputs.
+Bit-exact for counts, inlier index lists, the extracted plane sequence and the remaining cloud; plane
+coefficients bit-exact too (the refit is exact integer arithmetic on both sides)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def pr(lib_built):
+    import dialog_b200 as D
+    with D.PlaneRansac(0) as h:
+        yield h
+
+
+def _oparams(O, p, refit=None):
+    return O.make_params(p.distance_threshold, p.max_iterations, p.min_plane_size, p.probability,
+                         p.optimize_coefficients, p.seed, p.max_planes, p.dot_order,
+                         O.REFIT_FIXED if refit is None else refit)
+
+
+def _same_bits(a, b):
+    return np.asarray(a, np.float32).tobytes() == np.asarray(b, np.float32).tobytes()
+
+
+# ---------------------------------------------------------------------------------------------
+# K1 + K2: models from triples and inlier counts
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("order", [0, 1])
+@pytest.mark.parametrize("n,K", [(991, 51), (1000, 1), (1024, 32), (4099, 33), (100_000, 256), (300_001, 1024),
+                                 (50_000, 2500)])
+def test_score_counts_bit_exact(O, pr, scene2, double_shadow, order, n, K):
+    pts = double_shadow if n == 991 else scene2.points(0, n)
+    t = 0.005 if n == 991 else 0.1
+    tri = O.draw_sequence(pts.shape[0], K)
+    pr.set_cloud(pts)
+    counts, coeffs, good = pr.score(tri, t, order, want_models=True)
+    oc, og = O.models_from_triples(pts, tri)
+    assert (good == og).all()
+    assert _same_bits(coeffs[og], oc[og]) and np.isnan(coeffs[~og]).all()
+    want = O.count_batch(pts, np.nan_to_num(oc), t, order)
+    want[~og] = 0
+    assert (counts == want).all()
+
+
+def test_score_handles_bad_samples_nan_points_and_ragged_sizes(O, pr):
+    rng = np.random.default_rng(3)
+    pts = rng.normal(size=(2500, 3)).astype(np.float32)
+    pts[10] = pts[11]                    # duplicate
+    pts[100] = [np.nan, 0, 0]
+    pts[101] = [np.inf, 1, 2]
+    pts[200:203] = [[1, 2, 3], [2, 4, 6], [3, 6, 9]]   # collinear with equal ratios
+    tri = np.array([[200, 201, 202], [10, 11, 12], [0, 1, 2], [100, 5, 6], [7, 101, 9], [12, 10, 11]], np.int32)
+    pr.set_cloud(pts)
+    for order in (0, 1):
+        counts, coeffs, good = pr.score(tri, 0.25, order, want_models=True)
+        oc, og = O.models_from_triples(pts, tri)
+        assert (good == og).all() and not og[0] and not og[1]
+        ok = og & ~np.isnan(oc).any(1)
+        assert _same_bits(coeffs[ok], oc[ok])
+        want = np.array([O.count_within(pts, c, 0.25, order) if g else 0 for c, g in zip(oc, og)])
+        assert (counts == want).all()
+
+
+def test_score_epsilon_band_between_dot_orders(O, pr, scene3):
+    """north_star: masks/counts bit-exact except points within the stated band of the threshold, which are
+    enumerated.  GPU(FMA) vs oracle(PCL SSE2 order): every differing point lies within
+    1e-6 * (|ax|+|by|+|cz|+|d|) of t; GPU(PCL order) vs oracle(PCL order) has no exceptions."""
+    pts = scene3.points(0, 500_000)
+    tri = O.draw_sequence(pts.shape[0], 128)
+    pr.set_cloud(pts)
+    c_fma = pr.score(tri, 0.1, 1)
+    c_pcl = pr.score(tri, 0.1, 0)
+    oc, og = O.models_from_triples(pts, tri)
+    want_pcl = O.count_batch(pts, np.nan_to_num(oc), 0.1, O.DOT_PCL_SSE2)
+    assert (c_pcl == want_pcl).all()
+    exceptions = 0
+    for k in np.nonzero(c_fma != c_pcl)[0]:
+        r0 = O.residuals(pts, oc[k], O.DOT_PCL_SSE2).astype(np.float64)
+        r1 = O.residuals(pts, oc[k], O.DOT_FMA).astype(np.float64)
+        diff = (np.abs(r0) < 0.1) != (np.abs(r1) < 0.1)
+        mag = np.abs(pts[:, :3].astype(np.float64) * oc[k, :3].astype(np.float64)).sum(1) + abs(float(oc[k, 3]))
+        assert (np.abs(np.abs(r0[diff]) - 0.1) <= 1e-6 * mag[diff]).all()
+        assert abs(int(c_fma[k]) - int(c_pcl[k])) <= int(diff.sum())
+        exceptions += int(diff.sum())
+    print(f"enumerated threshold-band exceptions over 128 models x 500k points: {exceptions}")
+
+
+# ---------------------------------------------------------------------------------------------
+# segment(): RANSAC + refit + re-selection
+# ---------------------------------------------------------------------------------------------
+def _check_segment(O, pr, pts, prm):
+    import dialog_b200 as D
+    pr.set_cloud(pts)
+    coeff, inl, info = pr.segment_one(prm)
+    seg = O.segment(pts, _oparams(O, prm))
+    assert bool(info.ok) == seg.ok
+    assert info.iterations == seg.trace.iterations and info.draws == seg.trace.draws
+    if not seg.ok:
+        assert inl.size == 0 and (coeff == 0).all()
+        return
+    assert list(info.best_sample) == list(seg.trace.best_sample)
+    assert info.best_count == seg.trace.best_count
+    assert _same_bits(list(info.raw_coeff), list(seg.trace.raw_coeff))
+    if prm.optimize_coefficients:
+        assert info.scale_exp == seg.trace.scale_exp
+    assert _same_bits(coeff, seg.coeff), (coeff, seg.coeff)
+    assert inl.size == seg.inliers.size and (inl == seg.inliers).all()
+    assert info.n_inliers == seg.inliers.size
+
+
+@pytest.mark.parametrize("order", [0, 1])
+@pytest.mark.parametrize("prob,max_it,opt", [(0.99, 50, True), (1.0, 255, True), (1.0, 1023, False), (0.99, 2000, True)])
+def test_segment_one_matches_oracle(O, pr, scene2, order, prob, max_it, opt):
+    import dialog_b200 as D
+    pts = scene2.points(0, 120_000)
+    _check_segment(O, pr, pts, D.make_params(0.1, max_it, 500, prob, opt, 12345, 8, order))
+
+
+def test_segment_golden_double_shadow(O, pr, double_shadow):
+    """BASELINE config 1: the reference's bundled cloud with config.txt's threshold (0.1) and with 0.005."""
+    import dialog_b200 as D
+    cases = json.load(open(os.path.join(GOLDEN, "double_shadow_golden.json")))
+    pr.set_cloud(double_shadow)
+    n = 0
+    for c in cases:
+        p = c["params"]
+        if p["refit_mode"] != O.REFIT_FIXED:
+            continue
+        prm = D.make_params(p["distance_threshold"], p["max_iterations"], p["min_plane_size"], p["probability"],
+                            p["optimize_coefficients"], p["seed"], p["max_planes"], p["dot_order"])
+        coeff, inl, info = pr.segment_one(prm)
+        assert [float(v).hex() for v in coeff] == c["coeff"]
+        assert inl.size == c["n_inliers"] and info.iterations == c["iterations"]
+        assert list(info.best_sample) == c["best_sample"] and info.best_count == c["best_count"]
+        n += 1
+    assert n == 4
+
+
+def test_segment_degenerate_clouds(O, pr):
+    import dialog_b200 as D
+    prm = D.make_params(0.1, 50, 1, 0.99, True)
+    for pts in (np.zeros((0, 3), np.float32), np.zeros((2, 3), np.float32)):
+        _check_segment(O, pr, pts, prm)
+    i = np.arange(1, 51, dtype=np.float32)
+    _check_segment(O, pr, np.c_[i, 2 * i, 4 * i], prm)               # all samples collinear: no model
+    flat = np.c_[np.random.default_rng(0).random((5000, 2)), np.zeros(5000)].astype(np.float32)
+    _check_segment(O, pr, flat, prm)                                # every point an inlier, exit after 1 trial
+    pr.set_cloud(np.ones((50, 3), np.float32))                      # 0/0 samples: NaN model, no inliers
+    coeff, inl, info = pr.segment_one(prm)
+    assert info.ok and np.isnan(coeff).all() and inl.size == 0 and info.iterations == 51
+    tiny = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0]], np.float32)  # 3 inliers: refit returns the raw model
+    _check_segment(O, pr, tiny, prm)
+
+
+# ---------------------------------------------------------------------------------------------
+# extract_planes(): the peel loop
+# ---------------------------------------------------------------------------------------------
+def _check_extract(O, pr, pts, prm):
+    pr.set_cloud(pts)
+    ex = pr.extract_planes(prm)
+    want = O.extract_planes(pts, _oparams(O, prm))
+    assert len(ex.planes) == len(want.coeffs)
+    for k, p in enumerate(ex.planes):
+        assert _same_bits(p.coeff, want.coeffs[k]), (k, p.coeff, want.coeffs[k])
+        assert p.inliers_cur.size == want.inliers_cur[k].size
+        assert (p.inliers_cur == want.inliers_cur[k]).all()
+        assert (p.inliers_orig == want.inliers_orig[k]).all()
+        assert list(p.info.best_sample) == list(want.traces[k].best_sample)
+    rem = pr.remaining()
+    assert rem.shape == want.remaining.shape and rem.tobytes() == want.remaining.tobytes()
+    # calling again on the same staged cloud gives the same answer (staging is immutable)
+    ex2 = pr.extract_planes(prm)
+    assert len(ex2.planes) == len(ex.planes)
+    assert all(_same_bits(a.coeff, b.coeff) and (a.inliers_orig == b.inliers_orig).all()
+               for a, b in zip(ex.planes, ex2.planes))
+    return ex
+
+
+@pytest.mark.parametrize("order", [0, 1])
+def test_extract_three_planes_matches_oracle(O, pr, scene2, order):
+    import dialog_b200 as D
+    pts = scene2.points(0, 150_000)
+    ex = _check_extract(O, pr, pts, D.make_params(0.1, 255, 5000, 1.0, True, 12345, 8, order))
+    assert len(ex.planes) == 3
+
+
+def test_extract_indoor_scene_matches_oracle(O, pr, scene3):
+    import dialog_b200 as D
+    pts = scene3.points(0, 250_000)
+    ex = _check_extract(O, pr, pts, D.make_params(0.1, 511, 500, 1.0, True, 12345, 20, D.DOT_FMA))
+    assert len(ex.planes) == 20
+
+
+def test_extract_pcl_defaults_and_max_planes(O, pr, scene2):
+    import dialog_b200 as D
+    pts = scene2.points(0, 80_000)
+    _check_extract(O, pr, pts, D.make_params(0.1, 50, 500, 0.99, True, 12345, 2, D.DOT_PCL_SSE2))
+    _check_extract(O, pr, pts, D.make_params(0.1, 50, 500, 0.99, False, 12345, 6, D.DOT_FMA))
+    _check_extract(O, pr, pts, D.make_params(0.1, 50, 10**9, 0.99, True, 12345, 6, D.DOT_FMA))   # nothing big enough
+    _check_extract(O, pr, pts, D.make_params(0.1, 50, 500, 0.99, True, 12345, 0, D.DOT_FMA))     # max_planes = 0
+
+
+def test_extract_capacity_error(pr, scene2):
+    import ctypes as C
+    import dialog_b200 as D
+    from dialog_b200 import _lib
+    pts = scene2.points(0, 20_000)
+    pr.set_cloud(pts)
+    prm = D.make_params(0.1, 50, 500, 0.99, True)
+    coeffs = np.zeros((prm.max_planes, 4), np.float32)
+    offs = np.zeros(prm.max_planes + 1, np.uintp)
+    small = np.zeros(10, np.int32)
+    npl = C.c_int(0)
+    rc = _lib.load().plane_ransac_extract_planes(pr._h, C.byref(prm), coeffs.ctypes.data_as(C.c_void_p),
+                                                 small.ctypes.data_as(C.c_void_p), None, 10,
+                                                 offs.ctypes.data_as(C.c_void_p), C.byref(npl), None)
+    assert rc == -4 and b"inlier index buffers" in _lib.load().plane_ransac_last_error()
+
+
+# ---------------------------------------------------------------------------------------------
+# size-independent properties at BASELINE sizes (the oracle would take minutes there)
+# ---------------------------------------------------------------------------------------------
+def test_properties_at_10m_points(O, pr, scene3):
+    import dialog_b200 as D
+    n = 10_000_000
+    pts = scene3.points(0, n)
+    pr.set_cloud(pts)
+    prm = D.make_params(0.1, 4095, 500, 1.0, True, 12345, 20, D.DOT_FMA)
+    ex = pr.extract_planes(prm)
+    assert len(ex.planes) == 20
+    rem = pr.remaining()
+    allidx = np.concatenate([p.inliers_orig for p in ex.planes])
+    # partition: planes and the remaining cloud tile the input, order preserved
+    seen = np.zeros(n, bool)
+    seen[allidx] = True
+    assert seen.sum() == allidx.size                        # no index twice
+    assert rem.shape[0] == n - allidx.size
+    assert rem.tobytes() == pts[~seen].tobytes()            # stable compaction of the unclaimed points
+    for p in ex.planes:
+        assert (np.diff(p.inliers_cur) > 0).all() and (np.diff(p.inliers_orig) > 0).all()
+        assert p.info.n_inliers == p.inliers_cur.size and p.info.n_scored == 4096
+    # round 0 against the oracle on a sample of hypotheses: counts of the winning and 7 other draws
+    tri = O.draw_sequence(n, 4096)
+    pick = np.r_[[np.nonzero((tri == list(ex.planes[0].info.best_sample)).all(1))[0][0]], np.arange(7)]
+    got = pr.score(tri[pick], 0.1, D.DOT_FMA)
+    oc, og = O.models_from_triples(pts, tri[pick])
+    assert (got == O.count_batch(pts, np.nan_to_num(oc), 0.1, O.DOT_FMA, threads=8)).all()
+    assert got[0] == ex.planes[0].info.best_count and got[0] == got.max()
+    # every reported inlier really is within t of its plane, evaluated by the oracle
+    p0 = ex.planes[0]
+    r = O.residuals(pts[p0.inliers_orig], p0.coeff, O.DOT_FMA)
+    assert (np.abs(r) < np.float32(0.1)).all()
+    assert p0.inliers_orig.size == O.count_within(pts, p0.coeff, 0.1, O.DOT_FMA, mt=True)
