@@ -1,0 +1,312 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the plane-RANSAC hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (BASELINE.json configs[2], the configuration "ms per 10M-pt multi-plane extraction" is quoted
+on): a synthetic 10M-point indoor scene per GPU, 20 planes peeled iteratively, 4096 hypotheses scored per
+round (max_iterations = 4095, probability = 1.0), distance threshold 0.1 (Dialog/config.txt:29), minimum
+plane size 500 (Dialog/config.txt:20), PCL RNG seed 12345.  A step is one full extraction.  With N > 1
+ranks the cloud is N x 10M points sharded by contiguous index range (weak scaling); per-hypothesis counts
+and refit moments are summed with NCCL all-reduces, so the result equals the one-GPU result on the same
+cloud bit for bit.
+
+Printed (rank 0, one JSON line): value = point-hypotheses scored per second over the whole job with the
+cloud resident in HBM; ms_per_step = ms per extraction; e2e = the same metric through the C ABI with host
+buffers (pinned upload of the cloud + download of coefficients and inlier index lists inside the timed
+region); roofline (scoring kernel vs the FP32-FMA peak measured live, 6 FLOP per point-hypothesis) and
+roofline_hbm (compaction / refit vs MEASURED_PEAKS.json); cpu_baseline (the CPU oracle's PCL-faithful scalar
+loop on a bounded sample, rank 0 only).
+
+--impl reference times the CPU restatement of the reference's PCL path (oracle/, all host threads) on a
+bounded sample of the same workload.  PCL itself is not installable here.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "RANSAC point-hypotheses scored/sec; ms per 10M-pt multi-plane extraction"
+UNIT = "point-hypotheses/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--points", type=int, default=10_000_000, help="points per GPU")
+    ap.add_argument("--hyps", type=int, default=4096, help="hypotheses per round")
+    ap.add_argument("--planes", type=int, default=20)
+    ap.add_argument("--cpu-sample-hyps", type=int, default=512)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload_config(args, n_gpus):
+    return {
+        "workload": "configs[2]: synthetic indoor scene, %d points per GPU x %d GPU(s), %d planes peeled, %d "
+                    "hypotheses per round (max_iterations=%d, probability=1.0), t=0.1, min_plane=500, seed=12345"
+                    % (args.points, n_gpus, args.planes, args.hyps, args.hyps - 1),
+        "points_per_gpu": args.points, "points_total": args.points * n_gpus, "hypotheses_per_round": args.hyps,
+        "planes": args.planes, "distance_threshold": 0.1, "min_plane_size": 500, "dot_order": "fma",
+        "sharding": "points, contiguous index ranges; NCCL all-reduce of int32 counts + int64 moments" if n_gpus > 1 else "none",
+        "l2": "256 MiB fill kernel between timed steps (outside the timed region); cloud planes are 120 MB per GPU",
+    }
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                pass
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 9 for n, v in zip(names, r[5:9]) if v.lower().startswith("active")})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def measured_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return None
+
+
+def cpu_sample(args, pts, threads):
+    """PCL's countWithinDistance loop (the oracle) over the first S hypotheses of round 0."""
+    from oracle import oracle as O
+    S = args.cpu_sample_hyps
+    tri = O.draw_sequence(pts.shape[0], S)
+    coeffs, good = O.models_from_triples(pts, tri)
+    t0 = time.perf_counter()
+    O.count_batch(pts, np.nan_to_num(coeffs), 0.1, O.DOT_FMA, threads=threads)
+    dt = time.perf_counter() - t0
+    return pts.shape[0] * S / dt, dt
+
+
+def run_reference(args):
+    """Reference arm: the CPU restatement of the PCL path, all host threads, bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from dialog_b200 import synth
+    cores = os.cpu_count() or 1
+    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    pts = synth.indoor_scene().points(0, args.points)
+    from oracle import oracle as O
+    S = max(8, min(args.cpu_sample_hyps, 64))
+    tri = O.draw_sequence(pts.shape[0], S)
+    coeffs, good = O.models_from_triples(pts, tri)
+    coeffs = np.nan_to_num(coeffs)
+    times = []
+    for i in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        O.count_batch(pts, coeffs, 0.1, O.DOT_FMA, threads=cores)
+        if i >= args.warmup:
+            times.append(time.perf_counter() - t0)
+    ms = 1e3 * sum(times) / len(times)
+    value = pts.shape[0] * S / (ms * 1e-3)
+    sample = "countWithinDistance of the first %d hypotheses of round 0 over the %d-point cloud per step (the full " \
+             "step scores %d x %d rounds); OpenMP over points, %d threads" % (S, args.points, args.hyps, args.planes, cores)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": workload_config(args, args.gpus),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+            "note": "PCL 1.8 is not installable here; this is the CPU oracle (oracle/pr_oracle.c) restating its loop"}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import dialog_b200 as D
+    from dialog_b200 import build, synth
+    build.build()
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the plane-RANSAC backend has no CPU path")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    # ---- data: this rank's contiguous shard of the global cloud, generated in place ----
+    n_total = args.points * world
+    first, count = D.host_shard_range(n_total, world, rank)
+    scene = synth.indoor_scene()
+    pts = scene.points(first, first + count)
+    pinned = torch.empty((count, 4), dtype=torch.float32, pin_memory=True)
+    pinned.numpy()[:] = pts
+
+    pr = D.PlaneRansac(local_rank)
+    if world > 1:
+        uid = [D.PlaneRansac.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        pr.comm_init(world, rank, uid[0])
+    prm = D.make_params(0.1, args.hyps - 1, 500, 1.0, True, 12345, args.planes, D.DOT_FMA)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def pairs_of(ex):
+        return sum(int(i.n_cloud) * int(i.n_scored) for i in ex.infos)
+
+    # ---- resident arm: cloud staged once, timed region = extract_planes (coefficients only) ----
+    pr.set_cloud_ptr(pinned.data_ptr(), count)
+    peak_tf = pr.measure_ffma_peak()
+    for _ in range(args.warmup):
+        ex = pr.extract_planes(prm, want_indices=False)
+    pr.profile_enable(True)
+    pr.profile_reset()
+    clocks = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        clocks.start()
+    step_ms = []
+    for _ in range(args.steps):
+        pr.flush_l2()
+        barrier()
+        pr.timer_start()
+        ex = pr.extract_planes(prm, want_indices=False)
+        step_ms.append(pr.timer_stop())
+    barrier()
+    prof = pr.profile()
+    pr.profile_enable(False)
+    pairs_step = pairs_of(ex)
+    n_planes = len(ex.planes)
+    total_ms = sum(step_ms)
+
+    # ---- end-to-end arm: host cloud in, coefficients + inlier index lists out, every step ----
+    for _ in range(min(args.warmup, 2)):
+        pr.set_cloud_ptr(pinned.data_ptr(), count)
+        pr.extract_planes(prm, want_indices=True)
+    barrier()
+    e2e_ms = []
+    for _ in range(args.steps):
+        pr.flush_l2()
+        barrier()
+        pr.timer_start()
+        pr.set_cloud_ptr(pinned.data_ptr(), count)
+        ex2 = pr.extract_planes(prm, want_indices=True)
+        e2e_ms.append(pr.timer_stop())
+    barrier()
+    clock_info = clocks.stop() if rank == 0 else None
+    e2e_total_ms = sum(e2e_ms)
+    n_inl_local = sum(p.inliers_cur.size for p in ex2.planes)
+    n_draws = sum(int(i.n_scored) for i in ex2.infos)
+    h2d = count * 16 + n_draws * 12
+    d2h = n_inl_local * 8 + n_draws * 8 + len(ex2.infos) * (144 + 16 + 16)
+
+    # ---- max over ranks ----
+    t = torch.tensor([total_ms, e2e_total_ms], dtype=torch.float64, device="cuda")
+    agg = torch.tensor([float(h2d), float(d2h)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(agg, op=dist.ReduceOp.SUM)
+    total_ms, e2e_total_ms = t.tolist()
+    h2d_all, d2h_all = agg.tolist()
+
+    if rank == 0:
+        ms_per_step = total_ms / args.steps
+        value = pairs_step / (ms_per_step * 1e-3)
+        e2e_value = pairs_step / (e2e_total_ms / args.steps * 1e-3)
+        peaks = measured_peaks()
+        hbm_peak = peaks["hbm_gbs"] if peaks else 6650.0
+        score_tf = 6.0 * prof.pairs_scored / (prof.ms_score * 1e-3) / 1e12 if prof.ms_score > 0 else None
+        compact_gbs = prof.bytes_compact / (prof.ms_compact * 1e-3) / 1e9 if prof.ms_compact > 0 else None
+        refit_gbs = prof.bytes_refit / (prof.ms_refit * 1e-3) / 1e9 if prof.ms_refit > 0 else None
+        launches = (prof.launches_stage + prof.launches_models + prof.launches_score + prof.launches_refit +
+                    prof.launches_compact + prof.launches_other)
+        kernel_ms = prof.ms_models + prof.ms_score + prof.ms_refit + prof.ms_compact
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": workload_config(args, world),
+            "planes_extracted": n_planes, "pairs_per_step": pairs_step,
+            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_total_ms / args.steps,
+                    "h2d_bytes_per_step": int(h2d_all), "d2h_bytes_per_step": int(d2h_all)},
+            "gpu_launches": int(launches),
+            "roofline": {
+                "kernel": "score_kernel<8,FMA>", "bound": "fp32_fma", "achieved": score_tf, "peak": peak_tf,
+                "unit": "TFLOP/s", "frac": (score_tf / peak_tf) if score_tf and peak_tf else None, "traffic": None,
+                "peak_source": "FFMA2-only kernel timed live on this GPU (MEASURED_PEAKS.json has no FP32 figure; "
+                               "nominal 148 SM x 128 lanes x 2 x 1.965 GHz = 74.4)",
+                "algorithmic": "6 FLOP (3 FMA) per point-hypothesis x points x hypotheses per launch",
+                "ms_in_timed_region": prof.ms_score, "share_of_kernel_time": prof.ms_score / kernel_ms if kernel_ms else None},
+            "roofline_hbm": {
+                "compact": {"bound": "hbm", "achieved": compact_gbs, "peak": hbm_peak, "unit": "GB/s",
+                            "frac": compact_gbs / hbm_peak if compact_gbs else None, "ms": prof.ms_compact,
+                            "algorithmic": "16 B read per point + 16 B per remaining point + 8 B per inlier"},
+                "refit": {"bound": "hbm", "achieved": refit_gbs, "peak": hbm_peak, "unit": "GB/s",
+                          "frac": refit_gbs / hbm_peak if refit_gbs else None, "ms": prof.ms_refit,
+                          "algorithmic": "12 B read per point"},
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)"},
+            "kernel_ms_per_step": {"models": prof.ms_models / args.steps, "score": prof.ms_score / args.steps,
+                                   "refit": prof.ms_refit / args.steps, "compact": prof.ms_compact / args.steps},
+            "clocks": clock_info,
+        }
+        if not args.no_cpu_baseline:
+            v, dt = cpu_sample(args, pts, threads=1)
+            line["cpu_baseline"] = {
+                "value": v, "unit": UNIT, "cores": 1, "kind": "port", "seconds": dt,
+                "sample": "oracle countWithinDistance (PCL 1.8 scalar loop, 1 thread) over the first %d hypotheses of "
+                          "round 0 on rank 0's %d points" % (args.cpu_sample_hyps, count)}
+        print(json.dumps(line), flush=True)
+
+    pr.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -153,6 +153,7 @@ struct plane_ransac_ctx {
   bool global_valid = false;
 
   // measurement
+  cudaEvent_t timer_a = nullptr, timer_b = nullptr;
   bool profiling = false;
   std::vector<TimedSpan> spans;
   pr_profile prof;
@@ -583,6 +584,7 @@ void plane_ransac_destroy(plane_ransac_ctx* c) {
   dev_free(c->d_scratch); dev_free(c->d_inl_cur); dev_free(c->d_inl_orig); dev_free(c->d_flush); dev_free(c->batch_mem);
   pin_free(c->h_triples); pin_free(c->h_counts); pin_free(c->h_good); pin_free(c->h_refit);
   pin_free(c->h_totals); pin_free(c->h_small);
+  if (c->timer_a) { cudaEventDestroy(c->timer_a); cudaEventDestroy(c->timer_b); }
   cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -826,6 +828,27 @@ int plane_ransac_profile_get(plane_ransac_ctx* c, pr_profile* out) {
   if (!out) return fail(PR_ERR_INVALID, "null output");
   collect_spans(c);
   *out = c->prof;
+  return PR_OK;
+}
+
+int plane_ransac_timer_start(plane_ransac_ctx* c) {
+  PR_TRY(check_ctx(c));
+  if (!c->timer_a) {
+    PR_CUDA(cudaEventCreate(&c->timer_a));
+    PR_CUDA(cudaEventCreate(&c->timer_b));
+  }
+  PR_CUDA(cudaEventRecord(c->timer_a, c->stream));
+  return PR_OK;
+}
+
+int plane_ransac_timer_stop(plane_ransac_ctx* c, double* ms) {
+  PR_TRY(check_ctx(c));
+  if (!ms || !c->timer_a) return fail(PR_ERR_INVALID, "timer_stop without timer_start");
+  PR_CUDA(cudaEventRecord(c->timer_b, c->stream));
+  PR_CUDA(cudaEventSynchronize(c->timer_b));
+  float t = 0.f;
+  PR_CUDA(cudaEventElapsedTime(&t, c->timer_a, c->timer_b));
+  *ms = t;
   return PR_OK;
 }
 

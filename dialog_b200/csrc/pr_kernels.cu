@@ -74,7 +74,7 @@ __device__ __forceinline__ float2 plane_dot2(float a, float b, float c, float d,
   }
   // Separately rounded products and sums must stay scalar: ptxas 12.9 contracts mul.rn.f32x2 +
   // add.rn.f32x2 into FFMA2 even though both carry an explicit rounding mode (seen in SASS and as
-  // +-1 count differences against the oracle); scalar FMUL/FADD with .rn are never fused.
+  // +-1 count differences in the parity tests); scalar FMUL/FADD with .rn are never fused.
   return make_float2(plane_dot<0>(a, b, c, d, x.x, y.x, z.x), plane_dot<0>(a, b, c, d, x.y, y.y, z.y));
 }
 

@@ -190,6 +190,14 @@ class PlaneRansac:
         _lib.check(self._L.plane_ransac_profile_get(self._h, C.byref(p)))
         return p
 
+    def timer_start(self):
+        _lib.check(self._L.plane_ransac_timer_start(self._h))
+
+    def timer_stop(self) -> float:
+        v = C.c_double(0)
+        _lib.check(self._L.plane_ransac_timer_stop(self._h, C.byref(v)))
+        return v.value
+
     def measure_ffma_peak(self) -> float:
         v = C.c_double(0)
         _lib.check(self._L.plane_ransac_measure_ffma_peak(self._h, C.byref(v)))

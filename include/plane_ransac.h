@@ -160,6 +160,10 @@ int plane_ransac_shard_info(plane_ransac_ctx* ctx, long long* n_global_staged, l
 int plane_ransac_profile_enable(plane_ransac_ctx* ctx, int on);
 int plane_ransac_profile_reset(plane_ransac_ctx* ctx);
 int plane_ransac_profile_get(plane_ransac_ctx* ctx, pr_profile* out);
+/* Device-side stopwatch: CUDA events recorded on the context's stream (the stream every kernel and
+ * copy of this library is issued on).  stop synchronises and returns the elapsed milliseconds. */
+int plane_ransac_timer_start(plane_ransac_ctx* ctx);
+int plane_ransac_timer_stop(plane_ransac_ctx* ctx, double* ms);
 /* FP32 FMA peak of this device measured with an FFMA-only kernel (TFLOP/s), for the scoring roofline. */
 int plane_ransac_measure_ffma_peak(plane_ransac_ctx* ctx, double* tflops);
 /* Streaming copy bandwidth of this device (GB/s, read + write bytes), for the HBM rooflines. */
