@@ -10,6 +10,7 @@
 #include <nccl.h>
 
 #include <algorithm>
+#include <chrono>
 #include <climits>
 #include <cmath>
 #include <cstdarg>
@@ -86,6 +87,13 @@ int load_nccl() {
     ncclResult_t r__ = (expr);                                                                         \
     if (r__ != ncclSuccess) return fail(PR_ERR_COMM, "%s failed: %s", #expr, g_nccl.GetErrorString(r__)); \
   } while (0)
+
+struct HostTimer {
+  double* acc;
+  std::chrono::steady_clock::time_point t0;
+  explicit HostTimer(double* a) : acc(a), t0(std::chrono::steady_clock::now()) {}
+  ~HostTimer() { *acc += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); }
+};
 
 enum KClass { KC_STAGE = 0, KC_MODELS, KC_SCORE, KC_REFIT, KC_COMPACT, KC_OTHER, KC_COUNT };
 
@@ -252,6 +260,12 @@ void collect_spans(plane_ransac_ctx* c) {
   c->spans.clear();
 }
 
+int sync_stream(plane_ransac_ctx* c) {
+  HostTimer ht(&c->prof.host_ms_wait);
+  PR_CUDA(cudaStreamSynchronize(c->stream));
+  return PR_OK;
+}
+
 int check_ctx(plane_ransac_ctx* c) {
   if (!c) return fail(PR_ERR_INVALID, "null context");
   PR_CUDA(cudaSetDevice(c->device));
@@ -377,6 +391,7 @@ struct SegmentOut {
 int segment_core(plane_ransac_ctx* c, const pr_params* prm, pr::CloudView src, size_t n_local, long long n_global,
                  long long first, bool write_remaining, pr::CloudView dst, int32_t* d_inl_cur, int32_t* d_inl_orig,
                  pr_segment_info* info, SegmentOut* out) {
+  HostTimer whole(&c->prof.host_ms_total);
   pr_segment_info inf;
   std::memset(&inf, 0, sizeof(inf));
   inf.n_cloud = n_global;
@@ -404,34 +419,54 @@ int segment_core(plane_ransac_ctx* c, const pr_params* prm, pr::CloudView src, s
       if (B < 1) B = 1;
       if ((long long)total_draws + B > (long long)INT_MAX / 4) return fail(PR_ERR_INVALID, "too many draws");
       PR_TRY(reserve_draws(c, (size_t)total_draws + (size_t)B, total_draws > 0));
-      int32_t* ht = c->h_triples.p + 3 * (size_t)total_draws;
-      for (long long j = 0; j < B; ++j) sampler.draw(ht + 3 * j);
-      int32_t* dt = c->d_triples.p + 3 * (size_t)total_draws;
-      int4* dsp = c->d_sample_pts.p + 3 * (size_t)total_draws;
-      float4* dh = c->d_hyps.p + total_draws;
+      // The batch is issued in sub-batches so that the host draws the next triples (a sequential
+      // permutation walk, ~0.1 us per draw) while the device is already scoring the previous ones.
+      // Sub-batches double in size: drawing batch i+1 costs the host about as long as the device
+      // needs for batch i on a cloud of ~1.5M points, and less on larger ones.
+      long long prev_sb = 0;
+      for (long long done = 0; done < B;) {
+        long long sb = prev_sb == 0 ? std::min<long long>(B, 256) : std::min<long long>(B - done, 2 * prev_sb);
+        if (B - done - sb < 256) sb = B - done;
+        prev_sb = sb;
+        const size_t at = (size_t)total_draws + (size_t)done;
+        int32_t* ht = c->h_triples.p + 3 * at;
+        {
+          HostTimer tm(&c->prof.host_ms_sampling);
+          for (long long j = 0; j < sb; ++j) sampler.draw(ht + 3 * j);
+        }
+        int32_t* dt = c->d_triples.p + 3 * at;
+        int4* dsp = c->d_sample_pts.p + 3 * at;
+        float4* dh = c->d_hyps.p + at;
+        int32_t* dc = c->d_counts.p + at;
+        int32_t* dg = c->d_good.p + at;
+        PR_CUDA(cudaMemcpyAsync(dt, ht, 3 * sb * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+        {
+          Span sp(c, KC_MODELS, 2);
+          pr::launch_gather_samples(src, first, n_local, dt, (int)(3 * sb), dsp, 1, 0, c->stream);
+          if (c->comm) PR_NCCL(g_nccl.AllReduce(dsp, dsp, (size_t)(3 * sb) * 4, ncclInt32, ncclSum, c->comm, c->stream));
+          pr::launch_models(dsp, (int)sb, dh, dg, c->stream);
+        }
+        PR_CUDA(cudaMemsetAsync(dc, 0, sb * sizeof(int32_t), c->stream));
+        {
+          Span sp(c, KC_SCORE, 1);
+          pr::launch_score(src, n_local, 1, 0, dh, (int)sb, t, prm->dot_order, dc, c->num_sms, c->stream);
+          c->prof.pairs_scored += (long long)n_local * sb;
+        }
+        done += sb;
+      }
       int32_t* dc = c->d_counts.p + total_draws;
       int32_t* dg = c->d_good.p + total_draws;
-      PR_CUDA(cudaMemcpyAsync(dt, ht, 3 * B * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
-      {
-        Span sp(c, KC_MODELS, 2);
-        pr::launch_gather_samples(src, first, n_local, dt, (int)(3 * B), dsp, 1, 0, c->stream);
-        if (c->comm) PR_NCCL(g_nccl.AllReduce(dsp, dsp, (size_t)(3 * B) * 4, ncclInt32, ncclSum, c->comm, c->stream));
-        pr::launch_models(dsp, (int)B, dh, dg, c->stream);
-      }
-      PR_CUDA(cudaMemsetAsync(dc, 0, B * sizeof(int32_t), c->stream));
-      {
-        Span sp(c, KC_SCORE, 1);
-        pr::launch_score(src, n_local, 1, 0, dh, (int)B, t, prm->dot_order, dc, c->num_sms, c->stream);
-        c->prof.pairs_scored += (long long)n_local * B;
-      }
       if (c->comm) PR_NCCL(g_nccl.AllReduce(dc, dc, (size_t)B, ncclInt32, ncclSum, c->comm, c->stream));
       PR_CUDA(cudaGetLastError());
       PR_CUDA(cudaMemcpyAsync(c->h_counts.p + total_draws, dc, B * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
       PR_CUDA(cudaMemcpyAsync(c->h_good.p + total_draws, dg, B * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
-      PR_CUDA(cudaStreamSynchronize(c->stream));
-      std::vector<uint8_t> good8((size_t)B);
-      for (long long j = 0; j < B; ++j) good8[j] = c->h_good.p[total_draws + j] ? 1 : 0;
-      replay.feed(c->h_counts.p + total_draws, good8.data(), (int)B);
+      PR_TRY(sync_stream(c));
+      {
+        HostTimer tm(&c->prof.host_ms_replay);
+        std::vector<uint8_t> good8((size_t)B);
+        for (long long j = 0; j < B; ++j) good8[j] = c->h_good.p[total_draws + j] ? 1 : 0;
+        replay.feed(c->h_counts.p + total_draws, good8.data(), (int)B);
+      }
       total_draws += (int)B;
       prev_batch = (int)B;
     }
@@ -464,7 +499,7 @@ int segment_core(plane_ransac_ctx* c, const pr_params* prm, pr::CloudView src, s
     PR_CUDA(cudaMemcpyAsync(c->h_refit.p, c->d_refit.p, sizeof(pr::RefitOut), cudaMemcpyDeviceToHost, c->stream));
   }
   PR_CUDA(cudaMemcpyAsync(c->h_small.p, c->d_hyps.p + best, sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
-  PR_CUDA(cudaStreamSynchronize(c->stream));
+  PR_TRY(sync_stream(c));
   std::memcpy(inf.raw_coeff, c->h_small.p, 4 * sizeof(float));
   std::memcpy(refined, inf.raw_coeff, sizeof(refined));
   if (prm->optimize_coefficients) {
@@ -488,7 +523,7 @@ int segment_core(plane_ransac_ctx* c, const pr_params* prm, pr::CloudView src, s
   if (c->comm) PR_NCCL(g_nccl.AllGather(c->d_totals.p, c->d_totals.p + 2, 2, ncclInt64, c->comm, c->stream));
   PR_CUDA(cudaMemcpyAsync(c->h_totals.p, c->d_totals.p, (2 + (c->comm ? 2 * c->n_ranks : 0)) * sizeof(long long),
                           cudaMemcpyDeviceToHost, c->stream));
-  PR_CUDA(cudaStreamSynchronize(c->stream));
+  PR_TRY(sync_stream(c));
   out->n_rem_local = c->h_totals.p[0];
   out->n_inl_local = c->h_totals.p[1];
   out->n_inl_global = out->n_inl_local;
@@ -731,7 +766,7 @@ int plane_ransac_extract_planes(plane_ransac_ctx* c, const pr_params* prm, float
   c->first_current = first;
   if (off && inlier_cur) PR_CUDA(cudaMemcpyAsync(inlier_cur, c->d_inl_cur.p, off * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
   if (off && inlier_orig) PR_CUDA(cudaMemcpyAsync(inlier_orig, c->d_inl_orig.p, off * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
-  PR_CUDA(cudaStreamSynchronize(c->stream));
+  PR_TRY(sync_stream(c));
   return PR_OK;
 }
 

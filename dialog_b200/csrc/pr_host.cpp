@@ -33,23 +33,73 @@ uint32_t Mt19937::next() {
   return y;
 }
 
-int32_t IndexSampler::get(size_t i) const {
-  auto it = moved_.find(i);
-  return it == moved_.end() ? (int32_t)i : it->second;
+static constexpr uint32_t kEmptyKey = 0xFFFFFFFFu;
+
+IndexSampler::IndexSampler(size_t n, uint32_t seed) : rng_(seed), n_(n) {
+  head_[0] = 0;
+  head_[1] = 1;
+  head_[2] = 2;
+  keys_.assign(1u << 12, kEmptyKey);
+  vals_.assign(1u << 12, 0);
+  mask_ = (1u << 12) - 1;
+}
+
+static inline uint32_t hash_index(uint32_t k) { return (k * 2654435761u) >> 7; }
+
+int32_t IndexSampler::get(uint32_t j) const {
+  for (uint32_t h = hash_index(j) & mask_;; h = (h + 1) & mask_) {
+    if (keys_[h] == j) return vals_[h];
+    if (keys_[h] == kEmptyKey) return (int32_t)j;
+  }
+}
+
+void IndexSampler::grow() {
+  std::vector<uint32_t> ok;
+  std::vector<int32_t> ov;
+  ok.swap(keys_);
+  ov.swap(vals_);
+  const uint32_t cap = (mask_ + 1) * 4;
+  keys_.assign(cap, kEmptyKey);
+  vals_.assign(cap, 0);
+  mask_ = cap - 1;
+  used_ = 0;
+  for (size_t i = 0; i < ok.size(); ++i)
+    if (ok[i] != kEmptyKey) set(ok[i], ov[i]);
+}
+
+void IndexSampler::set(uint32_t j, int32_t v) {
+  for (uint32_t h = hash_index(j) & mask_;; h = (h + 1) & mask_) {
+    if (keys_[h] == j) {
+      vals_[h] = v;
+      return;
+    }
+    if (keys_[h] == kEmptyKey) {
+      keys_[h] = j;
+      vals_[h] = v;
+      if (++used_ * 3 > mask_) grow();
+      return;
+    }
+  }
 }
 
 void IndexSampler::draw(int32_t out[3]) {
-  for (size_t i = 0; i < 3; ++i) {
+  for (uint32_t i = 0; i < 3; ++i) {
     // rnd() = boost::uniform_int<>(0, INT_MAX) over mt19937 == rng() >> 1
     const uint32_t r = rng_.next() >> 1;
-    const size_t j = i + (size_t)r % (n_ - i);
-    const int32_t vi = get(i), vj = get(j);
-    moved_[i] = vj;
-    moved_[j] = vi;
+    const size_t j = n_ <= 0xFFFFFFFFull ? i + r % (uint32_t)(n_ - i) : i + (size_t)r % (n_ - i);
+    if (j < 3) {
+      const int32_t t = head_[i];
+      head_[i] = head_[j];
+      head_[j] = t;
+    } else {
+      const int32_t vj = get((uint32_t)j);
+      set((uint32_t)j, head_[i]);
+      head_[i] = vj;
+    }
   }
-  out[0] = get(0);
-  out[1] = get(1);
-  out[2] = get(2);
+  out[0] = head_[0];
+  out[1] = head_[1];
+  out[2] = head_[2];
 }
 
 RansacReplay::RansacReplay(long long n_points, int max_iterations, double probability)

@@ -5,7 +5,6 @@
 
 #include <cstddef>
 #include <cstdint>
-#include <unordered_map>
 #include <vector>
 
 namespace pr {
@@ -27,15 +26,21 @@ class Mt19937 {
 // entries touched so far are stored, so a 10^8-point cloud costs nothing to (re)initialise.
 class IndexSampler {
  public:
-  IndexSampler(size_t n, uint32_t seed) : rng_(seed), n_(n) {}
+  IndexSampler(size_t n, uint32_t seed);
   void draw(int32_t out[3]);
   size_t size() const { return n_; }
 
  private:
-  int32_t get(size_t i) const;
+  // shuffled_indices_[j] for j >= 3: open-addressing table of the entries that differ from identity
+  int32_t get(uint32_t j) const;
+  void set(uint32_t j, int32_t v);
+  void grow();
   Mt19937 rng_;
   size_t n_;
-  std::unordered_map<size_t, int32_t> moved_;
+  int32_t head_[3];  // shuffled_indices_[0..3), touched by every swap
+  std::vector<uint32_t> keys_;
+  std::vector<int32_t> vals_;
+  uint32_t mask_ = 0, used_ = 0;
 };
 
 // RandomSampleConsensus::computeModel's while-loop (PCL 1.8 ransac.hpp), fed one draw at a time.

@@ -94,6 +94,11 @@ typedef struct {
   long long points_compact;  /* points streamed by compaction launches                          */
   long long bytes_compact;   /* algorithmic bytes of compaction launches (read + written)       */
   long long bytes_refit;     /* algorithmic bytes of refit launches                             */
+  /* host wall time inside segment/extract calls, by phase (always accumulated) */
+  double host_ms_sampling;   /* drawing PCL's index triples                                     */
+  double host_ms_replay;     /* replaying RANSAC's sequential decisions + plane from moments    */
+  double host_ms_wait;       /* blocked in stream synchronisation (device work + copies)        */
+  double host_ms_total;      /* whole calls                                                     */
 } pr_profile;
 
 /* ---- lifetime ---------------------------------------------------------------------------- */
