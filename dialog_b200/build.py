@@ -68,7 +68,25 @@ def build(force: bool = False, verbose: bool = False) -> str:
             sys.stderr.write(" ".join(cmd) + "\n" + r.stdout + r.stderr)
         if r.returncode:
             raise RuntimeError("linking libplane_ransac.so failed")
+    build_demo(force)
     return LIB
+
+
+DEMO_SRC = os.path.join(os.path.dirname(HERE), "examples", "plane_detect_demo.cpp")
+DEMO_BIN = os.path.join(os.path.dirname(HERE), "examples", "plane_detect_demo")
+SHIM = os.path.join(os.path.dirname(HERE), "include", "PlaneDetectRansac.h")
+
+
+def build_demo(force: bool = False) -> str:
+    """The C++ program that drives include/PlaneDetectRansac.h (the PlaneDetect-style shim)."""
+    if force or _newer([DEMO_SRC, SHIM, LIB], DEMO_BIN):
+        cmd = [CXX, "-O2", "-std=c++17", "-Wall", "-Wextra", f"-I{os.path.join(os.path.dirname(HERE), 'include')}",
+               DEMO_SRC, "-o", DEMO_BIN, f"-L{HERE}", "-lplane_ransac", "-Wl,-rpath,$ORIGIN/../dialog_b200"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode:
+            sys.stderr.write(" ".join(cmd) + "\n" + r.stdout + r.stderr)
+            raise RuntimeError("building examples/plane_detect_demo failed")
+    return DEMO_BIN
 
 
 if __name__ == "__main__":

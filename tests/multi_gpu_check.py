@@ -1,0 +1,67 @@
+"""Launched under torchrun by tests/test_gpu_multi.py (and by hand on a multi-GPU box):
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
+        tests/multi_gpu_check.py
+
+Every rank stages a contiguous shard of the same cloud; the sharded extraction (NCCL all-reduce of counts and
+moments) must reproduce the single-GPU extraction of the whole cloud bit for bit: same coefficients, same
+per-plane inlier sets (local indices + shard offset == global indices), same remaining points."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import dialog_b200 as D  # noqa: E402
+from dialog_b200 import synth  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    n = int(os.environ.get("PR_CHECK_POINTS", "600000"))
+    pts = synth.indoor_scene().points(0, n)
+    prm = D.make_params(0.1, 1023, 500, 1.0, True, 12345, 20, D.DOT_FMA)
+
+    # single-GPU answer (every rank computes it on its own device)
+    with D.PlaneRansac(local) as one:
+        one.set_cloud(pts)
+        want = one.extract_planes(prm)
+        want_rem = one.remaining().copy()
+        want_counts = one.score(D.host_draw_triples(n, 300), 0.1)
+
+    first, count = D.host_shard_range(n, world, rank)
+    sh = D.PlaneRansac(local)
+    uid = [D.PlaneRansac.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(uid, src=0)
+    sh.comm_init(world, rank, uid[0])
+    sh.set_cloud(pts[first: first + count])
+    assert sh.shard_info()[:2] == (n, first)
+    got_counts = sh.score(D.host_draw_triples(n, 300), 0.1)
+    assert (got_counts == want_counts).all(), "sharded counts differ"
+    got = sh.extract_planes(prm)
+    assert len(got.planes) == len(want.planes), (len(got.planes), len(want.planes))
+    for k, (a, b) in enumerate(zip(got.planes, want.planes)):
+        assert a.coeff.tobytes() == b.coeff.tobytes(), f"plane {k}: coefficients differ"
+        assert a.info.n_inliers == b.info.n_inliers and list(a.info.best_sample) == list(b.info.best_sample)
+        mine = b.inliers_orig[(b.inliers_orig >= first) & (b.inliers_orig < first + count)] - first
+        assert (a.inliers_orig == mine).all(), f"plane {k}: inlier set differs on rank {rank}"
+    rem = sh.remaining()
+    claimed = np.zeros(n, bool)
+    claimed[np.concatenate([p.inliers_orig for p in want.planes])] = True
+    assert rem.tobytes() == pts[first: first + count][~claimed[first: first + count]].tobytes()
+    tot = torch.tensor([rem.shape[0]], device="cuda")
+    dist.all_reduce(tot)
+    assert int(tot.item()) == want_rem.shape[0]
+    sh.close()
+    dist.barrier()
+    if rank == 0:
+        print(f"multi-GPU check ok: {world} ranks, {len(got.planes)} planes, bit-identical to one GPU")
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,23 @@
+"""Sharded (one process per GPU, NCCL) extraction == single-GPU extraction, bit for bit.  Needs >= 2 GPUs."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+from conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+
+
+def test_sharded_extraction_matches_single_gpu(lib_built):
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs at least 2 GPUs")
+    world = 2 if n < 4 else 4
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+           "--master-addr", "127.0.0.1", "--master-port", "29511", os.path.join(ROOT, "tests", "multi_gpu_check.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "multi-GPU check ok" in r.stdout

@@ -258,3 +258,24 @@ def test_properties_at_10m_points(O, pr, scene3):
     r = O.residuals(pts[p0.inliers_orig], p0.coeff, O.DOT_FMA)
     assert (np.abs(r) < np.float32(0.1)).all()
     assert p0.inliers_orig.size == O.count_within(pts, p0.coeff, 0.1, O.DOT_FMA, mt=True)
+
+
+# ---------------------------------------------------------------------------------------------
+# the C++ shim (include/PlaneDetectRansac.h) through its demo program
+# ---------------------------------------------------------------------------------------------
+def test_cpp_shim_demo_matches_oracle(O, lib_built, double_shadow, tmp_path):
+    import subprocess
+    from dialog_b200 import build
+    demo = build.build_demo()
+    path = tmp_path / "cloud.f32"
+    double_shadow.astype("<f4").tofile(path)
+    r = subprocess.run([demo, str(path), "0.005", "50", "100"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    lines = r.stdout.strip().splitlines()
+    want = O.extract_planes(double_shadow, O.make_params(0.005, 50, 100, 0.99, True, 12345, 64, O.DOT_FMA, O.REFIT_FIXED))
+    head = lines[0].split()
+    assert int(head[1]) == 991 and int(head[3]) == len(want.coeffs) and int(head[5]) == want.remaining.shape[0]
+    for k, line in enumerate(lines[1:]):
+        f = line.split()
+        assert int(f[3]) == want.inliers_cur[k].size
+        assert [float.fromhex(v) for v in f[5:9]] == [float(v) for v in want.coeffs[k]]
