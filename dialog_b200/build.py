@@ -90,4 +90,4 @@ def build_demo(force: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose=True))
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))

@@ -426,7 +426,7 @@ int segment_core(plane_ransac_ctx* c, const pr_params* prm, pr::CloudView src, s
       long long prev_sb = 0;
       for (long long done = 0; done < B;) {
         long long sb = prev_sb == 0 ? std::min<long long>(B, 256) : std::min<long long>(B - done, 2 * prev_sb);
-        if (B - done - sb < 256) sb = B - done;
+        if (B - done - sb <= sb) sb = B - done;  // fold a short tail into the last sub-batch
         prev_sb = sb;
         const size_t at = (size_t)total_draws + (size_t)done;
         int32_t* ht = c->h_triples.p + 3 * at;

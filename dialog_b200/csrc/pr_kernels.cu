@@ -17,6 +17,8 @@
 
 #include <math_constants.h>
 
+#include <cstdlib>
+
 namespace pr {
 
 // ------------------------------------------------------------------------------------------------
@@ -231,21 +233,35 @@ void launch_models(const int4* sample_pts, int n_models_total, float4* hyps, int
 // (127 c mod 512) << 23; c < 512 is recovered as ((acc >> 23) * 383) & 511 (127 * 383 = 1 mod 512) and
 // folded into a plain counter every <= 64 steps (<= 256 increments).
 //
-// Tiles arrive through a kStages-deep ring of TMA bulk copies (one producer lane, full/empty
-// mbarriers).  The work list is (cloud, tile) items so that a batch of small clouds runs in one launch.
+// Tiles arrive through a kScoreStages-deep ring of TMA bulk copies completing on "full" mbarriers.
+// There is no producer warp: the last warp to finish a stage (shared-memory ticket) re-arms its
+// barrier and issues the copies for the tile kScoreStages ahead, so nothing ever spins on an empty
+// slot (a spinning producer lane cost ~17 % of the issue slots of its SM sub-partition in the first
+// ncu capture).  The work list is (cloud, tile) items so that a batch of small clouds runs in one launch.
 // ------------------------------------------------------------------------------------------------
-constexpr int kScoreConsumerWarps = 8;
-constexpr int kScoreThreads = (kScoreConsumerWarps + 1) * 32;
+constexpr int kScoreWarps = 8;
+constexpr int kScoreThreads = kScoreWarps * 32;
 constexpr int kScoreStages = 3;
 
+// One (cloud, tile) work item -> three bulk copies into stage `s`, completion on s_full[s].
+__device__ __forceinline__ void score_issue_tile(const float* X, const float* Y, const float* Z, size_t cloud_stride,
+                                                 int tiles_per_cloud, int item, float* stage, uint64_t* full) {
+  const int c = item / tiles_per_cloud, tl = item - c * tiles_per_cloud;
+  const size_t off = (size_t)c * cloud_stride + (size_t)tl * kTilePoints;
+  mbar_expect_tx(full, 3u * kTilePoints * sizeof(float));
+  tma_bulk_g2s(stage, X + off, kTilePoints * sizeof(float), full);
+  tma_bulk_g2s(stage + kTilePoints, Y + off, kTilePoints * sizeof(float), full);
+  tma_bulk_g2s(stage + 2 * kTilePoints, Z + off, kTilePoints * sizeof(float), full);
+}
+
 template <int H, int DOT>
-__global__ void __launch_bounds__(kScoreThreads, 2)
+__global__ void __launch_bounds__(kScoreThreads, H <= 4 ? 4 : 2)
     score_kernel(const float* __restrict__ X, const float* __restrict__ Y, const float* __restrict__ Z,
                  size_t cloud_stride, int tiles_per_cloud, int total_items, int items_per_cta,
                  const float4* __restrict__ hyps, int K, float t, int32_t* __restrict__ counts, int warps_h) {
-  __shared__ __align__(128) float s_pts[kScoreStages][3][kTilePoints];
+  __shared__ __align__(128) float s_pts[kScoreStages][3 * kTilePoints];
   __shared__ __align__(8) uint64_t s_full[kScoreStages];
-  __shared__ __align__(8) uint64_t s_empty[kScoreStages];
+  __shared__ int s_done[kScoreStages];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int item_begin = blockIdx.x * items_per_cta;
@@ -256,33 +272,17 @@ __global__ void __launch_bounds__(kScoreThreads, 2)
 #pragma unroll
     for (int s = 0; s < kScoreStages; ++s) {
       mbar_init(&s_full[s], 1);
-      mbar_init(&s_empty[s], kScoreConsumerWarps);
+      s_done[s] = 0;
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    // prologue: fill the ring
+    for (int s = 0; s < kScoreStages && s < n_items; ++s)
+      score_issue_tile(X, Y, Z, cloud_stride, tiles_per_cloud, item_begin + s, &s_pts[s][0], &s_full[s]);
   }
   __syncthreads();
 
-  if (warp == kScoreConsumerWarps) {
-    // ---- producer: one lane feeds the ring ----
-    if (lane == 0) {
-      for (int it = 0; it < n_items; ++it) {
-        const int s = it % kScoreStages;
-        if (it >= kScoreStages) mbar_wait(&s_empty[s], ((it / kScoreStages) - 1) & 1);
-        const int item = item_begin + it;
-        const int c = item / tiles_per_cloud, tl = item - c * tiles_per_cloud;
-        const size_t off = (size_t)c * cloud_stride + (size_t)tl * kTilePoints;
-        mbar_expect_tx(&s_full[s], 3u * kTilePoints * sizeof(float));
-        tma_bulk_g2s(&s_pts[s][0][0], X + off, kTilePoints * sizeof(float), &s_full[s]);
-        tma_bulk_g2s(&s_pts[s][1][0], Y + off, kTilePoints * sizeof(float), &s_full[s]);
-        tma_bulk_g2s(&s_pts[s][2][0], Z + off, kTilePoints * sizeof(float), &s_full[s]);
-      }
-    }
-    return;
-  }
-
-  // ---- consumers ----
   const int wh = warp % warps_h, wp = warp / warps_h;
-  const int pts_per_warp = kTilePoints / (kScoreConsumerWarps / warps_h);
+  const int pts_per_warp = kTilePoints / (kScoreWarps / warps_h);
   const int p_begin = wp * pts_per_warp;
   const int steps_per_flush = min(64, pts_per_warp / 4);
   const int k_stride = 32 * warps_h;
@@ -318,19 +318,25 @@ __global__ void __launch_bounds__(kScoreThreads, 2)
     }
 
     mbar_wait(&s_full[s], (it / kScoreStages) & 1);
-    const float* sx = &s_pts[s][0][p_begin];
-    const float* sy = &s_pts[s][1][p_begin];
-    const float* sz = &s_pts[s][2][p_begin];
+    const float* sx = &s_pts[s][p_begin];
+    const float* sy = sx + kTilePoints;
+    const float* sz = sx + 2 * kTilePoints;
 
     for (int p = 0; p < pts_per_warp; p += 4 * steps_per_flush) {
+      // software pipeline: the points of step q + 1 are loaded while step q computes
+      float4 x4 = *reinterpret_cast<const float4*>(sx + p);
+      float4 y4 = *reinterpret_cast<const float4*>(sy + p);
+      float4 z4 = *reinterpret_cast<const float4*>(sz + p);
 #pragma unroll 2
       for (int q = 0; q < steps_per_flush; ++q) {
-        const float4 x4 = *reinterpret_cast<const float4*>(sx + p + 4 * q);
-        const float4 y4 = *reinterpret_cast<const float4*>(sy + p + 4 * q);
-        const float4 z4 = *reinterpret_cast<const float4*>(sz + p + 4 * q);
         const float2 xa = make_float2(x4.x, x4.y), xb = make_float2(x4.z, x4.w);
         const float2 ya = make_float2(y4.x, y4.y), yb = make_float2(y4.z, y4.w);
         const float2 za = make_float2(z4.x, z4.y), zb = make_float2(z4.z, z4.w);
+        // past the end of the warp's range the prefetch wraps to its first step; the values are unused
+        const int pn = p + 4 * q + 4;
+        x4 = *reinterpret_cast<const float4*>(sx + (pn < pts_per_warp ? pn : 0));
+        y4 = *reinterpret_cast<const float4*>(sy + (pn < pts_per_warp ? pn : 0));
+        z4 = *reinterpret_cast<const float4*>(sz + (pn < pts_per_warp ? pn : 0));
 #pragma unroll
         for (int j = 0; j < H; ++j) {
           const float2 ra = plane_dot2<DOT>(ha[j], hb[j], hc[j], hd[j], xa, ya, za);
@@ -352,8 +358,22 @@ __global__ void __launch_bounds__(kScoreThreads, 2)
         acc[j] = 0u;
       }
     }
+
+    // release the stage; the last warp to finish refills it (no thread ever spins on an empty slot)
     __syncwarp();
-    if (lane == 0) mbar_arrive(&s_empty[s]);
+    if (lane == 0) {
+      __threadfence_block();
+      const int prev = atomicAdd(&s_done[s], 1);
+      if (prev == kScoreWarps - 1) {
+        s_done[s] = 0;
+        const int next = it + kScoreStages;
+        if (next < n_items) {
+          __threadfence_block();
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          score_issue_tile(X, Y, Z, cloud_stride, tiles_per_cloud, item_begin + next, &s_pts[s][0], &s_full[s]);
+        }
+      }
+    }
   }
 #pragma unroll
   for (int j = 0; j < H; ++j) {
@@ -373,12 +393,12 @@ static void launch_score_h(const float* X, const float* Y, const float* Z, size_
                            int n_clouds, const float4* hyps, int K, float t, int dot_order, int32_t* counts, int num_sms,
                            cudaStream_t s) {
   int warps_h = next_pow2((K + 32 * H - 1) / (32 * H));
-  if (warps_h > kScoreConsumerWarps) warps_h = kScoreConsumerWarps;
+  if (warps_h > kScoreWarps) warps_h = kScoreWarps;
   const int chunk = 32 * H * warps_h;
   const int n_chunks = (K + chunk - 1) / chunk;
   const long long total_items_ll = (long long)tiles_per_cloud * n_clouds;
   const int total_items = (int)total_items_ll;
-  int gx = (2 * num_sms) / n_chunks;
+  int gx = ((H <= 4 ? 4 : 2) * num_sms) / n_chunks;
   if (gx < 1) gx = 1;
   if (gx > total_items) gx = total_items;
   const int items_per_cta = (total_items + gx - 1) / gx;
@@ -398,6 +418,8 @@ void launch_score(CloudView cloud, size_t n_per_cloud, int n_clouds, size_t clou
   const int tiles_per_cloud = (int)((n_per_cloud + kTilePoints - 1) / kTilePoints);
   int H = next_pow2((K + 31) / 32);
   if (H > 8) H = 8;
+  static const int forced_h = [] { const char* e = getenv("PR_SCORE_H"); return e ? atoi(e) : 0; }();  // tuning knob
+  if (forced_h == 4 && H > 4) H = 4;
   switch (H) {
     case 1: launch_score_h<1>(cloud.x, cloud.y, cloud.z, cloud_stride, tiles_per_cloud, n_clouds, hyps, K, t, dot_order, counts, num_sms, s); break;
     case 2: launch_score_h<2>(cloud.x, cloud.y, cloud.z, cloud_stride, tiles_per_cloud, n_clouds, hyps, K, t, dot_order, counts, num_sms, s); break;
