@@ -434,47 +434,92 @@ void launch_score(CloudView cloud, size_t n_per_cloud, int n_clouds, size_t clou
 // hi * 2^32 + lo so that 64-bit accumulators cannot overflow).  Integer sums commute, so the result
 // does not depend on the thread, block or GPU count.
 // ------------------------------------------------------------------------------------------------
+constexpr int kRefitQueue = 160;  // per-warp inlier queue: up to 31 carried over + 128 new per iteration
+
+// Moments of one quantised inlier (see the section comment): 16 int64 partial sums per thread.
+__device__ __forceinline__ void refit_accumulate(long long acc[16], float x, float y, float z, double px, double py,
+                                                 double pz, double scale) {
+  const int qx = __double2int_rn(((double)x - px) * scale);  // |q| < 2^30 by construction of the scale
+  const int qy = __double2int_rn(((double)y - py) * scale);
+  const int qz = __double2int_rn(((double)z - pz) * scale);
+  acc[0] += 1;
+  acc[1] += qx;
+  acc[2] += qy;
+  acc[3] += qz;
+  const long long pr[6] = {(long long)qx * qx, (long long)qx * qy, (long long)qx * qz,
+                           (long long)qy * qy, (long long)qy * qz, (long long)qz * qz};
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    acc[4 + 2 * k] += pr[k] >> 32;
+    acc[5 + 2 * k] += pr[k] & 0xFFFFFFFFll;
+  }
+}
+
+// Inliers are ~10 % of the points, so evaluating the FP64/int64 moment code under a divergent branch
+// would run it at ~10 % lane utilisation and make the pass instruction-bound.  Instead each warp
+// pushes its inliers into a shared-memory queue (ballot + popc ranks) and runs the moment code on 32
+// queued points at a time; sums commute, so the queue order is irrelevant.
 template <int DOT>
-__global__ void __launch_bounds__(256) refit_kernel(const float* __restrict__ X, const float* __restrict__ Y,
-                                                    const float* __restrict__ Z, size_t n,
-                                                    const float4* __restrict__ hyps, const int4* __restrict__ sample_pts,
-                                                    int model_index, float t, double scale, RefitOut* __restrict__ out) {
+__global__ void __launch_bounds__(256, 4) refit_kernel(const float* __restrict__ X, const float* __restrict__ Y,
+                                                       const float* __restrict__ Z, size_t n,
+                                                       const float4* __restrict__ hyps, const int4* __restrict__ sample_pts,
+                                                       int model_index, float t, double scale, RefitOut* __restrict__ out) {
+  __shared__ float s_q[8][3][kRefitQueue];
+  __shared__ long long s_part[8][16];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  float* qx = s_q[warp][0];
+  float* qy = s_q[warp][1];
+  float* qz = s_q[warp][2];
+
   const float4 h = hyps[model_index];
   const int4 pv = sample_pts[3 * model_index];
   const double px = (double)__int_as_float(pv.x), py = (double)__int_as_float(pv.y), pz = (double)__int_as_float(pv.z);
   long long acc[16];
 #pragma unroll
   for (int i = 0; i < 16; ++i) acc[i] = 0;
+  int queued = 0;  // warp-uniform
 
   const size_t nvec = (n + 3) / 4;  // the tail of the last vector is NaN padding: never an inlier
   const size_t stride = (size_t)gridDim.x * blockDim.x;
-  for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += stride) {
-    const float4 x4 = __ldg(reinterpret_cast<const float4*>(X) + v);
-    const float4 y4 = __ldg(reinterpret_cast<const float4*>(Y) + v);
-    const float4 z4 = __ldg(reinterpret_cast<const float4*>(Z) + v);
-    const float xs[4] = {x4.x, x4.y, x4.z, x4.w}, ys[4] = {y4.x, y4.y, y4.z, y4.w}, zs[4] = {z4.x, z4.y, z4.z, z4.w};
+  // all lanes of a warp run the same number of iterations (ballots below need the full warp)
+  const size_t warp_first = (size_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31);
+  for (size_t vb = warp_first; vb < nvec; vb += stride) {
+    const size_t v = vb + lane;
+    float xs[4], ys[4], zs[4];
+    if (v < nvec) {
+      const float4 x4 = __ldg(reinterpret_cast<const float4*>(X) + v);
+      const float4 y4 = __ldg(reinterpret_cast<const float4*>(Y) + v);
+      const float4 z4 = __ldg(reinterpret_cast<const float4*>(Z) + v);
+      xs[0] = x4.x; xs[1] = x4.y; xs[2] = x4.z; xs[3] = x4.w;
+      ys[0] = y4.x; ys[1] = y4.y; ys[2] = y4.z; ys[3] = y4.w;
+      zs[0] = z4.x; zs[1] = z4.y; zs[2] = z4.z; zs[3] = z4.w;
+    } else {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) xs[e] = ys[e] = zs[e] = CUDART_NAN_F;
+    }
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       const float r = plane_dot<DOT>(h.x, h.y, h.z, h.w, xs[e], ys[e], zs[e]);
-      if (fabsf(r) < t) {
-        const long long qx = __double2ll_rn(((double)xs[e] - px) * scale);
-        const long long qy = __double2ll_rn(((double)ys[e] - py) * scale);
-        const long long qz = __double2ll_rn(((double)zs[e] - pz) * scale);
-        acc[0] += 1;
-        acc[1] += qx;
-        acc[2] += qy;
-        acc[3] += qz;
-        const long long pr[6] = {qx * qx, qx * qy, qx * qz, qy * qy, qy * qz, qz * qz};
-#pragma unroll
-        for (int k = 0; k < 6; ++k) {
-          acc[4 + 2 * k] += pr[k] >> 32;
-          acc[5 + 2 * k] += pr[k] & 0xFFFFFFFFll;
-        }
+      const bool in = fabsf(r) < t;
+      const unsigned m = __ballot_sync(0xFFFFFFFFu, in);
+      if (in) {
+        const int pos = queued + __popc(m & lt_mask);
+        qx[pos] = xs[e];
+        qy[pos] = ys[e];
+        qz[pos] = zs[e];
       }
+      queued += __popc(m);
     }
+    __syncwarp();
+    while (queued >= 32) {
+      queued -= 32;
+      refit_accumulate(acc, qx[queued + lane], qy[queued + lane], qz[queued + lane], px, py, pz, scale);
+    }
+    __syncwarp();
   }
-  __shared__ long long s_part[8][16];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane < queued) refit_accumulate(acc, qx[lane], qy[lane], qz[lane], px, py, pz, scale);
+
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
     long long v = acc[i];
@@ -502,6 +547,7 @@ void launch_refit(CloudView cloud, size_t n, const float4* hyps, const int4* sam
   const double scale = ldexp(1.0, scale_exp);
   size_t nvec = (n + 3) / 4;
   size_t blocks = (nvec + 255) / 256;
+  // one wave exactly: 4 resident CTAs per SM (launch bounds), grid-stride over the cloud
   if (blocks > (size_t)num_sms * 4) blocks = (size_t)num_sms * 4;
   if (blocks < 1) blocks = 1;
   if (dot_order == 1)
@@ -523,7 +569,7 @@ constexpr unsigned long long kTileInclusive = 2ull << 62;
 constexpr unsigned long long kTileValueMask = (1ull << 62) - 1;
 
 template <int DOT, bool WRITE_REM>
-__global__ void __launch_bounds__(kCompactThreads)
+__global__ void __launch_bounds__(kCompactThreads, 5)
     compact_kernel(const float* __restrict__ X, const float* __restrict__ Y, const float* __restrict__ Z,
                    const int32_t* __restrict__ O, size_t n, Plane4 pl, float t, float* __restrict__ DX,
                    float* __restrict__ DY, float* __restrict__ DZ, int32_t* __restrict__ DO, size_t dst_cap,
