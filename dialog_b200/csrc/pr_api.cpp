@@ -153,6 +153,14 @@ struct plane_ransac_ctx {
   size_t batch_clouds = 0, batch_n = 0, batch_stride = 0;
   DevBuf<float> batch_mem;
   pr::CloudView batch_view;
+  std::vector<int> batch_scale_exp;
+  DevBuf<uint32_t> d_batch_bbox;
+  DevBuf<int32_t> d_batch_idx;       // best triples (3 per cloud) / model index
+  DevBuf<double> d_batch_scale;
+  DevBuf<pr::RefitOut> d_batch_refit;
+  DevBuf<float4> d_batch_hyps;       // best / refined hypothesis per cloud
+  DevBuf<int4> d_batch_pts;
+  DevBuf<int32_t> d_batch_cnt;
 
   // sharding
   ncclComm_t comm = nullptr;
@@ -617,6 +625,8 @@ void plane_ransac_destroy(plane_ransac_ctx* c) {
   dev_free(c->aos); dev_free(c->d_bbox); dev_free(c->d_triples); dev_free(c->d_counts); dev_free(c->d_good);
   dev_free(c->d_sample_pts); dev_free(c->d_hyps); dev_free(c->d_refit); dev_free(c->d_totals);
   dev_free(c->d_scratch); dev_free(c->d_inl_cur); dev_free(c->d_inl_orig); dev_free(c->d_flush); dev_free(c->batch_mem);
+  dev_free(c->d_batch_bbox); dev_free(c->d_batch_idx); dev_free(c->d_batch_scale); dev_free(c->d_batch_refit);
+  dev_free(c->d_batch_hyps); dev_free(c->d_batch_pts); dev_free(c->d_batch_cnt);
   pin_free(c->h_triples); pin_free(c->h_counts); pin_free(c->h_good); pin_free(c->h_refit);
   pin_free(c->h_totals); pin_free(c->h_small);
   if (c->timer_a) { cudaEventDestroy(c->timer_a); cudaEventDestroy(c->timer_b); }
@@ -791,15 +801,201 @@ int plane_ransac_remaining(plane_ransac_ctx* c, pr_point* out, size_t cap, size_
 // ---- batch of small clouds --------------------------------------------------------------------
 int plane_ransac_set_cloud_batch(plane_ransac_ctx* c, const pr_point* pts, size_t n_clouds, size_t n_per_cloud) {
   PR_TRY(check_ctx(c));
-  (void)pts; (void)n_clouds; (void)n_per_cloud;
-  return fail(PR_ERR_INVALID, "batch staging is not built yet");
+  if (n_clouds == 0 || n_per_cloud == 0 || !pts) return fail(PR_ERR_INVALID, "empty batch");
+  if (n_per_cloud > (size_t)INT_MAX - 4096 || n_clouds > (size_t)1 << 24) return fail(PR_ERR_INVALID, "batch too large");
+  const size_t stride = (n_per_cloud + pr::kTilePoints - 1) / pr::kTilePoints * pr::kTilePoints;
+  const size_t cap = n_clouds * stride + pr::kTilePoints;
+  const size_t n_total = n_clouds * n_per_cloud;
+  PR_TRY(dev_reserve(c->aos, n_total));
+  PR_TRY(dev_reserve(c->batch_mem, 3 * cap));
+  PR_TRY(dev_reserve(c->d_batch_bbox, 6 * n_clouds));
+  PR_CUDA(cudaMemcpyAsync(c->aos.p, pts, n_total * sizeof(pr_point), cudaMemcpyHostToDevice, c->stream));
+  c->batch_view = planes_view(c->batch_mem.p, nullptr, cap);
+  {
+    Span sp(c, KC_STAGE, 2);
+    pr::launch_stage_batch(c->aos.p, n_clouds, n_per_cloud, stride, c->batch_view, c->d_batch_bbox.p, c->stream);
+  }
+  PR_CUDA(cudaGetLastError());
+  std::vector<uint32_t> keys(6 * n_clouds);
+  PR_CUDA(cudaMemcpyAsync(keys.data(), c->d_batch_bbox.p, keys.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+  PR_CUDA(cudaStreamSynchronize(c->stream));
+  c->batch_scale_exp.resize(n_clouds);
+  for (size_t i = 0; i < n_clouds; ++i) c->batch_scale_exp[i] = pr::scale_exp_from_bbox_keys(&keys[6 * i]);
+  c->batch_clouds = n_clouds;
+  c->batch_n = n_per_cloud;
+  c->batch_stride = stride;
+  return PR_OK;
 }
 
 int plane_ransac_segment_batch(plane_ransac_ctx* c, const pr_params* prm, float* coeffs, int32_t* n_inliers,
                                pr_segment_info* infos) {
   PR_TRY(check_ctx(c));
-  (void)prm; (void)coeffs; (void)n_inliers; (void)infos;
-  return fail(PR_ERR_INVALID, "batch segmentation is not built yet");
+  PR_TRY(check_params(prm));
+  if (c->batch_clouds == 0) return fail(PR_ERR_NO_CLOUD, "no batch staged");
+  if (!coeffs || !n_inliers) return fail(PR_ERR_INVALID, "null output");
+  HostTimer whole(&c->prof.host_ms_total);
+  const size_t C = c->batch_clouds, n = c->batch_n, stride = c->batch_stride;
+  const float t = pr::threshold_up(prm->distance_threshold);
+  std::vector<pr::RansacReplay> replay;
+  replay.reserve(C);
+  for (size_t i = 0; i < C; ++i) replay.emplace_back((long long)std::max<size_t>(n, 1), prm->max_iterations, prm->probability);
+  // every cloud has n points and the same seed, so PCL draws the same triples for every cloud
+  std::vector<int32_t> all_triples;
+  int total_draws = 0;
+  auto all_done = [&] {
+    for (auto& r : replay)
+      if (!r.done()) return false;
+    return true;
+  };
+  if (n >= 3 && !all_done()) {
+    pr::IndexSampler sampler(n, prm->seed);
+    long long prev = 0;
+    while (!all_done()) {
+      int min_it = INT_MAX;
+      for (auto& r : replay)
+        if (!r.done()) min_it = std::min(min_it, r.iterations());
+      const long long trials_left = (long long)prm->max_iterations + 1 - min_it;
+      long long B = prm->probability >= 1.0 ? trials_left : prev == 0 ? std::min<long long>(trials_left, 256)
+                                                                      : std::min<long long>(trials_left, 2 * prev);
+      if (B < 1) B = 1;
+      if ((double)B * (double)C > 4.0e8) B = std::max<long long>(1, (long long)(4.0e8 / (double)C));
+      prev = B;
+      const size_t CB = C * (size_t)B;
+      PR_TRY(reserve_draws(c, CB, false));  // sample_pts 3*CB, hyps CB, counts CB, good CB (triples 3*CB, over-sized)
+      all_triples.resize(3 * ((size_t)total_draws + (size_t)B));
+      int32_t* ht = all_triples.data() + 3 * (size_t)total_draws;
+      {
+        HostTimer tm(&c->prof.host_ms_sampling);
+        for (long long j = 0; j < B; ++j) sampler.draw(ht + 3 * j);
+      }
+      std::memcpy(c->h_triples.p, ht, 3 * (size_t)B * sizeof(int32_t));
+      PR_CUDA(cudaMemcpyAsync(c->d_triples.p, c->h_triples.p, 3 * (size_t)B * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+      {
+        Span sp(c, KC_MODELS, 2);
+        pr::launch_gather_samples(c->batch_view, 0, n, c->d_triples.p, (int)(3 * B), c->d_sample_pts.p, (int)C, stride, c->stream);
+        pr::launch_models(c->d_sample_pts.p, (int)CB, c->d_hyps.p, c->d_good.p, c->stream);
+      }
+      PR_CUDA(cudaMemsetAsync(c->d_counts.p, 0, CB * sizeof(int32_t), c->stream));
+      {
+        Span sp(c, KC_SCORE, 1);
+        pr::launch_score(c->batch_view, n, (int)C, stride, c->d_hyps.p, (int)B, t, prm->dot_order, c->d_counts.p, c->num_sms, c->stream);
+        c->prof.pairs_scored += (long long)n * (long long)CB;
+      }
+      PR_CUDA(cudaGetLastError());
+      PR_CUDA(cudaMemcpyAsync(c->h_counts.p, c->d_counts.p, CB * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+      PR_CUDA(cudaMemcpyAsync(c->h_good.p, c->d_good.p, CB * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+      PR_TRY(sync_stream(c));
+      {
+        HostTimer tm(&c->prof.host_ms_replay);
+        std::vector<uint8_t> good8((size_t)B);
+        for (size_t i = 0; i < C; ++i) {
+          if (replay[i].done()) continue;
+          const int32_t* g = c->h_good.p + i * (size_t)B;
+          for (long long j = 0; j < B; ++j) good8[j] = g[j] ? 1 : 0;
+          replay[i].feed(c->h_counts.p + i * (size_t)B, good8.data(), (int)B);
+        }
+      }
+      total_draws += (int)B;
+    }
+  }
+
+  // winners: per-cloud best triple -> model + pivot again (K = 1 per cloud), refit, final count
+  PR_TRY(dev_reserve(c->d_batch_idx, 3 * C));
+  PR_TRY(dev_reserve(c->d_batch_pts, 3 * C));
+  PR_TRY(dev_reserve(c->d_batch_hyps, C));
+  PR_TRY(dev_reserve(c->d_batch_cnt, 2 * C));
+  PR_TRY(dev_reserve(c->d_batch_scale, C));
+  PR_TRY(dev_reserve(c->d_batch_refit, C));
+  std::vector<int32_t> best_tri(3 * C, 0), model_idx(C, -1);
+  std::vector<double> scales(C);
+  for (size_t i = 0; i < C; ++i) {
+    const int b = replay[i].best_draw();
+    if (b >= 0) {
+      model_idx[i] = 0;
+      for (int k = 0; k < 3; ++k) best_tri[3 * i + k] = all_triples[3 * (size_t)b + k];
+    }
+    scales[i] = std::ldexp(1.0, c->batch_scale_exp[i]);
+  }
+  std::vector<float4> raw(C);
+  std::vector<pr::RefitOut> mom(C);
+  PR_CUDA(cudaMemcpyAsync(c->d_batch_idx.p, best_tri.data(), 3 * C * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+  {
+    Span sp(c, KC_MODELS, 2);
+    pr::launch_gather_samples(c->batch_view, 0, n, c->d_batch_idx.p, 3, c->d_batch_pts.p, (int)C, stride, c->stream, true);
+    pr::launch_models(c->d_batch_pts.p, (int)C, c->d_batch_hyps.p, c->d_batch_cnt.p + C, c->stream);
+  }
+  PR_CUDA(cudaMemcpyAsync(raw.data(), c->d_batch_hyps.p, C * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
+  if (prm->optimize_coefficients) {
+    PR_CUDA(cudaStreamSynchronize(c->stream));  // best_tri must be consumed before model_idx reuses the buffer
+    PR_CUDA(cudaMemcpyAsync(c->d_batch_idx.p, model_idx.data(), C * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+    PR_CUDA(cudaMemcpyAsync(c->d_batch_scale.p, scales.data(), C * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    PR_CUDA(cudaMemsetAsync(c->d_batch_refit.p, 0, C * sizeof(pr::RefitOut), c->stream));
+    {
+      Span sp(c, KC_REFIT, 1);
+      pr::launch_refit_batch(c->batch_view, n, stride, (int)C, c->d_batch_hyps.p, c->d_batch_pts.p, 1, c->d_batch_idx.p, t,
+                             prm->dot_order, c->d_batch_scale.p, c->d_batch_refit.p, c->stream);
+      c->prof.points_refit += (long long)(n * C);
+      c->prof.bytes_refit += 12ll * (long long)(n * C);
+    }
+    PR_CUDA(cudaMemcpyAsync(mom.data(), c->d_batch_refit.p, C * sizeof(pr::RefitOut), cudaMemcpyDeviceToHost, c->stream));
+  }
+  PR_CUDA(cudaGetLastError());
+  PR_TRY(sync_stream(c));
+  std::vector<float4> refined(C);
+  {
+    HostTimer tm(&c->prof.host_ms_replay);
+    for (size_t i = 0; i < C; ++i) {
+      refined[i] = raw[i];
+      if (prm->optimize_coefficients && model_idx[i] >= 0) {
+        int64_t m[16];
+        for (int k = 0; k < 16; ++k) m[k] = (int64_t)mom[i].m[k];
+        float out[4] = {raw[i].x, raw[i].y, raw[i].z, raw[i].w};
+        pr::plane_from_moments(m, mom[i].pivot, c->batch_scale_exp[i], out);
+        refined[i] = make_float4(out[0], out[1], out[2], out[3]);
+      }
+    }
+  }
+  std::vector<int32_t> final_cnt(C, 0);
+  if (prm->optimize_coefficients) {
+    PR_CUDA(cudaMemcpyAsync(c->d_batch_hyps.p, refined.data(), C * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
+    PR_CUDA(cudaMemsetAsync(c->d_batch_cnt.p, 0, C * sizeof(int32_t), c->stream));
+    {
+      Span sp(c, KC_SCORE, 1);
+      pr::launch_score(c->batch_view, n, (int)C, stride, c->d_batch_hyps.p, 1, t, prm->dot_order, c->d_batch_cnt.p, c->num_sms, c->stream);
+      c->prof.pairs_scored += (long long)(n * C);
+    }
+    PR_CUDA(cudaGetLastError());
+    PR_CUDA(cudaMemcpyAsync(final_cnt.data(), c->d_batch_cnt.p, C * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    PR_TRY(sync_stream(c));
+  }
+  for (size_t i = 0; i < C; ++i) {
+    const bool ok = model_idx[i] >= 0;
+    const int cnt = !ok ? 0 : prm->optimize_coefficients ? final_cnt[i] : replay[i].best_count();
+    n_inliers[i] = cnt;
+    const float z4[4] = {0, 0, 0, 0};
+    const float r4[4] = {refined[i].x, refined[i].y, refined[i].z, refined[i].w};
+    std::memcpy(coeffs + 4 * i, ok ? r4 : z4, 4 * sizeof(float));
+    if (infos) {
+      pr_segment_info inf;
+      std::memset(&inf, 0, sizeof(inf));
+      inf.ok = ok ? 1 : 0;
+      inf.iterations = replay[i].iterations();
+      inf.draws = replay[i].draws_used();
+      inf.skipped = replay[i].skipped();
+      inf.n_scored = total_draws;
+      inf.n_cloud = (long long)n;
+      inf.scale_exp = c->batch_scale_exp[i];
+      if (ok) {
+        for (int k = 0; k < 3; ++k) inf.best_sample[k] = best_tri[3 * i + k];
+        inf.best_count = replay[i].best_count();
+        inf.n_inliers_raw = inf.best_count;
+        inf.raw_coeff[0] = raw[i].x; inf.raw_coeff[1] = raw[i].y; inf.raw_coeff[2] = raw[i].z; inf.raw_coeff[3] = raw[i].w;
+        inf.n_inliers = cnt;
+      }
+      infos[i] = inf;
+    }
+  }
+  return PR_OK;
 }
 
 // ---- sharding -----------------------------------------------------------------------------------

@@ -137,6 +137,62 @@ __global__ void __launch_bounds__(256) unstage_kernel(const float* __restrict__ 
     aos[i] = make_float4(x[i], y[i], z[i], 1.0f);
 }
 
+// Batch of equal-sized clouds: cloud c occupies [c * stride, c * stride + n_per) of each plane, NaN up to
+// the next cloud; one bounding box per cloud.
+__global__ void bbox_init_batch_kernel(uint32_t* bbox, int n_clouds) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_clouds * 6) bbox[i] = (i % 6) < 3 ? 0xFFFFFFFFu : 0u;
+}
+
+__global__ void __launch_bounds__(256) stage_batch_kernel(const float4* __restrict__ aos, size_t n_per, size_t stride,
+                                                          float* __restrict__ x, float* __restrict__ y,
+                                                          float* __restrict__ z, size_t tail, uint32_t* __restrict__ bbox) {
+  const size_t c = blockIdx.y;
+  const bool last = c + 1 == gridDim.y;
+  const size_t span = stride + (last ? tail : 0);
+  uint32_t lo[3] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu}, hi[3] = {0u, 0u, 0u};
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < span; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t o = c * stride + i;
+    if (i < n_per) {
+      float4 p = __ldg(&aos[c * n_per + i]);
+      x[o] = p.x;
+      y[o] = p.y;
+      z[o] = p.z;
+      if (isfinite(p.x) && isfinite(p.y) && isfinite(p.z)) {
+        const float v[3] = {p.x, p.y, p.z};
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+          uint32_t k = float_order_key(v[a]);
+          lo[a] = min(lo[a], k);
+          hi[a] = max(hi[a], k);
+        }
+      }
+    } else {
+      x[o] = CUDART_NAN_F;
+      y[o] = CUDART_NAN_F;
+      z[o] = CUDART_NAN_F;
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    uint32_t l = __reduce_min_sync(0xFFFFFFFFu, lo[a]);
+    uint32_t h = __reduce_max_sync(0xFFFFFFFFu, hi[a]);
+    if ((threadIdx.x & 31) == 0) {
+      if (l != 0xFFFFFFFFu) atomicMin(&bbox[c * 6 + a], l);
+      if (h != 0u) atomicMax(&bbox[c * 6 + 3 + a], h);
+    }
+  }
+}
+
+void launch_stage_batch(const float4* aos, size_t n_clouds, size_t n_per, size_t stride, CloudView dst, uint32_t* bbox,
+                        cudaStream_t s) {
+  bbox_init_batch_kernel<<<(unsigned)((n_clouds * 6 + 255) / 256), 256, 0, s>>>(bbox, (int)n_clouds);
+  unsigned bx = (unsigned)((stride + kTilePoints + 255) / 256);
+  if (bx > 64) bx = 64;
+  dim3 grid(bx, (unsigned)n_clouds);
+  stage_batch_kernel<<<grid, 256, 0, s>>>(aos, n_per, stride, dst.x, dst.y, dst.z, dst.cap - n_clouds * stride, bbox);
+}
+
 void launch_bbox_init(uint32_t* bbox, cudaStream_t s) { bbox_init_kernel<<<1, 32, 0, s>>>(bbox); }
 
 void launch_stage(const float4* aos, size_t n, CloudView dst, uint32_t* bbox, cudaStream_t s) {
@@ -158,12 +214,13 @@ void launch_unstage(CloudView src, size_t n, float4* aos, cudaStream_t s) {
 __global__ void __launch_bounds__(256) gather_samples_kernel(const float* __restrict__ x, const float* __restrict__ y,
                                                              const float* __restrict__ z, long long first, size_t n,
                                                              const int32_t* __restrict__ triples, int n_samples,
-                                                             int4* __restrict__ out, int n_clouds, size_t cloud_stride) {
+                                                             int4* __restrict__ out, int n_clouds, size_t cloud_stride,
+                                                             bool per_cloud_triples) {
   const long long total = (long long)n_samples * n_clouds;
   for (long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x; s < total; s += (long long)gridDim.x * blockDim.x) {
     int c = (int)(s / n_samples);
     int j = (int)(s - (long long)c * n_samples);
-    long long local = (long long)triples[j] - first;
+    long long local = (long long)triples[per_cloud_triples ? s : j] - first;
     int4 v = make_int4(0, 0, 0, 0);
     if (local >= 0 && local < (long long)n) {
       size_t o = (size_t)c * cloud_stride + (size_t)local;
@@ -205,13 +262,13 @@ __global__ void __launch_bounds__(128) models_kernel(const int4* __restrict__ sa
 }
 
 void launch_gather_samples(CloudView cloud, long long first, size_t n, const int32_t* triples, int n_samples,
-                           int4* sample_pts, int n_clouds, size_t cloud_stride, cudaStream_t s) {
+                           int4* sample_pts, int n_clouds, size_t cloud_stride, cudaStream_t s, bool per_cloud_triples) {
   long long total = (long long)n_samples * n_clouds;
   if (total <= 0) return;
   long long blocks = (total + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
   gather_samples_kernel<<<(unsigned)blocks, 256, 0, s>>>(cloud.x, cloud.y, cloud.z, first, n, triples, n_samples,
-                                                         sample_pts, n_clouds, cloud_stride);
+                                                         sample_pts, n_clouds, cloud_stride, per_cloud_triples);
 }
 
 void launch_models(const int4* sample_pts, int n_models_total, float4* hyps, int32_t* good, cudaStream_t s) {
@@ -463,7 +520,21 @@ template <int DOT>
 __global__ void __launch_bounds__(256, 4) refit_kernel(const float* __restrict__ X, const float* __restrict__ Y,
                                                        const float* __restrict__ Z, size_t n,
                                                        const float4* __restrict__ hyps, const int4* __restrict__ sample_pts,
-                                                       int model_index, float t, double scale, RefitOut* __restrict__ out) {
+                                                       int model_index, float t, double scale, RefitOut* __restrict__ out,
+                                                       size_t cloud_stride, int K, const int32_t* __restrict__ model_idx_arr,
+                                                       const double* __restrict__ scale_arr) {
+  // batch mode (gridDim.y clouds): cloud c uses hypothesis c * K + model_idx_arr[c] and scale_arr[c]
+  if (model_idx_arr != nullptr) {
+    const size_t c = blockIdx.y;
+    const int mi = model_idx_arr[c];
+    if (mi < 0) return;  // no model for this cloud
+    X += c * cloud_stride;
+    Y += c * cloud_stride;
+    Z += c * cloud_stride;
+    model_index = (int)(c * (size_t)K) + mi;
+    scale = scale_arr[c];
+    out += c;
+  }
   __shared__ float s_q[8][3][kRefitQueue];
   __shared__ long long s_part[8][16];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -551,9 +622,24 @@ void launch_refit(CloudView cloud, size_t n, const float4* hyps, const int4* sam
   if (blocks > (size_t)num_sms * 4) blocks = (size_t)num_sms * 4;
   if (blocks < 1) blocks = 1;
   if (dot_order == 1)
-    refit_kernel<1><<<(unsigned)blocks, 256, 0, s>>>(cloud.x, cloud.y, cloud.z, n, hyps, sample_pts, model_index, t, scale, out);
+    refit_kernel<1><<<(unsigned)blocks, 256, 0, s>>>(cloud.x, cloud.y, cloud.z, n, hyps, sample_pts, model_index, t, scale, out, 0, 0, nullptr, nullptr);
   else
-    refit_kernel<0><<<(unsigned)blocks, 256, 0, s>>>(cloud.x, cloud.y, cloud.z, n, hyps, sample_pts, model_index, t, scale, out);
+    refit_kernel<0><<<(unsigned)blocks, 256, 0, s>>>(cloud.x, cloud.y, cloud.z, n, hyps, sample_pts, model_index, t, scale, out, 0, 0, nullptr, nullptr);
+}
+
+void launch_refit_batch(CloudView clouds, size_t n_per, size_t cloud_stride, int n_clouds, const float4* hyps,
+                        const int4* sample_pts, int K, const int32_t* model_idx, float t, int dot_order,
+                        const double* scales, RefitOut* outs, cudaStream_t s) {
+  if (n_clouds <= 0) return;
+  size_t nvec = (n_per + 3) / 4;
+  unsigned bx = (unsigned)((nvec + 255) / 256);
+  if (bx > 8) bx = 8;
+  if (bx < 1) bx = 1;
+  dim3 grid(bx, (unsigned)n_clouds);
+  if (dot_order == 1)
+    refit_kernel<1><<<grid, 256, 0, s>>>(clouds.x, clouds.y, clouds.z, n_per, hyps, sample_pts, 0, t, 1.0, outs, cloud_stride, K, model_idx, scales);
+  else
+    refit_kernel<0><<<grid, 256, 0, s>>>(clouds.x, clouds.y, clouds.z, n_per, hyps, sample_pts, 0, t, 1.0, outs, cloud_stride, K, model_idx, scales);
 }
 
 // ------------------------------------------------------------------------------------------------

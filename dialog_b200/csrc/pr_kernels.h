@@ -39,13 +39,19 @@ struct RefitOut {
 // bbox: 6 x uint32 ordered-float encodings {min x,y,z, max x,y,z}; must be initialised by bbox_init.
 void launch_bbox_init(uint32_t* bbox, cudaStream_t s);
 void launch_stage(const float4* aos, size_t n, CloudView dst, uint32_t* bbox, cudaStream_t s);
+// Batch of n_clouds equal-sized clouds: cloud c at element offset c * stride of each plane (stride = n_per
+// rounded up to a tile), NaN between clouds; bbox: 6 keys per cloud.
+void launch_stage_batch(const float4* aos, size_t n_clouds, size_t n_per, size_t stride, CloudView dst, uint32_t* bbox,
+                        cudaStream_t s);
 // planes -> AoS (w = 1)
 void launch_unstage(CloudView src, size_t n, float4* aos, cudaStream_t s);
 
 // K1a: sample_pts[s] = bits of point triples[s] if this rank owns it (first <= idx < first + n), else 0.
-// clouds > 1: batch mode, the same triples are gathered from every cloud (cloud_stride elements apart).
+// clouds > 1: batch mode, the same triples are gathered from every cloud (cloud_stride elements apart), or
+// with per_cloud_triples cloud c reads triples[c * n_samples ...].
 void launch_gather_samples(CloudView cloud, long long first, size_t n, const int32_t* triples, int n_samples,
-                           int4* sample_pts, int n_clouds, size_t cloud_stride, cudaStream_t s);
+                           int4* sample_pts, int n_clouds, size_t cloud_stride, cudaStream_t s,
+                           bool per_cloud_triples = false);
 // K1b: plane through each sample triple, PCL op order, no contraction; NaN plane + good = 0 when degenerate.
 void launch_models(const int4* sample_pts, int n_models_total, float4* hyps, int32_t* good, cudaStream_t s);
 
@@ -57,6 +63,11 @@ void launch_score(CloudView cloud, size_t n_per_cloud, int n_clouds, size_t clou
 // out must be zeroed.  sample_pts supplies the pivot (sample_pts[3 * model_index]).
 void launch_refit(CloudView cloud, size_t n, const float4* hyps, const int4* sample_pts, int model_index, float t,
                   int dot_order, int scale_exp, RefitOut* out, int num_sms, cudaStream_t s);
+
+// K3 for a batch: cloud c refits hypothesis c * K + model_idx[c] (skipped when negative) with scale 2^s_c.
+void launch_refit_batch(CloudView clouds, size_t n_per, size_t cloud_stride, int n_clouds, const float4* hyps,
+                        const int4* sample_pts, int K, const int32_t* model_idx, float t, int dot_order,
+                        const double* scales, RefitOut* outs, cudaStream_t s);
 
 // K5: stable partition by the inlier predicate of `plane`: remaining points -> dst (NaN re-padded),
 // inlier positions -> inl_cur, their original indices -> inl_orig.  totals[0] = remaining, totals[1] = inliers.

@@ -155,6 +155,30 @@ class PlaneRansac:
         ex.infos = [infos[k] for k in range(min(P + 1, mp))]
         return ex
 
+    # ---- batch of equal-sized small clouds (BASELINE config 5) ----
+    def set_cloud_batch(self, clouds: np.ndarray) -> None:
+        """clouds: (n_clouds, n_per_cloud, 3|4) float32."""
+        a = np.asarray(clouds)
+        if a.ndim != 3 or a.shape[2] not in (3, 4):
+            raise ValueError("batch must have shape (n_clouds, n_per_cloud, 3|4)")
+        flat = as_cloud(a.reshape(-1, a.shape[2]))
+        _lib.check(self._L.plane_ransac_set_cloud_batch(self._h, flat.ctypes.data_as(C.c_void_p), a.shape[0], a.shape[1]))
+        self._batch = a.shape[0]
+
+    def set_cloud_batch_ptr(self, host_ptr: int, n_clouds: int, n_per_cloud: int) -> None:
+        _lib.check(self._L.plane_ransac_set_cloud_batch(self._h, C.c_void_p(host_ptr), n_clouds, n_per_cloud))
+        self._batch = n_clouds
+
+    def segment_batch(self, params: PrParams, want_infos: bool = True):
+        """One segment() per cloud: (coeffs (n_clouds,4), n_inliers (n_clouds,), infos)."""
+        nc = self._batch
+        coeffs = np.zeros((nc, 4), np.float32)
+        cnt = np.zeros(nc, np.int32)
+        infos = (PrSegmentInfo * nc)() if want_infos else None
+        _lib.check(self._L.plane_ransac_segment_batch(self._h, C.byref(params), coeffs.ctypes.data_as(C.c_void_p),
+                                                      cnt.ctypes.data_as(C.c_void_p), infos))
+        return coeffs, cnt, infos
+
     def remaining(self) -> np.ndarray:
         _, n_cur = self.cloud_size()
         out = np.empty((max(n_cur, 1), 4), np.float32)

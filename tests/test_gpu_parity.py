@@ -26,7 +26,13 @@ def _oparams(O, p, refit=None):
 
 
 def _same_bits(a, b):
-    return np.asarray(a, np.float32).tobytes() == np.asarray(b, np.float32).tobytes()
+    """Bit-identical floats; NaNs match any NaN (payload/sign of a NaN is not part of the contract:
+    x86 produces 0xFFC00000 for 0/0, the GPU 0x7FFFFFFF)."""
+    a, b = np.asarray(a, np.float32), np.asarray(b, np.float32)
+    if a.shape != b.shape:
+        return False
+    na, nb = np.isnan(a), np.isnan(b)
+    return bool((na == nb).all()) and a[~na].tobytes() == b[~nb].tobytes()
 
 
 # ---------------------------------------------------------------------------------------------
@@ -279,3 +285,32 @@ def test_cpp_shim_demo_matches_oracle(O, lib_built, double_shadow, tmp_path):
         f = line.split()
         assert int(f[3]) == want.inliers_cur[k].size
         assert [float.fromhex(v) for v in f[5:9]] == [float(v) for v in want.coeffs[k]]
+
+
+# ---------------------------------------------------------------------------------------------
+# batch of small clouds (BASELINE config 5): one segment() per cloud, no peel
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n_clouds,n_per,max_it,prob,opt,order", [(37, 5000, 255, 1.0, True, 1), (16, 32768, 255, 1.0, True, 1),
+                                                                  (9, 1024, 50, 0.99, True, 0), (5, 3000, 99, 1.0, False, 1)])
+def test_segment_batch_matches_per_cloud_oracle(O, pr, n_clouds, n_per, max_it, prob, opt, order):
+    import dialog_b200 as D
+    from dialog_b200 import synth
+    clouds = np.stack([synth.tile_scene(cid).points(0, n_per) for cid in range(n_clouds)])
+    if n_per == 1024:
+        clouds[3] = 1.0                                   # all points identical: NaN model, 0 inliers
+        i = np.arange(1, n_per + 1, dtype=np.float32)
+        clouds[4, :, :3] = np.c_[i, 2 * i, 4 * i]         # all samples collinear: no model
+    prm = D.make_params(0.1, max_it, 500, prob, opt, 12345, 1, order)
+    pr.set_cloud_batch(clouds)
+    coeffs, cnt, infos = pr.segment_batch(prm)
+    for cid in range(n_clouds):
+        seg = O.segment(clouds[cid], _oparams(O, prm))
+        assert bool(infos[cid].ok) == seg.ok, cid
+        assert infos[cid].iterations == seg.trace.iterations and infos[cid].draws == seg.trace.draws
+        if not seg.ok:
+            assert cnt[cid] == 0 and (coeffs[cid] == 0).all()
+            continue
+        assert list(infos[cid].best_sample) == list(seg.trace.best_sample)
+        assert infos[cid].best_count == seg.trace.best_count
+        assert _same_bits(coeffs[cid], seg.coeff), (cid, coeffs[cid], seg.coeff)
+        assert cnt[cid] == seg.inliers.size
