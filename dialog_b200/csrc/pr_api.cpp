@@ -456,8 +456,8 @@ int segment_core(plane_ransac_ctx* c, const pr_params* prm, pr::CloudView src, s
         }
         PR_CUDA(cudaMemsetAsync(dc, 0, sb * sizeof(int32_t), c->stream));
         {
-          Span sp(c, KC_SCORE, 1);
-          pr::launch_score(src, n_local, 1, 0, dh, (int)sb, t, prm->dot_order, dc, c->num_sms, c->stream);
+          Span sp(c, KC_SCORE, 0);
+          c->prof.launches_score += pr::launch_score(src, n_local, 1, 0, dh, (int)sb, t, prm->dot_order, dc, c->num_sms, c->stream);
           c->prof.pairs_scored += (long long)n_local * sb;
         }
         done += sb;
@@ -684,8 +684,8 @@ int plane_ransac_score(plane_ransac_ctx* c, const int32_t* triples, int K, doubl
   }
   PR_CUDA(cudaMemsetAsync(c->d_counts.p, 0, (size_t)K * sizeof(int32_t), c->stream));
   {
-    Span sp(c, KC_SCORE, 1);
-    pr::launch_score(c->staged, c->n_staged, 1, 0, c->d_hyps.p, K, pr::threshold_up(t), dot_order, c->d_counts.p, c->num_sms, c->stream);
+    Span sp(c, KC_SCORE, 0);
+    c->prof.launches_score += pr::launch_score(c->staged, c->n_staged, 1, 0, c->d_hyps.p, K, pr::threshold_up(t), dot_order, c->d_counts.p, c->num_sms, c->stream);
     c->prof.pairs_scored += (long long)c->n_staged * K;
   }
   if (c->comm) PR_NCCL(g_nccl.AllReduce(c->d_counts.p, c->d_counts.p, (size_t)K, ncclInt32, ncclSum, c->comm, c->stream));
@@ -877,8 +877,8 @@ int plane_ransac_segment_batch(plane_ransac_ctx* c, const pr_params* prm, float*
       }
       PR_CUDA(cudaMemsetAsync(c->d_counts.p, 0, CB * sizeof(int32_t), c->stream));
       {
-        Span sp(c, KC_SCORE, 1);
-        pr::launch_score(c->batch_view, n, (int)C, stride, c->d_hyps.p, (int)B, t, prm->dot_order, c->d_counts.p, c->num_sms, c->stream);
+        Span sp(c, KC_SCORE, 0);
+        c->prof.launches_score += pr::launch_score(c->batch_view, n, (int)C, stride, c->d_hyps.p, (int)B, t, prm->dot_order, c->d_counts.p, c->num_sms, c->stream);
         c->prof.pairs_scored += (long long)n * (long long)CB;
       }
       PR_CUDA(cudaGetLastError());
@@ -960,8 +960,8 @@ int plane_ransac_segment_batch(plane_ransac_ctx* c, const pr_params* prm, float*
     PR_CUDA(cudaMemcpyAsync(c->d_batch_hyps.p, refined.data(), C * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
     PR_CUDA(cudaMemsetAsync(c->d_batch_cnt.p, 0, C * sizeof(int32_t), c->stream));
     {
-      Span sp(c, KC_SCORE, 1);
-      pr::launch_score(c->batch_view, n, (int)C, stride, c->d_batch_hyps.p, 1, t, prm->dot_order, c->d_batch_cnt.p, c->num_sms, c->stream);
+      Span sp(c, KC_SCORE, 0);
+      c->prof.launches_score += pr::launch_score(c->batch_view, n, (int)C, stride, c->d_batch_hyps.p, 1, t, prm->dot_order, c->d_batch_cnt.p, c->num_sms, c->stream);
       c->prof.pairs_scored += (long long)(n * C);
     }
     PR_CUDA(cudaGetLastError());
@@ -1036,6 +1036,24 @@ int plane_ransac_shard_info(plane_ransac_ctx* c, long long* n_global_staged, lon
   if (first_staged) *first_staged = c->first_staged;
   if (n_global_current) *n_global_current = c->n_global_current;
   if (first_current) *first_current = c->first_current;
+  return PR_OK;
+}
+
+int plane_ransac_host_alloc(size_t bytes, void** out) {
+  if (!out) return fail(PR_ERR_INVALID, "null output");
+  *out = nullptr;
+  if (cudaMallocHost(out, bytes ? bytes : 1) != cudaSuccess) {
+    cudaGetLastError();
+    return fail(PR_ERR_OOM, "cudaMallocHost of %zu bytes failed", bytes);
+  }
+  return PR_OK;
+}
+
+int plane_ransac_host_free(void* p) {
+  if (p && cudaFreeHost(p) != cudaSuccess) {
+    cudaGetLastError();
+    return fail(PR_ERR_CUDA, "cudaFreeHost failed");
+  }
   return PR_OK;
 }
 

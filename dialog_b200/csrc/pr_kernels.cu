@@ -299,6 +299,8 @@ void launch_models(const int4* sample_pts, int n_models_total, float4* hyps, int
 constexpr int kScoreWarps = 8;
 constexpr int kScoreThreads = kScoreWarps * 32;
 constexpr int kScoreStages = 3;
+constexpr int kScoreStepsPerFlush = 32;             // 128 points: <= 128 increments per counter between folds
+constexpr int kScoreStageFloats = 3 * kTilePoints + 4;  // + 16 bytes so the last prefetch stays inside the stage
 
 // One (cloud, tile) work item -> three bulk copies into stage `s`, completion on s_full[s].
 __device__ __forceinline__ void score_issue_tile(const float* X, const float* Y, const float* Z, size_t cloud_stride,
@@ -315,8 +317,10 @@ template <int H, int DOT>
 __global__ void __launch_bounds__(kScoreThreads, H <= 4 ? 4 : 2)
     score_kernel(const float* __restrict__ X, const float* __restrict__ Y, const float* __restrict__ Z,
                  size_t cloud_stride, int tiles_per_cloud, int total_items, int items_per_cta,
-                 const float4* __restrict__ hyps, int K, float t, int32_t* __restrict__ counts, int warps_h) {
-  __shared__ __align__(128) float s_pts[kScoreStages][3 * kTilePoints];
+                 const float4* __restrict__ hyps, int K, int k_begin, int k_end, float t,
+                 int32_t* __restrict__ counts, int warps_h) {
+  // hypotheses [k_begin, k_end) of the K per cloud are scored by this launch
+  __shared__ __align__(128) float s_pts[kScoreStages][kScoreStageFloats];
   __shared__ __align__(8) uint64_t s_full[kScoreStages];
   __shared__ int s_done[kScoreStages];
 
@@ -341,9 +345,8 @@ __global__ void __launch_bounds__(kScoreThreads, H <= 4 ? 4 : 2)
   const int wh = warp % warps_h, wp = warp / warps_h;
   const int pts_per_warp = kTilePoints / (kScoreWarps / warps_h);
   const int p_begin = wp * pts_per_warp;
-  const int steps_per_flush = min(64, pts_per_warp / 4);
   const int k_stride = 32 * warps_h;
-  const int k0 = blockIdx.y * (k_stride * H) + wh * 32 + lane;
+  const int k0 = k_begin + blockIdx.y * (k_stride * H) + wh * 32 + lane;
 
   float ha[H], hb[H], hc[H], hd[H];
   int cnt[H];
@@ -359,14 +362,14 @@ __global__ void __launch_bounds__(kScoreThreads, H <= 4 ? 4 : 2)
 #pragma unroll
         for (int j = 0; j < H; ++j) {
           const int k = k0 + j * k_stride;
-          if (k < K && cnt[j] != 0) atomicAdd(&counts[(size_t)cur_cloud * K + k], cnt[j]);
+          if (k < k_end && cnt[j] != 0) atomicAdd(&counts[(size_t)cur_cloud * K + k], cnt[j]);
         }
       }
 #pragma unroll
       for (int j = 0; j < H; ++j) {
         const int k = k0 + j * k_stride;
         float4 h = make_float4(CUDART_NAN_F, CUDART_NAN_F, CUDART_NAN_F, CUDART_NAN_F);
-        if (k < K) h = __ldg(&hyps[(size_t)c * K + k]);
+        if (k < k_end) h = __ldg(&hyps[(size_t)c * K + k]);
         ha[j] = h.x; hb[j] = h.y; hc[j] = h.z; hd[j] = h.w;
         cnt[j] = 0;
         acc[j] = 0u;
@@ -379,21 +382,21 @@ __global__ void __launch_bounds__(kScoreThreads, H <= 4 ? 4 : 2)
     const float* sy = sx + kTilePoints;
     const float* sz = sx + 2 * kTilePoints;
 
-    for (int p = 0; p < pts_per_warp; p += 4 * steps_per_flush) {
-      // software pipeline: the points of step q + 1 are loaded while step q computes
+    // 128-point chunks (32 steps of 4 points): compile-time trip count, counters folded after each chunk
+    for (int p = 0; p < pts_per_warp; p += 4 * kScoreStepsPerFlush) {
+      // software pipeline: the points of step q + 1 are loaded while step q computes (the load issued by
+      // the last step of a tile reads 16 bytes past its plane: the next plane, or the stage's tail pad)
       float4 x4 = *reinterpret_cast<const float4*>(sx + p);
       float4 y4 = *reinterpret_cast<const float4*>(sy + p);
       float4 z4 = *reinterpret_cast<const float4*>(sz + p);
 #pragma unroll 2
-      for (int q = 0; q < steps_per_flush; ++q) {
+      for (int q = 0; q < kScoreStepsPerFlush; ++q) {
         const float2 xa = make_float2(x4.x, x4.y), xb = make_float2(x4.z, x4.w);
         const float2 ya = make_float2(y4.x, y4.y), yb = make_float2(y4.z, y4.w);
         const float2 za = make_float2(z4.x, z4.y), zb = make_float2(z4.z, z4.w);
-        // past the end of the warp's range the prefetch wraps to its first step; the values are unused
-        const int pn = p + 4 * q + 4;
-        x4 = *reinterpret_cast<const float4*>(sx + (pn < pts_per_warp ? pn : 0));
-        y4 = *reinterpret_cast<const float4*>(sy + (pn < pts_per_warp ? pn : 0));
-        z4 = *reinterpret_cast<const float4*>(sz + (pn < pts_per_warp ? pn : 0));
+        x4 = *reinterpret_cast<const float4*>(sx + p + 4 * q + 4);
+        y4 = *reinterpret_cast<const float4*>(sy + p + 4 * q + 4);
+        z4 = *reinterpret_cast<const float4*>(sz + p + 4 * q + 4);
 #pragma unroll
         for (int j = 0; j < H; ++j) {
           const float2 ra = plane_dot2<DOT>(ha[j], hb[j], hc[j], hd[j], xa, ya, za);
@@ -435,7 +438,7 @@ __global__ void __launch_bounds__(kScoreThreads, H <= 4 ? 4 : 2)
 #pragma unroll
   for (int j = 0; j < H; ++j) {
     const int k = k0 + j * k_stride;
-    if (k < K && cnt[j] != 0) atomicAdd(&counts[(size_t)cur_cloud * K + k], cnt[j]);
+    if (k < k_end && cnt[j] != 0) atomicAdd(&counts[(size_t)cur_cloud * K + k], cnt[j]);
   }
 }
 
@@ -445,16 +448,14 @@ static int next_pow2(int v) {
   return p;
 }
 
+// One launch scoring hypotheses [k_begin, k_end) with H per lane and warps_h warps across hypotheses.
 template <int H>
 static void launch_score_h(const float* X, const float* Y, const float* Z, size_t cloud_stride, int tiles_per_cloud,
-                           int n_clouds, const float4* hyps, int K, float t, int dot_order, int32_t* counts, int num_sms,
-                           cudaStream_t s) {
-  int warps_h = next_pow2((K + 32 * H - 1) / (32 * H));
-  if (warps_h > kScoreWarps) warps_h = kScoreWarps;
+                           int n_clouds, const float4* hyps, int K, int k_begin, int k_end, int warps_h, float t,
+                           int dot_order, int32_t* counts, int num_sms, cudaStream_t s) {
   const int chunk = 32 * H * warps_h;
-  const int n_chunks = (K + chunk - 1) / chunk;
-  const long long total_items_ll = (long long)tiles_per_cloud * n_clouds;
-  const int total_items = (int)total_items_ll;
+  const int n_chunks = (k_end - k_begin + chunk - 1) / chunk;
+  const int total_items = tiles_per_cloud * n_clouds;
   int gx = ((H <= 4 ? 4 : 2) * num_sms) / n_chunks;
   if (gx < 1) gx = 1;
   if (gx > total_items) gx = total_items;
@@ -463,26 +464,48 @@ static void launch_score_h(const float* X, const float* Y, const float* Z, size_
   dim3 grid(gx, n_chunks);
   if (dot_order == 1)
     score_kernel<H, 1><<<grid, kScoreThreads, 0, s>>>(X, Y, Z, cloud_stride, tiles_per_cloud, total_items, items_per_cta,
-                                                      hyps, K, t, counts, warps_h);
+                                                      hyps, K, k_begin, k_end, t, counts, warps_h);
   else
     score_kernel<H, 0><<<grid, kScoreThreads, 0, s>>>(X, Y, Z, cloud_stride, tiles_per_cloud, total_items, items_per_cta,
-                                                      hyps, K, t, counts, warps_h);
+                                                      hyps, K, k_begin, k_end, t, counts, warps_h);
 }
 
-void launch_score(CloudView cloud, size_t n_per_cloud, int n_clouds, size_t cloud_stride, const float4* hyps, int K,
-                  float t, int dot_order, int32_t* counts, int num_sms, cudaStream_t s) {
-  if (K <= 0 || n_per_cloud == 0 || n_clouds <= 0) return;
+int launch_score(CloudView cloud, size_t n_per_cloud, int n_clouds, size_t cloud_stride, const float4* hyps, int K,
+                 float t, int dot_order, int32_t* counts, int num_sms, cudaStream_t s) {
+  if (K <= 0 || n_per_cloud == 0 || n_clouds <= 0) return 0;
   const int tiles_per_cloud = (int)((n_per_cloud + kTilePoints - 1) / kTilePoints);
-  int H = next_pow2((K + 31) / 32);
-  if (H > 8) H = 8;
   static const int forced_h = [] { const char* e = getenv("PR_SCORE_H"); return e ? atoi(e) : 0; }();  // tuning knob
-  if (forced_h == 4 && H > 4) H = 4;
-  switch (H) {
-    case 1: launch_score_h<1>(cloud.x, cloud.y, cloud.z, cloud_stride, tiles_per_cloud, n_clouds, hyps, K, t, dot_order, counts, num_sms, s); break;
-    case 2: launch_score_h<2>(cloud.x, cloud.y, cloud.z, cloud_stride, tiles_per_cloud, n_clouds, hyps, K, t, dot_order, counts, num_sms, s); break;
-    case 4: launch_score_h<4>(cloud.x, cloud.y, cloud.z, cloud_stride, tiles_per_cloud, n_clouds, hyps, K, t, dot_order, counts, num_sms, s); break;
-    default: launch_score_h<8>(cloud.x, cloud.y, cloud.z, cloud_stride, tiles_per_cloud, n_clouds, hyps, K, t, dot_order, counts, num_sms, s); break;
+  // Every lane slot of a launch costs the same whether or not it holds a hypothesis, so K is cut into
+  // launches whose slot count (32 * H * warps_h per chunk) matches: full 2048-wide chunks first, then
+  // powers of two, rounding the last pieces up when little is wasted.
+  int launches = 0;
+  int k = 0;
+  while (k < K) {
+    const int rest = K - k;
+    int H, warps_h, take;
+    if (rest >= 32 * 8 * kScoreWarps) {
+      H = 8; warps_h = kScoreWarps; take = rest / (32 * 8 * kScoreWarps) * (32 * 8 * kScoreWarps);
+    } else {
+      int slots = 32;  // largest power of two <= rest, at least one warp of single hypotheses
+      while (slots * 2 <= rest) slots *= 2;
+      // round up to the next power of two when that wastes at most a quarter of the launch (or < 64 slots)
+      if (rest > slots && 2 * slots - rest <= (slots / 2 > 64 ? slots / 2 : 64)) slots *= 2;
+      H = slots / 32 > 8 ? 8 : slots / 32;
+      warps_h = slots / (32 * H);
+      take = rest < slots ? rest : slots;
+    }
+    if (forced_h == 4 && H > 4) { warps_h = warps_h * H / 4 > kScoreWarps ? kScoreWarps : warps_h * H / 4; H = 4; }
+    const float* X = cloud.x; const float* Y = cloud.y; const float* Z = cloud.z;
+    switch (H) {
+      case 1: launch_score_h<1>(X, Y, Z, cloud_stride, tiles_per_cloud, n_clouds, hyps, K, k, k + take, warps_h, t, dot_order, counts, num_sms, s); break;
+      case 2: launch_score_h<2>(X, Y, Z, cloud_stride, tiles_per_cloud, n_clouds, hyps, K, k, k + take, warps_h, t, dot_order, counts, num_sms, s); break;
+      case 4: launch_score_h<4>(X, Y, Z, cloud_stride, tiles_per_cloud, n_clouds, hyps, K, k, k + take, warps_h, t, dot_order, counts, num_sms, s); break;
+      default: launch_score_h<8>(X, Y, Z, cloud_stride, tiles_per_cloud, n_clouds, hyps, K, k, k + take, warps_h, t, dot_order, counts, num_sms, s); break;
+    }
+    k += take;
+    ++launches;
   }
+  return launches;
 }
 
 // ------------------------------------------------------------------------------------------------

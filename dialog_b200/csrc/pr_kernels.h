@@ -56,8 +56,9 @@ void launch_gather_samples(CloudView cloud, long long first, size_t n, const int
 void launch_models(const int4* sample_pts, int n_models_total, float4* hyps, int32_t* good, cudaStream_t s);
 
 // K2: counts[c * K + k] += |{ i in cloud c : |hyp[c*K+k] . (p_i, 1)| < t }|.  counts must be zeroed.
-void launch_score(CloudView cloud, size_t n_per_cloud, int n_clouds, size_t cloud_stride, const float4* hyps,
-                  int K, float t, int dot_order, int32_t* counts, int num_sms, cudaStream_t s);
+// Returns the number of kernel launches it made (K is cut into launches that fill their lane slots).
+int launch_score(CloudView cloud, size_t n_per_cloud, int n_clouds, size_t cloud_stride, const float4* hyps,
+                 int K, float t, int dot_order, int32_t* counts, int num_sms, cudaStream_t s);
 
 // K3: inlier predicate with hyps[model_index] + exact integer moments about the model's first sample point.
 // out must be zeroed.  sample_pts supplies the pivot (sample_pts[3 * model_index]).

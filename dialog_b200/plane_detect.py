@@ -42,6 +42,36 @@ def as_cloud(points: np.ndarray) -> np.ndarray:
     return np.ascontiguousarray(a, dtype=np.float32)
 
 
+class PinnedArray:
+    """numpy view of page-locked host memory owned by the library (plane_ransac_host_alloc)."""
+
+    def __init__(self, shape, dtype):
+        self._L = _lib.load()
+        dt = np.dtype(dtype)
+        nbytes = int(np.prod(shape)) * dt.itemsize
+        p = C.c_void_p()
+        _lib.check(self._L.plane_ransac_host_alloc(max(nbytes, 1), C.byref(p)))
+        self._p = p
+        buf = (C.c_char * max(nbytes, 1)).from_address(p.value)
+        self.array = np.frombuffer(buf, dtype=dt, count=int(np.prod(shape))).reshape(shape)
+
+    @property
+    def ptr(self) -> int:
+        return self._p.value
+
+    def free(self):
+        if self._p is not None:
+            self.array = None
+            self._L.plane_ransac_host_free(self._p)
+            self._p = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
 @dataclass
 class Plane:
     """== struct Plane (Dialog/HeaderFile.h:81-88) restricted to what this path fills."""
@@ -69,9 +99,14 @@ class PlaneRansac:
         h = C.c_void_p()
         _lib.check(self._L.plane_ransac_create(C.byref(h), device))
         self._h = h
-        self._keep = None
+        self._idx_buf = None
+        self._batch = 0
 
     def close(self):
+        if getattr(self, "_idx_buf", None):
+            for b in self._idx_buf:
+                b.free()
+            self._idx_buf = None
         if getattr(self, "_h", None):
             self._L.plane_ransac_destroy(self._h)
             self._h = None
@@ -131,15 +166,20 @@ class PlaneRansac:
                                                     inl.ctypes.data_as(C.c_void_p), inl.size, C.byref(n), C.byref(info)))
         return coeff, inl[: n.value].copy(), info
 
-    def extract_planes(self, params: PrParams, want_indices: bool = True) -> Extraction:
+    def extract_planes(self, params: PrParams, want_indices: bool = True, copy: bool = True) -> Extraction:
+        """copy=False returns views into the context's pinned result buffers (valid until the next call)."""
         n_staged, _ = self.cloud_size()
         mp = params.max_planes
         coeffs = np.zeros((max(mp, 1), 4), np.float32)
         offs = np.zeros(mp + 1, np.uintp)
         npl = C.c_int(0)
         infos = (PrSegmentInfo * (mp + 1))()
-        cur = np.empty(max(n_staged, 1), np.int32) if want_indices else None
-        orig = np.empty(max(n_staged, 1), np.int32) if want_indices else None
+        cur = orig = None
+        if want_indices:
+            # page-locked result buffers, kept across calls (they are overwritten by the next call)
+            if self._idx_buf is None or self._idx_buf[0].array.size < max(n_staged, 1):
+                self._idx_buf = (PinnedArray((max(n_staged, 1),), np.int32), PinnedArray((max(n_staged, 1),), np.int32))
+            cur, orig = self._idx_buf[0].array, self._idx_buf[1].array
         _lib.check(self._L.plane_ransac_extract_planes(
             self._h, C.byref(params), coeffs.ctypes.data_as(C.c_void_p),
             cur.ctypes.data_as(C.c_void_p) if want_indices else None,
@@ -150,8 +190,9 @@ class PlaneRansac:
         ex = Extraction()
         for k in range(P):
             ex.planes.append(Plane(coeffs[k].copy(),
-                                   cur[o[k]: o[k + 1]].copy() if want_indices else None,
-                                   orig[o[k]: o[k + 1]].copy() if want_indices else None, infos[k]))
+                                   (cur[o[k]: o[k + 1]].copy() if copy else cur[o[k]: o[k + 1]]) if want_indices else None,
+                                   (orig[o[k]: o[k + 1]].copy() if copy else orig[o[k]: o[k + 1]]) if want_indices else None,
+                                   infos[k]))
         ex.infos = [infos[k] for k in range(min(P + 1, mp))]
         return ex
 

@@ -161,6 +161,13 @@ int plane_ransac_comm_init(plane_ransac_ctx* ctx, int n_ranks, int rank, const v
 int plane_ransac_shard_info(plane_ransac_ctx* ctx, long long* n_global_staged, long long* first_staged,
                             long long* n_global_current, long long* first_current);
 
+/* ---- pinned host buffers ---------------------------------------------------------------------
+ * Page-locked host memory for clouds and index lists (cudaMallocHost / cudaFreeHost): copies from and to
+ * such buffers run at full PCIe rate.  Any host pointer is accepted by the calls above; these are a
+ * convenience for callers without a CUDA runtime of their own. */
+int plane_ransac_host_alloc(size_t bytes, void** out);
+int plane_ransac_host_free(void* p);
+
 /* ---- measurement ------------------------------------------------------------------------- */
 int plane_ransac_profile_enable(plane_ransac_ctx* ctx, int on);
 int plane_ransac_profile_reset(plane_ransac_ctx* ctx);
