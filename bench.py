@@ -52,6 +52,10 @@ def parse_args():
     ap.add_argument("--planes", type=int, default=20)
     ap.add_argument("--cpu-sample-hyps", type=int, default=512)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--extras", action="store_true",
+                    help="also time BASELINE configs[1] (1M points, 3 planes, K=1024) and a slice of configs[4] "
+                         "(batch of 32K-point clouds, K=256) on rank 0's GPU; reported under 'extras'")
+    ap.add_argument("--batch-clouds", type=int, default=512)
     return ap.parse_args()
 
 
@@ -122,14 +126,14 @@ def cpu_sample(args, pts, threads):
     return pts.shape[0] * S / dt, dt
 
 
-def run_reference(args):
+def run_reference(args, out):
     """Reference arm: the CPU restatement of the PCL path, all host threads, bounded sample per step."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     from dialog_b200 import synth
     cores = os.cpu_count() or 1
-    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    os.environ["OMP_NUM_THREADS"] = str(cores)  # torchrun exports OMP_NUM_THREADS=1; this arm uses every host thread
     pts = synth.indoor_scene().points(0, args.points)
     from oracle import oracle as O
     S = max(8, min(args.cpu_sample_hyps, 64))
@@ -153,13 +157,64 @@ def run_reference(args):
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
             "note": "PCL 1.8 is not installable here; this is the CPU oracle (oracle/pr_oracle.c) restating its loop"}
-    print(json.dumps(line), flush=True)
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
+def run_extras(args, pr):
+    """The other single-GPU BASELINE configs, resident timing, rank 0 only."""
+    import dialog_b200 as D
+    from dialog_b200 import synth
+    out = {}
+    # configs[1]: 1M points, 3 planes + 1 % noise + 30 % outliers, 1024 hypotheses
+    pts = synth.three_planes_scene().points(0, 1_000_000)
+    pr.set_cloud(pts)
+    prm = D.make_params(0.1, 1023, 500, 1.0, True, 12345, 3, D.DOT_FMA)
+    for _ in range(3):
+        ex = pr.extract_planes(prm, want_indices=False)
+    ms = []
+    for _ in range(5):
+        pr.flush_l2()
+        pr.timer_start()
+        ex = pr.extract_planes(prm, want_indices=False)
+        ms.append(pr.timer_stop())
+    pairs = sum(int(i.n_cloud) * int(i.n_scored) for i in ex.infos)
+    out["configs[1]_1M_3planes_K1024"] = {"ms_per_extraction": sum(ms) / len(ms), "planes": len(ex.planes),
+                                          "point_hypotheses_per_s": pairs / (sum(ms) / len(ms) * 1e-3)}
+    # configs[4]: batch of 32K-point clouds, one plane each, 256 hypotheses per cloud (slice of the 4096 clouds)
+    nc = args.batch_clouds
+    clouds = np.stack([synth.tile_scene(cid).points(0, 32768) for cid in range(nc)])
+    pr.set_cloud_batch(clouds)
+    prm = D.make_params(0.1, 255, 500, 1.0, True, 12345, 1, D.DOT_FMA)
+    for _ in range(2):
+        pr.segment_batch(prm, want_infos=False)
+    ms = []
+    for _ in range(5):
+        pr.flush_l2()
+        pr.timer_start()
+        coeffs, cnt, _ = pr.segment_batch(prm, want_infos=False)
+        ms.append(pr.timer_stop())
+    pairs = nc * 32768 * 257
+    out["configs[4]_batch_32K_clouds_K256"] = {"clouds": nc, "ms_per_batch": sum(ms) / len(ms),
+                                               "clouds_per_s": nc / (sum(ms) / len(ms) * 1e-3),
+                                               "point_hypotheses_per_s": pairs / (sum(ms) / len(ms) * 1e-3),
+                                               "mean_inliers": float(cnt.mean())}
+    return out
+
+
+def claim_stdout():
+    """Keep fd 1 for the JSON line only: libraries (NCCL prints its version banner) write to stderr instead."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    return real
 
 
 def main():
     args = parse_args()
+    out = claim_stdout()
     if args.impl == "reference":
-        run_reference(args)
+        run_reference(args, out)
         return
 
     import torch
@@ -295,13 +350,16 @@ def main():
                                    "refit": prof.ms_refit / args.steps, "compact": prof.ms_compact / args.steps},
             "clocks": clock_info,
         }
+        if args.extras:
+            line["extras"] = run_extras(args, pr)
         if not args.no_cpu_baseline:
             v, dt = cpu_sample(args, pts, threads=1)
             line["cpu_baseline"] = {
                 "value": v, "unit": UNIT, "cores": 1, "kind": "port", "seconds": dt,
                 "sample": "oracle countWithinDistance (PCL 1.8 scalar loop, 1 thread) over the first %d hypotheses of "
                           "round 0 on rank 0's %d points" % (args.cpu_sample_hyps, count)}
-        print(json.dumps(line), flush=True)
+        out.write(json.dumps(line) + "\n")
+        out.flush()
 
     pr.close()
     if world > 1:
