@@ -14,11 +14,14 @@ LIB_PATH = os.path.join(HERE, "libplane_ransac.so")
 UNIQUE_ID_BYTES = 128
 DOT_PCL_SSE2 = 0
 DOT_FMA = 1
+STAGE_REMOVE_NONFINITE = 1
+STAGE_TRANSLATE_CENTROID = 2
 
 # every symbol include/plane_ransac.h declares (checked by tests/test_abi.py)
 SYMBOLS = [
     "plane_ransac_abi_version", "plane_ransac_last_error", "plane_ransac_default_params",
     "plane_ransac_create", "plane_ransac_destroy", "plane_ransac_set_cloud", "plane_ransac_set_cloud_device",
+    "plane_ransac_set_cloud_ex", "plane_ransac_staged_source_indices",
     "plane_ransac_cloud_size", "plane_ransac_score", "plane_ransac_segment_one", "plane_ransac_extract_planes",
     "plane_ransac_remaining", "plane_ransac_set_cloud_batch", "plane_ransac_segment_batch",
     "plane_ransac_comm_unique_id", "plane_ransac_comm_init", "plane_ransac_shard_info",
@@ -96,6 +99,8 @@ def load():
     L.plane_ransac_destroy.restype = None
     L.plane_ransac_set_cloud.argtypes = [vp, vp, sz]
     L.plane_ransac_set_cloud_device.argtypes = [vp, vp, sz]
+    L.plane_ransac_set_cloud_ex.argtypes = [vp, vp, sz, C.c_uint, C.POINTER(sz), vp]
+    L.plane_ransac_staged_source_indices.argtypes = [vp, vp, sz]
     L.plane_ransac_cloud_size.argtypes = [vp, C.POINTER(sz), C.POINTER(sz)]
     L.plane_ransac_score.argtypes = [vp, vp, C.c_int, C.c_double, C.c_int, vp, vp, vp]
     L.plane_ransac_segment_one.argtypes = [vp, C.POINTER(PrParams), vp, vp, sz, C.POINTER(sz), C.POINTER(PrSegmentInfo)]

@@ -130,7 +130,10 @@ struct plane_ransac_ctx {
   pr::CloudView current;
   size_t n_current = 0;
   int scale_exp = 0;
-  uint32_t bbox_keys[6] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0, 0, 0};
+  uint32_t bbox_keys[6] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0, 0, 0};         // this rank's points
+  uint32_t bbox_keys_global[6] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0, 0, 0};  // all ranks
+  DevBuf<int32_t> d_stage_map;  // staged point -> index in the caller's array (only after a filtered staging)
+  bool have_stage_map = false;
 
   DevBuf<float4> aos;        // AoS staging (upload / download)
   DevBuf<uint32_t> d_bbox;   // 6 keys
@@ -332,6 +335,7 @@ int refresh_global(plane_ransac_ctx* c) {
   if (!c->comm) {
     c->n_global_staged = (long long)c->n_staged;
     c->first_staged = 0;
+    std::memcpy(c->bbox_keys_global, c->bbox_keys, sizeof(c->bbox_keys));
     c->scale_exp = pr::scale_exp_from_bbox_keys(c->bbox_keys);
     c->global_valid = true;
     return PR_OK;
@@ -357,32 +361,104 @@ int refresh_global(plane_ransac_ctx* c) {
   }
   c->n_global_staged = total;
   c->first_staged = first;
+  std::memcpy(c->bbox_keys_global, keys, sizeof(keys));
   c->scale_exp = pr::scale_exp_from_bbox_keys(keys);
   c->global_valid = true;
   return PR_OK;
 }
 
-int stage_from_device(plane_ransac_ctx* c, const float4* d_aos, size_t n) {
+int stage_from_device(plane_ransac_ctx* c, const float4* d_aos, size_t n, unsigned flags = 0, size_t* n_kept = nullptr,
+                      float* centroid_out = nullptr) {
   const size_t cap = pr::padded_capacity(n);
   PR_TRY(dev_reserve(c->staged_mem, 3 * cap));
   PR_TRY(reserve_small(c));
   c->staged = planes_view(c->staged_mem.p, nullptr, cap);
-  {
-    Span sp(c, KC_STAGE, 2);
-    pr::launch_bbox_init(c->d_bbox.p, c->stream);
-    pr::launch_stage(d_aos, n, c->staged, c->d_bbox.p, c->stream);
+  c->have_stage_map = false;
+  size_t n_out = n;
+  if (flags & PR_STAGE_REMOVE_NONFINITE) {
+    // stage into a scratch cloud, then compact the finite points into the staged planes (order preserved)
+    PR_TRY(dev_reserve(c->work_mem[0], 3 * cap));
+    PR_TRY(dev_reserve(c->d_stage_map, cap));
+    PR_TRY(dev_reserve(c->d_scratch, pr::compact_scratch_bytes(n) + 64));
+    pr::CloudView tmp = planes_view(c->work_mem[0].p, nullptr, cap);
+    pr::CloudView dst = c->staged;
+    dst.orig = c->d_stage_map.p;
+    {
+      Span sp(c, KC_STAGE, 2 + (n ? 1 : 0));
+      pr::launch_bbox_init(c->d_bbox.p, c->stream);
+      pr::launch_stage(d_aos, n, tmp, c->d_bbox.p, c->stream);
+      pr::Plane4 none = {0, 0, 0, 0};
+      pr::launch_compact(tmp, n, none, 0.f, 2, dst, true, nullptr, nullptr, c->d_scratch.p, c->d_totals.p, c->stream);
+    }
+    PR_CUDA(cudaGetLastError());
+    PR_CUDA(cudaMemcpyAsync(c->h_totals.p, c->d_totals.p, 2 * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
+    PR_CUDA(cudaMemcpyAsync(c->bbox_keys, c->d_bbox.p, 6 * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    PR_CUDA(cudaStreamSynchronize(c->stream));
+    n_out = (size_t)c->h_totals.p[0];
+    if (n == 0) {  // launch_compact skipped: pad the empty staged cloud
+      Span sp(c, KC_STAGE, 1);
+      pr::launch_stage(d_aos, 0, c->staged, c->d_bbox.p, c->stream);
+    }
+    c->have_stage_map = true;
+  } else {
+    {
+      Span sp(c, KC_STAGE, 2);
+      pr::launch_bbox_init(c->d_bbox.p, c->stream);
+      pr::launch_stage(d_aos, n, c->staged, c->d_bbox.p, c->stream);
+    }
+    PR_CUDA(cudaGetLastError());
+    PR_CUDA(cudaMemcpyAsync(c->bbox_keys, c->d_bbox.p, 6 * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    PR_CUDA(cudaStreamSynchronize(c->stream));
   }
-  PR_CUDA(cudaGetLastError());
-  PR_CUDA(cudaMemcpyAsync(c->bbox_keys, c->d_bbox.p, 6 * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
-  PR_CUDA(cudaStreamSynchronize(c->stream));
-  c->n_staged = n;
+  c->n_staged = n_out;
   c->have_cloud = true;
   c->current = c->staged;
-  c->n_current = n;
+  c->n_current = n_out;
   c->global_valid = false;
   PR_TRY(refresh_global(c));
+  float centroid[3] = {0.f, 0.f, 0.f};
+  if (flags & PR_STAGE_TRANSLATE_CENTROID) {
+    // exact centroid over all ranks' finite points, about the global bbox corner on the refit grid
+    float lo[3];
+    double lod[3];
+    bool any = true;
+    for (int a = 0; a < 3; ++a) {
+      if (c->bbox_keys_global[a] > c->bbox_keys_global[3 + a]) any = false;
+      lo[a] = any ? pr::key_to_float(c->bbox_keys_global[a]) : 0.f;
+      lod[a] = (double)lo[a];
+    }
+    if (any) {
+      PR_CUDA(cudaMemsetAsync(c->d_totals.p, 0, 4 * sizeof(long long), c->stream));
+      {
+        Span sp(c, KC_STAGE, n_out ? 1 : 0);
+        pr::launch_centroid(c->staged, n_out, lod, c->scale_exp, c->d_totals.p, c->num_sms, c->stream);
+      }
+      if (c->comm) PR_NCCL(g_nccl.AllReduce(c->d_totals.p, c->d_totals.p, 4, ncclInt64, ncclSum, c->comm, c->stream));
+      PR_CUDA(cudaMemcpyAsync(c->h_totals.p, c->d_totals.p, 4 * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
+      PR_CUDA(cudaStreamSynchronize(c->stream));
+      if (pr::centroid_from_sums(c->h_totals.p, lo, c->scale_exp, centroid)) {
+        {
+          Span sp(c, KC_STAGE, n_out ? 1 : 0);
+          pr::launch_translate(c->staged, n_out, centroid, c->num_sms, c->stream);
+        }
+        PR_CUDA(cudaGetLastError());
+        // x -> fl(x - c) is monotonic, so the translated box is the box of the translated corners
+        for (int a = 0; a < 3; ++a) {
+          uint32_t* sets[2] = {c->bbox_keys, c->bbox_keys_global};
+          for (uint32_t* k : sets) {
+            if (k[a] > k[3 + a]) continue;
+            k[a] = pr::float_to_key(pr::key_to_float(k[a]) - centroid[a]);
+            k[3 + a] = pr::float_to_key(pr::key_to_float(k[3 + a]) - centroid[a]);
+          }
+        }
+        c->scale_exp = pr::scale_exp_from_bbox_keys(c->bbox_keys_global);
+      }
+    }
+  }
   c->n_global_current = c->n_global_staged;
   c->first_current = c->first_staged;
+  if (n_kept) *n_kept = n_out;
+  if (centroid_out) std::memcpy(centroid_out, centroid, sizeof(centroid));
   return PR_OK;
 }
 
@@ -429,12 +505,16 @@ int segment_core(plane_ransac_ctx* c, const pr_params* prm, pr::CloudView src, s
       PR_TRY(reserve_draws(c, (size_t)total_draws + (size_t)B, total_draws > 0));
       // The batch is issued in sub-batches so that the host draws the next triples (a sequential
       // permutation walk, ~0.1 us per draw) while the device is already scoring the previous ones.
-      // Sub-batches double in size: drawing batch i+1 costs the host about as long as the device
-      // needs for batch i on a cloud of ~1.5M points, and less on larger ones.
+      // Two sub-batches: the first is just large enough that scoring it (~N / 6.5e12 s per hypothesis)
+      // takes the device as long as drawing the rest takes the host (~0.12 us per draw); fewer, larger
+      // launches score more efficiently and, when sharded, need fewer collectives.
+      const double dev_s_per_hyp = (double)std::max<size_t>(n_local, 1) / 6.5e12, host_s_per_draw = 1.2e-7;
+      long long first_sb = 256;
+      while (first_sb < B && (double)first_sb < (double)B * host_s_per_draw / (dev_s_per_hyp + host_s_per_draw)) first_sb *= 2;
       long long prev_sb = 0;
       for (long long done = 0; done < B;) {
-        long long sb = prev_sb == 0 ? std::min<long long>(B, 256) : std::min<long long>(B - done, 2 * prev_sb);
-        if (B - done - sb <= sb) sb = B - done;  // fold a short tail into the last sub-batch
+        long long sb = prev_sb == 0 ? std::min<long long>(B, first_sb) : B - done;
+        if (B - done - sb <= 256) sb = B - done;  // fold a short tail into this sub-batch
         prev_sb = sb;
         const size_t at = (size_t)total_draws + (size_t)done;
         int32_t* ht = c->h_triples.p + 3 * at;
@@ -625,6 +705,7 @@ void plane_ransac_destroy(plane_ransac_ctx* c) {
   dev_free(c->aos); dev_free(c->d_bbox); dev_free(c->d_triples); dev_free(c->d_counts); dev_free(c->d_good);
   dev_free(c->d_sample_pts); dev_free(c->d_hyps); dev_free(c->d_refit); dev_free(c->d_totals);
   dev_free(c->d_scratch); dev_free(c->d_inl_cur); dev_free(c->d_inl_orig); dev_free(c->d_flush); dev_free(c->batch_mem);
+  dev_free(c->d_stage_map);
   dev_free(c->d_batch_bbox); dev_free(c->d_batch_idx); dev_free(c->d_batch_scale); dev_free(c->d_batch_refit);
   dev_free(c->d_batch_hyps); dev_free(c->d_batch_pts); dev_free(c->d_batch_cnt);
   pin_free(c->h_triples); pin_free(c->h_counts); pin_free(c->h_good); pin_free(c->h_refit);
@@ -641,6 +722,31 @@ int plane_ransac_set_cloud(plane_ransac_ctx* c, const pr_point* pts, size_t n) {
   PR_TRY(dev_reserve(c->aos, std::max<size_t>(n, 1)));
   if (n) PR_CUDA(cudaMemcpyAsync(c->aos.p, pts, n * sizeof(pr_point), cudaMemcpyHostToDevice, c->stream));
   return stage_from_device(c, c->aos.p, n);
+}
+
+int plane_ransac_set_cloud_ex(plane_ransac_ctx* c, const pr_point* pts, size_t n, unsigned flags, size_t* n_kept,
+                              float centroid[3]) {
+  PR_TRY(check_ctx(c));
+  if (!pts && n) return fail(PR_ERR_INVALID, "null cloud");
+  if (n > (size_t)INT_MAX - 4096) return fail(PR_ERR_INVALID, "cloud too large for 32-bit indices");
+  if (flags & ~(unsigned)(PR_STAGE_REMOVE_NONFINITE | PR_STAGE_TRANSLATE_CENTROID)) return fail(PR_ERR_INVALID, "unknown staging flag");
+  PR_TRY(dev_reserve(c->aos, std::max<size_t>(n, 1)));
+  if (n) PR_CUDA(cudaMemcpyAsync(c->aos.p, pts, n * sizeof(pr_point), cudaMemcpyHostToDevice, c->stream));
+  return stage_from_device(c, c->aos.p, n, flags, n_kept, centroid);
+}
+
+int plane_ransac_staged_source_indices(plane_ransac_ctx* c, int32_t* out, size_t cap) {
+  PR_TRY(check_ctx(c));
+  if (!c->have_cloud) return fail(PR_ERR_NO_CLOUD, "no cloud staged");
+  if (c->n_staged > cap || (!out && c->n_staged)) return fail(PR_ERR_CAPACITY, "output holds %zu indices, need %zu", cap, c->n_staged);
+  if (c->n_staged == 0) return PR_OK;
+  if (c->have_stage_map) {
+    PR_CUDA(cudaMemcpyAsync(out, c->d_stage_map.p, c->n_staged * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    PR_CUDA(cudaStreamSynchronize(c->stream));
+  } else {
+    for (size_t i = 0; i < c->n_staged; ++i) out[i] = (int32_t)i;
+  }
+  return PR_OK;
 }
 
 int plane_ransac_set_cloud_device(plane_ransac_ctx* c, const pr_point* dev_pts, size_t n) {

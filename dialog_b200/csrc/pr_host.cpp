@@ -154,11 +154,25 @@ bool RansacReplay::feed(const int32_t* counts, const uint8_t* good, int n) {
   return done_;
 }
 
-static float key_to_float(uint32_t k) {
+float key_to_float(uint32_t k) {
   uint32_t b = (k & 0x80000000u) ? (k ^ 0x80000000u) : ~k;
   float f;
   std::memcpy(&f, &b, 4);
   return f;
+}
+
+uint32_t float_to_key(float f) {
+  uint32_t b;
+  std::memcpy(&b, &f, 4);
+  return b ^ ((b >> 31) ? 0xFFFFFFFFu : 0x80000000u);
+}
+
+bool centroid_from_sums(const long long sums[4], const float lo[3], int scale_exp, float centroid[3]) {
+  if (sums[3] <= 0) return false;
+  const double inv = std::ldexp(1.0, -scale_exp);
+  for (int a = 0; a < 3; ++a)
+    centroid[a] = (float)((double)lo[a] + ((double)sums[a] / (double)sums[3]) * inv);
+  return true;
 }
 
 int scale_exp_from_bbox_keys(const uint32_t keys[6]) {

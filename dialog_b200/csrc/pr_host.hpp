@@ -73,6 +73,13 @@ class RansacReplay {
 // bounding box (ordered-float keys as written by the staging kernel: min x,y,z then max x,y,z).
 int scale_exp_from_bbox_keys(const uint32_t keys[6]);
 
+// Ordered-float key <-> float (keys compare like the floats they encode).
+uint32_t float_to_key(float f);
+float key_to_float(uint32_t k);
+// Exact centroid of the finite points from integer coordinate sums about `lo` on the 2^-scale_exp grid
+// (sums[3] = number of points); false when there are none.
+bool centroid_from_sums(const long long sums[4], const float lo[3], int scale_exp, float centroid[3]);
+
 // Least-squares plane from exact integer moments (DESIGN.md "refit").  Returns false (coeff
 // untouched) when fewer than 4 points contributed.
 bool plane_from_moments(const int64_t m[16], const float pivot[3], int scale_exp, float coeff[4]);

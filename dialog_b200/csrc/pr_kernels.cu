@@ -195,6 +195,63 @@ void launch_stage_batch(const float4* aos, size_t n_clouds, size_t n_per, size_t
 
 void launch_bbox_init(uint32_t* bbox, cudaStream_t s) { bbox_init_kernel<<<1, 32, 0, s>>>(bbox); }
 
+// Exact centroid (preProcess's translation, Dialog/PlaneDetect.h:458-481, made order-independent):
+// sums[0..3) = sum of rint((p - lo) * 2^s) over the finite points, sums[3] = their number.
+__global__ void __launch_bounds__(256) centroid_kernel(const float* __restrict__ X, const float* __restrict__ Y,
+                                                       const float* __restrict__ Z, size_t n, double lox, double loy,
+                                                       double loz, double scale, long long* __restrict__ sums) {
+  long long acc[4] = {0, 0, 0, 0};
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float x = X[i], y = Y[i], z = Z[i];
+    if (isfinite(x) && isfinite(y) && isfinite(z)) {
+      acc[0] += __double2ll_rn(((double)x - lox) * scale);
+      acc[1] += __double2ll_rn(((double)y - loy) * scale);
+      acc[2] += __double2ll_rn(((double)z - loz) * scale);
+      acc[3] += 1;
+    }
+  }
+  __shared__ long long s_part[8][4];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    long long v = acc[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xFFFFFFFFu, v, o);
+    if (lane == 0) s_part[warp][k] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    long long v = 0;
+    for (int w = 0; w < 8; ++w) v += s_part[w][threadIdx.x];
+    if (v) atomicAdd(reinterpret_cast<unsigned long long*>(&sums[threadIdx.x]), (unsigned long long)v);
+  }
+}
+
+__global__ void __launch_bounds__(256) translate_kernel(float* __restrict__ X, float* __restrict__ Y, float* __restrict__ Z,
+                                                        size_t n, float cx, float cy, float cz) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    X[i] = __fsub_rn(X[i], cx);  // points[i].x -= p.x, one float subtraction per coordinate
+    Y[i] = __fsub_rn(Y[i], cy);
+    Z[i] = __fsub_rn(Z[i], cz);
+  }
+}
+
+void launch_centroid(CloudView c, size_t n, const double lo[3], int scale_exp, long long* sums, int num_sms, cudaStream_t s) {
+  if (n == 0) return;
+  size_t blocks = (n + 255) / 256;
+  if (blocks > (size_t)num_sms * 8) blocks = (size_t)num_sms * 8;
+  centroid_kernel<<<(unsigned)blocks, 256, 0, s>>>(c.x, c.y, c.z, n, lo[0], lo[1], lo[2], ldexp(1.0, scale_exp), sums);
+}
+
+void launch_translate(CloudView c, size_t n, const float centroid[3], int num_sms, cudaStream_t s) {
+  if (n == 0) return;
+  size_t blocks = (n + 255) / 256;
+  if (blocks > (size_t)num_sms * 8) blocks = (size_t)num_sms * 8;
+  translate_kernel<<<(unsigned)blocks, 256, 0, s>>>(c.x, c.y, c.z, n, centroid[0], centroid[1], centroid[2]);
+}
+
 void launch_stage(const float4* aos, size_t n, CloudView dst, uint32_t* bbox, cudaStream_t s) {
   size_t blocks = (dst.cap + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
@@ -723,8 +780,13 @@ __global__ void __launch_bounds__(kCompactThreads, 5)
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       const bool valid = (i0 + e) < n;
-      const float r = plane_dot<DOT>(pl.a, pl.b, pl.c, pl.d, xs[u][e], ys[u][e], zs[u][e]);
-      const bool in = fabsf(r) < t;
+      bool in;
+      if (DOT == 2) {  // staging filter (pcl::removeNaNFromPointCloud): "inliers" are the non-finite points
+        in = !(isfinite(xs[u][e]) && isfinite(ys[u][e]) && isfinite(zs[u][e]));
+      } else {
+        const float r = plane_dot<DOT>(pl.a, pl.b, pl.c, pl.d, xs[u][e], ys[u][e], zs[u][e]);
+        in = fabsf(r) < t;
+      }
       if (valid && !in) keep[u] |= 1u << e;
       if (valid && in) inl[u] |= 1u << e;
     }
@@ -869,7 +931,9 @@ void launch_compact(CloudView src, size_t n, Plane4 plane, float t, int dot_orde
   compact_kernel<D, W><<<n_tiles, kCompactThreads, 0, s>>>(src.x, src.y, src.z, src.orig, n, plane, t, dst.x, dst.y,  \
                                                            dst.z, dst.orig, dst.cap, inl_cur, inl_orig, tile_state,   \
                                                            ticket, totals, n_tiles)
-  if (dot_order == 1) {
+  if (dot_order == 2) {
+    PR_COMPACT(2, true);
+  } else if (dot_order == 1) {
     if (write_remaining) PR_COMPACT(1, true); else PR_COMPACT(1, false);
   } else {
     if (write_remaining) PR_COMPACT(0, true); else PR_COMPACT(0, false);

@@ -43,6 +43,11 @@ void launch_stage(const float4* aos, size_t n, CloudView dst, uint32_t* bbox, cu
 // rounded up to a tile), NaN between clouds; bbox: 6 keys per cloud.
 void launch_stage_batch(const float4* aos, size_t n_clouds, size_t n_per, size_t stride, CloudView dst, uint32_t* bbox,
                         cudaStream_t s);
+// Staging extras (reference preProcess): exact integer coordinate sums about the bbox corner `lo` on the
+// 2^-scale_exp grid (sums[3] = number of finite points); in-place float translation by the centroid.
+// launch_compact with dot_order == 2 removes the non-finite points (pcl::removeNaNFromPointCloud).
+void launch_centroid(CloudView c, size_t n, const double lo[3], int scale_exp, long long* sums, int num_sms, cudaStream_t s);
+void launch_translate(CloudView c, size_t n, const float centroid[3], int num_sms, cudaStream_t s);
 // planes -> AoS (w = 1)
 void launch_unstage(CloudView src, size_t n, float4* aos, cudaStream_t s);
 

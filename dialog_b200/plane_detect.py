@@ -129,6 +129,19 @@ class PlaneRansac:
         _lib.check(self._L.plane_ransac_set_cloud(self._h, a.ctypes.data_as(C.c_void_p), a.shape[0]))
         return a.shape[0]
 
+    def set_cloud_preprocessed(self, points: np.ndarray, remove_nonfinite: bool = True, translate: bool = True):
+        """Stage with preProcess's NaN removal / centroid translation fused in (Dialog/PlaneDetect.h:449-481).
+        Returns (points kept, centroid, source index of every staged point)."""
+        a = as_cloud(points)
+        flags = (_lib.STAGE_REMOVE_NONFINITE if remove_nonfinite else 0) | (_lib.STAGE_TRANSLATE_CENTROID if translate else 0)
+        kept = C.c_size_t(0)
+        cen = np.zeros(3, np.float32)
+        _lib.check(self._L.plane_ransac_set_cloud_ex(self._h, a.ctypes.data_as(C.c_void_p), a.shape[0], flags,
+                                                     C.byref(kept), cen.ctypes.data_as(C.c_void_p)))
+        src = np.empty(max(kept.value, 1), np.int32)
+        _lib.check(self._L.plane_ransac_staged_source_indices(self._h, src.ctypes.data_as(C.c_void_p), src.size))
+        return kept.value, cen, src[: kept.value]
+
     def set_cloud_ptr(self, host_ptr: int, n: int) -> None:
         """Stage from a raw host address (e.g. a pinned torch tensor's data_ptr())."""
         _lib.check(self._L.plane_ransac_set_cloud(self._h, C.c_void_p(host_ptr), n))

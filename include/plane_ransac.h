@@ -115,6 +115,19 @@ void plane_ransac_destroy(plane_ransac_ctx* ctx);
 int plane_ransac_set_cloud(plane_ransac_ctx* ctx, const pr_point* pts, size_t n);
 /* Same, from a device pointer (AoS pr_point[] already in HBM on the context's device). */
 int plane_ransac_set_cloud_device(plane_ransac_ctx* ctx, const pr_point* dev_pts, size_t n);
+/* Staging with the reference's preProcess steps fused in (Dialog/PlaneDetect.h:449-481):
+ *   PR_STAGE_REMOVE_NONFINITE     pcl::removeNaNFromPointCloud: points with a NaN/Inf coordinate are dropped,
+ *                                 order preserved; later indices refer to the filtered cloud.
+ *   PR_STAGE_TRANSLATE_CENTROID   isConductTranslate: subtract the centroid of the (filtered) cloud, one float
+ *                                 subtraction per coordinate.  The centroid is the exactly rounded mean (integer
+ *                                 sums on the refit grid), not the reference's sequential float sum, so that
+ *                                 any thread/GPU count gives the same bits.
+ * n_kept / centroid are optional outputs.  plane_ransac_staged_source_indices returns, for each staged point,
+ * its index in the array given to set_cloud_ex (identity without the filter). */
+enum { PR_STAGE_REMOVE_NONFINITE = 1, PR_STAGE_TRANSLATE_CENTROID = 2 };
+int plane_ransac_set_cloud_ex(plane_ransac_ctx* ctx, const pr_point* pts, size_t n, unsigned flags, size_t* n_kept,
+                              float centroid[3]);
+int plane_ransac_staged_source_indices(plane_ransac_ctx* ctx, int32_t* out, size_t cap);
 /* n_staged: points given to set_cloud; n_current: points left after the last extract call. */
 int plane_ransac_cloud_size(plane_ransac_ctx* ctx, size_t* n_staged, size_t* n_current);
 

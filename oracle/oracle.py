@@ -97,6 +97,11 @@ def lib():
                                   C.POINTER(C.c_size_t), C.POINTER(Trace)]
         L.orc_extract_planes.argtypes = [vp, C.c_size_t, C.POINTER(Params), vp, vp, vp, C.c_size_t, vp,
                                          C.POINTER(C.c_int), vp, C.POINTER(C.c_size_t), C.POINTER(Trace)]
+        L.orc_remove_nonfinite.argtypes = [vp, C.c_size_t, vp, vp]
+        L.orc_remove_nonfinite.restype = C.c_size_t
+        L.orc_centroid_exact.argtypes = [vp, C.c_size_t, vp]
+        L.orc_translate.argtypes = [vp, C.c_size_t, vp]
+        L.orc_translate.restype = None
         L.orc_mt_seed.argtypes = [vp, C.c_uint32]
         L.orc_mt_next.argtypes = [vp]
         L.orc_mt_next.restype = C.c_uint32
@@ -232,6 +237,20 @@ def moments_total(m: np.ndarray):
     """Recombine the (hi, lo) split second moments into Python ints: [n, Sx, Sy, Sz, Sxx..Szz]."""
     m = [int(v) for v in m]
     return m[:4] + [m[4 + 2 * k] * (1 << 32) + m[5 + 2 * k] for k in range(6)]
+
+
+def preprocess(cloud, remove_nonfinite=True, translate=True):
+    """preProcess's first two steps: (filtered + translated cloud, source index map, centroid)."""
+    c = _cloud(cloud).copy()
+    idx = np.arange(c.shape[0], dtype=np.int32)
+    if remove_nonfinite:
+        out = np.empty_like(c)
+        m = lib().orc_remove_nonfinite(_p(c), c.shape[0], _p(out), _p(idx))
+        c, idx = out[:m].copy(), idx[:m].copy()
+    cen = np.zeros(3, np.float32)
+    if translate and lib().orc_centroid_exact(_p(c), c.shape[0], _p(cen)):
+        lib().orc_translate(_p(c), c.shape[0], _p(cen))
+    return c, idx, cen
 
 
 @dataclass

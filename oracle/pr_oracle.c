@@ -351,6 +351,48 @@ int orc_fixed_scale_exp(const orc_point* cloud, size_t n) {
   return 30 - e;
 }
 
+size_t orc_remove_nonfinite(const orc_point* cloud, size_t n, orc_point* out, int32_t* map) {
+  size_t m = 0;
+  for (size_t i = 0; i < n; ++i) {
+    if (!(isfinite(cloud[i].x) && isfinite(cloud[i].y) && isfinite(cloud[i].z))) continue;
+    if (map) map[m] = (int32_t)i;
+    out[m++] = cloud[i];
+  }
+  return m;
+}
+
+int orc_centroid_exact(const orc_point* cloud, size_t n, float centroid[3]) {
+  float lo[3] = {INFINITY, INFINITY, INFINITY};
+  size_t cnt = 0;
+  for (size_t i = 0; i < n; ++i) {
+    const float c[3] = {cloud[i].x, cloud[i].y, cloud[i].z};
+    if (!(isfinite(c[0]) && isfinite(c[1]) && isfinite(c[2]))) continue;
+    ++cnt;
+    for (int a = 0; a < 3; ++a)
+      if (c[a] < lo[a]) lo[a] = c[a];
+  }
+  centroid[0] = centroid[1] = centroid[2] = 0.0f;
+  if (!cnt) return 0;
+  const int s = orc_fixed_scale_exp(cloud, n);
+  const double sc = ldexp(1.0, s), inv = ldexp(1.0, -s);
+  long long sum[3] = {0, 0, 0};
+  for (size_t i = 0; i < n; ++i) {
+    const float c[3] = {cloud[i].x, cloud[i].y, cloud[i].z};
+    if (!(isfinite(c[0]) && isfinite(c[1]) && isfinite(c[2]))) continue;
+    for (int a = 0; a < 3; ++a) sum[a] += llrint(((double)c[a] - (double)lo[a]) * sc);
+  }
+  for (int a = 0; a < 3; ++a) centroid[a] = (float)((double)lo[a] + ((double)sum[a] / (double)cnt) * inv);
+  return 1;
+}
+
+void orc_translate(orc_point* cloud, size_t n, const float centroid[3]) {
+  for (size_t i = 0; i < n; ++i) {
+    cloud[i].x -= centroid[0];
+    cloud[i].y -= centroid[1];
+    cloud[i].z -= centroid[2];
+  }
+}
+
 typedef __int128 i128;
 
 int orc_plane_from_moments(const int64_t m[16], const float pivot[3], int scale_exp, float coeff_out[4]) {

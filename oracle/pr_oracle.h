@@ -114,6 +114,15 @@ int orc_refit_fixed(const orc_point* cloud, const int32_t* idx, size_t n_idx, co
  * with S_ab = hi * 2^32 + lo. */
 int orc_plane_from_moments(const int64_t m[16], const float pivot[3], int scale_exp, float coeff_out[4]);
 
+/* ---- staging steps of the reference's preProcess (Dialog/PlaneDetect.h:449-481) --------------
+ * pcl::removeNaNFromPointCloud: finite points in order; map[i] = source index.  Returns the count. */
+size_t orc_remove_nonfinite(const orc_point* cloud, size_t n, orc_point* out, int32_t* map);
+/* Exactly rounded centroid of the finite points (integer sums about the bbox corner on the refit grid —
+ * the order-independent form of preProcess's sequential float sum).  Returns 0 when there is no finite point. */
+int orc_centroid_exact(const orc_point* cloud, size_t n, float centroid[3]);
+/* points[i] -= centroid, one float subtraction per coordinate. */
+void orc_translate(orc_point* cloud, size_t n, const float centroid[3]);
+
 /* ---- RandomSampleConsensus::computeModel + SACSegmentation::segment ----------------------- */
 int orc_segment(const orc_point* cloud, size_t n, const orc_params* prm, int scale_exp_or_min,
                 float coeff[4], int32_t* inliers /* cap n */, size_t* n_inliers, orc_trace* trace);

@@ -314,3 +314,79 @@ def test_segment_batch_matches_per_cloud_oracle(O, pr, n_clouds, n_per, max_it, 
         assert infos[cid].best_count == seg.trace.best_count
         assert _same_bits(coeffs[cid], seg.coeff), (cid, coeffs[cid], seg.coeff)
         assert cnt[cid] == seg.inliers.size
+
+
+def test_properties_at_100m_points(pr, scene3):
+    """BASELINE configs[3] scale on one GPU (1.6 GB as pcl::PointXYZ): 10 shifted copies of a 10M-point storey.
+    Size-independent properties only: the planes and the remaining cloud tile the input in stable order, and
+    every copy of the floor is found as its own plane with the same inlier count."""
+    import dialog_b200 as D
+    base = scene3.points(0, 10_000_000)
+    n = 100_000_000
+    pts = np.empty((n, 4), np.float32)
+    for k in range(10):
+        pts[k * 10_000_000:(k + 1) * 10_000_000] = base
+        pts[k * 10_000_000:(k + 1) * 10_000_000, 2] += np.float32(8.0 * k)    # storeys 8 m apart
+    pr.set_cloud(pts)
+    prm = D.make_params(0.1, 511, 500, 1.0, True, 12345, 4, D.DOT_FMA)
+    ex = pr.extract_planes(prm, copy=False)
+    assert len(ex.planes) == 4
+    seen = np.zeros(n, bool)
+    total = 0
+    for p in ex.planes:
+        assert (np.diff(p.inliers_orig) > 0).all()
+        assert not seen[p.inliers_orig].any()
+        seen[p.inliers_orig] = True
+        total += p.inliers_orig.size
+        assert p.info.n_inliers == p.inliers_orig.size
+    rem = pr.remaining()
+    assert rem.shape[0] == n - total
+    assert np.array_equal(rem, pts[~seen])
+    pr.set_cloud(base[:1000])       # release the large buffers' contents for the following tests
+
+
+# ---------------------------------------------------------------------------------------------
+# staging with preProcess's NaN removal + centroid translation fused in (SURVEY.md §8f N1)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [0, 1, 5000, 70_001])
+def test_preprocessed_staging_matches_oracle(O, pr, scene2, n):
+    import dialog_b200 as D
+    pts = scene2.points(0, n) if n else np.zeros((0, 4), np.float32)
+    if n > 100:
+        pts[::97, 0] = np.nan
+        pts[5::211, 2] = np.inf
+        pts[:, :3] += np.float32(250.0)           # far from the origin: the translation matters
+    kept, cen, src = pr.set_cloud_preprocessed(pts)
+    want, want_src, want_cen = O.preprocess(pts)
+    assert kept == want.shape[0] and (src == want_src).all()
+    assert cen.tobytes() == want_cen.tobytes()
+    if n > 100:
+        mean64 = pts[np.isfinite(pts[:, :3]).all(1), :3].astype(np.float64).mean(0)
+        assert np.abs(cen - mean64).max() <= 1e-6 * 250.0
+    # the staged cloud is the oracle's preprocessed cloud: peel nothing and read it back
+    prm = D.make_params(0.1, 50, 10**9, 0.99, True, 12345, 1)
+    ex = pr.extract_planes(prm)
+    assert len(ex.planes) == 0
+    got = pr.remaining()
+    assert got.shape == want.shape and got.tobytes() == want.tobytes()
+    if n > 100:
+        # and the full extraction on it matches the oracle run on the preprocessed cloud
+        _check_extract(O, pr_reset(pr, pts), want, D.make_params(0.1, 127, 2000, 1.0, True, 12345, 4))
+
+
+def pr_reset(pr, pts):
+    pr.set_cloud_preprocessed(pts)
+    return _Staged(pr)
+
+
+class _Staged:
+    """Adapter: _check_extract calls set_cloud(); keep the preprocessed staging instead."""
+
+    def __init__(self, pr):
+        self._pr = pr
+
+    def set_cloud(self, pts):
+        return None
+
+    def __getattr__(self, k):
+        return getattr(self._pr, k)
