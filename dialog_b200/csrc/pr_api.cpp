@@ -132,6 +132,8 @@ struct plane_ransac_ctx {
   int scale_exp = 0;
   uint32_t bbox_keys[6] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0, 0, 0};         // this rank's points
   uint32_t bbox_keys_global[6] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0, 0, 0};  // all ranks
+  std::vector<size_t> last_offsets;   // plane offsets into d_inl_orig of the last extract call
+  std::vector<float> last_coeffs;     // 4 per plane
   DevBuf<int32_t> d_stage_map;  // staged point -> index in the caller's array (only after a filtered staging)
   bool have_stage_map = false;
 
@@ -374,6 +376,8 @@ int stage_from_device(plane_ransac_ctx* c, const float4* d_aos, size_t n, unsign
   PR_TRY(reserve_small(c));
   c->staged = planes_view(c->staged_mem.p, nullptr, cap);
   c->have_stage_map = false;
+  c->last_offsets.clear();
+  c->last_coeffs.clear();
   size_t n_out = n;
   if (flags & PR_STAGE_REMOVE_NONFINITE) {
     // stage into a scratch cloud, then compact the finite points into the staged planes (order preserved)
@@ -876,6 +880,8 @@ int plane_ransac_extract_planes(plane_ransac_ctx* c, const pr_params* prm, float
     }
   }
   *n_planes = planes;
+  c->last_offsets.assign(plane_offsets, plane_offsets + planes + 1);
+  c->last_coeffs.assign(coeffs, coeffs + 4 * (size_t)planes);
   c->current = src;
   c->n_current = n_local;
   c->n_global_current = n_global;
@@ -883,6 +889,27 @@ int plane_ransac_extract_planes(plane_ransac_ctx* c, const pr_params* prm, float
   if (off && inlier_cur) PR_CUDA(cudaMemcpyAsync(inlier_cur, c->d_inl_cur.p, off * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
   if (off && inlier_orig) PR_CUDA(cudaMemcpyAsync(inlier_orig, c->d_inl_orig.p, off * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
   PR_TRY(sync_stream(c));
+  return PR_OK;
+}
+
+int plane_ransac_plane_points(plane_ransac_ctx* c, int k, int project, pr_point* out, size_t cap, size_t* n) {
+  PR_TRY(check_ctx(c));
+  if (!c->have_cloud) return fail(PR_ERR_NO_CLOUD, "no cloud staged");
+  if (k < 0 || (size_t)k + 1 >= c->last_offsets.size()) return fail(PR_ERR_INVALID, "plane %d is not a plane of the last extract call", k);
+  const size_t off = c->last_offsets[k], cnt = c->last_offsets[k + 1] - off;
+  if (n) *n = cnt;
+  if (!out) return PR_OK;
+  if (cnt > cap) return fail(PR_ERR_CAPACITY, "output holds %zu points, need %zu", cap, cnt);
+  if (cnt == 0) return PR_OK;
+  PR_TRY(dev_reserve(c->aos, std::max(cnt, c->aos.cap)));
+  {
+    Span sp(c, KC_OTHER, 1);
+    pr::Plane4 pl = {c->last_coeffs[4 * k], c->last_coeffs[4 * k + 1], c->last_coeffs[4 * k + 2], c->last_coeffs[4 * k + 3]};
+    pr::launch_plane_points(c->staged, c->d_inl_orig.p + off, cnt, pl, project != 0, c->aos.p, c->stream);
+  }
+  PR_CUDA(cudaGetLastError());
+  PR_CUDA(cudaMemcpyAsync(out, c->aos.p, cnt * sizeof(pr_point), cudaMemcpyDeviceToHost, c->stream));
+  PR_CUDA(cudaStreamSynchronize(c->stream));
   return PR_OK;
 }
 

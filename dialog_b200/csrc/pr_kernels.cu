@@ -258,6 +258,35 @@ void launch_stage(const float4* aos, size_t n, CloudView dst, uint32_t* bbox, cu
   stage_kernel<<<(unsigned)blocks, 256, 0, s>>>(aos, n, dst.x, dst.y, dst.z, dst.cap, bbox);
 }
 
+// Plane::points_set for one plane (gather by inlier index), optionally projected onto the plane with the
+// reference's projPoint2Plane arithmetic (Dialog/PlaneDetect.h:1442-1448): lambda = 2.0 * (a*x + b*y + c*z + d)
+// in float, p' = p - lambda / 2.0 * n evaluated in double and rounded to float.
+__global__ void __launch_bounds__(256) plane_points_kernel(const float* __restrict__ x, const float* __restrict__ y,
+                                                           const float* __restrict__ z, const int32_t* __restrict__ idx,
+                                                           size_t n, Plane4 pl, bool project, float4* __restrict__ out) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const int32_t j = idx[i];
+    float px = x[j], py = y[j], pz = z[j];
+    if (project) {
+      const float inner = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(pl.a, px), __fmul_rn(pl.b, py)), __fmul_rn(pl.c, pz)), pl.d);
+      const float lambda = (float)(2.0 * (double)inner);
+      const double half = (double)lambda / 2.0;
+      px = (float)__dsub_rn((double)px, __dmul_rn(half, (double)pl.a));
+      py = (float)__dsub_rn((double)py, __dmul_rn(half, (double)pl.b));
+      pz = (float)__dsub_rn((double)pz, __dmul_rn(half, (double)pl.c));
+    }
+    out[i] = make_float4(px, py, pz, 1.0f);
+  }
+}
+
+void launch_plane_points(CloudView cloud, const int32_t* idx, size_t n, Plane4 pl, bool project, float4* out, cudaStream_t s) {
+  if (n == 0) return;
+  size_t blocks = (n + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  plane_points_kernel<<<(unsigned)blocks, 256, 0, s>>>(cloud.x, cloud.y, cloud.z, idx, n, pl, project, out);
+}
+
 void launch_unstage(CloudView src, size_t n, float4* aos, cudaStream_t s) {
   if (n == 0) return;
   size_t blocks = (n + 255) / 256;

@@ -48,6 +48,8 @@ void launch_stage_batch(const float4* aos, size_t n_clouds, size_t n_per, size_t
 // launch_compact with dot_order == 2 removes the non-finite points (pcl::removeNaNFromPointCloud).
 void launch_centroid(CloudView c, size_t n, const double lo[3], int scale_exp, long long* sums, int num_sms, cudaStream_t s);
 void launch_translate(CloudView c, size_t n, const float centroid[3], int num_sms, cudaStream_t s);
+// out[i] = cloud[idx[i]] (w = 1), optionally projected onto `pl` (reference projPoint2Plane arithmetic).
+void launch_plane_points(CloudView cloud, const int32_t* idx, size_t n, Plane4 pl, bool project, float4* out, cudaStream_t s);
 // planes -> AoS (w = 1)
 void launch_unstage(CloudView src, size_t n, float4* aos, cudaStream_t s);
 

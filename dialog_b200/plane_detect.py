@@ -233,6 +233,16 @@ class PlaneRansac:
                                                       cnt.ctypes.data_as(C.c_void_p), infos))
         return coeffs, cnt, infos
 
+    def plane_points(self, k: int, project: bool = False) -> np.ndarray:
+        """Plane::points_set of plane k of the last extract call; project=True gives the cloud polyPointCloud
+        hands to pcl::ConcaveHull (points projected onto the plane, Dialog/PlaneDetect.h:1391-1397)."""
+        n = C.c_size_t(0)
+        _lib.check(self._L.plane_ransac_plane_points(self._h, k, int(project), None, 0, C.byref(n)))
+        out = np.empty((max(n.value, 1), 4), np.float32)
+        _lib.check(self._L.plane_ransac_plane_points(self._h, k, int(project), out.ctypes.data_as(C.c_void_p),
+                                                     out.shape[0], C.byref(n)))
+        return out[: n.value]
+
     def remaining(self) -> np.ndarray:
         _, n_cur = self.cloud_size()
         out = np.empty((max(n_cur, 1), 4), np.float32)

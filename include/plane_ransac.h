@@ -152,6 +152,11 @@ int plane_ransac_segment_one(plane_ransac_ctx* ctx, const pr_params* prm, float 
 int plane_ransac_extract_planes(plane_ransac_ctx* ctx, const pr_params* prm, float* coeffs,
                                 int32_t* inlier_cur, int32_t* inlier_orig, size_t idx_cap,
                                 size_t* plane_offsets, int* n_planes, pr_segment_info* infos);
+/* Plane::points_set of plane k of the last extract call (Dialog/HeaderFile.h:85): its inlier points in index
+ * order, read from the staged cloud.  With project != 0 every point is projected onto the plane with the
+ * reference's projPoint2Plane arithmetic (Dialog/PlaneDetect.h:1442-1448) — the cloud polyPointCloud hands to
+ * pcl::ConcaveHull (Dialog/PlaneDetect.h:1391-1401).  out may be NULL to query the count. */
+int plane_ransac_plane_points(plane_ransac_ctx* ctx, int plane_index, int project, pr_point* out, size_t cap, size_t* n);
 /* Points left after the last extract call, original order (== the rebuilt source_cloud). */
 int plane_ransac_remaining(plane_ransac_ctx* ctx, pr_point* out, size_t cap, size_t* n);
 

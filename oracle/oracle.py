@@ -102,6 +102,8 @@ def lib():
         L.orc_centroid_exact.argtypes = [vp, C.c_size_t, vp]
         L.orc_translate.argtypes = [vp, C.c_size_t, vp]
         L.orc_translate.restype = None
+        L.orc_project_points.argtypes = [vp, vp, C.c_size_t, vp, vp]
+        L.orc_project_points.restype = None
         L.orc_mt_seed.argtypes = [vp, C.c_uint32]
         L.orc_mt_next.argtypes = [vp]
         L.orc_mt_next.restype = C.c_uint32
@@ -251,6 +253,15 @@ def preprocess(cloud, remove_nonfinite=True, translate=True):
     if translate and lib().orc_centroid_exact(_p(c), c.shape[0], _p(cen)):
         lib().orc_translate(_p(c), c.shape[0], _p(cen))
     return c, idx, cen
+
+
+def project_points(cloud, idx, coeff) -> np.ndarray:
+    c = _cloud(cloud)
+    i = np.ascontiguousarray(idx, np.int32)
+    co = np.ascontiguousarray(coeff, np.float32)
+    out = np.empty((i.size, 4), np.float32)
+    lib().orc_project_points(_p(c), _p(i), i.size, _p(co), _p(out))
+    return out
 
 
 @dataclass

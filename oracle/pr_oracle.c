@@ -393,6 +393,17 @@ void orc_translate(orc_point* cloud, size_t n, const float centroid[3]) {
   }
 }
 
+void orc_project_points(const orc_point* cloud, const int32_t* idx, size_t n_idx, const float coeff[4], orc_point* out) {
+  for (size_t i = 0; i < n_idx; ++i) {
+    const orc_point* p = &cloud[idx[i]];
+    float lambda = 2.0 * (coeff[0] * p->x + coeff[1] * p->y + coeff[2] * p->z + coeff[3]);
+    out[i].x = p->x - lambda / 2.0 * coeff[0];
+    out[i].y = p->y - lambda / 2.0 * coeff[1];
+    out[i].z = p->z - lambda / 2.0 * coeff[2];
+    out[i].w = 1.0f;
+  }
+}
+
 typedef __int128 i128;
 
 int orc_plane_from_moments(const int64_t m[16], const float pivot[3], int scale_exp, float coeff_out[4]) {

@@ -123,6 +123,10 @@ int orc_centroid_exact(const orc_point* cloud, size_t n, float centroid[3]);
 /* points[i] -= centroid, one float subtraction per coordinate. */
 void orc_translate(orc_point* cloud, size_t n, const float centroid[3]);
 
+/* projPoint2Plane (Dialog/PlaneDetect.h:1442-1448) applied to cloud[idx[i]]: lambda = 2.0 * (a*x + b*y + c*z + d)
+ * stored as float, dest = src - lambda / 2.0 * n evaluated in double and stored as float. */
+void orc_project_points(const orc_point* cloud, const int32_t* idx, size_t n_idx, const float coeff[4], orc_point* out);
+
 /* ---- RandomSampleConsensus::computeModel + SACSegmentation::segment ----------------------- */
 int orc_segment(const orc_point* cloud, size_t n, const orc_params* prm, int scale_exp_or_min,
                 float coeff[4], int32_t* inliers /* cap n */, size_t* n_inliers, orc_trace* trace);

@@ -390,3 +390,24 @@ class _Staged:
 
     def __getattr__(self, k):
         return getattr(self._pr, k)
+
+
+def test_plane_points_and_projection_match_oracle(O, pr, scene2):
+    """Hand-off to polyPlanes (SURVEY.md §8f N3): Plane::points_set and its projection onto the plane."""
+    import dialog_b200 as D
+    pts = scene2.points(0, 90_000)
+    pts[:, :3] += np.float32(12.5)
+    pr.set_cloud(pts)
+    ex = pr.extract_planes(D.make_params(0.1, 255, 3000, 1.0, True, 12345, 8))
+    assert len(ex.planes) == 3
+    for k, p in enumerate(ex.planes):
+        got = pr.plane_points(k)
+        assert got.tobytes() == pts[p.inliers_orig].tobytes()
+        proj = pr.plane_points(k, project=True)
+        want = O.project_points(pts, p.inliers_orig, p.coeff)
+        assert proj.tobytes() == want.tobytes()
+        # projected points lie on the plane to float accuracy
+        r = proj[:, :3].astype(np.float64) @ p.coeff[:3].astype(np.float64) + float(p.coeff[3])
+        assert np.abs(r).max() < 1e-4
+    with pytest.raises(D.PlaneRansacError):
+        pr.plane_points(3)
