@@ -52,6 +52,9 @@ def parse_args():
     ap.add_argument("--planes", type=int, default=20)
     ap.add_argument("--cpu-sample-hyps", type=int, default=512)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--scorer", default="brute", choices=["brute", "hier"],
+                    help="brute = the FP32-FMA-bound kernel the roofline is reported for (default); hier = same counts "
+                         "through the bounding-box culled scorer")
     ap.add_argument("--extras", action="store_true",
                     help="also time BASELINE configs[1] (1M points, 3 planes, K=1024) and a slice of configs[4] "
                          "(batch of 32K-point clouds, K=256) on rank 0's GPU; reported under 'extras'")
@@ -65,7 +68,7 @@ def workload_config(args, n_gpus):
                     "hypotheses per round (max_iterations=%d, probability=1.0), t=0.1, min_plane=500, seed=12345"
                     % (args.points, n_gpus, args.planes, args.hyps, args.hyps - 1),
         "points_per_gpu": args.points, "points_total": args.points * n_gpus, "hypotheses_per_round": args.hyps,
-        "planes": args.planes, "distance_threshold": 0.1, "min_plane_size": 500, "dot_order": "fma",
+        "planes": args.planes, "distance_threshold": 0.1, "min_plane_size": 500, "dot_order": "fma", "scorer": args.scorer,
         "sharding": "points, contiguous index ranges; NCCL all-reduce of int32 counts + int64 moments" if n_gpus > 1 else "none",
         "l2": "256 MiB fill kernel between timed steps (outside the timed region); cloud planes are 120 MB per GPU",
     }
@@ -245,7 +248,8 @@ def main():
         uid = [D.PlaneRansac.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
         pr.comm_init(world, rank, uid[0])
-    prm = D.make_params(0.1, args.hyps - 1, 500, 1.0, True, 12345, args.planes, D.DOT_FMA)
+    prm = D.make_params(0.1, args.hyps - 1, 500, 1.0, True, 12345, args.planes, D.DOT_FMA,
+                        D.SCORER_HIER if args.scorer == "hier" else D.SCORER_BRUTE)
 
     def barrier():
         torch.cuda.synchronize()
@@ -302,13 +306,34 @@ def main():
     h2d = count * 16 + n_draws * 12
     d2h = n_inl_local * 8 + n_draws * 8 + len(ex2.infos) * (144 + 16 + 16)
 
+    # ---- same workload through the opt-in hierarchical (bounding-box culled) scorer: identical planes ----
+    hier_ms = []
+    hier_same = None
+    if args.scorer == "brute":
+        prm_h = D.make_params(0.1, args.hyps - 1, 500, 1.0, True, 12345, args.planes, D.DOT_FMA, D.SCORER_HIER)
+        pr.set_cloud_ptr(pinned.data_ptr(), count)
+        for _ in range(2):
+            exh = pr.extract_planes(prm_h, want_indices=False)
+        barrier()
+        for _ in range(args.steps):
+            pr.flush_l2()
+            barrier()
+            pr.timer_start()
+            exh = pr.extract_planes(prm_h, want_indices=False)
+            hier_ms.append(pr.timer_stop())
+        barrier()
+        hier_same = len(exh.planes) == len(ex.planes) and all(
+            a.coeff.tobytes() == b.coeff.tobytes() and a.info.n_inliers == b.info.n_inliers
+            for a, b in zip(exh.planes, ex.planes))
+    hier_total_ms = sum(hier_ms)
+
     # ---- max over ranks ----
-    t = torch.tensor([total_ms, e2e_total_ms], dtype=torch.float64, device="cuda")
+    t = torch.tensor([total_ms, e2e_total_ms, hier_total_ms], dtype=torch.float64, device="cuda")
     agg = torch.tensor([float(h2d), float(d2h)], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(agg, op=dist.ReduceOp.SUM)
-    total_ms, e2e_total_ms = t.tolist()
+    total_ms, e2e_total_ms, hier_total_ms = t.tolist()
     h2d_all, d2h_all = agg.tolist()
 
     if rank == 0:
@@ -332,7 +357,10 @@ def main():
                     "h2d_bytes_per_step": int(h2d_all), "d2h_bytes_per_step": int(d2h_all)},
             "gpu_launches": int(launches),
             "roofline": {
-                "kernel": "score_kernel<8,FMA>", "bound": "fp32_fma", "achieved": score_tf, "peak": peak_tf,
+                "kernel": "score_kernel<8,FMA>" if args.scorer == "brute" else
+                          "score_hier_kernel (culled: 'achieved' counts the point-hypotheses decided, not the FMAs executed, "
+                          "so frac is not a pipe utilisation)",
+                "bound": "fp32_fma", "achieved": score_tf, "peak": peak_tf,
                 "unit": "TFLOP/s", "frac": (score_tf / peak_tf) if score_tf and peak_tf else None, "traffic": None,
                 "peak_source": "FFMA2-only kernel timed live on this GPU (MEASURED_PEAKS.json has no FP32 figure; "
                                "nominal 148 SM x 128 lanes x 2 x 1.965 GHz = 74.4)",
@@ -350,6 +378,12 @@ def main():
                                    "refit": prof.ms_refit / args.steps, "compact": prof.ms_compact / args.steps},
             "clocks": clock_info,
         }
+        if hier_ms:
+            line["hier_scorer"] = {
+                "ms_per_step": hier_total_ms / args.steps, "value": pairs_step / (hier_total_ms / args.steps * 1e-3),
+                "unit": UNIT, "identical_planes": bool(hier_same),
+                "note": "opt-in PR_SCORER_HIER: Morton-sorted copy + per-32-point boxes, blocks outside the threshold slab "
+                        "skipped, the rest evaluated with the same arithmetic; same counts, not the roofline kernel"}
         if args.extras:
             line["extras"] = run_extras(args, pr)
         if not args.no_cpu_baseline:

@@ -14,6 +14,8 @@ LIB_PATH = os.path.join(HERE, "libplane_ransac.so")
 UNIQUE_ID_BYTES = 128
 DOT_PCL_SSE2 = 0
 DOT_FMA = 1
+SCORER_BRUTE = 0
+SCORER_HIER = 1
 STAGE_REMOVE_NONFINITE = 1
 STAGE_TRANSLATE_CENTROID = 2
 
@@ -42,6 +44,7 @@ class PrParams(C.Structure):
         ("seed", C.c_uint),
         ("max_planes", C.c_int),
         ("dot_order", C.c_int),
+        ("scorer", C.c_int),
     ]
 
 

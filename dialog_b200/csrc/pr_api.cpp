@@ -132,6 +132,16 @@ struct plane_ransac_ctx {
   int scale_exp = 0;
   uint32_t bbox_keys[6] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0, 0, 0};         // this rank's points
   uint32_t bbox_keys_global[6] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0, 0, 0};  // all ranks
+  // hierarchical scorer: Morton-sorted copies (staged + two peel buffers), block boxes, sort scratch
+  DevBuf<float> sorted_mem[3];
+  pr::CloudView sorted_view[3];
+  bool sorted_staged_valid = false;
+  DevBuf<float4> d_bounds;
+  DevBuf<float2> d_aux;
+  DevBuf<uint32_t> d_keys, d_vals;
+  DevBuf<unsigned char> d_sort_temp;
+  DevBuf<long long> d_totals2;
+  float cmax = 0.f;
   std::vector<size_t> last_offsets;   // plane offsets into d_inl_orig of the last extract call
   std::vector<float> last_coeffs;     // 4 per plane
   DevBuf<int32_t> d_stage_map;  // staged point -> index in the caller's array (only after a filtered staging)
@@ -293,6 +303,7 @@ int check_params(const pr_params* p) {
   if (!(p->probability > 0.0) || p->probability > 1.0) return fail(PR_ERR_INVALID, "probability must be in (0, 1]");
   if (p->dot_order != PR_DOT_PCL_SSE2 && p->dot_order != PR_DOT_FMA) return fail(PR_ERR_INVALID, "unknown dot_order");
   if (p->max_planes < 0) return fail(PR_ERR_INVALID, "max_planes must be >= 0");
+  if (p->scorer != PR_SCORER_BRUTE && p->scorer != PR_SCORER_HIER) return fail(PR_ERR_INVALID, "unknown scorer");
   return PR_OK;
 }
 
@@ -378,6 +389,7 @@ int stage_from_device(plane_ransac_ctx* c, const float4* d_aos, size_t n, unsign
   c->have_stage_map = false;
   c->last_offsets.clear();
   c->last_coeffs.clear();
+  c->sorted_staged_valid = false;
   size_t n_out = n;
   if (flags & PR_STAGE_REMOVE_NONFINITE) {
     // stage into a scratch cloud, then compact the finite points into the staged planes (order preserved)
@@ -466,6 +478,38 @@ int stage_from_device(plane_ransac_ctx* c, const float4* d_aos, size_t n, unsign
   return PR_OK;
 }
 
+// Morton-sorted copy of the staged cloud for the hierarchical scorer (built once per staging).
+int ensure_sorted(plane_ransac_ctx* c, int n_buffers) {
+  const size_t cap = c->staged.cap, n = c->n_staged;
+  for (int i = 0; i < n_buffers; ++i) {
+    PR_TRY(dev_reserve(c->sorted_mem[i], 3 * cap));
+    c->sorted_view[i] = planes_view(c->sorted_mem[i].p, nullptr, cap);
+  }
+  PR_TRY(dev_reserve(c->d_bounds, 2 * ((cap + 31) / 32)));
+  PR_TRY(dev_reserve(c->d_totals2, 4));
+  if (c->sorted_staged_valid) return PR_OK;
+  float lo[3] = {0.f, 0.f, 0.f}, extent = 0.f, cmax = 0.f;
+  for (int a = 0; a < 3; ++a) {
+    if (c->bbox_keys[a] > c->bbox_keys[3 + a]) continue;
+    const float l = pr::key_to_float(c->bbox_keys[a]), h = pr::key_to_float(c->bbox_keys[3 + a]);
+    lo[a] = l;
+    extent = std::max(extent, h - l);
+    cmax = std::max(cmax, std::max(std::fabs(l), std::fabs(h)));
+  }
+  c->cmax = cmax;
+  PR_TRY(dev_reserve(c->d_keys, 2 * std::max<size_t>(n, 1)));
+  PR_TRY(dev_reserve(c->d_vals, 2 * std::max<size_t>(n, 1)));
+  const size_t tb = pr::sort_temp_bytes(std::max<size_t>(n, 1));
+  PR_TRY(dev_reserve(c->d_sort_temp, tb + 256));
+  {
+    Span sp(c, KC_STAGE, 3);
+    pr::launch_morton_sort(c->staged, n, lo, extent, c->d_keys.p, c->d_vals.p, c->d_sort_temp.p, tb, c->sorted_view[0], c->stream);
+  }
+  PR_CUDA(cudaGetLastError());
+  c->sorted_staged_valid = true;
+  return PR_OK;
+}
+
 struct SegmentOut {
   float coeff[4] = {0, 0, 0, 0};
   long long n_inl_local = 0, n_rem_local = 0;
@@ -478,7 +522,9 @@ struct SegmentOut {
 // write_remaining the non-inliers are compacted into dst.
 int segment_core(plane_ransac_ctx* c, const pr_params* prm, pr::CloudView src, size_t n_local, long long n_global,
                  long long first, bool write_remaining, pr::CloudView dst, int32_t* d_inl_cur, int32_t* d_inl_orig,
-                 pr_segment_info* info, SegmentOut* out) {
+                 pr_segment_info* info, SegmentOut* out, const pr::CloudView* ssrc = nullptr,
+                 const pr::CloudView* sdst = nullptr) {
+  // ssrc: Morton-sorted copy of src (hierarchical scorer); sdst receives its peeled remainder
   HostTimer whole(&c->prof.host_ms_total);
   pr_segment_info inf;
   std::memset(&inf, 0, sizeof(inf));
@@ -488,6 +534,12 @@ int segment_core(plane_ransac_ctx* c, const pr_params* prm, pr::CloudView src, s
   out->n_rem_local = (long long)n_local;
   const float t = pr::threshold_up(prm->distance_threshold);
   PR_TRY(reserve_small(c));
+
+  const bool hier = ssrc != nullptr && n_local > 0;
+  if (hier) {
+    Span sp(c, KC_SCORE, 1);
+    pr::launch_block_bounds(*ssrc, n_local, c->d_bounds.p, c->stream);
+  }
 
   pr::RansacReplay replay(std::max(1ll, n_global), prm->max_iterations, prm->probability);
   int total_draws = 0;
@@ -541,7 +593,13 @@ int segment_core(plane_ransac_ctx* c, const pr_params* prm, pr::CloudView src, s
         PR_CUDA(cudaMemsetAsync(dc, 0, sb * sizeof(int32_t), c->stream));
         {
           Span sp(c, KC_SCORE, 0);
-          c->prof.launches_score += pr::launch_score(src, n_local, 1, 0, dh, (int)sb, t, prm->dot_order, dc, c->num_sms, c->stream);
+          if (hier) {
+            PR_TRY(dev_reserve(c->d_aux, c->draw_cap));
+            c->prof.launches_score += pr::launch_score_hier(*ssrc, n_local, c->d_bounds.p, dh, c->d_aux.p + at, (int)sb, t, c->cmax,
+                                                            prm->dot_order, dc, c->num_sms, c->stream);
+          } else {
+            c->prof.launches_score += pr::launch_score(src, n_local, 1, 0, dh, (int)sb, t, prm->dot_order, dc, c->num_sms, c->stream);
+          }
           c->prof.pairs_scored += (long long)n_local * sb;
         }
         done += sb;
@@ -615,6 +673,14 @@ int segment_core(plane_ransac_ctx* c, const pr_params* prm, pr::CloudView src, s
   if (c->comm) PR_NCCL(g_nccl.AllGather(c->d_totals.p, c->d_totals.p + 2, 2, ncclInt64, c->comm, c->stream));
   PR_CUDA(cudaMemcpyAsync(c->h_totals.p, c->d_totals.p, (2 + (c->comm ? 2 * c->n_ranks : 0)) * sizeof(long long),
                           cudaMemcpyDeviceToHost, c->stream));
+  if (hier && sdst && write_remaining) {
+    // the sorted copy is peeled with the same predicate (stable, so it stays in Morton order)
+    Span sp(c, KC_COMPACT, 1);
+    pr::Plane4 pl = {refined[0], refined[1], refined[2], refined[3]};
+    pr::launch_compact(*ssrc, n_local, pl, t, prm->dot_order, *sdst, true, nullptr, nullptr, c->d_scratch.p, c->d_totals2.p, c->stream);
+    c->prof.points_compact += (long long)n_local;
+    c->prof.bytes_compact += 12ll * (long long)n_local;
+  }
   PR_TRY(sync_stream(c));
   out->n_rem_local = c->h_totals.p[0];
   out->n_inl_local = c->h_totals.p[1];
@@ -668,6 +734,7 @@ void plane_ransac_default_params(pr_params* p) {
   p->seed = 12345u;
   p->max_planes = 64;
   p->dot_order = PR_DOT_FMA;
+  p->scorer = PR_SCORER_BRUTE;
 }
 
 int plane_ransac_create(plane_ransac_ctx** out, int device_id) {
@@ -710,6 +777,9 @@ void plane_ransac_destroy(plane_ransac_ctx* c) {
   dev_free(c->d_sample_pts); dev_free(c->d_hyps); dev_free(c->d_refit); dev_free(c->d_totals);
   dev_free(c->d_scratch); dev_free(c->d_inl_cur); dev_free(c->d_inl_orig); dev_free(c->d_flush); dev_free(c->batch_mem);
   dev_free(c->d_stage_map);
+  for (int i = 0; i < 3; ++i) dev_free(c->sorted_mem[i]);
+  dev_free(c->d_bounds); dev_free(c->d_aux); dev_free(c->d_keys); dev_free(c->d_vals); dev_free(c->d_sort_temp);
+  dev_free(c->d_totals2);
   dev_free(c->d_batch_bbox); dev_free(c->d_batch_idx); dev_free(c->d_batch_scale); dev_free(c->d_batch_refit);
   dev_free(c->d_batch_hyps); dev_free(c->d_batch_pts); dev_free(c->d_batch_cnt);
   pin_free(c->h_triples); pin_free(c->h_counts); pin_free(c->h_good); pin_free(c->h_refit);
@@ -819,8 +889,10 @@ int plane_ransac_segment_one(plane_ransac_ctx* c, const pr_params* prm, float co
   PR_TRY(dev_reserve(c->d_inl_cur, std::max<size_t>(c->n_staged, 1)));
   SegmentOut so;
   pr::CloudView none;
+  const bool hier = prm->scorer == PR_SCORER_HIER;
+  if (hier) PR_TRY(ensure_sorted(c, 1));
   PR_TRY(segment_core(c, prm, c->staged, c->n_staged, c->n_global_staged, c->first_staged, false, none, c->d_inl_cur.p,
-                      nullptr, info, &so));
+                      nullptr, info, &so, hier ? &c->sorted_view[0] : nullptr, nullptr));
   std::memcpy(coeff, so.coeff, 4 * sizeof(float));
   *n_inliers = (size_t)so.n_inl_local;
   if (inliers) {
@@ -841,6 +913,9 @@ int plane_ransac_extract_planes(plane_ransac_ctx* c, const pr_params* prm, float
   if (!c->have_cloud) return fail(PR_ERR_NO_CLOUD, "no cloud staged");
   if (!coeffs || !plane_offsets || !n_planes) return fail(PR_ERR_INVALID, "null output");
   PR_TRY(reserve_work(c));
+  const bool hier = prm->scorer == PR_SCORER_HIER;
+  if (hier) PR_TRY(ensure_sorted(c, 3));
+  int s_cur = 0;  // index of the sorted copy that matches src
   pr::CloudView src = c->staged;
   size_t n_local = c->n_staged;
   long long n_global = c->n_global_staged, first = c->first_staged;
@@ -853,8 +928,9 @@ int plane_ransac_extract_planes(plane_ransac_ctx* c, const pr_params* prm, float
     pr::CloudView dst = c->work[planes & 1];
     SegmentOut so;
     pr_segment_info inf;
+    const int s_next = 1 + (planes & 1);
     PR_TRY(segment_core(c, prm, src, n_local, n_global, first, true, dst, c->d_inl_cur.p + off, c->d_inl_orig.p + off,
-                        &inf, &so));
+                        &inf, &so, hier ? &c->sorted_view[s_cur] : nullptr, hier ? &c->sorted_view[s_next] : nullptr));
     if (infos) infos[planes] = inf;
     const long long m = so.n_inl_global;
     if (m == 0 || m < (long long)std::max(0, prm->min_plane_size)) break;
@@ -865,6 +941,7 @@ int plane_ransac_extract_planes(plane_ransac_ctx* c, const pr_params* prm, float
     plane_offsets[planes + 1] = off;
     ++planes;
     src = dst;
+    s_cur = s_next;
     n_local = (size_t)so.n_rem_local;
     if (c->comm) {
       long long tot = 0, f = 0;

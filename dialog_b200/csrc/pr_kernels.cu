@@ -18,6 +18,7 @@
 #include <math_constants.h>
 
 #include <cstdlib>
+#include <cub/device/device_radix_sort.cuh>
 
 namespace pr {
 
@@ -594,6 +595,331 @@ int launch_score(CloudView cloud, size_t n_per_cloud, int n_clouds, size_t cloud
   return launches;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Hierarchical scorer (pr_params.scorer = PR_SCORER_HIER): same counts as K2, fewer evaluations.
+//
+// A copy of the cloud is kept in Morton order; every 32 consecutive points form a block with an
+// axis-aligned box (centre c, half-extent e rounded up).  For hypothesis (n, d) and a block,
+// |n.p + d| >= |n.c + d| - (|a|ex + |b|ey + |c|ez) for every point of the block, so a block whose box lies
+// farther than t + margin from the plane holds no inlier and a block whose box lies entirely within
+// t - margin holds only inliers; only the remaining blocks are evaluated point by point, with exactly
+// the arithmetic of K2.  margin = 2e-6 * ((|a|+|b|+|c|) * Cmax + |d|) dominates every FP32 rounding error
+// of the box test and of the per-point FMA chain (each is at most 3 * 2^-24 of that magnitude), so the
+// counts are bit-identical to the brute-force kernel.  Non-finite boxes or hypotheses fail both tests
+// and fall through to the exact evaluation.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t morton_spread10(uint32_t v) {
+  v &= 0x3FFu;
+  v = (v | (v << 16)) & 0x030000FFu;
+  v = (v | (v << 8)) & 0x0300F00Fu;
+  v = (v | (v << 4)) & 0x030C30C3u;
+  v = (v | (v << 2)) & 0x09249249u;
+  return v;
+}
+
+__global__ void __launch_bounds__(256) morton_kernel(const float* __restrict__ x, const float* __restrict__ y,
+                                                     const float* __restrict__ z, size_t n, float lox, float loy, float loz,
+                                                     float inv_extent, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float px = x[i], py = y[i], pz = z[i];
+    uint32_t k = 0x3FFFFFFFu;  // non-finite points sort to the end
+    if (isfinite(px) && isfinite(py) && isfinite(pz)) {
+      const uint32_t qx = (uint32_t)fminf(fmaxf((px - lox) * inv_extent, 0.f), 1023.f);
+      const uint32_t qy = (uint32_t)fminf(fmaxf((py - loy) * inv_extent, 0.f), 1023.f);
+      const uint32_t qz = (uint32_t)fminf(fmaxf((pz - loz) * inv_extent, 0.f), 1023.f);
+      k = morton_spread10(qx) | (morton_spread10(qy) << 1) | (morton_spread10(qz) << 2);
+    }
+    keys[i] = k;
+    vals[i] = (uint32_t)i;
+  }
+}
+
+__global__ void __launch_bounds__(256) gather_sorted_kernel(const float* __restrict__ x, const float* __restrict__ y,
+                                                            const float* __restrict__ z, const uint32_t* __restrict__ order,
+                                                            size_t n, float* __restrict__ sx, float* __restrict__ sy,
+                                                            float* __restrict__ sz, size_t cap) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += stride) {
+    float px = CUDART_NAN_F, py = CUDART_NAN_F, pz = CUDART_NAN_F;
+    if (i < n) {
+      const uint32_t j = order[i];
+      px = x[j];
+      py = y[j];
+      pz = z[j];
+    }
+    sx[i] = px;
+    sy[i] = py;
+    sz[i] = pz;
+  }
+}
+
+size_t sort_temp_bytes(size_t n) {
+  size_t bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr, (const uint32_t*)nullptr,
+                                  (uint32_t*)nullptr, (int)n, 0, 30);
+  return bytes;
+}
+
+// keys/vals: 2 * n uint32 each (in | out halves); temp: sort_temp_bytes(n)
+void launch_morton_sort(CloudView src, size_t n, const float lo[3], float extent, uint32_t* keys, uint32_t* vals, void* temp,
+                        size_t temp_bytes, CloudView dst, cudaStream_t s) {
+  size_t blocks = (dst.cap + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (n) {
+    const float inv = extent > 0.f ? 1023.999f / extent : 0.f;
+    morton_kernel<<<(unsigned)blocks, 256, 0, s>>>(src.x, src.y, src.z, n, lo[0], lo[1], lo[2], inv, keys, vals);
+    cub::DeviceRadixSort::SortPairs(temp, temp_bytes, keys, keys + n, vals, vals + n, (int)n, 0, 30, s);
+  }
+  gather_sorted_kernel<<<(unsigned)blocks, 256, 0, s>>>(src.x, src.y, src.z, vals + n, n, dst.x, dst.y, dst.z, dst.cap);
+}
+
+// one warp per 32-point block: box centre / half-extent (rounded up) over the finite points, their number
+__global__ void __launch_bounds__(256) block_bounds_kernel(const float* __restrict__ x, const float* __restrict__ y,
+                                                           const float* __restrict__ z, size_t n_blocks,
+                                                           float4* __restrict__ bounds) {
+  const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= n_blocks) return;
+  const size_t i = warp * 32 + lane;
+  const float p[3] = {x[i], y[i], z[i]};  // padding is NaN
+  const bool fin = isfinite(p[0]) && isfinite(p[1]) && isfinite(p[2]);
+  const unsigned fm = __ballot_sync(0xFFFFFFFFu, fin);
+  float c[3], e[3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    const uint32_t k = float_order_key(p[a]);
+    const uint32_t lo = __reduce_min_sync(0xFFFFFFFFu, fin ? k : 0xFFFFFFFFu);
+    const uint32_t hi = __reduce_max_sync(0xFFFFFFFFu, fin ? k : 0u);
+    const uint32_t lb = (lo & 0x80000000u) ? (lo ^ 0x80000000u) : ~lo, hb = (hi & 0x80000000u) ? (hi ^ 0x80000000u) : ~hi;
+    const float flo = __uint_as_float(lb), fhi = __uint_as_float(hb);
+    c[a] = 0.5f * flo + 0.5f * fhi;
+    e[a] = fmaxf(__fsub_ru(fhi, c[a]), __fsub_ru(c[a], flo));
+  }
+  if (lane == 0) {
+    if (fm == 0u) {  // no finite point: an infinite box is never culled and never "all in"
+      bounds[2 * warp] = make_float4(0.f, 0.f, 0.f, 0.f);
+      bounds[2 * warp + 1] = make_float4(CUDART_INF_F, CUDART_INF_F, CUDART_INF_F, 0.f);
+    } else {
+      bounds[2 * warp] = make_float4(c[0], c[1], c[2], (float)__popc(fm));
+      bounds[2 * warp + 1] = make_float4(e[0], e[1], e[2], 0.f);
+    }
+  }
+}
+
+void launch_block_bounds(CloudView sorted, size_t n, float4* bounds, cudaStream_t s) {
+  const size_t n_blocks = (n + 31) / 32;
+  if (n_blocks == 0) return;
+  const size_t ctas = (n_blocks * 32 + 255) / 256;
+  block_bounds_kernel<<<(unsigned)ctas, 256, 0, s>>>(sorted.x, sorted.y, sorted.z, n_blocks, bounds);
+}
+
+// per hypothesis: (t + margin, t - margin)
+__global__ void __launch_bounds__(128) hier_prepare_kernel(const float4* __restrict__ hyps, int K, float t, float cmax,
+                                                           float2* __restrict__ aux) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= K) return;
+  const float4 h = hyps[k];
+  const float m = __fmaf_ru(__fadd_ru(__fadd_ru(fabsf(h.x), fabsf(h.y)), fabsf(h.z)), cmax, fabsf(h.w));
+  const float margin = __fmul_ru(2e-6f, m);
+  aux[k] = make_float2(__fadd_ru(t, margin), __fsub_rd(t, margin));
+}
+
+constexpr int kHierMaxK = 4096;  // hypotheses per launch chunk (shared-memory counters, 16-bit queue entries)
+
+// Per tile of 1024 sorted points (32 blocks), hypotheses in phases of CH:
+//   A1  lane <-> hypothesis: test the tile's box; most hypotheses miss the whole tile.
+//   A2  per surviving hypothesis, lane <-> block: test the 32 block boxes; a hit appends the hypothesis
+//       to that block's queue (shared memory), an "all in" adds the block's point count.
+//   B   per block queue, 32 queued hypotheses at a time, lane <-> hypothesis: the block's 32 points are
+//       broadcast from shared memory and evaluated exactly like K2 (FFMA2 / FSET.BF / IADD3); warps
+//       take blocks from a shared ticket so uneven queues balance.
+// Phase B therefore runs at brute-force efficiency, but only on the (block, hypothesis) pairs whose box
+// straddles the threshold slab (a few per cent on the indoor scenes).
+// Dynamic shared memory: points 12 KB | counters 4 * kHierMaxK | queues 32 * CH * 2 | heads.
+template <int DOT, int CH>
+__global__ void __launch_bounds__(256, CH >= 1024 ? 2 : 3)
+    score_hier_kernel(const float* __restrict__ SX, const float* __restrict__ SY, const float* __restrict__ SZ,
+                      const float4* __restrict__ bounds, size_t n_blocks, int n_tiles, int tiles_per_cta,
+                      const float4* __restrict__ hyps, const float2* __restrict__ aux, int K, float t,
+                      int32_t* __restrict__ counts) {
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  float* s_x = reinterpret_cast<float*>(s_raw);
+  float* s_y = s_x + kTilePoints;
+  float* s_z = s_y + kTilePoints;
+  int* s_cnt = reinterpret_cast<int*>(s_z + kTilePoints);
+  unsigned short* s_q = reinterpret_cast<unsigned short*>(s_cnt + kHierMaxK);  // [32][CH]
+  int* s_qn = reinterpret_cast<int*>(s_q + 32 * CH);                           // [32] heads + [1] ticket
+  int* s_ticket = s_qn + 32;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int k_begin = blockIdx.y * kHierMaxK;
+  const int k_cnt = min(K - k_begin, kHierMaxK);
+  const int tile_begin = blockIdx.x * tiles_per_cta;
+  const int tile_end = min(n_tiles, tile_begin + tiles_per_cta);
+  if (tile_begin >= tile_end) return;
+  for (int i = threadIdx.x; i < k_cnt; i += blockDim.x) s_cnt[i] = 0;
+  if (threadIdx.x < 33) s_qn[threadIdx.x] = 0;
+
+  for (int tile = tile_begin; tile < tile_end; ++tile) {
+    __syncthreads();  // previous tile fully consumed; counters / queue heads initialised
+    {
+      const size_t base = (size_t)tile * kTilePoints;  // 256 threads x one float4 per plane
+      reinterpret_cast<float4*>(s_x)[threadIdx.x] = __ldg(reinterpret_cast<const float4*>(SX + base) + threadIdx.x);
+      reinterpret_cast<float4*>(s_y)[threadIdx.x] = __ldg(reinterpret_cast<const float4*>(SY + base) + threadIdx.x);
+      reinterpret_cast<float4*>(s_z)[threadIdx.x] = __ldg(reinterpret_cast<const float4*>(SZ + base) + threadIdx.x);
+    }
+    // lane <-> block of this tile
+    const size_t blk = (size_t)tile * 32 + lane;
+    const bool have = blk < n_blocks;
+    float4 bc = make_float4(0.f, 0.f, 0.f, 0.f), be = make_float4(CUDART_INF_F, CUDART_INF_F, CUDART_INF_F, 0.f);
+    if (have) {
+      bc = __ldg(&bounds[2 * blk]);
+      be = __ldg(&bounds[2 * blk + 1]);
+    }
+    // the tile's box from its block boxes (upper bounds rounded up, lower bounds rounded down)
+    float tc[3], te[3];
+    {
+      const float cs[3] = {bc.x, bc.y, bc.z}, es[3] = {be.x, be.y, be.z};
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        float lo = have ? __fsub_rd(cs[a], es[a]) : CUDART_INF_F;
+        float hi = have ? __fadd_ru(cs[a], es[a]) : -CUDART_INF_F;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          lo = fminf(lo, __shfl_xor_sync(0xFFFFFFFFu, lo, o));
+          hi = fmaxf(hi, __shfl_xor_sync(0xFFFFFFFFu, hi, o));
+        }
+        tc[a] = 0.5f * lo + 0.5f * hi;
+        te[a] = fmaxf(__fsub_ru(hi, tc[a]), __fsub_ru(tc[a], lo));
+      }
+    }
+    __syncthreads();
+
+    for (int cb = 0; cb < k_cnt; cb += CH) {
+      const int c_end = min(k_cnt, cb + CH);
+      // ---- phase A: warp w takes hypotheses cb + 32 * (w + 8 i) ----
+      for (int kb = cb + warp * 32; kb < c_end; kb += 256) {
+        const int kl = kb + lane;
+        float4 h = make_float4(CUDART_NAN_F, CUDART_NAN_F, CUDART_NAN_F, CUDART_NAN_F);
+        float2 th = make_float2(CUDART_NAN_F, CUDART_NAN_F);
+        if (kl < c_end) {
+          h = __ldg(&hyps[k_begin + kl]);
+          th = __ldg(&aux[k_begin + kl]);
+        }
+        // A1: tile box.  A miss needs a decisive test; NaN hypotheses fall through (and hit nothing point-wise)
+        const float trc = __fmaf_rn(h.x, tc[0], __fmaf_rn(h.y, tc[1], __fmaf_rn(h.z, tc[2], h.w)));
+        const float trho = __fmaf_rn(fabsf(h.x), te[0], __fmaf_rn(fabsf(h.y), te[1], __fmul_rn(fabsf(h.z), te[2])));
+        unsigned alive = __ballot_sync(0xFFFFFFFFu, kl < c_end && !((fabsf(trc) - trho) > th.x));
+        // A2: surviving hypotheses against the 32 block boxes
+        while (alive) {
+          const int src = __ffs(alive) - 1;
+          alive &= alive - 1;
+          const float ha = __shfl_sync(0xFFFFFFFFu, h.x, src), hb = __shfl_sync(0xFFFFFFFFu, h.y, src);
+          const float hc = __shfl_sync(0xFFFFFFFFu, h.z, src), hd = __shfl_sync(0xFFFFFFFFu, h.w, src);
+          const float t_out = __shfl_sync(0xFFFFFFFFu, th.x, src), t_in = __shfl_sync(0xFFFFFFFFu, th.y, src);
+          const float rc = __fmaf_rn(ha, bc.x, __fmaf_rn(hb, bc.y, __fmaf_rn(hc, bc.z, hd)));
+          const float rho = __fmaf_rn(fabsf(ha), be.x, __fmaf_rn(fabsf(hb), be.y, __fmul_rn(fabsf(hc), be.z)));
+          const bool out = (fabsf(rc) - rho) > t_out;
+          const bool ain = (fabsf(rc) + rho) < t_in;
+          const int q = kb + src;  // launch-chunk-local hypothesis index
+          if (have && ain) {
+            atomicAdd(&s_cnt[q], (int)bc.w);
+          } else if (have && !out) {
+            const int pos = atomicAdd(&s_qn[lane], 1);  // < CH: a hypothesis enters a block's queue at most once
+            s_q[lane * CH + pos] = (unsigned short)q;
+          }
+        }
+      }
+      __syncthreads();
+
+      // ---- phase B: blocks handed out by ticket; 32 queued hypotheses at a time, lane <-> hypothesis ----
+      while (true) {
+        int b = 0;
+        if (lane == 0) b = atomicAdd(s_ticket, 1);
+        b = __shfl_sync(0xFFFFFFFFu, b, 0);
+        if (b >= 32) break;
+        const int nq = s_qn[b];
+        const float* bx = s_x + b * 32;
+        const float* by = s_y + b * 32;
+        const float* bz = s_z + b * 32;
+        for (int g = 0; g < nq; g += 32) {
+          const bool valid = g + lane < nq;
+          const int q = valid ? (int)s_q[b * CH + g + lane] : 0;
+          float4 hq = make_float4(CUDART_NAN_F, CUDART_NAN_F, CUDART_NAN_F, CUDART_NAN_F);
+          if (valid) hq = __ldg(&hyps[k_begin + q]);
+          unsigned acc = 0u;
+#pragma unroll
+          for (int s4 = 0; s4 < 8; ++s4) {
+            const float4 x4 = *reinterpret_cast<const float4*>(bx + 4 * s4);
+            const float4 y4 = *reinterpret_cast<const float4*>(by + 4 * s4);
+            const float4 z4 = *reinterpret_cast<const float4*>(bz + 4 * s4);
+            const float2 ra = plane_dot2<DOT>(hq.x, hq.y, hq.z, hq.w, make_float2(x4.x, x4.y), make_float2(y4.x, y4.y),
+                                              make_float2(z4.x, z4.y));
+            const float2 rb = plane_dot2<DOT>(hq.x, hq.y, hq.z, hq.w, make_float2(x4.z, x4.w), make_float2(y4.z, y4.w),
+                                              make_float2(z4.z, z4.w));
+            float f0, f1, f2, f3;
+            asm("set.lt.f32.f32 %0, %1, %2;" : "=f"(f0) : "f"(fabsf(ra.x)), "f"(t));
+            asm("set.lt.f32.f32 %0, %1, %2;" : "=f"(f1) : "f"(fabsf(ra.y)), "f"(t));
+            asm("set.lt.f32.f32 %0, %1, %2;" : "=f"(f2) : "f"(fabsf(rb.x)), "f"(t));
+            asm("set.lt.f32.f32 %0, %1, %2;" : "=f"(f3) : "f"(fabsf(rb.y)), "f"(t));
+            acc = acc + __float_as_uint(f0) + __float_as_uint(f1);
+            acc = acc + __float_as_uint(f2) + __float_as_uint(f3);
+          }
+          const int c = (int)(((acc >> 23) * 383u) & 511u);  // <= 32 increments: no wrap
+          if (valid && c) atomicAdd(&s_cnt[q], c);
+        }
+      }
+      __syncthreads();
+      if (threadIdx.x < 33) s_qn[threadIdx.x] = 0;  // heads + ticket
+      __syncthreads();
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < k_cnt; i += blockDim.x) {
+    const int v = s_cnt[i];
+    if (v) atomicAdd(&counts[k_begin + i], v);
+  }
+}
+
+template <int DOT, int CH>
+static void launch_score_hier_t(dim3 grid, const float* SX, const float* SY, const float* SZ, const float4* bounds,
+                                size_t n_blocks, int n_tiles, int tiles_per_cta, const float4* hyps, const float2* aux,
+                                int K, float t, int32_t* counts, cudaStream_t s) {
+  const size_t smem = 3 * kTilePoints * sizeof(float) + kHierMaxK * sizeof(int) + 32 * CH * sizeof(unsigned short) + 33 * sizeof(int);
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(score_hier_kernel<DOT, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    configured = true;
+  }
+  score_hier_kernel<DOT, CH><<<grid, 256, smem, s>>>(SX, SY, SZ, bounds, n_blocks, n_tiles, tiles_per_cta, hyps, aux, K, t, counts);
+}
+
+int launch_score_hier(CloudView sorted, size_t n, const float4* bounds, const float4* hyps, float2* aux, int K, float t,
+                      float cmax, int dot_order, int32_t* counts, int num_sms, cudaStream_t s) {
+  if (K <= 0 || n == 0) return 0;
+  hier_prepare_kernel<<<(K + 127) / 128, 128, 0, s>>>(hyps, K, t, cmax, aux);
+  const int n_tiles = (int)((n + kTilePoints - 1) / kTilePoints);
+  const size_t n_blocks = (n + 31) / 32;
+  const int chunks = (K + kHierMaxK - 1) / kHierMaxK;
+  static const int ch_knob = [] { const char* e = getenv("PR_HIER_CH"); return e ? atoi(e) : 512; }();  // tuning knob (phase size: 256, 512 or 1024 hypotheses)
+  const int per_sm = ch_knob >= 1024 ? 2 : 3;
+  int gx = per_sm * num_sms / chunks;
+  if (gx < 1) gx = 1;
+  if (gx > n_tiles) gx = n_tiles;
+  const int tiles_per_cta = (n_tiles + gx - 1) / gx;
+  gx = (n_tiles + tiles_per_cta - 1) / tiles_per_cta;
+  dim3 grid(gx, chunks);
+#define PR_HIER(D, C) launch_score_hier_t<D, C>(grid, sorted.x, sorted.y, sorted.z, bounds, n_blocks, n_tiles, tiles_per_cta, hyps, aux, K, t, counts, s)
+  if (dot_order == 1) {
+    if (ch_knob >= 1024) PR_HIER(1, 1024); else if (ch_knob >= 512) PR_HIER(1, 512); else PR_HIER(1, 256);
+  } else {
+    if (ch_knob >= 1024) PR_HIER(0, 1024); else if (ch_knob >= 512) PR_HIER(0, 512); else PR_HIER(0, 256);
+  }
+#undef PR_HIER
+  return 2;
+}
+
 // ------------------------------------------------------------------------------------------------
 // K3: refit moments.  One predicated pass over the cloud; inliers are quantised to a 2^-s grid about
 // the pivot and their first and second moments summed as exact integers (second moments split into
@@ -914,7 +1240,7 @@ __global__ void __launch_bounds__(kCompactThreads, 5)
       DX[excl + j] = s_x[j];
       DY[excl + j] = s_y[j];
       DZ[excl + j] = s_z[j];
-      DO[excl + j] = s_o[j];
+      if (DO != nullptr) DO[excl + j] = s_o[j];
     }
   }
   for (int j = threadIdx.x; j < inl_total; j += kCompactThreads) {

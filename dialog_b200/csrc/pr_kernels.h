@@ -67,6 +67,15 @@ void launch_models(const int4* sample_pts, int n_models_total, float4* hyps, int
 int launch_score(CloudView cloud, size_t n_per_cloud, int n_clouds, size_t cloud_stride, const float4* hyps,
                  int K, float t, int dot_order, int32_t* counts, int num_sms, cudaStream_t s);
 
+// Hierarchical scorer: Morton-sorted copy of a cloud, per-32-point-block boxes, culled scoring with counts
+// identical to launch_score.  keys / vals: 2*n uint32 each; temp: sort_temp_bytes(n); bounds: 2 float4 per block.
+size_t sort_temp_bytes(size_t n);
+void launch_morton_sort(CloudView src, size_t n, const float lo[3], float extent, uint32_t* keys, uint32_t* vals, void* temp,
+                        size_t temp_bytes, CloudView dst, cudaStream_t s);
+void launch_block_bounds(CloudView sorted, size_t n, float4* bounds, cudaStream_t s);
+int launch_score_hier(CloudView sorted, size_t n, const float4* bounds, const float4* hyps, float2* aux, int K, float t,
+                      float cmax, int dot_order, int32_t* counts, int num_sms, cudaStream_t s);
+
 // K3: inlier predicate with hyps[model_index] + exact integer moments about the model's first sample point.
 // out must be zeroed.  sample_pts supplies the pivot (sample_pts[3 * model_index]).
 void launch_refit(CloudView cloud, size_t n, const float4* hyps, const int4* sample_pts, int model_index, float t,

@@ -66,6 +66,7 @@ class PlaneDetectRansac {
   void setOptimizeCoefficients(bool on) { prm_.optimize_coefficients = on ? 1 : 0; }
   void setMaxPlanes(int n) { prm_.max_planes = n; }
   void setDotOrder(int order) { prm_.dot_order = order; }
+  void setScorer(int scorer) { prm_.scorer = scorer; }
   const pr_params& params() const { return prm_; }
 
   // cloud in, planes out; `cloud` is replaced by the points no plane claimed (original order).

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define PLANE_RANSAC_ABI_VERSION 1
+#define PLANE_RANSAC_ABI_VERSION 2
 
 typedef struct plane_ransac_ctx plane_ransac_ctx;
 
@@ -55,6 +55,14 @@ typedef enum {
  * The two differ only for points whose residual is within rounding of the threshold. */
 enum { PR_DOT_PCL_SSE2 = 0, PR_DOT_FMA = 1 };
 
+/* How countWithinDistance is evaluated for the batch of hypotheses.  Both give identical counts.
+ *   PR_SCORER_BRUTE  every hypothesis against every point (the FP32-FMA-bound kernel; default).
+ *   PR_SCORER_HIER   a Morton-sorted copy of the cloud with a bounding box per 32 points: blocks whose box lies
+ *                    outside (or entirely inside) the threshold slab of a hypothesis are skipped (or counted
+ *                    whole); the rest are evaluated point by point with the same arithmetic.  Costs one sort per
+ *                    staged cloud and a second compaction per peel round; not used by the batch entry points. */
+enum { PR_SCORER_BRUTE = 0, PR_SCORER_HIER = 1 };
+
 /* pcl::SACSegmentation knobs + the peel stop rule. */
 typedef struct {
   double distance_threshold;  /* setDistanceThreshold(double); inlier iff |n·p + d| <  t (strict) */
@@ -65,6 +73,7 @@ typedef struct {
   unsigned seed;              /* 12345u = PCL's non-random SampleConsensusModel seed             */
   int max_planes;             /* bound on planes returned by plane_ransac_extract_planes         */
   int dot_order;              /* PR_DOT_*                                                         */
+  int scorer;                 /* PR_SCORER_*: how the inlier counts are computed (same counts either way) */
 } pr_params;
 
 /* What one segment() call decided (mirrors RandomSampleConsensus state; used by parity tests). */
@@ -104,7 +113,7 @@ typedef struct {
 /* ---- lifetime ---------------------------------------------------------------------------- */
 int plane_ransac_abi_version(void);
 const char* plane_ransac_last_error(void);
-void plane_ransac_default_params(pr_params* p); /* t=0.1, it=50, min=500, p=0.99, refit, 12345, 64, FMA */
+void plane_ransac_default_params(pr_params* p); /* t=0.1, it=50, min=500, p=0.99, refit, 12345, 64, FMA, brute */
 int plane_ransac_create(plane_ransac_ctx** ctx, int device_id);
 void plane_ransac_destroy(plane_ransac_ctx* ctx);
 

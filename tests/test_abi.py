@@ -29,12 +29,12 @@ def test_header_symbols_are_exported(lib_built):
 def test_abi_version_and_defaults(lib_built):
     from dialog_b200 import _lib
     L = _lib.load()
-    assert L.plane_ransac_abi_version() == 1
+    assert L.plane_ransac_abi_version() == 2
     p = _lib.PrParams()
     L.plane_ransac_default_params(ctypes.byref(p))
     # Dialog/config.txt:29 T_dist_point_plane, :20 T_num_of_single_plane; PCL SACSegmentation defaults
     assert (p.distance_threshold, p.max_iterations, p.min_plane_size, p.probability) == (0.1, 50, 500, 0.99)
-    assert (p.optimize_coefficients, p.seed, p.dot_order) == (1, 12345, _lib.DOT_FMA)
+    assert (p.optimize_coefficients, p.seed, p.dot_order, p.scorer) == (1, 12345, _lib.DOT_FMA, _lib.SCORER_BRUTE)
 
 
 def test_library_does_not_link_the_oracle_or_need_nccl_at_load(lib_built):

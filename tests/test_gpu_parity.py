@@ -411,3 +411,69 @@ def test_plane_points_and_projection_match_oracle(O, pr, scene2):
         assert np.abs(r).max() < 1e-4
     with pytest.raises(D.PlaneRansacError):
         pr.plane_points(3)
+
+
+# ---------------------------------------------------------------------------------------------
+# hierarchical scorer (PR_SCORER_HIER): identical results, fewer evaluations
+# ---------------------------------------------------------------------------------------------
+def _extract_both(pr, pts, **kw):
+    import dialog_b200 as D
+    pr.set_cloud(pts)
+    a = pr.extract_planes(D.make_params(scorer=D.SCORER_BRUTE, **kw))
+    ra = pr.remaining().copy()
+    b = pr.extract_planes(D.make_params(scorer=D.SCORER_HIER, **kw))
+    rb = pr.remaining().copy()
+    assert len(a.planes) == len(b.planes)
+    for p, q in zip(a.planes, b.planes):
+        assert _same_bits(p.coeff, q.coeff)
+        assert p.info.best_count == q.info.best_count and list(p.info.best_sample) == list(q.info.best_sample)
+        assert p.inliers_orig.size == q.inliers_orig.size and (p.inliers_orig == q.inliers_orig).all()
+    assert ra.tobytes() == rb.tobytes()
+    return a
+
+
+@pytest.mark.parametrize("order", [0, 1])
+def test_hier_scorer_matches_brute_and_oracle(O, pr, scene2, scene3, order):
+    import dialog_b200 as D
+    pts = scene3.points(0, 300_000)
+    ex = _extract_both(pr, pts, distance_threshold=0.1, max_iterations=511, min_plane_size=500, probability=1.0,
+                       max_planes=20, dot_order=order)
+    assert len(ex.planes) == 20
+    _check_extract(O, pr, scene2.points(0, 150_000),
+                   D.make_params(0.1, 255, 5000, 1.0, True, 12345, 8, order, D.SCORER_HIER))
+    _check_segment(O, pr, scene2.points(0, 60_000), D.make_params(0.1, 50, 500, 0.99, True, 12345, 8, order, D.SCORER_HIER))
+
+
+def test_hier_scorer_adversarial_clouds(O, pr):
+    """Cases built to stress the box test: far from the origin (large rounding), points sitting exactly on the
+    threshold, flat and degenerate boxes, NaN/Inf points, fewer points than one block, sizes off the tile grid."""
+    import dialog_b200 as D
+    rng = np.random.default_rng(11)
+    n = 50_001
+    xy = rng.uniform(-20, 20, size=(n, 2))
+    z = np.where(rng.random(n) < 0.5, 0.0, rng.choice([0.1, -0.1, 0.099999994, 0.100000001, 0.2, -0.3], n))
+    base = np.c_[xy, z].astype(np.float32)
+    clouds = {
+        "on_threshold": base,
+        "offset_4km": base + np.float32(4096.0),
+        "tiny_scale": (base * np.float32(1e-3)),
+        "with_nonfinite": base.copy(),
+        "small": base[:17],
+        "one_block": base[:32],
+        "grid": np.stack(np.meshgrid(np.arange(40), np.arange(40), np.arange(3)), -1).reshape(-1, 3).astype(np.float32) * 0.05,
+    }
+    clouds["with_nonfinite"][::53, 1] = np.nan
+    clouds["with_nonfinite"][7::97, 0] = np.inf
+    for name, pts in clouds.items():
+        t = 1e-4 if name == "tiny_scale" else 0.1
+        for order in (0, 1):
+            _extract_both(pr, pts, distance_threshold=t, max_iterations=127, min_plane_size=5, probability=1.0,
+                          max_planes=4, dot_order=order)
+            pr.set_cloud(pts)
+            prm = D.make_params(t, 63, 5, 0.99, True, 12345, 4, order, D.SCORER_HIER)
+            coeff, inl, info = pr.segment_one(prm)
+            seg = O.segment(pts, _oparams(O, prm))
+            assert bool(info.ok) == seg.ok and info.iterations == seg.trace.iterations, name
+            if seg.ok:
+                assert info.best_count == seg.trace.best_count, name
+                assert _same_bits(coeff, seg.coeff) and (inl == seg.inliers).all(), name
