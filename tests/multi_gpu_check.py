@@ -49,6 +49,11 @@ def main():
         assert a.info.n_inliers == b.info.n_inliers and list(a.info.best_sample) == list(b.info.best_sample)
         mine = b.inliers_orig[(b.inliers_orig >= first) & (b.inliers_orig < first + count)] - first
         assert (a.inliers_orig == mine).all(), f"plane {k}: inlier set differs on rank {rank}"
+    # the hierarchical scorer, sharded: every rank culls on its own Morton-sorted shard, same global answer
+    got_h = sh.extract_planes(D.make_params(0.1, 1023, 500, 1.0, True, 12345, 20, D.DOT_FMA, D.SCORER_HIER))
+    assert len(got_h.planes) == len(want.planes)
+    for k, (a, b) in enumerate(zip(got_h.planes, got.planes)):
+        assert a.coeff.tobytes() == b.coeff.tobytes() and (a.inliers_orig == b.inliers_orig).all(), f"hier plane {k}"
     rem = sh.remaining()
     claimed = np.zeros(n, bool)
     claimed[np.concatenate([p.inliers_orig for p in want.planes])] = True
