@@ -545,6 +545,7 @@ int segment_core(plane_ransac_ctx* c, const pr_params* prm, pr::CloudView src, s
   int total_draws = 0;
   if (n_global >= 3 && !replay.done()) {
     pr::IndexSampler sampler((size_t)n_global, prm->seed);
+    sampler.reserve((size_t)std::min<long long>((long long)prm->max_iterations + 1, 1 << 20));
     int prev_batch = 0;
     while (!replay.done()) {
       const long long trials_left = (long long)prm->max_iterations + 1 - replay.iterations();
@@ -561,10 +562,11 @@ int segment_core(plane_ransac_ctx* c, const pr_params* prm, pr::CloudView src, s
       PR_TRY(reserve_draws(c, (size_t)total_draws + (size_t)B, total_draws > 0));
       // The batch is issued in sub-batches so that the host draws the next triples (a sequential
       // permutation walk, ~0.1 us per draw) while the device is already scoring the previous ones.
-      // Two sub-batches: the first is just large enough that scoring it (~N / 6.5e12 s per hypothesis)
-      // takes the device as long as drawing the rest takes the host (~0.12 us per draw); fewer, larger
+      // Two sub-batches: the first is just large enough that scoring it (~N / 6.5e12 s per hypothesis, ~3x less
+      // with the hierarchical scorer)
+      // takes the device as long as drawing the rest takes the host (~0.08 us per draw); fewer, larger
       // launches score more efficiently and, when sharded, need fewer collectives.
-      const double dev_s_per_hyp = (double)std::max<size_t>(n_local, 1) / 6.5e12, host_s_per_draw = 1.2e-7;
+      const double dev_s_per_hyp = (double)std::max<size_t>(n_local, 1) / (hier ? 2.0e13 : 6.5e12), host_s_per_draw = 8e-8;
       long long first_sb = 256;
       while (first_sb < B && (double)first_sb < (double)B * host_s_per_draw / (dev_s_per_hyp + host_s_per_draw)) first_sb *= 2;
       long long prev_sb = 0;
@@ -1385,6 +1387,7 @@ int plane_ransac_host_draw_triples(size_t n_points, unsigned seed, int n_draws, 
   if (n_points < 3) return fail(PR_ERR_INVALID, "need at least 3 points to sample");
   if (n_draws < 0 || (n_draws && !triples)) return fail(PR_ERR_INVALID, "bad n_draws/triples");
   pr::IndexSampler s(n_points, seed);
+  s.reserve((size_t)n_draws);
   for (int k = 0; k < n_draws; ++k) s.draw(triples + 3 * (size_t)k);
   return PR_OK;
 }

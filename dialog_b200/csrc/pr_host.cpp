@@ -44,6 +44,15 @@ IndexSampler::IndexSampler(size_t n, uint32_t seed) : rng_(seed), n_(n) {
   mask_ = (1u << 12) - 1;
 }
 
+void IndexSampler::reserve(size_t draws) {
+  uint32_t cap = mask_ + 1;
+  while ((size_t)cap < draws * 3 * 4 && cap < (1u << 28)) cap <<= 1;  // load factor <= 1/4
+  if (cap == mask_ + 1 || used_ != 0) return;
+  keys_.assign(cap, kEmptyKey);
+  vals_.assign(cap, 0);
+  mask_ = cap - 1;
+}
+
 static inline uint32_t hash_index(uint32_t k) { return (k * 2654435761u) >> 7; }
 
 int32_t IndexSampler::get(uint32_t j) const {

@@ -28,6 +28,8 @@ class IndexSampler {
  public:
   IndexSampler(size_t n, uint32_t seed);
   void draw(int32_t out[3]);
+  // Size the table for this many draws up front (each draw touches up to three entries).
+  void reserve(size_t draws);
   size_t size() const { return n_; }
 
  private:

@@ -252,6 +252,13 @@ def test_properties_at_10m_points(O, pr, scene3):
     for p in ex.planes:
         assert (np.diff(p.inliers_cur) > 0).all() and (np.diff(p.inliers_orig) > 0).all()
         assert p.info.n_inliers == p.inliers_cur.size and p.info.n_scored == 4096
+    # the hierarchical scorer finds exactly the same 20 planes at this size
+    exh = pr.extract_planes(D.make_params(0.1, 4095, 500, 1.0, True, 12345, 20, D.DOT_FMA, D.SCORER_HIER))
+    assert len(exh.planes) == 20
+    for a, b in zip(exh.planes, ex.planes):
+        assert _same_bits(a.coeff, b.coeff) and a.info.best_count == b.info.best_count
+        assert np.array_equal(a.inliers_orig, b.inliers_orig)
+    assert pr.remaining().tobytes() == rem.tobytes()
     # round 0 against the oracle on a sample of hypotheses: counts of the winning and 7 other draws
     tri = O.draw_sequence(n, 4096)
     pick = np.r_[[np.nonzero((tri == list(ex.planes[0].info.best_sample)).all(1))[0][0]], np.arange(7)]
