@@ -737,7 +737,9 @@ constexpr int kHierMaxK = 4096;  // hypotheses per launch chunk (shared-memory c
 //       take blocks from a shared ticket so uneven queues balance.
 // Phase B therefore runs at brute-force efficiency, but only on the (block, hypothesis) pairs whose box
 // straddles the threshold slab (a few per cent on the indoor scenes).
-// Dynamic shared memory: points 12 KB | counters 4 * kHierMaxK | queues 32 * CH * 2 | heads.
+// Queue entries that do not fill a group of 32 are carried into the tile's next phase, so lanes idle only
+// in the last phase of a tile.
+// Dynamic shared memory: points 12 KB | counters 4 * kHierMaxK | queues 32 * (CH + 32) * 2 | heads.
 template <int DOT, int CH>
 __global__ void __launch_bounds__(256, CH >= 1024 ? 2 : 3)
     score_hier_kernel(const float* __restrict__ SX, const float* __restrict__ SY, const float* __restrict__ SZ,
@@ -749,8 +751,9 @@ __global__ void __launch_bounds__(256, CH >= 1024 ? 2 : 3)
   float* s_y = s_x + kTilePoints;
   float* s_z = s_y + kTilePoints;
   int* s_cnt = reinterpret_cast<int*>(s_z + kTilePoints);
-  unsigned short* s_q = reinterpret_cast<unsigned short*>(s_cnt + kHierMaxK);  // [32][CH]
-  int* s_qn = reinterpret_cast<int*>(s_q + 32 * CH);                           // [32] heads + [1] ticket
+  constexpr int CAP = CH + 32;  // per-block queue capacity: a phase's hits plus the carried remainder
+  unsigned short* s_q = reinterpret_cast<unsigned short*>(s_cnt + kHierMaxK);  // [32][CAP]
+  int* s_qn = reinterpret_cast<int*>(s_q + 32 * CAP);                          // [32] heads + [1] ticket
   int* s_ticket = s_qn + 32;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int k_begin = blockIdx.y * kHierMaxK;
@@ -826,8 +829,8 @@ __global__ void __launch_bounds__(256, CH >= 1024 ? 2 : 3)
           if (have && ain) {
             atomicAdd(&s_cnt[q], (int)bc.w);
           } else if (have && !out) {
-            const int pos = atomicAdd(&s_qn[lane], 1);  // < CH: a hypothesis enters a block's queue at most once
-            s_q[lane * CH + pos] = (unsigned short)q;
+            const int pos = atomicAdd(&s_qn[lane], 1);  // < CAP: at most CH new entries per phase + < 32 carried
+            s_q[lane * CAP + pos] = (unsigned short)q;
           }
         }
       }
@@ -840,12 +843,14 @@ __global__ void __launch_bounds__(256, CH >= 1024 ? 2 : 3)
         b = __shfl_sync(0xFFFFFFFFu, b, 0);
         if (b >= 32) break;
         const int nq = s_qn[b];
+        const bool last_phase = cb + CH >= k_cnt;
+        const int n_go = last_phase ? nq : (nq & ~31);  // full groups only, except in the tile's last phase
         const float* bx = s_x + b * 32;
         const float* by = s_y + b * 32;
         const float* bz = s_z + b * 32;
-        for (int g = 0; g < nq; g += 32) {
+        for (int g = 0; g < n_go; g += 32) {
           const bool valid = g + lane < nq;
-          const int q = valid ? (int)s_q[b * CH + g + lane] : 0;
+          const int q = valid ? (int)s_q[b * CAP + g + lane] : 0;
           float4 hq = make_float4(CUDART_NAN_F, CUDART_NAN_F, CUDART_NAN_F, CUDART_NAN_F);
           if (valid) hq = __ldg(&hyps[k_begin + q]);
           unsigned acc = 0u;
@@ -869,9 +874,16 @@ __global__ void __launch_bounds__(256, CH >= 1024 ? 2 : 3)
           const int c = (int)(((acc >> 23) * 383u) & 511u);  // <= 32 increments: no wrap
           if (valid && c) atomicAdd(&s_cnt[q], c);
         }
+        // carry the remainder (< 32 entries) to the front of the queue for the tile's next phase
+        const int rem = last_phase ? 0 : nq - n_go;
+        unsigned short keep = 0;
+        if (lane < rem) keep = s_q[b * CAP + n_go + lane];
+        __syncwarp();
+        if (lane < rem) s_q[b * CAP + lane] = keep;
+        if (lane == 0) s_qn[b] = rem;
       }
       __syncthreads();
-      if (threadIdx.x < 33) s_qn[threadIdx.x] = 0;  // heads + ticket
+      if (threadIdx.x == 0) *s_ticket = 0;
       __syncthreads();
     }
   }
@@ -886,7 +898,7 @@ template <int DOT, int CH>
 static void launch_score_hier_t(dim3 grid, const float* SX, const float* SY, const float* SZ, const float4* bounds,
                                 size_t n_blocks, int n_tiles, int tiles_per_cta, const float4* hyps, const float2* aux,
                                 int K, float t, int32_t* counts, cudaStream_t s) {
-  const size_t smem = 3 * kTilePoints * sizeof(float) + kHierMaxK * sizeof(int) + 32 * CH * sizeof(unsigned short) + 33 * sizeof(int);
+  const size_t smem = 3 * kTilePoints * sizeof(float) + kHierMaxK * sizeof(int) + 32 * (CH + 32) * sizeof(unsigned short) + 33 * sizeof(int);
   static bool configured = false;
   if (!configured) {
     cudaFuncSetAttribute(score_hier_kernel<DOT, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
