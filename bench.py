@@ -311,7 +311,6 @@ def main():
     hier_same = None
     if args.scorer == "brute":
         prm_h = D.make_params(0.1, args.hyps - 1, 500, 1.0, True, 12345, args.planes, D.DOT_FMA, D.SCORER_HIER)
-        pr.set_cloud_ptr(pinned.data_ptr(), count)
         for _ in range(2):
             exh = pr.extract_planes(prm_h, want_indices=False)
         barrier()

@@ -551,7 +551,7 @@ int segment_core(plane_ransac_ctx* c, const pr_params* prm, pr::CloudView src, s
       const long long trials_left = (long long)prm->max_iterations + 1 - replay.iterations();
       long long B;
       if (prm->probability >= 1.0) {
-        B = trials_left;
+        B = std::min<long long>(trials_left, 1 << 20);  // score-all mode: at most 1M hypotheses per device batch
       } else if (prev_batch == 0) {
         B = std::min<long long>(trials_left, 256);
       } else {
