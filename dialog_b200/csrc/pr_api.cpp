@@ -187,6 +187,7 @@ struct plane_ransac_ctx {
   cudaEvent_t timer_a = nullptr, timer_b = nullptr;
   bool profiling = false;
   std::vector<TimedSpan> spans;
+  std::vector<cudaEvent_t> event_pool;  // recycled by collect_spans: event creation costs microseconds
   pr_profile prof;
 };
 
@@ -246,6 +247,17 @@ void pin_free(PinBuf<T>& b) {
   b.cap = 0;
 }
 
+cudaEvent_t take_event(plane_ransac_ctx* c) {
+  cudaEvent_t e = nullptr;
+  if (!c->event_pool.empty()) {
+    e = c->event_pool.back();
+    c->event_pool.pop_back();
+  } else {
+    cudaEventCreate(&e);
+  }
+  return e;
+}
+
 // RAII span: records CUDA events around a kernel class when profiling, and counts launches.
 struct Span {
   plane_ransac_ctx* c;
@@ -256,8 +268,8 @@ struct Span {
                                &c->prof.launches_refit, &c->prof.launches_compact, &c->prof.launches_other};
     *lc[k] += launches;
     if (c->profiling) {
-      cudaEventCreate(&a);
-      cudaEventCreate(&b);
+      a = take_event(c);
+      b = take_event(c);
       cudaEventRecord(a, c->stream);
     }
   }
@@ -277,8 +289,8 @@ void collect_spans(plane_ransac_ctx* c) {
   for (auto& s : c->spans) {
     float t = 0.f;
     if (cudaEventElapsedTime(&t, s.a, s.b) == cudaSuccess) *ms[s.cls] += t;
-    cudaEventDestroy(s.a);
-    cudaEventDestroy(s.b);
+    c->event_pool.push_back(s.a);
+    c->event_pool.push_back(s.b);
   }
   c->spans.clear();
 }
@@ -787,6 +799,7 @@ void plane_ransac_destroy(plane_ransac_ctx* c) {
   pin_free(c->h_triples); pin_free(c->h_counts); pin_free(c->h_good); pin_free(c->h_refit);
   pin_free(c->h_totals); pin_free(c->h_small);
   if (c->timer_a) { cudaEventDestroy(c->timer_a); cudaEventDestroy(c->timer_b); }
+  for (cudaEvent_t e : c->event_pool) cudaEventDestroy(e);
   cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -885,6 +898,7 @@ int plane_ransac_score(plane_ransac_ctx* c, const int32_t* triples, int K, doubl
 int plane_ransac_segment_one(plane_ransac_ctx* c, const pr_params* prm, float coeff[4], int32_t* inliers, size_t cap,
                              size_t* n_inliers, pr_segment_info* info) {
   PR_TRY(check_ctx(c));
+  if (c->profiling) collect_spans(c);  // stream is idle here: fold finished spans, recycle their events
   PR_TRY(check_params(prm));
   if (!c->have_cloud) return fail(PR_ERR_NO_CLOUD, "no cloud staged");
   if (!coeff || !n_inliers) return fail(PR_ERR_INVALID, "null output");
@@ -911,6 +925,7 @@ int plane_ransac_extract_planes(plane_ransac_ctx* c, const pr_params* prm, float
                                 int32_t* inlier_orig, size_t idx_cap, size_t* plane_offsets, int* n_planes,
                                 pr_segment_info* infos) {
   PR_TRY(check_ctx(c));
+  if (c->profiling) collect_spans(c);  // stream is idle here: fold finished spans, recycle their events
   PR_TRY(check_params(prm));
   if (!c->have_cloud) return fail(PR_ERR_NO_CLOUD, "no cloud staged");
   if (!coeffs || !plane_offsets || !n_planes) return fail(PR_ERR_INVALID, "null output");
