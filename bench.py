@@ -110,6 +110,14 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
+def ncu_traffic():
+    """DRAM bytes per launch of the scoring kernel from the committed ncu capture (profiles/r01_traffic.json)."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+    except Exception:
+        return None
+
+
 def measured_peaks():
     try:
         return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -360,7 +368,9 @@ def main():
                           "score_hier_kernel (culled: 'achieved' counts the point-hypotheses decided, not the FMAs executed, "
                           "so frac is not a pipe utilisation)",
                 "bound": "fp32_fma", "achieved": score_tf, "peak": peak_tf,
-                "unit": "TFLOP/s", "frac": (score_tf / peak_tf) if score_tf and peak_tf else None, "traffic": None,
+                "unit": "TFLOP/s", "frac": (score_tf / peak_tf) if score_tf and peak_tf else None,
+                "traffic": (ncu_traffic() or {}).get("score_kernel_dram_bytes_per_launch"),
+                "traffic_note": (ncu_traffic() or {}).get("note"),
                 "peak_source": "FFMA2-only kernel timed live on this GPU (MEASURED_PEAKS.json has no FP32 figure; "
                                "nominal 148 SM x 128 lanes x 2 x 1.965 GHz = 74.4)",
                 "algorithmic": "6 FLOP (3 FMA) per point-hypothesis x points x hypotheses per launch",
