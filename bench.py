@@ -192,6 +192,31 @@ def run_extras(args, pr):
     pairs = sum(int(i.n_cloud) * int(i.n_scored) for i in ex.infos)
     out["configs[1]_1M_3planes_K1024"] = {"ms_per_extraction": sum(ms) / len(ms), "planes": len(ex.planes),
                                           "point_hypotheses_per_s": pairs / (sum(ms) / len(ms) * 1e-3)}
+    # BASELINE.md plan (a): PCL-default adaptive mode (max_iterations=50, probability=0.99) end to end on the 10M-point
+    # scene, GPU through the C ABI vs the CPU oracle (1 thread, the PCL-faithful loop), same planes required
+    from oracle import oracle as O
+    pts10 = synth.indoor_scene().points(0, args.points)
+    prm = D.make_params(0.1, 50, 500, 0.99, True, 12345, args.planes, D.DOT_FMA)
+    pr.set_cloud(pts10)
+    for _ in range(2):
+        exd = pr.extract_planes(prm, want_indices=True, copy=False)
+    ms = []
+    for _ in range(3):
+        pr.flush_l2()
+        pr.timer_start()
+        pr.set_cloud(pts10)
+        exd = pr.extract_planes(prm, want_indices=True, copy=False)
+        ms.append(pr.timer_stop())
+    t0 = time.perf_counter()
+    want = O.extract_planes(pts10, O.make_params(0.1, 50, 500, 0.99, True, 12345, args.planes, O.DOT_FMA, O.REFIT_FIXED))
+    cpu_s = time.perf_counter() - t0
+    same = len(want.coeffs) == len(exd.planes) and all(
+        p.coeff.tobytes() == want.coeffs[k].tobytes() and np.array_equal(p.inliers_orig, want.inliers_orig[k])
+        for k, p in enumerate(exd.planes))
+    out["pcl_default_adaptive_10M_end_to_end"] = {
+        "gpu_ms": sum(ms) / len(ms), "cpu_oracle_s": cpu_s, "cpu_threads": 1, "planes": len(exd.planes),
+        "identical_to_cpu_oracle": bool(same), "speedup": cpu_s / (sum(ms) / len(ms) * 1e-3),
+        "note": "host cloud in, coefficients + inlier indices out; max_iterations=50, probability=0.99"}
     # configs[4]: batch of 32K-point clouds, one plane each, 256 hypotheses per cloud (slice of the 4096 clouds)
     nc = args.batch_clouds
     clouds = np.stack([synth.tile_scene(cid).points(0, 32768) for cid in range(nc)])
