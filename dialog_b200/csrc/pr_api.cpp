@@ -581,6 +581,7 @@ int segment_core(plane_ransac_ctx* c, const pr_params* prm, pr::CloudView src, s
       const double dev_s_per_hyp = (double)std::max<size_t>(n_local, 1) / (hier ? 2.0e13 : 6.5e12), host_s_per_draw = 8e-8;
       long long first_sb = 256;
       while (first_sb < B && (double)first_sb < (double)B * host_s_per_draw / (dev_s_per_hyp + host_s_per_draw)) first_sb *= 2;
+      while (first_sb * 4 < B) first_sb *= 2;  // launches below a quarter of the batch score a few per cent less efficiently
       long long prev_sb = 0;
       for (long long done = 0; done < B;) {
         long long sb = prev_sb == 0 ? std::min<long long>(B, first_sb) : B - done;
