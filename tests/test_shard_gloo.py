@@ -4,7 +4,8 @@ Each rank owns a contiguous shard (plane_ransac_host_shard_range).  The oracle s
 kernels (it is the checker, never the product): per-shard inlier counts are summed with an all-reduce,
 the sample points are exchanged as integer bit patterns (owner contributes, others zero), the library's
 replay picks the winner, per-shard integer moments are all-reduced and the library turns them into the
-plane.  Everything must equal the single-process oracle on the whole cloud, bit for bit."""
+plane.  Two peel rounds are run so that the per-rank prefix of the peeled cloud (global index = prefix + local index) is
+exercised.  Everything must equal the single-process oracle on the whole cloud, bit for bit."""
 import os
 import sys
 
@@ -28,55 +29,70 @@ def _worker(rank, world, port, n, q):
 
         pts = synth.three_planes_scene().points(0, n)
         first, count = D.host_shard_range(n, world, rank)
-        shard = pts[first: first + count]
-        K, t, max_it = 200, 0.1, 199
-
-        # 1. identical draw stream on every rank (global indices)
-        tri = D.host_draw_triples(n, K)
-        # 2. sample points: owner contributes the bits, others zero; integer sum == exact transfer
-        flat = tri.reshape(-1)
-        mine = (flat >= first) & (flat < first + count)
-        bits = np.zeros((flat.size, 3), np.int32)
-        bits[mine] = shard[flat[mine] - first, :3].view(np.int32)
-        tb = torch.from_numpy(bits)
-        dist.all_reduce(tb)
-        sample_pts = tb.numpy().view(np.float32)
-        assert sample_pts.tobytes() == pts[flat, :3].tobytes()
-        # 3. models from the gathered points (same on every rank), counts on the shard, all-reduce
-        cloud9 = np.ones((flat.size, 4), np.float32)
-        cloud9[:, :3] = sample_pts
-        coeffs, good = O.models_from_triples(cloud9, np.arange(flat.size, dtype=np.int32).reshape(-1, 3))
-        local = O.count_batch(shard, np.nan_to_num(coeffs), t, O.DOT_FMA)
-        tc = torch.from_numpy(local.copy())
-        dist.all_reduce(tc)
-        counts = tc.numpy()
-        counts[~good] = 0
-        # 4. the library replays PCL's sequential decisions over the summed counts
-        rep = D.host_replay(counts, good, n, max_it, 1.0)
-        best = rep["best_draw"]
-        # 5. refit: per-shard exact integer moments about the winner's first sample point, summed
-        s = O.fixed_scale_exp(pts)     # global bounding box (the device path all-reduces min/max keys)
-        pivot = sample_pts[3 * best]
-        idx = O.select_within(shard, coeffs[best], t, O.DOT_FMA)
-        _, mom = O.refit_fixed(shard, idx, pivot, s, coeffs[best])
-        if idx.size < 4:               # refit_fixed zeroes the moments of tiny shards; accumulate them anyway
-            mom = np.zeros(16, np.int64)
-        tm = torch.from_numpy(mom.copy())
-        dist.all_reduce(tm)
-        refined = D.host_plane_from_moments(tm.numpy(), pivot, s)
-        # 6. final selection on the shard; global inlier count by all-reduce
-        inl = O.select_within(shard, refined, t, O.DOT_FMA)
-        tn = torch.tensor([inl.size])
-        dist.all_reduce(tn)
-
-        # single-process oracle on the whole cloud
-        seg = O.segment(pts, O.make_params(t, max_it, 500, 1.0, True, 12345, 8, O.DOT_FMA, O.REFIT_FIXED))
-        assert tri[best].tolist() == list(seg.trace.best_sample)
-        assert counts[best] == seg.trace.best_count and rep["iterations"] == seg.trace.iterations
-        assert refined.tobytes() == seg.coeff.tobytes()
-        assert int(tn.item()) == seg.inliers.size
-        want_local = seg.inliers[(seg.inliers >= first) & (seg.inliers < first + count)] - first
-        assert (inl == want_local).all()
+        shard = pts[first: first + count]            # this rank's current cloud (peeled round by round)
+        K, t, max_it, rounds = 200, 0.1, 199, 2
+        s = O.fixed_scale_exp(pts)                   # global bounding box (the device path all-reduces min/max keys)
+        want = O.extract_planes(pts, O.make_params(t, max_it, 500, 1.0, True, 12345, rounds, O.DOT_FMA, O.REFIT_FIXED))
+        assert len(want.coeffs) == rounds
+        orig = np.arange(first, first + count)       # original index of every point still in the shard
+        n_cur = n
+        for rnd in range(rounds):
+            # global size and this rank's first global index in the CURRENT (peeled) cloud: all-gather of shard sizes
+            sizes = [torch.zeros(1, dtype=torch.int64) for _ in range(world)]
+            dist.all_gather(sizes, torch.tensor([shard.shape[0]], dtype=torch.int64))
+            sizes = [int(v.item()) for v in sizes]
+            n_cur, first_cur = sum(sizes), sum(sizes[:rank])
+            # 1. identical draw stream on every rank (indices into the current global cloud)
+            tri = D.host_draw_triples(n_cur, K)
+            # 2. sample points: owner contributes the bits, others zero; integer sum == exact transfer
+            flat = tri.reshape(-1)
+            mine = (flat >= first_cur) & (flat < first_cur + shard.shape[0])
+            bits = np.zeros((flat.size, 3), np.int32)
+            bits[mine] = shard[flat[mine] - first_cur, :3].view(np.int32)
+            tb = torch.from_numpy(bits)
+            dist.all_reduce(tb)
+            sample_pts = tb.numpy().view(np.float32)
+            # 3. models from the gathered points (same on every rank), counts on the shard, all-reduce
+            cloud9 = np.ones((flat.size, 4), np.float32)
+            cloud9[:, :3] = sample_pts
+            coeffs, good = O.models_from_triples(cloud9, np.arange(flat.size, dtype=np.int32).reshape(-1, 3))
+            local = O.count_batch(shard, np.nan_to_num(coeffs), t, O.DOT_FMA)
+            tc = torch.from_numpy(local.copy())
+            dist.all_reduce(tc)
+            counts = tc.numpy()
+            counts[~good] = 0
+            # 4. the library replays PCL's sequential decisions over the summed counts
+            rep = D.host_replay(counts, good, n_cur, max_it, 1.0)
+            best = rep["best_draw"]
+            # 5. refit: per-shard exact integer moments about the winner's first sample point, summed
+            pivot = sample_pts[3 * best]
+            idx = O.select_within(shard, coeffs[best], t, O.DOT_FMA)
+            _, mom = O.refit_fixed(shard, idx, pivot, s, coeffs[best])
+            if idx.size < 4:           # refit_fixed zeroes the moments of tiny shards; accumulate them anyway
+                mom = np.zeros(16, np.int64)
+            tm = torch.from_numpy(mom.copy())
+            dist.all_reduce(tm)
+            refined = D.host_plane_from_moments(tm.numpy(), pivot, s)
+            # 6. final selection on the shard; local peel, order preserved
+            inl = O.select_within(shard, refined, t, O.DOT_FMA)
+            tn = torch.tensor([inl.size])
+            dist.all_reduce(tn)
+            # compare with round `rnd` of the single-process oracle on the whole cloud
+            assert tri[best].tolist() == list(want.traces[rnd].best_sample)
+            assert counts[best] == want.traces[rnd].best_count and rep["iterations"] == want.traces[rnd].iterations
+            assert refined.tobytes() == want.coeffs[rnd].tobytes()
+            assert int(tn.item()) == want.inliers_orig[rnd].size
+            w = want.inliers_orig[rnd]
+            assert (orig[inl] == w[(w >= first) & (w < first + count)]).all()
+            # local-current index + this rank's prefix == PCL's index into the current cloud
+            assert np.isin(inl + first_cur, want.inliers_cur[rnd]).all()
+            keep = np.ones(shard.shape[0], bool)
+            keep[inl] = False
+            shard, orig = shard[keep], orig[keep]
+        rest = want.remaining
+        sizes = [torch.zeros(1, dtype=torch.int64) for _ in range(world)]
+        dist.all_gather(sizes, torch.tensor([shard.shape[0]], dtype=torch.int64))
+        assert sum(int(v.item()) for v in sizes) == rest.shape[0]
         q.put((rank, "ok"))
     except Exception as e:  # noqa: BLE001
         import traceback
