@@ -183,7 +183,7 @@ class PlaneRansac:
     def extract_planes(self, params: PrParams, want_indices: bool = True, copy: bool = True) -> Extraction:
         """copy=False returns views into the context's pinned result buffers (valid until the next call)."""
         n_staged, _ = self.cloud_size()
-        mp = params.max_planes
+        mp = max(int(params.max_planes), 0)   # a negative value is rejected by the library
         coeffs = np.zeros((max(mp, 1), 4), np.float32)
         offs = np.zeros(mp + 1, np.uintp)
         npl = C.c_int(0)

@@ -484,3 +484,30 @@ def test_hier_scorer_adversarial_clouds(O, pr):
             if seg.ok:
                 assert info.best_count == seg.trace.best_count, name
                 assert _same_bits(coeff, seg.coeff) and (inl == seg.inliers).all(), name
+
+
+def test_error_paths(lib_built):
+    """Reference convention: message + early return, nothing thrown across the C boundary."""
+    import ctypes as C
+    import dialog_b200 as D
+    from dialog_b200 import _lib
+    L = _lib.load()
+    with D.PlaneRansac(0) as fresh:
+        with pytest.raises(D.PlaneRansacError) as e:
+            fresh.extract_planes(D.make_params())
+        assert e.value.code == -3                                   # PR_ERR_NO_CLOUD
+        fresh.set_cloud(np.zeros((10, 3), np.float32))
+        for bad in (dict(distance_threshold=0.0), dict(distance_threshold=float("nan")), dict(max_iterations=-1),
+                    dict(probability=0.0), dict(probability=1.5), dict(dot_order=7), dict(scorer=9), dict(max_planes=-2)):
+            with pytest.raises(D.PlaneRansacError) as e:
+                fresh.extract_planes(D.make_params(**bad))
+            assert e.value.code == -1, bad                          # PR_ERR_INVALID
+        with pytest.raises(D.PlaneRansacError):
+            fresh.score(np.array([[0, 1, 10]], np.int32), 0.1)      # index out of range
+        with pytest.raises(D.PlaneRansacError):
+            fresh.segment_batch(D.make_params())                    # no batch staged
+        h = C.c_void_p()
+        assert L.plane_ransac_create(C.byref(h), 9999) == -1 and b"out of range" in L.plane_ransac_last_error()
+        # the context is still usable after errors
+        coeff, inl, info = fresh.segment_one(D.make_params(0.1, 10, 1, 0.99, True))
+        assert info.iterations >= 1
