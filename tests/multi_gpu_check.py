@@ -61,6 +61,23 @@ def main():
     tot = torch.tensor([rem.shape[0]], device="cuda")
     dist.all_reduce(tot)
     assert int(tot.item()) == want_rem.shape[0]
+    # fused preProcess staging, sharded: the centroid is the global one (integer sums all-reduced), so the
+    # translated shards and the planes found on them equal the single-GPU preprocessed run
+    dirty = pts.copy()
+    dirty[::1013, 1] = np.nan
+    dirty[:, :3] += np.float32(100.0)
+    with D.PlaneRansac(local) as one:
+        kept1, cen1, src1 = one.set_cloud_preprocessed(dirty)
+        want_p = one.extract_planes(prm)
+    kept, cen, src = sh.set_cloud_preprocessed(dirty[first: first + count])
+    assert cen.tobytes() == cen1.tobytes(), (cen, cen1)
+    tot = torch.tensor([kept], device="cuda")
+    dist.all_reduce(tot)
+    assert int(tot.item()) == kept1
+    got_p = sh.extract_planes(prm)
+    assert len(got_p.planes) == len(want_p.planes)
+    for a, b in zip(got_p.planes, want_p.planes):
+        assert a.coeff.tobytes() == b.coeff.tobytes() and a.info.n_inliers == b.info.n_inliers
     sh.close()
     dist.barrier()
     if rank == 0:
