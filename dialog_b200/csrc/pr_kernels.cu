@@ -389,22 +389,48 @@ constexpr int kScoreStages = 3;
 constexpr int kScoreStepsPerFlush = 32;             // 128 points: <= 128 increments per counter between folds
 constexpr int kScoreStageFloats = 3 * kTilePoints + 4;  // + 16 bytes so the last prefetch stays inside the stage
 
-// One (cloud, tile) work item -> three bulk copies into stage `s`, completion on s_full[s].
-__device__ __forceinline__ void score_issue_tile(const float* X, const float* Y, const float* Z, size_t cloud_stride,
-                                                 int tiles_per_cloud, int item, float* stage, uint64_t* full) {
-  const int c = item / tiles_per_cloud, tl = item - c * tiles_per_cloud;
-  const size_t off = (size_t)c * cloud_stride + (size_t)tl * kTilePoints;
-  mbar_expect_tx(full, 3u * kTilePoints * sizeof(float));
-  tma_bulk_g2s(stage, X + off, kTilePoints * sizeof(float), full);
-  tma_bulk_g2s(stage + kTilePoints, Y + off, kTilePoints * sizeof(float), full);
-  tma_bulk_g2s(stage + 2 * kTilePoints, Z + off, kTilePoints * sizeof(float), full);
+// One tile (`len` points at element offset `off` of the planes) -> three bulk copies into stage `s`,
+// completion on s_full[s].
+__device__ __forceinline__ void score_issue_tile(const float* X, const float* Y, const float* Z, size_t off, int len,
+                                                 float* stage, uint64_t* full) {
+  mbar_expect_tx(full, 3u * (unsigned)len * sizeof(float));
+  tma_bulk_g2s(stage, X + off, (unsigned)len * sizeof(float), full);
+  tma_bulk_g2s(stage + kTilePoints, Y + off, (unsigned)len * sizeof(float), full);
+  tma_bulk_g2s(stage + 2 * kTilePoints, Z + off, (unsigned)len * sizeof(float), full);
+}
+
+// Work of one CTA.  Item mode (pts_per_cta == 0, batches of small clouds): items are (cloud, 1024-point tile)
+// pairs, items_per_cta of them per CTA.  Range mode (one cloud): the CTA owns the points
+// [blockIdx.x * pts_per_cta, +pts_per_cta) cut into 1024-point tiles with a shorter last one, so that the
+// cloud divides evenly over the CTA slots of the launch whatever its size (a whole-tile split loses up to
+// 1/(tiles per CTA) of the machine on the rounding, 6-8 % on a 2M-point round).
+struct ScoreSpan {
+  int n_items;
+  int item_begin;       // item mode
+  long long pt_begin;   // range mode
+  int pts;              // range mode: points of this CTA (multiple of the warp-split unit)
+};
+
+__device__ __forceinline__ void score_tile_of(const ScoreSpan& w, int it, int tiles_per_cloud, size_t cloud_stride, int pts_per_cta,
+                                              int* cloud, size_t* off, int* len) {
+  if (pts_per_cta == 0) {
+    const int item = w.item_begin + it;
+    const int c = item / tiles_per_cloud, tl = item - c * tiles_per_cloud;
+    *cloud = c;
+    *off = (size_t)c * cloud_stride + (size_t)tl * kTilePoints;
+    *len = kTilePoints;
+  } else {
+    *cloud = 0;
+    *off = (size_t)w.pt_begin + (size_t)it * kTilePoints;
+    *len = min(kTilePoints, w.pts - it * kTilePoints);
+  }
 }
 
 template <int H, int DOT>
 __global__ void __launch_bounds__(kScoreThreads, H <= 4 ? 4 : 2)
     score_kernel(const float* __restrict__ X, const float* __restrict__ Y, const float* __restrict__ Z,
-                 size_t cloud_stride, int tiles_per_cloud, int total_items, int items_per_cta,
-                 const float4* __restrict__ hyps, int K, int k_begin, int k_end, float t,
+                 size_t cloud_stride, int tiles_per_cloud, int total_items, int items_per_cta, int pts_per_cta,
+                 long long n_padded, const float4* __restrict__ hyps, int K, int k_begin, int k_end, float t,
                  int32_t* __restrict__ counts, int warps_h) {
   // hypotheses [k_begin, k_end) of the K per cloud are scored by this launch
   __shared__ __align__(128) float s_pts[kScoreStages][kScoreStageFloats];
@@ -412,8 +438,19 @@ __global__ void __launch_bounds__(kScoreThreads, H <= 4 ? 4 : 2)
   __shared__ int s_done[kScoreStages];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int item_begin = blockIdx.x * items_per_cta;
-  const int n_items = min(total_items, item_begin + items_per_cta) - item_begin;
+  ScoreSpan w;
+  if (pts_per_cta == 0) {
+    w.item_begin = blockIdx.x * items_per_cta;
+    w.n_items = min(total_items, w.item_begin + items_per_cta) - w.item_begin;
+    w.pt_begin = 0;
+    w.pts = 0;
+  } else {
+    w.item_begin = 0;
+    w.pt_begin = (long long)blockIdx.x * pts_per_cta;
+    w.pts = (int)min((long long)pts_per_cta, n_padded - w.pt_begin);
+    w.n_items = (w.pts + kTilePoints - 1) / kTilePoints;
+  }
+  const int n_items = w.n_items;
   if (n_items <= 0) return;
 
   if (threadIdx.x == 0) {
@@ -424,14 +461,17 @@ __global__ void __launch_bounds__(kScoreThreads, H <= 4 ? 4 : 2)
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     // prologue: fill the ring
-    for (int s = 0; s < kScoreStages && s < n_items; ++s)
-      score_issue_tile(X, Y, Z, cloud_stride, tiles_per_cloud, item_begin + s, &s_pts[s][0], &s_full[s]);
+    for (int s = 0; s < kScoreStages && s < n_items; ++s) {
+      int c_, len_;
+      size_t off_;
+      score_tile_of(w, s, tiles_per_cloud, cloud_stride, pts_per_cta, &c_, &off_, &len_);
+      score_issue_tile(X, Y, Z, off_, len_, &s_pts[s][0], &s_full[s]);
+    }
   }
   __syncthreads();
 
   const int wh = warp % warps_h, wp = warp / warps_h;
-  const int pts_per_warp = kTilePoints / (kScoreWarps / warps_h);
-  const int p_begin = wp * pts_per_warp;
+  const int warps_p = kScoreWarps / warps_h;
   const int k_stride = 32 * warps_h;
   const int k0 = k_begin + blockIdx.y * (k_stride * H) + wh * 32 + lane;
 
@@ -442,8 +482,11 @@ __global__ void __launch_bounds__(kScoreThreads, H <= 4 ? 4 : 2)
 
   for (int it = 0; it < n_items; ++it) {
     const int s = it % kScoreStages;
-    const int item = item_begin + it;
-    const int c = item / tiles_per_cloud;
+    int c, len;
+    size_t off;
+    score_tile_of(w, it, tiles_per_cloud, cloud_stride, pts_per_cta, &c, &off, &len);
+    const int pts_per_warp = len / warps_p;  // a multiple of 128: len is a multiple of 128 * warps_p
+    const int p_begin = wp * pts_per_warp;
     if (c != cur_cloud) {
       if (cur_cloud >= 0) {
 #pragma unroll
@@ -517,7 +560,10 @@ __global__ void __launch_bounds__(kScoreThreads, H <= 4 ? 4 : 2)
         if (next < n_items) {
           __threadfence_block();
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          score_issue_tile(X, Y, Z, cloud_stride, tiles_per_cloud, item_begin + next, &s_pts[s][0], &s_full[s]);
+          int c_, len_;
+          size_t off_;
+          score_tile_of(w, next, tiles_per_cloud, cloud_stride, pts_per_cta, &c_, &off_, &len_);
+          score_issue_tile(X, Y, Z, off_, len_, &s_pts[s][0], &s_full[s]);
         }
       }
     }
@@ -529,65 +575,87 @@ __global__ void __launch_bounds__(kScoreThreads, H <= 4 ? 4 : 2)
   }
 }
 
-static int next_pow2(int v) {
-  int p = 1;
-  while (p < v) p <<= 1;
-  return p;
-}
-
 // One launch scoring hypotheses [k_begin, k_end) with H per lane and warps_h warps across hypotheses.
 template <int H>
-static void launch_score_h(const float* X, const float* Y, const float* Z, size_t cloud_stride, int tiles_per_cloud,
+static void launch_score_h(const float* X, const float* Y, const float* Z, size_t n_per_cloud, size_t cloud_stride,
                            int n_clouds, const float4* hyps, int K, int k_begin, int k_end, int warps_h, float t,
-                           int dot_order, int32_t* counts, int num_sms, cudaStream_t s) {
+                           int dot_order, int32_t* counts, int num_sms, cudaStream_t s, bool range_mode) {
   const int chunk = 32 * H * warps_h;
   const int n_chunks = (k_end - k_begin + chunk - 1) / chunk;
-  const int total_items = tiles_per_cloud * n_clouds;
-  int gx = ((H <= 4 ? 4 : 2) * num_sms) / n_chunks;
-  if (gx < 1) gx = 1;
-  if (gx > total_items) gx = total_items;
-  const int items_per_cta = (total_items + gx - 1) / gx;
-  gx = (total_items + items_per_cta - 1) / items_per_cta;
+  int slots = ((H <= 4 ? 4 : 2) * num_sms) / n_chunks;
+  if (slots < 1) slots = 1;
+  const int tiles_per_cloud = (int)((n_per_cloud + kTilePoints - 1) / kTilePoints);
+  int total_items = 0, items_per_cta = 0, pts_per_cta = 0, gx;
+  long long n_padded = 0;
+  if (range_mode) {
+    // even split of the (padded) cloud in units every warp of the CTA can share: 128 points per warp
+    const long long unit = 128ll * (kScoreWarps / warps_h);
+    n_padded = ((long long)n_per_cloud + unit - 1) / unit * unit;
+    long long per = (n_padded + slots - 1) / slots;
+    per = (per + unit - 1) / unit * unit;
+    pts_per_cta = (int)per;
+    gx = (int)((n_padded + per - 1) / per);
+  } else {
+    total_items = tiles_per_cloud * n_clouds;
+    gx = slots > total_items ? total_items : slots;
+    items_per_cta = (total_items + gx - 1) / gx;
+    gx = (total_items + items_per_cta - 1) / items_per_cta;
+  }
   dim3 grid(gx, n_chunks);
   if (dot_order == 1)
     score_kernel<H, 1><<<grid, kScoreThreads, 0, s>>>(X, Y, Z, cloud_stride, tiles_per_cloud, total_items, items_per_cta,
-                                                      hyps, K, k_begin, k_end, t, counts, warps_h);
+                                                      pts_per_cta, n_padded, hyps, K, k_begin, k_end, t, counts, warps_h);
   else
     score_kernel<H, 0><<<grid, kScoreThreads, 0, s>>>(X, Y, Z, cloud_stride, tiles_per_cloud, total_items, items_per_cta,
-                                                      hyps, K, k_begin, k_end, t, counts, warps_h);
+                                                      pts_per_cta, n_padded, hyps, K, k_begin, k_end, t, counts, warps_h);
 }
 
 int launch_score(CloudView cloud, size_t n_per_cloud, int n_clouds, size_t cloud_stride, const float4* hyps, int K,
                  float t, int dot_order, int32_t* counts, int num_sms, cudaStream_t s) {
   if (K <= 0 || n_per_cloud == 0 || n_clouds <= 0) return 0;
-  const int tiles_per_cloud = (int)((n_per_cloud + kTilePoints - 1) / kTilePoints);
   static const int forced_h = [] { const char* e = getenv("PR_SCORE_H"); return e ? atoi(e) : 0; }();  // tuning knob
+  static const int geom = [] { const char* e = getenv("PR_SCORE_GEOM"); return e ? atoi(e) : 1; }();   // 0: round-1 whole-tile split
+  const bool range_mode = geom != 0 && n_clouds == 1;
   // Every lane slot of a launch costs the same whether or not it holds a hypothesis, so K is cut into
-  // launches whose slot count (32 * H * warps_h per chunk) matches: full 2048-wide chunks first, then
-  // powers of two, rounding the last pieces up when little is wasted.
+  // launches whose slot count (32 * H * warps_h per chunk, grid.y chunks) matches.  With the even point split
+  // any chunk count fills the machine, so the largest chunk width that wastes <= 1/32 of its slots takes all of
+  // K in one launch (3072 = 3 x 1024); otherwise full 2048-wide chunks first, then powers of two, rounding the
+  // last pieces up when little is wasted.
   int launches = 0;
   int k = 0;
   while (k < K) {
     const int rest = K - k;
-    int H, warps_h, take;
-    if (rest >= 32 * 8 * kScoreWarps) {
-      H = 8; warps_h = kScoreWarps; take = rest / (32 * 8 * kScoreWarps) * (32 * 8 * kScoreWarps);
-    } else {
-      int slots = 32;  // largest power of two <= rest, at least one warp of single hypotheses
-      while (slots * 2 <= rest) slots *= 2;
-      // round up to the next power of two when that wastes at most a quarter of the launch (or < 64 slots)
-      if (rest > slots && 2 * slots - rest <= (slots / 2 > 64 ? slots / 2 : 64)) slots *= 2;
-      H = slots / 32 > 8 ? 8 : slots / 32;
-      warps_h = slots / (32 * H);
-      take = rest < slots ? rest : slots;
+    int H = 0, warps_h = 0, take = 0;
+    if (range_mode && forced_h == 0) {
+      for (int wh = kScoreWarps; wh >= 1; wh /= 2) {
+        const int c = 32 * 8 * wh;
+        const int padded = (rest + c - 1) / c * c;
+        if (padded - rest <= rest / 32 && padded / c <= 2 * num_sms) {
+          H = 8; warps_h = wh; take = rest;
+          break;
+        }
+      }
+    }
+    if (take == 0) {
+      if (rest >= 32 * 8 * kScoreWarps) {
+        H = 8; warps_h = kScoreWarps; take = rest / (32 * 8 * kScoreWarps) * (32 * 8 * kScoreWarps);
+      } else {
+        int slots = 32;  // largest power of two <= rest, at least one warp of single hypotheses
+        while (slots * 2 <= rest) slots *= 2;
+        // round up to the next power of two when that wastes at most a quarter of the launch (or < 64 slots)
+        if (rest > slots && 2 * slots - rest <= (slots / 2 > 64 ? slots / 2 : 64)) slots *= 2;
+        H = slots / 32 > 8 ? 8 : slots / 32;
+        warps_h = slots / (32 * H);
+        take = rest < slots ? rest : slots;
+      }
     }
     if (forced_h == 4 && H > 4) { warps_h = warps_h * H / 4 > kScoreWarps ? kScoreWarps : warps_h * H / 4; H = 4; }
     const float* X = cloud.x; const float* Y = cloud.y; const float* Z = cloud.z;
     switch (H) {
-      case 1: launch_score_h<1>(X, Y, Z, cloud_stride, tiles_per_cloud, n_clouds, hyps, K, k, k + take, warps_h, t, dot_order, counts, num_sms, s); break;
-      case 2: launch_score_h<2>(X, Y, Z, cloud_stride, tiles_per_cloud, n_clouds, hyps, K, k, k + take, warps_h, t, dot_order, counts, num_sms, s); break;
-      case 4: launch_score_h<4>(X, Y, Z, cloud_stride, tiles_per_cloud, n_clouds, hyps, K, k, k + take, warps_h, t, dot_order, counts, num_sms, s); break;
-      default: launch_score_h<8>(X, Y, Z, cloud_stride, tiles_per_cloud, n_clouds, hyps, K, k, k + take, warps_h, t, dot_order, counts, num_sms, s); break;
+      case 1: launch_score_h<1>(X, Y, Z, n_per_cloud, cloud_stride, n_clouds, hyps, K, k, k + take, warps_h, t, dot_order, counts, num_sms, s, range_mode); break;
+      case 2: launch_score_h<2>(X, Y, Z, n_per_cloud, cloud_stride, n_clouds, hyps, K, k, k + take, warps_h, t, dot_order, counts, num_sms, s, range_mode); break;
+      case 4: launch_score_h<4>(X, Y, Z, n_per_cloud, cloud_stride, n_clouds, hyps, K, k, k + take, warps_h, t, dot_order, counts, num_sms, s, range_mode); break;
+      default: launch_score_h<8>(X, Y, Z, n_per_cloud, cloud_stride, n_clouds, hyps, K, k, k + take, warps_h, t, dot_order, counts, num_sms, s, range_mode); break;
     }
     k += take;
     ++launches;
