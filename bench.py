@@ -217,6 +217,41 @@ def run_extras(args, pr):
         "gpu_ms": sum(ms) / len(ms), "cpu_oracle_s": cpu_s, "cpu_threads": 1, "planes": len(exd.planes),
         "identical_to_cpu_oracle": bool(same), "speedup": cpu_s / (sum(ms) / len(ms) * 1e-3),
         "note": "host cloud in, coefficients + inlier indices out; max_iterations=50, probability=0.99"}
+    # the reference's postProcessPlanes re-absorption pass over what the extraction left, against the
+    # scene's patch outlines as the plane polygons (180 vertices each); CPU = the oracle restating isPointInPoly
+    # (identical to the reference's own source, tests/test_reabsorb.py), timed on a prefix of the remaining cloud
+    # (extraction at half the threshold, so that plane points beyond it are left for the pass to claim at T = 0.1)
+    scene = synth.indoor_scene()
+    pr.set_cloud(pts10)
+    ext = pr.extract_planes(D.make_params(0.05, 50, 500, 0.99, True, 12345, args.planes, D.DOT_FMA), want_indices=False)
+    rem = pr.remaining().copy()
+    coeffs = np.array([p.coeff for p in ext.planes], np.float32)
+    # polygon of plane k = outline of the generating patch whose normal / offset it matches best
+    borders = []
+    for c in coeffs:
+        err = [min(np.abs(q.coeff - c).max(), np.abs(q.coeff + c).max()) for q in scene.patches]
+        borders.append(scene.patches[int(np.argmin(err))].border())
+    ms = []
+    for rep in range(4):
+        pr.set_cloud(rem)
+        pr.flush_l2()
+        pr.timer_start()
+        cur, _, n_left = pr.reabsorb(coeffs, borders, 0.1, 20261018)
+        t_ms = pr.timer_stop()
+        if rep:  # the first call sizes the scratch buffers
+            ms.append(t_ms)
+    n_cpu = min(len(rem), 20000)
+    t0 = time.perf_counter()
+    want = O.reabsorb(rem[:n_cpu], coeffs, borders, 0.1, 20261018)
+    cpu_s = time.perf_counter() - t0
+    same = all(np.array_equal(a[a < n_cpu], b) for a, b in zip(cur, want.absorbed))
+    out["reabsorb_postProcessPlanes"] = {
+        "points": int(len(rem)), "planes": int(len(coeffs)), "border_vertices_per_plane": int(len(borders[0])),
+        "gpu_ms": sum(ms) / len(ms), "absorbed": int(sum(len(a) for a in cur)), "points_left": int(n_left),
+        "cpu_oracle_s_per_point": cpu_s / n_cpu, "cpu_sample_points": n_cpu, "cpu_threads": 1,
+        "cpu_s_extrapolated": cpu_s / n_cpu * len(rem), "identical_on_cpu_sample": bool(same),
+        "speedup_extrapolated": (cpu_s / n_cpu * len(rem)) / (sum(ms) / len(ms) * 1e-3),
+        "note": "cloud resident (set_cloud before the timer), polygon upload + kernels + index lists back inside it"}
     # configs[4]: batch of 32K-point clouds, one plane each, 256 hypotheses per cloud (slice of the 4096 clouds)
     nc = args.batch_clouds
     clouds = np.stack([synth.tile_scene(cid).points(0, 32768) for cid in range(nc)])

@@ -177,6 +177,15 @@ struct plane_ransac_ctx {
   DevBuf<int4> d_batch_pts;
   DevBuf<int32_t> d_batch_cnt;
 
+  // postProcessPlanes re-absorption scratch
+  DevBuf<pr::ReabsorbPlane> d_rb_planes;
+  DevBuf<float4> d_rb_border, d_rb_edges, d_rb_rays;
+  DevBuf<int32_t> d_rb_ray_edges, d_rb_counts, d_rb_out_cur, d_rb_out_orig;
+  DevBuf<unsigned long long> d_rb_counters, d_rb_keys;
+  DevBuf<uint2> d_rb_cand;
+  DevBuf<uint32_t> d_rb_claimed;
+  DevBuf<unsigned char> d_rb_temp;
+
   // sharding
   ncclComm_t comm = nullptr;
   int n_ranks = 1, rank = 0;
@@ -795,6 +804,9 @@ void plane_ransac_destroy(plane_ransac_ctx* c) {
   for (int i = 0; i < 3; ++i) dev_free(c->sorted_mem[i]);
   dev_free(c->d_bounds); dev_free(c->d_aux); dev_free(c->d_keys); dev_free(c->d_vals); dev_free(c->d_sort_temp);
   dev_free(c->d_totals2);
+  dev_free(c->d_rb_planes); dev_free(c->d_rb_border); dev_free(c->d_rb_edges); dev_free(c->d_rb_rays);
+  dev_free(c->d_rb_ray_edges); dev_free(c->d_rb_counts); dev_free(c->d_rb_out_cur); dev_free(c->d_rb_out_orig);
+  dev_free(c->d_rb_counters); dev_free(c->d_rb_keys); dev_free(c->d_rb_cand); dev_free(c->d_rb_claimed); dev_free(c->d_rb_temp);
   dev_free(c->d_batch_bbox); dev_free(c->d_batch_idx); dev_free(c->d_batch_scale); dev_free(c->d_batch_refit);
   dev_free(c->d_batch_hyps); dev_free(c->d_batch_pts); dev_free(c->d_batch_cnt);
   pin_free(c->h_triples); pin_free(c->h_counts); pin_free(c->h_good); pin_free(c->h_refit);
@@ -1023,6 +1035,147 @@ int plane_ransac_remaining(plane_ransac_ctx* c, pr_point* out, size_t cap, size_
   PR_CUDA(cudaGetLastError());
   PR_CUDA(cudaMemcpyAsync(out, c->aos.p, c->n_current * sizeof(pr_point), cudaMemcpyDeviceToHost, c->stream));
   PR_CUDA(cudaStreamSynchronize(c->stream));
+  return PR_OK;
+}
+
+
+// ---- postProcessPlanes re-absorption (Dialog/PlaneDetect.h:1454-1580) ------------------------------
+int plane_ransac_reabsorb(plane_ransac_ctx* c, const float* coeffs, const pr_point* border, const size_t* border_offsets,
+                          int n_planes, float dist_threshold, unsigned rand_seed, int32_t* absorbed_cur, int32_t* absorbed_orig,
+                          size_t idx_cap, size_t* plane_offsets, size_t* n_remaining) {
+  PR_TRY(check_ctx(c));
+  if (c->profiling) collect_spans(c);
+  if (!c->have_cloud) return fail(PR_ERR_NO_CLOUD, "no cloud staged");
+  if (n_planes < 0 || (n_planes && (!coeffs || !border || !border_offsets))) return fail(PR_ERR_INVALID, "bad plane arguments");
+  if (!plane_offsets) return fail(PR_ERR_INVALID, "null plane_offsets");
+  if (std::isnan(dist_threshold)) return fail(PR_ERR_INVALID, "dist_threshold is NaN");
+  const size_t P = (size_t)n_planes;
+  size_t n_border = 0;
+  for (size_t j = 0; j < P; ++j) {
+    if (border_offsets[j + 1] <= border_offsets[j]) return fail(PR_ERR_INVALID, "plane %zu has an empty border polygon", j);
+    if (border_offsets[j + 1] - border_offsets[j] > (size_t)INT_MAX / 16) return fail(PR_ERR_INVALID, "border polygon %zu too large", j);
+  }
+  if (P) n_border = border_offsets[P] - border_offsets[0];
+  if (n_border > (size_t)INT_MAX / 4) return fail(PR_ERR_INVALID, "too many border vertices");
+  for (size_t j = 0; j <= P; ++j) plane_offsets[j] = 0;
+  const size_t n = c->n_current;
+  if (n_remaining) *n_remaining = n;
+  if (P == 0 || n == 0) return PR_OK;
+  PR_TRY(reserve_small(c));
+  PR_TRY(reserve_work(c));
+
+  // per-call constants: planes, border vertices, the ten edge indices rand() % border.size() draws after srand(seed)
+  std::vector<pr::ReabsorbPlane> hp(P);
+  std::vector<int32_t> hre(10 * P);
+  for (size_t j = 0; j < P; ++j) {
+    hp[j].a = coeffs[4 * j]; hp[j].b = coeffs[4 * j + 1]; hp[j].c = coeffs[4 * j + 2]; hp[j].d = coeffs[4 * j + 3];
+    hp[j].border_begin = (int)(border_offsets[j] - border_offsets[0]);
+    hp[j].border_size = (int)(border_offsets[j + 1] - border_offsets[j]);
+    hp[j].pad0 = hp[j].pad1 = 0;
+    pr::msvc_rand_edges(rand_seed, hp[j].border_size, &hre[10 * j]);
+  }
+  PR_TRY(dev_reserve(c->d_rb_planes, P));
+  PR_TRY(dev_reserve(c->d_rb_ray_edges, 10 * P));
+  PR_TRY(dev_reserve(c->d_rb_border, n_border));
+  PR_TRY(dev_reserve(c->d_rb_edges, 3 * n_border));
+  PR_TRY(dev_reserve(c->d_rb_rays, 10 * P));
+  PR_TRY(dev_reserve(c->d_rb_counts, P));
+  PR_TRY(dev_reserve(c->d_rb_counters, 2));
+  PR_TRY(dev_reserve(c->d_rb_claimed, c->current.cap));
+  PR_CUDA(cudaMemcpyAsync(c->d_rb_planes.p, hp.data(), P * sizeof(pr::ReabsorbPlane), cudaMemcpyHostToDevice, c->stream));
+  PR_CUDA(cudaMemcpyAsync(c->d_rb_ray_edges.p, hre.data(), 10 * P * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+  PR_CUDA(cudaMemcpyAsync(c->d_rb_border.p, border + border_offsets[0], n_border * sizeof(pr_point), cudaMemcpyHostToDevice, c->stream));
+  PR_CUDA(cudaMemsetAsync(c->d_rb_counts.p, 0, P * sizeof(int32_t), c->stream));
+  PR_CUDA(cudaMemsetAsync(c->d_rb_counters.p, 0, 2 * sizeof(unsigned long long), c->stream));
+  PR_CUDA(cudaMemsetAsync(c->d_rb_claimed.p, 0, c->current.cap * sizeof(uint32_t), c->stream));
+  {
+    Span sp(c, KC_OTHER, 1);
+    pr::launch_reabsorb_prepare(c->d_rb_border.p, c->d_rb_planes.p, n_planes, c->d_rb_ray_edges.p, c->d_rb_edges.p, c->d_rb_rays.p, c->stream);
+  }
+  // R1: candidate pairs (retry once with the exact size when the first guess was too small)
+  unsigned long long h_counters[2] = {0, 0};
+  size_t cand_cap = std::max<size_t>(c->d_rb_cand.cap, std::max<size_t>(n, (size_t)1 << 16));
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    PR_TRY(dev_reserve(c->d_rb_cand, cand_cap));
+    {
+      Span sp(c, KC_OTHER, 1);
+      pr::launch_reabsorb_filter(c->current, n, c->d_rb_planes.p, n_planes, dist_threshold, c->d_rb_counters.p, c->d_rb_cand.p,
+                                 (unsigned long long)c->d_rb_cand.cap, c->num_sms, c->stream);
+    }
+    PR_CUDA(cudaGetLastError());
+    PR_CUDA(cudaMemcpyAsync(h_counters, c->d_rb_counters.p, sizeof(h_counters), cudaMemcpyDeviceToHost, c->stream));
+    PR_TRY(sync_stream(c));
+    if (h_counters[0] <= (unsigned long long)c->d_rb_cand.cap) break;
+    if (attempt == 1) return fail(PR_ERR_CUDA, "candidate count changed between passes");
+    cand_cap = (size_t)h_counters[0];
+    PR_CUDA(cudaMemsetAsync(c->d_rb_counters.p, 0, sizeof(unsigned long long), c->stream));
+  }
+  const unsigned long long n_cand = h_counters[0];
+  std::vector<int32_t> h_counts(P, 0);
+  unsigned long long n_abs = 0;
+  if (n_cand) {
+    // R2: polygon containment
+    PR_TRY(dev_reserve(c->d_rb_keys, 2 * (size_t)n_cand));
+    {
+      Span sp(c, KC_OTHER, 1);
+      pr::launch_reabsorb_poly(c->current, c->d_rb_cand.p, n_cand, c->d_rb_planes.p, c->d_rb_edges.p, c->d_rb_rays.p, c->d_rb_claimed.p,
+                               c->d_rb_keys.p, c->d_rb_counters.p + 1, c->d_rb_counts.p, c->num_sms, c->stream);
+    }
+    PR_CUDA(cudaGetLastError());
+    PR_CUDA(cudaMemcpyAsync(h_counters, c->d_rb_counters.p, sizeof(h_counters), cudaMemcpyDeviceToHost, c->stream));
+    PR_CUDA(cudaMemcpyAsync(h_counts.data(), c->d_rb_counts.p, P * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    PR_TRY(sync_stream(c));
+    n_abs = h_counters[1];
+  }
+  for (size_t j = 0; j < P; ++j) plane_offsets[j + 1] = plane_offsets[j] + (size_t)h_counts[j];
+  if ((absorbed_cur || absorbed_orig) && n_abs > idx_cap)
+    return fail(PR_ERR_CAPACITY, "absorbed index buffers hold %zu entries, need %llu", idx_cap, n_abs);
+  if (n_abs) {
+    // R3: per-plane ascending lists
+    int key_bits = 33;
+    while (key_bits < 64 && (P >> (key_bits - 32)) != 0) ++key_bits;
+    const size_t tb = pr::reabsorb_sort_temp_bytes((size_t)n_abs);
+    PR_TRY(dev_reserve(c->d_rb_temp, tb + 256));
+    PR_TRY(dev_reserve(c->d_rb_out_cur, (size_t)n_abs));
+    PR_TRY(dev_reserve(c->d_rb_out_orig, (size_t)n_abs));
+    {
+      Span sp(c, KC_OTHER, 3);
+      pr::launch_reabsorb_lists(c->d_rb_keys.p, c->d_rb_keys.p + n_cand, (size_t)n_abs, key_bits, c->d_rb_temp.p, tb, c->current.orig,
+                                c->d_rb_out_cur.p, c->d_rb_out_orig.p, c->stream);
+    }
+    PR_CUDA(cudaGetLastError());
+    if (absorbed_cur) PR_CUDA(cudaMemcpyAsync(absorbed_cur, c->d_rb_out_cur.p, n_abs * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    if (absorbed_orig) PR_CUDA(cudaMemcpyAsync(absorbed_orig, c->d_rb_out_orig.p, n_abs * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+  }
+  // peel: the unclaimed points become the current cloud (":1560-1566")
+  pr::CloudView dst = (c->current.x == c->work[0].x) ? c->work[1] : c->work[0];
+  PR_TRY(dev_reserve(c->d_scratch, pr::compact_scratch_bytes(n) + 64));
+  {
+    Span sp(c, KC_COMPACT, 1);
+    pr::Plane4 none = {0, 0, 0, 0};
+    pr::launch_compact(c->current, n, none, 0.f, 3, dst, true, nullptr, nullptr, c->d_scratch.p, c->d_totals.p, c->stream, c->d_rb_claimed.p);
+    c->prof.points_compact += (long long)n;
+  }
+  PR_CUDA(cudaGetLastError());
+  if (c->comm) PR_NCCL(g_nccl.AllGather(c->d_totals.p, c->d_totals.p + 2, 2, ncclInt64, c->comm, c->stream));
+  PR_CUDA(cudaMemcpyAsync(c->h_totals.p, c->d_totals.p, (2 + (c->comm ? 2 * c->n_ranks : 0)) * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
+  PR_TRY(sync_stream(c));
+  c->current = dst;
+  c->n_current = (size_t)c->h_totals.p[0];
+  c->prof.bytes_compact += 20ll * (long long)n + 16ll * (long long)c->n_current;
+  if (c->comm) {
+    long long tot = 0, f = 0;
+    for (int r = 0; r < c->n_ranks; ++r) {
+      if (r == c->rank) f = tot;
+      tot += c->h_totals.p[2 + 2 * r];
+    }
+    c->n_global_current = tot;
+    c->first_current = f;
+  } else {
+    c->n_global_current = (long long)c->n_current;
+    c->first_current = 0;
+  }
+  if (n_remaining) *n_remaining = c->n_current;
   return PR_OK;
 }
 
@@ -1420,6 +1573,12 @@ int plane_ransac_host_replay(const int32_t* counts, const uint8_t* good, int n_d
   if (draws_used) *draws_used = r.draws_used();
   if (skipped) *skipped = r.skipped();
   if (exhausted) *exhausted = done ? 0 : 1;
+  return PR_OK;
+}
+
+int plane_ransac_host_rand_edges(unsigned seed, int border_size, int32_t edges[10]) {
+  if (border_size <= 0 || !edges) return fail(PR_ERR_INVALID, "border_size must be > 0");
+  pr::msvc_rand_edges(seed, border_size, edges);
   return PR_OK;
 }
 

@@ -303,6 +303,15 @@ float threshold_up(double t) {
   return f;
 }
 
+void msvc_rand_edges(unsigned seed, int border_size, int32_t edges[10]) {
+  uint32_t hold = seed;
+  for (int i = 0; i < 10; ++i) {
+    hold = hold * 214013u + 2531011u;
+    const uint32_t r = (hold >> 16) & 0x7fffu;
+    edges[i] = (int32_t)(r % (uint32_t)border_size);
+  }
+}
+
 void shard_range(long long n_points, int n_ranks, int rank, long long* first, long long* count) {
   const long long base = n_points / n_ranks, rem = n_points % n_ranks;
   *first = base * rank + (rank < rem ? rank : rem);

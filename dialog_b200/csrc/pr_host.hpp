@@ -91,4 +91,8 @@ float threshold_up(double t);
 
 void shard_range(long long n_points, int n_ranks, int rank, long long* first, long long* count);
 
+// isPointInPoly's edge draws (Dialog/PlaneDetect.h:1905-1919): srand(seed), then ten times rand() % border_size with
+// the MSVC CRT generator (holdrand = holdrand * 214013 + 2531011; (holdrand >> 16) & 0x7fff).
+void msvc_rand_edges(unsigned seed, int border_size, int32_t edges[10]);
+
 }  // namespace pr

@@ -1175,7 +1175,7 @@ __global__ void __launch_bounds__(kCompactThreads, 5)
                    const int32_t* __restrict__ O, size_t n, Plane4 pl, float t, float* __restrict__ DX,
                    float* __restrict__ DY, float* __restrict__ DZ, int32_t* __restrict__ DO, size_t dst_cap,
                    int32_t* __restrict__ inl_cur, int32_t* __restrict__ inl_orig, unsigned long long* tile_state,
-                   unsigned* ticket, long long* __restrict__ totals, unsigned n_tiles) {
+                   unsigned* ticket, long long* __restrict__ totals, unsigned n_tiles, const uint32_t* __restrict__ flags) {
   __shared__ __align__(16) float s_x[kCompactTile];
   __shared__ __align__(16) float s_y[kCompactTile];
   __shared__ __align__(16) float s_z[kCompactTile];
@@ -1212,12 +1212,17 @@ __global__ void __launch_bounds__(kCompactThreads, 5)
     }
     keep[u] = 0u;
     inl[u] = 0u;
+    uint4 f4 = make_uint4(0u, 0u, 0u, 0u);
+    if (DOT == 3) f4 = __ldg(reinterpret_cast<const uint4*>(flags + i0));
+    const unsigned fl[4] = {f4.x, f4.y, f4.z, f4.w};
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       const bool valid = (i0 + e) < n;
       bool in;
       if (DOT == 2) {  // staging filter (pcl::removeNaNFromPointCloud): "inliers" are the non-finite points
         in = !(isfinite(xs[u][e]) && isfinite(ys[u][e]) && isfinite(zs[u][e]));
+      } else if (DOT == 3) {  // postProcessPlanes: "inliers" are the points some plane polygon claimed
+        in = fl[e] != 0u;
       } else {
         const float r = plane_dot<DOT>(pl.a, pl.b, pl.c, pl.d, xs[u][e], ys[u][e], zs[u][e]);
         in = fabsf(r) < t;
@@ -1353,7 +1358,7 @@ size_t compact_scratch_bytes(size_t n) {
 }
 
 void launch_compact(CloudView src, size_t n, Plane4 plane, float t, int dot_order, CloudView dst, bool write_remaining,
-                    int32_t* inl_cur, int32_t* inl_orig, void* scratch, long long* totals, cudaStream_t s) {
+                    int32_t* inl_cur, int32_t* inl_orig, void* scratch, long long* totals, cudaStream_t s, const uint32_t* flags) {
   if (n == 0) {
     cudaMemsetAsync(totals, 0, 2 * sizeof(long long), s);
     return;
@@ -1365,8 +1370,10 @@ void launch_compact(CloudView src, size_t n, Plane4 plane, float t, int dot_orde
 #define PR_COMPACT(D, W)                                                                                              \
   compact_kernel<D, W><<<n_tiles, kCompactThreads, 0, s>>>(src.x, src.y, src.z, src.orig, n, plane, t, dst.x, dst.y,  \
                                                            dst.z, dst.orig, dst.cap, inl_cur, inl_orig, tile_state,   \
-                                                           ticket, totals, n_tiles)
-  if (dot_order == 2) {
+                                                           ticket, totals, n_tiles, flags)
+  if (dot_order == 3) {
+    PR_COMPACT(3, true);
+  } else if (dot_order == 2) {
     PR_COMPACT(2, true);
   } else if (dot_order == 1) {
     if (write_remaining) PR_COMPACT(1, true); else PR_COMPACT(1, false);

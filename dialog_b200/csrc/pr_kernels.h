@@ -90,8 +90,33 @@ void launch_refit_batch(CloudView clouds, size_t n_per, size_t cloud_stride, int
 // inlier positions -> inl_cur, their original indices -> inl_orig.  totals[0] = remaining, totals[1] = inliers.
 // scratch: tile_state (n_tiles x uint64) + ticket, zeroed by the wrapper.
 size_t compact_scratch_bytes(size_t n);
+// dot_order == 2: predicate = point is non-finite (staging filter); dot_order == 3: predicate = flags[i] != 0
+// (flags: one uint32 per point, as long as the cloud's capacity).
 void launch_compact(CloudView src, size_t n, Plane4 plane, float t, int dot_order, CloudView dst, bool write_remaining,
-                    int32_t* inl_cur, int32_t* inl_orig, void* scratch, long long* totals, cudaStream_t s);
+                    int32_t* inl_cur, int32_t* inl_orig, void* scratch, long long* totals, cudaStream_t s,
+                    const uint32_t* flags = nullptr);
+
+// Re-absorption pass of the reference's postProcessPlanes (pr_reabsorb.cu).
+struct ReabsorbPlane {
+  float a, b, c, d;
+  int border_begin, border_size;  // vertices [border_begin, +border_size) of the concatenated border array
+  int pad0, pad1;
+};
+// edges: 3 float4 per border vertex; rays: 10 float4 per plane; ray_edges: 10 drawn edge indices per plane.
+void launch_reabsorb_prepare(const float4* border, const ReabsorbPlane* planes, int n_planes, const int32_t* ray_edges,
+                             float4* edges, float4* rays, cudaStream_t s);
+// R1: appends (point, plane) for every pair with dist <= t; *counter ends at the number of pairs found even when
+// it exceeds cap (then nothing beyond cap was written and the caller retries with a larger buffer).
+void launch_reabsorb_filter(CloudView cloud, size_t n, const ReabsorbPlane* planes, int n_planes, float t,
+                            unsigned long long* counter, uint2* cand, unsigned long long cap, int num_sms, cudaStream_t s);
+// R2: claimed[i] = 1, key (plane << 32 | i) appended, plane_counts[plane]++ for every pair inside its polygon.
+void launch_reabsorb_poly(CloudView cloud, const uint2* cand, unsigned long long n_cand, const ReabsorbPlane* planes,
+                          const float4* edges, const float4* rays, uint32_t* claimed, unsigned long long* keys,
+                          unsigned long long* n_absorbed, int32_t* plane_counts, int num_sms, cudaStream_t s);
+// R3: sorts the keys (per plane ascending point index) and splits them into current / original index lists.
+size_t reabsorb_sort_temp_bytes(size_t n);
+void launch_reabsorb_lists(const unsigned long long* keys_in, unsigned long long* keys_sorted, size_t n, int key_bits, void* temp,
+                           size_t temp_bytes, const int32_t* orig, int32_t* out_cur, int32_t* out_orig, cudaStream_t s);
 
 // Batch: per-cloud inlier count of per-cloud planes is K2 with K = 1; nothing else needed.
 

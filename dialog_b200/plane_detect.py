@@ -251,6 +251,40 @@ class PlaneRansac:
         _lib.check(self._L.plane_ransac_remaining(self._h, out.ctypes.data_as(C.c_void_p), out.shape[0], C.byref(n)))
         return out[: n.value]
 
+    def reabsorb(self, coeffs, borders, distance_threshold: float = 0.1, rand_seed: int = 0):
+        """postProcessPlanes' re-absorption pass (Dialog/PlaneDetect.h:1530-1566) over the current cloud: every point is
+        tested against every plane polygon with the reference's isPointInPoly; claimed points leave the cloud.
+        coeffs: (P,4); borders: P arrays (nb_j, 3|4) of polygon vertices (Plane::border); rand_seed: what the reference
+        passes to srand (time(0)).  Returns (per-plane ascending index lists into the cloud before the call, the same as
+        indices into the staged cloud, number of points left)."""
+        co = np.ascontiguousarray(coeffs, np.float32).reshape(-1, 4)
+        P = co.shape[0]
+        if len(borders) != P:
+            raise ValueError("one border polygon per plane")
+        bd = np.concatenate([as_cloud(b) for b in borders]) if P else np.zeros((0, 4), np.float32)
+        offs = np.zeros(P + 1, np.uintp)
+        if P:
+            offs[1:] = np.cumsum([len(b) for b in borders])
+        _, n_cur = self.cloud_size()
+        cap = max(1, n_cur)
+        po = np.zeros(P + 1, np.uintp)
+        nrem = C.c_size_t(0)
+        vp = C.c_void_p
+        while True:
+            cur = np.empty(cap, np.int32)
+            orig = np.empty(cap, np.int32)
+            try:
+                _lib.check(self._L.plane_ransac_reabsorb(self._h, co.ctypes.data_as(vp), bd.ctypes.data_as(vp), offs.ctypes.data_as(vp), P,
+                                                         float(distance_threshold), int(rand_seed) & 0xFFFFFFFF, cur.ctypes.data_as(vp),
+                                                         orig.ctypes.data_as(vp), cap, po.ctypes.data_as(vp), C.byref(nrem)))
+                break
+            except PlaneRansacError as e:  # a point can join several planes: the lists can outgrow the cloud
+                if e.code != -4 or cap >= max(1, n_cur) * max(P, 1):
+                    raise
+                cap = max(1, n_cur) * max(P, 1)
+        o = [int(v) for v in po]
+        return ([cur[o[j]: o[j + 1]].copy() for j in range(P)], [orig[o[j]: o[j + 1]].copy() for j in range(P)], int(nrem.value))
+
     # ---- sharding ----
     @staticmethod
     def comm_unique_id() -> bytes:
@@ -316,6 +350,13 @@ def host_replay(counts, good, n_points: int, max_iterations: int, probability: f
                                                     n_points, max_iterations, probability, *[C.byref(x) for x in v]))
     return dict(best_draw=v[0].value, iterations=v[1].value, draws_used=v[2].value, skipped=v[3].value,
                 exhausted=bool(v[4].value))
+
+
+def host_rand_edges(seed: int, border_size: int) -> np.ndarray:
+    """The ten border edges isPointInPoly draws after srand(seed) (MSVC CRT rand)."""
+    out = np.zeros(10, np.int32)
+    _lib.check(_lib.load().plane_ransac_host_rand_edges(int(seed) & 0xFFFFFFFF, int(border_size), out.ctypes.data_as(C.c_void_p)))
+    return out
 
 
 def host_shard_range(n_points: int, n_ranks: int, rank: int):

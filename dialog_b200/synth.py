@@ -53,6 +53,18 @@ class Patch:
         return np.array([n[0], n[1], n[2], -float(n @ np.asarray(self.origin, float))])
 
 
+    def border(self, per_side: int = 45) -> np.ndarray:
+        """The patch outline as a closed polygon of 4 * per_side vertices ((n,4) float32, w = 1) — what
+        pcl::ConcaveHull would hand back as Plane::border for this patch (the reference's saved polygon sets hold
+        ~180 vertices per polygon, Dialog/dataForPlane)."""
+        o, u, v = (np.asarray(a, float) for a in (self.origin, self.u, self.v))
+        t = np.arange(per_side) / per_side
+        pts = np.concatenate([o + t[:, None] * u, o + u + t[:, None] * v, o + u + v - t[:, None] * u, o + v - t[:, None] * v])
+        out = np.ones((pts.shape[0], 4), np.float32)
+        out[:, :3] = pts.astype(np.float32)
+        return out
+
+
 @dataclass
 class Scene:
     patches: list

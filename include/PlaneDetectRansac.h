@@ -98,6 +98,41 @@ class PlaneDetectRansac {
     return true;
   }
 
+  // postProcessPlanes' second half (Dialog/PlaneDetect.h:1530-1566) after detect(): every point still in `cloud` is
+  // tested against the planes' polygons (Plane::border, one per record in `borders`) with the reference's
+  // isPointInPoly; a claimed point is appended to every plane that contains it (indices into the cloud given to
+  // detect()) and `cloud` is replaced by the points no polygon claimed.  rand_seed: the reference's srand(time(0)).
+  bool postProcess(std::vector<PointXYZ>& cloud, std::vector<PlaneRecord>& planes,
+                   const std::vector<std::vector<PointXYZ>>& borders, unsigned rand_seed) {
+    if (!ctx_) return false;
+    const size_t P = planes.size();
+    if (borders.size() != P) { err_ = "one border polygon per plane"; return false; }
+    std::vector<float> coeffs(4 * (P ? P : 1));
+    std::vector<PointXYZ> bd;
+    std::vector<size_t> bo(P + 1, 0), po(P + 1, 0);
+    for (size_t k = 0; k < P; ++k) {
+      std::memcpy(&coeffs[4 * k], planes[k].coeff, 4 * sizeof(float));
+      bd.insert(bd.end(), borders[k].begin(), borders[k].end());
+      bo[k + 1] = bd.size();
+    }
+    size_t cap = cloud.size() ? cloud.size() : 1, n_rem = 0;
+    std::vector<int32_t> orig(cap);
+    int rc = plane_ransac_reabsorb(ctx_, coeffs.data(), reinterpret_cast<const pr_point*>(bd.data()), bo.data(), (int)P,
+                                   (float)prm_.distance_threshold, rand_seed, nullptr, orig.data(), cap, po.data(), &n_rem);
+    if (rc == PR_ERR_CAPACITY) {  // points claimed by several planes: the lists can outgrow the cloud
+      cap *= (P ? P : 1);
+      orig.resize(cap);
+      rc = plane_ransac_reabsorb(ctx_, coeffs.data(), reinterpret_cast<const pr_point*>(bd.data()), bo.data(), (int)P,
+                                 (float)prm_.distance_threshold, rand_seed, nullptr, orig.data(), cap, po.data(), &n_rem);
+    }
+    if (rc != PR_OK) return fail();
+    for (size_t k = 0; k < P; ++k) planes[k].indices.insert(planes[k].indices.end(), orig.begin() + po[k], orig.begin() + po[k + 1]);
+    std::vector<PointXYZ> rest(n_rem);
+    if (n_rem && plane_ransac_remaining(ctx_, reinterpret_cast<pr_point*>(rest.data()), n_rem, &n_rem) != PR_OK) return fail();
+    cloud.swap(rest);
+    return true;
+  }
+
 #ifdef PLANE_RANSAC_WITH_PCL
   // The north-star surface: (PointCloud<PointXYZ>::Ptr, threshold, max iterations, min plane size) ->
   // coefficients + inlier indices per plane; *cloud is replaced by the remaining points.

@@ -169,6 +169,24 @@ int plane_ransac_plane_points(plane_ransac_ctx* ctx, int plane_index, int projec
 /* Points left after the last extract call, original order (== the rebuilt source_cloud). */
 int plane_ransac_remaining(plane_ransac_ctx* ctx, pr_point* out, size_t cap, size_t* n);
 
+/* ---- postProcessPlanes re-absorption (Dialog/PlaneDetect.h:1454-1580) ------------------------------------------
+ * The reference's own use of the threshold test + peel: every point of the current cloud (what is left after the last
+ * extract call, or the staged cloud) is tested against every plane polygon with isPointInPoly (:1891-1955): distance to
+ * the plane <= dist_threshold (T_dist_point_plane, non-strict) by projPoint2Plane / distP2P, then ten in-plane rays,
+ * each perpendicular to a border edge drawn with rand() % border.size() after srand(rand_seed) — the reference seeds
+ * with time(0) at every call — intersected with every border edge by isBothLineSegsIntersect (:1957-2016); inside when
+ * at least five rays cross an odd number of edges.  A point joins every plane that contains it (:1549-1555 has no
+ * break) and the unclaimed points become the current cloud in their original order (:1560-1566), which
+ * plane_ransac_remaining returns.
+ *   coeffs: 4 floats per plane (a, b, c, d).  border: the polygons' vertices (Plane::border, e.g. from
+ *   pcl::ConcaveHull) concatenated; plane j owns border[border_offsets[j] .. border_offsets[j + 1]) (>= 1 vertex).
+ *   absorbed_cur / absorbed_orig (optional, idx_cap entries each): per plane the ascending indices of the points it
+ *   claimed, as positions in the cloud before this call / as indices into the staged cloud, delimited by
+ *   plane_offsets (n_planes + 1 entries).  When sharded every rank processes its shard; indices are rank-local. */
+int plane_ransac_reabsorb(plane_ransac_ctx* ctx, const float* coeffs, const pr_point* border, const size_t* border_offsets,
+                          int n_planes, float dist_threshold, unsigned rand_seed, int32_t* absorbed_cur,
+                          int32_t* absorbed_orig, size_t idx_cap, size_t* plane_offsets, size_t* n_remaining);
+
 /* ---- batch of equal-sized small clouds (per-scan tiles), one best plane each, no peel --------
  * pts: n_clouds * n_per_cloud points.  Every cloud runs segment() with the same parameters (and,
  * having the same size and seed, the same index triples).  coeffs: 4*n_clouds; n_inliers: n_clouds. */
@@ -220,6 +238,9 @@ int plane_ransac_host_draw_triples(size_t n_points, unsigned seed, int n_draws, 
 int plane_ransac_host_replay(const int32_t* counts, const uint8_t* good, int n_draws, long long n_points,
                              int max_iterations, double probability, int* best_draw, int* iterations,
                              int* draws_used, int* skipped, int* exhausted);
+/* The ten border-edge indices isPointInPoly draws: srand(seed), then rand() % border_size with the MSVC CRT
+ * generator (the reference is built with MSVC v140: Dialog/Dialog.vcxproj:20). */
+int plane_ransac_host_rand_edges(unsigned seed, int border_size, int32_t edges[10]);
 /* Contiguous shard [first, first + count) of rank r among n_ranks for n points. */
 int plane_ransac_host_shard_range(long long n_points, int n_ranks, int rank, long long* first,
                                   long long* count);

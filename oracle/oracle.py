@@ -62,7 +62,7 @@ def make_params(distance_threshold=0.1, max_iterations=50, min_plane_size=500, p
 
 def build(force: bool = False) -> str:
     """Compile the oracle with oracle/Makefile (gcc -O2 -ffp-contract=off)."""
-    src = [os.path.join(_HERE, f) for f in ("pr_oracle.c", "pr_oracle.h", "Makefile")]
+    src = [os.path.join(_HERE, f) for f in ("pr_oracle.c", "pr_oracle_poly.c", "pr_oracle.h", "Makefile")]
     if force or not os.path.exists(_SO) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in src):
         subprocess.run(["make", "-C", _HERE], check=True, capture_output=True)
     return _SO
@@ -104,6 +104,12 @@ def lib():
         L.orc_translate.restype = None
         L.orc_project_points.argtypes = [vp, vp, C.c_size_t, vp, vp]
         L.orc_project_points.restype = None
+        L.orc_msvc_rand_edges.argtypes = [C.c_uint, C.c_int, vp]
+        L.orc_msvc_rand_edges.restype = None
+        L.orc_segs_intersect.argtypes = [vp, vp, vp, vp]
+        L.orc_point_in_poly.argtypes = [vp, vp, vp, C.c_int, C.c_float, C.c_uint]
+        L.orc_reabsorb.argtypes = [vp, C.c_size_t, vp, vp, vp, C.c_int, C.c_float, C.c_uint, vp, C.c_size_t, vp, vp,
+                                   C.POINTER(C.c_size_t)]
         L.orc_mt_seed.argtypes = [vp, C.c_uint32]
         L.orc_mt_next.argtypes = [vp]
         L.orc_mt_next.restype = C.c_uint32
@@ -313,3 +319,103 @@ def extract_planes(cloud, params: Params) -> Extraction:
     return Extraction(coeffs[:P].copy(), [cur[o[k]: o[k + 1]].copy() for k in range(P)],
                       [orig[o[k]: o[k + 1]].copy() for k in range(P)], rem[: nrem.value].copy(),
                       [traces[k] for k in range(min(P + 1, mp))])
+
+
+# ---- postProcessPlanes re-absorption (Dialog/PlaneDetect.h:1454-1580) ---------------------------------------
+def msvc_rand_edges(seed: int, border_size: int) -> np.ndarray:
+    out = np.zeros(10, np.int32)
+    lib().orc_msvc_rand_edges(int(seed) & 0xFFFFFFFF, int(border_size), _p(out))
+    return out
+
+
+def segs_intersect(pa, pb, pc, pd) -> bool:
+    a, b, c, d = (_cloud(np.asarray(v, np.float32).reshape(1, -1)) for v in (pa, pb, pc, pd))
+    return bool(lib().orc_segs_intersect(_p(a), _p(b), _p(c), _p(d)))
+
+
+def points_in_poly(points, coeff, border, t, seed) -> np.ndarray:
+    pts, bd = _cloud(points), _cloud(border)
+    co = np.ascontiguousarray(coeff, np.float32)
+    L = lib()
+    out = np.zeros(pts.shape[0], bool)
+    for i in range(pts.shape[0]):
+        out[i] = bool(L.orc_point_in_poly(C.c_void_p(pts.ctypes.data + 16 * i), _p(co), _p(bd), bd.shape[0], float(t),
+                                          int(seed) & 0xFFFFFFFF))
+    return out
+
+
+@dataclass
+class Reabsorption:
+    absorbed: list              # per plane: ascending indices of the points it claimed
+    remaining_idx: np.ndarray   # ascending indices of the unclaimed points
+
+
+def reabsorb(cloud, coeffs, borders, t, seed) -> Reabsorption:
+    """borders: list of (nb_j, 3|4) arrays, one polygon per plane."""
+    c = _cloud(cloud)
+    co = np.ascontiguousarray(coeffs, np.float32).reshape(-1, 4)
+    P = co.shape[0]
+    bd = np.concatenate([_cloud(b) for b in borders]) if P else np.zeros((0, 4), np.float32)
+    offs = np.zeros(P + 1, np.uintp)
+    offs[1:] = np.cumsum([len(b) for b in borders])
+    cap = max(1, c.shape[0] * max(P, 1))
+    ab = np.empty(cap, np.int32)
+    po = np.zeros(P + 1, np.uintp)
+    rem = np.empty(max(1, c.shape[0]), np.int32)
+    nrem = C.c_size_t(0)
+    rc = lib().orc_reabsorb(_p(c), c.shape[0], _p(co), _p(bd), _p(offs), P, float(t), int(seed) & 0xFFFFFFFF, _p(ab), cap,
+                            _p(po), _p(rem), C.byref(nrem))
+    if rc != 0:
+        raise RuntimeError("orc_reabsorb failed (empty border?)")
+    o = [int(v) for v in po]
+    return Reabsorption([ab[o[j]: o[j + 1]].copy() for j in range(P)], rem[: nrem.value].copy())
+
+
+# ---- the reference's own source of the same predicate (oracle/build_ref.py) ------------------------------------
+_REF_SO = os.path.join(_HERE, "_ref", "libdialog_ref.so")
+_ref = None
+
+
+def ref_lib():
+    """oracle/_ref/libdialog_ref.so or None.  Built from /root/reference where that exists; prebuilt otherwise."""
+    global _ref
+    if _ref is None:
+        if os.path.exists("/root/reference/Dialog/PlaneDetect.h"):
+            import importlib.util
+            spec = importlib.util.spec_from_file_location("_orc_build_ref", os.path.join(_HERE, "build_ref.py"))
+            mod = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(mod)
+            mod.build()
+        if not os.path.exists(_REF_SO):
+            return None
+        L = C.CDLL(_REF_SO)
+        vp = C.c_void_p
+        L.ref_segs_intersect.argtypes = [vp, vp, vp, vp]
+        L.ref_points_in_poly.argtypes = [vp, C.c_size_t, vp, vp, C.c_int, C.c_float, C.c_uint, vp]
+        L.ref_points_in_poly.restype = None
+        L.ref_project.argtypes = [vp, vp, vp, vp]
+        L.ref_project.restype = None
+        _ref = L
+    return _ref
+
+
+def ref_points_in_poly(points, coeff, border, t, seed) -> np.ndarray:
+    pts, bd = _cloud(points), _cloud(border)
+    co = np.ascontiguousarray(coeff, np.float32)
+    out = np.zeros(pts.shape[0], np.uint8)
+    ref_lib().ref_points_in_poly(_p(pts), pts.shape[0], _p(co), _p(bd), bd.shape[0], float(t), int(seed) & 0xFFFFFFFF, _p(out))
+    return out.astype(bool)
+
+
+def ref_segs_intersect(pa, pb, pc, pd) -> bool:
+    a, b, c, d = (np.ascontiguousarray(v, np.float32)[:3].copy() for v in (pa, pb, pc, pd))
+    return bool(ref_lib().ref_segs_intersect(_p(a), _p(b), _p(c), _p(d)))
+
+
+def ref_project(p, coeff):
+    pp = np.ascontiguousarray(p, np.float32)[:3].copy()
+    co = np.ascontiguousarray(coeff, np.float32)
+    out = np.zeros(3, np.float32)
+    d = np.zeros(1, np.float32)
+    ref_lib().ref_project(_p(pp), _p(co), _p(out), _p(d))
+    return out, float(d[0])

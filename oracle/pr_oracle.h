@@ -127,6 +127,35 @@ void orc_translate(orc_point* cloud, size_t n, const float centroid[3]);
  * stored as float, dest = src - lambda / 2.0 * n evaluated in double and stored as float. */
 void orc_project_points(const orc_point* cloud, const int32_t* idx, size_t n_idx, const float coeff[4], orc_point* out);
 
+/* ---- postProcessPlanes re-absorption (Dialog/PlaneDetect.h:1454-1580; REFERENCE code, not PCL) --------------
+ * The reference's own use of the threshold test + peel: every still-unclaimed point is tested against every
+ * newly found plane polygon with isPointInPoly (:1891-1955) and claimed by each plane that contains it
+ * (no break: a point can join several planes); the unclaimed rest becomes the new source_cloud (:1560-1566).
+ *
+ * Arithmetic restated op for op in FP32 without contraction (MSVC v140 x64 /fp:precise):
+ *   getInfoBetPointAndPlane / projPoint2Plane / distP2P (:1442-1448, 2019-2023, 203-207); dist > T rejects
+ *   (non-strict: dist == T stays a candidate).
+ *   isBothLineSegsIntersect (:1957-2016).
+ * CHOICES (libraries the reference links but does not vendor; flagged for re-verification):
+ *   Eigen Vector3f dot / squaredNorm reduce as e0 + (e1 + e2) (redux_novec_unroller halves the range);
+ *   normalize() divides each component by sqrt(squaredNorm) when squaredNorm > 0 (Eigen >= 3.3);
+ *   pow(a, 0.5f) is taken as the correctly rounded sqrtf(a);
+ *   rand() is the MSVC CRT generator (holdrand = holdrand * 214013 + 2531011; (holdrand >> 16) & 0x7fff),
+ *   re-seeded by srand(seed) at every isPointInPoly call as the reference does with srand(time(0)), so the ten
+ *   ray edges of a plane are a function of (seed, border size) alone. */
+void orc_msvc_rand_edges(unsigned seed, int border_size, int edges[10]);
+int orc_segs_intersect(const orc_point* pa, const orc_point* pb, const orc_point* pc, const orc_point* pd);
+/* 1 if isPointInPoly(p, plane{coeff, border}) with T_dist_point_plane = t, srand(seed). */
+int orc_point_in_poly(const orc_point* p, const float coeff[4], const orc_point* border, int n_border, float t,
+                      unsigned seed);
+/* The loop of postProcessPlanes over an unclaimed cloud: planes j in [0, n_planes) with coeffs[4j..] and border
+ * vertices border[border_offsets[j] .. border_offsets[j+1]).  absorbed: per plane the indices of the points it
+ * claimed, ascending, concatenated; plane_offsets: n_planes + 1; remaining_idx: indices of the unclaimed points,
+ * ascending.  Returns 0, or -1 when a capacity is too small or a border is empty. */
+int orc_reabsorb(const orc_point* cloud, size_t n, const float* coeffs, const orc_point* border,
+                 const size_t* border_offsets, int n_planes, float t, unsigned seed, int32_t* absorbed, size_t absorbed_cap,
+                 size_t* plane_offsets, int32_t* remaining_idx, size_t* n_remaining);
+
 /* ---- RandomSampleConsensus::computeModel + SACSegmentation::segment ----------------------- */
 int orc_segment(const orc_point* cloud, size_t n, const orc_params* prm, int scale_exp_or_min,
                 float coeff[4], int32_t* inliers /* cap n */, size_t* n_inliers, orc_trace* trace);
