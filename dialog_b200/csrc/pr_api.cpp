@@ -189,6 +189,13 @@ struct plane_ransac_ctx {
   // sharding
   ncclComm_t comm = nullptr;
   int n_ranks = 1, rank = 0;
+  // peer-memory exchanges (pr_p2p.cu): this rank's mailbox, the peers' mailboxes mapped through CUDA IPC
+  bool p2p_on = false;
+  unsigned char* p2p_mailbox = nullptr;
+  pr::P2PView p2p_view{};
+  unsigned long long p2p_epoch[4] = {0, 0, 0, 0};  // per channel, identical on every rank
+  DevBuf<unsigned> d_p2p_aux;                       // [0..4) producer tickets, [4] timeout flag
+  PinBuf<unsigned> h_p2p_err;
   long long n_global_staged = 0, first_staged = 0, n_global_current = 0, first_current = 0;
   bool global_valid = false;
 
@@ -531,6 +538,109 @@ int ensure_sorted(plane_ransac_ctx* c, int n_buffers) {
   return PR_OK;
 }
 
+// ---- per-round exchanges: peer-memory kernels when the mailboxes are mapped, NCCL otherwise ------------------------
+// Mailbox layout (bytes): flags[4 channels][8 ranks] u64, then per channel two buffers (epoch parity):
+//   samples  int4[3 * kP2PMaxHyps]                (every entry written by the rank that owns the sampled point)
+//   counts   int32[8 ranks][kP2PMaxHyps]          (summed in rank order by the consumer)
+//   refit    int64[8 ranks][16], totals int64[8 ranks][2]
+// A buffer is rewritten two exchanges of its channel later; a peer can only get there after this rank produced the
+// exchange in between, which in stream order follows this rank's consumption of the buffer.
+constexpr size_t kP2PMaxHyps = 16384;
+enum { P2P_SAMPLES = 0, P2P_COUNTS = 1, P2P_REFIT = 2, P2P_TOTALS = 3 };
+constexpr size_t kP2PFlagBytes = 4 * pr::kP2PMaxRanks * sizeof(unsigned long long);
+constexpr size_t kP2PSamplesBytes = 3 * kP2PMaxHyps * sizeof(int4);
+constexpr size_t kP2PCountsSlot = kP2PMaxHyps * sizeof(int32_t);
+constexpr size_t kP2PRefitSlot = 16 * sizeof(long long);
+constexpr size_t kP2PTotalsSlot = 2 * sizeof(long long);
+constexpr size_t kP2POffSamples = kP2PFlagBytes;
+constexpr size_t kP2POffCounts = kP2POffSamples + 2 * kP2PSamplesBytes;
+constexpr size_t kP2POffRefit = kP2POffCounts + 2 * pr::kP2PMaxRanks * kP2PCountsSlot;
+constexpr size_t kP2POffTotals = kP2POffRefit + 2 * pr::kP2PMaxRanks * kP2PRefitSlot;
+constexpr size_t kP2PMailboxBytes = kP2POffTotals + 2 * pr::kP2PMaxRanks * kP2PTotalsSlot;
+
+inline size_t p2p_flag_off(int ch) { return (size_t)ch * pr::kP2PMaxRanks * sizeof(unsigned long long); }
+
+// K1a + its exchange: sample points of `n_samples` indices into dsp on every rank.
+int exchange_samples(plane_ransac_ctx* c, pr::CloudView src, long long first, size_t n_local, const int32_t* dt, int n_samples,
+                     int4* dsp) {
+  if (c->p2p_on && (size_t)n_samples <= 3 * kP2PMaxHyps) {
+    const unsigned long long e = ++c->p2p_epoch[P2P_SAMPLES];
+    const size_t off = kP2POffSamples + (size_t)(e & 1) * kP2PSamplesBytes;
+    pr::launch_p2p_gather_samples(c->p2p_view, src, first, n_local, dt, n_samples, off, p2p_flag_off(P2P_SAMPLES), e,
+                                  c->d_p2p_aux.p + P2P_SAMPLES, c->stream);
+    pr::launch_p2p_wait_copy(c->p2p_view, off, p2p_flag_off(P2P_SAMPLES), e, dsp, (size_t)n_samples * sizeof(int4),
+                             c->d_p2p_aux.p + 4, c->stream);
+    return PR_OK;
+  }
+  pr::launch_gather_samples(src, first, n_local, dt, n_samples, dsp, 1, 0, c->stream);
+  if (c->comm) PR_NCCL(g_nccl.AllReduce(dsp, dsp, (size_t)n_samples * 4, ncclInt32, ncclSum, c->comm, c->stream));
+  return PR_OK;
+}
+
+// counts[0..n) summed over ranks, in place.
+int exchange_counts(plane_ransac_ctx* c, int32_t* dc, size_t n) {
+  if (!c->comm) return PR_OK;
+  if (c->p2p_on && n <= kP2PMaxHyps) {
+    const unsigned long long e = ++c->p2p_epoch[P2P_COUNTS];
+    const size_t base = kP2POffCounts + (size_t)(e & 1) * pr::kP2PMaxRanks * kP2PCountsSlot;
+    pr::launch_p2p_push(c->p2p_view, dc, n * sizeof(int32_t), base + (size_t)c->rank * kP2PCountsSlot, p2p_flag_off(P2P_COUNTS), e,
+                        c->d_p2p_aux.p + P2P_COUNTS, c->stream);
+    pr::launch_p2p_wait_sum_i32(c->p2p_view, base, kP2PCountsSlot, p2p_flag_off(P2P_COUNTS), e, dc, n, c->d_p2p_aux.p + 4, c->stream);
+    return PR_OK;
+  }
+  PR_NCCL(g_nccl.AllReduce(dc, dc, n, ncclInt32, ncclSum, c->comm, c->stream));
+  return PR_OK;
+}
+
+// the 16 integer moments of d_refit summed over ranks, in place (the pivot behind them is identical everywhere).
+int exchange_refit(plane_ransac_ctx* c) {
+  if (!c->comm) return PR_OK;
+  if (c->p2p_on) {
+    const unsigned long long e = ++c->p2p_epoch[P2P_REFIT];
+    const size_t base = kP2POffRefit + (size_t)(e & 1) * pr::kP2PMaxRanks * kP2PRefitSlot;
+    pr::launch_p2p_push(c->p2p_view, c->d_refit.p, kP2PRefitSlot, base + (size_t)c->rank * kP2PRefitSlot, p2p_flag_off(P2P_REFIT), e,
+                        c->d_p2p_aux.p + P2P_REFIT, c->stream);
+    pr::launch_p2p_wait_sum_i64(c->p2p_view, base, kP2PRefitSlot, p2p_flag_off(P2P_REFIT), e,
+                                reinterpret_cast<long long*>(c->d_refit.p), 16, c->d_p2p_aux.p + 4, c->stream);
+    return PR_OK;
+  }
+  PR_NCCL(g_nccl.AllReduce(c->d_refit.p, c->d_refit.p, 16, ncclInt64, ncclSum, c->comm, c->stream));
+  return PR_OK;
+}
+
+// all-gather of (remaining, inliers): d_totals[0..2) of every rank -> d_totals[2 + 2r ..).
+int exchange_totals(plane_ransac_ctx* c) {
+  if (!c->comm) return PR_OK;
+  if (c->p2p_on) {
+    const unsigned long long e = ++c->p2p_epoch[P2P_TOTALS];
+    const size_t base = kP2POffTotals + (size_t)(e & 1) * pr::kP2PMaxRanks * kP2PTotalsSlot;
+    pr::launch_p2p_push(c->p2p_view, c->d_totals.p, kP2PTotalsSlot, base + (size_t)c->rank * kP2PTotalsSlot, p2p_flag_off(P2P_TOTALS), e,
+                        c->d_p2p_aux.p + P2P_TOTALS, c->stream);
+    pr::launch_p2p_wait_copy(c->p2p_view, base, p2p_flag_off(P2P_TOTALS), e, c->d_totals.p + 2, (size_t)c->n_ranks * kP2PTotalsSlot,
+                             c->d_p2p_aux.p + 4, c->stream);
+    return PR_OK;
+  }
+  PR_NCCL(g_nccl.AllGather(c->d_totals.p, c->d_totals.p + 2, 2, ncclInt64, c->comm, c->stream));
+  return PR_OK;
+}
+
+void p2p_teardown(plane_ransac_ctx* c) {
+  for (int r = 0; r < pr::kP2PMaxRanks; ++r) {
+    if (c->p2p_view.peers[r] && r != c->rank) cudaIpcCloseMemHandle(c->p2p_view.peers[r]);
+    c->p2p_view.peers[r] = nullptr;
+  }
+  if (c->p2p_mailbox) cudaFree(c->p2p_mailbox);
+  c->p2p_mailbox = nullptr;
+  c->p2p_on = false;
+  cudaGetLastError();
+}
+
+// After a stream synchronisation: did a consumer give up waiting for a peer?
+int p2p_check(plane_ransac_ctx* c) {
+  if (c->p2p_on && c->h_p2p_err.p && *c->h_p2p_err.p) return fail(PR_ERR_COMM, "a peer rank did not deliver its part of an exchange within 3 s");
+  return PR_OK;
+}
+
 struct SegmentOut {
   float coeff[4] = {0, 0, 0, 0};
   long long n_inl_local = 0, n_rem_local = 0;
@@ -610,8 +720,7 @@ int segment_core(plane_ransac_ctx* c, const pr_params* prm, pr::CloudView src, s
         PR_CUDA(cudaMemcpyAsync(dt, ht, 3 * sb * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
         {
           Span sp(c, KC_MODELS, 2);
-          pr::launch_gather_samples(src, first, n_local, dt, (int)(3 * sb), dsp, 1, 0, c->stream);
-          if (c->comm) PR_NCCL(g_nccl.AllReduce(dsp, dsp, (size_t)(3 * sb) * 4, ncclInt32, ncclSum, c->comm, c->stream));
+          PR_TRY(exchange_samples(c, src, first, n_local, dt, (int)(3 * sb), dsp));
           pr::launch_models(dsp, (int)sb, dh, dg, c->stream);
         }
         PR_CUDA(cudaMemsetAsync(dc, 0, sb * sizeof(int32_t), c->stream));
@@ -630,7 +739,7 @@ int segment_core(plane_ransac_ctx* c, const pr_params* prm, pr::CloudView src, s
       }
       int32_t* dc = c->d_counts.p + total_draws;
       int32_t* dg = c->d_good.p + total_draws;
-      if (c->comm) PR_NCCL(g_nccl.AllReduce(dc, dc, (size_t)B, ncclInt32, ncclSum, c->comm, c->stream));
+      PR_TRY(exchange_counts(c, dc, (size_t)B));
       PR_CUDA(cudaGetLastError());
       PR_CUDA(cudaMemcpyAsync(c->h_counts.p + total_draws, dc, B * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
       PR_CUDA(cudaMemcpyAsync(c->h_good.p + total_draws, dg, B * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
@@ -669,7 +778,7 @@ int segment_core(plane_ransac_ctx* c, const pr_params* prm, pr::CloudView src, s
       c->prof.points_refit += (long long)n_local;
       c->prof.bytes_refit += 12ll * (long long)n_local;
     }
-    if (c->comm) PR_NCCL(g_nccl.AllReduce(c->d_refit.p, c->d_refit.p, 16, ncclInt64, ncclSum, c->comm, c->stream));
+    PR_TRY(exchange_refit(c));
     PR_CUDA(cudaMemcpyAsync(c->h_refit.p, c->d_refit.p, sizeof(pr::RefitOut), cudaMemcpyDeviceToHost, c->stream));
   }
   PR_CUDA(cudaMemcpyAsync(c->h_small.p, c->d_hyps.p + best, sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
@@ -694,9 +803,10 @@ int segment_core(plane_ransac_ctx* c, const pr_params* prm, pr::CloudView src, s
     c->prof.points_compact += (long long)n_local;
   }
   PR_CUDA(cudaGetLastError());
-  if (c->comm) PR_NCCL(g_nccl.AllGather(c->d_totals.p, c->d_totals.p + 2, 2, ncclInt64, c->comm, c->stream));
+  PR_TRY(exchange_totals(c));
   PR_CUDA(cudaMemcpyAsync(c->h_totals.p, c->d_totals.p, (2 + (c->comm ? 2 * c->n_ranks : 0)) * sizeof(long long),
                           cudaMemcpyDeviceToHost, c->stream));
+  if (c->p2p_on) PR_CUDA(cudaMemcpyAsync(c->h_p2p_err.p, c->d_p2p_aux.p + 4, sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
   if (hier && sdst && write_remaining) {
     // the sorted copy is peeled with the same predicate (stable, so it stays in Morton order)
     Span sp(c, KC_COMPACT, 1);
@@ -706,6 +816,7 @@ int segment_core(plane_ransac_ctx* c, const pr_params* prm, pr::CloudView src, s
     c->prof.bytes_compact += 12ll * (long long)n_local;
   }
   PR_TRY(sync_stream(c));
+  PR_TRY(p2p_check(c));
   out->n_rem_local = c->h_totals.p[0];
   out->n_inl_local = c->h_totals.p[1];
   out->n_inl_global = out->n_inl_local;
@@ -794,6 +905,9 @@ void plane_ransac_destroy(plane_ransac_ctx* c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   collect_spans(c);
+  p2p_teardown(c);
+  dev_free(c->d_p2p_aux);
+  pin_free(c->h_p2p_err);
   if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
   dev_free(c->staged_mem);
   for (int i = 0; i < 2; ++i) { dev_free(c->work_mem[i]); dev_free(c->work_orig[i]); }
@@ -1390,6 +1504,83 @@ int plane_ransac_comm_unique_id(void* out128) {
   return PR_OK;
 }
 
+namespace {
+
+// Maps every peer's mailbox (CUDA IPC over NVLink).  Collective; all ranks end with the same p2p_on: if any rank
+// cannot map a peer (no P2P path, IPC unavailable) or PR_P2P=0 is set, every rank keeps the NCCL exchanges.
+int p2p_setup(plane_ransac_ctx* c) {
+  c->p2p_on = false;
+  if (c->n_ranks < 2) return PR_OK;
+  const char* env = getenv("PR_P2P");
+  int ok = (c->n_ranks <= pr::kP2PMaxRanks && !(env && atoi(env) == 0)) ? 1 : 0;
+  PR_TRY(dev_reserve(c->d_p2p_aux, 8));
+  PR_TRY(pin_reserve(c->h_p2p_err, 1));
+  *c->h_p2p_err.p = 0;
+  PR_CUDA(cudaMemsetAsync(c->d_p2p_aux.p, 0, 8 * sizeof(unsigned), c->stream));
+  cudaIpcMemHandle_t mine;
+  std::memset(&mine, 0, sizeof(mine));
+  if (ok) {
+    if (cudaMalloc(&c->p2p_mailbox, kP2PMailboxBytes) != cudaSuccess || cudaMemset(c->p2p_mailbox, 0, kP2PMailboxBytes) != cudaSuccess ||
+        cudaDeviceSynchronize() != cudaSuccess || cudaIpcGetMemHandle(&mine, c->p2p_mailbox) != cudaSuccess) {
+      cudaGetLastError();
+      ok = 0;
+    }
+  }
+  // all-gather of the handles (64 bytes each) and of the per-rank verdicts through NCCL
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t size");
+  const size_t rec = 64 + 8;
+  DevBuf<unsigned char> d_h;
+  PR_TRY(dev_reserve(d_h, rec * (size_t)(c->n_ranks + 1)));
+  std::vector<unsigned char> h((size_t)(c->n_ranks + 1) * rec, 0);
+  std::memcpy(h.data(), &mine, 64);
+  h[64] = (unsigned char)ok;
+  int rc = PR_OK;
+  auto gather = [&]() -> int {
+    PR_CUDA(cudaMemcpyAsync(d_h.p, h.data(), rec, cudaMemcpyHostToDevice, c->stream));
+    PR_NCCL(g_nccl.AllGather(d_h.p, d_h.p + rec, rec, ncclUint8, c->comm, c->stream));
+    PR_CUDA(cudaMemcpyAsync(h.data() + rec, d_h.p + rec, rec * (size_t)c->n_ranks, cudaMemcpyDeviceToHost, c->stream));
+    PR_CUDA(cudaStreamSynchronize(c->stream));
+    return PR_OK;
+  };
+  rc = gather();
+  if (rc == PR_OK) {
+    for (int r = 0; r < c->n_ranks; ++r) ok = ok && h[rec * (size_t)(r + 1) + 64];
+    c->p2p_view.n_ranks = c->n_ranks;
+    c->p2p_view.rank = c->rank;
+    for (int r = 0; r < pr::kP2PMaxRanks; ++r) c->p2p_view.peers[r] = nullptr;
+    if (ok) {
+      for (int r = 0; r < c->n_ranks; ++r) {
+        if (r == c->rank) {
+          c->p2p_view.peers[r] = c->p2p_mailbox;
+          continue;
+        }
+        cudaIpcMemHandle_t hr;
+        std::memcpy(&hr, h.data() + rec * (size_t)(r + 1), 64);
+        void* ptr = nullptr;
+        if (cudaIpcOpenMemHandle(&ptr, hr, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+          cudaGetLastError();
+          ok = 0;
+          break;
+        }
+        c->p2p_view.peers[r] = static_cast<unsigned char*>(ptr);
+      }
+    }
+    // second round: did every rank map every peer?
+    h[64] = (unsigned char)ok;
+    rc = gather();
+    if (rc == PR_OK)
+      for (int r = 0; r < c->n_ranks; ++r) ok = ok && h[rec * (size_t)(r + 1) + 64];
+  }
+  dev_free(d_h);
+  if (rc != PR_OK) ok = 0;
+  if (!ok) p2p_teardown(c);
+  c->p2p_on = ok != 0;
+  for (auto& e : c->p2p_epoch) e = 0;
+  return rc;
+}
+
+}  // namespace
+
 int plane_ransac_comm_init(plane_ransac_ctx* c, int n_ranks, int rank, const void* unique_id128) {
   PR_TRY(check_ctx(c));
   if (n_ranks < 1 || rank < 0 || rank >= n_ranks || !unique_id128) return fail(PR_ERR_INVALID, "bad rank/n_ranks/id");
@@ -1401,6 +1592,7 @@ int plane_ransac_comm_init(plane_ransac_ctx* c, int n_ranks, int rank, const voi
   c->n_ranks = n_ranks;
   c->rank = rank;
   PR_TRY(reserve_small(c));
+  PR_TRY(p2p_setup(c));
   if (c->have_cloud) {
     PR_TRY(refresh_global(c));
     c->n_global_current = c->n_global_staged;
@@ -1408,6 +1600,8 @@ int plane_ransac_comm_init(plane_ransac_ctx* c, int n_ranks, int rank, const voi
   }
   return PR_OK;
 }
+
+int plane_ransac_comm_p2p_enabled(plane_ransac_ctx* c) { return c && c->p2p_on ? 1 : 0; }
 
 int plane_ransac_shard_info(plane_ransac_ctx* c, long long* n_global_staged, long long* first_staged,
                             long long* n_global_current, long long* first_current) {

@@ -296,6 +296,10 @@ class PlaneRansac:
         buf = C.create_string_buffer(unique_id, _lib.UNIQUE_ID_BYTES)
         _lib.check(self._L.plane_ransac_comm_init(self._h, n_ranks, rank, buf))
 
+    def p2p_enabled(self) -> bool:
+        """True when the per-round exchanges run as peer-memory kernels over NVLink instead of NCCL collectives."""
+        return bool(self._L.plane_ransac_comm_p2p_enabled(self._h))
+
     def shard_info(self):
         v = [C.c_longlong(0) for _ in range(4)]
         _lib.check(self._L.plane_ransac_shard_info(self._h, *[C.byref(x) for x in v]))

@@ -202,6 +202,11 @@ int plane_ransac_segment_batch(plane_ransac_ctx* ctx, const pr_params* prm, floa
 #define PLANE_RANSAC_UNIQUE_ID_BYTES 128
 int plane_ransac_comm_unique_id(void* out128);
 int plane_ransac_comm_init(plane_ransac_ctx* ctx, int n_ranks, int rank, const void* unique_id128);
+/* 1 when the per-round exchanges (sample points, per-hypothesis counts, refit moments, remaining counts) run as
+ * peer-memory kernels: every rank owns a mailbox in its HBM that the peers map with CUDA IPC and write over NVLink,
+ * flags with system-scope release/acquire, sums in rank order (bit-identical to one GPU).  0: NCCL collectives (set
+ * PR_P2P=0, more than 8 ranks, or a peer that could not be mapped — decided collectively at comm_init). */
+int plane_ransac_comm_p2p_enabled(plane_ransac_ctx* ctx);
 /* Global size and this rank's first global index for the staged / current cloud. */
 int plane_ransac_shard_info(plane_ransac_ctx* ctx, long long* n_global_staged, long long* first_staged,
                             long long* n_global_current, long long* first_current);

@@ -38,6 +38,8 @@ def main():
     uid = [D.PlaneRansac.comm_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(uid, src=0)
     sh.comm_init(world, rank, uid[0])
+    want_p2p = os.environ.get("PR_P2P", "1") != "0"
+    assert sh.p2p_enabled() == want_p2p, f"peer-memory exchanges: enabled={sh.p2p_enabled()}, expected {want_p2p}"
     sh.set_cloud(pts[first: first + count])
     assert sh.shard_info()[:2] == (n, first)
     got_counts = sh.score(D.host_draw_triples(n, 300), 0.1)
@@ -81,7 +83,8 @@ def main():
     sh.close()
     dist.barrier()
     if rank == 0:
-        print(f"multi-GPU check ok: {world} ranks, {len(got.planes)} planes, bit-identical to one GPU")
+        print(f"multi-GPU check ok: {world} ranks, {len(got.planes)} planes, bit-identical to one GPU, "
+              f"exchanges: {'peer-memory kernels' if want_p2p else 'NCCL'}")
     dist.destroy_process_group()
 
 

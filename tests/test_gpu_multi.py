@@ -10,7 +10,8 @@ from conftest import ROOT
 pytestmark = pytest.mark.gpu
 
 
-def test_sharded_extraction_matches_single_gpu(lib_built):
+@pytest.mark.parametrize("p2p", ["1", "0"])
+def test_sharded_extraction_matches_single_gpu(lib_built, p2p):
     import torch
     n = torch.cuda.device_count()
     if n < 2:
@@ -18,6 +19,7 @@ def test_sharded_extraction_matches_single_gpu(lib_built):
     world = 2 if n < 4 else 4
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
            "--master-addr", "127.0.0.1", "--master-port", "29511", os.path.join(ROOT, "tests", "multi_gpu_check.py")]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, PR_P2P=p2p))
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "multi-GPU check ok" in r.stdout
+    assert ("peer-memory kernels" if p2p == "1" else "NCCL") in r.stdout
