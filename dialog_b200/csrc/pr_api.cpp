@@ -120,6 +120,8 @@ struct plane_ransac_ctx {
   int device = 0;
   int num_sms = 148;
   cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;  // index lists go back to pinned host buffers while later rounds compute
+  cudaEvent_t copy_ready = nullptr;
 
   // staged cloud (immutable) and the two peel buffers
   pr::CloudView staged, work[2];
@@ -566,10 +568,8 @@ int exchange_samples(plane_ransac_ctx* c, pr::CloudView src, long long first, si
   if (c->p2p_on && (size_t)n_samples <= 3 * kP2PMaxHyps) {
     const unsigned long long e = ++c->p2p_epoch[P2P_SAMPLES];
     const size_t off = kP2POffSamples + (size_t)(e & 1) * kP2PSamplesBytes;
-    pr::launch_p2p_gather_samples(c->p2p_view, src, first, n_local, dt, n_samples, off, p2p_flag_off(P2P_SAMPLES), e,
-                                  c->d_p2p_aux.p + P2P_SAMPLES, c->stream);
-    pr::launch_p2p_wait_copy(c->p2p_view, off, p2p_flag_off(P2P_SAMPLES), e, dsp, (size_t)n_samples * sizeof(int4),
-                             c->d_p2p_aux.p + 4, c->stream);
+    pr::launch_p2p_samples(c->p2p_view, src, first, n_local, dt, n_samples, off, p2p_flag_off(P2P_SAMPLES), e, dsp,
+                           c->d_p2p_aux.p + 4, c->stream);
     return PR_OK;
   }
   pr::launch_gather_samples(src, first, n_local, dt, n_samples, dsp, 1, 0, c->stream);
@@ -583,9 +583,7 @@ int exchange_counts(plane_ransac_ctx* c, int32_t* dc, size_t n) {
   if (c->p2p_on && n <= kP2PMaxHyps) {
     const unsigned long long e = ++c->p2p_epoch[P2P_COUNTS];
     const size_t base = kP2POffCounts + (size_t)(e & 1) * pr::kP2PMaxRanks * kP2PCountsSlot;
-    pr::launch_p2p_push(c->p2p_view, dc, n * sizeof(int32_t), base + (size_t)c->rank * kP2PCountsSlot, p2p_flag_off(P2P_COUNTS), e,
-                        c->d_p2p_aux.p + P2P_COUNTS, c->stream);
-    pr::launch_p2p_wait_sum_i32(c->p2p_view, base, kP2PCountsSlot, p2p_flag_off(P2P_COUNTS), e, dc, n, c->d_p2p_aux.p + 4, c->stream);
+    pr::launch_p2p_allreduce_i32(c->p2p_view, dc, n, base, kP2PCountsSlot, p2p_flag_off(P2P_COUNTS), e, dc, c->d_p2p_aux.p + 4, c->stream);
     return PR_OK;
   }
   PR_NCCL(g_nccl.AllReduce(dc, dc, n, ncclInt32, ncclSum, c->comm, c->stream));
@@ -598,10 +596,8 @@ int exchange_refit(plane_ransac_ctx* c) {
   if (c->p2p_on) {
     const unsigned long long e = ++c->p2p_epoch[P2P_REFIT];
     const size_t base = kP2POffRefit + (size_t)(e & 1) * pr::kP2PMaxRanks * kP2PRefitSlot;
-    pr::launch_p2p_push(c->p2p_view, c->d_refit.p, kP2PRefitSlot, base + (size_t)c->rank * kP2PRefitSlot, p2p_flag_off(P2P_REFIT), e,
-                        c->d_p2p_aux.p + P2P_REFIT, c->stream);
-    pr::launch_p2p_wait_sum_i64(c->p2p_view, base, kP2PRefitSlot, p2p_flag_off(P2P_REFIT), e,
-                                reinterpret_cast<long long*>(c->d_refit.p), 16, c->d_p2p_aux.p + 4, c->stream);
+    long long* m = reinterpret_cast<long long*>(c->d_refit.p);
+    pr::launch_p2p_allreduce_i64(c->p2p_view, m, 16, base, kP2PRefitSlot, p2p_flag_off(P2P_REFIT), e, m, c->d_p2p_aux.p + 4, c->stream);
     return PR_OK;
   }
   PR_NCCL(g_nccl.AllReduce(c->d_refit.p, c->d_refit.p, 16, ncclInt64, ncclSum, c->comm, c->stream));
@@ -614,10 +610,8 @@ int exchange_totals(plane_ransac_ctx* c) {
   if (c->p2p_on) {
     const unsigned long long e = ++c->p2p_epoch[P2P_TOTALS];
     const size_t base = kP2POffTotals + (size_t)(e & 1) * pr::kP2PMaxRanks * kP2PTotalsSlot;
-    pr::launch_p2p_push(c->p2p_view, c->d_totals.p, kP2PTotalsSlot, base + (size_t)c->rank * kP2PTotalsSlot, p2p_flag_off(P2P_TOTALS), e,
-                        c->d_p2p_aux.p + P2P_TOTALS, c->stream);
-    pr::launch_p2p_wait_copy(c->p2p_view, base, p2p_flag_off(P2P_TOTALS), e, c->d_totals.p + 2, (size_t)c->n_ranks * kP2PTotalsSlot,
-                             c->d_p2p_aux.p + 4, c->stream);
+    pr::launch_p2p_allgather_i64(c->p2p_view, c->d_totals.p, 2, base, kP2PTotalsSlot, p2p_flag_off(P2P_TOTALS), e, c->d_totals.p + 2,
+                                 c->d_p2p_aux.p + 4, c->stream);
     return PR_OK;
   }
   PR_NCCL(g_nccl.AllGather(c->d_totals.p, c->d_totals.p + 2, 2, ncclInt64, c->comm, c->stream));
@@ -892,7 +886,11 @@ int plane_ransac_create(plane_ransac_ctx** out, int device_id) {
   c->device = device_id;
   c->num_sms = prop.multiProcessorCount;
   std::memset(&c->prof, 0, sizeof(c->prof));
-  if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+  if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&c->copy_ready, cudaEventDisableTiming) != cudaSuccess) {
+    if (c->stream) cudaStreamDestroy(c->stream);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     delete c;
     return fail(PR_ERR_CUDA, "cudaStreamCreate failed");
   }
@@ -927,6 +925,9 @@ void plane_ransac_destroy(plane_ransac_ctx* c) {
   pin_free(c->h_totals); pin_free(c->h_small);
   if (c->timer_a) { cudaEventDestroy(c->timer_a); cudaEventDestroy(c->timer_b); }
   for (cudaEvent_t e : c->event_pool) cudaEventDestroy(e);
+  cudaStreamSynchronize(c->copy_stream);
+  cudaEventDestroy(c->copy_ready);
+  cudaStreamDestroy(c->copy_stream);
   cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -1068,6 +1069,16 @@ int plane_ransac_extract_planes(plane_ransac_ctx* c, const pr_params* prm, float
   plane_offsets[0] = 0;
   *n_planes = 0;
   const bool want_lists = inlier_cur || inlier_orig;
+  // Pinned destination buffers: each plane's index lists go back on the copy stream as soon as its round is done,
+  // under the scoring of the following rounds (a pageable destination would make the copy block the host instead).
+  auto is_pinned = [](const void* p) {
+    cudaPointerAttributes a;
+    if (!p) return true;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+  };
+  const bool overlap_copy = want_lists && is_pinned(inlier_cur) && is_pinned(inlier_orig);
+  size_t copied = 0;
   while (planes < prm->max_planes) {
     pr::CloudView dst = c->work[planes & 1];
     SegmentOut so;
@@ -1084,6 +1095,11 @@ int plane_ransac_extract_planes(plane_ransac_ctx* c, const pr_params* prm, float
     off += (size_t)so.n_inl_local;
     plane_offsets[planes + 1] = off;
     ++planes;
+    if (overlap_copy && off > copied) {  // segment_core ended with a stream synchronisation: the lists are complete
+      if (inlier_cur) PR_CUDA(cudaMemcpyAsync(inlier_cur + copied, c->d_inl_cur.p + copied, (off - copied) * sizeof(int32_t), cudaMemcpyDeviceToHost, c->copy_stream));
+      if (inlier_orig) PR_CUDA(cudaMemcpyAsync(inlier_orig + copied, c->d_inl_orig.p + copied, (off - copied) * sizeof(int32_t), cudaMemcpyDeviceToHost, c->copy_stream));
+      copied = off;
+    }
     src = dst;
     s_cur = s_next;
     n_local = (size_t)so.n_rem_local;
@@ -1107,8 +1123,12 @@ int plane_ransac_extract_planes(plane_ransac_ctx* c, const pr_params* prm, float
   c->n_current = n_local;
   c->n_global_current = n_global;
   c->first_current = first;
-  if (off && inlier_cur) PR_CUDA(cudaMemcpyAsync(inlier_cur, c->d_inl_cur.p, off * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
-  if (off && inlier_orig) PR_CUDA(cudaMemcpyAsync(inlier_orig, c->d_inl_orig.p, off * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+  if (overlap_copy) {
+    PR_CUDA(cudaStreamSynchronize(c->copy_stream));
+  } else {
+    if (off && inlier_cur) PR_CUDA(cudaMemcpyAsync(inlier_cur, c->d_inl_cur.p, off * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    if (off && inlier_orig) PR_CUDA(cudaMemcpyAsync(inlier_orig, c->d_inl_orig.p, off * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+  }
   PR_TRY(sync_stream(c));
   return PR_OK;
 }

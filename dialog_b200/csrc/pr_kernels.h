@@ -129,20 +129,19 @@ struct P2PView {
   int n_ranks;
   int rank;
 };
-// Producers: copy `bytes` from src into every peer's mailbox at dst_off, then raise flag[rank] = epoch (at flag_off,
-// kP2PMaxRanks x uint64) in every peer's mailbox.  ticket: one zeroed unsigned per producer kind.
-void launch_p2p_push(const P2PView& v, const void* src, size_t bytes, size_t dst_off, size_t flag_off, unsigned long long epoch,
-                     unsigned* ticket, cudaStream_t s);
-// K1a fused with its exchange: the owner of sample s writes the point's bits into every peer's sample buffer at sp_off.
-void launch_p2p_gather_samples(const P2PView& v, CloudView cloud, long long first, size_t n, const int32_t* triples, int n_samples,
-                               size_t sp_off, size_t flag_off, unsigned long long epoch, unsigned* ticket, cudaStream_t s);
-// Consumers: wait (bounded, *err = 1 on timeout) until every rank's flag reached epoch, then copy / sum in rank order.
-void launch_p2p_wait_copy(const P2PView& v, size_t src_off, size_t flag_off, unsigned long long epoch, void* dst, size_t bytes,
-                          unsigned* err, cudaStream_t s);
-void launch_p2p_wait_sum_i32(const P2PView& v, size_t slot_off, size_t slot_stride, size_t flag_off, unsigned long long epoch,
-                             int32_t* dst, size_t n, unsigned* err, cudaStream_t s);
-void launch_p2p_wait_sum_i64(const P2PView& v, size_t slot_off, size_t slot_stride, size_t flag_off, unsigned long long epoch,
-                             long long* dst, size_t n, unsigned* err, cudaStream_t s);
+// One single-CTA kernel per exchange: store this rank's contribution into every peer's mailbox slot
+// (slot_off + rank * slot_stride), raise flag[rank] = epoch in every peer's flag array (flag_off, kP2PMaxRanks x
+// uint64), wait (bounded; *err = 1 on timeout) for every rank's flag locally, then sum / concatenate in rank order.
+void launch_p2p_allreduce_i32(const P2PView& v, const int32_t* src, size_t n, size_t slot_off, size_t slot_stride, size_t flag_off,
+                              unsigned long long epoch, int32_t* dst, unsigned* err, cudaStream_t s);
+void launch_p2p_allreduce_i64(const P2PView& v, const long long* src, size_t n, size_t slot_off, size_t slot_stride, size_t flag_off,
+                              unsigned long long epoch, long long* dst, unsigned* err, cudaStream_t s);
+void launch_p2p_allgather_i64(const P2PView& v, const long long* src, size_t n, size_t slot_off, size_t slot_stride, size_t flag_off,
+                              unsigned long long epoch, long long* dst, unsigned* err, cudaStream_t s);
+// K1a fused with its exchange: the owner of sample s writes the point's bits into every rank's sample buffer (sp_off);
+// dst receives all n_samples entries.
+void launch_p2p_samples(const P2PView& v, CloudView cloud, long long first, size_t n, const int32_t* triples, int n_samples,
+                        size_t sp_off, size_t flag_off, unsigned long long epoch, int4* dst, unsigned* err, cudaStream_t s);
 
 // Measurement helpers.
 void launch_ffma_peak(float* out, int iters, int grid, cudaStream_t s);
