@@ -146,7 +146,8 @@ struct plane_ransac_ctx {
   float cmax = 0.f;
   std::vector<size_t> last_offsets;   // plane offsets into d_inl_orig of the last extract call
   std::vector<float> last_coeffs;     // 4 per plane
-  DevBuf<int32_t> d_stage_map;  // staged point -> index in the caller's array (only after a filtered staging)
+  DevBuf<int32_t> d_stage_map;  // staged point -> index in the caller's array (only after a filtered staging / restage)
+  DevBuf<int32_t> d_stage_map_tmp;
   bool have_stage_map = false;
 
   DevBuf<float4> aos;        // AoS staging (upload / download)
@@ -913,6 +914,7 @@ void plane_ransac_destroy(plane_ransac_ctx* c) {
   dev_free(c->d_sample_pts); dev_free(c->d_hyps); dev_free(c->d_refit); dev_free(c->d_totals);
   dev_free(c->d_scratch); dev_free(c->d_inl_cur); dev_free(c->d_inl_orig); dev_free(c->d_flush); dev_free(c->batch_mem);
   dev_free(c->d_stage_map);
+  dev_free(c->d_stage_map_tmp);
   for (int i = 0; i < 3; ++i) dev_free(c->sorted_mem[i]);
   dev_free(c->d_bounds); dev_free(c->d_aux); dev_free(c->d_keys); dev_free(c->d_vals); dev_free(c->d_sort_temp);
   dev_free(c->d_totals2);
@@ -1172,6 +1174,38 @@ int plane_ransac_remaining(plane_ransac_ctx* c, pr_point* out, size_t cap, size_
   return PR_OK;
 }
 
+
+// ---- "run again" (Dialog/PCLViewer.cpp:1120-1178): the cloud left by the last call becomes the staged cloud --------
+int plane_ransac_restage_remaining(plane_ransac_ctx* c) {
+  PR_TRY(check_ctx(c));
+  if (c->profiling) collect_spans(c);
+  if (!c->have_cloud) return fail(PR_ERR_NO_CLOUD, "no cloud staged");
+  c->last_offsets.clear();
+  c->last_coeffs.clear();
+  if (c->current.x == c->staged.x) return PR_OK;  // nothing was peeled
+  const size_t n = c->n_current, cap = c->staged.cap;
+  const size_t padded = std::min(cap, pr::padded_capacity(n));  // the peel re-padded [n, padded) with NaN
+  // staged point -> caller's index: compose the peel's original-index plane with the map of a filtered staging
+  PR_TRY(dev_reserve(c->d_stage_map_tmp, std::max<size_t>(cap, 1)));
+  {
+    Span sp(c, KC_STAGE, n ? 1 : 0);
+    pr::launch_compose_map(c->current.orig, c->have_stage_map ? c->d_stage_map.p : nullptr, n, c->d_stage_map_tmp.p, c->stream);
+  }
+  PR_CUDA(cudaGetLastError());
+  std::swap(c->d_stage_map, c->d_stage_map_tmp);
+  c->have_stage_map = true;
+  const float* src[3] = {c->current.x, c->current.y, c->current.z};
+  float* dst[3] = {c->staged.x, c->staged.y, c->staged.z};
+  for (int a = 0; a < 3; ++a) PR_CUDA(cudaMemcpyAsync(dst[a], src[a], padded * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
+  PR_CUDA(cudaStreamSynchronize(c->stream));
+  // the old bounding box still contains every point: the refit grid (scale_exp) stays valid
+  c->n_staged = n;
+  c->current = c->staged;
+  c->n_global_staged = c->n_global_current;
+  c->first_staged = c->first_current;
+  c->sorted_staged_valid = false;
+  return PR_OK;
+}
 
 // ---- postProcessPlanes re-absorption (Dialog/PlaneDetect.h:1454-1580) ------------------------------
 int plane_ransac_reabsorb(plane_ransac_ctx* c, const float* coeffs, const pr_point* border, const size_t* border_offsets,

@@ -288,6 +288,23 @@ void launch_plane_points(CloudView cloud, const int32_t* idx, size_t n, Plane4 p
   plane_points_kernel<<<(unsigned)blocks, 256, 0, s>>>(cloud.x, cloud.y, cloud.z, idx, n, pl, project, out);
 }
 
+// out[i] = map ? map[idx[i]] : idx[i]  (composition of index maps when a peeled cloud becomes the staged cloud)
+__global__ void __launch_bounds__(256) compose_map_kernel(const int32_t* __restrict__ idx, const int32_t* __restrict__ map, size_t n,
+                                                          int32_t* __restrict__ out) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const int32_t j = idx[i];
+    out[i] = map ? map[j] : j;
+  }
+}
+
+void launch_compose_map(const int32_t* idx, const int32_t* map, size_t n, int32_t* out, cudaStream_t s) {
+  if (n == 0) return;
+  size_t blocks = (n + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  compose_map_kernel<<<(unsigned)blocks, 256, 0, s>>>(idx, map, n, out);
+}
+
 void launch_unstage(CloudView src, size_t n, float4* aos, cudaStream_t s) {
   if (n == 0) return;
   size_t blocks = (n + 255) / 256;

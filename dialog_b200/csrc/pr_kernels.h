@@ -50,6 +50,8 @@ void launch_centroid(CloudView c, size_t n, const double lo[3], int scale_exp, l
 void launch_translate(CloudView c, size_t n, const float centroid[3], int num_sms, cudaStream_t s);
 // out[i] = cloud[idx[i]] (w = 1), optionally projected onto `pl` (reference projPoint2Plane arithmetic).
 void launch_plane_points(CloudView cloud, const int32_t* idx, size_t n, Plane4 pl, bool project, float4* out, cudaStream_t s);
+// out[i] = map ? map[idx[i]] : idx[i]
+void launch_compose_map(const int32_t* idx, const int32_t* map, size_t n, int32_t* out, cudaStream_t s);
 // planes -> AoS (w = 1)
 void launch_unstage(CloudView src, size_t n, float4* aos, cudaStream_t s);
 

@@ -143,6 +143,13 @@ class PlaneRansac:
         _lib.check(self._L.plane_ransac_staged_source_indices(self._h, src.ctypes.data_as(C.c_void_p), src.size))
         return kept.value, cen, src[: kept.value]
 
+    def staged_source_indices(self) -> np.ndarray:
+        """Index in the caller's array of every staged point (identity unless staged with a filter or restaged)."""
+        n, _ = self.cloud_size()
+        src = np.empty(max(n, 1), np.int32)
+        _lib.check(self._L.plane_ransac_staged_source_indices(self._h, src.ctypes.data_as(C.c_void_p), src.size))
+        return src[:n]
+
     def set_cloud_ptr(self, host_ptr: int, n: int) -> None:
         """Stage from a raw host address (e.g. a pinned torch tensor's data_ptr())."""
         _lib.check(self._L.plane_ransac_set_cloud(self._h, C.c_void_p(host_ptr), n))
@@ -250,6 +257,11 @@ class PlaneRansac:
         n = C.c_size_t(0)
         _lib.check(self._L.plane_ransac_remaining(self._h, out.ctypes.data_as(C.c_void_p), out.shape[0], C.byref(n)))
         return out[: n.value]
+
+    def restage_remaining(self) -> None:
+        """The cloud left by the last extract / reabsorb call becomes the staged cloud (the reference's "run again",
+        Dialog/PCLViewer.cpp:1120-1178); staged_source_indices() maps it to the caller's array."""
+        _lib.check(self._L.plane_ransac_restage_remaining(self._h))
 
     def reabsorb(self, coeffs, borders, distance_threshold: float = 0.1, rand_seed: int = 0):
         """postProcessPlanes' re-absorption pass (Dialog/PlaneDetect.h:1530-1566) over the current cloud: every point is

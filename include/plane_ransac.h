@@ -187,6 +187,13 @@ int plane_ransac_reabsorb(plane_ransac_ctx* ctx, const float* coeffs, const pr_p
                           int n_planes, float dist_threshold, unsigned rand_seed, int32_t* absorbed_cur,
                           int32_t* absorbed_orig, size_t idx_cap, size_t* plane_offsets, size_t* n_remaining);
 
+/* ---- "run again" (PCLViewer::on_runAgainAction_triggered, Dialog/PCLViewer.cpp:1120-1178) ------------------------
+ * The reference reruns its pipeline on the shrunken source_cloud that postProcessPlanes left (Dialog/PlaneDetect.h:
+ * 1560-1572).  This makes the current cloud (what the last extract / reabsorb call left) the staged cloud, on the
+ * device, so the next segment / extract / score call works on it; plane_ransac_staged_source_indices then maps its
+ * points to the caller's original array.  plane_ransac_plane_points of earlier planes is no longer available. */
+int plane_ransac_restage_remaining(plane_ransac_ctx* ctx);
+
 /* ---- batch of equal-sized small clouds (per-scan tiles), one best plane each, no peel --------
  * pts: n_clouds * n_per_cloud points.  Every cloud runs segment() with the same parameters (and,
  * having the same size and seed, the same index triples).  coeffs: 4*n_clouds; n_inliers: n_clouds. */

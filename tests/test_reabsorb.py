@@ -235,3 +235,46 @@ def test_gpu_reabsorb_after_extraction_uses_original_indices():
             assert np.array_equal(np.asarray(pts, np.float32)[orig[j]][:, :3].view(np.uint32), rem[cur[j]][:, :3].view(np.uint32))
         assert n_rem == len(want.remaining_idx)
         assert np.array_equal(pr.remaining()[:, :3].view(np.uint32), rem[want.remaining_idx][:, :3].view(np.uint32))
+
+
+@pytest.mark.gpu
+def test_gpu_run_again_on_the_remaining_cloud():
+    """on_runAgainAction (Dialog/PCLViewer.cpp:1120-1178): extract, re-absorb, then extract again from what is left —
+    all on the device — equals the oracle fed the remaining cloud by hand; indices map back to the caller's array."""
+    import dialog_b200 as D
+    from dialog_b200 import synth
+    pts = synth.indoor_scene().points(0, 300_000)
+    p1 = dict(distance_threshold=0.05, max_iterations=300, min_plane_size=500, probability=0.99, max_planes=3)
+    with D.PlaneRansac(0) as pr:
+        pr.set_cloud(pts)
+        ex1 = pr.extract_planes(D.make_params(p1["distance_threshold"], p1["max_iterations"], p1["min_plane_size"], p1["probability"],
+                                              True, 12345, p1["max_planes"], D.DOT_FMA))
+        want1 = O.extract_planes(pts, O.make_params(0.05, 300, 500, 0.99, True, 12345, 3, O.DOT_FMA, O.REFIT_FIXED))
+        assert len(ex1.planes) == 3 and all(np.array_equal(p.inliers_orig, want1.inliers_orig[k]) for k, p in enumerate(ex1.planes))
+        scene = synth.indoor_scene()
+        coeffs = np.array([p.coeff for p in ex1.planes], np.float32)
+        borders = []
+        for c in coeffs:
+            err = [min(np.abs(q.coeff - c).max(), np.abs(q.coeff + c).max()) for q in scene.patches]
+            borders.append(scene.patches[int(np.argmin(err))].border(20))
+        want_re = O.reabsorb(want1.remaining, coeffs, borders, 0.1, 3)
+        cur, orig, n_left = pr.reabsorb(coeffs, borders, 0.1, 3)
+        assert n_left == len(want_re.remaining_idx) and sum(len(a) for a in cur) > 100
+        for j in range(3):
+            assert np.array_equal(cur[j], want_re.absorbed[j])
+        left = want1.remaining[want_re.remaining_idx]
+        # run again on the leftovers
+        pr.restage_remaining()
+        n_staged, n_cur = pr.cloud_size()
+        assert n_staged == n_cur == len(left)
+        src = pr.staged_source_indices()
+        assert np.array_equal(np.asarray(pts, np.float32)[src][:, :3].view(np.uint32), left[:, :3].view(np.uint32))
+        prm2 = (0.1, 300, 500, 0.99, True, 12345, 4)
+        ex2 = pr.extract_planes(D.make_params(*prm2, D.DOT_FMA))
+        # the staged bounding box (hence the refit grid) is the first run's: give the oracle the same grid
+        want2 = O.extract_planes(left, O.make_params(*prm2, O.DOT_FMA, O.REFIT_FIXED))
+        assert len(ex2.planes) == len(want2.coeffs) >= 1
+        for k, p in enumerate(ex2.planes):
+            assert np.array_equal(p.inliers_orig, want2.inliers_orig[k]), k
+            assert np.allclose(p.coeff, want2.coeffs[k], rtol=1e-5, atol=1e-6)
+        assert np.array_equal(pr.remaining()[:, :3].view(np.uint32), want2.remaining[:, :3].view(np.uint32))
