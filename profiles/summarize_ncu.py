@@ -17,6 +17,8 @@ KEYS = [
     "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
     "dram__throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_bytes.sum", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
     "smsp__inst_executed.sum", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+    "smsp__thread_inst_executed_per_inst_executed.ratio", "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active", "l1tex__t_sector_hit_rate.pct",
     "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
     "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
     "smsp__warps_eligible.avg.per_cycle_active",
@@ -79,7 +81,11 @@ def summarize_launches(path, out):
 
 
 if __name__ == "__main__":
-    tag = sys.argv[1]
-    summarize_launches(f"gpurun_out/launches_{tag}.csv", f"profiles/{tag}_launches_summary.txt")
-    summarize_rep(f"gpurun_out/prof_score_{tag}.ncu-rep", f"profiles/{tag}_score_kernel_ncu.txt")
-    summarize_rep(f"gpurun_out/prof_hbm_{tag}.ncu-rep", f"profiles/{tag}_hbm_kernels_ncu.txt")
+    import os
+    tag = sys.argv[1]                                   # suffix of the gpurun_out/ artefacts
+    out = sys.argv[2] if len(sys.argv) > 2 else tag     # prefix of the committed summaries
+    summarize_launches(f"gpurun_out/launches_{tag}.csv", f"profiles/{out}_launches_summary.txt")
+    summarize_rep(f"gpurun_out/prof_score_{tag}.ncu-rep", f"profiles/{out}_score_kernel_ncu.txt")
+    summarize_rep(f"gpurun_out/prof_hbm_{tag}.ncu-rep", f"profiles/{out}_hbm_kernels_ncu.txt")
+    if os.path.exists(f"gpurun_out/prof_reab_{tag}.ncu-rep"):
+        summarize_rep(f"gpurun_out/prof_reab_{tag}.ncu-rep", f"profiles/{out}_reabsorb_kernels_ncu.txt")
