@@ -62,14 +62,21 @@ def parse_args():
     return ap.parse_args()
 
 
-def workload_config(args, n_gpus):
+def workload_config(args, n_gpus, p2p=None):
+    if n_gpus <= 1:
+        sharding = "none"
+    elif p2p:
+        sharding = ("points, contiguous index ranges; per round the sample points, int32 counts, int64 moments and remaining "
+                    "counts are exchanged by single-kernel peer-memory exchanges over NVLink (CUDA IPC mailboxes)")
+    else:
+        sharding = "points, contiguous index ranges; NCCL all-reduce of int32 counts + int64 moments"
     return {
         "workload": "configs[2]: synthetic indoor scene, %d points per GPU x %d GPU(s), %d planes peeled, %d "
                     "hypotheses per round (max_iterations=%d, probability=1.0), t=0.1, min_plane=500, seed=12345"
                     % (args.points, n_gpus, args.planes, args.hyps, args.hyps - 1),
         "points_per_gpu": args.points, "points_total": args.points * n_gpus, "hypotheses_per_round": args.hyps,
         "planes": args.planes, "distance_threshold": 0.1, "min_plane_size": 500, "dot_order": "fma", "scorer": args.scorer,
-        "sharding": "points, contiguous index ranges; NCCL all-reduce of int32 counts + int64 moments" if n_gpus > 1 else "none",
+        "sharding": sharding,
         "l2": "256 MiB fill kernel between timed steps (outside the timed region); cloud planes are 120 MB per GPU",
     }
 
@@ -418,7 +425,7 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": workload_config(args, world),
+            "dtype": "f32", "data": "synthetic", "config": workload_config(args, world, pr.p2p_enabled()),
             "planes_extracted": n_planes, "pairs_per_step": pairs_step,
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_total_ms / args.steps,
                     "h2d_bytes_per_step": int(h2d_all), "d2h_bytes_per_step": int(d2h_all)},
