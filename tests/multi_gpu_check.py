@@ -63,6 +63,29 @@ def main():
     tot = torch.tensor([rem.shape[0]], device="cuda")
     dist.all_reduce(tot)
     assert int(tot.item()) == want_rem.shape[0]
+    # re-absorption pass, sharded: every rank claims on its shard; the union is the single-GPU answer
+    scene = synth.indoor_scene()
+    prm_t = D.make_params(0.05, 200, 500, 0.99, True, 12345, 6, D.DOT_FMA)
+    with D.PlaneRansac(local) as one:
+        one.set_cloud(pts)
+        ex_t = one.extract_planes(prm_t)
+        coeffs = np.array([p.coeff for p in ex_t.planes], np.float32)
+        borders = []
+        for c in coeffs:
+            err = [min(np.abs(q.coeff - c).max(), np.abs(q.coeff + c).max()) for q in scene.patches]
+            borders.append(scene.patches[int(np.argmin(err))].border(12))
+        _, want_orig, want_left = one.reabsorb(coeffs, borders, 0.1, 9)
+    sh.set_cloud(pts[first: first + count])
+    got_t = sh.extract_planes(prm_t)
+    assert [p.coeff.tobytes() for p in got_t.planes] == [p.coeff.tobytes() for p in ex_t.planes]
+    _, got_orig, got_left = sh.reabsorb(coeffs, borders, 0.1, 9)
+    for k in range(len(coeffs)):
+        mine = want_orig[k][(want_orig[k] >= first) & (want_orig[k] < first + count)] - first
+        assert (got_orig[k] == mine).all(), f"re-absorption, plane {k}, rank {rank}"
+    tot = torch.tensor([got_left], device="cuda")
+    dist.all_reduce(tot)
+    assert int(tot.item()) == want_left and sh.shard_info()[2] == want_left
+    assert sum(len(a) for a in want_orig) > 50
     # fused preProcess staging, sharded: the centroid is the global one (integer sums all-reduced), so the
     # translated shards and the planes found on them equal the single-GPU preprocessed run
     dirty = pts.copy()

@@ -6,7 +6,7 @@ base = synth.indoor_scene().points(0, 10_000_000)
 pr = D.PlaneRansac(0)
 hbm = pr.measure_copy_bw(1 << 30)
 print(f"copy kernel bandwidth (read+write): {hbm:.0f} GB/s")
-for rep in (1, 5):
+for rep in (1, 5, 10):
     pts = np.tile(base, (rep, 1)) if rep > 1 else base
     n = pts.shape[0]
     pr.set_cloud(pts)

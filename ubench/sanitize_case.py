@@ -16,6 +16,18 @@ for sc in (D.SCORER_BRUTE, D.SCORER_HIER):
 coeff, inl, info = pr.segment_one(D.make_params(0.1, 50, 500, 0.99, True))
 print("segment_one", inl.size, info.iterations)
 print("plane points", pr.plane_points(0, project=True).shape, "remaining", pr.remaining().shape)
+# re-absorption pass + run again
+coeffs = np.array([p.coeff for p in ex.planes], np.float32)
+borders = []
+for c in coeffs:
+    n = c[:3].astype(np.float64); u = np.cross(n, [1.0, 0, 0]); u /= np.linalg.norm(u); v = np.cross(n, u)
+    o = np.array([1.5, 1.5, 1.5]); o = o - (n @ o + c[3]) * n
+    borders.append(np.array([o + 1.4 * (np.cos(a) * u + np.sin(a) * v) for a in np.linspace(0, 2 * np.pi, 37, endpoint=False)], np.float32))
+cur, orig, left = pr.reabsorb(coeffs, borders, 0.2, 42)
+print("reabsorb", [a.size for a in cur], "left", left)
+pr.restage_remaining()
+ex = pr.extract_planes(D.make_params(0.1, 100, 200, 1.0, True, 12345, 2))
+print("run again", len(ex.planes), pr.staged_source_indices().shape)
 clouds = np.stack([synth.tile_scene(c).points(0, 3000) for c in range(5)])
 pr.set_cloud_batch(clouds)
 print("batch", pr.segment_batch(D.make_params(0.1, 63, 500, 1.0, True))[1])
