@@ -202,6 +202,8 @@ struct plane_ransac_ctx {
   long long n_global_staged = 0, first_staged = 0, n_global_current = 0, first_current = 0;
   bool global_valid = false;
 
+  pr::IndexSampler sampler;
+
   // measurement
   cudaEvent_t timer_a = nullptr, timer_b = nullptr;
   bool profiling = false;
@@ -670,7 +672,8 @@ int segment_core(plane_ransac_ctx* c, const pr_params* prm, pr::CloudView src, s
   pr::RansacReplay replay(std::max(1ll, n_global), prm->max_iterations, prm->probability);
   int total_draws = 0;
   if (n_global >= 3 && !replay.done()) {
-    pr::IndexSampler sampler((size_t)n_global, prm->seed);
+    pr::IndexSampler& sampler = c->sampler;  // kept across rounds: a reset clears only the touched table slots
+    sampler.reset((size_t)n_global, prm->seed);
     sampler.reserve((size_t)std::min<long long>((long long)prm->max_iterations + 1, 1 << 20));
     int prev_batch = 0;
     while (!replay.done()) {

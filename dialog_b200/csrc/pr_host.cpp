@@ -17,12 +17,13 @@ void Mt19937::seed_with(uint32_t seed) {
 
 uint32_t Mt19937::next() {
   if (idx_ >= 624) {
-    for (int i = 0; i < 624; ++i) {
-      uint32_t y = (mt_[i] & 0x80000000u) | (mt_[(i + 1) % 624] & 0x7fffffffu);
-      uint32_t v = mt_[(i + 397) % 624] ^ (y >> 1);
-      if (y & 1u) v ^= 0x9908b0dfu;
-      mt_[i] = v;
-    }
+    auto twist = [this](int i, int i1, int im) {
+      const uint32_t y = (mt_[i] & 0x80000000u) | (mt_[i1] & 0x7fffffffu);
+      mt_[i] = mt_[im] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+    };
+    for (int i = 0; i < 227; ++i) twist(i, i + 1, i + 397);
+    for (int i = 227; i < 623; ++i) twist(i, i + 1, i - 227);
+    twist(623, 0, 396);
     idx_ = 0;
   }
   uint32_t y = mt_[idx_++];
@@ -35,75 +36,108 @@ uint32_t Mt19937::next() {
 
 static constexpr uint32_t kEmptyKey = 0xFFFFFFFFu;
 
-IndexSampler::IndexSampler(size_t n, uint32_t seed) : rng_(seed), n_(n) {
+void IndexSampler::extend_raw(size_t upto) {
+  while (raw_.size() < upto) {
+    const size_t at = raw_.size();
+    raw_.resize(at + 1248);
+    for (size_t k = at; k < raw_.size(); ++k) raw_[k] = rng_.next() >> 1;
+  }
+}
+
+void IndexSampler::reset(size_t n, uint32_t seed) {
+  if (!raw_valid_ || raw_seed_ != seed) {
+    rng_.seed_with(seed);
+    raw_.clear();
+    raw_seed_ = seed;
+    raw_valid_ = true;
+  }
+  pos_ = 0;
+  n_ = n;
   head_[0] = 0;
   head_[1] = 1;
   head_[2] = 2;
-  keys_.assign(1u << 12, kEmptyKey);
-  vals_.assign(1u << 12, 0);
-  mask_ = (1u << 12) - 1;
+  if (slots_.empty()) {
+    slots_.assign(1u << 12, Slot{kEmptyKey, 0});
+    mask_ = (1u << 12) - 1;
+  } else if (touched_.size() * 4 > slots_.size()) {
+    std::fill(slots_.begin(), slots_.end(), Slot{kEmptyKey, 0});
+  } else {
+    for (uint32_t h : touched_) slots_[h].key = kEmptyKey;
+  }
+  touched_.clear();
+  for (int i = 0; i < 3; ++i) {
+    const uint64_t d = n > (size_t)i ? (uint64_t)(n - i) : 1;
+    d_[i] = d <= 0xFFFFFFFFull ? (uint32_t)d : 0u;  // 0: divisor does not fit 32 bits, use the plain operator
+    m_[i] = d_[i] ? UINT64_C(0xFFFFFFFFFFFFFFFF) / d_[i] + 1 : 0;
+  }
 }
 
 void IndexSampler::reserve(size_t draws) {
+  if (!touched_.empty()) return;
   uint32_t cap = mask_ + 1;
   while ((size_t)cap < draws * 3 * 4 && cap < (1u << 28)) cap <<= 1;  // load factor <= 1/4
-  if (cap == mask_ + 1 || used_ != 0) return;
-  keys_.assign(cap, kEmptyKey);
-  vals_.assign(cap, 0);
+  if (cap == mask_ + 1) return;
+  slots_.assign(cap, Slot{kEmptyKey, 0});
   mask_ = cap - 1;
 }
 
 static inline uint32_t hash_index(uint32_t k) { return (k * 2654435761u) >> 7; }
 
-int32_t IndexSampler::get(uint32_t j) const {
-  for (uint32_t h = hash_index(j) & mask_;; h = (h + 1) & mask_) {
-    if (keys_[h] == j) return vals_[h];
-    if (keys_[h] == kEmptyKey) return (int32_t)j;
-  }
-}
-
 void IndexSampler::grow() {
-  std::vector<uint32_t> ok;
-  std::vector<int32_t> ov;
-  ok.swap(keys_);
-  ov.swap(vals_);
+  std::vector<Slot> old;
+  old.swap(slots_);
   const uint32_t cap = (mask_ + 1) * 4;
-  keys_.assign(cap, kEmptyKey);
-  vals_.assign(cap, 0);
+  slots_.assign(cap, Slot{kEmptyKey, 0});
   mask_ = cap - 1;
-  used_ = 0;
-  for (size_t i = 0; i < ok.size(); ++i)
-    if (ok[i] != kEmptyKey) set(ok[i], ov[i]);
+  touched_.clear();
+  for (const Slot& s : old)
+    if (s.key != kEmptyKey) exchange(s.key, s.val);
 }
 
-void IndexSampler::set(uint32_t j, int32_t v) {
+int32_t IndexSampler::exchange(uint32_t j, int32_t v) {
   for (uint32_t h = hash_index(j) & mask_;; h = (h + 1) & mask_) {
-    if (keys_[h] == j) {
-      vals_[h] = v;
-      return;
+    Slot& s = slots_[h];
+    if (s.key == j) {
+      const int32_t old = s.val;
+      s.val = v;
+      return old;
     }
-    if (keys_[h] == kEmptyKey) {
-      keys_[h] = j;
-      vals_[h] = v;
-      if (++used_ * 3 > mask_) grow();
-      return;
+    if (s.key == kEmptyKey) {
+      s.key = j;
+      s.val = v;
+      touched_.push_back(h);
+      if (touched_.size() * 3 > mask_) grow();
+      return (int32_t)j;  // untouched entries hold the identity
     }
   }
+}
+
+inline size_t IndexSampler::index_of(uint32_t i, uint32_t r) const {
+  if (d_[i]) {
+    const uint64_t low = m_[i] * r;  // r % d_[i]
+    return i + (size_t)(((unsigned __int128)low * d_[i]) >> 64);
+  }
+  return i + (size_t)r % (n_ - i);
 }
 
 void IndexSampler::draw(int32_t out[3]) {
+  if (pos_ + 6 > raw_.size()) extend_raw(pos_ + 6);
+  const uint32_t* rr = raw_.data() + pos_;
+  pos_ += 3;
+  // the table slots of the NEXT draw: its indices depend only on the random stream, not on the permutation
+  for (uint32_t i = 0; i < 3; ++i) {
+    const size_t jn = index_of(i, rr[3 + i]);
+    if (jn >= 3) __builtin_prefetch(&slots_[hash_index((uint32_t)jn) & mask_], 1, 1);
+  }
   for (uint32_t i = 0; i < 3; ++i) {
     // rnd() = boost::uniform_int<>(0, INT_MAX) over mt19937 == rng() >> 1
-    const uint32_t r = rng_.next() >> 1;
-    const size_t j = n_ <= 0xFFFFFFFFull ? i + r % (uint32_t)(n_ - i) : i + (size_t)r % (n_ - i);
+    const size_t j = index_of(i, rr[i]);
     if (j < 3) {
       const int32_t t = head_[i];
       head_[i] = head_[j];
       head_[j] = t;
     } else {
-      const int32_t vj = get((uint32_t)j);
-      set((uint32_t)j, head_[i]);
-      head_[i] = vj;
+      head_[i] = exchange((uint32_t)j, head_[i]);
     }
   }
   out[0] = head_[0];

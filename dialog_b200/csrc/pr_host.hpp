@@ -26,23 +26,40 @@ class Mt19937 {
 // entries touched so far are stored, so a 10^8-point cloud costs nothing to (re)initialise.
 class IndexSampler {
  public:
-  IndexSampler(size_t n, uint32_t seed);
+  IndexSampler() : n_(0) {}
+  IndexSampler(size_t n, uint32_t seed) { reset(n, seed); }
+  // Start over for a cloud of n points (fresh RNG, identity permutation); the table allocation is kept and only the
+  // slots touched since the last reset are cleared, so a peel round costs microseconds whatever the table size.
+  void reset(size_t n, uint32_t seed);
   void draw(int32_t out[3]);
   // Size the table for this many draws up front (each draw touches up to three entries).
   void reserve(size_t draws);
   size_t size() const { return n_; }
 
  private:
-  // shuffled_indices_[j] for j >= 3: open-addressing table of the entries that differ from identity
-  int32_t get(uint32_t j) const;
-  void set(uint32_t j, int32_t v);
+  // shuffled_indices_[j] for j >= 3: open-addressing table (key and value side by side: one cache line per probe)
+  // of the entries that differ from the identity
+  struct Slot { uint32_t key; int32_t val; };
+  int32_t exchange(uint32_t j, int32_t v);  // old = shuffled[j]; shuffled[j] = v; return old
   void grow();
+  void extend_raw(size_t upto);
+  inline size_t index_of(uint32_t i, uint32_t r) const;
+  // rnd() values (rng() >> 1).  PCL reseeds the generator for every segment() call, so every peel round consumes
+  // the same stream: it is generated once per seed and replayed; knowing the next values also lets draw() prefetch
+  // the table slots of the following draw.
   Mt19937 rng_;
+  std::vector<uint32_t> raw_;
+  uint32_t raw_seed_ = 0;
+  bool raw_valid_ = false;
+  size_t pos_ = 0;
   size_t n_;
   int32_t head_[3];  // shuffled_indices_[0..3), touched by every swap
-  std::vector<uint32_t> keys_;
-  std::vector<int32_t> vals_;
-  uint32_t mask_ = 0, used_ = 0;
+  std::vector<Slot> slots_;
+  std::vector<uint32_t> touched_;
+  uint32_t mask_ = 0;
+  // r % (n - i) by multiplication (Lemire's fastmod, exact for 32-bit operands): m_[i] = 2^64 / (n - i) + 1
+  uint64_t m_[3] = {0, 0, 0};
+  uint32_t d_[3] = {1, 1, 1};
 };
 
 // RandomSampleConsensus::computeModel's while-loop (PCL 1.8 ransac.hpp), fed one draw at a time.
