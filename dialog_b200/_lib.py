@@ -23,7 +23,7 @@ STAGE_TRANSLATE_CENTROID = 2
 SYMBOLS = [
     "plane_ransac_abi_version", "plane_ransac_last_error", "plane_ransac_default_params",
     "plane_ransac_create", "plane_ransac_destroy", "plane_ransac_set_cloud", "plane_ransac_set_cloud_device",
-    "plane_ransac_set_cloud_ex", "plane_ransac_staged_source_indices",
+    "plane_ransac_set_cloud_ex", "plane_ransac_set_cloud_async", "plane_ransac_staged_source_indices",
     "plane_ransac_cloud_size", "plane_ransac_score", "plane_ransac_segment_one", "plane_ransac_extract_planes",
     "plane_ransac_plane_points", "plane_ransac_remaining", "plane_ransac_reabsorb", "plane_ransac_restage_remaining", "plane_ransac_set_cloud_batch", "plane_ransac_segment_batch",
     "plane_ransac_comm_unique_id", "plane_ransac_comm_init", "plane_ransac_comm_p2p_enabled", "plane_ransac_shard_info",
@@ -102,6 +102,7 @@ def load():
     L.plane_ransac_destroy.restype = None
     L.plane_ransac_set_cloud.argtypes = [vp, vp, sz]
     L.plane_ransac_set_cloud_device.argtypes = [vp, vp, sz]
+    L.plane_ransac_set_cloud_async.argtypes = [vp, vp, sz]
     L.plane_ransac_set_cloud_ex.argtypes = [vp, vp, sz, C.c_uint, C.POINTER(sz), vp]
     L.plane_ransac_staged_source_indices.argtypes = [vp, vp, sz]
     L.plane_ransac_cloud_size.argtypes = [vp, C.POINTER(sz), C.POINTER(sz)]

@@ -204,6 +204,17 @@ struct plane_ransac_ctx {
 
   pr::IndexSampler sampler;
 
+  // chunked upload queued by plane_ransac_set_cloud_async: copies run on copy_stream, chunk k is complete at ev[k];
+  // the first scoring pass (or any other call that needs the cloud) stages and consumes the chunks as they arrive
+  struct PendingUpload {
+    bool active = false;
+    const pr_point* host = nullptr;
+    size_t n = 0, chunk = 0;
+    int n_chunks = 0, next = 0;
+    std::vector<cudaEvent_t> ev;
+  } pend;
+  PinBuf<int4> h_sample_pts;
+
   // measurement
   cudaEvent_t timer_a = nullptr, timer_b = nullptr;
   bool profiling = false;
@@ -322,9 +333,14 @@ int sync_stream(plane_ransac_ctx* c) {
   return PR_OK;
 }
 
-int check_ctx(plane_ransac_ctx* c) {
+int ensure_staged(plane_ransac_ctx* c);
+
+// keep_pending: the caller deals with a queued asynchronous upload itself (the scoring pass that overlaps it, or a
+// new set_cloud that replaces it); every other entry point first lets the upload land.
+int check_ctx(plane_ransac_ctx* c, bool keep_pending = false) {
   if (!c) return fail(PR_ERR_INVALID, "null context");
   PR_CUDA(cudaSetDevice(c->device));
+  if (!keep_pending && c->pend.active) PR_TRY(ensure_staged(c));
   return PR_OK;
 }
 
@@ -361,6 +377,7 @@ int reserve_draws(plane_ransac_ctx* c, size_t need, bool keep) {
   PR_TRY(pin_reserve(c->h_triples, 3 * cap, keep));
   PR_TRY(pin_reserve(c->h_counts, cap, keep));
   PR_TRY(pin_reserve(c->h_good, cap, keep));
+  PR_TRY(pin_reserve(c->h_sample_pts, 3 * cap, keep));
   c->draw_cap = cap;
   return PR_OK;
 }
@@ -509,6 +526,55 @@ int stage_from_device(plane_ransac_ctx* c, const float4* d_aos, size_t n, unsign
   if (n_kept) *n_kept = n_out;
   if (centroid_out) std::memcpy(centroid_out, centroid, sizeof(centroid));
   return PR_OK;
+}
+
+// ---- asynchronous chunked staging ----------------------------------------------------------------------------------
+// Stage chunk k of a queued upload on the main stream once its copy has landed.
+int stage_pending_chunk(plane_ransac_ctx* c, int k, pr::CloudView* view, size_t* n_chunk) {
+  auto& u = c->pend;
+  const size_t off = (size_t)k * u.chunk;
+  const size_t cnt = std::min(u.chunk, u.n - off);
+  const bool last = k == u.n_chunks - 1;
+  pr::CloudView v = c->staged;
+  v.x += off; v.y += off; v.z += off;
+  v.cap = last ? c->staged.cap - off : cnt;  // only the last chunk writes the NaN padding
+  PR_CUDA(cudaStreamWaitEvent(c->stream, u.ev[k], 0));
+  {
+    Span sp(c, KC_STAGE, 1);
+    pr::launch_stage(c->aos.p + off, cnt, v, c->d_bbox.p, c->stream);
+  }
+  if (view) *view = v;
+  if (n_chunk) *n_chunk = cnt;
+  return PR_OK;
+}
+
+// After the last chunk was staged and the stream synchronised: bounding box -> refit grid.
+int finalize_pending(plane_ransac_ctx* c) {
+  c->pend.active = false;
+  c->pend.host = nullptr;
+  c->global_valid = false;
+  PR_TRY(refresh_global(c));
+  c->n_global_current = c->n_global_staged;
+  c->first_current = c->first_staged;
+  return PR_OK;
+}
+
+int ensure_staged(plane_ransac_ctx* c) {
+  auto& u = c->pend;
+  if (!u.active) return PR_OK;
+  for (; u.next < u.n_chunks; ++u.next) PR_TRY(stage_pending_chunk(c, u.next, nullptr, nullptr));
+  PR_CUDA(cudaGetLastError());
+  PR_CUDA(cudaMemcpyAsync(c->bbox_keys, c->d_bbox.p, 6 * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+  PR_CUDA(cudaStreamSynchronize(c->stream));
+  return finalize_pending(c);
+}
+
+void cancel_pending(plane_ransac_ctx* c) {
+  if (!c->pend.active) return;
+  cudaStreamSynchronize(c->copy_stream);
+  c->pend.active = false;
+  c->pend.host = nullptr;
+  c->have_cloud = false;
 }
 
 // Morton-sorted copy of the staged cloud for the hierarchical scorer (built once per staging).
@@ -671,6 +737,10 @@ int segment_core(plane_ransac_ctx* c, const pr_params* prm, pr::CloudView src, s
 
   pr::RansacReplay replay(std::max(1ll, n_global), prm->max_iterations, prm->probability);
   int total_draws = 0;
+  // A cloud still arriving from plane_ransac_set_cloud_async: the first batch of hypotheses is scored chunk by chunk
+  // as the copies land (the sample points come from the caller's host buffer), so the upload hides under the scoring.
+  const bool overlap = c->pend.active && src.x == c->staged.x && !hier && n_global >= 3 && !replay.done();
+  if (c->pend.active && !overlap) PR_TRY(ensure_staged(c));
   if (n_global >= 3 && !replay.done()) {
     pr::IndexSampler& sampler = c->sampler;  // kept across rounds: a reset clears only the touched table slots
     sampler.reset((size_t)n_global, prm->seed);
@@ -689,6 +759,47 @@ int segment_core(plane_ransac_ctx* c, const pr_params* prm, pr::CloudView src, s
       if (B < 1) B = 1;
       if ((long long)total_draws + B > (long long)INT_MAX / 4) return fail(PR_ERR_INVALID, "too many draws");
       PR_TRY(reserve_draws(c, (size_t)total_draws + (size_t)B, total_draws > 0));
+      if (overlap && c->pend.active) {
+        auto& u = c->pend;
+        int32_t* ht = c->h_triples.p;
+        {
+          HostTimer tm(&c->prof.host_ms_sampling);
+          for (long long j = 0; j < B; ++j) sampler.draw(ht + 3 * j);
+        }
+        int4* hsp = c->h_sample_pts.p;
+        for (long long i = 0; i < 3 * B; ++i) {
+          const long long local = (long long)ht[i] - first;  // sharded: only the owner of a point contributes its bits
+          int4 v = {0, 0, 0, 0};
+          if (local >= 0 && local < (long long)n_local) {
+            const pr_point& q = u.host[local];
+            std::memcpy(&v.x, &q.x, 4);
+            std::memcpy(&v.y, &q.y, 4);
+            std::memcpy(&v.z, &q.z, 4);
+            v.w = 0x3F800000;
+          }
+          hsp[i] = v;
+        }
+        // no cudaMemcpy here: a host-to-device copy would queue behind the cloud's chunks on the copy engine; a
+        // kernel reads the (pinned, device-visible) sample points over PCIe instead
+        {
+          Span sp(c, KC_MODELS, 2);
+          pr::launch_copy(reinterpret_cast<const float4*>(hsp), reinterpret_cast<float4*>(c->d_sample_pts.p), (size_t)(3 * B), c->num_sms, c->stream);
+          if (c->comm)  // once per extraction, not per round: NCCL is fine here
+            PR_NCCL(g_nccl.AllReduce(c->d_sample_pts.p, c->d_sample_pts.p, (size_t)(3 * B) * 4, ncclInt32, ncclSum, c->comm, c->stream));
+          pr::launch_models(c->d_sample_pts.p, (int)B, c->d_hyps.p, c->d_good.p, c->stream);
+        }
+        PR_CUDA(cudaMemsetAsync(c->d_counts.p, 0, B * sizeof(int32_t), c->stream));
+        for (; u.next < u.n_chunks;) {
+          pr::CloudView view;
+          size_t cnt = 0;
+          PR_TRY(stage_pending_chunk(c, u.next, &view, &cnt));
+          ++u.next;
+          Span sp(c, KC_SCORE, 0);
+          c->prof.launches_score += pr::launch_score(view, cnt, 1, 0, c->d_hyps.p, (int)B, t, prm->dot_order, c->d_counts.p, c->num_sms, c->stream);
+          c->prof.pairs_scored += (long long)cnt * B;
+        }
+        PR_CUDA(cudaMemcpyAsync(c->bbox_keys, c->d_bbox.p, 6 * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+      } else {
       // The batch is issued in sub-batches so that the host draws the next triples (a sequential
       // permutation walk, ~0.1 us per draw) while the device is already scoring the previous ones.
       // Two sub-batches: the first is just large enough that scoring it (~N / 6.5e12 s per hypothesis, ~3x less
@@ -735,6 +846,7 @@ int segment_core(plane_ransac_ctx* c, const pr_params* prm, pr::CloudView src, s
         }
         done += sb;
       }
+      }
       int32_t* dc = c->d_counts.p + total_draws;
       int32_t* dg = c->d_good.p + total_draws;
       PR_TRY(exchange_counts(c, dc, (size_t)B));
@@ -742,6 +854,10 @@ int segment_core(plane_ransac_ctx* c, const pr_params* prm, pr::CloudView src, s
       PR_CUDA(cudaMemcpyAsync(c->h_counts.p + total_draws, dc, B * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
       PR_CUDA(cudaMemcpyAsync(c->h_good.p + total_draws, dg, B * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
       PR_TRY(sync_stream(c));
+      if (c->pend.active) {  // the whole cloud is staged now: bounding box -> refit grid
+        PR_TRY(finalize_pending(c));
+        inf.scale_exp = c->scale_exp;
+      }
       {
         HostTimer tm(&c->prof.host_ms_replay);
         std::vector<uint8_t> good8((size_t)B);
@@ -926,7 +1042,8 @@ void plane_ransac_destroy(plane_ransac_ctx* c) {
   dev_free(c->d_rb_counters); dev_free(c->d_rb_keys); dev_free(c->d_rb_cand); dev_free(c->d_rb_claimed); dev_free(c->d_rb_temp);
   dev_free(c->d_batch_bbox); dev_free(c->d_batch_idx); dev_free(c->d_batch_scale); dev_free(c->d_batch_refit);
   dev_free(c->d_batch_hyps); dev_free(c->d_batch_pts); dev_free(c->d_batch_cnt);
-  pin_free(c->h_triples); pin_free(c->h_counts); pin_free(c->h_good); pin_free(c->h_refit);
+  pin_free(c->h_triples); pin_free(c->h_counts); pin_free(c->h_good); pin_free(c->h_refit); pin_free(c->h_sample_pts);
+  for (cudaEvent_t e : c->pend.ev) cudaEventDestroy(e);
   pin_free(c->h_totals); pin_free(c->h_small);
   if (c->timer_a) { cudaEventDestroy(c->timer_a); cudaEventDestroy(c->timer_b); }
   for (cudaEvent_t e : c->event_pool) cudaEventDestroy(e);
@@ -938,7 +1055,8 @@ void plane_ransac_destroy(plane_ransac_ctx* c) {
 }
 
 int plane_ransac_set_cloud(plane_ransac_ctx* c, const pr_point* pts, size_t n) {
-  PR_TRY(check_ctx(c));
+  PR_TRY(check_ctx(c, true));
+  cancel_pending(c);
   if (!pts && n) return fail(PR_ERR_INVALID, "null cloud");
   if (n > (size_t)INT_MAX - 4096) return fail(PR_ERR_INVALID, "cloud too large for 32-bit indices");
   PR_TRY(dev_reserve(c->aos, std::max<size_t>(n, 1)));
@@ -946,9 +1064,78 @@ int plane_ransac_set_cloud(plane_ransac_ctx* c, const pr_point* pts, size_t n) {
   return stage_from_device(c, c->aos.p, n);
 }
 
+int plane_ransac_set_cloud_async(plane_ransac_ctx* c, const pr_point* pts, size_t n) {
+  PR_TRY(check_ctx(c, true));
+  cancel_pending(c);
+  if (!pts && n) return fail(PR_ERR_INVALID, "null cloud");
+  if (n > (size_t)INT_MAX - 4096) return fail(PR_ERR_INVALID, "cloud too large for 32-bit indices");
+  // small clouds and pageable memory (the copy would block the host anyway) take the synchronous path; every rank of
+  // a sharded context must therefore make the same choice (same size class, pinned everywhere)
+  cudaPointerAttributes attr;
+  const bool pinned = n && cudaPointerGetAttributes(&attr, pts) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+  cudaGetLastError();
+  if (!pinned || n < ((size_t)1 << 21)) return plane_ransac_set_cloud(c, pts, n);
+
+  const size_t cap = pr::padded_capacity(n);
+  PR_TRY(dev_reserve(c->aos, n));
+  PR_TRY(dev_reserve(c->staged_mem, 3 * cap));
+  PR_TRY(reserve_small(c));
+  c->staged = planes_view(c->staged_mem.p, nullptr, cap);
+  c->have_stage_map = false;
+  c->last_offsets.clear();
+  c->last_coeffs.clear();
+  c->sorted_staged_valid = false;
+  auto& u = c->pend;
+  u.n_chunks = 8;
+  u.chunk = ((n + u.n_chunks - 1) / u.n_chunks + pr::kTilePoints - 1) / pr::kTilePoints * pr::kTilePoints;
+  u.n_chunks = (int)((n + u.chunk - 1) / u.chunk);
+  while ((int)u.ev.size() < u.n_chunks) {
+    cudaEvent_t e = nullptr;
+    PR_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    u.ev.push_back(e);
+  }
+  pr::launch_bbox_init(c->d_bbox.p, c->stream);
+  c->prof.launches_stage += 1;
+  for (int k = 0; k < u.n_chunks; ++k) {
+    const size_t off = (size_t)k * u.chunk, cnt = std::min(u.chunk, n - off);
+    PR_CUDA(cudaMemcpyAsync(c->aos.p + off, pts + off, cnt * sizeof(pr_point), cudaMemcpyHostToDevice, c->copy_stream));
+    PR_CUDA(cudaEventRecord(u.ev[k], c->copy_stream));
+  }
+  u.active = true;
+  u.host = pts;
+  u.n = n;
+  u.next = 0;
+  c->n_staged = n;
+  c->have_cloud = true;
+  c->current = c->staged;
+  c->n_current = n;
+  c->n_global_staged = c->n_global_current = (long long)n;
+  c->first_staged = c->first_current = 0;
+  c->global_valid = false;
+  if (c->comm) {
+    // the global size and this rank's offset are needed before the first draw; the bounding box follows when the
+    // last chunk is staged (finalize_pending)
+    long long* d = c->d_totals.p;
+    c->h_totals.p[0] = (long long)n;
+    PR_CUDA(cudaMemcpyAsync(d, c->h_totals.p, sizeof(long long), cudaMemcpyHostToDevice, c->stream));
+    PR_NCCL(g_nccl.AllGather(d, d + 2, 1, ncclInt64, c->comm, c->stream));
+    PR_CUDA(cudaMemcpyAsync(c->h_totals.p + 2, d + 2, c->n_ranks * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
+    PR_CUDA(cudaStreamSynchronize(c->stream));
+    long long first = 0, total = 0;
+    for (int r = 0; r < c->n_ranks; ++r) {
+      if (r == c->rank) first = total;
+      total += c->h_totals.p[2 + r];
+    }
+    c->n_global_staged = c->n_global_current = total;
+    c->first_staged = c->first_current = first;
+  }
+  return PR_OK;
+}
+
 int plane_ransac_set_cloud_ex(plane_ransac_ctx* c, const pr_point* pts, size_t n, unsigned flags, size_t* n_kept,
                               float centroid[3]) {
-  PR_TRY(check_ctx(c));
+  PR_TRY(check_ctx(c, true));
+  cancel_pending(c);
   if (!pts && n) return fail(PR_ERR_INVALID, "null cloud");
   if (n > (size_t)INT_MAX - 4096) return fail(PR_ERR_INVALID, "cloud too large for 32-bit indices");
   if (flags & ~(unsigned)(PR_STAGE_REMOVE_NONFINITE | PR_STAGE_TRANSLATE_CENTROID)) return fail(PR_ERR_INVALID, "unknown staging flag");
@@ -972,7 +1159,8 @@ int plane_ransac_staged_source_indices(plane_ransac_ctx* c, int32_t* out, size_t
 }
 
 int plane_ransac_set_cloud_device(plane_ransac_ctx* c, const pr_point* dev_pts, size_t n) {
-  PR_TRY(check_ctx(c));
+  PR_TRY(check_ctx(c, true));
+  cancel_pending(c);
   if (!dev_pts && n) return fail(PR_ERR_INVALID, "null cloud");
   if (n > (size_t)INT_MAX - 4096) return fail(PR_ERR_INVALID, "cloud too large for 32-bit indices");
   cudaPointerAttributes attr;
@@ -1030,7 +1218,7 @@ int plane_ransac_score(plane_ransac_ctx* c, const int32_t* triples, int K, doubl
 
 int plane_ransac_segment_one(plane_ransac_ctx* c, const pr_params* prm, float coeff[4], int32_t* inliers, size_t cap,
                              size_t* n_inliers, pr_segment_info* info) {
-  PR_TRY(check_ctx(c));
+  PR_TRY(check_ctx(c, true));
   if (c->profiling) collect_spans(c);  // stream is idle here: fold finished spans, recycle their events
   PR_TRY(check_params(prm));
   if (!c->have_cloud) return fail(PR_ERR_NO_CLOUD, "no cloud staged");
@@ -1039,9 +1227,11 @@ int plane_ransac_segment_one(plane_ransac_ctx* c, const pr_params* prm, float co
   SegmentOut so;
   pr::CloudView none;
   const bool hier = prm->scorer == PR_SCORER_HIER;
+  if (hier) PR_TRY(ensure_staged(c));
   if (hier) PR_TRY(ensure_sorted(c, 1));
   PR_TRY(segment_core(c, prm, c->staged, c->n_staged, c->n_global_staged, c->first_staged, false, none, c->d_inl_cur.p,
                       nullptr, info, &so, hier ? &c->sorted_view[0] : nullptr, nullptr));
+  if (c->pend.active) PR_TRY(ensure_staged(c));
   std::memcpy(coeff, so.coeff, 4 * sizeof(float));
   *n_inliers = (size_t)so.n_inl_local;
   if (inliers) {
@@ -1057,13 +1247,14 @@ int plane_ransac_segment_one(plane_ransac_ctx* c, const pr_params* prm, float co
 int plane_ransac_extract_planes(plane_ransac_ctx* c, const pr_params* prm, float* coeffs, int32_t* inlier_cur,
                                 int32_t* inlier_orig, size_t idx_cap, size_t* plane_offsets, int* n_planes,
                                 pr_segment_info* infos) {
-  PR_TRY(check_ctx(c));
+  PR_TRY(check_ctx(c, true));
   if (c->profiling) collect_spans(c);  // stream is idle here: fold finished spans, recycle their events
   PR_TRY(check_params(prm));
   if (!c->have_cloud) return fail(PR_ERR_NO_CLOUD, "no cloud staged");
   if (!coeffs || !plane_offsets || !n_planes) return fail(PR_ERR_INVALID, "null output");
   PR_TRY(reserve_work(c));
   const bool hier = prm->scorer == PR_SCORER_HIER;
+  if (hier) PR_TRY(ensure_staged(c));
   if (hier) PR_TRY(ensure_sorted(c, 3));
   int s_cur = 0;  // index of the sorted copy that matches src
   pr::CloudView src = c->staged;
@@ -1121,6 +1312,7 @@ int plane_ransac_extract_planes(plane_ransac_ctx* c, const pr_params* prm, float
       first = 0;
     }
   }
+  if (c->pend.active) PR_TRY(ensure_staged(c));
   *n_planes = planes;
   c->last_offsets.assign(plane_offsets, plane_offsets + planes + 1);
   c->last_coeffs.assign(coeffs, coeffs + 4 * (size_t)planes);

@@ -150,9 +150,12 @@ class PlaneRansac:
         _lib.check(self._L.plane_ransac_staged_source_indices(self._h, src.ctypes.data_as(C.c_void_p), src.size))
         return src[:n]
 
-    def set_cloud_ptr(self, host_ptr: int, n: int) -> None:
-        """Stage from a raw host address (e.g. a pinned torch tensor's data_ptr())."""
-        _lib.check(self._L.plane_ransac_set_cloud(self._h, C.c_void_p(host_ptr), n))
+    def set_cloud_ptr(self, host_ptr: int, n: int, overlap: bool = False) -> None:
+        """Stage from a raw host address (e.g. a pinned torch tensor's data_ptr()).  overlap=True queues the upload
+        and lets the next extract / segment call score the chunks as they land (plane_ransac_set_cloud_async: the
+        buffer must be pinned and stay untouched until that call returns)."""
+        f = self._L.plane_ransac_set_cloud_async if overlap else self._L.plane_ransac_set_cloud
+        _lib.check(f(self._h, C.c_void_p(host_ptr), n))
 
     def set_cloud_device_ptr(self, dev_ptr: int, n: int) -> None:
         _lib.check(self._L.plane_ransac_set_cloud_device(self._h, C.c_void_p(dev_ptr), n))

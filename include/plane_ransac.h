@@ -124,6 +124,14 @@ void plane_ransac_destroy(plane_ransac_ctx* ctx);
 int plane_ransac_set_cloud(plane_ransac_ctx* ctx, const pr_point* pts, size_t n);
 /* Same, from a device pointer (AoS pr_point[] already in HBM on the context's device). */
 int plane_ransac_set_cloud_device(plane_ransac_ctx* ctx, const pr_point* dev_pts, size_t n);
+/* Like plane_ransac_set_cloud, but returns as soon as the upload is queued: the cloud travels in chunks on a copy
+ * stream and the next plane_ransac_extract_planes / plane_ransac_segment_one call stages and scores each chunk as it
+ * lands (the sample points of its first batch are read from pts directly), so the host-to-device copy hides under
+ * the first scoring pass.  pts must be page-locked (plane_ransac_host_alloc, cudaHostAlloc, a pinned torch tensor) and
+ * must stay valid and unchanged until the next call on ctx returns; any other call first waits for the upload.
+ * Pageable memory and clouds under 2M points take the synchronous path of plane_ransac_set_cloud (in a sharded context
+ * every rank must pass the same kind of buffer and a shard of the same size class, so that all make the same choice). */
+int plane_ransac_set_cloud_async(plane_ransac_ctx* ctx, const pr_point* pts, size_t n);
 /* Staging with the reference's preProcess steps fused in (Dialog/PlaneDetect.h:449-481):
  *   PR_STAGE_REMOVE_NONFINITE     pcl::removeNaNFromPointCloud: points with a NaN/Inf coordinate are dropped,
  *                                 order preserved; later indices refer to the filtered cloud.

@@ -63,6 +63,25 @@ def main():
     tot = torch.tensor([rem.shape[0]], device="cuda")
     dist.all_reduce(tot)
     assert int(tot.item()) == want_rem.shape[0]
+    # overlapped upload, sharded: chunks scored as they land on every rank, same answer (shards of >= 2M points)
+    n_big = 2_200_000 * world
+    big = synth.indoor_scene().points(0, n_big)
+    prm_b = D.make_params(0.1, 1023, 500, 1.0, True, 12345, 3, D.DOT_FMA)
+    with D.PlaneRansac(local) as one:
+        one.set_cloud(big)
+        want_b = one.extract_planes(prm_b)
+    fb, cb = D.host_shard_range(n_big, world, rank)
+    pin = D.PinnedArray((cb, 4), np.float32)
+    pin.array[:] = big[fb: fb + cb]
+    sh.set_cloud_ptr(pin.ptr, cb, overlap=True)
+    assert sh.shard_info()[:2] == (n_big, fb)
+    got_b = sh.extract_planes(prm_b)
+    assert len(got_b.planes) == len(want_b.planes) == 3
+    for k, (a, b) in enumerate(zip(got_b.planes, want_b.planes)):
+        assert a.coeff.tobytes() == b.coeff.tobytes() and a.info.scale_exp == b.info.scale_exp, f"async upload, plane {k}"
+        mine = b.inliers_orig[(b.inliers_orig >= fb) & (b.inliers_orig < fb + cb)] - fb
+        assert (a.inliers_orig == mine).all(), f"async upload, plane {k}: inlier set differs on rank {rank}"
+    pin.free()
     # re-absorption pass, sharded: every rank claims on its shard; the union is the single-GPU answer
     scene = synth.indoor_scene()
     prm_t = D.make_params(0.05, 200, 500, 0.99, True, 12345, 6, D.DOT_FMA)

@@ -511,3 +511,50 @@ def test_error_paths(lib_built):
         # the context is still usable after errors
         coeff, inl, info = fresh.segment_one(D.make_params(0.1, 10, 1, 0.99, True))
         assert info.iterations >= 1
+
+
+@pytest.mark.gpu
+def test_async_upload_scored_chunk_by_chunk_matches_synchronous_staging(lib_built):
+    """plane_ransac_set_cloud_async: the first batch is scored on the chunks as their copies land (sample points read
+    from the caller's pinned buffer); planes, index lists, remaining cloud and refit grid equal the synchronous path,
+    in score-all mode, in PCL's adaptive mode, with NaN points, and when another call interrupts the upload."""
+    import dialog_b200 as D
+    from dialog_b200 import synth
+    n = 3_000_017
+    pts = synth.indoor_scene().points(0, n)
+    pts[::100_003, 1] = np.nan
+    pin = D.PinnedArray((n, 4), np.float32)
+    pin.array[:] = pts
+    for prm in (D.make_params(0.1, 2047, 500, 1.0, True, 12345, 5, D.DOT_FMA),
+                D.make_params(0.1, 50, 500, 0.99, True, 12345, 5, D.DOT_FMA),
+                D.make_params(0.1, 700, 500, 1.0, True, 12345, 3, D.DOT_PCL_SSE2),
+                D.make_params(0.1, 500, 500, 1.0, True, 12345, 3, D.DOT_FMA, D.SCORER_HIER)):
+        with D.PlaneRansac(0) as a, D.PlaneRansac(0) as b:
+            a.set_cloud(pts)
+            want = a.extract_planes(prm)
+            b.set_cloud_ptr(pin.ptr, n, overlap=True)
+            got = b.extract_planes(prm)
+            assert len(got.planes) == len(want.planes) >= 3
+            for p, q in zip(got.planes, want.planes):
+                assert p.coeff.tobytes() == q.coeff.tobytes()
+                assert np.array_equal(p.inliers_orig, q.inliers_orig) and np.array_equal(p.inliers_cur, q.inliers_cur)
+                assert p.info.scale_exp == q.info.scale_exp and list(p.info.best_sample) == list(q.info.best_sample)
+            assert b.remaining().tobytes() == a.remaining().tobytes()
+            # a second extraction from the now staged cloud, and segment_one right after an async upload
+            again = b.extract_planes(prm)
+            assert [p.coeff.tobytes() for p in again.planes] == [p.coeff.tobytes() for p in want.planes]
+            b.set_cloud_ptr(pin.ptr, n, overlap=True)
+            c1, i1, _ = b.segment_one(prm)
+            c0, i0, _ = a.segment_one(prm)
+            assert c1.tobytes() == c0.tobytes() and np.array_equal(i1, i0)
+            # any other call first lets the upload land
+            b.set_cloud_ptr(pin.ptr, n, overlap=True)
+            tri = D.host_draw_triples(n, 64)
+            assert np.array_equal(b.score(tri, 0.1), a.score(tri, 0.1))
+            b.set_cloud_ptr(pin.ptr, n, overlap=True)
+            assert b.remaining().tobytes() == np.ascontiguousarray(pts).tobytes()
+            # replaced before it was consumed
+            b.set_cloud_ptr(pin.ptr, n, overlap=True)
+            b.set_cloud(pts[:50_000])
+            assert b.cloud_size() == (50_000, 50_000)
+    pin.free()
