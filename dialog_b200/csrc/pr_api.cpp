@@ -767,6 +767,10 @@ int segment_core(plane_ransac_ctx* c, const pr_params* prm, pr::CloudView src, s
           for (long long j = 0; j < B; ++j) sampler.draw(ht + 3 * j);
         }
         int4* hsp = c->h_sample_pts.p;
+        for (long long i = 0; i < 3 * B; ++i) {  // random reads of a buffer far larger than the caches: fetch them all first
+          const long long local = (long long)ht[i] - first;
+          if (local >= 0 && local < (long long)n_local) __builtin_prefetch(&u.host[local], 0, 0);
+        }
         for (long long i = 0; i < 3 * B; ++i) {
           const long long local = (long long)ht[i] - first;  // sharded: only the owner of a point contributes its bits
           int4 v = {0, 0, 0, 0};
