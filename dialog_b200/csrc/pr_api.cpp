@@ -189,6 +189,14 @@ struct plane_ransac_ctx {
   DevBuf<uint32_t> d_rb_claimed;
   DevBuf<unsigned char> d_rb_temp;
 
+  // normal estimation scratch
+  DevBuf<unsigned long long> d_nrm_keys;
+  DevBuf<uint32_t> d_nrm_idx;
+  DevBuf<float> d_nrm_xyz;
+  DevBuf<float4> d_nrm_out;
+  DevBuf<int32_t> d_nrm_cnt;
+  DevBuf<unsigned char> d_nrm_temp;
+
   // sharding
   ncclComm_t comm = nullptr;
   int n_ranks = 1, rank = 0;
@@ -1044,6 +1052,8 @@ void plane_ransac_destroy(plane_ransac_ctx* c) {
   dev_free(c->d_rb_planes); dev_free(c->d_rb_border); dev_free(c->d_rb_edges); dev_free(c->d_rb_rays);
   dev_free(c->d_rb_ray_edges); dev_free(c->d_rb_counts); dev_free(c->d_rb_out_cur); dev_free(c->d_rb_out_orig);
   dev_free(c->d_rb_counters); dev_free(c->d_rb_keys); dev_free(c->d_rb_cand); dev_free(c->d_rb_claimed); dev_free(c->d_rb_temp);
+  dev_free(c->d_nrm_keys); dev_free(c->d_nrm_idx); dev_free(c->d_nrm_xyz); dev_free(c->d_nrm_out); dev_free(c->d_nrm_cnt);
+  dev_free(c->d_nrm_temp);
   dev_free(c->d_batch_bbox); dev_free(c->d_batch_idx); dev_free(c->d_batch_scale); dev_free(c->d_batch_refit);
   dev_free(c->d_batch_hyps); dev_free(c->d_batch_pts); dev_free(c->d_batch_cnt);
   pin_free(c->h_triples); pin_free(c->h_counts); pin_free(c->h_good); pin_free(c->h_refit); pin_free(c->h_sample_pts);
@@ -1373,6 +1383,64 @@ int plane_ransac_remaining(plane_ransac_ctx* c, pr_point* out, size_t cap, size_
   return PR_OK;
 }
 
+
+// ---- pcl::NormalEstimationOMP with a radius search (Dialog/PlaneDetect.h:515-545) ----------------------------------
+int plane_ransac_estimate_normals(plane_ransac_ctx* c, double radius, const float viewpoint[3], pr_normal* out, size_t cap,
+                                  int32_t* n_neighbors) {
+  PR_TRY(check_ctx(c));
+  if (c->profiling) collect_spans(c);
+  if (!c->have_cloud) return fail(PR_ERR_NO_CLOUD, "no cloud staged");
+  if (!(radius > 0.0) || !std::isfinite(radius)) return fail(PR_ERR_INVALID, "radius must be finite and > 0");
+  if (c->comm) return fail(PR_ERR_INVALID, "normal estimation needs the whole cloud on one GPU (neighbourhoods cross shard boundaries)");
+  const size_t n = c->n_current;
+  if (n > cap || (!out && n)) return fail(PR_ERR_CAPACITY, "output holds %zu normals, need %zu", cap, n);
+  if (n == 0) return PR_OK;
+  // uniform grid over the bounding box of the staged cloud (a superset of the current one), cell = radius (1 + 1e-6):
+  // every neighbour within the radius lies in the 27 cells around a point's cell
+  pr::NormalsGrid g;
+  const double h = radius * (1.0 + 1e-6);
+  g.inv_h = 1.0 / h;
+  double cells = 1.0;
+  for (int a = 0; a < 3; ++a) {
+    double lo = 0.0, hi = 0.0;
+    if (c->bbox_keys[a] <= c->bbox_keys[3 + a]) {
+      lo = (double)pr::key_to_float(c->bbox_keys[a]);
+      hi = (double)pr::key_to_float(c->bbox_keys[3 + a]);
+    }
+    g.lo[a] = lo;
+    const double d = std::floor((hi - lo) * g.inv_h) + 1.0;
+    if (!(d >= 1.0) || d > 2097152.0) return fail(PR_ERR_INVALID, "radius %g is too small for the cloud extent %g", radius, hi - lo);
+    g.dim[a] = (long long)d;
+    cells *= d;
+  }
+  if (cells > 9.0e18) return fail(PR_ERR_INVALID, "radius too small for the cloud extent");
+  g.no_cell = (unsigned long long)g.dim[0] * (unsigned long long)g.dim[1] * (unsigned long long)g.dim[2];
+  int key_bits = 1;
+  while (key_bits < 64 && (g.no_cell >> key_bits) != 0) ++key_bits;
+  int e = 0;
+  (void)std::frexp(radius, &e);  // radius < 2^e: neighbour offsets times 2^(18 - e) stay below 2^18
+  const double scale = std::ldexp(1.0, 18 - e);
+  const float r2 = (float)(radius * radius);
+  const float vp[3] = {viewpoint ? viewpoint[0] : 0.f, viewpoint ? viewpoint[1] : 0.f, viewpoint ? viewpoint[2] : 0.f};
+  PR_TRY(dev_reserve(c->d_nrm_keys, 2 * n));
+  PR_TRY(dev_reserve(c->d_nrm_idx, 2 * n));
+  PR_TRY(dev_reserve(c->d_nrm_xyz, 3 * n));
+  PR_TRY(dev_reserve(c->d_nrm_out, n));
+  PR_TRY(dev_reserve(c->d_nrm_cnt, n));
+  const size_t tb = pr::normals_sort_temp_bytes(n);
+  PR_TRY(dev_reserve(c->d_nrm_temp, tb + 256));
+  {
+    Span sp(c, KC_OTHER, 4);
+    pr::launch_normals_sort(c->current, n, g, key_bits, c->d_nrm_keys.p, c->d_nrm_idx.p, c->d_nrm_temp.p, tb, c->d_nrm_xyz.p, c->stream);
+    pr::launch_normals(c->d_nrm_xyz.p, c->d_nrm_keys.p + n, c->d_nrm_idx.p + n, n, g, r2, scale, vp, c->d_nrm_out.p,
+                       n_neighbors ? c->d_nrm_cnt.p : nullptr, c->stream);
+  }
+  PR_CUDA(cudaGetLastError());
+  PR_CUDA(cudaMemcpyAsync(out, c->d_nrm_out.p, n * sizeof(pr_normal), cudaMemcpyDeviceToHost, c->stream));
+  if (n_neighbors) PR_CUDA(cudaMemcpyAsync(n_neighbors, c->d_nrm_cnt.p, n * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+  PR_TRY(sync_stream(c));
+  return PR_OK;
+}
 
 // ---- "run again" (Dialog/PCLViewer.cpp:1120-1178): the cloud left by the last call becomes the staged cloud --------
 int plane_ransac_restage_remaining(plane_ransac_ctx* c) {

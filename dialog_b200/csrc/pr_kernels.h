@@ -122,6 +122,22 @@ void launch_reabsorb_lists(const unsigned long long* keys_in, unsigned long long
 
 // Batch: per-cloud inlier count of per-cloud planes is K2 with K = 1; nothing else needed.
 
+// ---- point normals by radius PCA (pr_normals.cu): pcl::NormalEstimationOMP with a radius search -------------------
+struct NormalsGrid {
+  double lo[3];        // grid origin (lower corner of the cloud's bounding box)
+  double inv_h;        // 1 / cell size, cell size = radius * (1 + 1e-6)
+  long long dim[3];    // cells per axis
+  unsigned long long no_cell;  // dim[0] * dim[1] * dim[2]: the key of non-finite points
+};
+size_t normals_sort_temp_bytes(size_t n);
+// cell keys -> sorted (key, index) pairs in keys[n..2n), idx[n..2n) -> coordinates in that order (x | y | z, n each)
+void launch_normals_sort(CloudView cloud, size_t n, const NormalsGrid& g, int key_bits, unsigned long long* keys, uint32_t* idx,
+                         void* temp, size_t temp_bytes, float* sorted_xyz, cudaStream_t s);
+// out[idx] = (normal_x, normal_y, normal_z, curvature), NaN for non-finite points and points with < 3 neighbours
+void launch_normals(const float* sorted_xyz, const unsigned long long* sorted_keys, const uint32_t* sorted_idx, size_t n,
+                    const NormalsGrid& g, float r2, double scale, const float vp[3], float4* out, int32_t* n_neighbors,
+                    cudaStream_t s);
+
 // ---- per-round exchanges of the point-sharded path through peer memory (pr_p2p.cu) ------------------------------
 // Every rank owns a mailbox in its HBM that all peers map with CUDA IPC; peers[r] is rank r's mailbox as seen from
 // this process (peers[rank] is the local allocation).

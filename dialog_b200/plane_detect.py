@@ -261,6 +261,19 @@ class PlaneRansac:
         _lib.check(self._L.plane_ransac_remaining(self._h, out.ctypes.data_as(C.c_void_p), out.shape[0], C.byref(n)))
         return out[: n.value]
 
+    def estimate_normals(self, radius: float, viewpoint=(0.0, 0.0, 0.0), want_counts: bool = False):
+        """estimateNormal() of the reference (pcl::NormalEstimationOMP, radius search) on the current cloud:
+        (n,4) float32 rows (normal_x, normal_y, normal_z, curvature), NaN where PCL yields NaN; with want_counts also the
+        number of neighbours per point."""
+        _, n = self.cloud_size()
+        out = np.empty((max(n, 1), 4), np.float32)
+        cnt = np.zeros(max(n, 1), np.int32) if want_counts else None
+        vp = np.ascontiguousarray(viewpoint, np.float32)
+        _lib.check(self._L.plane_ransac_estimate_normals(self._h, float(radius), vp.ctypes.data_as(C.c_void_p),
+                                                         out.ctypes.data_as(C.c_void_p), out.shape[0],
+                                                         cnt.ctypes.data_as(C.c_void_p) if want_counts else None))
+        return (out[:n], cnt[:n]) if want_counts else out[:n]
+
     def restage_remaining(self) -> None:
         """The cloud left by the last extract / reabsorb call becomes the staged cloud (the reference's "run again",
         Dialog/PCLViewer.cpp:1120-1178); staged_source_indices() maps it to the caller's array."""

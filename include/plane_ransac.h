@@ -195,6 +195,19 @@ int plane_ransac_reabsorb(plane_ransac_ctx* ctx, const float* coeffs, const pr_p
                           int n_planes, float dist_threshold, unsigned rand_seed, int32_t* absorbed_cur,
                           int32_t* absorbed_orig, size_t idx_cap, size_t* plane_offsets, size_t* n_remaining);
 
+/* ---- estimateNormal() (Dialog/PlaneDetect.h:515-545): pcl::NormalEstimationOMP<PointXYZ, Normal> with
+ * setRadiusSearch(radius) (r_for_estimate_normal, Dialog/config.txt:4) on the current cloud.  Neighbours of a point: the
+ * finite points whose FP32 squared distance (FLANN's L2_Simple order) is strictly below (float)(radius * radius), the
+ * point itself included; fewer than three, or a non-finite point, give NaN.  normal = eigenvector of the smallest
+ * eigenvalue of the neighbourhood covariance (PCL's eigen33 closed form), curvature = |lambda_0 / trace|, flipped
+ * towards viewpoint (NULL = the origin, PCL's default).  The covariance is accumulated as exact integers on a grid of
+ * 2^-18 of the radius about each point, so the result does not depend on any traversal order (PCL's own float sums
+ * depend on FLANN's neighbour order; they agree to ~1e-3 in the normal on noisy data).  n_neighbors is optional.
+ * Single GPU only. */
+typedef struct { float normal_x, normal_y, normal_z, curvature; } pr_normal;   /* == pcl::Normal's first 3 + curvature */
+int plane_ransac_estimate_normals(plane_ransac_ctx* ctx, double radius, const float viewpoint[3], pr_normal* out,
+                                  size_t cap, int32_t* n_neighbors);
+
 /* ---- "run again" (PCLViewer::on_runAgainAction_triggered, Dialog/PCLViewer.cpp:1120-1178) ------------------------
  * The reference reruns its pipeline on the shrunken source_cloud that postProcessPlanes left (Dialog/PlaneDetect.h:
  * 1560-1572).  This makes the current cloud (what the last extract / reabsorb call left) the staged cloud, on the

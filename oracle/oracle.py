@@ -110,6 +110,8 @@ def lib():
         L.orc_point_in_poly.argtypes = [vp, vp, vp, C.c_int, C.c_float, C.c_uint]
         L.orc_reabsorb.argtypes = [vp, C.c_size_t, vp, vp, vp, C.c_int, C.c_float, C.c_uint, vp, C.c_size_t, vp, vp,
                                    C.POINTER(C.c_size_t)]
+        L.orc_estimate_normals.argtypes = [vp, C.c_size_t, C.c_double, vp, C.c_int, vp, vp]
+        L.orc_normals_scale_exp.argtypes = [C.c_double]
         L.orc_mt_seed.argtypes = [vp, C.c_uint32]
         L.orc_mt_next.argtypes = [vp]
         L.orc_mt_next.restype = C.c_uint32
@@ -369,6 +371,21 @@ def reabsorb(cloud, coeffs, borders, t, seed) -> Reabsorption:
         raise RuntimeError("orc_reabsorb failed (empty border?)")
     o = [int(v) for v in po]
     return Reabsorption([ab[o[j]: o[j + 1]].copy() for j in range(P)], rem[: nrem.value].copy())
+
+
+NORMALS_PCL_FLOAT = 0
+NORMALS_FIXED = 1
+
+
+def estimate_normals(cloud, radius, viewpoint=(0.0, 0.0, 0.0), mode=NORMALS_FIXED):
+    """pcl::NormalEstimationOMP with a radius search: ((n,4) normal_x, normal_y, normal_z, curvature; neighbour counts)."""
+    c = _cloud(cloud)
+    vp = np.ascontiguousarray(viewpoint, np.float32)
+    out = np.empty((c.shape[0], 4), np.float32)
+    cnt = np.zeros(c.shape[0], np.int32)
+    if lib().orc_estimate_normals(_p(c), c.shape[0], float(radius), _p(vp), int(mode), _p(out), _p(cnt)) != 0:
+        raise ValueError("bad radius")
+    return out, cnt
 
 
 # ---- the reference's own source of the same predicate (oracle/build_ref.py) ------------------------------------

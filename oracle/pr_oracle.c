@@ -614,3 +614,124 @@ int orc_extract_planes(const orc_point* cloud, size_t n, const orc_params* prm, 
   free(cur); free(orig); free(inl);
   return rc;
 }
+
+/* =========================================================================================
+ * Normal estimation: pcl::NormalEstimationOMP<PointXYZ, Normal> with setRadiusSearch(r), the stage in front of
+ * the reference's detector (Dialog/PlaneDetect.h:515-545, r_for_estimate_normal = 0.5 in Dialog/config.txt:4).
+ * PCL 1.8 features/impl/normal_3d_omp.hpp + normal_3d.h + kdtree/impl/kdtree_flann.hpp (PARITY UNPINNED, see header):
+ *   neighbours of p_i : the finite points p_j with L2_Simple distance ((dx*dx + dy*dy) + dz*dz, FP32, dx = p_i.x - p_j.x)
+ *                       strictly below (float)(r * r); p_i itself is one of them
+ *   fewer than 3 neighbours or a non-finite p_i -> NaN normal and curvature
+ *   computePointNormal: centroid + covariance of the neighbours -> eigen33 -> normal = eigenvector of the smallest
+ *                       eigenvalue, curvature = |lambda_0 / trace|
+ *   flipNormalTowardsViewpoint(p_i, vp): negate when (vp - p_i) . n < 0   (FP32, left to right)
+ * ORC_NORMALS_PCL_FLOAT accumulates like PCL (nine float sums over the neighbours in ascending distance order, ties by
+ * index — FLANN's order among equal distances is not defined) and runs eigen33 in float.
+ * ORC_NORMALS_FIXED is the order-independent form a parallel device reproduces: neighbour coordinates relative to
+ * p_i quantised to a 2^-s grid (r * 2^s < 2^18), exact integer moments, 128-bit covariance numerators, eigen33 in
+ * double; same neighbour sets, same NaN pattern.
+ * ========================================================================================= */
+typedef struct { float d; int32_t j; } orc_nb;
+
+static int nb_cmp(const void* a, const void* b) {
+  const orc_nb* x = (const orc_nb*)a;
+  const orc_nb* y = (const orc_nb*)b;
+  if (x->d < y->d) return -1;
+  if (x->d > y->d) return 1;
+  return (x->j > y->j) - (x->j < y->j);
+}
+
+static inline int finite_pt(const orc_point* p) { return isfinite(p->x) && isfinite(p->y) && isfinite(p->z); }
+
+int orc_normals_scale_exp(double radius) {
+  int e;
+  (void)frexp(radius, &e); /* radius < 2^e */
+  return 18 - e;
+}
+
+int orc_estimate_normals(const orc_point* cloud, size_t n, double radius, const float vp[3], int mode, float* out,
+                         int32_t* n_neighbors) {
+  if (!(radius > 0.0) || !isfinite(radius)) return -1;
+  const float r2 = (float)(radius * radius);
+  const int s = orc_normals_scale_exp(radius);
+  const double scale = ldexp(1.0, s);
+  int fail = 0;
+#pragma omp parallel
+  {
+    orc_nb* nb = (orc_nb*)malloc((n ? n : 1) * sizeof(orc_nb));
+    if (!nb) {
+#pragma omp atomic write
+      fail = 1;
+    }
+#pragma omp for schedule(dynamic, 64)
+    for (long long ii = 0; ii < (long long)n; ++ii) {
+      const size_t i = (size_t)ii;
+      float* o = out + 4 * i;
+      o[0] = o[1] = o[2] = o[3] = NAN;
+      if (n_neighbors) n_neighbors[i] = 0;
+      if (!nb) continue;
+      const orc_point* p = &cloud[i];
+      if (!finite_pt(p)) continue;
+      size_t m = 0;
+      for (size_t j = 0; j < n; ++j) {
+        const orc_point* q = &cloud[j];
+        if (!finite_pt(q)) continue;
+        const float dx = p->x - q->x, dy = p->y - q->y, dz = p->z - q->z;
+        const float d = (dx * dx + dy * dy) + dz * dz;
+        if (d < r2) { nb[m].d = d; nb[m].j = (int32_t)j; ++m; }
+      }
+      if (n_neighbors) n_neighbors[i] = (int32_t)m;
+      if (m < 3) continue;
+      float nx, ny, nz, curv;
+      if (mode == ORC_NORMALS_PCL_FLOAT) {
+        qsort(nb, m, sizeof(orc_nb), nb_cmp);
+        float accu[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+        for (size_t k = 0; k < m; ++k) {
+          const orc_point* q = &cloud[nb[k].j];
+          accu[0] += q->x * q->x; accu[1] += q->x * q->y; accu[2] += q->x * q->z;
+          accu[3] += q->y * q->y; accu[4] += q->y * q->z; accu[5] += q->z * q->z;
+          accu[6] += q->x; accu[7] += q->y; accu[8] += q->z;
+        }
+        const float cnt = (float)m;
+        for (int k = 0; k < 9; ++k) accu[k] = accu[k] / cnt;
+        float cov[9];
+        cov[0] = accu[0] - accu[6] * accu[6]; cov[1] = accu[1] - accu[6] * accu[7]; cov[2] = accu[2] - accu[6] * accu[8];
+        cov[4] = accu[3] - accu[7] * accu[7]; cov[5] = accu[4] - accu[7] * accu[8]; cov[8] = accu[5] - accu[8] * accu[8];
+        cov[3] = cov[1]; cov[6] = cov[2]; cov[7] = cov[5];
+        float ev, v[3];
+        eigen33_f(cov, &ev, v);
+        const float sum = cov[0] + cov[4] + cov[8];
+        curv = sum != 0.0f ? fabsf(ev / sum) : 0.0f;
+        nx = v[0]; ny = v[1]; nz = v[2];
+      } else {
+        int64_t S[3] = {0, 0, 0};
+        typedef __int128 i128n;
+        int64_t Q[6] = {0, 0, 0, 0, 0, 0};
+        for (size_t k = 0; k < m; ++k) {
+          const orc_point* q = &cloud[nb[k].j];
+          const int64_t a = llrint(((double)q->x - (double)p->x) * scale);
+          const int64_t b = llrint(((double)q->y - (double)p->y) * scale);
+          const int64_t c = llrint(((double)q->z - (double)p->z) * scale);
+          S[0] += a; S[1] += b; S[2] += c;
+          Q[0] += a * a; Q[1] += a * b; Q[2] += a * c; Q[3] += b * b; Q[4] += b * c; Q[5] += c * c;
+        }
+        static const int A[6] = {0, 0, 0, 1, 1, 2}, B[6] = {0, 1, 2, 1, 2, 2};
+        double C[6];
+        for (int k = 0; k < 6; ++k) C[k] = (double)((i128n)(int64_t)m * (i128n)Q[k] - (i128n)S[A[k]] * (i128n)S[B[k]]);
+        const double cov[9] = {C[0], C[1], C[2], C[1], C[3], C[4], C[2], C[4], C[5]};
+        double ev, v[3];
+        eigen33_d(cov, &ev, v);
+        const double sum = C[0] + C[3] + C[5];
+        curv = sum != 0.0 ? (float)fabs(ev / sum) : 0.0f;
+        nx = (float)v[0]; ny = (float)v[1]; nz = (float)v[2];
+      }
+      /* flipNormalTowardsViewpoint (normal_3d.h, the float& overload) */
+      const float vx = vp[0] - p->x, vy = vp[1] - p->y, vz = vp[2] - p->z;
+      const float cos_theta = (vx * nx + vy * ny + vz * nz);
+      if (cos_theta < 0) { nx *= -1; ny *= -1; nz *= -1; }
+      o[0] = nx; o[1] = ny; o[2] = nz; o[3] = curv;
+    }
+    free(nb);
+  }
+  return fail ? -1 : 0;
+}

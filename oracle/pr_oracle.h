@@ -156,6 +156,14 @@ int orc_reabsorb(const orc_point* cloud, size_t n, const float* coeffs, const or
                  const size_t* border_offsets, int n_planes, float t, unsigned seed, int32_t* absorbed, size_t absorbed_cap,
                  size_t* plane_offsets, int32_t* remaining_idx, size_t* n_remaining);
 
+/* ---- pcl::NormalEstimationOMP with a radius search (Dialog/PlaneDetect.h:515-545), see pr_oracle.c --------------
+ * out: 4 floats per point (normal_x, normal_y, normal_z, curvature), NaN where PCL yields NaN; n_neighbors (optional):
+ * neighbours found per point (the point itself included).  Brute force over all pairs: small clouds only. */
+enum { ORC_NORMALS_PCL_FLOAT = 0, ORC_NORMALS_FIXED = 1 };
+int orc_normals_scale_exp(double radius);
+int orc_estimate_normals(const orc_point* cloud, size_t n, double radius, const float vp[3], int mode, float* out,
+                         int32_t* n_neighbors);
+
 /* ---- RandomSampleConsensus::computeModel + SACSegmentation::segment ----------------------- */
 int orc_segment(const orc_point* cloud, size_t n, const orc_params* prm, int scale_exp_or_min,
                 float coeff[4], int32_t* inliers /* cap n */, size_t* n_inliers, orc_trace* trace);

@@ -1,0 +1,110 @@
+"""estimateNormal() (Dialog/PlaneDetect.h:515-545): pcl::NormalEstimationOMP with a radius search.
+
+CPU: the oracle's two modes (PCL's float accumulation, the order-independent integer form) on known answers and against
+each other.  GPU: plane_ransac_estimate_normals against the integer-form oracle — neighbour counts and the NaN pattern
+exactly, normals to 1e-5 and curvature to 1e-5 relative (the eigen solve runs in double on both sides, with libm on the
+host and CUDA's math library on the device)."""
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+
+
+def noisy_scene(n, seed=0):
+    from dialog_b200 import synth
+    pts = synth.three_planes_scene(seed=20260002 + seed).points(0, n)
+    return pts
+
+
+def test_oracle_normals_known_answers():
+    # a 21 x 21 lattice in the plane z = 2 with spacing 0.1: interior points see the 13 lattice points within r = 0.21
+    g = np.arange(21, dtype=np.float32) * np.float32(0.1)
+    xy = np.stack(np.meshgrid(g, g, indexing="ij"), -1).reshape(-1, 2)
+    pts = np.concatenate([xy, np.full((len(xy), 1), 2.0, np.float32)], 1).astype(np.float32)
+    for mode in (O.NORMALS_FIXED, O.NORMALS_PCL_FLOAT):
+        nrm, cnt = O.estimate_normals(pts, 0.21, viewpoint=(0, 0, 0), mode=mode)
+        interior = (xy[:, 0] > 0.25) & (xy[:, 0] < 1.75) & (xy[:, 1] > 0.25) & (xy[:, 1] < 1.75)
+        assert set(cnt[interior]) == {13}
+        assert cnt.min() == 6  # corners: the point, 2 + 2 along the edges, 1 diagonal
+        # the plane is z = 2 and the viewpoint is below it: normals point down, curvature ~ 0
+        assert np.allclose(nrm[interior][:, :3], [0, 0, -1], atol=2e-3 if mode == O.NORMALS_PCL_FLOAT else 1e-6)
+        assert np.all(nrm[interior][:, 3] < 1e-4)
+    # viewpoint above the plane flips them
+    up, _ = O.estimate_normals(pts, 0.21, viewpoint=(1, 1, 10), mode=O.NORMALS_FIXED)
+    assert np.allclose(up[interior][:, :3], [0, 0, 1], atol=1e-6)
+
+
+def test_oracle_normals_nan_and_sparse_points():
+    pts = noisy_scene(3000)
+    pts = np.concatenate([pts, [[50, 50, 50, 1], [50.05, 50, 50, 1], [np.nan, 0, 0, 1]]]).astype(np.float32)
+    nrm, cnt = O.estimate_normals(pts, 0.2)
+    assert cnt[-3] == 2 and cnt[-2] == 2 and cnt[-1] == 0          # the isolated pair sees itself + the other point
+    assert np.isnan(nrm[-3:]).all()                                # fewer than 3 neighbours, or a non-finite point
+    ok = cnt >= 3
+    assert np.isfinite(nrm[ok]).all() and np.isnan(nrm[~ok]).all()
+    assert np.allclose(np.linalg.norm(nrm[ok][:, :3], axis=1), 1.0, atol=1e-6)
+    # strict '<' on the FP32 squared distance: a point at exactly r is not a neighbour
+    three = np.array([[0, 0, 0, 1], [0.5, 0, 0, 1], [0, 0.25, 0, 1]], np.float32)
+    _, c = O.estimate_normals(three, 0.5)
+    assert c.tolist() == [2, 1, 2]
+
+
+def test_oracle_modes_agree_on_noisy_planes():
+    pts = noisy_scene(5000)
+    a, ca = O.estimate_normals(pts, 0.25, mode=O.NORMALS_FIXED)
+    b, cb = O.estimate_normals(pts, 0.25, mode=O.NORMALS_PCL_FLOAT)
+    assert np.array_equal(ca, cb)
+    ok = ca >= 8
+    d = np.abs(a[ok] - b[ok])
+    # PCL sums absolute coordinates in float: its normals carry ~1e-4 of noise on a 3 m scene; the integer form does not
+    assert np.median(d[:, :3].max(1)) < 2e-4 and np.percentile(d[:, :3].max(1), 99) < 2e-2
+    assert np.median(d[:, 3]) < 1e-4
+
+
+def _compare(got, got_cnt, want, want_cnt):
+    assert np.array_equal(got_cnt, want_cnt)
+    assert np.array_equal(np.isnan(got), np.isnan(want))
+    ok = want_cnt >= 3
+    dn = np.abs(got[ok][:, :3] - want[ok][:, :3]).max(1)
+    # a normal within rounding of perpendicular to the view ray may flip the other way: allow the sign there only
+    flipped = np.abs(got[ok][:, :3] + want[ok][:, :3]).max(1)
+    assert np.all(np.minimum(dn, flipped) < 1e-5), float(np.minimum(dn, flipped).max())
+    assert (dn < 1e-5).mean() > 0.999
+    assert np.allclose(got[ok][:, 3], want[ok][:, 3], rtol=1e-5, atol=1e-9)
+
+
+@pytest.mark.gpu
+def test_gpu_normals_match_oracle():
+    import dialog_b200 as D
+    pts = noisy_scene(20000, seed=1)
+    pts[::997, 2] = np.nan
+    with D.PlaneRansac(0) as pr:
+        pr.set_cloud(pts)
+        for radius, vp in ((0.12, (0, 0, 0)), (0.3, (1.5, 1.5, 9.0)), (0.05, (0, 0, 0))):
+            want, want_cnt = O.estimate_normals(pts, radius, vp, O.NORMALS_FIXED)
+            got, got_cnt = pr.estimate_normals(radius, vp, want_counts=True)
+            _compare(got, got_cnt, want, want_cnt)
+        assert (want_cnt >= 3).sum() > 1000
+        with pytest.raises(D.PlaneRansacError):
+            pr.estimate_normals(0.0)
+
+
+@pytest.mark.gpu
+def test_gpu_normals_after_peel_and_far_from_origin():
+    """Normals of what an extraction left (the reference re-estimates them on the shrunken cloud, PlaneDetect.h:1572),
+    and a cloud 500 m from the origin where PCL's float sums lose the plane but the integer form does not."""
+    import dialog_b200 as D
+    pts = noisy_scene(15000, seed=2)
+    with D.PlaneRansac(0) as pr:
+        pr.set_cloud(pts)
+        pr.extract_planes(D.make_params(0.1, 300, 500, 0.99, True, 12345, 1, D.DOT_FMA))
+        rem = pr.remaining().copy()
+        want, want_cnt = O.estimate_normals(rem, 0.2)
+        got, got_cnt = pr.estimate_normals(0.2, want_counts=True)
+        _compare(got, got_cnt, want, want_cnt)
+        far = pts.copy()
+        far[:, :3] += np.float32(500.0)
+        pr.set_cloud(far)
+        want, want_cnt = O.estimate_normals(far, 0.2, (500, 500, 500))
+        got, got_cnt = pr.estimate_normals(0.2, (500, 500, 500), want_counts=True)
+        _compare(got, got_cnt, want, want_cnt)
