@@ -259,6 +259,26 @@ def run_extras(args, pr):
         "cpu_s_extrapolated": cpu_s / n_cpu * len(rem), "identical_on_cpu_sample": bool(same),
         "speedup_extrapolated": (cpu_s / n_cpu * len(rem)) / (sum(ms) / len(ms) * 1e-3),
         "note": "cloud resident (set_cloud before the timer), polygon upload + kernels + index lists back inside it"}
+    # estimateNormal() (pcl::NormalEstimationOMP, radius search) on the 10M-point scene
+    pr.set_cloud(pts10)
+    pr.estimate_normals(0.1)
+    ms = []
+    for _ in range(2):
+        pr.timer_start()
+        nrm, ncnt = pr.estimate_normals(0.1, want_counts=True)
+        ms.append(pr.timer_stop())
+    n_chk = 4000
+    want_n, want_c = O.estimate_normals(pts10[:n_chk], 0.1)   # brute-force oracle on a prefix: neighbourhoods differ from
+    sub_n, sub_c = None, None                                  # the full cloud's, so the check stages the same prefix
+    pr.set_cloud(pts10[:n_chk])
+    sub_n, sub_c = pr.estimate_normals(0.1, want_counts=True)
+    okn = want_c >= 3
+    dn = np.minimum(np.abs(sub_n[okn][:, :3] - want_n[okn][:, :3]).max(1), np.abs(sub_n[okn][:, :3] + want_n[okn][:, :3]).max(1))
+    out["estimate_normals_10M_r0.1"] = {
+        "gpu_ms": min(ms), "mean_neighbours": float(ncnt.mean()), "neighbour_pairs_per_s": float(ncnt.astype(np.int64).sum()) / (min(ms) * 1e-3),
+        "nan_normals": int(np.isnan(nrm[:, 0]).sum()),
+        "oracle_check": {"points": n_chk, "counts_identical": bool(np.array_equal(sub_c, want_c)), "max_normal_diff": float(dn.max()) if okn.any() else 0.0},
+        "note": "includes the 160 MB + 40 MB download of normals and counts to pageable host memory"}
     # configs[4]: batch of 32K-point clouds, one plane each, 256 hypotheses per cloud (slice of the 4096 clouds)
     nc = args.batch_clouds
     clouds = np.stack([synth.tile_scene(cid).points(0, 32768) for cid in range(nc)])
