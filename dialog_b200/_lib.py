@@ -25,7 +25,7 @@ SYMBOLS = [
     "plane_ransac_create", "plane_ransac_destroy", "plane_ransac_set_cloud", "plane_ransac_set_cloud_device",
     "plane_ransac_set_cloud_ex", "plane_ransac_set_cloud_async", "plane_ransac_staged_source_indices",
     "plane_ransac_cloud_size", "plane_ransac_score", "plane_ransac_segment_one", "plane_ransac_extract_planes",
-    "plane_ransac_plane_points", "plane_ransac_remaining", "plane_ransac_reabsorb", "plane_ransac_estimate_normals", "plane_ransac_restage_remaining", "plane_ransac_set_cloud_batch", "plane_ransac_segment_batch",
+    "plane_ransac_plane_points", "plane_ransac_remaining", "plane_ransac_reabsorb", "plane_ransac_estimate_normals", "plane_ransac_cluster_filter", "plane_ransac_restage_remaining", "plane_ransac_set_cloud_batch", "plane_ransac_segment_batch",
     "plane_ransac_comm_unique_id", "plane_ransac_comm_init", "plane_ransac_comm_p2p_enabled", "plane_ransac_shard_info",
     "plane_ransac_host_alloc", "plane_ransac_host_free", "plane_ransac_profile_enable", "plane_ransac_profile_reset", "plane_ransac_profile_get",
     "plane_ransac_timer_start", "plane_ransac_timer_stop", "plane_ransac_measure_ffma_peak", "plane_ransac_measure_copy_bw", "plane_ransac_flush_l2",
@@ -114,6 +114,7 @@ def load():
     L.plane_ransac_reabsorb.argtypes = [vp, vp, vp, vp, C.c_int, C.c_float, C.c_uint, vp, vp, sz, vp, C.POINTER(sz)]
     L.plane_ransac_restage_remaining.argtypes = [vp]
     L.plane_ransac_estimate_normals.argtypes = [vp, C.c_double, vp, vp, sz, vp]
+    L.plane_ransac_cluster_filter.argtypes = [vp, C.c_double, C.c_int, C.POINTER(sz), C.POINTER(sz)]
     L.plane_ransac_set_cloud_batch.argtypes = [vp, vp, sz, sz]
     L.plane_ransac_segment_batch.argtypes = [vp, C.POINTER(PrParams), vp, vp, vp]
     L.plane_ransac_comm_unique_id.argtypes = [vp]

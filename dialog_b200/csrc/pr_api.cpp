@@ -1384,19 +1384,14 @@ int plane_ransac_remaining(plane_ransac_ctx* c, pr_point* out, size_t cap, size_
 }
 
 
-// ---- pcl::NormalEstimationOMP with a radius search (Dialog/PlaneDetect.h:515-545) ----------------------------------
-int plane_ransac_estimate_normals(plane_ransac_ctx* c, double radius, const float viewpoint[3], pr_normal* out, size_t cap,
-                                  int32_t* n_neighbors) {
-  PR_TRY(check_ctx(c));
-  if (c->profiling) collect_spans(c);
-  if (!c->have_cloud) return fail(PR_ERR_NO_CLOUD, "no cloud staged");
-  if (!(radius > 0.0) || !std::isfinite(radius)) return fail(PR_ERR_INVALID, "radius must be finite and > 0");
-  if (c->comm) return fail(PR_ERR_INVALID, "normal estimation needs the whole cloud on one GPU (neighbourhoods cross shard boundaries)");
+// ---- cell-ordered copy of the current cloud: shared by normal estimation and clusterFilt ----------------------------
+} // extern "C"
+namespace {
+// Uniform grid over the bounding box of the staged cloud (a superset of the current one), cell = radius (1 + 1e-6), so
+// that every neighbour within the radius lies in the 27 cells around a point's cell; points sorted by cell key.
+// Leaves sorted keys in d_nrm_keys[n..2n), sorted indices in d_nrm_idx[n..2n), sorted coordinates in d_nrm_xyz.
+int build_cell_order(plane_ransac_ctx* c, double radius, pr::NormalsGrid* grid) {
   const size_t n = c->n_current;
-  if (n > cap || (!out && n)) return fail(PR_ERR_CAPACITY, "output holds %zu normals, need %zu", cap, n);
-  if (n == 0) return PR_OK;
-  // uniform grid over the bounding box of the staged cloud (a superset of the current one), cell = radius (1 + 1e-6):
-  // every neighbour within the radius lies in the 27 cells around a point's cell
   pr::NormalsGrid g;
   const double h = radius * (1.0 + 1e-6);
   g.inv_h = 1.0 / h;
@@ -1417,21 +1412,43 @@ int plane_ransac_estimate_normals(plane_ransac_ctx* c, double radius, const floa
   g.no_cell = (unsigned long long)g.dim[0] * (unsigned long long)g.dim[1] * (unsigned long long)g.dim[2];
   int key_bits = 1;
   while (key_bits < 64 && (g.no_cell >> key_bits) != 0) ++key_bits;
+  PR_TRY(dev_reserve(c->d_nrm_keys, 2 * n));
+  PR_TRY(dev_reserve(c->d_nrm_idx, 2 * n));
+  PR_TRY(dev_reserve(c->d_nrm_xyz, 3 * n));
+  const size_t tb = pr::normals_sort_temp_bytes(n);
+  PR_TRY(dev_reserve(c->d_nrm_temp, tb + 256));
+  {
+    Span sp(c, KC_OTHER, 3);
+    pr::launch_normals_sort(c->current, n, g, key_bits, c->d_nrm_keys.p, c->d_nrm_idx.p, c->d_nrm_temp.p, tb, c->d_nrm_xyz.p, c->stream);
+  }
+  *grid = g;
+  return PR_OK;
+}
+}  // namespace
+extern "C" {
+
+// ---- pcl::NormalEstimationOMP with a radius search (Dialog/PlaneDetect.h:515-545) ----------------------------------
+int plane_ransac_estimate_normals(plane_ransac_ctx* c, double radius, const float viewpoint[3], pr_normal* out, size_t cap,
+                                  int32_t* n_neighbors) {
+  PR_TRY(check_ctx(c));
+  if (c->profiling) collect_spans(c);
+  if (!c->have_cloud) return fail(PR_ERR_NO_CLOUD, "no cloud staged");
+  if (!(radius > 0.0) || !std::isfinite(radius)) return fail(PR_ERR_INVALID, "radius must be finite and > 0");
+  if (c->comm) return fail(PR_ERR_INVALID, "normal estimation needs the whole cloud on one GPU (neighbourhoods cross shard boundaries)");
+  const size_t n = c->n_current;
+  if (n > cap || (!out && n)) return fail(PR_ERR_CAPACITY, "output holds %zu normals, need %zu", cap, n);
+  if (n == 0) return PR_OK;
+  pr::NormalsGrid g;
+  PR_TRY(build_cell_order(c, radius, &g));
   int e = 0;
   (void)std::frexp(radius, &e);  // radius < 2^e: neighbour offsets times 2^(18 - e) stay below 2^18
   const double scale = std::ldexp(1.0, 18 - e);
   const float r2 = (float)(radius * radius);
   const float vp[3] = {viewpoint ? viewpoint[0] : 0.f, viewpoint ? viewpoint[1] : 0.f, viewpoint ? viewpoint[2] : 0.f};
-  PR_TRY(dev_reserve(c->d_nrm_keys, 2 * n));
-  PR_TRY(dev_reserve(c->d_nrm_idx, 2 * n));
-  PR_TRY(dev_reserve(c->d_nrm_xyz, 3 * n));
   PR_TRY(dev_reserve(c->d_nrm_out, n));
   PR_TRY(dev_reserve(c->d_nrm_cnt, n));
-  const size_t tb = pr::normals_sort_temp_bytes(n);
-  PR_TRY(dev_reserve(c->d_nrm_temp, tb + 256));
   {
-    Span sp(c, KC_OTHER, 4);
-    pr::launch_normals_sort(c->current, n, g, key_bits, c->d_nrm_keys.p, c->d_nrm_idx.p, c->d_nrm_temp.p, tb, c->d_nrm_xyz.p, c->stream);
+    Span sp(c, KC_OTHER, 1);
     pr::launch_normals(c->d_nrm_xyz.p, c->d_nrm_keys.p + n, c->d_nrm_idx.p + n, n, g, r2, scale, vp, c->d_nrm_out.p,
                        n_neighbors ? c->d_nrm_cnt.p : nullptr, c->stream);
   }
@@ -1439,6 +1456,54 @@ int plane_ransac_estimate_normals(plane_ransac_ctx* c, double radius, const floa
   PR_CUDA(cudaMemcpyAsync(out, c->d_nrm_out.p, n * sizeof(pr_normal), cudaMemcpyDeviceToHost, c->stream));
   if (n_neighbors) PR_CUDA(cudaMemcpyAsync(n_neighbors, c->d_nrm_cnt.p, n * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
   PR_TRY(sync_stream(c));
+  return PR_OK;
+}
+
+// ---- clusterFilt (Dialog/PlaneDetect.h:1582-1656) --------------------------------------------------------------------
+int plane_ransac_cluster_filter(plane_ransac_ctx* c, double radius, int max_small_cluster, size_t* n_removed, size_t* n_remaining) {
+  PR_TRY(check_ctx(c));
+  if (c->profiling) collect_spans(c);
+  if (!c->have_cloud) return fail(PR_ERR_NO_CLOUD, "no cloud staged");
+  if (!(radius > 0.0) || !std::isfinite(radius)) return fail(PR_ERR_INVALID, "radius must be finite and > 0");
+  if (max_small_cluster < 0) return fail(PR_ERR_INVALID, "max_small_cluster must be >= 0");
+  if (c->comm) return fail(PR_ERR_INVALID, "clusterFilt needs the whole cloud on one GPU (clusters cross shard boundaries)");
+  const size_t n = c->n_current;
+  if (n_removed) *n_removed = 0;
+  if (n_remaining) *n_remaining = n;
+  if (n == 0) return PR_OK;
+  PR_TRY(reserve_small(c));
+  PR_TRY(reserve_work(c));
+  pr::NormalsGrid g;
+  PR_TRY(build_cell_order(c, radius, &g));
+  // union-find scratch: parent in the unsorted half of the index buffer, sizes in the count buffer
+  PR_TRY(dev_reserve(c->d_nrm_cnt, n));
+  PR_TRY(dev_reserve(c->d_rb_claimed, c->current.cap));
+  PR_CUDA(cudaMemsetAsync(c->d_rb_claimed.p, 0, c->current.cap * sizeof(uint32_t), c->stream));
+  {
+    Span sp(c, KC_OTHER, 4);
+    pr::launch_cluster_flags(c->d_nrm_xyz.p, c->d_nrm_keys.p + n, c->d_nrm_idx.p + n, n, g, (float)(radius * radius),
+                             (uint32_t)max_small_cluster, c->d_nrm_idx.p, reinterpret_cast<uint32_t*>(c->d_nrm_cnt.p),
+                             c->d_rb_claimed.p, c->stream);
+  }
+  PR_CUDA(cudaGetLastError());
+  pr::CloudView dst = (c->current.x == c->work[0].x) ? c->work[1] : c->work[0];
+  PR_TRY(dev_reserve(c->d_scratch, pr::compact_scratch_bytes(n) + 64));
+  {
+    Span sp(c, KC_COMPACT, 1);
+    pr::Plane4 none = {0, 0, 0, 0};
+    pr::launch_compact(c->current, n, none, 0.f, 3, dst, true, nullptr, nullptr, c->d_scratch.p, c->d_totals.p, c->stream, c->d_rb_claimed.p);
+    c->prof.points_compact += (long long)n;
+  }
+  PR_CUDA(cudaGetLastError());
+  PR_CUDA(cudaMemcpyAsync(c->h_totals.p, c->d_totals.p, 2 * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
+  PR_TRY(sync_stream(c));
+  c->current = dst;
+  c->n_current = (size_t)c->h_totals.p[0];
+  c->n_global_current = (long long)c->n_current;
+  c->first_current = 0;
+  c->prof.bytes_compact += 20ll * (long long)n + 16ll * (long long)c->n_current;
+  if (n_removed) *n_removed = (size_t)c->h_totals.p[1];
+  if (n_remaining) *n_remaining = c->n_current;
   return PR_OK;
 }
 

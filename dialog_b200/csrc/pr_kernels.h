@@ -138,6 +138,12 @@ void launch_normals(const float* sorted_xyz, const unsigned long long* sorted_ke
                     const NormalsGrid& g, float r2, double scale, const float vp[3], float4* out, int32_t* n_neighbors,
                     cudaStream_t s);
 
+// clusterFilt: connected components of the radius graph over the same cell-sorted points (lock-free union-find);
+// flags[original index] = 1 for the points of components with at most max_small points.  parent, sizes: n uint32 each.
+void launch_cluster_flags(const float* sorted_xyz, const unsigned long long* sorted_keys, const uint32_t* sorted_idx, size_t n,
+                          const NormalsGrid& g, float r2, uint32_t max_small, uint32_t* parent, uint32_t* sizes, uint32_t* flags,
+                          cudaStream_t s);
+
 // ---- per-round exchanges of the point-sharded path through peer memory (pr_p2p.cu) ------------------------------
 // Every rank owns a mailbox in its HBM that all peers map with CUDA IPC; peers[r] is rank r's mailbox as seen from
 // this process (peers[rank] is the local allocation).

@@ -204,7 +204,112 @@ __global__ void __launch_bounds__(128) normals_kernel(const float* __restrict__ 
   if (n_neighbors) n_neighbors[dst] = cnt;
 }
 
+// ---- clusterFilt (Dialog/PlaneDetect.h:1582-1656): connected components of the radius graph ---------------------
+// The reference grows clusters by BFS over kd-tree radius searches and drops every cluster with at most T_cluster_num
+// points.  Components do not depend on the traversal, so a lock-free union-find over the same cell-sorted points gives
+// the same partition: every point hooks to each earlier (sorted order) point within the radius.
+__device__ __forceinline__ uint32_t uf_find(uint32_t* parent, uint32_t i) {
+  volatile uint32_t* vp = parent;  // other threads hook and compress concurrently: always read memory
+  uint32_t p = vp[i];
+  while (p != i) {  // path halving (every value ever stored in parent[x] is an ancestor of x)
+    const uint32_t gp = vp[p];
+    if (gp != p) vp[i] = gp;
+    i = p;
+    p = gp;
+  }
+  return i;
+}
+
+__device__ __forceinline__ void uf_union(uint32_t* parent, uint32_t a, uint32_t b) {
+  while (true) {
+    a = uf_find(parent, a);
+    b = uf_find(parent, b);
+    if (a == b) return;
+    if (a < b) { const uint32_t t = a; a = b; b = t; }  // hook the larger root under the smaller
+    const uint32_t old = atomicCAS(&parent[a], a, b);
+    if (old == a) return;
+  }
+}
+
+// After the union kernel has finished the forest is final: roots are looked up without writing (a path-compressing
+// find running beside another thread's final store could leave a non-root behind).
+__device__ __forceinline__ uint32_t uf_root_readonly(const uint32_t* __restrict__ parent, uint32_t i) {
+  uint32_t p = parent[i];
+  while (p != i) {
+    i = p;
+    p = parent[i];
+  }
+  return i;
+}
+
+__global__ void __launch_bounds__(256) cluster_init_kernel(uint32_t* __restrict__ parent, uint32_t* __restrict__ sizes, size_t n) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    parent[i] = (uint32_t)i;
+    sizes[i] = 0u;
+  }
+}
+
+__global__ void __launch_bounds__(128) cluster_union_kernel(const float* __restrict__ sx, const float* __restrict__ sy,
+                                                            const float* __restrict__ sz, const unsigned long long* __restrict__ keys,
+                                                            size_t n, NormalsGrid g, float r2, uint32_t* __restrict__ parent) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const size_t n_finite = lower_bound_key(keys, n, g.no_cell);
+  if (i >= n_finite) return;
+  const float px = sx[i], py = sy[i], pz = sz[i];
+  const unsigned long long k = keys[i];
+  const long long cx = (long long)(k % (unsigned long long)g.dim[0]);
+  const long long cy = (long long)((k / (unsigned long long)g.dim[0]) % (unsigned long long)g.dim[1]);
+  const long long cz = (long long)(k / ((unsigned long long)g.dim[0] * (unsigned long long)g.dim[1]));
+  const long long x0 = max(cx - 1, 0ll), x1 = min(cx + 1, g.dim[0] - 1);
+  for (long long zz = max(cz - 1, 0ll); zz <= min(cz + 1, g.dim[2] - 1); ++zz) {
+    for (long long yy = max(cy - 1, 0ll); yy <= min(cy + 1, g.dim[1] - 1); ++yy) {
+      const unsigned long long row = (unsigned long long)((zz * g.dim[1] + yy) * g.dim[0]);
+      const size_t b = lower_bound_key(keys, n_finite, row + (unsigned long long)x0);
+      size_t e = lower_bound_key(keys, n_finite, row + (unsigned long long)x1 + 1ull);
+      if (e > i) e = i;  // each pair once: only earlier points
+      for (size_t j = b; j < e; ++j) {
+        const float dx = __fsub_rn(px, __ldg(sx + j)), dy = __fsub_rn(py, __ldg(sy + j)), dz = __fsub_rn(pz, __ldg(sz + j));
+        const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+        if (d2 < r2 && uf_find(parent, (uint32_t)i) != uf_find(parent, (uint32_t)j)) uf_union(parent, (uint32_t)i, (uint32_t)j);
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) cluster_count_kernel(const uint32_t* __restrict__ parent, uint32_t* __restrict__ sizes, size_t n) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    atomicAdd(&sizes[uf_root_readonly(parent, (uint32_t)i)], 1u);
+}
+
+// flags[original index] = 1 for every point to drop: clusters with at most max_small points; non-finite points form no
+// cluster in the reference's kd-tree and are kept as they are (keep_nonfinite) — they never reach clusterFilt there.
+__global__ void __launch_bounds__(256) cluster_flag_kernel(const uint32_t* __restrict__ parent, const uint32_t* __restrict__ sizes,
+                                                           const uint32_t* __restrict__ idx, const unsigned long long* __restrict__ keys,
+                                                           size_t n, unsigned long long no_cell, uint32_t max_small,
+                                                           uint32_t* __restrict__ flags) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const bool finite = keys[i] != no_cell;
+    flags[idx[i]] = (finite && sizes[uf_root_readonly(parent, (uint32_t)i)] <= max_small) ? 1u : 0u;
+  }
+}
+
 }  // namespace
+
+void launch_cluster_flags(const float* sorted_xyz, const unsigned long long* sorted_keys, const uint32_t* sorted_idx, size_t n,
+                          const NormalsGrid& g, float r2, uint32_t max_small, uint32_t* parent, uint32_t* sizes, uint32_t* flags,
+                          cudaStream_t s) {
+  if (n == 0) return;
+  size_t blocks = (n + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  cluster_init_kernel<<<(unsigned)blocks, 256, 0, s>>>(parent, sizes, n);
+  cluster_union_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(sorted_xyz, sorted_xyz + n, sorted_xyz + 2 * n, sorted_keys, n, g, r2, parent);
+  cluster_count_kernel<<<(unsigned)blocks, 256, 0, s>>>(parent, sizes, n);
+  cluster_flag_kernel<<<(unsigned)blocks, 256, 0, s>>>(parent, sizes, sorted_idx, sorted_keys, n, g.no_cell, max_small, flags);
+}
 
 size_t normals_sort_temp_bytes(size_t n) {
   size_t bytes = 0;

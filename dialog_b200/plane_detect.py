@@ -274,6 +274,13 @@ class PlaneRansac:
                                                          cnt.ctypes.data_as(C.c_void_p) if want_counts else None))
         return (out[:n], cnt[:n]) if want_counts else out[:n]
 
+    def cluster_filter(self, radius: float, max_small_cluster: int):
+        """clusterFilt() (Dialog/PlaneDetect.h:1582-1656): drop every connected component of the radius graph with at
+        most max_small_cluster points from the current cloud.  Returns (points removed, points left)."""
+        a, b = C.c_size_t(0), C.c_size_t(0)
+        _lib.check(self._L.plane_ransac_cluster_filter(self._h, float(radius), int(max_small_cluster), C.byref(a), C.byref(b)))
+        return a.value, b.value
+
     def restage_remaining(self) -> None:
         """The cloud left by the last extract / reabsorb call becomes the staged cloud (the reference's "run again",
         Dialog/PCLViewer.cpp:1120-1178); staged_source_indices() maps it to the caller's array."""

@@ -208,6 +208,16 @@ typedef struct { float normal_x, normal_y, normal_z, curvature; } pr_normal;   /
 int plane_ransac_estimate_normals(plane_ransac_ctx* ctx, double radius, const float viewpoint[3], pr_normal* out,
                                   size_t cap, int32_t* n_neighbors);
 
+/* ---- clusterFilt() (Dialog/PlaneDetect.h:1582-1656), the last step of postProcessPlanes: the current cloud is split into
+ * the connected components of its radius graph (an edge where FLANN's FP32 squared distance is < (float)(radius * radius);
+ * the reference uses radius_local, Dialog/config.txt:22) and every component with at most max_small_cluster points
+ * (T_cluster_num, config.txt:30; the reference tests "size <= T") is dropped; the rest stays in its original order.
+ * The reference grows clusters by BFS; components do not depend on the order, so a parallel union-find gives the same
+ * result.  (One deviation: the reference skips the first radius-search hit as "the point itself", which splits exact
+ * duplicates off when FLANN lists the duplicate first; here duplicates are connected.)  Single GPU only. */
+int plane_ransac_cluster_filter(plane_ransac_ctx* ctx, double radius, int max_small_cluster, size_t* n_removed,
+                                size_t* n_remaining);
+
 /* ---- "run again" (PCLViewer::on_runAgainAction_triggered, Dialog/PCLViewer.cpp:1120-1178) ------------------------
  * The reference reruns its pipeline on the shrunken source_cloud that postProcessPlanes left (Dialog/PlaneDetect.h:
  * 1560-1572).  This makes the current cloud (what the last extract / reabsorb call left) the staged cloud, on the

@@ -112,6 +112,7 @@ def lib():
                                    C.POINTER(C.c_size_t)]
         L.orc_estimate_normals.argtypes = [vp, C.c_size_t, C.c_double, vp, C.c_int, vp, vp]
         L.orc_normals_scale_exp.argtypes = [C.c_double]
+        L.orc_cluster_filter.argtypes = [vp, C.c_size_t, C.c_double, C.c_int, vp]
         L.orc_mt_seed.argtypes = [vp, C.c_uint32]
         L.orc_mt_next.argtypes = [vp]
         L.orc_mt_next.restype = C.c_uint32
@@ -386,6 +387,15 @@ def estimate_normals(cloud, radius, viewpoint=(0.0, 0.0, 0.0), mode=NORMALS_FIXE
     if lib().orc_estimate_normals(_p(c), c.shape[0], float(radius), _p(vp), int(mode), _p(out), _p(cnt)) != 0:
         raise ValueError("bad radius")
     return out, cnt
+
+
+def cluster_filter(cloud, radius, max_small_cluster) -> np.ndarray:
+    """clusterFilt: boolean keep mask (False for points of radius-graph components with <= max_small_cluster points)."""
+    c = _cloud(cloud)
+    keep = np.ones(c.shape[0], np.uint8)
+    if lib().orc_cluster_filter(_p(c), c.shape[0], float(radius), int(max_small_cluster), _p(keep)) != 0:
+        raise ValueError("bad radius")
+    return keep.astype(bool)
 
 
 # ---- the reference's own source of the same predicate (oracle/build_ref.py) ------------------------------------

@@ -735,3 +735,48 @@ int orc_estimate_normals(const orc_point* cloud, size_t n, double radius, const 
   }
   return fail ? -1 : 0;
 }
+
+/* =========================================================================================
+ * clusterFilt (Dialog/PlaneDetect.h:1582-1656; reference code): clusters are grown by BFS over kd-tree radius searches
+ * (radius_local) and every cluster with at most T_cluster_num points is dropped from source_cloud ("indices.size() <=
+ * T_cluster_num").  The clusters are the connected components of the radius graph, whatever the seed order; an edge is
+ * FLANN's predicate (FP32 L2_Simple distance strictly below (float)(r * r)).  keep[i] = 0 for dropped points.
+ * Deviation noted in include/plane_ransac.h: the reference skips the first search hit as "the query itself", which can
+ * split exact duplicates off; here they are connected.  Non-finite points are left alone (keep = 1).
+ * ========================================================================================= */
+static int32_t uf_root(int32_t* parent, int32_t i) {
+  while (parent[i] != i) {
+    parent[i] = parent[parent[i]];
+    i = parent[i];
+  }
+  return i;
+}
+
+int orc_cluster_filter(const orc_point* cloud, size_t n, double radius, int max_small_cluster, uint8_t* keep) {
+  if (!(radius > 0.0) || !isfinite(radius)) return -1;
+  const float r2 = (float)(radius * radius);
+  int32_t* parent = (int32_t*)malloc((n ? n : 1) * sizeof(int32_t));
+  int32_t* size = (int32_t*)calloc(n ? n : 1, sizeof(int32_t));
+  if (!parent || !size) { free(parent); free(size); return -1; }
+  for (size_t i = 0; i < n; ++i) parent[i] = (int32_t)i;
+  for (size_t i = 0; i < n; ++i) {
+    const orc_point* p = &cloud[i];
+    if (!finite_pt(p)) continue;
+    for (size_t j = 0; j < i; ++j) {
+      const orc_point* q = &cloud[j];
+      if (!finite_pt(q)) continue;
+      const float dx = p->x - q->x, dy = p->y - q->y, dz = p->z - q->z;
+      const float d = (dx * dx + dy * dy) + dz * dz;
+      if (d < r2) {
+        const int32_t a = uf_root(parent, (int32_t)i), b = uf_root(parent, (int32_t)j);
+        if (a != b) parent[a > b ? a : b] = a > b ? b : a;
+      }
+    }
+  }
+  for (size_t i = 0; i < n; ++i) size[uf_root(parent, (int32_t)i)]++;
+  for (size_t i = 0; i < n; ++i)
+    keep[i] = (finite_pt(&cloud[i]) && size[uf_root(parent, (int32_t)i)] <= max_small_cluster) ? 0 : 1;
+  free(parent);
+  free(size);
+  return 0;
+}

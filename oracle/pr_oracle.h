@@ -164,6 +164,10 @@ int orc_normals_scale_exp(double radius);
 int orc_estimate_normals(const orc_point* cloud, size_t n, double radius, const float vp[3], int mode, float* out,
                          int32_t* n_neighbors);
 
+/* ---- clusterFilt (Dialog/PlaneDetect.h:1582-1656): keep[i] = 0 for the points of radius-graph components with at most
+ * max_small_cluster points.  Brute force over all pairs: small clouds only. */
+int orc_cluster_filter(const orc_point* cloud, size_t n, double radius, int max_small_cluster, uint8_t* keep);
+
 /* ---- RandomSampleConsensus::computeModel + SACSegmentation::segment ----------------------- */
 int orc_segment(const orc_point* cloud, size_t n, const orc_params* prm, int scale_exp_or_min,
                 float coeff[4], int32_t* inliers /* cap n */, size_t* n_inliers, orc_trace* trace);

@@ -108,3 +108,65 @@ def test_gpu_normals_after_peel_and_far_from_origin():
         want, want_cnt = O.estimate_normals(far, 0.2, (500, 500, 500))
         got, got_cnt = pr.estimate_normals(0.2, (500, 500, 500), want_counts=True)
         _compare(got, got_cnt, want, want_cnt)
+
+
+# ---- clusterFilt (Dialog/PlaneDetect.h:1582-1656) ---------------------------------------------------------------------
+def blobs(seed=0):
+    """Gaussian blobs of very different sizes + scattered singles: (cloud, blob id per point)."""
+    rng = np.random.default_rng(seed)
+    sizes = [3000, 1200, 501, 500, 499, 60, 7, 1, 1]
+    parts, ids = [], []
+    for b, m in enumerate(sizes):
+        c = rng.uniform(-20, 20, 3)
+        parts.append(c + rng.normal(0, 0.15, (m, 3)))
+        ids += [b] * m
+    pts = np.ones((sum(sizes), 4), np.float32)
+    pts[:, :3] = np.concatenate(parts)
+    perm = rng.permutation(len(pts))
+    return np.ascontiguousarray(pts[perm]), np.array(ids)[perm]
+
+
+def test_oracle_cluster_filter_known_answers():
+    pts, ids = blobs()
+    keep = O.cluster_filter(pts, 0.3, 500)
+    # blobs are dense (sigma 0.15, radius 0.3): big ones survive whole, "<= 500" ones go (a few fringe points of a big
+    # blob may be cut off as their own tiny components)
+    for b, m in enumerate([3000, 1200, 501, 500, 499, 60, 7, 1, 1]):
+        frac = keep[ids == b].mean()
+        assert (frac > 0.97) if m > 505 else (frac == 0.0 if m <= 500 else True), (b, m, frac)
+    assert O.cluster_filter(pts, 0.3, 0).all()          # nothing has <= 0 points
+    assert not O.cluster_filter(pts, 0.3, 10**6).any()  # everything is small
+    # a chain of points 0.09 apart is one component at r = 0.1 and 40 singletons at r = 0.08
+    chain = np.zeros((40, 4), np.float32)
+    chain[:, 0] = np.arange(40) * np.float32(0.09)
+    assert O.cluster_filter(chain, 0.1, 39).all() and not O.cluster_filter(chain, 0.1, 40).any()
+    assert not O.cluster_filter(chain, 0.08, 1).any()
+
+
+@pytest.mark.gpu
+def test_gpu_cluster_filter_matches_oracle():
+    import dialog_b200 as D
+    pts, _ = blobs(3)
+    pts[5, 0] = np.nan
+    chain = np.zeros((300, 4), np.float32)
+    chain[:, 0] = 40 + np.arange(300) * np.float32(0.25)   # a long thin component crossing many cells
+    chain[:, 3] = 1
+    cloud = np.ascontiguousarray(np.concatenate([pts, chain]))
+    with D.PlaneRansac(0) as pr:
+        for radius, small in ((0.3, 500), (0.3, 299), (0.12, 20), (1.0, 2999), (0.3, 0)):
+            pr.set_cloud(cloud)
+            keep = O.cluster_filter(cloud, radius, small)
+            removed, left = pr.cluster_filter(radius, small)
+            assert (removed, left) == (int((~keep).sum()), int(keep.sum())), (radius, small)
+            got = pr.remaining()
+            assert got.tobytes() == cloud[keep].tobytes(), (radius, small)
+        # after a peel: the filter works on what the extraction left, and a second pass removes nothing more
+        from dialog_b200 import synth
+        scene = synth.three_planes_scene().points(0, 20000)
+        pr.set_cloud(scene)
+        pr.extract_planes(D.make_params(0.1, 200, 500, 0.99, True, 12345, 2, D.DOT_FMA))
+        rem = pr.remaining().copy()
+        keep = O.cluster_filter(rem, 0.15, 30)
+        removed, left = pr.cluster_filter(0.15, 30)
+        assert left == int(keep.sum()) and pr.remaining().tobytes() == rem[keep].tobytes()
+        assert pr.cluster_filter(0.15, 30) == (0, left)
