@@ -59,6 +59,7 @@ def parse_args():
                     help="also time BASELINE configs[1] (1M points, 3 planes, K=1024) and a slice of configs[4] "
                          "(batch of 32K-point clouds, K=256) on rank 0's GPU; reported under 'extras'")
     ap.add_argument("--batch-clouds", type=int, default=512)
+    ap.add_argument("--no-hbm-100m", action="store_true", help="skip the single-launch 100M-point compaction / refit measurement")
     return ap.parse_args()
 
 
@@ -480,6 +481,26 @@ def main():
                 "unit": UNIT, "identical_planes": bool(hier_same),
                 "note": "opt-in PR_SCORER_HIER: Morton-sorted copy + per-32-point boxes, blocks outside the threshold slab "
                         "skipped, the rest evaluated with the same arithmetic; same counts, not the roofline kernel"}
+        if world == 1 and not args.no_hbm_100m:
+            # the HBM kernels at the north star's scene size: one segment + peel over 100M points (the 10M-point cloud
+            # tiled ten times), timed alone; the figures above are averages over the shrinking 10M-point rounds
+            big = np.tile(pts, (max(1, 100_000_000 // max(count, 1)), 1))
+            pr.set_cloud(big)
+            prm1 = D.make_params(0.1, 255, 500, 1.0, True, 12345, 1, D.DOT_FMA)
+            pr.extract_planes(prm1, want_indices=False)
+            pr.profile_enable(True)
+            pr.profile_reset()
+            for _ in range(3):
+                pr.extract_planes(prm1, want_indices=False)
+            pb = pr.profile()
+            pr.profile_enable(False)
+            cg = pb.bytes_compact / (pb.ms_compact * 1e-3) / 1e9 if pb.ms_compact > 0 else None
+            rg = pb.bytes_refit / (pb.ms_refit * 1e-3) / 1e9 if pb.ms_refit > 0 else None
+            line["roofline_hbm"]["single_launch_%dM_points" % (big.shape[0] // 1_000_000)] = {
+                "compact": {"achieved": cg, "frac": cg / hbm_peak if cg else None, "ms": pb.ms_compact / 3},
+                "refit": {"achieved": rg, "frac": rg / hbm_peak if rg else None, "ms": pb.ms_refit / 3},
+                "unit": "GB/s", "peak": hbm_peak}
+            del big
         if args.extras:
             line["extras"] = run_extras(args, pr)
         if not args.no_cpu_baseline:

@@ -708,7 +708,7 @@ void p2p_teardown(plane_ransac_ctx* c) {
 
 // After a stream synchronisation: did a consumer give up waiting for a peer?
 int p2p_check(plane_ransac_ctx* c) {
-  if (c->p2p_on && c->h_p2p_err.p && *c->h_p2p_err.p) return fail(PR_ERR_COMM, "a peer rank did not deliver its part of an exchange within 3 s");
+  if (c->p2p_on && c->h_p2p_err.p && *c->h_p2p_err.p) return fail(PR_ERR_COMM, "a peer rank did not deliver its part of an exchange within ~20 s");
   return PR_OK;
 }
 

@@ -45,7 +45,7 @@ __device__ __forceinline__ bool p2p_signal_and_wait(const P2PView& v, size_t fla
     const unsigned long long* f = reinterpret_cast<const unsigned long long*>(v.peers[v.rank] + flag_off) + r;
     const long long t0 = clock64();
     while (ld_acquire_sys(f) < epoch) {
-      if (clock64() - t0 > 6000000000ll) {  // ~3 s: a lost peer becomes an error code, not a hung GPU
+      if (clock64() - t0 > 40000000000ll) {  // ~20 s: a lost peer becomes an error code, not a hung GPU
         atomicExch(err, 1u);
         s_bad = 1;
         break;

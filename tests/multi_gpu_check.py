@@ -73,6 +73,7 @@ def main():
     fb, cb = D.host_shard_range(n_big, world, rank)
     pin = D.PinnedArray((cb, 4), np.float32)
     pin.array[:] = big[fb: fb + cb]
+    dist.barrier()  # the ranks generated and solved the big cloud on their own: line them up before the collective calls
     sh.set_cloud_ptr(pin.ptr, cb, overlap=True)
     assert sh.shard_info()[:2] == (n_big, fb)
     got_b = sh.extract_planes(prm_b)
@@ -94,6 +95,7 @@ def main():
             err = [min(np.abs(q.coeff - c).max(), np.abs(q.coeff + c).max()) for q in scene.patches]
             borders.append(scene.patches[int(np.argmin(err))].border(12))
         _, want_orig, want_left = one.reabsorb(coeffs, borders, 0.1, 9)
+    dist.barrier()
     sh.set_cloud(pts[first: first + count])
     got_t = sh.extract_planes(prm_t)
     assert [p.coeff.tobytes() for p in got_t.planes] == [p.coeff.tobytes() for p in ex_t.planes]
