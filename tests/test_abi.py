@@ -64,3 +64,28 @@ def test_create_without_gpu_fails_loudly(lib_built):
     with pytest.raises(PlaneRansacError) as e:
         PlaneRansac(0)
     assert "no CPU fallback" in str(e.value)
+
+
+def test_header_is_plain_c99_and_shim_compiles(tmp_path):
+    """include/plane_ransac.h is the FFI surface (cgo / ctypes / JNI bind to it): it must compile as C99 on its own; the
+    C++ shim (PlaneDetect-style surface incl. postProcess) must compile against it."""
+    import shutil
+    import subprocess
+    cc = shutil.which("/usr/bin/gcc") or shutil.which("gcc")
+    cxx = shutil.which("/usr/bin/g++") or shutil.which("g++")
+    c_src = tmp_path / "abi.c"
+    c_src.write_text('#include "plane_ransac.h"\nint main(void){ pr_params p; plane_ransac_default_params(&p); '
+                     'return (int)sizeof(pr_normal) - 16 + (int)sizeof(pr_point) - 16; }\n')
+    inc = os.path.join(ROOT, "include")
+    r = subprocess.run([cc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", f"-I{inc}", "-c", str(c_src), "-o", str(tmp_path / "abi.o")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    cpp_src = tmp_path / "shim.cpp"
+    cpp_src.write_text('#include "PlaneDetectRansac.h"\n'
+                       'bool use(plane_detect_ransac::PlaneDetectRansac& d, std::vector<plane_detect_ransac::PointXYZ>& c) {\n'
+                       '  std::vector<plane_detect_ransac::PlaneRecord> p;\n'
+                       '  std::vector<std::vector<plane_detect_ransac::PointXYZ>> b;\n'
+                       '  return d.detect(c, p) && d.postProcess(c, p, b, 1u);\n}\n')
+    r = subprocess.run([cxx, "-std=c++17", "-Wall", "-Wextra", "-Werror", f"-I{inc}", "-c", str(cpp_src), "-o", str(tmp_path / "shim.o")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
