@@ -93,3 +93,16 @@ def test_shard_ranges_tile_the_cloud(n, r):
     assert nxt == n
     sizes = [D.host_shard_range(n, r, k)[1] for k in range(r)]
     assert max(sizes) - min(sizes) <= 1
+
+
+def test_host_rand_edges_is_the_msvc_generator(lib_built):
+    """isPointInPoly's edge draws (Dialog/PlaneDetect.h:1905-1919): srand(seed), rand() % border.size() with the MSVC CRT
+    generator — the library's host helper against the oracle's and against the generator's well-known first values."""
+    import dialog_b200 as D
+    from oracle import oracle as O
+    assert D.host_rand_edges(1, 32768).tolist() == [41, 18467, 6334, 26500, 19169, 15724, 11478, 29358, 26962, 24464]
+    for seed in (0, 1, 12345, 2**31 - 1, 2**32 - 1, 1729):
+        for nb in (1, 2, 3, 77, 337, 100000):
+            assert np.array_equal(D.host_rand_edges(seed, nb), O.msvc_rand_edges(seed, nb)), (seed, nb)
+    with pytest.raises(D.PlaneRansacError):
+        D.host_rand_edges(1, 0)
