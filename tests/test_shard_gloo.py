@@ -93,6 +93,24 @@ def _worker(rank, world, port, n, q):
         sizes = [torch.zeros(1, dtype=torch.int64) for _ in range(world)]
         dist.all_gather(sizes, torch.tensor([shard.shape[0]], dtype=torch.int64))
         assert sum(int(v.item()) for v in sizes) == rest.shape[0]
+        # postProcessPlanes re-absorption, sharded: the predicate is per point, so every rank claims on its own shard
+        # with no data exchange; only the remaining counts are gathered (the new prefix of the peeled cloud)
+        scene = synth.three_planes_scene()
+        borders = []
+        for c in want.coeffs:
+            err = [min(np.abs(q.coeff - c).max(), np.abs(q.coeff + c).max()) for q in scene.patches]
+            borders.append(scene.patches[int(np.argmin(err))].border(10))
+        whole = O.reabsorb(rest, want.coeffs, borders, 0.2, 31)
+        mine = O.reabsorb(shard, want.coeffs, borders, 0.2, 31)
+        sizes = [int(v.item()) for v in sizes]
+        first_cur = sum(sizes[:rank])
+        for k in range(rounds):
+            w = whole.absorbed[k]
+            assert np.array_equal(mine.absorbed[k] + first_cur, w[(w >= first_cur) & (w < first_cur + shard.shape[0])])
+        left = [torch.zeros(1, dtype=torch.int64) for _ in range(world)]
+        dist.all_gather(left, torch.tensor([mine.remaining_idx.size], dtype=torch.int64))
+        assert sum(int(v.item()) for v in left) == whole.remaining_idx.size
+        assert sum(len(a) for a in whole.absorbed) > 20
         q.put((rank, "ok"))
     except Exception as e:  # noqa: BLE001
         import traceback
