@@ -974,6 +974,117 @@ int reserve_work(plane_ransac_ctx* c) {
   return PR_OK;
 }
 
+// ---- cell-ordered copy of the current cloud: shared by normal estimation and clusterFilt ----------------------------
+// Uniform grid over the bounding box of the staged cloud (a superset of the current one), cell = radius (1 + 1e-6), so
+// that every neighbour within the radius lies in the 27 cells around a point's cell; points sorted by cell key.
+// Leaves sorted keys in d_nrm_keys[n..2n), sorted indices in d_nrm_idx[n..2n), sorted coordinates in d_nrm_xyz.
+int build_cell_order(plane_ransac_ctx* c, double radius, pr::NormalsGrid* grid) {
+  const size_t n = c->n_current;
+  pr::NormalsGrid g;
+  const double h = radius * (1.0 + 1e-6);
+  g.inv_h = 1.0 / h;
+  double cells = 1.0;
+  for (int a = 0; a < 3; ++a) {
+    double lo = 0.0, hi = 0.0;
+    if (c->bbox_keys[a] <= c->bbox_keys[3 + a]) {
+      lo = (double)pr::key_to_float(c->bbox_keys[a]);
+      hi = (double)pr::key_to_float(c->bbox_keys[3 + a]);
+    }
+    g.lo[a] = lo;
+    const double d = std::floor((hi - lo) * g.inv_h) + 1.0;
+    if (!(d >= 1.0) || d > 2097152.0) return fail(PR_ERR_INVALID, "radius %g is too small for the cloud extent %g", radius, hi - lo);
+    g.dim[a] = (long long)d;
+    cells *= d;
+  }
+  if (cells > 9.0e18) return fail(PR_ERR_INVALID, "radius too small for the cloud extent");
+  g.no_cell = (unsigned long long)g.dim[0] * (unsigned long long)g.dim[1] * (unsigned long long)g.dim[2];
+  int key_bits = 1;
+  while (key_bits < 64 && (g.no_cell >> key_bits) != 0) ++key_bits;
+  PR_TRY(dev_reserve(c->d_nrm_keys, 2 * n));
+  PR_TRY(dev_reserve(c->d_nrm_idx, 2 * n));
+  PR_TRY(dev_reserve(c->d_nrm_xyz, 3 * n));
+  const size_t tb = pr::normals_sort_temp_bytes(n);
+  PR_TRY(dev_reserve(c->d_nrm_temp, tb + 256));
+  {
+    Span sp(c, KC_OTHER, 3);
+    pr::launch_normals_sort(c->current, n, g, key_bits, c->d_nrm_keys.p, c->d_nrm_idx.p, c->d_nrm_temp.p, tb, c->d_nrm_xyz.p, c->stream);
+  }
+  *grid = g;
+  return PR_OK;
+}
+// Maps every peer's mailbox (CUDA IPC over NVLink).  Collective; all ranks end with the same p2p_on: if any rank
+// cannot map a peer (no P2P path, IPC unavailable) or PR_P2P=0 is set, every rank keeps the NCCL exchanges.
+int p2p_setup(plane_ransac_ctx* c) {
+  c->p2p_on = false;
+  if (c->n_ranks < 2) return PR_OK;
+  const char* env = getenv("PR_P2P");
+  int ok = (c->n_ranks <= pr::kP2PMaxRanks && !(env && atoi(env) == 0)) ? 1 : 0;
+  PR_TRY(dev_reserve(c->d_p2p_aux, 8));
+  PR_TRY(pin_reserve(c->h_p2p_err, 1));
+  *c->h_p2p_err.p = 0;
+  PR_CUDA(cudaMemsetAsync(c->d_p2p_aux.p, 0, 8 * sizeof(unsigned), c->stream));
+  cudaIpcMemHandle_t mine;
+  std::memset(&mine, 0, sizeof(mine));
+  if (ok) {
+    if (cudaMalloc(&c->p2p_mailbox, kP2PMailboxBytes) != cudaSuccess || cudaMemset(c->p2p_mailbox, 0, kP2PMailboxBytes) != cudaSuccess ||
+        cudaDeviceSynchronize() != cudaSuccess || cudaIpcGetMemHandle(&mine, c->p2p_mailbox) != cudaSuccess) {
+      cudaGetLastError();
+      ok = 0;
+    }
+  }
+  // all-gather of the handles (64 bytes each) and of the per-rank verdicts through NCCL
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t size");
+  const size_t rec = 64 + 8;
+  DevBuf<unsigned char> d_h;
+  PR_TRY(dev_reserve(d_h, rec * (size_t)(c->n_ranks + 1)));
+  std::vector<unsigned char> h((size_t)(c->n_ranks + 1) * rec, 0);
+  std::memcpy(h.data(), &mine, 64);
+  h[64] = (unsigned char)ok;
+  int rc = PR_OK;
+  auto gather = [&]() -> int {
+    PR_CUDA(cudaMemcpyAsync(d_h.p, h.data(), rec, cudaMemcpyHostToDevice, c->stream));
+    PR_NCCL(g_nccl.AllGather(d_h.p, d_h.p + rec, rec, ncclUint8, c->comm, c->stream));
+    PR_CUDA(cudaMemcpyAsync(h.data() + rec, d_h.p + rec, rec * (size_t)c->n_ranks, cudaMemcpyDeviceToHost, c->stream));
+    PR_CUDA(cudaStreamSynchronize(c->stream));
+    return PR_OK;
+  };
+  rc = gather();
+  if (rc == PR_OK) {
+    for (int r = 0; r < c->n_ranks; ++r) ok = ok && h[rec * (size_t)(r + 1) + 64];
+    c->p2p_view.n_ranks = c->n_ranks;
+    c->p2p_view.rank = c->rank;
+    for (int r = 0; r < pr::kP2PMaxRanks; ++r) c->p2p_view.peers[r] = nullptr;
+    if (ok) {
+      for (int r = 0; r < c->n_ranks; ++r) {
+        if (r == c->rank) {
+          c->p2p_view.peers[r] = c->p2p_mailbox;
+          continue;
+        }
+        cudaIpcMemHandle_t hr;
+        std::memcpy(&hr, h.data() + rec * (size_t)(r + 1), 64);
+        void* ptr = nullptr;
+        if (cudaIpcOpenMemHandle(&ptr, hr, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+          cudaGetLastError();
+          ok = 0;
+          break;
+        }
+        c->p2p_view.peers[r] = static_cast<unsigned char*>(ptr);
+      }
+    }
+    // second round: did every rank map every peer?
+    h[64] = (unsigned char)ok;
+    rc = gather();
+    if (rc == PR_OK)
+      for (int r = 0; r < c->n_ranks; ++r) ok = ok && h[rec * (size_t)(r + 1) + 64];
+  }
+  dev_free(d_h);
+  if (rc != PR_OK) ok = 0;
+  if (!ok) p2p_teardown(c);
+  c->p2p_on = ok != 0;
+  for (auto& e : c->p2p_epoch) e = 0;
+  return rc;
+}
+
 }  // namespace
 
 // =================================================================================================
@@ -1383,49 +1494,6 @@ int plane_ransac_remaining(plane_ransac_ctx* c, pr_point* out, size_t cap, size_
   return PR_OK;
 }
 
-
-// ---- cell-ordered copy of the current cloud: shared by normal estimation and clusterFilt ----------------------------
-} // extern "C"
-namespace {
-// Uniform grid over the bounding box of the staged cloud (a superset of the current one), cell = radius (1 + 1e-6), so
-// that every neighbour within the radius lies in the 27 cells around a point's cell; points sorted by cell key.
-// Leaves sorted keys in d_nrm_keys[n..2n), sorted indices in d_nrm_idx[n..2n), sorted coordinates in d_nrm_xyz.
-int build_cell_order(plane_ransac_ctx* c, double radius, pr::NormalsGrid* grid) {
-  const size_t n = c->n_current;
-  pr::NormalsGrid g;
-  const double h = radius * (1.0 + 1e-6);
-  g.inv_h = 1.0 / h;
-  double cells = 1.0;
-  for (int a = 0; a < 3; ++a) {
-    double lo = 0.0, hi = 0.0;
-    if (c->bbox_keys[a] <= c->bbox_keys[3 + a]) {
-      lo = (double)pr::key_to_float(c->bbox_keys[a]);
-      hi = (double)pr::key_to_float(c->bbox_keys[3 + a]);
-    }
-    g.lo[a] = lo;
-    const double d = std::floor((hi - lo) * g.inv_h) + 1.0;
-    if (!(d >= 1.0) || d > 2097152.0) return fail(PR_ERR_INVALID, "radius %g is too small for the cloud extent %g", radius, hi - lo);
-    g.dim[a] = (long long)d;
-    cells *= d;
-  }
-  if (cells > 9.0e18) return fail(PR_ERR_INVALID, "radius too small for the cloud extent");
-  g.no_cell = (unsigned long long)g.dim[0] * (unsigned long long)g.dim[1] * (unsigned long long)g.dim[2];
-  int key_bits = 1;
-  while (key_bits < 64 && (g.no_cell >> key_bits) != 0) ++key_bits;
-  PR_TRY(dev_reserve(c->d_nrm_keys, 2 * n));
-  PR_TRY(dev_reserve(c->d_nrm_idx, 2 * n));
-  PR_TRY(dev_reserve(c->d_nrm_xyz, 3 * n));
-  const size_t tb = pr::normals_sort_temp_bytes(n);
-  PR_TRY(dev_reserve(c->d_nrm_temp, tb + 256));
-  {
-    Span sp(c, KC_OTHER, 3);
-    pr::launch_normals_sort(c->current, n, g, key_bits, c->d_nrm_keys.p, c->d_nrm_idx.p, c->d_nrm_temp.p, tb, c->d_nrm_xyz.p, c->stream);
-  }
-  *grid = g;
-  return PR_OK;
-}
-}  // namespace
-extern "C" {
 
 // ---- pcl::NormalEstimationOMP with a radius search (Dialog/PlaneDetect.h:515-545) ----------------------------------
 int plane_ransac_estimate_normals(plane_ransac_ctx* c, double radius, const float viewpoint[3], pr_normal* out, size_t cap,
@@ -1889,83 +1957,6 @@ int plane_ransac_comm_unique_id(void* out128) {
   std::memcpy(out128, &id, sizeof(id));
   return PR_OK;
 }
-
-namespace {
-
-// Maps every peer's mailbox (CUDA IPC over NVLink).  Collective; all ranks end with the same p2p_on: if any rank
-// cannot map a peer (no P2P path, IPC unavailable) or PR_P2P=0 is set, every rank keeps the NCCL exchanges.
-int p2p_setup(plane_ransac_ctx* c) {
-  c->p2p_on = false;
-  if (c->n_ranks < 2) return PR_OK;
-  const char* env = getenv("PR_P2P");
-  int ok = (c->n_ranks <= pr::kP2PMaxRanks && !(env && atoi(env) == 0)) ? 1 : 0;
-  PR_TRY(dev_reserve(c->d_p2p_aux, 8));
-  PR_TRY(pin_reserve(c->h_p2p_err, 1));
-  *c->h_p2p_err.p = 0;
-  PR_CUDA(cudaMemsetAsync(c->d_p2p_aux.p, 0, 8 * sizeof(unsigned), c->stream));
-  cudaIpcMemHandle_t mine;
-  std::memset(&mine, 0, sizeof(mine));
-  if (ok) {
-    if (cudaMalloc(&c->p2p_mailbox, kP2PMailboxBytes) != cudaSuccess || cudaMemset(c->p2p_mailbox, 0, kP2PMailboxBytes) != cudaSuccess ||
-        cudaDeviceSynchronize() != cudaSuccess || cudaIpcGetMemHandle(&mine, c->p2p_mailbox) != cudaSuccess) {
-      cudaGetLastError();
-      ok = 0;
-    }
-  }
-  // all-gather of the handles (64 bytes each) and of the per-rank verdicts through NCCL
-  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t size");
-  const size_t rec = 64 + 8;
-  DevBuf<unsigned char> d_h;
-  PR_TRY(dev_reserve(d_h, rec * (size_t)(c->n_ranks + 1)));
-  std::vector<unsigned char> h((size_t)(c->n_ranks + 1) * rec, 0);
-  std::memcpy(h.data(), &mine, 64);
-  h[64] = (unsigned char)ok;
-  int rc = PR_OK;
-  auto gather = [&]() -> int {
-    PR_CUDA(cudaMemcpyAsync(d_h.p, h.data(), rec, cudaMemcpyHostToDevice, c->stream));
-    PR_NCCL(g_nccl.AllGather(d_h.p, d_h.p + rec, rec, ncclUint8, c->comm, c->stream));
-    PR_CUDA(cudaMemcpyAsync(h.data() + rec, d_h.p + rec, rec * (size_t)c->n_ranks, cudaMemcpyDeviceToHost, c->stream));
-    PR_CUDA(cudaStreamSynchronize(c->stream));
-    return PR_OK;
-  };
-  rc = gather();
-  if (rc == PR_OK) {
-    for (int r = 0; r < c->n_ranks; ++r) ok = ok && h[rec * (size_t)(r + 1) + 64];
-    c->p2p_view.n_ranks = c->n_ranks;
-    c->p2p_view.rank = c->rank;
-    for (int r = 0; r < pr::kP2PMaxRanks; ++r) c->p2p_view.peers[r] = nullptr;
-    if (ok) {
-      for (int r = 0; r < c->n_ranks; ++r) {
-        if (r == c->rank) {
-          c->p2p_view.peers[r] = c->p2p_mailbox;
-          continue;
-        }
-        cudaIpcMemHandle_t hr;
-        std::memcpy(&hr, h.data() + rec * (size_t)(r + 1), 64);
-        void* ptr = nullptr;
-        if (cudaIpcOpenMemHandle(&ptr, hr, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
-          cudaGetLastError();
-          ok = 0;
-          break;
-        }
-        c->p2p_view.peers[r] = static_cast<unsigned char*>(ptr);
-      }
-    }
-    // second round: did every rank map every peer?
-    h[64] = (unsigned char)ok;
-    rc = gather();
-    if (rc == PR_OK)
-      for (int r = 0; r < c->n_ranks; ++r) ok = ok && h[rec * (size_t)(r + 1) + 64];
-  }
-  dev_free(d_h);
-  if (rc != PR_OK) ok = 0;
-  if (!ok) p2p_teardown(c);
-  c->p2p_on = ok != 0;
-  for (auto& e : c->p2p_epoch) e = 0;
-  return rc;
-}
-
-}  // namespace
 
 int plane_ransac_comm_init(plane_ransac_ctx* c, int n_ranks, int rank, const void* unique_id128) {
   PR_TRY(check_ctx(c));
