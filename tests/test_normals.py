@@ -170,3 +170,32 @@ def test_gpu_cluster_filter_matches_oracle():
         removed, left = pr.cluster_filter(0.15, 30)
         assert left == int(keep.sum()) and pr.remaining().tobytes() == rem[keep].tobytes()
         assert pr.cluster_filter(0.15, 30) == (0, left)
+
+
+def test_oracle_normals_against_numpy_pca():
+    """Independent check of the oracle: float64 numpy PCA over the same FLANN neighbourhoods (brute force) gives the same
+    normals up to sign and the same curvature."""
+    pts = noisy_scene(1500)
+    r = 0.3
+    nrm, cnt = O.estimate_normals(pts, r, mode=O.NORMALS_FIXED)
+    xyz32 = pts[:, :3]
+    checked = 0
+    for i in range(0, len(pts), 7):
+        d = xyz32[i] - xyz32
+        d2 = (d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]) + d[:, 2] * d[:, 2]      # float32, FLANN's order
+        nb = np.nonzero(d2 < np.float32(r * r))[0]
+        assert len(nb) == cnt[i]
+        if len(nb) < 5:
+            continue
+        q = xyz32[nb].astype(np.float64)
+        w, v = np.linalg.eigh(np.cov(q.T, bias=True))
+        if w[1] - w[0] < 1e-3 * w[2]:
+            continue                                                        # near-degenerate: direction ill defined
+        n_ref = v[:, 0]
+        assert min(np.abs(nrm[i, :3] - n_ref).max(), np.abs(nrm[i, :3] + n_ref).max()) < 5e-5, i
+        # the 2^-18-of-the-radius grid shows in the curvature of small neighbourhoods at the 1e-5 level
+        assert abs(nrm[i, 3] - w[0] / w.sum()) < 1e-4 * max(1e-3, w[0] / w.sum()) + 1e-7
+        # PCL's viewpoint rule with the default viewpoint (origin): (vp - p) . n >= 0
+        assert float(-(xyz32[i].astype(np.float64)) @ nrm[i, :3].astype(np.float64)) >= -1e-6
+        checked += 1
+    assert checked > 100
