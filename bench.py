@@ -257,12 +257,23 @@ def run_extras(args, pr):
     want = O.reabsorb(rem[:n_cpu], coeffs, borders, 0.1, 20261018)
     cpu_s = time.perf_counter() - t0
     same = all(np.array_equal(a[a < n_cpu], b) for a, b in zip(cur, want.absorbed))
+    # the same prefix through the reference's OWN isPointInPoly source (oracle/_ref, built by oracle/build_ref.py)
+    ref_s, ref_same = None, None
+    if O.ref_lib() is not None:
+        t0 = time.perf_counter()
+        ref_masks = [O.ref_points_in_poly(rem[:n_cpu], coeffs[k], borders[k], 0.1, 20261018) for k in range(len(coeffs))]
+        ref_s = time.perf_counter() - t0
+        ref_same = all(np.array_equal(np.nonzero(m)[0], a[a < n_cpu]) for m, a in zip(ref_masks, cur))
     out["reabsorb_postProcessPlanes"] = {
         "points": int(len(rem)), "planes": int(len(coeffs)), "border_vertices_per_plane": int(len(borders[0])),
         "gpu_ms": sum(ms) / len(ms), "absorbed": int(sum(len(a) for a in cur)), "points_left": int(n_left),
         "cpu_oracle_s_per_point": cpu_s / n_cpu, "cpu_sample_points": n_cpu, "cpu_threads": 1,
         "cpu_s_extrapolated": cpu_s / n_cpu * len(rem), "identical_on_cpu_sample": bool(same),
         "speedup_extrapolated": (cpu_s / n_cpu * len(rem)) / (sum(ms) / len(ms) * 1e-3),
+        "reference_source": None if ref_s is None else {
+            "kind": "reference", "what": "Dialog/PlaneDetect.h isPointInPoly compiled over oracle/ref_shim.h (oracle/_ref), 1 thread",
+            "s_per_point": ref_s / n_cpu, "s_extrapolated": ref_s / n_cpu * len(rem), "identical_on_cpu_sample": bool(ref_same),
+            "speedup_extrapolated": (ref_s / n_cpu * len(rem)) / (sum(ms) / len(ms) * 1e-3)},
         "note": "cloud resident (set_cloud before the timer), polygon upload + kernels + index lists back inside it"}
     # estimateNormal() (pcl::NormalEstimationOMP, radius search) on the 10M-point scene
     pr.set_cloud(pts10)
