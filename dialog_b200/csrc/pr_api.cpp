@@ -2132,6 +2132,13 @@ int plane_ransac_host_draw_triples(size_t n_points, unsigned seed, int n_draws, 
   return PR_OK;
 }
 
+int plane_ransac_host_draw_triples_parallel(size_t n_points, unsigned seed, int n_draws, int32_t* triples, int* fell_back) {
+  if (n_points < 3 || n_points > (size_t)INT_MAX) return fail(PR_ERR_INVALID, "need 3 .. INT_MAX points to sample");
+  if (n_draws < 0 || (n_draws && !triples) || !fell_back) return fail(PR_ERR_INVALID, "bad n_draws/triples");
+  *fell_back = pr::draw_triples_parallel(n_points, seed, n_draws, triples) ? 0 : 1;
+  return PR_OK;
+}
+
 int plane_ransac_host_replay(const int32_t* counts, const uint8_t* good, int n_draws, long long n_points,
                              int max_iterations, double probability, int* best_draw, int* iterations, int* draws_used,
                              int* skipped, int* exhausted) {

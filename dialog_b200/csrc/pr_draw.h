@@ -1,0 +1,111 @@
+// pr_draw.h — PCL's sample stream (SampleConsensusModel::drawIndexSample, pcl/sample_consensus/sac_model.h, the
+// sampler behind the reference's only SAC call, Dialog/SimplifyVerticesSize.cpp:64-67) evaluated in parallel.
+//
+// The sequential definition: shuffled[] starts as the identity over the N indices of the round's cloud; draw t runs
+// op s = 3t + i for i = 0, 1, 2:   swap(shuffled[i], shuffled[i + rnd_s % (N - i)])   and returns shuffled[0..3).
+// rnd_s is the s-th value of mt19937(seed) >> 1 and does not depend on N, so the stream is generated once per seed.
+//
+// Write a_s = s % 3, b_s = a_s + rnd_s % (N - a_s), v_s = content of position b_s just before op s.  Op s leaves v_s
+// in position a_s, and no later op of the same draw touches position a_s again (op i only touches positions >= i),
+// so draw t returns (v_3t, v_3t+1, v_3t+2).  Position b_s holds b_s itself unless an earlier op touched it, which is
+// rare (about (3K)^2 / 2N ops of a round collide): every op is therefore evaluated independently (v_s = b_s), the few
+// ops whose position was picked by another op or lies in the head {0, 1, 2} are collected, sorted by s and replayed
+// sequentially with the exact swap semantics.  draw_resolve below is that replay; the kernels in pr_kernels.cu and the
+// host emulation behind plane_ransac_host_draw_triples_parallel (CPU tests against pr::IndexSampler) share it.
+#pragma once
+
+#include <stdint.h>
+
+#include "pr_math.h"  // PR_HD
+
+namespace pr {
+
+constexpr uint32_t kDrawNoOp = 0xFFFFFFFFu;
+constexpr uint64_t kDrawEmptySlot = ~0ull;
+// Collected ops the sequential replay accepts (more: the round falls back to the host sampler).
+constexpr int kDrawMaxCollisions = 2048;
+
+PR_HD uint32_t draw_position(uint32_t s, uint32_t rnd, uint32_t n_points) {
+  const uint32_t a = s % 3u;
+  return a + rnd % (n_points - a);
+}
+
+PR_HD uint32_t draw_hash(uint32_t q) { return (q * 2654435761u) >> 5; }
+
+// Content of head position p (0..2) just before op s: the later of the last swap that had p as its first operand
+// (every third op; it left v there) and the last recorded swap of another head position with p.
+PR_HD int32_t draw_head_before(uint32_t p, uint32_t s, const int32_t* v, const long long hw_time[3], const int32_t hw_val[3]) {
+  const uint32_t d = (s % 3u + 3u - p) % 3u;
+  const long long ua = (long long)s - (d == 0 ? 3 : (long long)d);  // last op before s with a == p (negative: none)
+  const long long tb = hw_time[p];
+  if (tb >= 0 && tb > ua) return hw_val[p];
+  if (ua >= 0) return v[ua];
+  return (int32_t)p;
+}
+
+// Sequential replay of the collected ops (ascending s, duplicates allowed).  v[s] holds b_s on entry for every op and
+// the exact v_s on return.  map_*: open-addressing scratch with map_mask + 1 >= 2 * n_ops slots, keys preset to
+// kDrawNoOp.
+PR_HD void draw_resolve(const uint32_t* ops_sorted, int n_ops, int32_t* v, uint32_t* map_keys, int32_t* map_vals,
+                        uint32_t map_mask) {
+  long long hw_time[3] = {-1, -1, -1};
+  int32_t hw_val[3] = {0, 0, 0};
+  uint32_t prev = kDrawNoOp;
+  for (int i = 0; i < n_ops; ++i) {
+    const uint32_t s = ops_sorted[i];
+    if (s == prev) continue;
+    prev = s;
+    const uint32_t a = s % 3u;
+    const uint32_t q = (uint32_t)v[s];  // still b_s: every op is replayed once
+    const int32_t w = draw_head_before(a, s, v, hw_time, hw_val);
+    int32_t val;
+    if (q < 3u) {
+      val = draw_head_before(q, s, v, hw_time, hw_val);
+      if (q != a) {
+        hw_time[q] = (long long)s;
+        hw_val[q] = w;
+      }
+    } else {
+      uint32_t h = draw_hash(q) & map_mask;
+      while (map_keys[h] != kDrawNoOp && map_keys[h] != q) h = (h + 1) & map_mask;
+      val = map_keys[h] == q ? map_vals[h] : (int32_t)q;
+      map_keys[h] = q;
+      map_vals[h] = w;
+    }
+    v[s] = val;
+  }
+}
+
+// Parallel phase, one call per op: v[s] = b_s; ops in the head and ops whose position another op also picked are
+// appended to coll (the first op of a position is appended by whoever finds it there; duplicates are fine).  The
+// counter keeps counting past coll_cap so that the overflow is visible.  A: atomics policy (device / host emulation).
+template <class A>
+PR_HD void draw_scatter(uint32_t s, uint32_t rnd, uint32_t n_points, int32_t* v, unsigned long long* table, uint32_t table_mask,
+                        uint32_t* coll, uint32_t* coll_count, uint32_t coll_cap) {
+  const uint32_t q = draw_position(s, rnd, n_points);
+  v[s] = (int32_t)q;
+  uint32_t first_other = kDrawNoOp;
+  bool collide = q < 3u;
+  if (!collide) {
+    const unsigned long long mine = ((unsigned long long)q << 32) | s;
+    uint32_t h = draw_hash(q) & table_mask;
+    for (;;) {
+      const unsigned long long old = A::cas(&table[h], kDrawEmptySlot, mine);
+      if (old == kDrawEmptySlot) break;
+      if ((uint32_t)(old >> 32) == q) {
+        collide = true;
+        first_other = (uint32_t)old;
+        break;
+      }
+      h = (h + 1) & table_mask;
+    }
+  }
+  if (collide) {
+    const uint32_t n_new = first_other != kDrawNoOp ? 2u : 1u;
+    const uint32_t at = A::add(coll_count, n_new);
+    if (at < coll_cap) coll[at] = s;
+    if (n_new == 2u && at + 1 < coll_cap) coll[at + 1] = first_other;
+  }
+}
+
+}  // namespace pr

@@ -2,9 +2,13 @@
 // common/impl/eigen.hpp); PCL itself is not part of the reference tree.
 #include "pr_host.hpp"
 
+#include "pr_draw.h"
+#include "pr_math.h"
+
 #include <cfloat>
 #include <climits>
 #include <cmath>
+#include <algorithm>
 #include <cstring>
 
 namespace pr {
@@ -145,6 +149,53 @@ void IndexSampler::draw(int32_t out[3]) {
   out[2] = head_[2];
 }
 
+void fill_rnd_stream(uint32_t seed, size_t count, uint32_t* out) {
+  Mt19937 rng(seed);
+  for (size_t k = 0; k < count; ++k) out[k] = rng.next() >> 1;
+}
+
+namespace {
+struct HostAtomics {
+  static unsigned long long cas(unsigned long long* p, unsigned long long expect, unsigned long long v) {
+    const unsigned long long old = *p;
+    if (old == expect) *p = v;
+    return old;
+  }
+  static uint32_t add(uint32_t* p, uint32_t v) {
+    const uint32_t old = *p;
+    *p += v;
+    return old;
+  }
+};
+}  // namespace
+
+bool draw_triples_parallel(size_t n_points, uint32_t seed, int n_draws, int32_t* triples) {
+  const size_t n_ops = 3 * (size_t)n_draws;
+  if (n_ops == 0) return true;
+  std::vector<uint32_t> rnd(n_ops);
+  fill_rnd_stream(seed, n_ops, rnd.data());
+  size_t cap = 1024;
+  while (cap < 4 * n_ops) cap <<= 1;
+  std::vector<unsigned long long> table(cap, kDrawEmptySlot);
+  std::vector<uint32_t> coll(2 * kDrawMaxCollisions);
+  uint32_t n_coll = 0;
+  // the device runs the ops in any order: emulate the reverse one, so that the op that owns a table slot is never
+  // the earliest op of its position
+  for (size_t k = n_ops; k-- > 0;)
+    draw_scatter<HostAtomics>((uint32_t)k, rnd[k], (uint32_t)n_points, triples, table.data(), (uint32_t)(cap - 1), coll.data(), &n_coll,
+                              (uint32_t)coll.size());
+  if (n_coll > (uint32_t)coll.size()) return false;
+  std::sort(coll.begin(), coll.begin() + n_coll);
+  const size_t distinct = (size_t)(std::unique(coll.begin(), coll.begin() + n_coll) - coll.begin());
+  if (distinct > (size_t)kDrawMaxCollisions) return false;
+  uint32_t map_cap = 16;
+  while (map_cap < 2 * distinct) map_cap <<= 1;
+  std::vector<uint32_t> mk(map_cap, kDrawNoOp);
+  std::vector<int32_t> mv(map_cap, 0);
+  draw_resolve(coll.data(), (int)distinct, triples, mk.data(), mv.data(), map_cap - 1);
+  return true;
+}
+
 RansacReplay::RansacReplay(long long n_points, int max_iterations, double probability)
     : one_over_n_(1.0 / (double)n_points),
       log_probability_(std::log(1.0 - probability)),
@@ -231,104 +282,12 @@ int scale_exp_from_bbox_keys(const uint32_t keys[6]) {
   return 30 - e;
 }
 
-// --- pcl::eigen33 / computeRoots / computeRoots2 (common/impl/eigen.hpp) in double ---------------
-static void roots2(double b, double c, double roots[3]) {
-  roots[0] = 0.0;
-  double d = b * b - 4.0 * c;
-  if (d < 0.0) d = 0.0;
-  const double sd = std::sqrt(d);
-  roots[2] = 0.5 * (b + sd);
-  roots[1] = 0.5 * (b - sd);
-}
-
-static void roots3(const double m[9], double roots[3]) {
-  const double c0 = m[0] * m[4] * m[8] + 2.0 * m[1] * m[2] * m[5] - m[0] * m[5] * m[5] - m[4] * m[2] * m[2] -
-                    m[8] * m[1] * m[1];
-  const double c1 = m[0] * m[4] - m[1] * m[1] + m[0] * m[8] - m[2] * m[2] + m[4] * m[8] - m[5] * m[5];
-  const double c2 = m[0] + m[4] + m[8];
-  if (std::fabs(c0) < DBL_EPSILON) {
-    roots2(c2, c1, roots);
-    return;
-  }
-  const double s_inv3 = 1.0 / 3.0;
-  const double s_sqrt3 = std::sqrt(3.0);
-  const double c2_over_3 = c2 * s_inv3;
-  double a_over_3 = (c1 - c2 * c2_over_3) * s_inv3;
-  if (a_over_3 > 0.0) a_over_3 = 0.0;
-  const double half_b = 0.5 * (c0 + c2_over_3 * (2.0 * c2_over_3 * c2_over_3 - c1));
-  double q = half_b * half_b + a_over_3 * a_over_3 * a_over_3;
-  if (q > 0.0) q = 0.0;
-  const double rho = std::sqrt(-a_over_3);
-  const double theta = std::atan2(std::sqrt(-q), half_b) * s_inv3;
-  const double cos_theta = std::cos(theta);
-  const double sin_theta = std::sin(theta);
-  roots[0] = c2_over_3 + 2.0 * rho * cos_theta;
-  roots[1] = c2_over_3 - rho * (cos_theta + s_sqrt3 * sin_theta);
-  roots[2] = c2_over_3 - rho * (cos_theta - s_sqrt3 * sin_theta);
-  double tmp;
-  if (roots[0] >= roots[1]) { tmp = roots[0]; roots[0] = roots[1]; roots[1] = tmp; }
-  if (roots[1] >= roots[2]) {
-    tmp = roots[1]; roots[1] = roots[2]; roots[2] = tmp;
-    if (roots[0] >= roots[1]) { tmp = roots[0]; roots[0] = roots[1]; roots[1] = tmp; }
-  }
-  if (roots[0] <= 0) roots2(c2, c1, roots);
-}
-
-static void smallest_eigenvector(const double mat[9], double vec[3]) {
-  double scale = 0.0;
-  for (int i = 0; i < 9; ++i) {
-    const double a = std::fabs(mat[i]);
-    if (a > scale) scale = a;
-  }
-  if (scale <= DBL_MIN) scale = 1.0;
-  double s[9];
-  for (int i = 0; i < 9; ++i) s[i] = mat[i] / scale;
-  double ev[3];
-  roots3(s, ev);
-  s[0] -= ev[0];
-  s[4] -= ev[0];
-  s[8] -= ev[0];
-  const double *r0 = s, *r1 = s + 3, *r2 = s + 6;
-  const double v1[3] = {r0[1] * r1[2] - r0[2] * r1[1], r0[2] * r1[0] - r0[0] * r1[2], r0[0] * r1[1] - r0[1] * r1[0]};
-  const double v2[3] = {r0[1] * r2[2] - r0[2] * r2[1], r0[2] * r2[0] - r0[0] * r2[2], r0[0] * r2[1] - r0[1] * r2[0]};
-  const double v3[3] = {r1[1] * r2[2] - r1[2] * r2[1], r1[2] * r2[0] - r1[0] * r2[2], r1[0] * r2[1] - r1[1] * r2[0]};
-  const double len1 = v1[0] * v1[0] + v1[1] * v1[1] + v1[2] * v1[2];
-  const double len2 = v2[0] * v2[0] + v2[1] * v2[1] + v2[2] * v2[2];
-  const double len3 = v3[0] * v3[0] + v3[1] * v3[1] + v3[2] * v3[2];
-  const double* best;
-  double len;
-  if (len1 >= len2 && len1 >= len3) { best = v1; len = len1; }
-  else if (len2 >= len1 && len2 >= len3) { best = v2; len = len2; }
-  else { best = v3; len = len3; }
-  const double nrm = std::sqrt(len);
-  vec[0] = best[0] / nrm;
-  vec[1] = best[1] / nrm;
-  vec[2] = best[2] / nrm;
-}
-
+// --- pcl::eigen33 / computeRoots / computeRoots2 (common/impl/eigen.hpp) in double: pr_math.h, the same source the
+// device-side round loop runs (portable atan2 / sin / cos, so host and kernel agree bit for bit) ---------------------
 bool plane_from_moments(const int64_t m[16], const float pivot[3], int scale_exp, float coeff[4]) {
-  typedef __int128 i128;
-  const int64_t n = m[0];
-  if (n < 4) return false;
-  const i128 S[3] = {m[1], m[2], m[3]};
-  i128 Sab[6];
-  for (int k = 0; k < 6; ++k) Sab[k] = (i128)m[4 + 2 * k] * ((i128)1 << 32) + (i128)m[5 + 2 * k];
-  static const int A[6] = {0, 0, 0, 1, 1, 2}, B[6] = {0, 1, 2, 1, 2, 2};
-  double C[6];
-  for (int k = 0; k < 6; ++k) C[k] = (double)((i128)n * Sab[k] - S[A[k]] * S[B[k]]);
-  const double cov[9] = {C[0], C[1], C[2], C[1], C[3], C[4], C[2], C[4], C[5]};
-  double v[3];
-  smallest_eigenvector(cov, v);
-  const double inv = std::ldexp(1.0, -scale_exp);
-  const double cx = (double)pivot[0] + ((double)m[1] / (double)n) * inv;
-  const double cy = (double)pivot[1] + ((double)m[2] / (double)n) * inv;
-  const double cz = (double)pivot[2] + ((double)m[3] / (double)n) * inv;
-  const double d = -((v[0] * cx + v[1] * cy) + v[2] * cz);
-  coeff[0] = (float)v[0];
-  coeff[1] = (float)v[1];
-  coeff[2] = (float)v[2];
-  coeff[3] = (float)d;
-  return true;
+  long long mm[16];
+  for (int i = 0; i < 16; ++i) mm[i] = (long long)m[i];
+  return pm_plane_from_moments(mm, pivot, scale_exp, coeff);
 }
 
 float threshold_up(double t) {

@@ -62,6 +62,13 @@ class IndexSampler {
   uint32_t d_[3] = {1, 1, 1};
 };
 
+// The first `count` values of rnd() = mt19937(seed)() >> 1, the stream drawIndexSample consumes.
+void fill_rnd_stream(uint32_t seed, size_t count, uint32_t* out);
+// The parallel formulation of the sampler the device-side round loop runs (pr_draw.h), emulated on the host with the
+// same per-op code: triples of the first n_draws draws over n_points indices.  Returns false when more than
+// kDrawMaxCollisions ops would have to be replayed sequentially (the device then leaves the round to the host sampler).
+bool draw_triples_parallel(size_t n_points, uint32_t seed, int n_draws, int32_t* triples);
+
 // RandomSampleConsensus::computeModel's while-loop (PCL 1.8 ransac.hpp), fed one draw at a time.
 // The draw stream does not depend on the scores, so the device scores a batch of draws and this
 // object replays PCL's sequential decisions (strict '>' first-best, adaptive k, iteration cap,

@@ -381,6 +381,15 @@ def host_draw_triples(n_points: int, n_draws: int, seed: int = 12345) -> np.ndar
     return out
 
 
+def host_draw_triples_parallel(n_points: int, n_draws: int, seed: int = 12345):
+    """The same triples through the parallel formulation of the sampler that the device-side round loop runs
+    (csrc/pr_draw.h).  Returns None when it hands the round back to the sequential sampler (too many colliding ops)."""
+    out = np.empty((n_draws, 3), np.int32)
+    fb = C.c_int(0)
+    _lib.check(_lib.load().plane_ransac_host_draw_triples_parallel(n_points, seed, n_draws, out.ctypes.data_as(C.c_void_p), C.byref(fb)))
+    return None if fb.value else out
+
+
 def host_replay(counts, good, n_points: int, max_iterations: int, probability: float):
     c = np.ascontiguousarray(counts, np.int32)
     g = np.ascontiguousarray(good, np.uint8)

@@ -274,6 +274,11 @@ int plane_ransac_flush_l2(plane_ransac_ctx* ctx);
 /* ---- host-side logic, exported for tests and multi-process drivers (no device work) -----------
  * The first n_draws triples SampleConsensusModel::drawIndexSample yields for n points. */
 int plane_ransac_host_draw_triples(size_t n_points, unsigned seed, int n_draws, int32_t* triples);
+/* The same triples through the parallel formulation the device-side round loop uses (csrc/pr_draw.h): every op of the
+ * partial Fisher-Yates walk is evaluated independently and only the ops whose position was also picked by another op
+ * are replayed sequentially.  *fell_back = 1 (triples untouched beyond scratch use) when more ops collide than the
+ * device replays; the device then leaves that round to the sequential host sampler. */
+int plane_ransac_host_draw_triples_parallel(size_t n_points, unsigned seed, int n_draws, int32_t* triples, int* fell_back);
 /* RandomSampleConsensus::computeModel's loop replayed over per-draw results: counts[j] is the
  * inlier count of draw j, good[j] isSampleGood's verdict.  Returns the index of the winning draw in
  * *best_draw (-1: none), fills iterations/draws_used/skipped, and sets *exhausted when the loop

@@ -19,6 +19,28 @@ def test_sampler_matches_oracle(O, n):
     assert (D.host_draw_triples(n, 20, seed=7) == O.draw_sequence(n, 20, seed=7)).all()
 
 
+@pytest.mark.parametrize("n,draws", [(3, 5), (3, 500), (4, 100), (10, 600), (100, 300), (1000, 600), (32768, 256), (32768, 640),
+                                     (100_000, 4096), (1_000_000, 4096), (2_200_000, 4096), (10_000_000, 4096),
+                                     (2**31 - 5000, 4096)])
+def test_parallel_sampler_equals_the_sequential_walk(n, draws):
+    """The formulation the device-side round loop runs (csrc/pr_draw.h, same per-op code emulated on the host): independent
+    ops + a sequential replay of the colliding ones gives PCL's triples exactly, down to clouds where every op collides."""
+    for seed in (12345, 7):
+        got = D.host_draw_triples_parallel(n, draws, seed=seed)
+        assert got is not None
+        assert (got == D.host_draw_triples(n, draws, seed=seed)).all()
+
+
+def test_parallel_sampler_hands_crowded_rounds_back():
+    # ~ (3K)^2 / N colliding ops: more than the device replays sequentially -> the round goes to the host sampler
+    assert D.host_draw_triples_parallel(5000, 4096) is None
+    rng = np.random.default_rng(3)
+    for _ in range(60):
+        n, k = int(10 ** rng.uniform(0.5, 7)), int(rng.integers(1, 3000))
+        got = D.host_draw_triples_parallel(n, k)
+        assert got is None or (got == D.host_draw_triples(n, k)).all()
+
+
 def test_sampler_rejects_tiny_clouds():
     with pytest.raises(D.PlaneRansacError):
         D.host_draw_triples(2, 1)
