@@ -19,6 +19,7 @@
 #include <string>
 #include <vector>
 
+#include "pr_draw.h"
 #include "pr_host.hpp"
 #include "pr_kernels.h"
 
@@ -204,13 +205,27 @@ struct plane_ransac_ctx {
   bool p2p_on = false;
   unsigned char* p2p_mailbox = nullptr;
   pr::P2PView p2p_view{};
-  unsigned long long p2p_epoch[4] = {0, 0, 0, 0};  // per channel, identical on every rank
-  DevBuf<unsigned> d_p2p_aux;                       // [0..4) producer tickets, [4] timeout flag
+  DevBuf<unsigned long long> d_p2p_epoch;           // per channel, identical on every rank; advanced by the exchange kernels
+  DevBuf<unsigned> d_p2p_aux;                       // [4] timeout flag
+  bool comm_failed = false;                         // an exchange timed out: the ranks are out of step for good
   PinBuf<unsigned> h_p2p_err;
   long long n_global_staged = 0, first_staged = 0, n_global_current = 0, first_current = 0;
   bool global_valid = false;
 
   pr::IndexSampler sampler;
+  int round_loop = PR_LOOP_AUTO;
+
+  // peel loop without the host (run_chain): device-resident round state, per-round records, the sampler's scratch
+  DevBuf<pr::RoundState> d_state;
+  PinBuf<pr::RoundState> h_state;
+  DevBuf<pr::RoundRecord> d_recs;
+  PinBuf<pr::RoundRecord> h_recs;
+  std::vector<cudaEvent_t> round_ev;
+  DevBuf<uint32_t> d_rnd;  // mt19937(seed) >> 1, the stream every round's draws consume
+  uint32_t rnd_seed = 0;
+  size_t rnd_count = 0;
+  DevBuf<unsigned long long> d_draw_table;
+  DevBuf<uint32_t> d_draw_coll;  // kDrawCollCap entries + the counter
 
   // chunked upload queued by plane_ransac_set_cloud_async: copies run on copy_stream, chunk k is complete at ev[k];
   // the first scoring pass (or any other call that needs the cloud) stages and consumes the chunks as they arrive
@@ -639,28 +654,26 @@ constexpr size_t kP2PMailboxBytes = kP2POffTotals + 2 * pr::kP2PMaxRanks * kP2PT
 
 inline size_t p2p_flag_off(int ch) { return (size_t)ch * pr::kP2PMaxRanks * sizeof(unsigned long long); }
 
-// K1a + its exchange: sample points of `n_samples` indices into dsp on every rank.
+// K1a + its exchange: sample points of `n_samples` indices into dsp on every rank.  st: the shard extent comes from the
+// device-resident round state and the exchange is skipped once the peel loop has stopped (run_chain).
 int exchange_samples(plane_ransac_ctx* c, pr::CloudView src, long long first, size_t n_local, const int32_t* dt, int n_samples,
-                     int4* dsp) {
+                     int4* dsp, const pr::RoundState* st = nullptr) {
   if (c->p2p_on && (size_t)n_samples <= 3 * kP2PMaxHyps) {
-    const unsigned long long e = ++c->p2p_epoch[P2P_SAMPLES];
-    const size_t off = kP2POffSamples + (size_t)(e & 1) * kP2PSamplesBytes;
-    pr::launch_p2p_samples(c->p2p_view, src, first, n_local, dt, n_samples, off, p2p_flag_off(P2P_SAMPLES), e, dsp,
-                           c->d_p2p_aux.p + 4, c->stream);
+    pr::launch_p2p_samples(c->p2p_view, src, first, n_local, dt, n_samples, kP2POffSamples, kP2PSamplesBytes, p2p_flag_off(P2P_SAMPLES),
+                           c->d_p2p_epoch.p + P2P_SAMPLES, dsp, c->d_p2p_aux.p + 4, c->stream, st);
     return PR_OK;
   }
-  pr::launch_gather_samples(src, first, n_local, dt, n_samples, dsp, 1, 0, c->stream);
+  pr::launch_gather_samples(src, first, n_local, dt, n_samples, dsp, 1, 0, c->stream, false, st);
   if (c->comm) PR_NCCL(g_nccl.AllReduce(dsp, dsp, (size_t)n_samples * 4, ncclInt32, ncclSum, c->comm, c->stream));
   return PR_OK;
 }
 
 // counts[0..n) summed over ranks, in place.
-int exchange_counts(plane_ransac_ctx* c, int32_t* dc, size_t n) {
+int exchange_counts(plane_ransac_ctx* c, int32_t* dc, size_t n, const pr::RoundState* st = nullptr) {
   if (!c->comm) return PR_OK;
   if (c->p2p_on && n <= kP2PMaxHyps) {
-    const unsigned long long e = ++c->p2p_epoch[P2P_COUNTS];
-    const size_t base = kP2POffCounts + (size_t)(e & 1) * pr::kP2PMaxRanks * kP2PCountsSlot;
-    pr::launch_p2p_allreduce_i32(c->p2p_view, dc, n, base, kP2PCountsSlot, p2p_flag_off(P2P_COUNTS), e, dc, c->d_p2p_aux.p + 4, c->stream);
+    pr::launch_p2p_allreduce_i32(c->p2p_view, dc, n, kP2POffCounts, pr::kP2PMaxRanks * kP2PCountsSlot, kP2PCountsSlot, p2p_flag_off(P2P_COUNTS),
+                                 c->d_p2p_epoch.p + P2P_COUNTS, dc, c->d_p2p_aux.p + 4, c->stream, st);
     return PR_OK;
   }
   PR_NCCL(g_nccl.AllReduce(dc, dc, n, ncclInt32, ncclSum, c->comm, c->stream));
@@ -668,13 +681,12 @@ int exchange_counts(plane_ransac_ctx* c, int32_t* dc, size_t n) {
 }
 
 // the 16 integer moments of d_refit summed over ranks, in place (the pivot behind them is identical everywhere).
-int exchange_refit(plane_ransac_ctx* c) {
+int exchange_refit(plane_ransac_ctx* c, const pr::RoundState* st = nullptr) {
   if (!c->comm) return PR_OK;
   if (c->p2p_on) {
-    const unsigned long long e = ++c->p2p_epoch[P2P_REFIT];
-    const size_t base = kP2POffRefit + (size_t)(e & 1) * pr::kP2PMaxRanks * kP2PRefitSlot;
     long long* m = reinterpret_cast<long long*>(c->d_refit.p);
-    pr::launch_p2p_allreduce_i64(c->p2p_view, m, 16, base, kP2PRefitSlot, p2p_flag_off(P2P_REFIT), e, m, c->d_p2p_aux.p + 4, c->stream);
+    pr::launch_p2p_allreduce_i64(c->p2p_view, m, 16, kP2POffRefit, pr::kP2PMaxRanks * kP2PRefitSlot, kP2PRefitSlot, p2p_flag_off(P2P_REFIT),
+                                 c->d_p2p_epoch.p + P2P_REFIT, m, c->d_p2p_aux.p + 4, c->stream, st);
     return PR_OK;
   }
   PR_NCCL(g_nccl.AllReduce(c->d_refit.p, c->d_refit.p, 16, ncclInt64, ncclSum, c->comm, c->stream));
@@ -682,23 +694,29 @@ int exchange_refit(plane_ransac_ctx* c) {
 }
 
 // all-gather of (remaining, inliers): d_totals[0..2) of every rank -> d_totals[2 + 2r ..).
-int exchange_totals(plane_ransac_ctx* c) {
+int exchange_totals(plane_ransac_ctx* c, const pr::RoundState* st = nullptr) {
   if (!c->comm) return PR_OK;
   if (c->p2p_on) {
-    const unsigned long long e = ++c->p2p_epoch[P2P_TOTALS];
-    const size_t base = kP2POffTotals + (size_t)(e & 1) * pr::kP2PMaxRanks * kP2PTotalsSlot;
-    pr::launch_p2p_allgather_i64(c->p2p_view, c->d_totals.p, 2, base, kP2PTotalsSlot, p2p_flag_off(P2P_TOTALS), e, c->d_totals.p + 2,
-                                 c->d_p2p_aux.p + 4, c->stream);
+    pr::launch_p2p_allgather_i64(c->p2p_view, c->d_totals.p, 2, kP2POffTotals, pr::kP2PMaxRanks * kP2PTotalsSlot, kP2PTotalsSlot,
+                                 p2p_flag_off(P2P_TOTALS), c->d_p2p_epoch.p + P2P_TOTALS, c->d_totals.p + 2, c->d_p2p_aux.p + 4, c->stream, st);
     return PR_OK;
   }
   PR_NCCL(g_nccl.AllGather(c->d_totals.p, c->d_totals.p + 2, 2, ncclInt64, c->comm, c->stream));
   return PR_OK;
 }
 
-void p2p_teardown(plane_ransac_ctx* c) {
+// collective: every rank of the communicator is in this call (destroy of a context whose mailboxes are mapped, or the
+// agreed failure of p2p_setup)
+void p2p_teardown(plane_ransac_ctx* c, bool collective) {
   for (int r = 0; r < pr::kP2PMaxRanks; ++r) {
     if (c->p2p_view.peers[r] && r != c->rank) cudaIpcCloseMemHandle(c->p2p_view.peers[r]);
     c->p2p_view.peers[r] = nullptr;
+  }
+  // no rank frees its mailbox while a peer may still have it mapped: every rank closes its mappings first, then all
+  // meet in one NCCL all-reduce (skipped when an exchange had timed out: the peers cannot be relied on any more)
+  if (collective && c->comm && c->n_ranks > 1 && !c->comm_failed && c->d_totals.p && g_nccl.AllReduce) {
+    if (g_nccl.AllReduce(c->d_totals.p, c->d_totals.p, 1, ncclInt64, ncclSum, c->comm, c->stream) == ncclSuccess)
+      cudaStreamSynchronize(c->stream);
   }
   if (c->p2p_mailbox) cudaFree(c->p2p_mailbox);
   c->p2p_mailbox = nullptr;
@@ -708,8 +726,27 @@ void p2p_teardown(plane_ransac_ctx* c) {
 
 // After a stream synchronisation: did a consumer give up waiting for a peer?
 int p2p_check(plane_ransac_ctx* c) {
-  if (c->p2p_on && c->h_p2p_err.p && *c->h_p2p_err.p) return fail(PR_ERR_COMM, "a peer rank did not deliver its part of an exchange within ~20 s");
+  if (c->p2p_on && c->h_p2p_err.p && *c->h_p2p_err.p) {
+    // the ranks are out of step from here on (the late peer's epochs no longer match): every later collective call
+    // on this context fails at once instead of waiting 20 s again or consuming unreduced data
+    c->comm_failed = true;
+    *c->h_p2p_err.p = 0;
+    cudaMemsetAsync(c->d_p2p_aux.p + 4, 0, sizeof(unsigned), c->stream);
+    return fail(PR_ERR_COMM, "a peer rank did not deliver its part of an exchange within ~20 s; the communicator is unusable");
+  }
   return PR_OK;
+}
+
+int check_comm(plane_ransac_ctx* c) {
+  if (c->comm && c->comm_failed) return fail(PR_ERR_COMM, "an earlier exchange timed out; destroy this context and create the communicator again");
+  return PR_OK;
+}
+
+// Bytes one peel launch moves (what the HBM roofline of K5 is computed from): the coordinate planes of the source, its
+// original-index plane when it has one (the staged cloud has none: the index is the position), the remaining cloud
+// with its index plane, and 4 B per inlier for each list written.
+long long compact_bytes(const pr::CloudView& src, size_t n, bool write_remaining, long long n_rem, long long n_inl, bool cur, bool orig) {
+  return (src.orig ? 16ll : 12ll) * (long long)n + (write_remaining ? 16ll * n_rem : 0) + ((cur ? 4ll : 0) + (orig ? 4ll : 0)) * n_inl;
 }
 
 struct SegmentOut {
@@ -728,6 +765,7 @@ int segment_core(plane_ransac_ctx* c, const pr_params* prm, pr::CloudView src, s
                  const pr::CloudView* sdst = nullptr) {
   // ssrc: Morton-sorted copy of src (hierarchical scorer); sdst receives its peeled remainder
   HostTimer whole(&c->prof.host_ms_total);
+  PR_TRY(check_comm(c));
   pr_segment_info inf;
   std::memset(&inf, 0, sizeof(inf));
   inf.n_cloud = n_global;
@@ -818,7 +856,11 @@ int segment_core(plane_ransac_ctx* c, const pr_params* prm, pr::CloudView src, s
       // with the hierarchical scorer)
       // takes the device as long as drawing the rest takes the host (~0.08 us per draw); fewer, larger
       // launches score more efficiently and, when sharded, need fewer collectives.
-      const double dev_s_per_hyp = (double)std::max<size_t>(n_local, 1) / (hier ? 2.0e13 : 6.5e12), host_s_per_draw = 8e-8;
+      // Sized from quantities every rank agrees on (the global size and the requested scorer, never the local shard
+      // size): each sub-batch issues collectives, so all ranks must cut the batch identically however unevenly the
+      // peeled planes leave the shards.
+      const double pts_per_rank = (double)std::max<long long>(n_global / std::max(1, c->n_ranks), 1);
+      const double dev_s_per_hyp = pts_per_rank / (ssrc != nullptr ? 2.0e13 : 6.5e12), host_s_per_draw = 8e-8;
       long long first_sb = 256;
       while (first_sb < B && (double)first_sb < (double)B * host_s_per_draw / (dev_s_per_hyp + host_s_per_draw)) first_sb *= 2;
       while (first_sb * 4 < B) first_sb *= 2;  // launches below a quarter of the batch score a few per cent less efficiently
@@ -865,7 +907,9 @@ int segment_core(plane_ransac_ctx* c, const pr_params* prm, pr::CloudView src, s
       PR_CUDA(cudaGetLastError());
       PR_CUDA(cudaMemcpyAsync(c->h_counts.p + total_draws, dc, B * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
       PR_CUDA(cudaMemcpyAsync(c->h_good.p + total_draws, dg, B * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+      if (c->p2p_on) PR_CUDA(cudaMemcpyAsync(c->h_p2p_err.p, c->d_p2p_aux.p + 4, sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
       PR_TRY(sync_stream(c));
+      PR_TRY(p2p_check(c));  // a timed-out exchange left unreduced counts: stop before anything consumes them
       if (c->pend.active) {  // the whole cloud is staged now: bounding box -> refit grid
         PR_TRY(finalize_pending(c));
         inf.scale_exp = c->scale_exp;
@@ -954,11 +998,229 @@ int segment_core(plane_ransac_ctx* c, const pr_params* prm, pr::CloudView src, s
       out->n_inl_global += c->h_totals.p[2 + 2 * r + 1];
     }
   }
-  c->prof.bytes_compact += 16ll * (long long)n_local + (write_remaining ? 16ll * out->n_rem_local : 0) +
-                           ((d_inl_cur ? 4ll : 0) + (d_inl_orig ? 4ll : 0)) * out->n_inl_local;
+  c->prof.bytes_compact += compact_bytes(src, n_local, write_remaining, out->n_rem_local, out->n_inl_local, d_inl_cur != nullptr, d_inl_orig != nullptr);
   std::memcpy(out->coeff, refined, sizeof(refined));
   inf.n_inliers = (int)out->n_inl_global;
   if (info) *info = inf;
+  return PR_OK;
+}
+
+// Where the peel loop stands: shared by the rounds the device runs on its own (run_chain) and the host-driven ones.
+struct PeelCursor {
+  int planes = 0;        // planes accepted so far
+  pr::CloudView src;     // cloud of the next round
+  size_t n_local = 0;
+  long long n_global = 0, first = 0;
+  size_t off = 0;        // inlier-list entries written so far (this rank)
+  int s_cur = 0;         // hierarchical scorer: which sorted copy matches src
+};
+
+// The caller's index lists: each plane's segment is copied as soon as its round is complete when the destination is
+// pinned.  A destination that turns out too small never interrupts the peel (when sharded every rank has to finish the
+// round's collectives): the copies stop and the call reports PR_ERR_CAPACITY once the device state is consistent.
+struct ListCopier {
+  int32_t* cur = nullptr;
+  int32_t* orig = nullptr;
+  size_t cap = 0;
+  bool overlap = false, overflow = false;
+  size_t needed = 0;
+  bool wanted() const { return cur || orig; }
+  int on_plane(plane_ransac_ctx* c, size_t begin, size_t end, cudaEvent_t ready) {
+    if (!wanted()) return PR_OK;
+    if (end > cap) {
+      overflow = true;
+      needed = end;
+      return PR_OK;
+    }
+    if (!overlap || overflow || end == begin) return PR_OK;
+    if (ready) PR_CUDA(cudaStreamWaitEvent(c->copy_stream, ready, 0));
+    if (cur) PR_CUDA(cudaMemcpyAsync(cur + begin, c->d_inl_cur.p + begin, (end - begin) * sizeof(int32_t), cudaMemcpyDeviceToHost, c->copy_stream));
+    if (orig) PR_CUDA(cudaMemcpyAsync(orig + begin, c->d_inl_orig.p + begin, (end - begin) * sizeof(int32_t), cudaMemcpyDeviceToHost, c->copy_stream));
+    return PR_OK;
+  }
+};
+
+// ---- the peel loop without the host ----------------------------------------------------------------------------------
+// Score-all mode (probability 1: PCL scores max_iterations + 1 samples per round whatever the counts are) with the
+// brute-force scorer: nothing the host decides depends on device results, so whole rounds are queued ahead —
+// draws, models, scores, computeModel's decision, refit, closed-form plane, peel and the stop rule all run as kernels
+// driven by a RoundState in HBM (pr_chain.cu) — and the host only reads each round's record as it completes (to return
+// the index lists under the following rounds and to stop queueing once the loop has ended).  Rounds that need PCL's
+// redraw rule (a degenerate sample) or whose sampler has too many colliding picks are handed back to the host-driven
+// loop (segment_core), which gives the same result.
+constexpr int kChainMaxHyps = 16384;  // one exchange kernel per quantity (kP2PMaxHyps), one block-wide decision kernel
+constexpr int kChainLookahead = 3;    // rounds queued beyond the last one whose record was read
+
+bool chain_eligible(const plane_ransac_ctx* c, const pr_params* prm, long long n_global) {
+  static const bool enabled = [] { const char* e = getenv("PR_CHAIN"); return !(e && atoi(e) == 0); }();
+  if (!enabled || c->round_loop == PR_LOOP_HOST || c->pend.active) return false;
+  if (!(prm->probability >= 1.0) || prm->scorer != PR_SCORER_BRUTE) return false;
+  if (prm->max_iterations < 1 || (long long)prm->max_iterations + 1 > kChainMaxHyps) return false;
+  if (c->comm && !c->p2p_on) return false;
+  // about (3K)^2 / N of a round's picks collide; beyond what the device replays the round would come straight back
+  const double k = (double)prm->max_iterations + 1.0;
+  if (n_global < 3 || 9.0 * k * k / (double)n_global > 0.75 * pr::kDrawMaxCollisions) return false;
+  return true;
+}
+
+int run_chain(plane_ransac_ctx* c, const pr_params* prm, PeelCursor& cur, float* coeffs, size_t* plane_offsets, pr_segment_info* infos,
+              ListCopier& lists, bool* stopped, bool* handed_back) {
+  HostTimer whole(&c->prof.host_ms_total);
+  const int K = prm->max_iterations + 1;
+  const float t = pr::threshold_up(prm->distance_threshold);
+  const int max_rounds = prm->max_planes - cur.planes;
+  const int planes_at_start = cur.planes;
+  PR_TRY(reserve_draws(c, (size_t)K, false));
+  PR_TRY(reserve_small(c));
+  PR_TRY(dev_reserve(c->d_state, 1));
+  PR_TRY(pin_reserve(c->h_state, 1));
+  PR_TRY(dev_reserve(c->d_recs, (size_t)max_rounds));
+  PR_TRY(pin_reserve(c->h_recs, (size_t)max_rounds));
+  while ((int)c->round_ev.size() < max_rounds) {
+    cudaEvent_t e = nullptr;
+    PR_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    c->round_ev.push_back(e);
+  }
+  const size_t slots = pr::draw_table_slots(K);
+  PR_TRY(dev_reserve(c->d_draw_table, slots));
+  PR_TRY(dev_reserve(c->d_draw_coll, (size_t)pr::kDrawCollCap + 4));
+  PR_TRY(dev_reserve(c->d_scratch, pr::compact_scratch_bytes(cur.n_local) + 64));
+  if (!c->d_rnd.p || c->rnd_seed != prm->seed || c->rnd_count < 3 * (size_t)K) {
+    // the stream does not depend on the cloud: generated once per seed, staged through the (pinned) triple buffer
+    PR_TRY(dev_reserve(c->d_rnd, 3 * (size_t)K));
+    pr::fill_rnd_stream(prm->seed, 3 * (size_t)K, reinterpret_cast<uint32_t*>(c->h_triples.p));
+    PR_CUDA(cudaMemcpyAsync(c->d_rnd.p, c->h_triples.p, 3 * (size_t)K * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+    PR_CUDA(cudaStreamSynchronize(c->stream));
+    c->rnd_seed = prm->seed;
+    c->rnd_count = 3 * (size_t)K;
+  }
+  pr::RoundState* rs = c->d_state.p;
+  {
+    pr::RoundState h;
+    std::memset(&h, 0, sizeof(h));
+    h.n_local = (long long)cur.n_local;
+    h.n_global = cur.n_global;
+    h.first = cur.first;
+    h.inl_off = (long long)cur.off;
+    h.round = cur.planes;
+    h.best = -1;
+    *c->h_state.p = h;
+    PR_CUDA(cudaMemcpyAsync(rs, c->h_state.p, sizeof(h), cudaMemcpyHostToDevice, c->stream));
+    PR_CUDA(cudaMemsetAsync(c->d_recs.p, 0, (size_t)max_rounds * sizeof(pr::RoundRecord), c->stream));
+  }
+  size_t n_bound = cur.n_local;  // upper bound of this rank's cloud for the rounds queued from here on
+  int launched = 0, consumed = 0;
+  bool stop_seen = false;
+  std::vector<pr::CloudView> dst_of((size_t)max_rounds);
+  while (consumed < launched || (!stop_seen && launched < max_rounds)) {
+    while (!stop_seen && launched < max_rounds && launched < consumed + kChainLookahead) {
+      const int r = launched, round_index = planes_at_start + r;
+      const pr::CloudView src = r == 0 ? cur.src : c->work[(round_index - 1) & 1];
+      const pr::CloudView dst = c->work[round_index & 1];
+      dst_of[r] = dst;
+      pr::RoundRecord* rec = c->d_recs.p + r;
+      {
+        Span sp(c, KC_MODELS, 4);
+        pr::launch_draw(c->d_rnd.p, K, rs, c->d_triples.p, c->d_draw_table.p, slots, c->d_draw_coll.p, c->d_draw_coll.p + pr::kDrawCollCap, rec, c->stream);
+        PR_TRY(exchange_samples(c, src, 0, 0, c->d_triples.p, 3 * K, c->d_sample_pts.p, rs));
+        pr::launch_models(c->d_sample_pts.p, K, c->d_hyps.p, c->d_good.p, c->stream);
+      }
+      PR_CUDA(cudaMemsetAsync(c->d_counts.p, 0, (size_t)K * sizeof(int32_t), c->stream));
+      {
+        Span sp(c, KC_SCORE, 0);
+        c->prof.launches_score += pr::launch_score(src, n_bound, 1, 0, c->d_hyps.p, K, t, prm->dot_order, c->d_counts.p, c->num_sms, c->stream, rs);
+      }
+      PR_TRY(exchange_counts(c, c->d_counts.p, (size_t)K, rs));
+      {
+        Span sp(c, KC_OTHER, 1);
+        pr::launch_replay(c->d_counts.p, c->d_good.p, K, rs, rec, c->stream);
+      }
+      if (prm->optimize_coefficients) {
+        PR_CUDA(cudaMemsetAsync(c->d_refit.p, 0, sizeof(pr::RefitOut), c->stream));
+        {
+          Span sp(c, KC_REFIT, 1);
+          pr::launch_refit(src, n_bound, c->d_hyps.p, c->d_sample_pts.p, 0, t, prm->dot_order, c->scale_exp, c->d_refit.p, c->num_sms, c->stream, rs);
+        }
+        PR_TRY(exchange_refit(c, rs));
+      }
+      {
+        Span sp(c, KC_OTHER, 1);
+        pr::launch_finish(rs, c->d_hyps.p, c->d_triples.p, c->d_refit.p, prm->optimize_coefficients ? 1 : 0, c->scale_exp, K, rec, c->stream);
+      }
+      {
+        Span sp(c, KC_COMPACT, 1);
+        const pr::Plane4 none = {0, 0, 0, 0};
+        pr::launch_compact(src, n_bound, none, t, prm->dot_order, dst, true, c->d_inl_cur.p, c->d_inl_orig.p, c->d_scratch.p, c->d_totals.p,
+                           c->stream, nullptr, rs);
+      }
+      PR_TRY(exchange_totals(c, rs));
+      {
+        Span sp(c, KC_OTHER, 1);
+        pr::launch_advance(rs, c->d_totals.p, c->n_ranks, c->rank, prm->min_plane_size, rec, c->stream);
+      }
+      PR_CUDA(cudaGetLastError());
+      PR_CUDA(cudaMemcpyAsync(c->h_recs.p + r, rec, sizeof(pr::RoundRecord), cudaMemcpyDeviceToHost, c->stream));
+      PR_CUDA(cudaEventRecord(c->round_ev[r], c->stream));
+      ++launched;
+    }
+    {
+      HostTimer ht(&c->prof.host_ms_wait);
+      PR_CUDA(cudaEventSynchronize(c->round_ev[consumed]));
+    }
+    const pr::RoundRecord rec = c->h_recs.p[consumed];
+    const int r = consumed++;
+    if (stop_seen || !rec.ran) {  // queued behind the end of the loop: nothing ran
+      stop_seen = true;
+      continue;
+    }
+    if (rec.stop == 2) {  // the round goes back to the host-driven loop; the state is that of its start
+      stop_seen = true;
+      *handed_back = true;
+      continue;
+    }
+    pr_segment_info inf;
+    std::memset(&inf, 0, sizeof(inf));
+    inf.n_cloud = rec.n_cloud;
+    inf.scale_exp = c->scale_exp;
+    inf.ok = rec.ok;
+    if (rec.ok) {
+      inf.n_scored = inf.iterations = inf.draws = rec.n_draws;
+      inf.best_count = inf.n_inliers_raw = rec.best_count;
+      for (int i = 0; i < 3; ++i) inf.best_sample[i] = rec.best_sample[i];
+      std::memcpy(inf.raw_coeff, rec.raw, sizeof(rec.raw));
+      inf.n_inliers = (int)rec.n_inl_global;
+      const pr::CloudView src = r == 0 ? cur.src : dst_of[r - 1];
+      c->prof.pairs_scored += rec.n_local * (long long)K;
+      if (prm->optimize_coefficients) {
+        c->prof.points_refit += rec.n_local;
+        c->prof.bytes_refit += 12ll * rec.n_local;
+      }
+      c->prof.points_compact += rec.n_local;
+      c->prof.bytes_compact += compact_bytes(src, (size_t)rec.n_local, true, rec.n_rem_local, rec.n_inl_local, true, true);
+    }
+    if (infos) infos[cur.planes] = inf;
+    if (!rec.accepted) {
+      stop_seen = true;
+      *stopped = true;
+      continue;
+    }
+    std::memcpy(coeffs + 4 * cur.planes, rec.refined, 4 * sizeof(float));
+    const size_t begin = (size_t)rec.inl_off;
+    cur.off = begin + (size_t)rec.n_inl_local;
+    plane_offsets[cur.planes + 1] = cur.off;
+    ++cur.planes;
+    PR_TRY(lists.on_plane(c, begin, cur.off, c->round_ev[r]));
+    cur.src = dst_of[r];
+    cur.n_local = (size_t)rec.n_rem_local;
+    cur.n_global = rec.n_rem_global;
+    cur.first = c->comm ? rec.first_after : 0;
+    n_bound = cur.n_local;
+  }
+  if (c->p2p_on) {
+    PR_CUDA(cudaMemcpyAsync(c->h_p2p_err.p, c->d_p2p_aux.p + 4, sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
+    PR_TRY(sync_stream(c));
+    PR_TRY(p2p_check(c));
+  }
   return PR_OK;
 }
 
@@ -1078,10 +1340,14 @@ int p2p_setup(plane_ransac_ctx* c) {
       for (int r = 0; r < c->n_ranks; ++r) ok = ok && h[rec * (size_t)(r + 1) + 64];
   }
   dev_free(d_h);
+  if (!ok) p2p_teardown(c, rc == PR_OK);
   if (rc != PR_OK) ok = 0;
-  if (!ok) p2p_teardown(c);
   c->p2p_on = ok != 0;
-  for (auto& e : c->p2p_epoch) e = 0;
+  if (rc == PR_OK) {
+    PR_TRY(dev_reserve(c->d_p2p_epoch, 4));
+    PR_CUDA(cudaMemsetAsync(c->d_p2p_epoch.p, 0, 4 * sizeof(unsigned long long), c->stream));
+    PR_CUDA(cudaStreamSynchronize(c->stream));
+  }
   return rc;
 }
 
@@ -1146,9 +1412,13 @@ void plane_ransac_destroy(plane_ransac_ctx* c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   collect_spans(c);
-  p2p_teardown(c);
+  p2p_teardown(c, c->p2p_on);
   dev_free(c->d_p2p_aux);
+  dev_free(c->d_p2p_epoch);
   pin_free(c->h_p2p_err);
+  dev_free(c->d_state); pin_free(c->h_state); dev_free(c->d_recs); pin_free(c->h_recs);
+  dev_free(c->d_rnd); dev_free(c->d_draw_table); dev_free(c->d_draw_coll);
+  for (cudaEvent_t e : c->round_ev) cudaEventDestroy(e);
   if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
   dev_free(c->staged_mem);
   for (int i = 0; i < 2; ++i) { dev_free(c->work_mem[i]); dev_free(c->work_orig[i]); }
@@ -1375,21 +1645,24 @@ int plane_ransac_extract_planes(plane_ransac_ctx* c, const pr_params* prm, float
   PR_TRY(check_ctx(c, true));
   if (c->profiling) collect_spans(c);  // stream is idle here: fold finished spans, recycle their events
   PR_TRY(check_params(prm));
+  PR_TRY(check_comm(c));
   if (!c->have_cloud) return fail(PR_ERR_NO_CLOUD, "no cloud staged");
   if (!coeffs || !plane_offsets || !n_planes) return fail(PR_ERR_INVALID, "null output");
   PR_TRY(reserve_work(c));
   const bool hier = prm->scorer == PR_SCORER_HIER;
   if (hier) PR_TRY(ensure_staged(c));
   if (hier) PR_TRY(ensure_sorted(c, 3));
-  int s_cur = 0;  // index of the sorted copy that matches src
-  pr::CloudView src = c->staged;
-  size_t n_local = c->n_staged;
-  long long n_global = c->n_global_staged, first = c->first_staged;
-  int planes = 0;
-  size_t off = 0;
+  PeelCursor cur;
+  cur.src = c->staged;
+  cur.n_local = c->n_staged;
+  cur.n_global = c->n_global_staged;
+  cur.first = c->first_staged;
   plane_offsets[0] = 0;
   *n_planes = 0;
-  const bool want_lists = inlier_cur || inlier_orig;
+  ListCopier lists;
+  lists.cur = inlier_cur;
+  lists.orig = inlier_orig;
+  lists.cap = idx_cap;
   // Pinned destination buffers: each plane's index lists go back on the copy stream as soon as its round is done,
   // under the scoring of the following rounds (a pageable destination would make the copy block the host instead).
   auto is_pinned = [](const void* p) {
@@ -1398,60 +1671,91 @@ int plane_ransac_extract_planes(plane_ransac_ctx* c, const pr_params* prm, float
     if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
     return a.type == cudaMemoryTypeHost;
   };
-  const bool overlap_copy = want_lists && is_pinned(inlier_cur) && is_pinned(inlier_orig);
-  size_t copied = 0;
-  while (planes < prm->max_planes) {
-    pr::CloudView dst = c->work[planes & 1];
+  lists.overlap = lists.wanted() && is_pinned(inlier_cur) && is_pinned(inlier_orig);
+  // Any failure below leaves the context on the staged cloud (work[0] / work[1] may hold a half-finished round) with
+  // no copy still in flight towards the caller's buffers.
+  auto bail = [&](int rc) {
+    cudaStreamSynchronize(c->copy_stream);
+    cudaStreamSynchronize(c->stream);
+    c->current = c->staged;
+    c->n_current = c->n_staged;
+    c->n_global_current = c->n_global_staged;
+    c->first_current = c->first_staged;
+    c->last_offsets.clear();
+    c->last_coeffs.clear();
+    return rc;
+  };
+  int handed_back = 0;
+  bool finished = false;
+  while (!finished && cur.planes < prm->max_planes) {
+    if (chain_eligible(c, prm, cur.n_global) && handed_back < 2) {
+      bool stopped = false, back = false;
+      const int rc = run_chain(c, prm, cur, coeffs, plane_offsets, infos, lists, &stopped, &back);
+      if (rc != PR_OK) return bail(rc);
+      if (stopped) break;
+      if (!back) continue;  // every queued round was accepted: the loop condition ends the call
+      ++handed_back;        // the round in flight needs the host (crowded sampler or a bad sample): one host-driven round
+    }
+    pr::CloudView dst = c->work[cur.planes & 1];
     SegmentOut so;
     pr_segment_info inf;
-    const int s_next = 1 + (planes & 1);
-    PR_TRY(segment_core(c, prm, src, n_local, n_global, first, true, dst, c->d_inl_cur.p + off, c->d_inl_orig.p + off,
-                        &inf, &so, hier ? &c->sorted_view[s_cur] : nullptr, hier ? &c->sorted_view[s_next] : nullptr));
-    if (infos) infos[planes] = inf;
+    const int s_next = 1 + (cur.planes & 1);
+    const int rc = segment_core(c, prm, cur.src, cur.n_local, cur.n_global, cur.first, true, dst, c->d_inl_cur.p + cur.off,
+                                c->d_inl_orig.p + cur.off, &inf, &so, hier ? &c->sorted_view[cur.s_cur] : nullptr,
+                                hier ? &c->sorted_view[s_next] : nullptr);
+    if (rc != PR_OK) return bail(rc);
+    if (infos) infos[cur.planes] = inf;
     const long long m = so.n_inl_global;
     if (m == 0 || m < (long long)std::max(0, prm->min_plane_size)) break;
-    if (want_lists && off + (size_t)so.n_inl_local > idx_cap)
-      return fail(PR_ERR_CAPACITY, "inlier index buffers hold %zu entries, need at least %zu", idx_cap, off + (size_t)so.n_inl_local);
-    std::memcpy(coeffs + 4 * planes, so.coeff, 4 * sizeof(float));
-    off += (size_t)so.n_inl_local;
-    plane_offsets[planes + 1] = off;
-    ++planes;
-    if (overlap_copy && off > copied) {  // segment_core ended with a stream synchronisation: the lists are complete
-      if (inlier_cur) PR_CUDA(cudaMemcpyAsync(inlier_cur + copied, c->d_inl_cur.p + copied, (off - copied) * sizeof(int32_t), cudaMemcpyDeviceToHost, c->copy_stream));
-      if (inlier_orig) PR_CUDA(cudaMemcpyAsync(inlier_orig + copied, c->d_inl_orig.p + copied, (off - copied) * sizeof(int32_t), cudaMemcpyDeviceToHost, c->copy_stream));
-      copied = off;
-    }
-    src = dst;
-    s_cur = s_next;
-    n_local = (size_t)so.n_rem_local;
+    std::memcpy(coeffs + 4 * cur.planes, so.coeff, 4 * sizeof(float));
+    const size_t begin = cur.off;
+    cur.off += (size_t)so.n_inl_local;
+    plane_offsets[cur.planes + 1] = cur.off;
+    ++cur.planes;
+    // segment_core ended with a stream synchronisation: the lists are complete
+    { const int rc2 = lists.on_plane(c, begin, cur.off, nullptr); if (rc2 != PR_OK) return bail(rc2); }
+    cur.src = dst;
+    cur.s_cur = s_next;
+    cur.n_local = (size_t)so.n_rem_local;
     if (c->comm) {
       long long tot = 0, f = 0;
       for (int r = 0; r < c->n_ranks; ++r) {
         if (r == c->rank) f = tot;
         tot += so.rem_per_rank[r];
       }
-      n_global = tot;
-      first = f;
+      cur.n_global = tot;
+      cur.first = f;
     } else {
-      n_global = (long long)n_local;
-      first = 0;
+      cur.n_global = (long long)cur.n_local;
+      cur.first = 0;
     }
   }
-  if (c->pend.active) PR_TRY(ensure_staged(c));
-  *n_planes = planes;
-  c->last_offsets.assign(plane_offsets, plane_offsets + planes + 1);
-  c->last_coeffs.assign(coeffs, coeffs + 4 * (size_t)planes);
-  c->current = src;
-  c->n_current = n_local;
-  c->n_global_current = n_global;
-  c->first_current = first;
-  if (overlap_copy) {
+  if (c->pend.active) { const int rc = ensure_staged(c); if (rc != PR_OK) return bail(rc); }
+  *n_planes = cur.planes;
+  c->last_offsets.assign(plane_offsets, plane_offsets + cur.planes + 1);
+  c->last_coeffs.assign(coeffs, coeffs + 4 * (size_t)cur.planes);
+  c->current = cur.src;
+  c->n_current = cur.n_local;
+  c->n_global_current = cur.n_global;
+  c->first_current = cur.first;
+  if (lists.overlap) {
     PR_CUDA(cudaStreamSynchronize(c->copy_stream));
-  } else {
-    if (off && inlier_cur) PR_CUDA(cudaMemcpyAsync(inlier_cur, c->d_inl_cur.p, off * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
-    if (off && inlier_orig) PR_CUDA(cudaMemcpyAsync(inlier_orig, c->d_inl_orig.p, off * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+  } else if (!lists.overflow) {
+    if (cur.off && inlier_cur) PR_CUDA(cudaMemcpyAsync(inlier_cur, c->d_inl_cur.p, cur.off * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    if (cur.off && inlier_orig) PR_CUDA(cudaMemcpyAsync(inlier_orig, c->d_inl_orig.p, cur.off * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
   }
   PR_TRY(sync_stream(c));
+  // The peel itself is complete and consistent (every rank ran every collective); only the caller's index buffers were
+  // too small: coefficients, offsets and plane_ransac_remaining / plane_points are valid, the lists are not.
+  if (lists.overflow)
+    return fail(PR_ERR_CAPACITY, "inlier index buffers hold %zu entries, need at least %zu", idx_cap, lists.needed);
+  return PR_OK;
+}
+
+int plane_ransac_set_round_loop(plane_ransac_ctx* c, int mode) {
+  if (!c) return fail(PR_ERR_INVALID, "null context");
+  if (mode != PR_LOOP_AUTO && mode != PR_LOOP_HOST) return fail(PR_ERR_INVALID, "unknown round-loop mode");
+  c->round_loop = mode;
   return PR_OK;
 }
 
@@ -1555,6 +1859,7 @@ int plane_ransac_cluster_filter(plane_ransac_ctx* c, double radius, int max_smal
   }
   PR_CUDA(cudaGetLastError());
   pr::CloudView dst = (c->current.x == c->work[0].x) ? c->work[1] : c->work[0];
+  const pr::CloudView src_before = c->current;
   PR_TRY(dev_reserve(c->d_scratch, pr::compact_scratch_bytes(n) + 64));
   {
     Span sp(c, KC_COMPACT, 1);
@@ -1569,7 +1874,7 @@ int plane_ransac_cluster_filter(plane_ransac_ctx* c, double radius, int max_smal
   c->n_current = (size_t)c->h_totals.p[0];
   c->n_global_current = (long long)c->n_current;
   c->first_current = 0;
-  c->prof.bytes_compact += 20ll * (long long)n + 16ll * (long long)c->n_current;
+  c->prof.bytes_compact += 4ll * (long long)n + compact_bytes(src_before, n, true, (long long)c->n_current, 0, false, false);
   if (n_removed) *n_removed = (size_t)c->h_totals.p[1];
   if (n_remaining) *n_remaining = c->n_current;
   return PR_OK;
@@ -1728,9 +2033,9 @@ int plane_ransac_reabsorb(plane_ransac_ctx* c, const float* coeffs, const pr_poi
   if (c->comm) PR_NCCL(g_nccl.AllGather(c->d_totals.p, c->d_totals.p + 2, 2, ncclInt64, c->comm, c->stream));
   PR_CUDA(cudaMemcpyAsync(c->h_totals.p, c->d_totals.p, (2 + (c->comm ? 2 * c->n_ranks : 0)) * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
   PR_TRY(sync_stream(c));
+  c->prof.bytes_compact += 4ll * (long long)n + compact_bytes(c->current, n, true, c->h_totals.p[0], 0, false, false);
   c->current = dst;
   c->n_current = (size_t)c->h_totals.p[0];
-  c->prof.bytes_compact += 20ll * (long long)n + 16ll * (long long)c->n_current;
   if (c->comm) {
     long long tot = 0, f = 0;
     for (int r = 0; r < c->n_ranks; ++r) {

@@ -24,6 +24,8 @@ constexpr uint32_t kDrawNoOp = 0xFFFFFFFFu;
 constexpr uint64_t kDrawEmptySlot = ~0ull;
 // Collected ops the sequential replay accepts (more: the round falls back to the host sampler).
 constexpr int kDrawMaxCollisions = 2048;
+// Capacity of the collected list (an op can be listed more than once).
+constexpr int kDrawCollCap = 3072;
 
 PR_HD uint32_t draw_position(uint32_t s, uint32_t rnd, uint32_t n_points) {
   const uint32_t a = s % 3u;

@@ -177,7 +177,7 @@ bool draw_triples_parallel(size_t n_points, uint32_t seed, int n_draws, int32_t*
   size_t cap = 1024;
   while (cap < 4 * n_ops) cap <<= 1;
   std::vector<unsigned long long> table(cap, kDrawEmptySlot);
-  std::vector<uint32_t> coll(2 * kDrawMaxCollisions);
+  std::vector<uint32_t> coll(kDrawCollCap);
   uint32_t n_coll = 0;
   // the device runs the ops in any order: emulate the reverse one, so that the op that owns a table slot is never
   // the earliest op of its position

@@ -319,7 +319,12 @@ __global__ void __launch_bounds__(256) gather_samples_kernel(const float* __rest
                                                              const float* __restrict__ z, long long first, size_t n,
                                                              const int32_t* __restrict__ triples, int n_samples,
                                                              int4* __restrict__ out, int n_clouds, size_t cloud_stride,
-                                                             bool per_cloud_triples) {
+                                                             bool per_cloud_triples, const RoundState* __restrict__ st) {
+  if (st != nullptr) {  // peel loop without the host: this round's shard extent lives on the device
+    if (st->stop) return;
+    first = st->first;
+    n = (size_t)st->n_local;
+  }
   const long long total = (long long)n_samples * n_clouds;
   for (long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x; s < total; s += (long long)gridDim.x * blockDim.x) {
     int c = (int)(s / n_samples);
@@ -366,13 +371,14 @@ __global__ void __launch_bounds__(128) models_kernel(const int4* __restrict__ sa
 }
 
 void launch_gather_samples(CloudView cloud, long long first, size_t n, const int32_t* triples, int n_samples,
-                           int4* sample_pts, int n_clouds, size_t cloud_stride, cudaStream_t s, bool per_cloud_triples) {
+                           int4* sample_pts, int n_clouds, size_t cloud_stride, cudaStream_t s, bool per_cloud_triples,
+                           const RoundState* st) {
   long long total = (long long)n_samples * n_clouds;
   if (total <= 0) return;
   long long blocks = (total + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
   gather_samples_kernel<<<(unsigned)blocks, 256, 0, s>>>(cloud.x, cloud.y, cloud.z, first, n, triples, n_samples,
-                                                         sample_pts, n_clouds, cloud_stride, per_cloud_triples);
+                                                         sample_pts, n_clouds, cloud_stride, per_cloud_triples, st);
 }
 
 void launch_models(const int4* sample_pts, int n_models_total, float4* hyps, int32_t* good, cudaStream_t s) {
@@ -448,8 +454,18 @@ __global__ void __launch_bounds__(kScoreThreads, H <= 4 ? 4 : 2)
     score_kernel(const float* __restrict__ X, const float* __restrict__ Y, const float* __restrict__ Z,
                  size_t cloud_stride, int tiles_per_cloud, int total_items, int items_per_cta, int pts_per_cta,
                  long long n_padded, const float4* __restrict__ hyps, int K, int k_begin, int k_end, float t,
-                 int32_t* __restrict__ counts, int warps_h) {
+                 int32_t* __restrict__ counts, int warps_h, const RoundState* __restrict__ st) {
   // hypotheses [k_begin, k_end) of the K per cloud are scored by this launch
+  if (st != nullptr) {
+    // peel loop without the host (range mode): the even split of launch_score_h, from the cloud size on the device
+    if (st->stop) return;
+    const long long unit = 128ll * (kScoreWarps / warps_h);
+    n_padded = (st->n_local + unit - 1) / unit * unit;
+    long long per = (n_padded + gridDim.x - 1) / gridDim.x;
+    per = (per + unit - 1) / unit * unit;
+    pts_per_cta = (int)per;
+    if (n_padded == 0) return;
+  }
   __shared__ __align__(128) float s_pts[kScoreStages][kScoreStageFloats];
   __shared__ __align__(8) uint64_t s_full[kScoreStages];
   __shared__ int s_done[kScoreStages];
@@ -596,7 +612,7 @@ __global__ void __launch_bounds__(kScoreThreads, H <= 4 ? 4 : 2)
 template <int H>
 static void launch_score_h(const float* X, const float* Y, const float* Z, size_t n_per_cloud, size_t cloud_stride,
                            int n_clouds, const float4* hyps, int K, int k_begin, int k_end, int warps_h, float t,
-                           int dot_order, int32_t* counts, int num_sms, cudaStream_t s, bool range_mode) {
+                           int dot_order, int32_t* counts, int num_sms, cudaStream_t s, bool range_mode, const RoundState* st) {
   const int chunk = 32 * H * warps_h;
   const int n_chunks = (k_end - k_begin + chunk - 1) / chunk;
   int slots = ((H <= 4 ? 4 : 2) * num_sms) / n_chunks;
@@ -612,6 +628,7 @@ static void launch_score_h(const float* X, const float* Y, const float* Z, size_
     per = (per + unit - 1) / unit * unit;
     pts_per_cta = (int)per;
     gx = (int)((n_padded + per - 1) / per);
+    if (st != nullptr) gx = slots;  // the device recomputes the split for the round's actual size
   } else {
     total_items = tiles_per_cloud * n_clouds;
     gx = slots > total_items ? total_items : slots;
@@ -621,18 +638,19 @@ static void launch_score_h(const float* X, const float* Y, const float* Z, size_
   dim3 grid(gx, n_chunks);
   if (dot_order == 1)
     score_kernel<H, 1><<<grid, kScoreThreads, 0, s>>>(X, Y, Z, cloud_stride, tiles_per_cloud, total_items, items_per_cta,
-                                                      pts_per_cta, n_padded, hyps, K, k_begin, k_end, t, counts, warps_h);
+                                                      pts_per_cta, n_padded, hyps, K, k_begin, k_end, t, counts, warps_h, st);
   else
     score_kernel<H, 0><<<grid, kScoreThreads, 0, s>>>(X, Y, Z, cloud_stride, tiles_per_cloud, total_items, items_per_cta,
-                                                      pts_per_cta, n_padded, hyps, K, k_begin, k_end, t, counts, warps_h);
+                                                      pts_per_cta, n_padded, hyps, K, k_begin, k_end, t, counts, warps_h, st);
 }
 
 int launch_score(CloudView cloud, size_t n_per_cloud, int n_clouds, size_t cloud_stride, const float4* hyps, int K,
-                 float t, int dot_order, int32_t* counts, int num_sms, cudaStream_t s) {
+                 float t, int dot_order, int32_t* counts, int num_sms, cudaStream_t s, const RoundState* st) {
   if (K <= 0 || n_per_cloud == 0 || n_clouds <= 0) return 0;
   static const int forced_h = [] { const char* e = getenv("PR_SCORE_H"); return e ? atoi(e) : 0; }();  // tuning knob
   static const int geom = [] { const char* e = getenv("PR_SCORE_GEOM"); return e ? atoi(e) : 1; }();   // 0: round-1 whole-tile split
-  const bool range_mode = geom != 0 && n_clouds == 1;
+  const bool range_mode = (geom != 0 || st != nullptr) && n_clouds == 1;
+  if (st != nullptr && !range_mode) return 0;
   // Every lane slot of a launch costs the same whether or not it holds a hypothesis, so K is cut into
   // launches whose slot count (32 * H * warps_h per chunk, grid.y chunks) matches.  With the even point split
   // any chunk count fills the machine, so the largest chunk width that wastes <= 1/32 of its slots takes all of
@@ -669,10 +687,10 @@ int launch_score(CloudView cloud, size_t n_per_cloud, int n_clouds, size_t cloud
     if (forced_h == 4 && H > 4) { warps_h = warps_h * H / 4 > kScoreWarps ? kScoreWarps : warps_h * H / 4; H = 4; }
     const float* X = cloud.x; const float* Y = cloud.y; const float* Z = cloud.z;
     switch (H) {
-      case 1: launch_score_h<1>(X, Y, Z, n_per_cloud, cloud_stride, n_clouds, hyps, K, k, k + take, warps_h, t, dot_order, counts, num_sms, s, range_mode); break;
-      case 2: launch_score_h<2>(X, Y, Z, n_per_cloud, cloud_stride, n_clouds, hyps, K, k, k + take, warps_h, t, dot_order, counts, num_sms, s, range_mode); break;
-      case 4: launch_score_h<4>(X, Y, Z, n_per_cloud, cloud_stride, n_clouds, hyps, K, k, k + take, warps_h, t, dot_order, counts, num_sms, s, range_mode); break;
-      default: launch_score_h<8>(X, Y, Z, n_per_cloud, cloud_stride, n_clouds, hyps, K, k, k + take, warps_h, t, dot_order, counts, num_sms, s, range_mode); break;
+      case 1: launch_score_h<1>(X, Y, Z, n_per_cloud, cloud_stride, n_clouds, hyps, K, k, k + take, warps_h, t, dot_order, counts, num_sms, s, range_mode, st); break;
+      case 2: launch_score_h<2>(X, Y, Z, n_per_cloud, cloud_stride, n_clouds, hyps, K, k, k + take, warps_h, t, dot_order, counts, num_sms, s, range_mode, st); break;
+      case 4: launch_score_h<4>(X, Y, Z, n_per_cloud, cloud_stride, n_clouds, hyps, K, k, k + take, warps_h, t, dot_order, counts, num_sms, s, range_mode, st); break;
+      default: launch_score_h<8>(X, Y, Z, n_per_cloud, cloud_stride, n_clouds, hyps, K, k, k + take, warps_h, t, dot_order, counts, num_sms, s, range_mode, st); break;
     }
     k += take;
     ++launches;
@@ -1054,7 +1072,12 @@ __global__ void __launch_bounds__(256, 4) refit_kernel(const float* __restrict__
                                                        const float4* __restrict__ hyps, const int4* __restrict__ sample_pts,
                                                        int model_index, float t, double scale, RefitOut* __restrict__ out,
                                                        size_t cloud_stride, int K, const int32_t* __restrict__ model_idx_arr,
-                                                       const double* __restrict__ scale_arr) {
+                                                       const double* __restrict__ scale_arr, const RoundState* __restrict__ st) {
+  if (st != nullptr) {  // peel loop without the host: size and winning draw of this round live on the device
+    if (st->stop || st->best < 0) return;
+    n = (size_t)st->n_local;
+    model_index = st->best;
+  }
   // batch mode (gridDim.y clouds): cloud c uses hypothesis c * K + model_idx_arr[c] and scale_arr[c]
   if (model_idx_arr != nullptr) {
     const size_t c = blockIdx.y;
@@ -1146,7 +1169,7 @@ __global__ void __launch_bounds__(256, 4) refit_kernel(const float* __restrict__
 }
 
 void launch_refit(CloudView cloud, size_t n, const float4* hyps, const int4* sample_pts, int model_index, float t,
-                  int dot_order, int scale_exp, RefitOut* out, int num_sms, cudaStream_t s) {
+                  int dot_order, int scale_exp, RefitOut* out, int num_sms, cudaStream_t s, const RoundState* st) {
   const double scale = ldexp(1.0, scale_exp);
   size_t nvec = (n + 3) / 4;
   size_t blocks = (nvec + 255) / 256;
@@ -1154,9 +1177,9 @@ void launch_refit(CloudView cloud, size_t n, const float4* hyps, const int4* sam
   if (blocks > (size_t)num_sms * 4) blocks = (size_t)num_sms * 4;
   if (blocks < 1) blocks = 1;
   if (dot_order == 1)
-    refit_kernel<1><<<(unsigned)blocks, 256, 0, s>>>(cloud.x, cloud.y, cloud.z, n, hyps, sample_pts, model_index, t, scale, out, 0, 0, nullptr, nullptr);
+    refit_kernel<1><<<(unsigned)blocks, 256, 0, s>>>(cloud.x, cloud.y, cloud.z, n, hyps, sample_pts, model_index, t, scale, out, 0, 0, nullptr, nullptr, st);
   else
-    refit_kernel<0><<<(unsigned)blocks, 256, 0, s>>>(cloud.x, cloud.y, cloud.z, n, hyps, sample_pts, model_index, t, scale, out, 0, 0, nullptr, nullptr);
+    refit_kernel<0><<<(unsigned)blocks, 256, 0, s>>>(cloud.x, cloud.y, cloud.z, n, hyps, sample_pts, model_index, t, scale, out, 0, 0, nullptr, nullptr, st);
 }
 
 void launch_refit_batch(CloudView clouds, size_t n_per, size_t cloud_stride, int n_clouds, const float4* hyps,
@@ -1169,9 +1192,9 @@ void launch_refit_batch(CloudView clouds, size_t n_per, size_t cloud_stride, int
   if (bx < 1) bx = 1;
   dim3 grid(bx, (unsigned)n_clouds);
   if (dot_order == 1)
-    refit_kernel<1><<<grid, 256, 0, s>>>(clouds.x, clouds.y, clouds.z, n_per, hyps, sample_pts, 0, t, 1.0, outs, cloud_stride, K, model_idx, scales);
+    refit_kernel<1><<<grid, 256, 0, s>>>(clouds.x, clouds.y, clouds.z, n_per, hyps, sample_pts, 0, t, 1.0, outs, cloud_stride, K, model_idx, scales, nullptr);
   else
-    refit_kernel<0><<<grid, 256, 0, s>>>(clouds.x, clouds.y, clouds.z, n_per, hyps, sample_pts, 0, t, 1.0, outs, cloud_stride, K, model_idx, scales);
+    refit_kernel<0><<<grid, 256, 0, s>>>(clouds.x, clouds.y, clouds.z, n_per, hyps, sample_pts, 0, t, 1.0, outs, cloud_stride, K, model_idx, scales, nullptr);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1180,6 +1203,12 @@ void launch_refit_batch(CloudView clouds, size_t n_per, size_t cloud_stride, int
 // on the number of KEPT points; the inlier rank of a point is its position minus the kept points
 // before it, so one scan serves both outputs.  Both outputs are staged in shared memory (kept points
 // from the front, inliers from the back of the same arrays) and written out contiguously.
+//
+// The look-back is block-wide: thread j inspects the descriptor of tile - 1 - j, so one step covers 256
+// predecessors.  With ~740 tiles in flight on 148 SMs the nearest tile whose inclusive prefix is already
+// published lies hundreds of tiles back; a warp-wide (32-descriptor) window walks that distance in ~20
+// dependent L2 round trips per tile, which is what bounded the round-1 kernel at 66 % of the HBM rate
+// (tile lifetime ~10 us against ~2 us of loads and stores); 256 descriptors per step make it one or two.
 // ------------------------------------------------------------------------------------------------
 constexpr int kCompactThreads = 256;
 constexpr unsigned long long kTileAggregate = 1ull << 62;
@@ -1192,18 +1221,43 @@ __global__ void __launch_bounds__(kCompactThreads, 5)
                    const int32_t* __restrict__ O, size_t n, Plane4 pl, float t, float* __restrict__ DX,
                    float* __restrict__ DY, float* __restrict__ DZ, int32_t* __restrict__ DO, size_t dst_cap,
                    int32_t* __restrict__ inl_cur, int32_t* __restrict__ inl_orig, unsigned long long* tile_state,
-                   unsigned* ticket, long long* __restrict__ totals, unsigned n_tiles, const uint32_t* __restrict__ flags) {
+                   unsigned* ticket, long long* __restrict__ totals, const uint32_t* __restrict__ flags,
+                   const RoundState* __restrict__ st) {
   __shared__ __align__(16) float s_x[kCompactTile];
   __shared__ __align__(16) float s_y[kCompactTile];
   __shared__ __align__(16) float s_z[kCompactTile];
   __shared__ __align__(16) int s_o[kCompactTile];
   __shared__ int s_warp[2][8];
   __shared__ unsigned s_tile;
-  __shared__ long long s_excl;
+  __shared__ long long s_lb_sum[8];
+  __shared__ int s_lb_found[8];
+
+  if (st != nullptr) {
+    // peel loop without the host: size, plane and list offset of this round live on the device; the grid was sized
+    // for an upper bound of n
+    if (st->stop) return;
+    n = (size_t)st->n_local;
+    pl.a = st->plane[0]; pl.b = st->plane[1]; pl.c = st->plane[2]; pl.d = st->plane[3];
+    if (inl_cur) inl_cur += st->inl_off;
+    if (inl_orig) inl_orig += st->inl_off;
+  }
+  const unsigned n_tiles = (unsigned)((n + kCompactTile - 1) / kCompactTile);
 
   if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
   __syncthreads();
   const unsigned tile = s_tile;
+  if (n_tiles == 0) {  // empty cloud (a shard whose points were all peeled): totals and padding only
+    if (tile == 0) {
+      if (threadIdx.x == 0) { totals[0] = 0; totals[1] = 0; }
+      if (WRITE_REM) {
+        size_t pad_end = kTilePoints;
+        if (pad_end > dst_cap) pad_end = dst_cap;
+        for (size_t j = threadIdx.x; j < pad_end; j += kCompactThreads) { DX[j] = CUDART_NAN_F; DY[j] = CUDART_NAN_F; DZ[j] = CUDART_NAN_F; }
+      }
+    }
+    return;
+  }
+  if (tile >= n_tiles) return;  // surplus CTAs of an upper-bound grid
   const size_t base = (size_t)tile * kCompactTile;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -1281,37 +1335,11 @@ __global__ void __launch_bounds__(kCompactThreads, 5)
   const int valid_in_tile = remaining_pts < (size_t)kCompactTile ? (int)remaining_pts : kCompactTile;
   const int inl_total = valid_in_tile - keep_total;
 
-  // decoupled look-back (warp 0)
-  if (warp == 0) {
-    long long excl = 0;
-    if (tile == 0) {
-      if (lane == 0) atomicExch(&tile_state[0], kTileInclusive | (unsigned long long)keep_total);
-    } else {
-      if (lane == 0) atomicExch(&tile_state[tile], kTileAggregate | (unsigned long long)keep_total);
-      long long look = (long long)tile - 1;
-      while (true) {
-        const long long idx = look - lane;
-        unsigned long long st = kTileInclusive;  // lanes before tile 0 contribute an inclusive 0
-        if (idx >= 0) {
-          do {
-            st = *reinterpret_cast<volatile unsigned long long*>(&tile_state[idx]);
-          } while ((st >> 62) == 0ull);
-        }
-        const unsigned incl_mask = __ballot_sync(0xFFFFFFFFu, (st >> 62) == 2ull);
-        const int first_incl = incl_mask ? (__ffs(incl_mask) - 1) : 32;
-        long long val = (lane <= first_incl) ? (long long)(st & kTileValueMask) : 0ll;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) val += __shfl_down_sync(0xFFFFFFFFu, val, o);
-        excl += __shfl_sync(0xFFFFFFFFu, val, 0);
-        if (incl_mask) break;
-        look -= 32;
-      }
-      if (lane == 0) atomicExch(&tile_state[tile], kTileInclusive | (unsigned long long)(excl + keep_total));
-    }
-    if (lane == 0) s_excl = excl;
-  }
+  // publish this tile's aggregate before anything waits on a predecessor
+  if (threadIdx.x == 0)
+    atomicExch(&tile_state[tile], (tile == 0 ? kTileInclusive : kTileAggregate) | (unsigned long long)keep_total);
 
-  // stage both partitions in shared memory
+  // stage both partitions in shared memory (local ranks only: overlaps the predecessors' progress)
 #pragma unroll
   for (int u = 0; u < 2; ++u) {
     int kr = (u ? round_total[0] : 0) + warp_excl[u] + lane_excl[u];  // kept rank within the tile
@@ -1333,8 +1361,45 @@ __global__ void __launch_bounds__(kCompactThreads, 5)
       }
     }
   }
-  __syncthreads();
-  const long long excl = s_excl;
+
+  // block-wide decoupled look-back: kept points of all earlier tiles
+  long long excl = 0;
+  if (tile == 0) {
+    __syncthreads();
+  } else {
+    long long back = (long long)tile - 1;
+    while (true) {
+      const long long idx = back - (long long)threadIdx.x;
+      unsigned long long stv = kTileInclusive;  // positions before tile 0 contribute an inclusive 0
+      if (idx >= 0) {
+        do {
+          stv = *reinterpret_cast<volatile unsigned long long*>(&tile_state[idx]);
+        } while ((stv >> 62) == 0ull);
+      }
+      const unsigned incl_mask = __ballot_sync(0xFFFFFFFFu, (stv >> 62) == 2ull);
+      const int first_incl = incl_mask ? (__ffs(incl_mask) - 1) : 32;
+      long long val = (lane <= first_incl) ? (long long)(stv & kTileValueMask) : 0ll;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) val += __shfl_down_sync(0xFFFFFFFFu, val, o);
+      if (lane == 0) {
+        s_lb_sum[warp] = val;
+        s_lb_found[warp] = incl_mask != 0u;
+      }
+      __syncthreads();
+      bool found = false;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) {
+        if (!found) {
+          excl += s_lb_sum[w];
+          found = s_lb_found[w] != 0;
+        }
+      }
+      if (found) break;
+      back -= kCompactThreads;
+      __syncthreads();  // the per-warp slots are rewritten by the next step
+    }
+    if (threadIdx.x == 0) atomicExch(&tile_state[tile], kTileInclusive | (unsigned long long)(excl + keep_total));
+  }
   const long long inl_excl = (long long)base - excl;
 
   if (WRITE_REM) {
@@ -1375,19 +1440,21 @@ size_t compact_scratch_bytes(size_t n) {
 }
 
 void launch_compact(CloudView src, size_t n, Plane4 plane, float t, int dot_order, CloudView dst, bool write_remaining,
-                    int32_t* inl_cur, int32_t* inl_orig, void* scratch, long long* totals, cudaStream_t s, const uint32_t* flags) {
-  if (n == 0) {
+                    int32_t* inl_cur, int32_t* inl_orig, void* scratch, long long* totals, cudaStream_t s, const uint32_t* flags,
+                    const RoundState* st) {
+  if (n == 0 && st == nullptr) {
     cudaMemsetAsync(totals, 0, 2 * sizeof(long long), s);
     return;
   }
-  const unsigned n_tiles = (unsigned)((n + kCompactTile - 1) / kCompactTile);
+  unsigned n_tiles = (unsigned)((n + kCompactTile - 1) / kCompactTile);
+  if (n_tiles == 0) n_tiles = 1;  // st mode: one CTA writes the totals and the padding of an empty shard
   cudaMemsetAsync(scratch, 0, compact_scratch_bytes(n), s);
   unsigned long long* tile_state = reinterpret_cast<unsigned long long*>(scratch);
-  unsigned* ticket = reinterpret_cast<unsigned*>(tile_state + n_tiles);
+  unsigned* ticket = reinterpret_cast<unsigned*>(tile_state + (n + kCompactTile - 1) / kCompactTile);
 #define PR_COMPACT(D, W)                                                                                              \
   compact_kernel<D, W><<<n_tiles, kCompactThreads, 0, s>>>(src.x, src.y, src.z, src.orig, n, plane, t, dst.x, dst.y,  \
                                                            dst.z, dst.orig, dst.cap, inl_cur, inl_orig, tile_state,   \
-                                                           ticket, totals, n_tiles, flags)
+                                                           ticket, totals, flags, st)
   if (dot_order == 3) {
     PR_COMPACT(3, true);
   } else if (dot_order == 2) {

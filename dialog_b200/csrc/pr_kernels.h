@@ -35,6 +35,38 @@ struct RefitOut {
   float pivot[4];
 };
 
+// ---- device-resident state of the peel loop (score-all mode): every kernel of a round reads its sizes, the winning
+// draw and the refined plane from here, so a whole extraction is queued without the host in the loop (pr_chain.cu).
+struct RoundState {
+  long long n_local;    // points of this rank's current cloud
+  long long n_global;   // ... of all ranks
+  long long first;      // global index of this rank's first point
+  long long inl_off;    // inlier-list entries written so far (this rank)
+  int round;            // planes accepted so far
+  int stop;             // 0: running; 1: finished (plane too small / no model); 2: the round in flight goes back to the host loop
+  int best;             // winning draw of the round in flight, -1: none
+  int best_count;       // its inlier count
+  float plane[4];       // coefficients of the round's final selection
+  int pad[4];
+};
+// What one round decided; the host reads record r once round r has run (pr_segment_info + the peel bookkeeping).
+struct RoundRecord {
+  int ran;              // 0: the round was skipped (the loop had stopped before it)
+  int accepted;         // the plane passed the minimum-size rule and was peeled
+  int stop;             // RoundState::stop after the round
+  int ok;               // a model was found
+  int best, best_count;
+  int best_sample[3];
+  int n_draws;
+  float raw[4], refined[4];
+  long long n_cloud;                      // global size of the round's cloud
+  long long n_local;                      // this rank's share of it
+  long long n_inl_local, n_rem_local;     // this rank: inliers peeled / points left
+  long long n_inl_global, n_rem_global;
+  long long first_after;                  // this rank's first global index in the remaining cloud
+  long long inl_off;                      // where this round's inlier lists start (this rank)
+};
+
 // K0: AoS pr_point[n] -> planes (NaN padded to cap) + bounding box of the finite points.
 // bbox: 6 x uint32 ordered-float encodings {min x,y,z, max x,y,z}; must be initialised by bbox_init.
 void launch_bbox_init(uint32_t* bbox, cudaStream_t s);
@@ -60,14 +92,16 @@ void launch_unstage(CloudView src, size_t n, float4* aos, cudaStream_t s);
 // with per_cloud_triples cloud c reads triples[c * n_samples ...].
 void launch_gather_samples(CloudView cloud, long long first, size_t n, const int32_t* triples, int n_samples,
                            int4* sample_pts, int n_clouds, size_t cloud_stride, cudaStream_t s,
-                           bool per_cloud_triples = false);
+                           bool per_cloud_triples = false, const RoundState* st = nullptr);
 // K1b: plane through each sample triple, PCL op order, no contraction; NaN plane + good = 0 when degenerate.
 void launch_models(const int4* sample_pts, int n_models_total, float4* hyps, int32_t* good, cudaStream_t s);
 
 // K2: counts[c * K + k] += |{ i in cloud c : |hyp[c*K+k] . (p_i, 1)| < t }|.  counts must be zeroed.
 // Returns the number of kernel launches it made (K is cut into launches that fill their lane slots).
+// st (single cloud only): the cloud size is st->n_local, read on the device (n_per_cloud is then only an upper bound), and
+// the launch does nothing once st->stop is set.
 int launch_score(CloudView cloud, size_t n_per_cloud, int n_clouds, size_t cloud_stride, const float4* hyps,
-                 int K, float t, int dot_order, int32_t* counts, int num_sms, cudaStream_t s);
+                 int K, float t, int dot_order, int32_t* counts, int num_sms, cudaStream_t s, const RoundState* st = nullptr);
 
 // Hierarchical scorer: Morton-sorted copy of a cloud, per-32-point-block boxes, culled scoring with counts
 // identical to launch_score.  keys / vals: 2*n uint32 each; temp: sort_temp_bytes(n); bounds: 2 float4 per block.
@@ -80,8 +114,9 @@ int launch_score_hier(CloudView sorted, size_t n, const float4* bounds, const fl
 
 // K3: inlier predicate with hyps[model_index] + exact integer moments about the model's first sample point.
 // out must be zeroed.  sample_pts supplies the pivot (sample_pts[3 * model_index]).
+// st: n = st->n_local and model_index = st->best are read on the device (n is then an upper bound for the grid).
 void launch_refit(CloudView cloud, size_t n, const float4* hyps, const int4* sample_pts, int model_index, float t,
-                  int dot_order, int scale_exp, RefitOut* out, int num_sms, cudaStream_t s);
+                  int dot_order, int scale_exp, RefitOut* out, int num_sms, cudaStream_t s, const RoundState* st = nullptr);
 
 // K3 for a batch: cloud c refits hypothesis c * K + model_idx[c] (skipped when negative) with scale 2^s_c.
 void launch_refit_batch(CloudView clouds, size_t n_per, size_t cloud_stride, int n_clouds, const float4* hyps,
@@ -94,9 +129,11 @@ void launch_refit_batch(CloudView clouds, size_t n_per, size_t cloud_stride, int
 size_t compact_scratch_bytes(size_t n);
 // dot_order == 2: predicate = point is non-finite (staging filter); dot_order == 3: predicate = flags[i] != 0
 // (flags: one uint32 per point, as long as the cloud's capacity).
+// st: n = st->n_local, the plane = st->plane and the list offset st->inl_off are read on the device (n is then an upper
+// bound for the grid and the scratch size).
 void launch_compact(CloudView src, size_t n, Plane4 plane, float t, int dot_order, CloudView dst, bool write_remaining,
                     int32_t* inl_cur, int32_t* inl_orig, void* scratch, long long* totals, cudaStream_t s,
-                    const uint32_t* flags = nullptr);
+                    const uint32_t* flags = nullptr, const RoundState* st = nullptr);
 
 // Re-absorption pass of the reference's postProcessPlanes (pr_reabsorb.cu).
 struct ReabsorbPlane {
@@ -154,18 +191,40 @@ struct P2PView {
   int rank;
 };
 // One single-CTA kernel per exchange: store this rank's contribution into every peer's mailbox slot
-// (slot_off + rank * slot_stride), raise flag[rank] = epoch in every peer's flag array (flag_off, kP2PMaxRanks x
-// uint64), wait (bounded; *err = 1 on timeout) for every rank's flag locally, then sum / concatenate in rank order.
-void launch_p2p_allreduce_i32(const P2PView& v, const int32_t* src, size_t n, size_t slot_off, size_t slot_stride, size_t flag_off,
-                              unsigned long long epoch, int32_t* dst, unsigned* err, cudaStream_t s);
-void launch_p2p_allreduce_i64(const P2PView& v, const long long* src, size_t n, size_t slot_off, size_t slot_stride, size_t flag_off,
-                              unsigned long long epoch, long long* dst, unsigned* err, cudaStream_t s);
-void launch_p2p_allgather_i64(const P2PView& v, const long long* src, size_t n, size_t slot_off, size_t slot_stride, size_t flag_off,
-                              unsigned long long epoch, long long* dst, unsigned* err, cudaStream_t s);
+// (slot_off + parity * buffer_bytes + rank * slot_stride), raise flag[rank] = epoch in every peer's flag array (flag_off,
+// kP2PMaxRanks x uint64), wait (bounded; *err = 1 on timeout) for every rank's flag locally, then sum / concatenate in
+// rank order.  The epoch is *epoch_ctr + 1 (device counter, advanced by the kernel); parity = epoch & 1 selects one of
+// the channel's two buffers.  st: the exchange is skipped (no epoch consumed) once st->stop is set.
+void launch_p2p_allreduce_i32(const P2PView& v, const int32_t* src, size_t n, size_t slot_off, size_t buffer_bytes, size_t slot_stride,
+                              size_t flag_off, unsigned long long* epoch_ctr, int32_t* dst, unsigned* err, cudaStream_t s,
+                              const RoundState* st = nullptr);
+void launch_p2p_allreduce_i64(const P2PView& v, const long long* src, size_t n, size_t slot_off, size_t buffer_bytes, size_t slot_stride,
+                              size_t flag_off, unsigned long long* epoch_ctr, long long* dst, unsigned* err, cudaStream_t s,
+                              const RoundState* st = nullptr);
+void launch_p2p_allgather_i64(const P2PView& v, const long long* src, size_t n, size_t slot_off, size_t buffer_bytes, size_t slot_stride,
+                              size_t flag_off, unsigned long long* epoch_ctr, long long* dst, unsigned* err, cudaStream_t s,
+                              const RoundState* st = nullptr);
 // K1a fused with its exchange: the owner of sample s writes the point's bits into every rank's sample buffer (sp_off);
-// dst receives all n_samples entries.
+// dst receives all n_samples entries.  st: shard extent (first, n) from the device state.
 void launch_p2p_samples(const P2PView& v, CloudView cloud, long long first, size_t n, const int32_t* triples, int n_samples,
-                        size_t sp_off, size_t flag_off, unsigned long long epoch, int4* dst, unsigned* err, cudaStream_t s);
+                        size_t sp_off, size_t buffer_bytes, size_t flag_off, unsigned long long* epoch_ctr, int4* dst, unsigned* err,
+                        cudaStream_t s, const RoundState* st = nullptr);
+
+// ---- the peel loop without the host (pr_chain.cu): per-round kernels driven by a RoundState in HBM ------------------
+// PCL's index triples for a cloud of st->n_global points: rnd = the first 3 * n_draws values of mt19937(seed) >> 1,
+// table = draw_table_slots(n_draws) uint64 of scratch, coll = kDrawCollCap uint32 + coll_count.  Sets st->stop = 2 when
+// the round has to go back to the sequential host sampler, 1 when the cloud has fewer than 3 points.
+size_t draw_table_slots(int n_draws);
+void launch_draw(const uint32_t* rnd, int n_draws, RoundState* st, int32_t* triples, unsigned long long* table, size_t table_slots,
+                 uint32_t* coll, uint32_t* coll_count, RoundRecord* rec, cudaStream_t s);
+// computeModel's decision over K counts (score-all mode): st->best / best_count, or st->stop = 2 when a bad sample means
+// PCL would draw beyond the K scored hypotheses.
+void launch_replay(const int32_t* counts, const int32_t* good, int K, RoundState* st, RoundRecord* rec, cudaStream_t s);
+// st->plane = refined coefficients (closed form from the summed moments, pr_math.h) or the raw model; fills the record.
+void launch_finish(RoundState* st, const float4* hyps, const int32_t* triples, const RefitOut* refit, int optimize, int scale_exp,
+                   int n_draws, RoundRecord* rec, cudaStream_t s);
+// Minimum-plane-size rule on the global inlier count; on acceptance the state moves to the remaining cloud.
+void launch_advance(RoundState* st, const long long* totals, int n_ranks, int rank, int min_plane, RoundRecord* rec, cudaStream_t s);
 
 // Measurement helpers.
 void launch_ffma_peak(float* out, int iters, int grid, cudaStream_t s);

@@ -5,7 +5,7 @@
 // those come from the portable implementations below (fdlibm's algorithms: argument reduction by table for atan,
 // minimax polynomials on [-pi/4, pi/4] for sin and cos), accurate to < 1 ulp, instead of a platform libm, because
 // glibc's and CUDA's functions differ in the last bit and the peel loop runs without the host in it.
-// The oracle keeps libm; tests/test_host_logic.py checks that both give the same FP32 coefficients.
+// The CPU checker under tests/ keeps libm; tests/test_host_logic.py checks that both give the same FP32 coefficients.
 #pragma once
 
 #include <stdint.h>

@@ -4,7 +4,7 @@
 // its cost is latency, not bandwidth.  Instead of one NCCL collective each (~40 us at 8 ranks), every rank
 // owns a "mailbox" in its HBM that all peers map through CUDA IPC; one kernel per exchange stores this rank's
 // contribution straight into every peer's mailbox (plain st.global over NVLink), fences at system scope,
-// raises a per-source flag (st.release.sys) carrying a monotonically increasing epoch, spins (bounded) on its
+// raises a per-source flag (st.release.sys) carrying a monotonically increasing epoch (kept on the device), spins (bounded) on its
 // own flags (ld.acquire.sys) and reduces the slots in rank order, which keeps integer sums bit-identical to
 // the single-GPU result.  No flag is ever reset; every channel has two buffers used alternately (epoch parity),
 // and a peer can only rewrite a buffer after this rank produced the exchange in between, which in stream order
@@ -56,11 +56,26 @@ __device__ __forceinline__ bool p2p_signal_and_wait(const P2PView& v, size_t fla
   return s_bad == 0;
 }
 
+// Epochs live on the device (one counter per channel, identical on every rank because every rank runs or skips the same
+// exchanges): every thread reads the counter on entry, thread 0 stores the new value once the exchange is complete.
+// A kernel queued by the host-free peel loop returns at once when the loop has stopped (st->stop, the same on every
+// rank), without consuming an epoch, so two exchanges that use the same buffer always have a completed one between them.
+__device__ __forceinline__ bool p2p_enter(const RoundState* st, const unsigned long long* epoch_ctr, const unsigned* err,
+                                          unsigned long long* epoch) {
+  if (st != nullptr && st->stop) return false;
+  if (*reinterpret_cast<const volatile unsigned*>(err)) return false;  // an earlier exchange timed out: do not wait 20 s again
+  *epoch = *epoch_ctr + 1ull;
+  return true;
+}
+
 // dst[i] = sum over ranks (rank order) of every rank's src[i]; in place is fine (src is read before the barrier).
 template <typename T>
-__global__ void __launch_bounds__(kP2PThreads) p2p_allreduce_kernel(P2PView v, const T* src, size_t n, size_t slot_off,
-                                                                    size_t slot_stride, size_t flag_off, unsigned long long epoch,
-                                                                    T* dst, unsigned* err) {
+__global__ void __launch_bounds__(kP2PThreads) p2p_allreduce_kernel(P2PView v, const T* src, size_t n, size_t slot_off, size_t buffer_bytes,
+                                                                    size_t slot_stride, size_t flag_off, unsigned long long* epoch_ctr,
+                                                                    T* dst, unsigned* err, const RoundState* st) {
+  unsigned long long epoch;
+  if (!p2p_enter(st, epoch_ctr, err, &epoch)) return;
+  slot_off += (size_t)(epoch & 1ull) * buffer_bytes;
   for (int r = 0; r < v.n_ranks; ++r) {
     T* out = reinterpret_cast<T*>(v.peers[r] + slot_off + (size_t)v.rank * slot_stride);
     for (size_t i = threadIdx.x; i < n; i += kP2PThreads) out[i] = src[i];
@@ -72,13 +87,18 @@ __global__ void __launch_bounds__(kP2PThreads) p2p_allreduce_kernel(P2PView v, c
       acc += __ldcg(reinterpret_cast<const T*>(v.peers[v.rank] + slot_off + (size_t)r * slot_stride) + i);
     dst[i] = acc;
   }
+  if (threadIdx.x == 0) *epoch_ctr = epoch;
 }
 
 // dst[r * n + i] = rank r's src[i]
 template <typename T>
 __global__ void __launch_bounds__(kP2PThreads) p2p_allgather_kernel(P2PView v, const T* __restrict__ src, size_t n, size_t slot_off,
-                                                                    size_t slot_stride, size_t flag_off, unsigned long long epoch,
-                                                                    T* __restrict__ dst, unsigned* err) {
+                                                                    size_t buffer_bytes, size_t slot_stride, size_t flag_off,
+                                                                    unsigned long long* epoch_ctr, T* __restrict__ dst, unsigned* err,
+                                                                    const RoundState* st) {
+  unsigned long long epoch;
+  if (!p2p_enter(st, epoch_ctr, err, &epoch)) return;
+  slot_off += (size_t)(epoch & 1ull) * buffer_bytes;
   for (int r = 0; r < v.n_ranks; ++r) {
     T* out = reinterpret_cast<T*>(v.peers[r] + slot_off + (size_t)v.rank * slot_stride);
     for (size_t i = threadIdx.x; i < n; i += kP2PThreads) out[i] = src[i];
@@ -88,6 +108,7 @@ __global__ void __launch_bounds__(kP2PThreads) p2p_allgather_kernel(P2PView v, c
     const size_t r = i / n, k = i - r * n;
     dst[i] = __ldcg(reinterpret_cast<const T*>(v.peers[v.rank] + slot_off + r * slot_stride) + k);
   }
+  if (threadIdx.x == 0) *epoch_ctr = epoch;
 }
 
 // K1a fused with its exchange: the owner of sample s writes the point's bits into every rank's sample buffer; after
@@ -95,8 +116,15 @@ __global__ void __launch_bounds__(kP2PThreads) p2p_allgather_kernel(P2PView v, c
 __global__ void __launch_bounds__(kP2PThreads) p2p_samples_kernel(P2PView v, const float* __restrict__ x, const float* __restrict__ y,
                                                                   const float* __restrict__ z, long long first, size_t n,
                                                                   const int32_t* __restrict__ triples, int n_samples, size_t sp_off,
-                                                                  size_t flag_off, unsigned long long epoch, int4* __restrict__ dst,
-                                                                  unsigned* err) {
+                                                                  size_t buffer_bytes, size_t flag_off, unsigned long long* epoch_ctr,
+                                                                  int4* __restrict__ dst, unsigned* err, const RoundState* st) {
+  unsigned long long epoch;
+  if (!p2p_enter(st, epoch_ctr, err, &epoch)) return;
+  if (st != nullptr) {
+    first = st->first;
+    n = (size_t)st->n_local;
+  }
+  sp_off += (size_t)(epoch & 1ull) * buffer_bytes;
   for (int s = threadIdx.x; s < n_samples; s += kP2PThreads) {
     const long long local = (long long)triples[s] - first;
     if (local >= 0 && local < (long long)n) {
@@ -107,26 +135,29 @@ __global__ void __launch_bounds__(kP2PThreads) p2p_samples_kernel(P2PView v, con
   if (!p2p_signal_and_wait(v, flag_off, epoch, err)) return;
   const int4* in = reinterpret_cast<const int4*>(v.peers[v.rank] + sp_off);
   for (int s = threadIdx.x; s < n_samples; s += kP2PThreads) dst[s] = __ldcg(in + s);
+  if (threadIdx.x == 0) *epoch_ctr = epoch;
 }
 
-void launch_p2p_allreduce_i32(const P2PView& v, const int32_t* src, size_t n, size_t slot_off, size_t slot_stride, size_t flag_off,
-                              unsigned long long epoch, int32_t* dst, unsigned* err, cudaStream_t s) {
-  p2p_allreduce_kernel<int32_t><<<1, kP2PThreads, 0, s>>>(v, src, n, slot_off, slot_stride, flag_off, epoch, dst, err);
+void launch_p2p_allreduce_i32(const P2PView& v, const int32_t* src, size_t n, size_t slot_off, size_t buffer_bytes, size_t slot_stride,
+                              size_t flag_off, unsigned long long* epoch_ctr, int32_t* dst, unsigned* err, cudaStream_t s, const RoundState* st) {
+  p2p_allreduce_kernel<int32_t><<<1, kP2PThreads, 0, s>>>(v, src, n, slot_off, buffer_bytes, slot_stride, flag_off, epoch_ctr, dst, err, st);
 }
 
-void launch_p2p_allreduce_i64(const P2PView& v, const long long* src, size_t n, size_t slot_off, size_t slot_stride, size_t flag_off,
-                              unsigned long long epoch, long long* dst, unsigned* err, cudaStream_t s) {
-  p2p_allreduce_kernel<long long><<<1, kP2PThreads, 0, s>>>(v, src, n, slot_off, slot_stride, flag_off, epoch, dst, err);
+void launch_p2p_allreduce_i64(const P2PView& v, const long long* src, size_t n, size_t slot_off, size_t buffer_bytes, size_t slot_stride,
+                              size_t flag_off, unsigned long long* epoch_ctr, long long* dst, unsigned* err, cudaStream_t s, const RoundState* st) {
+  p2p_allreduce_kernel<long long><<<1, kP2PThreads, 0, s>>>(v, src, n, slot_off, buffer_bytes, slot_stride, flag_off, epoch_ctr, dst, err, st);
 }
 
-void launch_p2p_allgather_i64(const P2PView& v, const long long* src, size_t n, size_t slot_off, size_t slot_stride, size_t flag_off,
-                              unsigned long long epoch, long long* dst, unsigned* err, cudaStream_t s) {
-  p2p_allgather_kernel<long long><<<1, kP2PThreads, 0, s>>>(v, src, n, slot_off, slot_stride, flag_off, epoch, dst, err);
+void launch_p2p_allgather_i64(const P2PView& v, const long long* src, size_t n, size_t slot_off, size_t buffer_bytes, size_t slot_stride,
+                              size_t flag_off, unsigned long long* epoch_ctr, long long* dst, unsigned* err, cudaStream_t s, const RoundState* st) {
+  p2p_allgather_kernel<long long><<<1, kP2PThreads, 0, s>>>(v, src, n, slot_off, buffer_bytes, slot_stride, flag_off, epoch_ctr, dst, err, st);
 }
 
 void launch_p2p_samples(const P2PView& v, CloudView cloud, long long first, size_t n, const int32_t* triples, int n_samples,
-                        size_t sp_off, size_t flag_off, unsigned long long epoch, int4* dst, unsigned* err, cudaStream_t s) {
-  p2p_samples_kernel<<<1, kP2PThreads, 0, s>>>(v, cloud.x, cloud.y, cloud.z, first, n, triples, n_samples, sp_off, flag_off, epoch, dst, err);
+                        size_t sp_off, size_t buffer_bytes, size_t flag_off, unsigned long long* epoch_ctr, int4* dst, unsigned* err,
+                        cudaStream_t s, const RoundState* st) {
+  p2p_samples_kernel<<<1, kP2PThreads, 0, s>>>(v, cloud.x, cloud.y, cloud.z, first, n, triples, n_samples, sp_off, buffer_bytes, flag_off,
+                                              epoch_ctr, dst, err, st);
 }
 
 }  // namespace pr

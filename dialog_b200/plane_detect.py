@@ -370,6 +370,11 @@ class PlaneRansac:
         _lib.check(self._L.plane_ransac_measure_copy_bw(self._h, nbytes, C.byref(v)))
         return v.value
 
+    def set_round_loop(self, host: bool):
+        """host=True: every peel round is driven by the host (PR_LOOP_HOST); False: the default, whole rounds queued on the
+        device in score-all mode.  Same results either way."""
+        _lib.check(self._L.plane_ransac_set_round_loop(self._h, 1 if host else 0))
+
     def flush_l2(self):
         _lib.check(self._L.plane_ransac_flush_l2(self._h))
 

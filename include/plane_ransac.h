@@ -169,6 +169,15 @@ int plane_ransac_segment_one(plane_ransac_ctx* ctx, const pr_params* prm, float 
 int plane_ransac_extract_planes(plane_ransac_ctx* ctx, const pr_params* prm, float* coeffs,
                                 int32_t* inlier_cur, int32_t* inlier_orig, size_t idx_cap,
                                 size_t* plane_offsets, int* n_planes, pr_segment_info* infos);
+/* Who drives the peel loop of plane_ransac_extract_planes.  Both give identical results.
+ *   PR_LOOP_AUTO  (default) in score-all mode (probability = 1, brute scorer, at most 16384 hypotheses per round) whole
+ *                 rounds are queued on the device — PCL's index triples, computeModel's decision, the closed-form
+ *                 refit and the minimum-size rule run as kernels on a device-resident round state — and the host only
+ *                 reads each round's record as it completes; rounds that need PCL's redraw rule fall back to the host.
+ *   PR_LOOP_HOST  every round is driven by the host: it draws the triples, replays computeModel over the counts and
+ *                 solves the refit, with three stream synchronisations per round (the adaptive mode always runs so). */
+enum { PR_LOOP_AUTO = 0, PR_LOOP_HOST = 1 };
+int plane_ransac_set_round_loop(plane_ransac_ctx* ctx, int mode);
 /* Plane::points_set of plane k of the last extract call (Dialog/HeaderFile.h:85): its inlier points in index
  * order, read from the staged cloud.  With project != 0 every point is projected onto the plane with the
  * reference's projPoint2Plane arithmetic (Dialog/PlaneDetect.h:1442-1448) — the cloud polyPointCloud hands to
