@@ -449,7 +449,7 @@ __device__ __forceinline__ void score_tile_of(const ScoreSpan& w, int it, int ti
   }
 }
 
-template <int H, int DOT>
+template <int H, int DOT, int UNR>
 __global__ void __launch_bounds__(kScoreThreads, H <= 4 ? 4 : 2)
     score_kernel(const float* __restrict__ X, const float* __restrict__ Y, const float* __restrict__ Z,
                  size_t cloud_stride, int tiles_per_cloud, int total_items, int items_per_cta, int pts_per_cta,
@@ -545,14 +545,16 @@ __global__ void __launch_bounds__(kScoreThreads, H <= 4 ? 4 : 2)
     const float* sy = sx + kTilePoints;
     const float* sz = sx + 2 * kTilePoints;
 
-    // 128-point chunks (32 steps of 4 points): compile-time trip count, counters folded after each chunk
+    // 128-point chunks (32 steps of 4 points): compile-time trip count; the packed counters hold up to 511 increments,
+    // so they are folded into the plain counters every third chunk (384 increments) and at the end of the tile
+    int pending = 0;
     for (int p = 0; p < pts_per_warp; p += 4 * kScoreStepsPerFlush) {
       // software pipeline: the points of step q + 1 are loaded while step q computes (the load issued by
       // the last step of a tile reads 16 bytes past its plane: the next plane, or the stage's tail pad)
       float4 x4 = *reinterpret_cast<const float4*>(sx + p);
       float4 y4 = *reinterpret_cast<const float4*>(sy + p);
       float4 z4 = *reinterpret_cast<const float4*>(sz + p);
-#pragma unroll 2
+#pragma unroll UNR
       for (int q = 0; q < kScoreStepsPerFlush; ++q) {
         const float2 xa = make_float2(x4.x, x4.y), xb = make_float2(x4.z, x4.w);
         const float2 ya = make_float2(y4.x, y4.y), yb = make_float2(y4.z, y4.w);
@@ -575,11 +577,19 @@ __global__ void __launch_bounds__(kScoreThreads, H <= 4 ? 4 : 2)
           acc[j] = a;
         }
       }
+      if (++pending == 3) {
+        pending = 0;
 #pragma unroll
-      for (int j = 0; j < H; ++j) {
-        cnt[j] += (int)(((acc[j] >> 23) * 383u) & 511u);
-        acc[j] = 0u;
+        for (int j = 0; j < H; ++j) {
+          cnt[j] += (int)(((acc[j] >> 23) * 383u) & 511u);
+          acc[j] = 0u;
+        }
       }
+    }
+#pragma unroll
+    for (int j = 0; j < H; ++j) {
+      cnt[j] += (int)(((acc[j] >> 23) * 383u) & 511u);
+      acc[j] = 0u;
     }
 
     // release the stage; the last warp to finish refills it (no thread ever spins on an empty slot)
@@ -636,12 +646,18 @@ static void launch_score_h(const float* X, const float* Y, const float* Z, size_
     gx = (total_items + items_per_cta - 1) / items_per_cta;
   }
   dim3 grid(gx, n_chunks);
-  if (dot_order == 1)
-    score_kernel<H, 1><<<grid, kScoreThreads, 0, s>>>(X, Y, Z, cloud_stride, tiles_per_cloud, total_items, items_per_cta,
-                                                      pts_per_cta, n_padded, hyps, K, k_begin, k_end, t, counts, warps_h, st);
-  else
-    score_kernel<H, 0><<<grid, kScoreThreads, 0, s>>>(X, Y, Z, cloud_stride, tiles_per_cloud, total_items, items_per_cta,
-                                                      pts_per_cta, n_padded, hyps, K, k_begin, k_end, t, counts, warps_h, st);
+  static const int unroll = [] { const char* e = getenv("PR_SCORE_UNROLL"); return e ? atoi(e) : 2; }();  // tuning knob (H = 8, FMA order)
+#define PR_SCORE(HH, D, U)                                                                                                   \
+  score_kernel<HH, D, U><<<grid, kScoreThreads, 0, s>>>(X, Y, Z, cloud_stride, tiles_per_cloud, total_items, items_per_cta, \
+                                                        pts_per_cta, n_padded, hyps, K, k_begin, k_end, t, counts, warps_h, st)
+  if (dot_order == 1) {
+    if (H == 8 && unroll == 4) PR_SCORE(8, 1, 4);
+    else if (H == 8 && unroll == 8) PR_SCORE(8, 1, 8);
+    else PR_SCORE(H, 1, 2);
+  } else {
+    PR_SCORE(H, 0, 2);
+  }
+#undef PR_SCORE
 }
 
 int launch_score(CloudView cloud, size_t n_per_cloud, int n_clouds, size_t cloud_stride, const float4* hyps, int K,
@@ -1372,8 +1388,10 @@ __global__ void __launch_bounds__(kCompactThreads, 5)
       const long long idx = back - (long long)threadIdx.x;
       unsigned long long stv = kTileInclusive;  // positions before tile 0 contribute an inclusive 0
       if (idx >= 0) {
+        unsigned spins = 0;
         do {
           stv = *reinterpret_cast<volatile unsigned long long*>(&tile_state[idx]);
+          if (++spins > (1u << 24)) __trap();  // seconds of polling: a lost descriptor becomes a launch failure, not a hung GPU
         } while ((stv >> 62) == 0ull);
       }
       const unsigned incl_mask = __ballot_sync(0xFFFFFFFFu, (stv >> 62) == 2ull);

@@ -51,6 +51,14 @@ def main():
         assert a.info.n_inliers == b.info.n_inliers and list(a.info.best_sample) == list(b.info.best_sample)
         mine = b.inliers_orig[(b.inliers_orig >= first) & (b.inliers_orig < first + count)] - first
         assert (a.inliers_orig == mine).all(), f"plane {k}: inlier set differs on rank {rank}"
+    # the host-driven loop (three synchronisations per round) gives the same planes as the device-driven default
+    sh.set_round_loop(host=True)
+    got_hl = sh.extract_planes(prm)
+    sh.set_round_loop(host=False)
+    assert len(got_hl.planes) == len(got.planes)
+    for k, (a, b) in enumerate(zip(got_hl.planes, got.planes)):
+        assert a.coeff.tobytes() == b.coeff.tobytes() and (a.inliers_orig == b.inliers_orig).all(), f"host loop, plane {k}"
+        assert list(a.info.best_sample) == list(b.info.best_sample) and a.info.best_count == b.info.best_count
     # the hierarchical scorer, sharded: every rank culls on its own Morton-sorted shard, same global answer
     got_h = sh.extract_planes(D.make_params(0.1, 1023, 500, 1.0, True, 12345, 20, D.DOT_FMA, D.SCORER_HIER))
     assert len(got_h.planes) == len(want.planes)
@@ -63,6 +71,34 @@ def main():
     tot = torch.tensor([rem.shape[0]], device="cuda")
     dist.all_reduce(tot)
     assert int(tot.item()) == want_rem.shape[0]
+    # unbalanced shards: rank 0 holds one whole 300k-point plane plus a sliver of the scene, so after the first peel its
+    # shard is a fraction of the others'.  Everything a rank derives its collectives from (sub-batch sizes, exchange
+    # mode) must come from global quantities; 8192 hypotheses per round make the host-driven loop cut sub-batches.
+    rng = np.random.default_rng(5)
+    slab = np.ones((300_000, 4), np.float32)
+    slab[:, 0] = rng.uniform(0, 30, 300_000)
+    slab[:, 1] = rng.uniform(0, 20, 300_000)
+    slab[:, 2] = 9.0 + rng.normal(0, 0.02, 300_000)
+    lop = np.concatenate([slab, pts[:300_000]])
+    cuts = [0, 330_000] + [330_000 + (270_000 * (r + 1)) // (world - 1) for r in range(world - 1)]
+    prm_u = D.make_params(0.1, 8191, 500, 1.0, True, 12345, 6, D.DOT_FMA)
+    with D.PlaneRansac(local) as one:
+        one.set_cloud(lop)
+        want_u = one.extract_planes(prm_u)
+    assert want_u.planes[0].info.n_inliers >= 300_000
+    dist.barrier()
+    f_u, c_u = cuts[rank], cuts[rank + 1] - cuts[rank]
+    sh.set_cloud(lop[f_u: f_u + c_u])
+    assert sh.shard_info()[:2] == (lop.shape[0], f_u)
+    for host_loop in (False, True):
+        sh.set_round_loop(host=host_loop)
+        got_u = sh.extract_planes(prm_u)
+        assert len(got_u.planes) == len(want_u.planes) == 6
+        for k, (a, b) in enumerate(zip(got_u.planes, want_u.planes)):
+            assert a.coeff.tobytes() == b.coeff.tobytes() and a.info.n_inliers == b.info.n_inliers, f"unbalanced, plane {k}"
+            mine = b.inliers_orig[(b.inliers_orig >= f_u) & (b.inliers_orig < f_u + c_u)] - f_u
+            assert (a.inliers_orig == mine).all(), f"unbalanced shards, plane {k}: inlier set differs on rank {rank}"
+    sh.set_round_loop(host=False)
     # overlapped upload, sharded: chunks scored as they land on every rank, same answer (shards of >= 2M points)
     n_big = 2_200_000 * world
     big = synth.indoor_scene().points(0, n_big)

@@ -213,6 +213,98 @@ def test_extract_pcl_defaults_and_max_planes(O, pr, scene2):
     _check_extract(O, pr, pts, D.make_params(0.1, 50, 500, 0.99, True, 12345, 0, D.DOT_FMA))     # max_planes = 0
 
 
+def _same_extraction(a, b):
+    assert len(a.planes) == len(b.planes)
+    for k, (p, q) in enumerate(zip(a.planes, b.planes)):
+        assert _same_bits(p.coeff, q.coeff), k
+        assert np.array_equal(p.inliers_cur, q.inliers_cur) and np.array_equal(p.inliers_orig, q.inliers_orig), k
+        for f in ("ok", "iterations", "draws", "skipped", "best_count", "n_inliers_raw", "n_inliers", "scale_exp", "n_scored", "n_cloud"):
+            assert getattr(p.info, f) == getattr(q.info, f), (k, f)
+        assert list(p.info.best_sample) == list(q.info.best_sample) and _same_bits(list(p.info.raw_coeff), list(q.info.raw_coeff))
+    assert len(a.infos) == len(b.infos)
+    if len(a.infos) > len(a.planes):      # the rejected last segment() call is reported the same way
+        assert a.infos[-1].ok == b.infos[-1].ok and a.infos[-1].n_inliers == b.infos[-1].n_inliers
+        assert a.infos[-1].n_cloud == b.infos[-1].n_cloud
+
+
+@pytest.mark.parametrize("scene,n,max_it,min_plane,max_planes,opt,order", [
+    ("s2", 150_000, 255, 5000, 8, True, 1), ("s2", 150_000, 255, 5000, 2, True, 0), ("s3", 250_000, 511, 500, 20, True, 1),
+    ("s3", 90_000, 99, 500, 30, False, 1), ("s2", 40_000, 31, 10**9, 4, True, 1), ("s3", 1_200_000, 1023, 500, 12, True, 1)])
+def test_device_round_loop_equals_host_loop(O, pr, scene2, scene3, scene, n, max_it, min_plane, max_planes, opt, order):
+    """Score-all mode: whole rounds queued on the device (PCL's triples, computeModel's decision, the closed-form refit
+    and the stop rule as kernels on a device-resident state) against the same rounds driven by the host."""
+    import dialog_b200 as D
+    pts = (scene2 if scene == "s2" else scene3).points(0, n)
+    prm = D.make_params(0.1, max_it, min_plane, 1.0, opt, 12345, max_planes, order)
+    pr.set_cloud(pts)
+    dev = pr.extract_planes(prm)
+    rem_dev = pr.remaining().copy()
+    pr.set_round_loop(host=True)
+    try:
+        host = pr.extract_planes(prm)
+        rem_host = pr.remaining().copy()
+    finally:
+        pr.set_round_loop(host=False)
+    _same_extraction(dev, host)
+    assert rem_dev.tobytes() == rem_host.tobytes()
+    if n <= 250_000:
+        want = O.extract_planes(pts, _oparams(O, prm))
+        assert len(want.coeffs) == len(dev.planes)
+        for k, p in enumerate(dev.planes):
+            assert _same_bits(p.coeff, want.coeffs[k]) and np.array_equal(p.inliers_orig, want.inliers_orig[k])
+        assert rem_dev.tobytes() == want.remaining.tobytes()
+
+
+def test_device_round_loop_hands_rounds_back(O, pr, scene2):
+    """Rounds the device cannot decide alone go back to the host-driven loop and give PCL's answer: duplicated points make
+    degenerate samples (PCL redraws them, so more than max_iterations + 1 draws are consumed), and a small cloud with many
+    hypotheses has more colliding picks than the device-side sampler replays."""
+    import dialog_b200 as D
+    pts = scene2.points(0, 120_000).copy()
+    pts[::7] = pts[3]                                   # every 7th point is the same point: ~6 % of the triples are bad
+    prm = D.make_params(0.1, 255, 2000, 1.0, True, 12345, 5, D.DOT_FMA)
+    ex = _check_extract(O, pr, pts, prm)
+    assert any(i.draws > i.iterations for i in ex.infos)
+    small = scene2.points(0, 60_000)
+    _check_extract(O, pr, small, D.make_params(0.1, 2047, 2000, 1.0, True, 12345, 4, D.DOT_FMA))    # (3K)^2 / N ~ 630 colliding picks
+    _check_extract(O, pr, small[:9000], D.make_params(0.1, 1023, 300, 1.0, True, 12345, 4, D.DOT_FMA))  # not eligible: host loop
+
+
+def test_extract_flat_and_empty_rounds(O, pr):
+    """Compaction extremes across hundreds of tiles: every point an inlier (nothing kept), and no inlier at all."""
+    import dialog_b200 as D
+    rng = np.random.default_rng(11)
+    flat = np.c_[rng.random((700_000, 2)) * 50, np.zeros(700_000)].astype(np.float32)
+    ex = _check_extract(O, pr, flat, D.make_params(0.1, 63, 500, 1.0, True, 12345, 3, D.DOT_FMA))
+    assert len(ex.planes) == 1 and ex.planes[0].inliers_cur.size == 700_000
+    blob = rng.normal(size=(650_000, 3)).astype(np.float32) * 40
+    ex = _check_extract(O, pr, blob, D.make_params(1e-4, 63, 500, 1.0, True, 12345, 3, D.DOT_FMA))
+    assert len(ex.planes) == 0
+
+
+def test_config2_at_its_named_size(O, pr, scene2):
+    """BASELINE configs[1] as stated: 1M points, 3 planes + noise + 30 % outliers, 1024 hypotheses per round — the whole
+    3-plane peel and the full 1024-entry count vector of round 0 against the oracle."""
+    import dialog_b200 as D
+    pts = scene2.points(0, 1_000_000)
+    prm = D.make_params(0.1, 1023, 500, 1.0, True, 12345, 3, D.DOT_FMA)
+    pr.set_cloud(pts)
+    tri = O.draw_sequence(pts.shape[0], 1024)
+    counts = pr.score(tri, 0.1, D.DOT_FMA)
+    oc, og = O.models_from_triples(pts, tri)
+    want_counts = O.count_batch(pts, np.nan_to_num(oc), 0.1, O.DOT_FMA, threads=8)
+    want_counts[~og] = 0
+    assert (counts == want_counts).all()
+    ex = pr.extract_planes(prm)
+    want = O.extract_planes(pts, _oparams(O, prm))
+    assert len(ex.planes) == len(want.coeffs) == 3
+    for k, p in enumerate(ex.planes):
+        assert _same_bits(p.coeff, want.coeffs[k]) and np.array_equal(p.inliers_orig, want.inliers_orig[k])
+        assert list(p.info.best_sample) == list(want.traces[k].best_sample)
+    assert ex.planes[0].info.best_count == int(want_counts.max())
+    assert pr.remaining().tobytes() == want.remaining.tobytes()
+
+
 def test_extract_capacity_error(pr, scene2):
     import ctypes as C
     import dialog_b200 as D
@@ -323,7 +415,7 @@ def test_segment_batch_matches_per_cloud_oracle(O, pr, n_clouds, n_per, max_it, 
         assert cnt[cid] == seg.inliers.size
 
 
-def test_properties_at_100m_points(pr, scene3):
+def test_properties_at_100m_points(O, pr, scene3):
     """BASELINE configs[3] scale on one GPU (1.6 GB as pcl::PointXYZ): 10 shifted copies of a 10M-point storey.
     Size-independent properties only: the planes and the remaining cloud tile the input in stable order, and
     every copy of the floor is found as its own plane with the same inlier count."""
@@ -349,6 +441,19 @@ def test_properties_at_100m_points(pr, scene3):
     rem = pr.remaining()
     assert rem.shape[0] == n - total
     assert np.array_equal(rem, pts[~seen])
+    del rem, seen
+    # round 0 against the oracle at this size: the counts of the winning draw and of 8 others, and the winner's
+    # refined inlier count (8 host threads, ~10 s)
+    tri = O.draw_sequence(n, 512)
+    win = np.nonzero((tri == list(ex.planes[0].info.best_sample)).all(1))[0][0]
+    pick = np.r_[[win], np.arange(8)]
+    got = pr.score(tri[pick], 0.1, D.DOT_FMA)
+    oc, og = O.models_from_triples(pts, tri[pick])
+    want = O.count_batch(pts, np.nan_to_num(oc), 0.1, O.DOT_FMA, threads=8)
+    want[~og] = 0
+    assert (got == want).all()
+    assert got[0] == ex.planes[0].info.best_count
+    assert ex.planes[0].inliers_orig.size == O.count_within(pts, ex.planes[0].coeff, 0.1, O.DOT_FMA, mt=True)
     pr.set_cloud(base[:1000])       # release the large buffers' contents for the following tests
 
 
