@@ -60,6 +60,10 @@ def parse_args():
                          "(batch of 32K-point clouds, K=256) on rank 0's GPU; reported under 'extras'")
     ap.add_argument("--batch-clouds", type=int, default=512)
     ap.add_argument("--no-hbm-100m", action="store_true", help="skip the single-launch 100M-point compaction / refit measurement")
+    ap.add_argument("--no-config4", action="store_true",
+                    help="skip BASELINE configs[3]: the 100M-point scene sharded over the N ranks (strong scaling), with the "
+                         "sharded result checked against one GPU solving the whole cloud")
+    ap.add_argument("--config4-points", type=int, default=100_000_000)
     return ap.parse_args()
 
 
@@ -316,6 +320,175 @@ def run_extras(args, pr):
     return out
 
 
+def _mix64(g):
+    """Order-independent 64-bit hash ingredient of an index array (wrap-around arithmetic)."""
+    with np.errstate(over="ignore"):
+        x = (g.astype(np.uint64) + np.uint64(1)) * np.uint64(0x9E3779B97F4A7C15)
+        x ^= x >> np.uint64(29)
+        x *= np.uint64(0xBF58476D1CE4E5B9)
+        x ^= x >> np.uint64(32)
+        return x
+
+
+def storeys_cloud(base, first, count):
+    """BASELINE configs[3] scene: global point i is point (i mod len(base)) of the 10M-point indoor storey, lifted by
+    8 m per storey (i div len(base)); rows [first, first + count)."""
+    nb = base.shape[0]
+    out = np.empty((count, 4), np.float32)
+    done = 0
+    while done < count:
+        g = first + done
+        storey, off = divmod(g, nb)
+        take = min(nb - off, count - done)
+        out[done:done + take] = base[off:off + take]
+        out[done:done + take, 2] += np.float32(8.0 * storey)
+        done += take
+    return out
+
+
+def run_config4(args, torch, dist, D, local_rank, world, rank, hbm_peak, peak_tf):
+    """BASELINE configs[3]: one 100M-point scene, sharded by contiguous index range over the N ranks (strong scaling),
+    20 planes x 4096 hypotheses.  Outside the headline timer.  With N > 1 rank 0 also solves the whole cloud on its own
+    GPU (the shards are gathered over NCCL) and the sharded planes must equal it: coefficients, global inlier counts and
+    an order-independent hash of every plane's global inlier indices."""
+    from dialog_b200 import synth
+    n_total = args.config4_points
+    base = synth.indoor_scene().points(0, min(10_000_000, n_total))
+    first, count = D.host_shard_range(n_total, world, rank)
+    shard = storeys_cloud(base, first, count)
+    del base
+    pinned = torch.empty((count, 4), dtype=torch.float32, pin_memory=True)
+    pinned.numpy()[:] = shard
+    del shard
+    prm = D.make_params(0.1, args.hyps - 1, 500, 1.0, True, 12345, args.planes, D.DOT_FMA)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    pr = D.PlaneRansac(local_rank)
+    if world > 1:
+        uid = [D.PlaneRansac.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        pr.comm_init(world, rank, uid[0])
+    pr.set_cloud_ptr(pinned.data_ptr(), count)
+    ex = pr.extract_planes(prm, want_indices=True, copy=False)   # warm-up; also the result that is checked
+    pr.profile_enable(True)
+    pr.profile_reset()
+    ms = []
+    for _ in range(2):
+        pr.flush_l2()
+        barrier()
+        pr.timer_start()
+        ex = pr.extract_planes(prm, want_indices=False)
+        ms.append(pr.timer_stop())
+    barrier()
+    prof = pr.profile()
+    pr.profile_enable(False)
+    ex = pr.extract_planes(prm, want_indices=True, copy=False)
+    pairs = sum(int(i.n_cloud) * int(i.n_scored) for i in ex.infos)
+    # per-plane fingerprints of this rank's part, summed over ranks
+    P = len(ex.planes)
+    fp = np.zeros((args.planes, 2), np.int64)
+    for k, p in enumerate(ex.planes):
+        g = p.inliers_orig.astype(np.int64) + first
+        fp[k, 0] = p.inliers_orig.size
+        fp[k, 1] = _mix64(g).sum(dtype=np.uint64).astype(np.int64) if g.size else 0
+    t = torch.tensor([sum(ms)], dtype=torch.float64, device="cuda")
+    fpt = torch.from_numpy(fp).cuda()
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(fpt, op=dist.ReduceOp.SUM)
+    ms_step = t.item() / 2
+    out = {"points_total": n_total, "n_gpus": world, "planes": P, "hypotheses_per_round": args.hyps,
+           "scaling": "strong", "ms_per_extraction": ms_step, "value": pairs / (ms_step * 1e-3), "unit": UNIT,
+           "scene": "ten 10M-point indoor storeys 8 m apart (walls coplanar across storeys), contiguous index-range shards"}
+    if rank == 0:
+        score_tf = 6.0 * prof.pairs_scored / (prof.ms_score * 1e-3) / 1e12 if prof.ms_score > 0 else None
+        out["roofline"] = {"kernel": "score_kernel<8,FMA>", "bound": "fp32_fma", "achieved": score_tf, "peak": peak_tf, "unit": "TFLOP/s",
+                           "frac": score_tf / peak_tf if score_tf else None, "note": "rank 0's launches"}
+        out["roofline_hbm"] = hbm_block(prof, hbm_peak)
+        out["kernel_ms_per_extraction"] = {"models_draw": prof.ms_models / 2, "score": prof.ms_score / 2, "refit": prof.ms_refit / 2,
+                                           "compact": prof.ms_compact / 2, "other": prof.ms_other / 2}
+    # one GPU on the whole cloud (rank 0): gathered shards -> plane_ransac_set_cloud_device
+    if world > 1:
+        dev = pinned.cuda()
+        sizes = [D.host_shard_range(n_total, world, r)[1] for r in range(world)]
+        if rank == 0:
+            whole_t = torch.empty((n_total, 4), dtype=torch.float32, device="cuda")
+            parts = list(whole_t.split(sizes))
+            dist.gather(dev, parts, dst=0)
+        else:
+            dist.gather(dev, None, dst=0)
+        del dev
+        if rank == 0:
+            one = D.PlaneRansac(local_rank)
+            one.set_cloud_device_ptr(whole_t.data_ptr(), n_total)
+            del whole_t, parts
+            one.extract_planes(prm, want_indices=False)
+            one_ms = []
+            for _ in range(2):
+                one.flush_l2()
+                one.timer_start()
+                ex1 = one.extract_planes(prm, want_indices=False)
+                one_ms.append(one.timer_stop())
+            ex1 = one.extract_planes(prm, want_indices=True, copy=False)
+            same = len(ex1.planes) == P
+            got = fpt.cpu().numpy()
+            for k, p in enumerate(ex1.planes):
+                if not same:
+                    break
+                h = _mix64(p.inliers_orig.astype(np.int64)).sum(dtype=np.uint64).astype(np.int64) if p.inliers_orig.size else 0
+                same = (p.coeff.tobytes() == ex.planes[k].coeff.tobytes() and p.info.n_inliers == ex.planes[k].info.n_inliers
+                        and int(got[k, 0]) == p.inliers_orig.size and int(got[k, 1]) == int(h))
+            one.close()
+            t1 = sum(one_ms) / 2
+            out["one_gpu_ms_per_extraction"] = t1
+            out["efficiency_vs_1gpu"] = t1 / (world * ms_step)
+            out["sharded_identical_to_single_gpu"] = bool(same)
+            out["identity_check"] = "coefficients bit for bit, global inlier count and an order-independent 64-bit hash of the global inlier indices, every plane"
+        dist.barrier()
+    else:
+        out["efficiency_vs_1gpu"] = 1.0
+        out["sharded_identical_to_single_gpu"] = None
+        if not args.no_hbm_100m:
+            # one segment() + peel over the whole staged cloud (round 0: 12 B per point read), three times
+            prm1 = D.make_params(0.1, 255, 500, 1.0, True, 12345, 1, D.DOT_FMA)
+            pr.extract_planes(prm1, want_indices=False)
+            pr.profile_enable(True)
+            pr.profile_reset()
+            for _ in range(3):
+                pr.extract_planes(prm1, want_indices=False)
+            pb = pr.profile()
+            pr.profile_enable(False)
+            hb = hbm_block(pb, hbm_peak)
+            hb["compact"]["ms"] = pb.ms_compact / 3
+            hb["refit"]["ms"] = pb.ms_refit / 3
+            hb["compact"]["bytes"] = int(pb.bytes_compact // 3)
+            out["single_launch"] = hb
+    pr.close()
+    return out if rank == 0 else None
+
+
+def hbm_block(prof, hbm_peak):
+    """HBM rooflines of the peel (K5) and refit (K3) launches in a profile: bytes actually moved, and SURVEY §8d's formula."""
+    c_gbs = prof.bytes_compact / (prof.ms_compact * 1e-3) / 1e9 if prof.ms_compact > 0 else None
+    survey = 16 * prof.points_compact + 16 * prof.points_kept + 4 * prof.points_peeled
+    s_gbs = survey / (prof.ms_compact * 1e-3) / 1e9 if prof.ms_compact > 0 else None
+    r_gbs = prof.bytes_refit / (prof.ms_refit * 1e-3) / 1e9 if prof.ms_refit > 0 else None
+    return {
+        "compact": {"bound": "hbm", "achieved": c_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": c_gbs / hbm_peak if c_gbs else None,
+                    "ms": prof.ms_compact, "bytes": int(prof.bytes_compact),
+                    "algorithmic": "bytes moved: 12 B per point read (16 B once the cloud carries its original-index plane, "
+                                   "i.e. after the first peel) + 16 B per kept point + 4 B per inlier per list written",
+                    "frac_survey_8d_formula": s_gbs / hbm_peak if s_gbs else None,
+                    "survey_8d_formula": "16 N + 16 N_rem + 4 N_inl (charges an index-plane read the staged cloud does not have)"},
+        "refit": {"bound": "hbm", "achieved": r_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": r_gbs / hbm_peak if r_gbs else None,
+                  "ms": prof.ms_refit, "algorithmic": "12 B read per point"}}
+
+
 def claim_stdout():
     """Keep fd 1 for the JSON line only: libraries (NCCL prints its version banner) write to stderr instead."""
     sys.stdout.flush()
@@ -453,8 +626,6 @@ def main():
         peaks = measured_peaks()
         hbm_peak = peaks["hbm_gbs"] if peaks else 6650.0
         score_tf = 6.0 * prof.pairs_scored / (prof.ms_score * 1e-3) / 1e12 if prof.ms_score > 0 else None
-        compact_gbs = prof.bytes_compact / (prof.ms_compact * 1e-3) / 1e9 if prof.ms_compact > 0 else None
-        refit_gbs = prof.bytes_refit / (prof.ms_refit * 1e-3) / 1e9 if prof.ms_refit > 0 else None
         launches = (prof.launches_stage + prof.launches_models + prof.launches_score + prof.launches_refit +
                     prof.launches_compact + prof.launches_other)
         kernel_ms = prof.ms_models + prof.ms_score + prof.ms_refit + prof.ms_compact
@@ -478,16 +649,16 @@ def main():
                                "nominal 148 SM x 128 lanes x 2 x 1.965 GHz = 74.4)",
                 "algorithmic": "6 FLOP (3 FMA) per point-hypothesis x points x hypotheses per launch",
                 "ms_in_timed_region": prof.ms_score, "share_of_kernel_time": prof.ms_score / kernel_ms if kernel_ms else None},
-            "roofline_hbm": {
-                "compact": {"bound": "hbm", "achieved": compact_gbs, "peak": hbm_peak, "unit": "GB/s",
-                            "frac": compact_gbs / hbm_peak if compact_gbs else None, "ms": prof.ms_compact,
-                            "algorithmic": "16 B read per point + 16 B per remaining point + 8 B per inlier"},
-                "refit": {"bound": "hbm", "achieved": refit_gbs, "peak": hbm_peak, "unit": "GB/s",
-                          "frac": refit_gbs / hbm_peak if refit_gbs else None, "ms": prof.ms_refit,
-                          "algorithmic": "12 B read per point"},
-                "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)"},
-            "kernel_ms_per_step": {"models": prof.ms_models / args.steps, "score": prof.ms_score / args.steps,
-                                   "refit": prof.ms_refit / args.steps, "compact": prof.ms_compact / args.steps},
+            "roofline_hbm": dict(hbm_block(prof, hbm_peak),
+                                 peak_source="MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
+                                 note="averages over the 20 shrinking rounds of the 10M-point extraction (the later rounds are "
+                                      "launch-latency bound); single_launch_100M below is the kernel at the north-star scene size"),
+            "kernel_ms_per_step": {"models_draw": prof.ms_models / args.steps, "score": prof.ms_score / args.steps,
+                                   "refit": prof.ms_refit / args.steps, "compact": prof.ms_compact / args.steps,
+                                   "other": prof.ms_other / args.steps,
+                                   "step_minus_kernels": ms_per_step - (kernel_ms + prof.ms_other) / args.steps},
+            "round_loop": "device-resident (PR_LOOP_AUTO): draws, computeModel's decision, closed-form refit and the stop rule run "
+                          "as kernels; the host reads one record per round",
             "clocks": clock_info,
         }
         if hier_ms:
@@ -496,28 +667,19 @@ def main():
                 "unit": UNIT, "identical_planes": bool(hier_same),
                 "note": "opt-in PR_SCORER_HIER: Morton-sorted copy + per-32-point boxes, blocks outside the threshold slab "
                         "skipped, the rest evaluated with the same arithmetic; same counts, not the roofline kernel"}
-        if world == 1 and not args.no_hbm_100m:
-            # the HBM kernels at the north star's scene size: one segment + peel over 100M points (the 10M-point cloud
-            # tiled ten times), timed alone; the figures above are averages over the shrinking 10M-point rounds
-            big = np.tile(pts, (max(1, 100_000_000 // max(count, 1)), 1))
-            pr.set_cloud(big)
-            prm1 = D.make_params(0.1, 255, 500, 1.0, True, 12345, 1, D.DOT_FMA)
-            pr.extract_planes(prm1, want_indices=False)
-            pr.profile_enable(True)
-            pr.profile_reset()
-            for _ in range(3):
-                pr.extract_planes(prm1, want_indices=False)
-            pb = pr.profile()
-            pr.profile_enable(False)
-            cg = pb.bytes_compact / (pb.ms_compact * 1e-3) / 1e9 if pb.ms_compact > 0 else None
-            rg = pb.bytes_refit / (pb.ms_refit * 1e-3) / 1e9 if pb.ms_refit > 0 else None
-            line["roofline_hbm"]["single_launch_%dM_points" % (big.shape[0] // 1_000_000)] = {
-                "compact": {"achieved": cg, "frac": cg / hbm_peak if cg else None, "ms": pb.ms_compact / 3},
-                "refit": {"achieved": rg, "frac": rg / hbm_peak if rg else None, "ms": pb.ms_refit / 3},
-                "unit": "GB/s", "peak": hbm_peak}
-            del big
         if args.extras:
             line["extras"] = run_extras(args, pr)
+    # ---- BASELINE configs[3]: the 100M-point scene sharded over the N ranks, outside the headline timer ----
+    pr.close()
+    c4 = None
+    if not args.no_config4:
+        c4 = run_config4(args, torch, dist, D, local_rank, world, rank, hbm_peak if rank == 0 else None, peak_tf)
+    if rank == 0:
+        if c4 and "single_launch" in c4:
+            # the HBM kernels at the north star's scene size, one launch each, timed alone; the figures in roofline_hbm
+            # proper are averages over the shrinking 10M-point rounds
+            line["roofline_hbm"]["single_launch_%dM_points" % (c4["points_total"] // 1_000_000)] = c4.pop("single_launch")
+        line["config4_100M"] = c4
         if not args.no_cpu_baseline:
             v, dt = cpu_sample(args, pts, threads=1)
             line["cpu_baseline"] = {
@@ -526,8 +688,6 @@ def main():
                           "round 0 on rank 0's %d points" % (args.cpu_sample_hyps, count)}
         out.write(json.dumps(line) + "\n")
         out.flush()
-
-    pr.close()
     if world > 1:
         dist.destroy_process_group()
 

@@ -70,7 +70,8 @@ class PrProfile(C.Structure):
                [(n, C.c_longlong) for n in ("launches_stage", "launches_models", "launches_score", "launches_refit",
                                             "launches_compact", "launches_other", "pairs_scored", "points_refit",
                                             "points_compact", "bytes_compact", "bytes_refit")] + \
-               [(n, C.c_double) for n in ("host_ms_sampling", "host_ms_replay", "host_ms_wait", "host_ms_total")]
+               [(n, C.c_double) for n in ("host_ms_sampling", "host_ms_replay", "host_ms_wait", "host_ms_total")] + \
+               [(n, C.c_longlong) for n in ("points_kept", "points_peeled")]
 
 
 class PlaneRansacError(RuntimeError):

@@ -218,8 +218,8 @@ struct plane_ransac_ctx {
   // peel loop without the host (run_chain): device-resident round state, per-round records, the sampler's scratch
   DevBuf<pr::RoundState> d_state;
   PinBuf<pr::RoundState> h_state;
-  DevBuf<pr::RoundRecord> d_recs;
-  PinBuf<pr::RoundRecord> h_recs;
+  PinBuf<pr::RoundRecord> h_recs;  // page-locked and device-visible: the kernels write the records straight into it
+  DevBuf<unsigned> d_chain_tickets;
   std::vector<cudaEvent_t> round_ev;
   DevBuf<uint32_t> d_rnd;  // mt19937(seed) >> 1, the stream every round's draws consume
   uint32_t rnd_seed = 0;
@@ -999,6 +999,8 @@ int segment_core(plane_ransac_ctx* c, const pr_params* prm, pr::CloudView src, s
     }
   }
   c->prof.bytes_compact += compact_bytes(src, n_local, write_remaining, out->n_rem_local, out->n_inl_local, d_inl_cur != nullptr, d_inl_orig != nullptr);
+  c->prof.points_kept += write_remaining ? out->n_rem_local : 0;
+  c->prof.points_peeled += out->n_inl_local;
   std::memcpy(out->coeff, refined, sizeof(refined));
   inf.n_inliers = (int)out->n_inl_global;
   if (info) *info = inf;
@@ -1070,12 +1072,13 @@ int run_chain(plane_ransac_ctx* c, const pr_params* prm, PeelCursor& cur, float*
   const float t = pr::threshold_up(prm->distance_threshold);
   const int max_rounds = prm->max_planes - cur.planes;
   const int planes_at_start = cur.planes;
+  const bool sharded = c->comm != nullptr;
   PR_TRY(reserve_draws(c, (size_t)K, false));
   PR_TRY(reserve_small(c));
   PR_TRY(dev_reserve(c->d_state, 1));
   PR_TRY(pin_reserve(c->h_state, 1));
-  PR_TRY(dev_reserve(c->d_recs, (size_t)max_rounds));
   PR_TRY(pin_reserve(c->h_recs, (size_t)max_rounds));
+  PR_TRY(dev_reserve(c->d_chain_tickets, 4));
   while ((int)c->round_ev.size() < max_rounds) {
     cudaEvent_t e = nullptr;
     PR_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -1084,7 +1087,8 @@ int run_chain(plane_ransac_ctx* c, const pr_params* prm, PeelCursor& cur, float*
   const size_t slots = pr::draw_table_slots(K);
   PR_TRY(dev_reserve(c->d_draw_table, slots));
   PR_TRY(dev_reserve(c->d_draw_coll, (size_t)pr::kDrawCollCap + 4));
-  PR_TRY(dev_reserve(c->d_scratch, pr::compact_scratch_bytes(cur.n_local) + 64));
+  const size_t scratch_bytes = (pr::compact_scratch_bytes(cur.n_local) + 7) / 8 * 8;
+  PR_TRY(dev_reserve(c->d_scratch, scratch_bytes + 64));
   if (!c->d_rnd.p || c->rnd_seed != prm->seed || c->rnd_count < 3 * (size_t)K) {
     // the stream does not depend on the cloud: generated once per seed, staged through the (pinned) triple buffer
     PR_TRY(dev_reserve(c->d_rnd, 3 * (size_t)K));
@@ -1106,7 +1110,7 @@ int run_chain(plane_ransac_ctx* c, const pr_params* prm, PeelCursor& cur, float*
     h.best = -1;
     *c->h_state.p = h;
     PR_CUDA(cudaMemcpyAsync(rs, c->h_state.p, sizeof(h), cudaMemcpyHostToDevice, c->stream));
-    PR_CUDA(cudaMemsetAsync(c->d_recs.p, 0, (size_t)max_rounds * sizeof(pr::RoundRecord), c->stream));
+    std::memset(c->h_recs.p, 0, (size_t)max_rounds * sizeof(pr::RoundRecord));  // ran = 0 until a round's kernels say otherwise
   }
   size_t n_bound = cur.n_local;  // upper bound of this rank's cloud for the rounds queued from here on
   int launched = 0, consumed = 0;
@@ -1118,14 +1122,20 @@ int run_chain(plane_ransac_ctx* c, const pr_params* prm, PeelCursor& cur, float*
       const pr::CloudView src = r == 0 ? cur.src : c->work[(round_index - 1) & 1];
       const pr::CloudView dst = c->work[round_index & 1];
       dst_of[r] = dst;
-      pr::RoundRecord* rec = c->d_recs.p + r;
+      pr::RoundRecord* rec = c->h_recs.p + r;  // mapped host memory (unified addressing)
+      uint32_t* coll_count = c->d_draw_coll.p + pr::kDrawCollCap;
       {
-        Span sp(c, KC_MODELS, 4);
-        pr::launch_draw(c->d_rnd.p, K, rs, c->d_triples.p, c->d_draw_table.p, slots, c->d_draw_coll.p, c->d_draw_coll.p + pr::kDrawCollCap, rec, c->stream);
-        PR_TRY(exchange_samples(c, src, 0, 0, c->d_triples.p, 3 * K, c->d_sample_pts.p, rs));
-        pr::launch_models(c->d_sample_pts.p, K, c->d_hyps.p, c->d_good.p, c->stream);
+        Span sp(c, KC_MODELS, sharded ? 5 : 4);
+        pr::launch_round_prep(rs, c->d_draw_table.p, slots, coll_count, c->d_counts.p, K, c->d_refit.p, c->d_scratch.p, scratch_bytes,
+                              c->d_chain_tickets.p, c->num_sms, c->stream);
+        pr::launch_draw(c->d_rnd.p, K, rs, c->d_triples.p, c->d_draw_table.p, slots, c->d_draw_coll.p, coll_count, rec, c->stream);
+        if (sharded) {
+          PR_TRY(exchange_samples(c, src, 0, 0, c->d_triples.p, 3 * K, c->d_sample_pts.p, rs));
+          pr::launch_models(c->d_sample_pts.p, K, c->d_hyps.p, c->d_good.p, c->stream);
+        } else {
+          pr::launch_gather_models(src, c->d_triples.p, K, c->d_sample_pts.p, c->d_hyps.p, c->d_good.p, rs, c->stream);
+        }
       }
-      PR_CUDA(cudaMemsetAsync(c->d_counts.p, 0, (size_t)K * sizeof(int32_t), c->stream));
       {
         Span sp(c, KC_SCORE, 0);
         c->prof.launches_score += pr::launch_score(src, n_bound, 1, 0, c->d_hyps.p, K, t, prm->dot_order, c->d_counts.p, c->num_sms, c->stream, rs);
@@ -1135,15 +1145,23 @@ int run_chain(plane_ransac_ctx* c, const pr_params* prm, PeelCursor& cur, float*
         Span sp(c, KC_OTHER, 1);
         pr::launch_replay(c->d_counts.p, c->d_good.p, K, rs, rec, c->stream);
       }
+      // one GPU: the closed-form plane runs in the last block of the refit, the stop rule in the last tile of the peel
+      pr::ChainTail tail;
+      tail.rec = rec;
+      tail.ticket = c->d_chain_tickets.p;
+      tail.triples = c->d_triples.p;
+      tail.scale_exp = c->scale_exp;
+      tail.n_draws = K;
+      tail.min_plane = prm->min_plane_size;
       if (prm->optimize_coefficients) {
-        PR_CUDA(cudaMemsetAsync(c->d_refit.p, 0, sizeof(pr::RefitOut), c->stream));
         {
           Span sp(c, KC_REFIT, 1);
-          pr::launch_refit(src, n_bound, c->d_hyps.p, c->d_sample_pts.p, 0, t, prm->dot_order, c->scale_exp, c->d_refit.p, c->num_sms, c->stream, rs);
+          pr::launch_refit(src, n_bound, c->d_hyps.p, c->d_sample_pts.p, 0, t, prm->dot_order, c->scale_exp, c->d_refit.p, c->num_sms, c->stream, rs,
+                           sharded ? nullptr : &tail);
         }
         PR_TRY(exchange_refit(c, rs));
       }
-      {
+      if (sharded || !prm->optimize_coefficients) {
         Span sp(c, KC_OTHER, 1);
         pr::launch_finish(rs, c->d_hyps.p, c->d_triples.p, c->d_refit.p, prm->optimize_coefficients ? 1 : 0, c->scale_exp, K, rec, c->stream);
       }
@@ -1151,15 +1169,14 @@ int run_chain(plane_ransac_ctx* c, const pr_params* prm, PeelCursor& cur, float*
         Span sp(c, KC_COMPACT, 1);
         const pr::Plane4 none = {0, 0, 0, 0};
         pr::launch_compact(src, n_bound, none, t, prm->dot_order, dst, true, c->d_inl_cur.p, c->d_inl_orig.p, c->d_scratch.p, c->d_totals.p,
-                           c->stream, nullptr, rs);
+                           c->stream, nullptr, rs, sharded ? nullptr : &tail);
       }
-      PR_TRY(exchange_totals(c, rs));
-      {
+      if (sharded) {
+        PR_TRY(exchange_totals(c, rs));
         Span sp(c, KC_OTHER, 1);
         pr::launch_advance(rs, c->d_totals.p, c->n_ranks, c->rank, prm->min_plane_size, rec, c->stream);
       }
       PR_CUDA(cudaGetLastError());
-      PR_CUDA(cudaMemcpyAsync(c->h_recs.p + r, rec, sizeof(pr::RoundRecord), cudaMemcpyDeviceToHost, c->stream));
       PR_CUDA(cudaEventRecord(c->round_ev[r], c->stream));
       ++launched;
     }
@@ -1197,6 +1214,8 @@ int run_chain(plane_ransac_ctx* c, const pr_params* prm, PeelCursor& cur, float*
       }
       c->prof.points_compact += rec.n_local;
       c->prof.bytes_compact += compact_bytes(src, (size_t)rec.n_local, true, rec.n_rem_local, rec.n_inl_local, true, true);
+      c->prof.points_kept += rec.n_rem_local;
+      c->prof.points_peeled += rec.n_inl_local;
     }
     if (infos) infos[cur.planes] = inf;
     if (!rec.accepted) {
@@ -1416,7 +1435,7 @@ void plane_ransac_destroy(plane_ransac_ctx* c) {
   dev_free(c->d_p2p_aux);
   dev_free(c->d_p2p_epoch);
   pin_free(c->h_p2p_err);
-  dev_free(c->d_state); pin_free(c->h_state); dev_free(c->d_recs); pin_free(c->h_recs);
+  dev_free(c->d_state); pin_free(c->h_state); pin_free(c->h_recs); dev_free(c->d_chain_tickets);
   dev_free(c->d_rnd); dev_free(c->d_draw_table); dev_free(c->d_draw_coll);
   for (cudaEvent_t e : c->round_ev) cudaEventDestroy(e);
   if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);

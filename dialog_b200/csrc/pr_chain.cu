@@ -10,6 +10,7 @@
 // so the host queues whole rounds ahead and only reads the per-round records (pr_api.cpp run_chain).
 #include "pr_kernels.h"
 
+#include "pr_chain_dev.cuh"
 #include "pr_draw.h"
 #include "pr_math.h"
 
@@ -34,22 +35,49 @@ __global__ void __launch_bounds__(256) draw_scatter_kernel(const uint32_t* __res
     draw_scatter<DevAtomics>((uint32_t)s, rnd[s], n_points, v, table, table_mask, coll, coll_count, (uint32_t)kDrawCollCap);
 }
 
+// ---- round preparation: every buffer the round's kernels accumulate into, cleared by one launch ------------------------
+__global__ void __launch_bounds__(256) round_prep_kernel(const RoundState* __restrict__ st, unsigned long long* __restrict__ table, size_t table_slots,
+                                                         uint32_t* __restrict__ coll_count, int32_t* __restrict__ counts, int K,
+                                                         RefitOut* __restrict__ refit, unsigned long long* __restrict__ scratch,
+                                                         size_t scratch_words, unsigned* __restrict__ tickets) {
+  if (st->stop) return;
+  const size_t stride = (size_t)gridDim.x * blockDim.x, i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (size_t i = i0; i < table_slots; i += stride) table[i] = kDrawEmptySlot;
+  for (size_t i = i0; i < scratch_words; i += stride) scratch[i] = 0ull;
+  for (size_t i = i0; i < (size_t)K; i += stride) counts[i] = 0;
+  if (i0 < sizeof(RefitOut) / sizeof(long long)) reinterpret_cast<long long*>(refit)[i0] = 0;
+  if (i0 == 0) {
+    *coll_count = 0u;
+    tickets[0] = 0u;
+  }
+}
+
 // ---- sampler, sequential phase: the colliding ops, sorted by op index, replayed by one thread ------------------------------
+// Everything the replay reads is staged in shared memory first (the sorted list, v at each op and at the three ops before
+// it, the position map), so the sequential part never waits on HBM.
 constexpr int kResolveThreads = 1024;
 constexpr int kResolveMapSlots = 2 * kDrawMaxCollisions;
+constexpr size_t kResolveSmemBytes = (size_t)kDrawCollCap * 4 + (size_t)kDrawCollCap * 16 + (size_t)kResolveMapSlots * 8;
+
+struct SmemFetch {
+  const uint32_t* sorted;
+  const int32_t* pre;  // 4 per listed op: v[s], v[s - 1], v[s - 2], v[s - 3]
+  __device__ __forceinline__ int32_t operator()(int i, uint32_t idx) const { return pre[4 * i + (int)(sorted[i] - idx)]; }
+};
 
 __global__ void __launch_bounds__(kResolveThreads) draw_resolve_kernel(RoundState* st, int32_t* v, const uint32_t* __restrict__ coll,
                                                                        const uint32_t* __restrict__ coll_count, RoundRecord* rec) {
-  __shared__ uint32_t s_sorted[kDrawCollCap];
-  __shared__ uint32_t s_keys[kResolveMapSlots];
-  __shared__ int32_t s_vals[kResolveMapSlots];
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  uint32_t* s_sorted = reinterpret_cast<uint32_t*>(s_raw);
+  int32_t* s_pre = reinterpret_cast<int32_t*>(s_raw + (size_t)kDrawCollCap * 4);
+  uint32_t* s_keys = reinterpret_cast<uint32_t*>(s_raw + (size_t)kDrawCollCap * 20);
+  int32_t* s_vals = reinterpret_cast<int32_t*>(s_raw + (size_t)kDrawCollCap * 20 + (size_t)kResolveMapSlots * 4);
   __shared__ int s_distinct;
   if (st->stop) return;
   if (st->n_global < 3) {  // getSamples: "Can not select 0 unique points out of N": segment() returns no model
     if (threadIdx.x == 0) {
       st->stop = 1;
       st->best = -1;
-      rec->ran = 1;
       rec->stop = 1;
       rec->n_cloud = st->n_global;
       rec->n_local = st->n_local;
@@ -57,6 +85,8 @@ __global__ void __launch_bounds__(kResolveThreads) draw_resolve_kernel(RoundStat
       rec->n_rem_global = st->n_global;
       rec->first_after = st->first;
       rec->inl_off = st->inl_off;
+      __threadfence_system();
+      rec->ran = 1;
     }
     return;
   }
@@ -64,8 +94,9 @@ __global__ void __launch_bounds__(kResolveThreads) draw_resolve_kernel(RoundStat
   if (n_c > (uint32_t)kDrawCollCap) {  // crowded round: the sequential host sampler takes it
     if (threadIdx.x == 0) {
       st->stop = 2;
-      rec->ran = 1;
       rec->stop = 2;
+      __threadfence_system();
+      rec->ran = 1;
     }
     return;
   }
@@ -82,17 +113,23 @@ __global__ void __launch_bounds__(kResolveThreads) draw_resolve_kernel(RoundStat
     s_sorted[rank] = mine;
   }
   __syncthreads();
-  for (uint32_t i = threadIdx.x; i < n_c; i += kResolveThreads)
-    if (i == 0 || s_sorted[i] != s_sorted[i - 1]) atomicAdd(&s_distinct, 1);
+  for (uint32_t i = threadIdx.x; i < n_c; i += kResolveThreads) {
+    const uint32_t s = s_sorted[i];
+    if (i == 0 || s != s_sorted[i - 1]) atomicAdd(&s_distinct, 1);
+#pragma unroll
+    for (uint32_t k = 0; k < 4; ++k) s_pre[4 * i + k] = s >= k ? v[s - k] : 0;
+  }
   __syncthreads();
   if (threadIdx.x != 0) return;
   if (s_distinct > kDrawMaxCollisions) {
     st->stop = 2;
-    rec->ran = 1;
     rec->stop = 2;
+    __threadfence_system();
+    rec->ran = 1;
     return;
   }
-  draw_resolve(s_sorted, (int)n_c, v, s_keys, s_vals, (uint32_t)(kResolveMapSlots - 1));
+  SmemFetch fetch{s_sorted, s_pre};
+  draw_resolve(s_sorted, (int)n_c, v, fetch, s_keys, s_vals, (uint32_t)(kResolveMapSlots - 1));
 }
 
 // ---- RandomSampleConsensus::computeModel over the K counts of a score-all round ------------------------------------------
@@ -124,86 +161,46 @@ __global__ void __launch_bounds__(kReplayThreads) replay_kernel(const int32_t* _
   for (int w = 1; w < kReplayThreads / 32; ++w) best = s_best[w] > best ? s_best[w] : best;
   if (!all_good) {
     st->stop = 2;
-    rec->ran = 1;
     rec->stop = 2;
+    __threadfence_system();
+    rec->ran = 1;
     return;
   }
   st->best = (int)(0xFFFFFFFFu - (unsigned)(best & 0xFFFFFFFFull));
   st->best_count = (int)(best >> 32);
 }
 
-// ---- refined plane of the round (PCL optimizeModelCoefficients) + the round's record ----------------------------------
+// ---- refined plane + stop rule as their own kernels (sharded clouds: an exchange sits between them and K3 / K5; on one
+// GPU they run in the last block of refit_kernel / compact_kernel instead) ---------------------------------------------
 __global__ void finish_kernel(RoundState* st, const float4* __restrict__ hyps, const int32_t* __restrict__ triples,
                               const RefitOut* __restrict__ refit, int optimize, int scale_exp, int n_draws, RoundRecord* rec) {
   if (threadIdx.x != 0 || st->stop) return;
-  const int best = st->best;
-  const float4 raw = hyps[best];
-  float refined[4] = {raw.x, raw.y, raw.z, raw.w};
-  if (optimize) {
-    long long m[16];
-    for (int i = 0; i < 16; ++i) m[i] = refit->m[i];
-    const float pivot[3] = {refit->pivot[0], refit->pivot[1], refit->pivot[2]};
-    pm_plane_from_moments(m, pivot, scale_exp, refined);  // < 4 inliers: keeps the sample's model
-  }
-  for (int i = 0; i < 4; ++i) st->plane[i] = refined[i];
-  rec->ok = 1;
-  rec->best = best;
-  rec->best_count = st->best_count;
-  for (int i = 0; i < 3; ++i) rec->best_sample[i] = triples[3 * best + i];
-  rec->n_draws = n_draws;
-  rec->raw[0] = raw.x; rec->raw[1] = raw.y; rec->raw[2] = raw.z; rec->raw[3] = raw.w;
-  for (int i = 0; i < 4; ++i) rec->refined[i] = refined[i];
+  long long m[16];
+  for (int i = 0; i < 16; ++i) m[i] = refit->m[i];
+  const float pivot[3] = {refit->pivot[0], refit->pivot[1], refit->pivot[2]};
+  chain_finish(st, hyps, triples, m, pivot, optimize, scale_exp, n_draws, rec);
 }
 
-// ---- the peel's stop rule and the next round's sizes -------------------------------------------------------------------
-// totals: [0] points left / [1] inliers peeled on this rank; sharded: [2 + 2r], [3 + 2r] the same for every rank r.
 __global__ void advance_kernel(RoundState* st, const long long* __restrict__ totals, int n_ranks, int rank, int min_plane,
                                RoundRecord* rec) {
   if (threadIdx.x != 0 || st->stop) return;
-  const long long rem_local = totals[0], inl_local = totals[1];
-  long long rem_global = rem_local, inl_global = inl_local, first_after = 0;
-  if (n_ranks > 1) {
-    rem_global = 0;
-    inl_global = 0;
-    for (int r = 0; r < n_ranks; ++r) {
-      if (r == rank) first_after = rem_global;
-      rem_global += totals[2 + 2 * r];
-      inl_global += totals[3 + 2 * r];
-    }
-  }
-  rec->ran = 1;
-  rec->n_cloud = st->n_global;
-  rec->n_local = st->n_local;
-  rec->n_inl_local = inl_local;
-  rec->n_rem_local = rem_local;
-  rec->n_inl_global = inl_global;
-  rec->n_rem_global = rem_global;
-  rec->first_after = first_after;
-  rec->inl_off = st->inl_off;
-  const long long need = min_plane > 0 ? (long long)min_plane : 0ll;
-  const bool accepted = !(inl_global == 0 || inl_global < need);
-  rec->accepted = accepted ? 1 : 0;
-  if (accepted) {
-    st->inl_off += inl_local;
-    st->n_local = rem_local;
-    st->n_global = rem_global;
-    st->first = first_after;
-    st->round += 1;
-  } else {
-    st->stop = 1;
-  }
-  rec->stop = st->stop;
+  chain_advance(st, totals, n_ranks, rank, min_plane, rec);
+}
+
+void launch_round_prep(const RoundState* st, unsigned long long* table, size_t table_slots, uint32_t* coll_count, int32_t* counts, int K,
+                       RefitOut* refit, void* scratch, size_t scratch_bytes, unsigned* tickets, int num_sms, cudaStream_t s) {
+  round_prep_kernel<<<num_sms * 2, 256, 0, s>>>(st, table, table_slots, coll_count, counts, K, refit,
+                                               reinterpret_cast<unsigned long long*>(scratch), scratch_bytes / 8, tickets);
 }
 
 void launch_draw(const uint32_t* rnd, int n_draws, RoundState* st, int32_t* triples, unsigned long long* table, size_t table_slots,
                  uint32_t* coll, uint32_t* coll_count, RoundRecord* rec, cudaStream_t s) {
   const int n_ops = 3 * n_draws;
-  cudaMemsetAsync(table, 0xFF, table_slots * sizeof(unsigned long long), s);
-  cudaMemsetAsync(coll_count, 0, sizeof(uint32_t), s);
   int blocks = (n_ops + 255) / 256;
   if (blocks > 148 * 4) blocks = 148 * 4;
   draw_scatter_kernel<<<blocks, 256, 0, s>>>(rnd, n_ops, st, triples, table, (uint32_t)(table_slots - 1), coll, coll_count);
-  draw_resolve_kernel<<<1, kResolveThreads, 0, s>>>(st, triples, coll, coll_count, rec);
+  cudaFuncSetAttribute(draw_resolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kResolveSmemBytes);  // per device: cheap, unconditional
+  draw_resolve_kernel<<<1, kResolveThreads, kResolveSmemBytes, s>>>(st, triples, coll, coll_count, rec);
 }
 
 size_t draw_table_slots(int n_draws) {

@@ -34,35 +34,48 @@ PR_HD uint32_t draw_position(uint32_t s, uint32_t rnd, uint32_t n_points) {
 
 PR_HD uint32_t draw_hash(uint32_t q) { return (q * 2654435761u) >> 5; }
 
-// Content of head position p (0..2) just before op s: the later of the last swap that had p as its first operand
-// (every third op; it left v there) and the last recorded swap of another head position with p.
-PR_HD int32_t draw_head_before(uint32_t p, uint32_t s, const int32_t* v, const long long hw_time[3], const int32_t hw_val[3]) {
-  const uint32_t d = (s % 3u + 3u - p) % 3u;
-  const long long ua = (long long)s - (d == 0 ? 3 : (long long)d);  // last op before s with a == p (negative: none)
-  const long long tb = hw_time[p];
-  if (tb >= 0 && tb > ua) return hw_val[p];
-  if (ua >= 0) return v[ua];
-  return (int32_t)p;
-}
-
 // Sequential replay of the collected ops (ascending s, duplicates allowed).  v[s] holds b_s on entry for every op and
-// the exact v_s on return.  map_*: open-addressing scratch with map_mask + 1 >= 2 * n_ops slots, keys preset to
-// kDrawNoOp.
-PR_HD void draw_resolve(const uint32_t* ops_sorted, int n_ops, int32_t* v, uint32_t* map_keys, int32_t* map_vals,
+// the exact v_s on return.  The replay of op s reads v at s and at up to three earlier ops (s - 1, s - 2, s - 3: the last
+// swaps of the head positions); fetch(i, idx) supplies those values as they were BEFORE the replay (i = position in
+// ops_sorted; the kernel prefetches them into shared memory in parallel, the host reads v), and the three most
+// recently replayed ops are kept in registers because their values have changed since.  map_*: open-addressing
+// scratch with map_mask + 1 >= 2 * n_ops slots, keys preset to kDrawNoOp.
+template <class Fetch>
+PR_HD void draw_resolve(const uint32_t* ops_sorted, int n_ops, int32_t* v, Fetch fetch, uint32_t* map_keys, int32_t* map_vals,
                         uint32_t map_mask) {
-  long long hw_time[3] = {-1, -1, -1};
+  long long hw_time[3] = {-1, -1, -1};  // last swap of ANOTHER head position with head position p, and what it left there
   int32_t hw_val[3] = {0, 0, 0};
+  long long done_s[3] = {-1, -1, -1};   // the three most recently replayed ops
+  int32_t done_v[3] = {0, 0, 0};
   uint32_t prev = kDrawNoOp;
   for (int i = 0; i < n_ops; ++i) {
     const uint32_t s = ops_sorted[i];
     if (s == prev) continue;
     prev = s;
     const uint32_t a = s % 3u;
-    const uint32_t q = (uint32_t)v[s];  // still b_s: every op is replayed once
-    const int32_t w = draw_head_before(a, s, v, hw_time, hw_val);
+    const uint32_t q = (uint32_t)fetch(i, s);  // b_s: every op is replayed once
+    // content of head position p just before op s: the later of the last op that had p as its first operand (every
+    // third op; it left its v there) and the last recorded swap of another head position with p
+    int32_t head[3];
+#pragma unroll
+    for (uint32_t p = 0; p < 3u; ++p) {
+      const uint32_t d = (s % 3u + 3u - p) % 3u;
+      const long long ua = (long long)s - (d == 0 ? 3 : (long long)d);  // negative: no such op yet
+      int32_t val = (int32_t)p;
+      if (hw_time[p] >= 0 && hw_time[p] > ua) {
+        val = hw_val[p];
+      } else if (ua >= 0) {
+        val = fetch(i, (uint32_t)ua);
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+          if (done_s[k] == ua) val = done_v[k];
+      }
+      head[p] = val;
+    }
+    const int32_t w = head[a];
     int32_t val;
     if (q < 3u) {
-      val = draw_head_before(q, s, v, hw_time, hw_val);
+      val = head[q];
       if (q != a) {
         hw_time[q] = (long long)s;
         hw_val[q] = w;
@@ -75,6 +88,9 @@ PR_HD void draw_resolve(const uint32_t* ops_sorted, int n_ops, int32_t* v, uint3
       map_vals[h] = w;
     }
     v[s] = val;
+    done_s[2] = done_s[1]; done_v[2] = done_v[1];
+    done_s[1] = done_s[0]; done_v[1] = done_v[0];
+    done_s[0] = (long long)s; done_v[0] = val;
   }
 }
 

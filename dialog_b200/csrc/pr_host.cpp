@@ -192,7 +192,7 @@ bool draw_triples_parallel(size_t n_points, uint32_t seed, int n_draws, int32_t*
   while (map_cap < 2 * distinct) map_cap <<= 1;
   std::vector<uint32_t> mk(map_cap, kDrawNoOp);
   std::vector<int32_t> mv(map_cap, 0);
-  draw_resolve(coll.data(), (int)distinct, triples, mk.data(), mv.data(), map_cap - 1);
+  draw_resolve(coll.data(), (int)distinct, triples, [triples](int, uint32_t idx) { return triples[idx]; }, mk.data(), mv.data(), map_cap - 1);
   return true;
 }
 

@@ -17,6 +17,8 @@
 
 #include <math_constants.h>
 
+#include "pr_chain_dev.cuh"
+
 #include <cstdlib>
 #include <cub/device/device_radix_sort.cuh>
 
@@ -341,11 +343,7 @@ __global__ void __launch_bounds__(256) gather_samples_kernel(const float* __rest
 
 // PCL SampleConsensusModelPlane::isSampleGood + computeModelCoefficients (sac_model_plane.hpp), FP32,
 // every operation rounded on its own; reductions in Eigen's SSE2 order (e0 + e2) + (e1 + e3).
-__global__ void __launch_bounds__(128) models_kernel(const int4* __restrict__ sample_pts, int n_models,
-                                                     float4* __restrict__ hyps, int32_t* __restrict__ good) {
-  int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= n_models) return;
-  int4 q0 = sample_pts[3 * k], q1 = sample_pts[3 * k + 1], q2 = sample_pts[3 * k + 2];
+__device__ __forceinline__ bool model_from_sample(int4 q0, int4 q1, int4 q2, float4* out) {
   float p0x = __int_as_float(q0.x), p0y = __int_as_float(q0.y), p0z = __int_as_float(q0.z);
   float ux = __fsub_rn(__int_as_float(q1.x), p0x), uy = __fsub_rn(__int_as_float(q1.y), p0y),
         uz = __fsub_rn(__int_as_float(q1.z), p0z);
@@ -366,8 +364,48 @@ __global__ void __launch_bounds__(128) models_kernel(const int4* __restrict__ sa
     float dot = __fadd_rn(__fadd_rn(__fmul_rn(nx, p0x), __fmul_rn(nz, p0z)), __fadd_rn(__fmul_rn(ny, p0y), 0.0f));
     h = make_float4(nx, ny, nz, __fmul_rn(-1.0f, dot));
   }
+  *out = h;
+  return ok;
+}
+
+__global__ void __launch_bounds__(128) models_kernel(const int4* __restrict__ sample_pts, int n_models,
+                                                     float4* __restrict__ hyps, int32_t* __restrict__ good) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n_models) return;
+  float4 h;
+  const bool ok = model_from_sample(sample_pts[3 * k], sample_pts[3 * k + 1], sample_pts[3 * k + 2], &h);
   hyps[k] = h;
   good[k] = ok ? 1 : 0;
+}
+
+// K1a + K1b in one launch for a cloud on one GPU driven by the device-resident round state: every thread gathers its
+// three sample points (kept in sample_pts: the refit takes its pivot from there) and forms the model.
+__global__ void __launch_bounds__(128) gather_models_kernel(const float* __restrict__ x, const float* __restrict__ y,
+                                                            const float* __restrict__ z, const int32_t* __restrict__ triples,
+                                                            int n_models, int4* __restrict__ sample_pts, float4* __restrict__ hyps,
+                                                            int32_t* __restrict__ good, const RoundState* __restrict__ st) {
+  if (st->stop) return;
+  const long long n = st->n_local;
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n_models) return;
+  int4 q[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const long long j = (long long)triples[3 * k + i];
+    q[i] = make_int4(0, 0, 0, 0);
+    if (j >= 0 && j < n) q[i] = make_int4(__float_as_int(x[j]), __float_as_int(y[j]), __float_as_int(z[j]), 0x3F800000);
+    sample_pts[3 * k + i] = q[i];
+  }
+  float4 h;
+  const bool ok = model_from_sample(q[0], q[1], q[2], &h);
+  hyps[k] = h;
+  good[k] = ok ? 1 : 0;
+}
+
+void launch_gather_models(CloudView cloud, const int32_t* triples, int n_models, int4* sample_pts, float4* hyps, int32_t* good,
+                          const RoundState* st, cudaStream_t s) {
+  if (n_models <= 0) return;
+  gather_models_kernel<<<(n_models + 127) / 128, 128, 0, s>>>(cloud.x, cloud.y, cloud.z, triples, n_models, sample_pts, hyps, good, st);
 }
 
 void launch_gather_samples(CloudView cloud, long long first, size_t n, const int32_t* triples, int n_samples,
@@ -646,7 +684,7 @@ static void launch_score_h(const float* X, const float* Y, const float* Z, size_
     gx = (total_items + items_per_cta - 1) / items_per_cta;
   }
   dim3 grid(gx, n_chunks);
-  static const int unroll = [] { const char* e = getenv("PR_SCORE_UNROLL"); return e ? atoi(e) : 2; }();  // tuning knob (H = 8, FMA order)
+  static const int unroll = [] { const char* e = getenv("PR_SCORE_UNROLL"); return e ? atoi(e) : 8; }();  // tuning knob (H = 8, FMA order): 8 measured best (60.4 % vs 59.2 % at 2)
 #define PR_SCORE(HH, D, U)                                                                                                   \
   score_kernel<HH, D, U><<<grid, kScoreThreads, 0, s>>>(X, Y, Z, cloud_stride, tiles_per_cloud, total_items, items_per_cta, \
                                                         pts_per_cta, n_padded, hyps, K, k_begin, k_end, t, counts, warps_h, st)
@@ -1088,7 +1126,7 @@ __global__ void __launch_bounds__(256, 4) refit_kernel(const float* __restrict__
                                                        const float4* __restrict__ hyps, const int4* __restrict__ sample_pts,
                                                        int model_index, float t, double scale, RefitOut* __restrict__ out,
                                                        size_t cloud_stride, int K, const int32_t* __restrict__ model_idx_arr,
-                                                       const double* __restrict__ scale_arr, const RoundState* __restrict__ st) {
+                                                       const double* __restrict__ scale_arr, RoundState* st, ChainTail tail) {
   if (st != nullptr) {  // peel loop without the host: size and winning draw of this round live on the device
     if (st->stop || st->best < 0) return;
     n = (size_t)st->n_local;
@@ -1182,20 +1220,38 @@ __global__ void __launch_bounds__(256, 4) refit_kernel(const float* __restrict__
     out->pivot[2] = __int_as_float(pv.z);
     out->pivot[3] = 0.0f;
   }
+  if (tail.rec != nullptr) {
+    // one GPU, host-free loop: the last block to finish turns the summed moments into the round's plane
+    __shared__ bool s_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(tail.ticket, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (s_last && threadIdx.x == 0) {
+      __threadfence();
+      long long m[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) m[i] = __ldcg(&out->m[i]);
+      const float pivot[3] = {__int_as_float(pv.x), __int_as_float(pv.y), __int_as_float(pv.z)};
+      chain_finish(st, hyps, tail.triples, m, pivot, 1, tail.scale_exp, tail.n_draws, tail.rec);
+    }
+  }
 }
 
 void launch_refit(CloudView cloud, size_t n, const float4* hyps, const int4* sample_pts, int model_index, float t,
-                  int dot_order, int scale_exp, RefitOut* out, int num_sms, cudaStream_t s, const RoundState* st) {
+                  int dot_order, int scale_exp, RefitOut* out, int num_sms, cudaStream_t s, RoundState* st, const ChainTail* tail) {
   const double scale = ldexp(1.0, scale_exp);
+  ChainTail tl;
+  if (tail) tl = *tail;
   size_t nvec = (n + 3) / 4;
   size_t blocks = (nvec + 255) / 256;
   // one wave exactly: 4 resident CTAs per SM (launch bounds), grid-stride over the cloud
   if (blocks > (size_t)num_sms * 4) blocks = (size_t)num_sms * 4;
   if (blocks < 1) blocks = 1;
   if (dot_order == 1)
-    refit_kernel<1><<<(unsigned)blocks, 256, 0, s>>>(cloud.x, cloud.y, cloud.z, n, hyps, sample_pts, model_index, t, scale, out, 0, 0, nullptr, nullptr, st);
+    refit_kernel<1><<<(unsigned)blocks, 256, 0, s>>>(cloud.x, cloud.y, cloud.z, n, hyps, sample_pts, model_index, t, scale, out, 0, 0, nullptr, nullptr, st, tl);
   else
-    refit_kernel<0><<<(unsigned)blocks, 256, 0, s>>>(cloud.x, cloud.y, cloud.z, n, hyps, sample_pts, model_index, t, scale, out, 0, 0, nullptr, nullptr, st);
+    refit_kernel<0><<<(unsigned)blocks, 256, 0, s>>>(cloud.x, cloud.y, cloud.z, n, hyps, sample_pts, model_index, t, scale, out, 0, 0, nullptr, nullptr, st, tl);
 }
 
 void launch_refit_batch(CloudView clouds, size_t n_per, size_t cloud_stride, int n_clouds, const float4* hyps,
@@ -1208,9 +1264,9 @@ void launch_refit_batch(CloudView clouds, size_t n_per, size_t cloud_stride, int
   if (bx < 1) bx = 1;
   dim3 grid(bx, (unsigned)n_clouds);
   if (dot_order == 1)
-    refit_kernel<1><<<grid, 256, 0, s>>>(clouds.x, clouds.y, clouds.z, n_per, hyps, sample_pts, 0, t, 1.0, outs, cloud_stride, K, model_idx, scales, nullptr);
+    refit_kernel<1><<<grid, 256, 0, s>>>(clouds.x, clouds.y, clouds.z, n_per, hyps, sample_pts, 0, t, 1.0, outs, cloud_stride, K, model_idx, scales, nullptr, ChainTail());
   else
-    refit_kernel<0><<<grid, 256, 0, s>>>(clouds.x, clouds.y, clouds.z, n_per, hyps, sample_pts, 0, t, 1.0, outs, cloud_stride, K, model_idx, scales, nullptr);
+    refit_kernel<0><<<grid, 256, 0, s>>>(clouds.x, clouds.y, clouds.z, n_per, hyps, sample_pts, 0, t, 1.0, outs, cloud_stride, K, model_idx, scales, nullptr, ChainTail());
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1238,7 +1294,7 @@ __global__ void __launch_bounds__(kCompactThreads, 5)
                    float* __restrict__ DY, float* __restrict__ DZ, int32_t* __restrict__ DO, size_t dst_cap,
                    int32_t* __restrict__ inl_cur, int32_t* __restrict__ inl_orig, unsigned long long* tile_state,
                    unsigned* ticket, long long* __restrict__ totals, const uint32_t* __restrict__ flags,
-                   const RoundState* __restrict__ st) {
+                   RoundState* st, ChainTail tail) {
   __shared__ __align__(16) float s_x[kCompactTile];
   __shared__ __align__(16) float s_y[kCompactTile];
   __shared__ __align__(16) float s_z[kCompactTile];
@@ -1264,7 +1320,11 @@ __global__ void __launch_bounds__(kCompactThreads, 5)
   const unsigned tile = s_tile;
   if (n_tiles == 0) {  // empty cloud (a shard whose points were all peeled): totals and padding only
     if (tile == 0) {
-      if (threadIdx.x == 0) { totals[0] = 0; totals[1] = 0; }
+      if (threadIdx.x == 0) {
+        totals[0] = 0;
+        totals[1] = 0;
+        if (tail.rec != nullptr) chain_advance(st, totals, 1, 0, tail.min_plane, tail.rec);
+      }
       if (WRITE_REM) {
         size_t pad_end = kTilePoints;
         if (pad_end > dst_cap) pad_end = dst_cap;
@@ -1439,6 +1499,10 @@ __global__ void __launch_bounds__(kCompactThreads, 5)
     if (threadIdx.x == 0) {
       totals[0] = total_keep;
       totals[1] = (long long)n - total_keep;
+      // one GPU, host-free loop: the stop rule and the next round's sizes.  Every CTA that owns a tile read the state
+      // before it took its ticket, i.e. before this (last) tile could complete its look-back; surplus CTAs that start
+      // later see a smaller cloud or the stop flag and leave either way.
+      if (tail.rec != nullptr) chain_advance(st, totals, 1, 0, tail.min_plane, tail.rec);
     }
     if (WRITE_REM) {
       size_t pad_end = ((size_t)total_keep + kTilePoints - 1) / kTilePoints * kTilePoints + kTilePoints;
@@ -1459,20 +1523,22 @@ size_t compact_scratch_bytes(size_t n) {
 
 void launch_compact(CloudView src, size_t n, Plane4 plane, float t, int dot_order, CloudView dst, bool write_remaining,
                     int32_t* inl_cur, int32_t* inl_orig, void* scratch, long long* totals, cudaStream_t s, const uint32_t* flags,
-                    const RoundState* st) {
+                    RoundState* st, const ChainTail* tail) {
   if (n == 0 && st == nullptr) {
     cudaMemsetAsync(totals, 0, 2 * sizeof(long long), s);
     return;
   }
   unsigned n_tiles = (unsigned)((n + kCompactTile - 1) / kCompactTile);
   if (n_tiles == 0) n_tiles = 1;  // st mode: one CTA writes the totals and the padding of an empty shard
-  cudaMemsetAsync(scratch, 0, compact_scratch_bytes(n), s);
+  if (st == nullptr) cudaMemsetAsync(scratch, 0, compact_scratch_bytes(n), s);  // st mode: cleared by the round's prep kernel
+  ChainTail tl;
+  if (tail) tl = *tail;
   unsigned long long* tile_state = reinterpret_cast<unsigned long long*>(scratch);
   unsigned* ticket = reinterpret_cast<unsigned*>(tile_state + (n + kCompactTile - 1) / kCompactTile);
 #define PR_COMPACT(D, W)                                                                                              \
   compact_kernel<D, W><<<n_tiles, kCompactThreads, 0, s>>>(src.x, src.y, src.z, src.orig, n, plane, t, dst.x, dst.y,  \
                                                            dst.z, dst.orig, dst.cap, inl_cur, inl_orig, tile_state,   \
-                                                           ticket, totals, flags, st)
+                                                           ticket, totals, flags, st, tl)
   if (dot_order == 3) {
     PR_COMPACT(3, true);
   } else if (dot_order == 2) {

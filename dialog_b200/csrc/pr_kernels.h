@@ -67,6 +67,16 @@ struct RoundRecord {
   long long inl_off;                      // where this round's inlier lists start (this rank)
 };
 
+// On one GPU the last block of K3 / K5 also runs the step that follows it in the host-free loop (closed-form plane /
+// stop rule), see pr_chain_dev.cuh; rec == nullptr: plain kernel.
+struct ChainTail {
+  RoundRecord* rec = nullptr;
+  unsigned* ticket = nullptr;         // K3: blocks-done counter, zeroed by the round's prep kernel
+  const int32_t* triples = nullptr;   // K3: the round's index triples (for the record)
+  int scale_exp = 0, n_draws = 0;     // K3
+  int min_plane = 0;                  // K5
+};
+
 // K0: AoS pr_point[n] -> planes (NaN padded to cap) + bounding box of the finite points.
 // bbox: 6 x uint32 ordered-float encodings {min x,y,z, max x,y,z}; must be initialised by bbox_init.
 void launch_bbox_init(uint32_t* bbox, cudaStream_t s);
@@ -93,6 +103,10 @@ void launch_unstage(CloudView src, size_t n, float4* aos, cudaStream_t s);
 void launch_gather_samples(CloudView cloud, long long first, size_t n, const int32_t* triples, int n_samples,
                            int4* sample_pts, int n_clouds, size_t cloud_stride, cudaStream_t s,
                            bool per_cloud_triples = false, const RoundState* st = nullptr);
+// K1a + K1b in one launch (one GPU, host-free loop): gathers the three sample points of every triple from the cloud of
+// st->n_local points into sample_pts and forms the models.
+void launch_gather_models(CloudView cloud, const int32_t* triples, int n_models, int4* sample_pts, float4* hyps, int32_t* good,
+                          const RoundState* st, cudaStream_t s);
 // K1b: plane through each sample triple, PCL op order, no contraction; NaN plane + good = 0 when degenerate.
 void launch_models(const int4* sample_pts, int n_models_total, float4* hyps, int32_t* good, cudaStream_t s);
 
@@ -116,7 +130,8 @@ int launch_score_hier(CloudView sorted, size_t n, const float4* bounds, const fl
 // out must be zeroed.  sample_pts supplies the pivot (sample_pts[3 * model_index]).
 // st: n = st->n_local and model_index = st->best are read on the device (n is then an upper bound for the grid).
 void launch_refit(CloudView cloud, size_t n, const float4* hyps, const int4* sample_pts, int model_index, float t,
-                  int dot_order, int scale_exp, RefitOut* out, int num_sms, cudaStream_t s, const RoundState* st = nullptr);
+                  int dot_order, int scale_exp, RefitOut* out, int num_sms, cudaStream_t s, RoundState* st = nullptr,
+                  const ChainTail* tail = nullptr);
 
 // K3 for a batch: cloud c refits hypothesis c * K + model_idx[c] (skipped when negative) with scale 2^s_c.
 void launch_refit_batch(CloudView clouds, size_t n_per, size_t cloud_stride, int n_clouds, const float4* hyps,
@@ -133,7 +148,7 @@ size_t compact_scratch_bytes(size_t n);
 // bound for the grid and the scratch size).
 void launch_compact(CloudView src, size_t n, Plane4 plane, float t, int dot_order, CloudView dst, bool write_remaining,
                     int32_t* inl_cur, int32_t* inl_orig, void* scratch, long long* totals, cudaStream_t s,
-                    const uint32_t* flags = nullptr, const RoundState* st = nullptr);
+                    const uint32_t* flags = nullptr, RoundState* st = nullptr, const ChainTail* tail = nullptr);
 
 // Re-absorption pass of the reference's postProcessPlanes (pr_reabsorb.cu).
 struct ReabsorbPlane {
@@ -215,6 +230,10 @@ void launch_p2p_samples(const P2PView& v, CloudView cloud, long long first, size
 // table = draw_table_slots(n_draws) uint64 of scratch, coll = kDrawCollCap uint32 + coll_count.  Sets st->stop = 2 when
 // the round has to go back to the sequential host sampler, 1 when the cloud has fewer than 3 points.
 size_t draw_table_slots(int n_draws);
+// One launch clears everything a round accumulates into: the sampler's table and collision count, the K counts, the
+// refit moments, the compaction descriptors (scratch) and the blocks-done ticket.
+void launch_round_prep(const RoundState* st, unsigned long long* table, size_t table_slots, uint32_t* coll_count, int32_t* counts, int K,
+                       RefitOut* refit, void* scratch, size_t scratch_bytes, unsigned* tickets, int num_sms, cudaStream_t s);
 void launch_draw(const uint32_t* rnd, int n_draws, RoundState* st, int32_t* triples, unsigned long long* table, size_t table_slots,
                  uint32_t* coll, uint32_t* coll_count, RoundRecord* rec, cudaStream_t s);
 // computeModel's decision over K counts (score-all mode): st->best / best_count, or st->stop = 2 when a bad sample means

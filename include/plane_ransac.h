@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define PLANE_RANSAC_ABI_VERSION 2
+#define PLANE_RANSAC_ABI_VERSION 3
 
 typedef struct plane_ransac_ctx plane_ransac_ctx;
 
@@ -101,13 +101,18 @@ typedef struct {
   long long pairs_scored;    /* sum of points x hypotheses over score launches (this rank)      */
   long long points_refit;    /* points streamed by refit launches                               */
   long long points_compact;  /* points streamed by compaction launches                          */
-  long long bytes_compact;   /* algorithmic bytes of compaction launches (read + written)       */
+  long long bytes_compact;   /* bytes compaction launches move: 12 B per point read (16 B when the cloud carries an
+                                original-index plane, i.e. after the first peel), 16 B per kept point, 4 B per
+                                inlier and list written                                           */
   long long bytes_refit;     /* algorithmic bytes of refit launches                             */
   /* host wall time inside segment/extract calls, by phase (always accumulated) */
   double host_ms_sampling;   /* drawing PCL's index triples                                     */
   double host_ms_replay;     /* replaying RANSAC's sequential decisions + plane from moments    */
   double host_ms_wait;       /* blocked in stream synchronisation (device work + copies)        */
   double host_ms_total;      /* whole calls                                                     */
+  /* peel launches of segment / extract calls (ABI 3): what the compaction kept and what it peeled off */
+  long long points_kept;     /* points written to the remaining cloud                           */
+  long long points_peeled;   /* inliers written to the index lists                              */
 } pr_profile;
 
 /* ---- lifetime ---------------------------------------------------------------------------- */

@@ -29,7 +29,7 @@ def test_header_symbols_are_exported(lib_built):
 def test_abi_version_and_defaults(lib_built):
     from dialog_b200 import _lib
     L = _lib.load()
-    assert L.plane_ransac_abi_version() == 2
+    assert L.plane_ransac_abi_version() == 3
     p = _lib.PrParams()
     L.plane_ransac_default_params(ctypes.byref(p))
     # Dialog/config.txt:29 T_dist_point_plane, :20 T_num_of_single_plane; PCL SACSegmentation defaults
