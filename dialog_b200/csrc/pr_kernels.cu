@@ -691,6 +691,8 @@ static void launch_score_h(const float* X, const float* Y, const float* Z, size_
   if (dot_order == 1) {
     if (H == 8 && unroll == 4) PR_SCORE(8, 1, 4);
     else if (H == 8 && unroll == 8) PR_SCORE(8, 1, 8);
+    else if (H == 8 && unroll == 16) PR_SCORE(8, 1, 16);
+    else if (H == 8 && unroll == 32) PR_SCORE(8, 1, 32);
     else PR_SCORE(H, 1, 2);
   } else {
     PR_SCORE(H, 0, 2);
