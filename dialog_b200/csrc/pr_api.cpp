@@ -2333,6 +2333,23 @@ int plane_ransac_host_free(void* p) {
   return PR_OK;
 }
 
+int plane_ransac_host_register(void* p, size_t bytes) {
+  if (!p || !bytes) return fail(PR_ERR_INVALID, "null or empty range");
+  if (cudaHostRegister(p, bytes, cudaHostRegisterPortable) != cudaSuccess) {
+    const cudaError_t e = cudaGetLastError();
+    return fail(PR_ERR_CUDA, "cudaHostRegister of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+  }
+  return PR_OK;
+}
+
+int plane_ransac_host_unregister(void* p) {
+  if (p && cudaHostUnregister(p) != cudaSuccess) {
+    cudaGetLastError();
+    return fail(PR_ERR_CUDA, "cudaHostUnregister failed");
+  }
+  return PR_OK;
+}
+
 // ---- measurement ----------------------------------------------------------------------------------
 int plane_ransac_profile_enable(plane_ransac_ctx* c, int on) {
   PR_TRY(check_ctx(c));

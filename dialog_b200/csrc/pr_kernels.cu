@@ -684,7 +684,7 @@ static void launch_score_h(const float* X, const float* Y, const float* Z, size_
     gx = (total_items + items_per_cta - 1) / items_per_cta;
   }
   dim3 grid(gx, n_chunks);
-  static const int unroll = [] { const char* e = getenv("PR_SCORE_UNROLL"); return e ? atoi(e) : 8; }();  // tuning knob (H = 8, FMA order): 8 measured best (60.4 % vs 59.2 % at 2)
+  static const int unroll = [] { const char* e = getenv("PR_SCORE_UNROLL"); return e ? atoi(e) : 16; }();  // tuning knob (H = 8, FMA order): % of FP32 peak at N = 10M, K = 4096: 59.2 (2), 60.3 (8), 61.0 (16), 50.9 (32: instruction cache)
 #define PR_SCORE(HH, D, U)                                                                                                   \
   score_kernel<HH, D, U><<<grid, kScoreThreads, 0, s>>>(X, Y, Z, cloud_stride, tiles_per_cloud, total_items, items_per_cta, \
                                                         pts_per_cta, n_padded, hyps, K, k_begin, k_end, t, counts, warps_h, st)

@@ -269,6 +269,11 @@ int plane_ransac_shard_info(plane_ransac_ctx* ctx, long long* n_global_staged, l
  * convenience for callers without a CUDA runtime of their own. */
 int plane_ransac_host_alloc(size_t bytes, void** out);
 int plane_ransac_host_free(void* p);
+/* Page-locks memory the caller already owns (cudaHostRegister / cudaHostUnregister), e.g. the storage of a
+ * pcl::PointCloud (the reference's source_cloud, Dialog/PlaneDetect.h:104), so that plane_ransac_set_cloud_async takes
+ * the overlapped upload on it.  Unregister before the memory is freed or reallocated. */
+int plane_ransac_host_register(void* p, size_t bytes);
+int plane_ransac_host_unregister(void* p);
 
 /* ---- measurement ------------------------------------------------------------------------- */
 int plane_ransac_profile_enable(plane_ransac_ctx* ctx, int on);

@@ -89,3 +89,19 @@ def test_header_is_plain_c99_and_shim_compiles(tmp_path):
     r = subprocess.run([cxx, "-std=c++17", "-Wall", "-Wextra", "-Werror", f"-I{inc}", "-c", str(cpp_src), "-o", str(tmp_path / "shim.o")],
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
+
+
+def test_pcl_overload_compiles_and_links_against_stub_pcl(lib_built, tmp_path):
+    """The PLANE_RANSAC_WITH_PCL overload (pcl::PointCloud<pcl::PointXYZ>::Ptr in, pcl::ModelCoefficients +
+    pcl::PointIndices out — the surface north_star names) over a 30-line stand-in for the four PCL headers it includes:
+    PCL itself is not in this image.  tests/test_gpu_parity.py runs the resulting program on the GPU box."""
+    import shutil
+    import subprocess
+    cxx = shutil.which("/usr/bin/g++") or shutil.which("g++")
+    out = tmp_path / "pcl_overload_check"
+    r = subprocess.run([cxx, "-O1", "-std=c++17", "-Wall", "-Wextra", "-Werror", f"-I{os.path.join(ROOT, 'include')}",
+                        f"-I{os.path.join(ROOT, 'tests', 'pcl_stub')}", os.path.join(ROOT, "tests", "pcl_overload_check.cpp"), "-o", str(out),
+                        f"-L{os.path.join(ROOT, 'dialog_b200')}", "-lplane_ransac", f"-Wl,-rpath,{os.path.join(ROOT, 'dialog_b200')}"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert out.exists()

@@ -7,7 +7,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import GOLDEN
+from conftest import GOLDEN, ROOT
 
 pytestmark = pytest.mark.gpu
 
@@ -384,6 +384,107 @@ def test_cpp_shim_demo_matches_oracle(O, lib_built, double_shadow, tmp_path):
         f = line.split()
         assert int(f[3]) == want.inliers_cur[k].size
         assert [float.fromhex(v) for v in f[5:9]] == [float(v) for v in want.coeffs[k]]
+
+
+def _list_hash(idx):
+    """examples/plane_detect_demo.cpp list_hash: sum of (index + 1) * (position + 1) mod 2^64."""
+    idx = np.asarray(idx)
+    with np.errstate(over="ignore"):
+        return int(((idx.astype(np.uint64) + np.uint64(1)) * (np.arange(idx.size, dtype=np.uint64) + np.uint64(1))).sum(dtype=np.uint64))
+
+
+def _plane_lines(lines, prefix):
+    out = []
+    for ln in lines:
+        f = ln.split()
+        if ln.startswith(prefix + " ") and f[len(prefix.split())].isdigit():
+            k = len(prefix.split())
+            out.append((int(f[k + 2]), [float.fromhex(v) for v in f[k + 4:k + 8]], int(f[k + 9])))
+    return out
+
+
+def test_cpp_shim_pipeline_matches_oracle(O, lib_built, scene2, tmp_path):
+    """The drop-in C++ surface end to end, as PCLViewer drives PlaneDetect (Dialog/PCLViewer.cpp:1120-1235): detect ->
+    postProcess (re-absorption against plane outlines) -> clusterFilter -> runAgain, every stage against the oracle."""
+    import subprocess
+    from dialog_b200 import build
+    demo = build.build_demo()
+    n = 60_000
+    pts = scene2.points(0, n)
+    path, bpath = tmp_path / "cloud.f32", tmp_path / "borders.bin"
+    pts[:, :3].astype("<f4").tofile(path)
+    t, post_t, seed, radius, tnum = 0.05, 0.1, 7, 0.2, 12
+    r = subprocess.run([demo, str(path), str(t), "300", "1500", "--prob", "1.0", "--max-planes", "3",
+                        "--pipeline", str(seed), str(radius), str(tnum), str(bpath), str(post_t)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    lines = r.stdout.strip().splitlines()
+    prm = O.make_params(t, 300, 1500, 1.0, True, 12345, 3, O.DOT_FMA, O.REFIT_FIXED)
+    want = O.extract_planes(pts, prm)
+    head = lines[0].split()
+    assert int(head[1]) == n and int(head[3]) == len(want.coeffs) == 3 and int(head[5]) == want.remaining.shape[0]
+    got = _plane_lines(lines, "plane")
+    assert len(got) == 3
+    for k, (cnt, coeff, h) in enumerate(got):
+        assert cnt == want.inliers_orig[k].size and coeff == [float(v) for v in want.coeffs[k]]
+        assert h == _list_hash(want.inliers_orig[k])
+    # the outlines the program built (a checker only replays the pass, it does not re-derive the polygons)
+    raw = np.fromfile(bpath, np.uint8)
+    borders, at = [], 0
+    while at < raw.size:
+        m = int(raw[at:at + 4].view(np.uint32)[0])
+        borders.append(raw[at + 4: at + 4 + 16 * m].view(np.float32).reshape(m, 4).copy())
+        at += 4 + 16 * m
+    assert len(borders) == 3 and all(len(b) == 32 for b in borders)
+    claimed = np.zeros(n, bool)
+    claimed[np.concatenate(want.inliers_orig)] = True
+    rem_idx = np.nonzero(~claimed)[0]
+    rb = O.reabsorb(want.remaining, want.coeffs, borders, np.float32(post_t), seed)
+    post = [ln.split() for ln in lines if ln.startswith("post plane")]
+    assert len(post) == 3 and sum(int(f[4]) for f in post) > 200
+    for k, f in enumerate(post):
+        assert int(f[4]) == rb.absorbed[k].size and int(f[6]) == _list_hash(rem_idx[rb.absorbed[k]])
+    rem2 = rem_idx[rb.remaining_idx]
+    assert int([ln for ln in lines if ln.startswith("post remaining")][0].split()[2]) == rem2.size
+    keep = O.cluster_filter(pts[rem2], radius, tnum)
+    cl = [ln for ln in lines if ln.startswith("cluster")][0].split()
+    assert int(cl[2]) == int((~keep).sum()) > 0 and int(cl[4]) == int(keep.sum())
+    left = rem2[keep]
+    again = O.extract_planes(pts[left], prm)
+    ah = [ln for ln in lines if ln.startswith("again planes")][0].split()
+    assert int(ah[2]) == len(again.coeffs) and int(ah[4]) == again.remaining.shape[0]
+    for k, (cnt, coeff, h) in enumerate(_plane_lines(lines, "again plane")):
+        assert cnt == again.inliers_orig[k].size and coeff == [float(v) for v in again.coeffs[k]]
+        assert h == _list_hash(left[again.inliers_orig[k]])      # indices refer to the cloud given to the first call
+
+
+@pytest.mark.parametrize("pin", [False, True])
+def test_pcl_overload_runs_on_stub_pcl(O, lib_built, scene2, tmp_path, pin):
+    """pcl::PointCloud<pcl::PointXYZ>::Ptr in, pcl::ModelCoefficients / pcl::PointIndices out, the cloud shrunk in place to
+    the unclaimed points — compiled against the stand-in PCL headers of tests/pcl_stub, with the caller's storage read
+    where it lies (pageable) or page-locked in place (the overlapped upload: 2.5M points)."""
+    import shutil
+    import subprocess
+    cxx = shutil.which("/usr/bin/g++") or shutil.which("g++")
+    exe = tmp_path / "pcl_overload_check"
+    root = ROOT
+    r = subprocess.run([cxx, "-O2", "-std=c++17", f"-I{os.path.join(root, 'include')}", f"-I{os.path.join(root, 'tests', 'pcl_stub')}",
+                        os.path.join(root, "tests", "pcl_overload_check.cpp"), "-o", str(exe), f"-L{os.path.join(root, 'dialog_b200')}",
+                        "-lplane_ransac", f"-Wl,-rpath,{os.path.join(root, 'dialog_b200')}"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    n = 2_500_000 if pin else 90_000
+    pts = scene2.points(0, n)
+    path = tmp_path / "cloud.f32"
+    pts[:, :3].astype("<f4").tofile(path)
+    r = subprocess.run([str(exe), str(path), "0.1", "50", "2000"] + (["pin"] if pin else []), capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    lines = r.stdout.strip().splitlines()
+    want = O.extract_planes(pts, O.make_params(0.1, 50, 2000, 0.99, True, 12345, 64, O.DOT_FMA, O.REFIT_FIXED))
+    head = lines[0].split()
+    assert int(head[1]) == n and int(head[3]) == len(want.coeffs) and int(head[5]) == want.remaining.shape[0] == int(head[7])
+    for k, (cnt, coeff, h) in enumerate(_plane_lines(lines, "plane")):
+        assert cnt == want.inliers_orig[k].size and coeff == [float(v) for v in want.coeffs[k]] and h == _list_hash(want.inliers_orig[k])
+    got_sum = float.fromhex(lines[-1].split()[1])
+    assert abs(got_sum - float(want.remaining[:, :3].astype(np.float64).sum())) <= 1e-9 * abs(got_sum)   # the cloud now holds the leftovers
 
 
 # ---------------------------------------------------------------------------------------------
