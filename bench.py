@@ -64,6 +64,10 @@ def parse_args():
                     help="skip BASELINE configs[3]: the 100M-point scene sharded over the N ranks (strong scaling), with the "
                          "sharded result checked against one GPU solving the whole cloud")
     ap.add_argument("--config4-points", type=int, default=100_000_000)
+    ap.add_argument("--no-config5", action="store_true",
+                    help="skip BASELINE configs[4]: 512 x N clouds of 32K points (the full 4096-cloud batch at N = 8), sharded "
+                         "by cloud id over the N ranks")
+    ap.add_argument("--config5-clouds-per-gpu", type=int, default=512)
     return ap.parse_args()
 
 
@@ -472,6 +476,74 @@ def run_config4(args, torch, dist, D, local_rank, world, rank, hbm_peak, peak_tf
     return out if rank == 0 else None
 
 
+def run_config5(args, torch, dist, D, local_rank, world, rank, peak_tf):
+    """BASELINE configs[4]: a batch of 32K-point clouds (per-scan tiles), one segment() each with 256 hypotheses, sharded
+    by cloud id (cloud_id % N == rank) — replicas only, no data-path collective; one gather of the results at the end.
+    512 clouds per GPU: the full 4096-cloud batch at N = 8, a slice of it below."""
+    from dialog_b200 import synth
+    n_per, K = 32768, 256
+    total = args.config5_clouds_per_gpu * world
+    ids = [cid for cid in range(total) if cid % world == rank]
+    pinned = torch.empty((len(ids), n_per, 4), dtype=torch.float32, pin_memory=True)
+    host = pinned.numpy()
+    for j, cid in enumerate(ids):
+        host[j] = synth.tile_scene(cid).points(0, n_per)
+    prm = D.make_params(0.1, K - 1, 500, 1.0, True, 12345, 1, D.DOT_FMA)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    pr = D.PlaneRansac(local_rank)
+    pr.set_cloud_batch_ptr(pinned.data_ptr(), len(ids), n_per)
+    for _ in range(3):
+        coeffs, cnt, _ = pr.segment_batch(prm, want_infos=False)
+    pr.profile_enable(True)
+    pr.profile_reset()
+    ms, e2e = [], []
+    for _ in range(5):
+        pr.flush_l2()
+        barrier()
+        pr.timer_start()
+        coeffs, cnt, _ = pr.segment_batch(prm, want_infos=False)
+        ms.append(pr.timer_stop())
+    prof = pr.profile()
+    pr.profile_enable(False)
+    for _ in range(3):      # host tiles in -> coefficients, counts and every cloud's inlier index list out
+        pr.flush_l2()
+        barrier()
+        pr.timer_start()
+        pr.set_cloud_batch_ptr(pinned.data_ptr(), len(ids), n_per)
+        coeffs, cnt, _, lists = pr.segment_batch(prm, want_infos=False, want_lists=True)
+        e2e.append(pr.timer_stop())
+    barrier()
+    t = torch.tensor([sum(ms) / len(ms), sum(e2e) / len(e2e)], dtype=torch.float64, device="cuda")
+    res = torch.from_numpy(np.concatenate([coeffs, cnt[:, None].astype(np.float32)], 1)).cuda()
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        parts = [torch.empty_like(res) for _ in range(world)] if rank == 0 else None
+        dist.gather(res, parts, dst=0)       # the one exchange of the config: results to rank 0
+        if rank == 0:
+            res = torch.cat(parts)
+    pr.close()
+    if rank != 0:
+        return None
+    ms_b, ms_e = t.tolist()
+    pairs = total * n_per * (K + 1)      # K hypotheses + the final selection per cloud
+    score_tf = 6.0 * prof.pairs_scored / (prof.ms_score * 1e-3) / 1e12 if prof.ms_score > 0 else None
+    return {"clouds_total": total, "clouds_per_gpu": len(ids), "points_per_cloud": n_per, "hypotheses_per_cloud": K, "n_gpus": world,
+            "sharding": "cloud_id % n_gpus, no collective; one gather of (coefficients, count) per cloud at the end",
+            "ms_per_batch": ms_b, "clouds_per_s": total / (ms_b * 1e-3), "point_hypotheses_per_s": pairs / (ms_b * 1e-3),
+            "frac_of_fp32_peak_whole_call": 6.0 * pairs / (ms_b * 1e-3) / 1e12 / (peak_tf * world),
+            "score_kernel_frac_of_fp32_peak": score_tf / peak_tf if score_tf else None,
+            "kernel_ms": {"gather_models": prof.ms_models / 5, "score": prof.ms_score / 5, "refit": prof.ms_refit / 5, "other": prof.ms_other / 5},
+            "e2e_ms_per_batch": ms_e, "e2e_clouds_per_s": total / (ms_e * 1e-3),
+            "e2e_note": "pinned host tiles in (%d MB per GPU), coefficients + counts + every cloud's inlier index list out" % (len(ids) * n_per * 16 // 2**20),
+            "mean_inliers": float(res[:, 4].mean().item()), "clouds_with_plane": int((res[:, 4] >= 500).sum().item())}
+
+
 def hbm_block(prof, hbm_peak):
     """HBM rooflines of the peel (K5) and refit (K3) launches in a profile: bytes actually moved, and SURVEY §8d's formula."""
     c_gbs = prof.bytes_compact / (prof.ms_compact * 1e-3) / 1e9 if prof.ms_compact > 0 else None
@@ -674,7 +746,11 @@ def main():
     c4 = None
     if not args.no_config4:
         c4 = run_config4(args, torch, dist, D, local_rank, world, rank, hbm_peak if rank == 0 else None, peak_tf)
+    c5 = None
+    if not args.no_config5:
+        c5 = run_config5(args, torch, dist, D, local_rank, world, rank, peak_tf)
     if rank == 0:
+        line["config5_batch"] = c5
         if c4 and "single_launch" in c4:
             # the HBM kernels at the north star's scene size, one launch each, timed alone; the figures in roofline_hbm
             # proper are averages over the shrinking 10M-point rounds

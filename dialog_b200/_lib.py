@@ -25,7 +25,7 @@ SYMBOLS = [
     "plane_ransac_create", "plane_ransac_destroy", "plane_ransac_set_cloud", "plane_ransac_set_cloud_device",
     "plane_ransac_set_cloud_ex", "plane_ransac_set_cloud_async", "plane_ransac_staged_source_indices",
     "plane_ransac_cloud_size", "plane_ransac_score", "plane_ransac_segment_one", "plane_ransac_extract_planes",
-    "plane_ransac_plane_points", "plane_ransac_set_round_loop", "plane_ransac_remaining", "plane_ransac_reabsorb", "plane_ransac_estimate_normals", "plane_ransac_cluster_filter", "plane_ransac_restage_remaining", "plane_ransac_set_cloud_batch", "plane_ransac_segment_batch",
+    "plane_ransac_plane_points", "plane_ransac_set_round_loop", "plane_ransac_remaining", "plane_ransac_reabsorb", "plane_ransac_estimate_normals", "plane_ransac_cluster_filter", "plane_ransac_restage_remaining", "plane_ransac_set_cloud_batch", "plane_ransac_segment_batch", "plane_ransac_segment_batch_lists",
     "plane_ransac_comm_unique_id", "plane_ransac_comm_init", "plane_ransac_comm_p2p_enabled", "plane_ransac_shard_info",
     "plane_ransac_host_alloc", "plane_ransac_host_free", "plane_ransac_host_register", "plane_ransac_host_unregister", "plane_ransac_profile_enable", "plane_ransac_profile_reset", "plane_ransac_profile_get",
     "plane_ransac_timer_start", "plane_ransac_timer_stop", "plane_ransac_measure_ffma_peak", "plane_ransac_measure_copy_bw", "plane_ransac_flush_l2",
@@ -135,6 +135,7 @@ def load():
     L.plane_ransac_measure_copy_bw.argtypes = [vp, sz, C.POINTER(C.c_double)]
     L.plane_ransac_flush_l2.argtypes = [vp]
     L.plane_ransac_host_draw_triples.argtypes = [sz, C.c_uint, C.c_int, vp]
+    L.plane_ransac_segment_batch_lists.argtypes = [vp, C.POINTER(PrParams), vp, vp, vp, sz, vp, vp]
     L.plane_ransac_set_round_loop.argtypes = [vp, C.c_int]
     L.plane_ransac_host_draw_triples_parallel.argtypes = [sz, C.c_uint, C.c_int, vp, C.POINTER(C.c_int)]
     L.plane_ransac_host_replay.argtypes = [vp, vp, C.c_int, C.c_longlong, C.c_int, C.c_double] + [C.POINTER(C.c_int)] * 5

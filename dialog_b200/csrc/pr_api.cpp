@@ -180,6 +180,14 @@ struct plane_ransac_ctx {
   DevBuf<float4> d_batch_hyps;       // best / refined hypothesis per cloud
   DevBuf<int4> d_batch_pts;
   DevBuf<int32_t> d_batch_cnt;
+  // device-driven batch path: per-cloud winner, raw model, list offsets, the lists; grid exponents uploaded at staging
+  DevBuf<int32_t> d_batch_best, d_batch_bestcnt, d_batch_sexp, d_batch_lists;
+  DevBuf<float4> d_batch_raw;
+  DevBuf<unsigned long long> d_batch_offs;
+  DevBuf<int> d_batch_flag;
+  std::vector<int32_t> batch_tri;  // the K triples every cloud of the batch draws (same size, same seed)
+  size_t batch_tri_n = 0;
+  unsigned batch_tri_seed = 0;
 
   // postProcessPlanes re-absorption scratch
   DevBuf<pr::ReabsorbPlane> d_rb_planes;
@@ -1456,6 +1464,8 @@ void plane_ransac_destroy(plane_ransac_ctx* c) {
   dev_free(c->d_nrm_temp);
   dev_free(c->d_batch_bbox); dev_free(c->d_batch_idx); dev_free(c->d_batch_scale); dev_free(c->d_batch_refit);
   dev_free(c->d_batch_hyps); dev_free(c->d_batch_pts); dev_free(c->d_batch_cnt);
+  dev_free(c->d_batch_best); dev_free(c->d_batch_bestcnt); dev_free(c->d_batch_sexp); dev_free(c->d_batch_lists);
+  dev_free(c->d_batch_raw); dev_free(c->d_batch_offs); dev_free(c->d_batch_flag);
   pin_free(c->h_triples); pin_free(c->h_counts); pin_free(c->h_good); pin_free(c->h_refit); pin_free(c->h_sample_pts);
   for (cudaEvent_t e : c->pend.ev) cudaEventDestroy(e);
   pin_free(c->h_totals); pin_free(c->h_small);
@@ -2094,18 +2104,157 @@ int plane_ransac_set_cloud_batch(plane_ransac_ctx* c, const pr_point* pts, size_
   PR_CUDA(cudaStreamSynchronize(c->stream));
   c->batch_scale_exp.resize(n_clouds);
   for (size_t i = 0; i < n_clouds; ++i) c->batch_scale_exp[i] = pr::scale_exp_from_bbox_keys(&keys[6 * i]);
+  {
+    std::vector<double> scales(n_clouds);
+    for (size_t i = 0; i < n_clouds; ++i) scales[i] = std::ldexp(1.0, c->batch_scale_exp[i]);
+    PR_TRY(dev_reserve(c->d_batch_sexp, n_clouds));
+    PR_TRY(dev_reserve(c->d_batch_scale, n_clouds));
+    PR_CUDA(cudaMemcpyAsync(c->d_batch_sexp.p, c->batch_scale_exp.data(), n_clouds * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    PR_CUDA(cudaMemcpyAsync(c->d_batch_scale.p, scales.data(), n_clouds * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    PR_CUDA(cudaStreamSynchronize(c->stream));
+  }
   c->batch_clouds = n_clouds;
   c->batch_n = n_per_cloud;
   c->batch_stride = stride;
   return PR_OK;
 }
 
-int plane_ransac_segment_batch(plane_ransac_ctx* c, const pr_params* prm, float* coeffs, int32_t* n_inliers,
-                               pr_segment_info* infos) {
-  PR_TRY(check_ctx(c));
-  PR_TRY(check_params(prm));
-  if (c->batch_clouds == 0) return fail(PR_ERR_NO_CLOUD, "no batch staged");
-  if (!coeffs || !n_inliers) return fail(PR_ERR_INVALID, "null output");
+}  // extern "C"
+
+namespace {
+
+// Every cloud's ascending inlier list for the planes in d_batch_hyps (clouds with ok[c] < 0 have none): offsets, then
+// the lists themselves into the caller's buffer.
+int batch_lists_out(plane_ransac_ctx* c, const pr_params* prm, const int32_t* d_ok, const int32_t* d_cnt, int32_t* inliers, size_t cap,
+                    size_t* offsets) {
+  const size_t C = c->batch_clouds, n = c->batch_n;
+  if (!offsets) return PR_OK;
+  const float t = pr::threshold_up(prm->distance_threshold);
+  PR_TRY(dev_reserve(c->d_batch_offs, C + 1));
+  const size_t dev_cap = inliers ? std::min(cap, C * n) : 0;
+  if (dev_cap) PR_TRY(dev_reserve(c->d_batch_lists, dev_cap));
+  {
+    Span sp(c, KC_COMPACT, dev_cap ? 2 : 1);
+    pr::launch_batch_lists(c->batch_view, n, c->batch_stride, (int)C, c->d_batch_hyps.p, d_ok, t, prm->dot_order, d_cnt, c->d_batch_offs.p, dev_cap,
+                           dev_cap ? c->d_batch_lists.p : nullptr, c->stream);
+  }
+  PR_CUDA(cudaGetLastError());
+  static_assert(sizeof(size_t) == sizeof(unsigned long long), "size_t is 64 bits");
+  PR_CUDA(cudaMemcpyAsync(offsets, c->d_batch_offs.p, (C + 1) * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+  PR_TRY(sync_stream(c));
+  const size_t total = offsets[C];
+  if (inliers && total > cap) return fail(PR_ERR_CAPACITY, "inlier buffer holds %zu entries, the batch has %zu inliers", cap, total);
+  if (inliers && total) {
+    PR_CUDA(cudaMemcpyAsync(inliers, c->d_batch_lists.p, total * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    PR_TRY(sync_stream(c));
+  }
+  return PR_OK;
+}
+
+// Score-all mode without the host in the loop: every step of segment() for all clouds is a launch; one read-back at the
+// end.  *fell_back: a degenerate sample somewhere needs PCL's redraw rule — the host-driven path redoes the batch.
+int segment_batch_device(plane_ransac_ctx* c, const pr_params* prm, float* coeffs, int32_t* n_inliers, int32_t* inliers, size_t cap,
+                         size_t* offsets, pr_segment_info* infos, bool* fell_back) {
+  HostTimer whole(&c->prof.host_ms_total);
+  const size_t C = c->batch_clouds, n = c->batch_n, stride = c->batch_stride;
+  const int K = prm->max_iterations + 1;
+  const size_t CK = C * (size_t)K;
+  const float t = pr::threshold_up(prm->distance_threshold);
+  *fell_back = false;
+  if (c->batch_tri.size() != 3 * (size_t)K || c->batch_tri_n != n || c->batch_tri_seed != prm->seed) {
+    // every cloud has n points and the same seed, so PCL draws the same triples for every cloud: drawn once and kept
+    HostTimer tm(&c->prof.host_ms_sampling);
+    c->batch_tri.resize(3 * (size_t)K);
+    pr::IndexSampler sampler(n, prm->seed);
+    for (int j = 0; j < K; ++j) sampler.draw(c->batch_tri.data() + 3 * j);
+    c->batch_tri_n = n;
+    c->batch_tri_seed = prm->seed;
+  }
+  PR_TRY(reserve_draws(c, CK, false));
+  PR_TRY(dev_reserve(c->d_batch_best, C));
+  PR_TRY(dev_reserve(c->d_batch_bestcnt, C));
+  PR_TRY(dev_reserve(c->d_batch_flag, 1));
+  PR_TRY(dev_reserve(c->d_batch_refit, C));
+  PR_TRY(dev_reserve(c->d_batch_raw, C));
+  PR_TRY(dev_reserve(c->d_batch_hyps, C));
+  PR_TRY(dev_reserve(c->d_batch_cnt, 2 * C));
+  std::memcpy(c->h_triples.p, c->batch_tri.data(), 3 * (size_t)K * sizeof(int32_t));
+  PR_CUDA(cudaMemcpyAsync(c->d_triples.p, c->h_triples.p, 3 * (size_t)K * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+  {
+    Span sp(c, KC_MODELS, 2);
+    pr::launch_gather_samples(c->batch_view, 0, n, c->d_triples.p, 3 * K, c->d_sample_pts.p, (int)C, stride, c->stream);
+    pr::launch_models(c->d_sample_pts.p, (int)CK, c->d_hyps.p, c->d_good.p, c->stream);
+  }
+  PR_CUDA(cudaMemsetAsync(c->d_counts.p, 0, CK * sizeof(int32_t), c->stream));
+  {
+    Span sp(c, KC_SCORE, 0);
+    c->prof.launches_score += pr::launch_score(c->batch_view, n, (int)C, stride, c->d_hyps.p, K, t, prm->dot_order, c->d_counts.p, c->num_sms, c->stream);
+    c->prof.pairs_scored += (long long)n * (long long)CK;
+  }
+  PR_CUDA(cudaMemsetAsync(c->d_batch_flag.p, 0, sizeof(int), c->stream));
+  {
+    Span sp(c, KC_OTHER, 1);
+    pr::launch_batch_replay(c->d_counts.p, c->d_good.p, K, (int)C, c->d_batch_best.p, c->d_batch_bestcnt.p, c->d_batch_flag.p, c->stream);
+  }
+  if (prm->optimize_coefficients) {
+    PR_CUDA(cudaMemsetAsync(c->d_batch_refit.p, 0, C * sizeof(pr::RefitOut), c->stream));
+    Span sp(c, KC_REFIT, 1);
+    pr::launch_refit_batch(c->batch_view, n, stride, (int)C, c->d_hyps.p, c->d_sample_pts.p, K, c->d_batch_best.p, t, prm->dot_order,
+                           c->d_batch_scale.p, c->d_batch_refit.p, c->stream);
+    c->prof.points_refit += (long long)(n * C);
+    c->prof.bytes_refit += 12ll * (long long)(n * C);
+  }
+  {
+    Span sp(c, KC_OTHER, 1);
+    pr::launch_batch_finish(c->d_hyps.p, K, c->d_batch_best.p, c->d_batch_refit.p, c->d_batch_sexp.p, prm->optimize_coefficients ? 1 : 0,
+                            (int)C, c->d_batch_raw.p, c->d_batch_hyps.p, c->stream);
+  }
+  const int32_t* d_final = c->d_batch_bestcnt.p;  // without the refit the raw model's count is the final one
+  if (prm->optimize_coefficients) {
+    PR_CUDA(cudaMemsetAsync(c->d_batch_cnt.p, 0, C * sizeof(int32_t), c->stream));
+    Span sp(c, KC_SCORE, 0);
+    c->prof.launches_score += pr::launch_score(c->batch_view, n, (int)C, stride, c->d_batch_hyps.p, 1, t, prm->dot_order, c->d_batch_cnt.p, c->num_sms, c->stream);
+    c->prof.pairs_scored += (long long)(n * C);
+    d_final = c->d_batch_cnt.p;
+  }
+  PR_CUDA(cudaGetLastError());
+  std::vector<int32_t> best(C), best_cnt(C), final_cnt(C);
+  std::vector<float4> raw(C), refined(C);
+  int flag = 0;
+  PR_CUDA(cudaMemcpyAsync(&flag, c->d_batch_flag.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  PR_CUDA(cudaMemcpyAsync(best.data(), c->d_batch_best.p, C * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+  PR_CUDA(cudaMemcpyAsync(best_cnt.data(), c->d_batch_bestcnt.p, C * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+  PR_CUDA(cudaMemcpyAsync(final_cnt.data(), d_final, C * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+  PR_CUDA(cudaMemcpyAsync(raw.data(), c->d_batch_raw.p, C * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
+  PR_CUDA(cudaMemcpyAsync(refined.data(), c->d_batch_hyps.p, C * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
+  PR_TRY(sync_stream(c));
+  if (flag) {
+    *fell_back = true;
+    return PR_OK;
+  }
+  for (size_t i = 0; i < C; ++i) {
+    n_inliers[i] = final_cnt[i];
+    const float r4[4] = {refined[i].x, refined[i].y, refined[i].z, refined[i].w};
+    std::memcpy(coeffs + 4 * i, r4, sizeof(r4));
+    if (infos) {
+      pr_segment_info inf;
+      std::memset(&inf, 0, sizeof(inf));
+      inf.ok = 1;
+      inf.iterations = inf.draws = inf.n_scored = K;
+      inf.n_cloud = (long long)n;
+      inf.scale_exp = c->batch_scale_exp[i];
+      for (int k = 0; k < 3; ++k) inf.best_sample[k] = c->batch_tri[3 * (size_t)best[i] + k];
+      inf.best_count = inf.n_inliers_raw = best_cnt[i];
+      inf.raw_coeff[0] = raw[i].x; inf.raw_coeff[1] = raw[i].y; inf.raw_coeff[2] = raw[i].z; inf.raw_coeff[3] = raw[i].w;
+      inf.n_inliers = final_cnt[i];
+      infos[i] = inf;
+    }
+  }
+  return batch_lists_out(c, prm, c->d_batch_best.p, d_final, inliers, cap, offsets);
+}
+
+int segment_batch_host(plane_ransac_ctx* c, const pr_params* prm, float* coeffs, int32_t* n_inliers, int32_t* inliers, size_t cap,
+                       size_t* offsets, pr_segment_info* infos) {
   HostTimer whole(&c->prof.host_ms_total);
   const size_t C = c->batch_clouds, n = c->batch_n, stride = c->batch_stride;
   const float t = pr::threshold_up(prm->distance_threshold);
@@ -2268,7 +2417,38 @@ int plane_ransac_segment_batch(plane_ransac_ctx* c, const pr_params* prm, float*
       infos[i] = inf;
     }
   }
-  return PR_OK;
+  if (!offsets) return PR_OK;
+  // index lists: the final planes and a per-cloud "has a model" flag on the device, then the same list kernels
+  PR_CUDA(cudaMemcpyAsync(c->d_batch_hyps.p, refined.data(), C * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
+  PR_CUDA(cudaMemcpyAsync(c->d_batch_idx.p, model_idx.data(), C * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+  PR_CUDA(cudaMemcpyAsync(c->d_batch_cnt.p, n_inliers, C * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+  return batch_lists_out(c, prm, c->d_batch_idx.p, c->d_batch_cnt.p, inliers, cap, offsets);
+}
+
+}  // namespace
+
+extern "C" {
+
+int plane_ransac_segment_batch_lists(plane_ransac_ctx* c, const pr_params* prm, float* coeffs, int32_t* n_inliers, int32_t* inliers,
+                                     size_t cap, size_t* offsets, pr_segment_info* infos) {
+  PR_TRY(check_ctx(c));
+  if (c->profiling) collect_spans(c);
+  PR_TRY(check_params(prm));
+  if (c->batch_clouds == 0) return fail(PR_ERR_NO_CLOUD, "no batch staged");
+  if (!coeffs || !n_inliers) return fail(PR_ERR_INVALID, "null output");
+  if (inliers && !offsets) return fail(PR_ERR_INVALID, "inlier lists need the offsets array");
+  const bool device_loop = c->round_loop != PR_LOOP_HOST && prm->probability >= 1.0 && prm->max_iterations >= 1 && c->batch_n >= 3 &&
+                           (double)c->batch_clouds * ((double)prm->max_iterations + 1.0) <= 4.0e8;
+  if (device_loop) {
+    bool fell_back = false;
+    PR_TRY(segment_batch_device(c, prm, coeffs, n_inliers, inliers, cap, offsets, infos, &fell_back));
+    if (!fell_back) return PR_OK;
+  }
+  return segment_batch_host(c, prm, coeffs, n_inliers, inliers, cap, offsets, infos);
+}
+
+int plane_ransac_segment_batch(plane_ransac_ctx* c, const pr_params* prm, float* coeffs, int32_t* n_inliers, pr_segment_info* infos) {
+  return plane_ransac_segment_batch_lists(c, prm, coeffs, n_inliers, nullptr, 0, nullptr, infos);
 }
 
 // ---- sharding -----------------------------------------------------------------------------------

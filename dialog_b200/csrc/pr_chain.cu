@@ -10,6 +10,8 @@
 // so the host queues whole rounds ahead and only reads the per-round records (pr_api.cpp run_chain).
 #include "pr_kernels.h"
 
+#include <math_constants.h>
+
 #include "pr_chain_dev.cuh"
 #include "pr_draw.h"
 #include "pr_math.h"
@@ -220,6 +222,180 @@ void launch_finish(RoundState* st, const float4* hyps, const int32_t* triples, c
 
 void launch_advance(RoundState* st, const long long* totals, int n_ranks, int rank, int min_plane, RoundRecord* rec, cudaStream_t s) {
   advance_kernel<<<1, 32, 0, s>>>(st, totals, n_ranks, rank, min_plane, rec);
+}
+
+}  // namespace pr
+
+// =====================================================================================================================
+// Batch of equal-sized small clouds (BASELINE configs[4]: per-scan tiles), score-all mode, without the host in the loop:
+// one segment() per cloud — computeModel's decision, the closed-form refit and the final selection with its index list
+// (pcl::SACSegmentation::segment's `inliers`) — as a fixed sequence of launches over all clouds.
+// =====================================================================================================================
+namespace pr {
+
+// computeModel over the K counts of every cloud: best[c] = first draw with the largest count, or -1 and *any_bad = 1 when
+// a degenerate sample among the K draws means PCL would have drawn further (the host-driven path then redoes the batch).
+__global__ void __launch_bounds__(128) batch_replay_kernel(const int32_t* __restrict__ counts, const int32_t* __restrict__ good, int K,
+                                                           int32_t* __restrict__ best, int32_t* __restrict__ best_count, int* any_bad) {
+  __shared__ unsigned long long s_best[4];
+  const size_t c = blockIdx.x;
+  unsigned long long b = 0ull;
+  int all_good = 1;
+  for (int j = threadIdx.x; j < K; j += 128) {
+    if (!good[c * K + j]) all_good = 0;
+    const unsigned long long key = ((unsigned long long)(unsigned)counts[c * K + j] << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)j);
+    b = key > b ? key : b;
+  }
+  all_good = __syncthreads_and(all_good);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long other = __shfl_down_sync(0xFFFFFFFFu, b, o);
+    b = other > b ? other : b;
+  }
+  if ((threadIdx.x & 31) == 0) s_best[threadIdx.x >> 5] = b;
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  for (int w = 1; w < 4; ++w) b = s_best[w] > b ? s_best[w] : b;
+  if (!all_good) {
+    best[c] = -1;
+    best_count[c] = 0;
+    *any_bad = 1;
+    return;
+  }
+  best[c] = (int32_t)(0xFFFFFFFFu - (unsigned)(b & 0xFFFFFFFFull));
+  best_count[c] = (int32_t)(b >> 32);
+}
+
+// refined[c] = closed-form plane from cloud c's moments (or its raw model), thread per cloud
+__global__ void __launch_bounds__(64) batch_finish_kernel(const float4* __restrict__ hyps, int K, const int32_t* __restrict__ best,
+                                                          const RefitOut* __restrict__ refit, const int32_t* __restrict__ scale_exp,
+                                                          int optimize, int n_clouds, float4* __restrict__ raw, float4* __restrict__ refined) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_clouds) return;
+  const int b = best[c];
+  if (b < 0) {
+    raw[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+    refined[c] = make_float4(CUDART_NAN_F, CUDART_NAN_F, CUDART_NAN_F, CUDART_NAN_F);  // never an inlier: the final count is 0
+    return;
+  }
+  const float4 h = hyps[(size_t)c * K + b];
+  float out[4] = {h.x, h.y, h.z, h.w};
+  if (optimize) {
+    long long m[16];
+    for (int i = 0; i < 16; ++i) m[i] = refit[c].m[i];
+    const float pivot[3] = {refit[c].pivot[0], refit[c].pivot[1], refit[c].pivot[2]};
+    pm_plane_from_moments(m, pivot, scale_exp[c], out);
+  }
+  raw[c] = h;
+  refined[c] = make_float4(out[0], out[1], out[2], out[3]);
+}
+
+// offs[0 .. C] = exclusive scan of cnt[0 .. C) (one block; C is a few thousand)
+__global__ void __launch_bounds__(1024) batch_offsets_kernel(const int32_t* __restrict__ cnt, int n_clouds, unsigned long long* __restrict__ offs) {
+  __shared__ unsigned long long s_warp[32];
+  __shared__ unsigned long long s_carry;
+  if (threadIdx.x == 0) s_carry = 0ull;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int base = 0; base < n_clouds; base += 1024) {
+    const int i = base + threadIdx.x;
+    const unsigned long long mine = i < n_clouds ? (unsigned long long)cnt[i] : 0ull;
+    unsigned long long v = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned long long y = __shfl_up_sync(0xFFFFFFFFu, v, o);
+      if (lane >= o) v += y;
+    }
+    if (lane == 31) s_warp[warp] = v;
+    __syncthreads();
+    unsigned long long before = s_carry;
+    for (int w = 0; w < warp; ++w) before += s_warp[w];
+    if (i < n_clouds) offs[i] = before + v - mine;
+    __syncthreads();
+    if (threadIdx.x == 1023) s_carry = before + v;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) offs[n_clouds] = s_carry;
+}
+
+// selectWithinDistance with the final coefficients, per cloud, ascending: out[offs[c] + r] = index (within cloud c) of its
+// r-th inlier.  One block per cloud walks the cloud in 1024-point steps with a block-wide scan per step.
+template <int DOT>
+__global__ void __launch_bounds__(256) batch_lists_kernel(const float* __restrict__ X, const float* __restrict__ Y, const float* __restrict__ Z,
+                                                          size_t n_per, size_t stride, const float4* __restrict__ planes,
+                                                          const int32_t* __restrict__ best, float t,
+                                                          const unsigned long long* __restrict__ offs, size_t cap, int32_t* __restrict__ out) {
+  __shared__ int s_warp[8];
+  __shared__ int s_base;
+  const size_t c = blockIdx.x;
+  if (best[c] < 0) return;
+  const float4 pl = planes[c];
+  const unsigned long long o0 = offs[c];
+  if (o0 + (offs[c + 1] - o0) > cap) return;  // the caller's buffer cannot hold this cloud's list: reported by the host
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) s_base = 0;
+  __syncthreads();
+  const float* x = X + c * stride;
+  const float* y = Y + c * stride;
+  const float* z = Z + c * stride;
+  for (size_t p0 = 0; p0 < n_per; p0 += 1024) {
+    const size_t i0 = p0 + 4 * threadIdx.x;  // the planes are NaN-padded to the stride: no bounds check on the loads
+    const float4 x4 = *reinterpret_cast<const float4*>(x + i0);
+    const float4 y4 = *reinterpret_cast<const float4*>(y + i0);
+    const float4 z4 = *reinterpret_cast<const float4*>(z + i0);
+    const float xs[4] = {x4.x, x4.y, x4.z, x4.w}, ys[4] = {y4.x, y4.y, y4.z, y4.w}, zs[4] = {z4.x, z4.y, z4.z, z4.w};
+    unsigned in = 0u;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float r;
+      if (DOT == 1) r = __fmaf_rn(pl.x, xs[e], __fmaf_rn(pl.y, ys[e], __fmaf_rn(pl.z, zs[e], pl.w)));
+      else r = __fadd_rn(__fadd_rn(__fmul_rn(pl.x, xs[e]), __fmul_rn(pl.z, zs[e])), __fadd_rn(__fmul_rn(pl.y, ys[e]), pl.w));
+      if (i0 + e < n_per && fabsf(r) < t) in |= 1u << e;
+    }
+    const int k = __popc(in);
+    int v = k;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int yv = __shfl_up_sync(0xFFFFFFFFu, v, o);
+      if (lane >= o) v += yv;
+    }
+    if (lane == 31) s_warp[warp] = v;
+    __syncthreads();
+    int before = s_base;
+    int total = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      if (w < warp) before += s_warp[w];
+      total += s_warp[w];
+    }
+    int rnk = before + v - k;
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+      if (in & (1u << e)) out[o0 + (unsigned long long)(rnk++)] = (int32_t)(i0 + e);
+    __syncthreads();
+    if (threadIdx.x == 0) s_base += total;
+    __syncthreads();
+  }
+}
+
+void launch_batch_replay(const int32_t* counts, const int32_t* good, int K, int n_clouds, int32_t* best, int32_t* best_count, int* any_bad,
+                         cudaStream_t s) {
+  batch_replay_kernel<<<n_clouds, 128, 0, s>>>(counts, good, K, best, best_count, any_bad);
+}
+
+void launch_batch_finish(const float4* hyps, int K, const int32_t* best, const RefitOut* refit, const int32_t* scale_exp, int optimize,
+                         int n_clouds, float4* raw, float4* refined, cudaStream_t s) {
+  batch_finish_kernel<<<(n_clouds + 63) / 64, 64, 0, s>>>(hyps, K, best, refit, scale_exp, optimize, n_clouds, raw, refined);
+}
+
+void launch_batch_lists(CloudView clouds, size_t n_per, size_t stride, int n_clouds, const float4* planes, const int32_t* best, float t,
+                        int dot_order, const int32_t* cnt, unsigned long long* offs, size_t cap, int32_t* out, cudaStream_t s) {
+  batch_offsets_kernel<<<1, 1024, 0, s>>>(cnt, n_clouds, offs);
+  if (out == nullptr) return;
+  if (dot_order == 1)
+    batch_lists_kernel<1><<<n_clouds, 256, 0, s>>>(clouds.x, clouds.y, clouds.z, n_per, stride, planes, best, t, offs, cap, out);
+  else
+    batch_lists_kernel<0><<<n_clouds, 256, 0, s>>>(clouds.x, clouds.y, clouds.z, n_per, stride, planes, best, t, offs, cap, out);
 }
 
 }  // namespace pr

@@ -245,6 +245,18 @@ void launch_finish(RoundState* st, const float4* hyps, const int32_t* triples, c
 // Minimum-plane-size rule on the global inlier count; on acceptance the state moves to the remaining cloud.
 void launch_advance(RoundState* st, const long long* totals, int n_ranks, int rank, int min_plane, RoundRecord* rec, cudaStream_t s);
 
+// ---- batch of small clouds without the host in the loop (score-all mode; pr_chain.cu) ----------------------------------
+// best[c] = computeModel's winner among cloud c's K draws (-1 + *any_bad when a degenerate sample needs PCL's redraw).
+void launch_batch_replay(const int32_t* counts, const int32_t* good, int K, int n_clouds, int32_t* best, int32_t* best_count, int* any_bad,
+                         cudaStream_t s);
+// raw[c] = hyps[c * K + best[c]]; refined[c] = closed-form plane from refit[c] on the 2^-scale_exp[c] grid (or raw[c]).
+void launch_batch_finish(const float4* hyps, int K, const int32_t* best, const RefitOut* refit, const int32_t* scale_exp, int optimize,
+                         int n_clouds, float4* raw, float4* refined, cudaStream_t s);
+// offs = exclusive scan of the per-cloud final counts; out (optional, cap entries) receives every cloud's ascending
+// inlier indices at offs[c] (clouds whose list would not fit are skipped).
+void launch_batch_lists(CloudView clouds, size_t n_per, size_t stride, int n_clouds, const float4* planes, const int32_t* best, float t,
+                        int dot_order, const int32_t* cnt, unsigned long long* offs, size_t cap, int32_t* out, cudaStream_t s);
+
 // Measurement helpers.
 void launch_ffma_peak(float* out, int iters, int grid, cudaStream_t s);
 void launch_copy(const float4* src, float4* dst, size_t n_vec, int num_sms, cudaStream_t s);

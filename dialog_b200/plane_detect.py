@@ -102,6 +102,7 @@ class PlaneRansac:
         self._h = h
         self._idx_buf = None
         self._batch = 0
+        self._batch_n = 0
 
     def close(self):
         if getattr(self, "_idx_buf", None):
@@ -229,20 +230,36 @@ class PlaneRansac:
         flat = as_cloud(a.reshape(-1, a.shape[2]))
         _lib.check(self._L.plane_ransac_set_cloud_batch(self._h, flat.ctypes.data_as(C.c_void_p), a.shape[0], a.shape[1]))
         self._batch = a.shape[0]
+        self._batch_n = a.shape[1]
 
     def set_cloud_batch_ptr(self, host_ptr: int, n_clouds: int, n_per_cloud: int) -> None:
         _lib.check(self._L.plane_ransac_set_cloud_batch(self._h, C.c_void_p(host_ptr), n_clouds, n_per_cloud))
         self._batch = n_clouds
+        self._batch_n = n_per_cloud
 
-    def segment_batch(self, params: PrParams, want_infos: bool = True):
-        """One segment() per cloud: (coeffs (n_clouds,4), n_inliers (n_clouds,), infos)."""
+    def segment_batch(self, params: PrParams, want_infos: bool = True, want_lists: bool = False):
+        """One segment() per cloud: (coeffs (n_clouds,4), n_inliers (n_clouds,), infos) and, with want_lists, a fourth
+        item: the list of per-cloud ascending inlier index arrays (views into one buffer)."""
         nc = self._batch
         coeffs = np.zeros((nc, 4), np.float32)
         cnt = np.zeros(nc, np.int32)
         infos = (PrSegmentInfo * nc)() if want_infos else None
-        _lib.check(self._L.plane_ransac_segment_batch(self._h, C.byref(params), coeffs.ctypes.data_as(C.c_void_p),
-                                                      cnt.ctypes.data_as(C.c_void_p), infos))
-        return coeffs, cnt, infos
+        if not want_lists:
+            _lib.check(self._L.plane_ransac_segment_batch(self._h, C.byref(params), coeffs.ctypes.data_as(C.c_void_p),
+                                                          cnt.ctypes.data_as(C.c_void_p), infos))
+            return coeffs, cnt, infos
+        offs = np.zeros(nc + 1, np.uintp)
+        cap = max(1, self._batch_n * nc // 2)
+        for _ in range(2):
+            buf = np.empty(cap, np.int32)
+            rc = self._L.plane_ransac_segment_batch_lists(self._h, C.byref(params), coeffs.ctypes.data_as(C.c_void_p),
+                                                          cnt.ctypes.data_as(C.c_void_p), buf.ctypes.data_as(C.c_void_p), cap,
+                                                          offs.ctypes.data_as(C.c_void_p), infos)
+            if rc != -4:
+                break
+            cap = int(offs[nc])    # PR_ERR_CAPACITY: the offsets say how much is needed
+        _lib.check(rc)
+        return coeffs, cnt, infos, [buf[int(offs[k]): int(offs[k + 1])] for k in range(nc)]
 
     def plane_points(self, k: int, project: bool = False) -> np.ndarray:
         """Plane::points_set of plane k of the last extract call; project=True gives the cloud polyPointCloud

@@ -241,11 +241,19 @@ int plane_ransac_restage_remaining(plane_ransac_ctx* ctx);
 
 /* ---- batch of equal-sized small clouds (per-scan tiles), one best plane each, no peel --------
  * pts: n_clouds * n_per_cloud points.  Every cloud runs segment() with the same parameters (and,
- * having the same size and seed, the same index triples).  coeffs: 4*n_clouds; n_inliers: n_clouds. */
+ * having the same size and seed, the same index triples).  coeffs: 4*n_clouds; n_inliers: n_clouds.
+ * Single best plane per cloud, no peel (a tile that needs its planes peeled is a cloud for plane_ransac_extract_planes). */
 int plane_ransac_set_cloud_batch(plane_ransac_ctx* ctx, const pr_point* pts, size_t n_clouds,
                                  size_t n_per_cloud);
 int plane_ransac_segment_batch(plane_ransac_ctx* ctx, const pr_params* prm, float* coeffs,
                                int32_t* n_inliers, pr_segment_info* infos /* optional, n_clouds */);
+/* The same with segment()'s `inliers` output for every cloud: offsets (n_clouds + 1 entries) delimits the clouds' lists
+ * inside `inliers` (capacity cap entries in total; NULL to get the offsets alone); each list holds ascending indices into
+ * its own cloud.  When the lists do not fit, coefficients, counts and offsets are still filled and PR_ERR_CAPACITY is
+ * returned (offsets[n_clouds] is the capacity needed).  In score-all mode the whole batch runs without the host in the
+ * loop (see PR_LOOP_AUTO); a shard of a larger batch (cloud_id % n_gpu == rank) is just a smaller batch: no collective. */
+int plane_ransac_segment_batch_lists(plane_ransac_ctx* ctx, const pr_params* prm, float* coeffs, int32_t* n_inliers,
+                                     int32_t* inliers, size_t cap, size_t* offsets, pr_segment_info* infos);
 
 /* ---- point-sharded multi-GPU (one process per GPU; NCCL over NVLink) -------------------------
  * Rank r stages its contiguous index range of the global cloud with plane_ransac_set_cloud; after

@@ -160,6 +160,19 @@ def main():
     assert len(got_p.planes) == len(want_p.planes)
     for a, b in zip(got_p.planes, want_p.planes):
         assert a.coeff.tobytes() == b.coeff.tobytes() and a.info.n_inliers == b.info.n_inliers
+    # BASELINE configs[4]: a batch of 32K-point tiles sharded by cloud id (cloud_id % world == rank): replicas only, no
+    # collective — every rank checks its 64 clouds against the per-cloud answer of a plain single-GPU context
+    from oracle import oracle as O
+    ids = [cid for cid in range(64 * world) if cid % world == rank]
+    tiles = np.stack([synth.tile_scene(cid).points(0, 32768) for cid in ids])
+    prm_b5 = D.make_params(0.1, 255, 500, 1.0, True, 12345, 1, D.DOT_FMA)
+    with D.PlaneRansac(local) as tb:
+        tb.set_cloud_batch(tiles)
+        bc, bn, bi, bl = tb.segment_batch(prm_b5, want_lists=True)
+    for j, cid in enumerate(ids[:: max(1, len(ids) // 16)]):     # 16 of the 64 against the CPU oracle (the rest: see tests/test_gpu_parity.py)
+        k = ids.index(cid)
+        seg = O.segment(tiles[k], O.make_params(0.1, 255, 500, 1.0, True, 12345, 1, O.DOT_FMA, O.REFIT_FIXED))
+        assert seg.ok and bc[k].tobytes() == seg.coeff.tobytes() and np.array_equal(bl[k], seg.inliers), f"batch cloud {cid} on rank {rank}"
     sh.close()
     dist.barrier()
     if rank == 0:

@@ -490,8 +490,9 @@ def test_pcl_overload_runs_on_stub_pcl(O, lib_built, scene2, tmp_path, pin):
 # ---------------------------------------------------------------------------------------------
 # batch of small clouds (BASELINE config 5): one segment() per cloud, no peel
 # ---------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("n_clouds,n_per,max_it,prob,opt,order", [(37, 5000, 255, 1.0, True, 1), (16, 32768, 255, 1.0, True, 1),
-                                                                  (9, 1024, 50, 0.99, True, 0), (5, 3000, 99, 1.0, False, 1)])
+@pytest.mark.parametrize("n_clouds,n_per,max_it,prob,opt,order", [(37, 5000, 255, 1.0, True, 1), (64, 32768, 255, 1.0, True, 1),
+                                                                  (9, 1024, 50, 0.99, True, 0), (5, 3000, 99, 1.0, False, 1),
+                                                                  (9, 1024, 63, 1.0, True, 1)])
 def test_segment_batch_matches_per_cloud_oracle(O, pr, n_clouds, n_per, max_it, prob, opt, order):
     import dialog_b200 as D
     from dialog_b200 import synth
@@ -502,9 +503,21 @@ def test_segment_batch_matches_per_cloud_oracle(O, pr, n_clouds, n_per, max_it, 
         clouds[4, :, :3] = np.c_[i, 2 * i, 4 * i]         # all samples collinear: no model
     prm = D.make_params(0.1, max_it, 500, prob, opt, 12345, 1, order)
     pr.set_cloud_batch(clouds)
-    coeffs, cnt, infos = pr.segment_batch(prm)
+    coeffs, cnt, infos, lists = pr.segment_batch(prm, want_lists=True)
+    c2, n2, _ = pr.segment_batch(prm)                   # counts-only entry point: same planes
+    assert _same_bits(c2, coeffs) and (n2 == cnt).all()
+    pr.set_round_loop(host=True)                        # the host-driven path gives the same batch
+    try:
+        c3, n3, i3, l3 = pr.segment_batch(prm, want_lists=True)
+    finally:
+        pr.set_round_loop(host=False)
+    assert _same_bits(c3, coeffs) and (n3 == cnt).all() and all(np.array_equal(a, b) for a, b in zip(l3, lists))
+    assert all(i3[k].best_count == infos[k].best_count and list(i3[k].best_sample) == list(infos[k].best_sample) for k in range(n_clouds))
     for cid in range(n_clouds):
         seg = O.segment(clouds[cid], _oparams(O, prm))
+        assert lists[cid].size == cnt[cid]
+        if seg.ok:
+            assert np.array_equal(lists[cid], seg.inliers), cid
         assert bool(infos[cid].ok) == seg.ok, cid
         assert infos[cid].iterations == seg.trace.iterations and infos[cid].draws == seg.trace.draws
         if not seg.ok:
