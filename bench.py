@@ -531,14 +531,15 @@ def run_config5(args, torch, dist, D, local_rank, world, rank, peak_tf):
     if rank != 0:
         return None
     ms_b, ms_e = t.tolist()
-    pairs = total * n_per * (K + 1)      # K hypotheses + the final selection per cloud
+    pairs = total * n_per * K
     score_tf = 6.0 * prof.pairs_scored / (prof.ms_score * 1e-3) / 1e12 if prof.ms_score > 0 else None
     return {"clouds_total": total, "clouds_per_gpu": len(ids), "points_per_cloud": n_per, "hypotheses_per_cloud": K, "n_gpus": world,
             "sharding": "cloud_id % n_gpus, no collective; one gather of (coefficients, count) per cloud at the end",
             "ms_per_batch": ms_b, "clouds_per_s": total / (ms_b * 1e-3), "point_hypotheses_per_s": pairs / (ms_b * 1e-3),
             "frac_of_fp32_peak_whole_call": 6.0 * pairs / (ms_b * 1e-3) / 1e12 / (peak_tf * world),
             "score_kernel_frac_of_fp32_peak": score_tf / peak_tf if score_tf else None,
-            "kernel_ms": {"gather_models": prof.ms_models / 5, "score": prof.ms_score / 5, "refit": prof.ms_refit / 5, "other": prof.ms_other / 5},
+            "kernel_ms": {"gather_models": prof.ms_models / 5, "score": prof.ms_score / 5, "refit": prof.ms_refit / 5,
+                          "final_count": prof.ms_compact / 5, "other": prof.ms_other / 5},
             "e2e_ms_per_batch": ms_e, "e2e_clouds_per_s": total / (ms_e * 1e-3),
             "e2e_note": "pinned host tiles in (%d MB per GPU), coefficients + counts + every cloud's inlier index list out" % (len(ids) * n_per * 16 // 2**20),
             "mean_inliers": float(res[:, 4].mean().item()), "clouds_with_plane": int((res[:, 4] >= 500).sum().item())}

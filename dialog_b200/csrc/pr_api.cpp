@@ -2211,10 +2211,8 @@ int segment_batch_device(plane_ransac_ctx* c, const pr_params* prm, float* coeff
   }
   const int32_t* d_final = c->d_batch_bestcnt.p;  // without the refit the raw model's count is the final one
   if (prm->optimize_coefficients) {
-    PR_CUDA(cudaMemsetAsync(c->d_batch_cnt.p, 0, C * sizeof(int32_t), c->stream));
-    Span sp(c, KC_SCORE, 0);
-    c->prof.launches_score += pr::launch_score(c->batch_view, n, (int)C, stride, c->d_batch_hyps.p, 1, t, prm->dot_order, c->d_batch_cnt.p, c->num_sms, c->stream);
-    c->prof.pairs_scored += (long long)(n * C);
+    Span sp(c, KC_COMPACT, 1);
+    pr::launch_batch_count(c->batch_view, n, stride, (int)C, c->d_batch_hyps.p, c->d_batch_best.p, t, prm->dot_order, c->d_batch_cnt.p, c->stream);
     d_final = c->d_batch_cnt.p;
   }
   PR_CUDA(cudaGetLastError());

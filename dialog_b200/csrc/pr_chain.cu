@@ -378,6 +378,52 @@ __global__ void __launch_bounds__(256) batch_lists_kernel(const float* __restric
   }
 }
 
+// countWithinDistance of one plane per cloud (the final selection's size): block per cloud, HBM-bound.  (K2 with one
+// hypothesis per cloud would leave 31 of 32 lanes of its hypothesis-per-lane layout empty.)
+template <int DOT>
+__global__ void __launch_bounds__(256) batch_count_kernel(const float* __restrict__ X, const float* __restrict__ Y, const float* __restrict__ Z,
+                                                          size_t n_per, size_t stride, const float4* __restrict__ planes,
+                                                          const int32_t* __restrict__ best, float t, int32_t* __restrict__ cnt) {
+  __shared__ int s_warp[8];
+  const size_t c = blockIdx.x;
+  if (best[c] < 0) {
+    if (threadIdx.x == 0) cnt[c] = 0;
+    return;
+  }
+  const float4 pl = planes[c];
+  const float* x = X + c * stride;
+  const float* y = Y + c * stride;
+  const float* z = Z + c * stride;
+  int k = 0;
+  for (size_t i0 = 4 * (size_t)threadIdx.x; i0 < n_per; i0 += 1024) {
+    const float4 x4 = *reinterpret_cast<const float4*>(x + i0);
+    const float4 y4 = *reinterpret_cast<const float4*>(y + i0);
+    const float4 z4 = *reinterpret_cast<const float4*>(z + i0);
+    const float xs[4] = {x4.x, x4.y, x4.z, x4.w}, ys[4] = {y4.x, y4.y, y4.z, y4.w}, zs[4] = {z4.x, z4.y, z4.z, z4.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float r;
+      if (DOT == 1) r = __fmaf_rn(pl.x, xs[e], __fmaf_rn(pl.y, ys[e], __fmaf_rn(pl.z, zs[e], pl.w)));
+      else r = __fadd_rn(__fadd_rn(__fmul_rn(pl.x, xs[e]), __fmul_rn(pl.z, zs[e])), __fadd_rn(__fmul_rn(pl.y, ys[e]), pl.w));
+      k += (i0 + e < n_per && fabsf(r) < t) ? 1 : 0;
+    }
+  }
+  k = __reduce_add_sync(0xFFFFFFFFu, k);
+  if ((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = k;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int total = 0;
+    for (int w = 0; w < 8; ++w) total += s_warp[w];
+    cnt[c] = total;
+  }
+}
+
+void launch_batch_count(CloudView clouds, size_t n_per, size_t stride, int n_clouds, const float4* planes, const int32_t* best, float t,
+                        int dot_order, int32_t* cnt, cudaStream_t s) {
+  if (dot_order == 1) batch_count_kernel<1><<<n_clouds, 256, 0, s>>>(clouds.x, clouds.y, clouds.z, n_per, stride, planes, best, t, cnt);
+  else batch_count_kernel<0><<<n_clouds, 256, 0, s>>>(clouds.x, clouds.y, clouds.z, n_per, stride, planes, best, t, cnt);
+}
+
 void launch_batch_replay(const int32_t* counts, const int32_t* good, int K, int n_clouds, int32_t* best, int32_t* best_count, int* any_bad,
                          cudaStream_t s) {
   batch_replay_kernel<<<n_clouds, 128, 0, s>>>(counts, good, K, best, best_count, any_bad);

@@ -252,6 +252,9 @@ void launch_batch_replay(const int32_t* counts, const int32_t* good, int K, int 
 // raw[c] = hyps[c * K + best[c]]; refined[c] = closed-form plane from refit[c] on the 2^-scale_exp[c] grid (or raw[c]).
 void launch_batch_finish(const float4* hyps, int K, const int32_t* best, const RefitOut* refit, const int32_t* scale_exp, int optimize,
                          int n_clouds, float4* raw, float4* refined, cudaStream_t s);
+// cnt[c] = |{ i in cloud c : |planes[c] . (p_i, 1)| < t }| (0 where best[c] < 0)
+void launch_batch_count(CloudView clouds, size_t n_per, size_t stride, int n_clouds, const float4* planes, const int32_t* best, float t,
+                        int dot_order, int32_t* cnt, cudaStream_t s);
 // offs = exclusive scan of the per-cloud final counts; out (optional, cap entries) receives every cloud's ascending
 // inlier indices at offs[c] (clouds whose list would not fit are skipped).
 void launch_batch_lists(CloudView clouds, size_t n_per, size_t stride, int n_clouds, const float4* planes, const int32_t* best, float t,
