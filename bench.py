@@ -683,6 +683,14 @@ def main():
             for a, b in zip(exh.planes, ex.planes))
     hier_total_ms = sum(hier_ms)
 
+    # ---- per-rank time spent inside the exchange kernels waiting for the peers (lag of the slowest rank + NVLink round trip) ----
+    waits = None
+    if world > 1:
+        w = torch.tensor([list(prof.p2p_wait_ms) + [float(x) for x in prof.p2p_exchanges]], dtype=torch.float64, device="cuda")
+        allw = [torch.zeros_like(w) for _ in range(world)]
+        dist.all_gather(allw, w)
+        waits = [[v / args.steps for v in x.flatten().tolist()] for x in allw]
+
     # ---- max over ranks ----
     t = torch.tensor([total_ms, e2e_total_ms, hier_total_ms], dtype=torch.float64, device="cuda")
     agg = torch.tensor([float(h2d), float(d2h)], dtype=torch.float64, device="cuda")
@@ -734,6 +742,12 @@ def main():
                           "as kernels; the host reads one record per round",
             "clocks": clock_info,
         }
+        if waits:
+            line["exchange_wait_ms_per_step_by_rank"] = {
+                "channels": ["sample points", "counts", "refit moments", "remaining counts"],
+                "wait_ms": [x[:4] for x in waits], "exchanges_per_step": waits[0][4:],
+                "note": "time each rank's exchange kernels spin on the peers' flags inside the resident timed region: a rank that "
+                        "finishes its kernels early waits for the slowest one (straggling), every rank pays the NVLink round trip"}
         if hier_ms:
             line["hier_scorer"] = {
                 "ms_per_step": hier_total_ms / args.steps, "value": pairs_step / (hier_total_ms / args.steps * 1e-3),

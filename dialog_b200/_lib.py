@@ -71,7 +71,8 @@ class PrProfile(C.Structure):
                                             "launches_compact", "launches_other", "pairs_scored", "points_refit",
                                             "points_compact", "bytes_compact", "bytes_refit")] + \
                [(n, C.c_double) for n in ("host_ms_sampling", "host_ms_replay", "host_ms_wait", "host_ms_total")] + \
-               [(n, C.c_longlong) for n in ("points_kept", "points_peeled")]
+               [(n, C.c_longlong) for n in ("points_kept", "points_peeled")] + \
+               [("p2p_wait_ms", C.c_double * 4), ("p2p_exchanges", C.c_longlong * 4)]
 
 
 class PlaneRansacError(RuntimeError):

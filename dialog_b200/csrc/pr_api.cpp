@@ -215,6 +215,7 @@ struct plane_ransac_ctx {
   pr::P2PView p2p_view{};
   DevBuf<unsigned long long> d_p2p_epoch;           // per channel, identical on every rank; advanced by the exchange kernels
   DevBuf<unsigned> d_p2p_aux;                       // [4] timeout flag
+  DevBuf<unsigned long long> d_p2p_wait;            // per channel: ns spent waiting for the peers' flags, exchanges
   bool comm_failed = false;                         // an exchange timed out: the ranks are out of step for good
   PinBuf<unsigned> h_p2p_err;
   long long n_global_staged = 0, first_staged = 0, n_global_current = 0, first_current = 0;
@@ -663,12 +664,15 @@ constexpr size_t kP2PMailboxBytes = kP2POffTotals + 2 * pr::kP2PMaxRanks * kP2PT
 inline size_t p2p_flag_off(int ch) { return (size_t)ch * pr::kP2PMaxRanks * sizeof(unsigned long long); }
 
 // K1a + its exchange: sample points of `n_samples` indices into dsp on every rank.  st: the shard extent comes from the
-// device-resident round state and the exchange is skipped once the peel loop has stopped (run_chain).
+// device-resident round state and the exchange is skipped once the peel loop has stopped (run_chain); tail: the small
+// step that consumes the result, run by the exchange kernel itself (peer-memory mode only — check with p2p_takes_tail).
+bool p2p_takes_tail(const plane_ransac_ctx* c, size_t n_hyps) { return c->p2p_on && n_hyps <= kP2PMaxHyps; }
+
 int exchange_samples(plane_ransac_ctx* c, pr::CloudView src, long long first, size_t n_local, const int32_t* dt, int n_samples,
-                     int4* dsp, const pr::RoundState* st = nullptr) {
+                     int4* dsp, pr::RoundState* st = nullptr, const pr::P2PTail* tail = nullptr) {
   if (c->p2p_on && (size_t)n_samples <= 3 * kP2PMaxHyps) {
     pr::launch_p2p_samples(c->p2p_view, src, first, n_local, dt, n_samples, kP2POffSamples, kP2PSamplesBytes, p2p_flag_off(P2P_SAMPLES),
-                           c->d_p2p_epoch.p + P2P_SAMPLES, dsp, c->d_p2p_aux.p + 4, c->stream, st);
+                           c->d_p2p_epoch.p + P2P_SAMPLES, dsp, c->d_p2p_aux.p + 4, c->stream, st, c->d_p2p_wait.p + 2 * P2P_SAMPLES, tail);
     return PR_OK;
   }
   pr::launch_gather_samples(src, first, n_local, dt, n_samples, dsp, 1, 0, c->stream, false, st);
@@ -677,11 +681,11 @@ int exchange_samples(plane_ransac_ctx* c, pr::CloudView src, long long first, si
 }
 
 // counts[0..n) summed over ranks, in place.
-int exchange_counts(plane_ransac_ctx* c, int32_t* dc, size_t n, const pr::RoundState* st = nullptr) {
+int exchange_counts(plane_ransac_ctx* c, int32_t* dc, size_t n, pr::RoundState* st = nullptr, const pr::P2PTail* tail = nullptr) {
   if (!c->comm) return PR_OK;
   if (c->p2p_on && n <= kP2PMaxHyps) {
     pr::launch_p2p_allreduce_i32(c->p2p_view, dc, n, kP2POffCounts, pr::kP2PMaxRanks * kP2PCountsSlot, kP2PCountsSlot, p2p_flag_off(P2P_COUNTS),
-                                 c->d_p2p_epoch.p + P2P_COUNTS, dc, c->d_p2p_aux.p + 4, c->stream, st);
+                                 c->d_p2p_epoch.p + P2P_COUNTS, dc, c->d_p2p_aux.p + 4, c->stream, st, c->d_p2p_wait.p + 2 * P2P_COUNTS, tail);
     return PR_OK;
   }
   PR_NCCL(g_nccl.AllReduce(dc, dc, n, ncclInt32, ncclSum, c->comm, c->stream));
@@ -689,12 +693,12 @@ int exchange_counts(plane_ransac_ctx* c, int32_t* dc, size_t n, const pr::RoundS
 }
 
 // the 16 integer moments of d_refit summed over ranks, in place (the pivot behind them is identical everywhere).
-int exchange_refit(plane_ransac_ctx* c, const pr::RoundState* st = nullptr) {
+int exchange_refit(plane_ransac_ctx* c, pr::RoundState* st = nullptr, const pr::P2PTail* tail = nullptr) {
   if (!c->comm) return PR_OK;
   if (c->p2p_on) {
     long long* m = reinterpret_cast<long long*>(c->d_refit.p);
     pr::launch_p2p_allreduce_i64(c->p2p_view, m, 16, kP2POffRefit, pr::kP2PMaxRanks * kP2PRefitSlot, kP2PRefitSlot, p2p_flag_off(P2P_REFIT),
-                                 c->d_p2p_epoch.p + P2P_REFIT, m, c->d_p2p_aux.p + 4, c->stream, st);
+                                 c->d_p2p_epoch.p + P2P_REFIT, m, c->d_p2p_aux.p + 4, c->stream, st, c->d_p2p_wait.p + 2 * P2P_REFIT, tail);
     return PR_OK;
   }
   PR_NCCL(g_nccl.AllReduce(c->d_refit.p, c->d_refit.p, 16, ncclInt64, ncclSum, c->comm, c->stream));
@@ -702,11 +706,12 @@ int exchange_refit(plane_ransac_ctx* c, const pr::RoundState* st = nullptr) {
 }
 
 // all-gather of (remaining, inliers): d_totals[0..2) of every rank -> d_totals[2 + 2r ..).
-int exchange_totals(plane_ransac_ctx* c, const pr::RoundState* st = nullptr) {
+int exchange_totals(plane_ransac_ctx* c, pr::RoundState* st = nullptr, const pr::P2PTail* tail = nullptr) {
   if (!c->comm) return PR_OK;
   if (c->p2p_on) {
     pr::launch_p2p_allgather_i64(c->p2p_view, c->d_totals.p, 2, kP2POffTotals, pr::kP2PMaxRanks * kP2PTotalsSlot, kP2PTotalsSlot,
-                                 p2p_flag_off(P2P_TOTALS), c->d_p2p_epoch.p + P2P_TOTALS, c->d_totals.p + 2, c->d_p2p_aux.p + 4, c->stream, st);
+                                 p2p_flag_off(P2P_TOTALS), c->d_p2p_epoch.p + P2P_TOTALS, c->d_totals.p + 2, c->d_p2p_aux.p + 4, c->stream, st,
+                                 c->d_p2p_wait.p + 2 * P2P_TOTALS, tail);
     return PR_OK;
   }
   PR_NCCL(g_nccl.AllGather(c->d_totals.p, c->d_totals.p + 2, 2, ncclInt64, c->comm, c->stream));
@@ -1133,13 +1138,16 @@ int run_chain(plane_ransac_ctx* c, const pr_params* prm, PeelCursor& cur, float*
       pr::RoundRecord* rec = c->h_recs.p + r;  // mapped host memory (unified addressing)
       uint32_t* coll_count = c->d_draw_coll.p + pr::kDrawCollCap;
       {
-        Span sp(c, KC_MODELS, sharded ? 5 : 4);
+        Span sp(c, KC_MODELS, 4);
         pr::launch_round_prep(rs, c->d_draw_table.p, slots, coll_count, c->d_counts.p, K, c->d_refit.p, c->d_scratch.p, scratch_bytes,
                               c->d_chain_tickets.p, c->num_sms, c->stream);
         pr::launch_draw(c->d_rnd.p, K, rs, c->d_triples.p, c->d_draw_table.p, slots, c->d_draw_coll.p, coll_count, rec, c->stream);
-        if (sharded) {
-          PR_TRY(exchange_samples(c, src, 0, 0, c->d_triples.p, 3 * K, c->d_sample_pts.p, rs));
-          pr::launch_models(c->d_sample_pts.p, K, c->d_hyps.p, c->d_good.p, c->stream);
+        if (sharded) {  // (chain_eligible: sharded implies peer-memory exchanges, which run the consuming step themselves)
+          pr::P2PTail tm;
+          tm.kind = pr::P2PTail::kModels;
+          tm.hyps_out = c->d_hyps.p;
+          tm.good_out = c->d_good.p;
+          PR_TRY(exchange_samples(c, src, 0, 0, c->d_triples.p, 3 * K, c->d_sample_pts.p, rs, &tm));
         } else {
           pr::launch_gather_models(src, c->d_triples.p, K, c->d_sample_pts.p, c->d_hyps.p, c->d_good.p, rs, c->stream);
         }
@@ -1148,8 +1156,14 @@ int run_chain(plane_ransac_ctx* c, const pr_params* prm, PeelCursor& cur, float*
         Span sp(c, KC_SCORE, 0);
         c->prof.launches_score += pr::launch_score(src, n_bound, 1, 0, c->d_hyps.p, K, t, prm->dot_order, c->d_counts.p, c->num_sms, c->stream, rs);
       }
-      PR_TRY(exchange_counts(c, c->d_counts.p, (size_t)K, rs));
-      {
+      if (sharded) {
+        Span sp(c, KC_OTHER, 1);
+        pr::P2PTail tr;
+        tr.kind = pr::P2PTail::kReplay;
+        tr.rec = rec;
+        tr.good = c->d_good.p;
+        PR_TRY(exchange_counts(c, c->d_counts.p, (size_t)K, rs, &tr));
+      } else {
         Span sp(c, KC_OTHER, 1);
         pr::launch_replay(c->d_counts.p, c->d_good.p, K, rs, rec, c->stream);
       }
@@ -1167,11 +1181,21 @@ int run_chain(plane_ransac_ctx* c, const pr_params* prm, PeelCursor& cur, float*
           pr::launch_refit(src, n_bound, c->d_hyps.p, c->d_sample_pts.p, 0, t, prm->dot_order, c->scale_exp, c->d_refit.p, c->num_sms, c->stream, rs,
                            sharded ? nullptr : &tail);
         }
-        PR_TRY(exchange_refit(c, rs));
-      }
-      if (sharded || !prm->optimize_coefficients) {
+        if (sharded) {
+          Span sp(c, KC_OTHER, 1);
+          pr::P2PTail tf;
+          tf.kind = pr::P2PTail::kFinish;
+          tf.rec = rec;
+          tf.hyps = c->d_hyps.p;
+          tf.triples = c->d_triples.p;
+          tf.optimize = 1;
+          tf.scale_exp = c->scale_exp;
+          tf.n_draws = K;
+          PR_TRY(exchange_refit(c, rs, &tf));
+        }
+      } else {
         Span sp(c, KC_OTHER, 1);
-        pr::launch_finish(rs, c->d_hyps.p, c->d_triples.p, c->d_refit.p, prm->optimize_coefficients ? 1 : 0, c->scale_exp, K, rec, c->stream);
+        pr::launch_finish(rs, c->d_hyps.p, c->d_triples.p, c->d_refit.p, 0, c->scale_exp, K, rec, c->stream);
       }
       {
         Span sp(c, KC_COMPACT, 1);
@@ -1180,9 +1204,12 @@ int run_chain(plane_ransac_ctx* c, const pr_params* prm, PeelCursor& cur, float*
                            c->stream, nullptr, rs, sharded ? nullptr : &tail);
       }
       if (sharded) {
-        PR_TRY(exchange_totals(c, rs));
         Span sp(c, KC_OTHER, 1);
-        pr::launch_advance(rs, c->d_totals.p, c->n_ranks, c->rank, prm->min_plane_size, rec, c->stream);
+        pr::P2PTail ta;
+        ta.kind = pr::P2PTail::kAdvance;
+        ta.rec = rec;
+        ta.min_plane = prm->min_plane_size;
+        PR_TRY(exchange_totals(c, rs, &ta));
       }
       PR_CUDA(cudaGetLastError());
       PR_CUDA(cudaEventRecord(c->round_ev[r], c->stream));
@@ -1372,7 +1399,9 @@ int p2p_setup(plane_ransac_ctx* c) {
   c->p2p_on = ok != 0;
   if (rc == PR_OK) {
     PR_TRY(dev_reserve(c->d_p2p_epoch, 4));
+    PR_TRY(dev_reserve(c->d_p2p_wait, 8));
     PR_CUDA(cudaMemsetAsync(c->d_p2p_epoch.p, 0, 4 * sizeof(unsigned long long), c->stream));
+    PR_CUDA(cudaMemsetAsync(c->d_p2p_wait.p, 0, 8 * sizeof(unsigned long long), c->stream));
     PR_CUDA(cudaStreamSynchronize(c->stream));
   }
   return rc;
@@ -1442,6 +1471,7 @@ void plane_ransac_destroy(plane_ransac_ctx* c) {
   p2p_teardown(c, c->p2p_on);
   dev_free(c->d_p2p_aux);
   dev_free(c->d_p2p_epoch);
+  dev_free(c->d_p2p_wait);
   pin_free(c->h_p2p_err);
   dev_free(c->d_state); pin_free(c->h_state); pin_free(c->h_recs); dev_free(c->d_chain_tickets);
   dev_free(c->d_rnd); dev_free(c->d_draw_table); dev_free(c->d_draw_coll);
@@ -2540,6 +2570,7 @@ int plane_ransac_profile_reset(plane_ransac_ctx* c) {
   PR_TRY(check_ctx(c));
   collect_spans(c);
   std::memset(&c->prof, 0, sizeof(c->prof));
+  if (c->d_p2p_wait.p) PR_CUDA(cudaMemsetAsync(c->d_p2p_wait.p, 0, 8 * sizeof(unsigned long long), c->stream));
   return PR_OK;
 }
 
@@ -2548,6 +2579,15 @@ int plane_ransac_profile_get(plane_ransac_ctx* c, pr_profile* out) {
   if (!out) return fail(PR_ERR_INVALID, "null output");
   collect_spans(c);
   *out = c->prof;
+  if (c->d_p2p_wait.p) {
+    unsigned long long w[8];
+    PR_CUDA(cudaMemcpyAsync(w, c->d_p2p_wait.p, sizeof(w), cudaMemcpyDeviceToHost, c->stream));
+    PR_CUDA(cudaStreamSynchronize(c->stream));
+    for (int ch = 0; ch < 4; ++ch) {
+      out->p2p_wait_ms[ch] = (double)w[2 * ch] * 1e-6;
+      out->p2p_exchanges[ch] = (long long)w[2 * ch + 1];
+    }
+  }
   return PR_OK;
 }
 

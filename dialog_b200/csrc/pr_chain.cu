@@ -134,42 +134,11 @@ __global__ void __launch_bounds__(kResolveThreads) draw_resolve_kernel(RoundStat
   draw_resolve(s_sorted, (int)n_c, v, fetch, s_keys, s_vals, (uint32_t)(kResolveMapSlots - 1));
 }
 
-// ---- RandomSampleConsensus::computeModel over the K counts of a score-all round ------------------------------------------
-// With probability 1 the loop scores max_iterations + 1 good samples and keeps the first one with the largest count
-// (strict '>' against n_best = -INT_MAX).  A bad sample among the K draws means the loop needs more draws than were
-// scored: the round goes back to the host loop (stop = 2), which replays PCL's redraw rule.
-constexpr int kReplayThreads = 1024;
-
-__global__ void __launch_bounds__(kReplayThreads) replay_kernel(const int32_t* __restrict__ counts, const int32_t* __restrict__ good, int K,
-                                                                RoundState* st, RoundRecord* rec) {
-  __shared__ unsigned long long s_best[kReplayThreads / 32];
+// ---- computeModel's decision over the K counts (pr_chain_dev.cuh chain_replay_block) as its own kernel (one GPU) ------
+__global__ void __launch_bounds__(kChainBlock) replay_kernel(const int32_t* __restrict__ counts, const int32_t* __restrict__ good, int K,
+                                                             RoundState* st, RoundRecord* rec) {
   if (st->stop) return;
-  unsigned long long best = 0ull;
-  int all_good = 1;
-  for (int j = threadIdx.x; j < K; j += kReplayThreads) {
-    if (!good[j]) all_good = 0;
-    const unsigned long long key = ((unsigned long long)(unsigned)counts[j] << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)j);
-    best = key > best ? key : best;
-  }
-  all_good = __syncthreads_and(all_good);
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const unsigned long long other = __shfl_down_sync(0xFFFFFFFFu, best, o);
-    best = other > best ? other : best;
-  }
-  if ((threadIdx.x & 31) == 0) s_best[threadIdx.x >> 5] = best;
-  __syncthreads();
-  if (threadIdx.x != 0) return;
-  for (int w = 1; w < kReplayThreads / 32; ++w) best = s_best[w] > best ? s_best[w] : best;
-  if (!all_good) {
-    st->stop = 2;
-    rec->stop = 2;
-    __threadfence_system();
-    rec->ran = 1;
-    return;
-  }
-  st->best = (int)(0xFFFFFFFFu - (unsigned)(best & 0xFFFFFFFFull));
-  st->best_count = (int)(best >> 32);
+  chain_replay_block(counts, good, K, st, rec);
 }
 
 // ---- refined plane + stop rule as their own kernels (sharded clouds: an exchange sits between them and K3 / K5; on one
@@ -212,7 +181,7 @@ size_t draw_table_slots(int n_draws) {
 }
 
 void launch_replay(const int32_t* counts, const int32_t* good, int K, RoundState* st, RoundRecord* rec, cudaStream_t s) {
-  replay_kernel<<<1, kReplayThreads, 0, s>>>(counts, good, K, st, rec);
+  replay_kernel<<<1, kChainBlock, 0, s>>>(counts, good, K, st, rec);
 }
 
 void launch_finish(RoundState* st, const float4* hyps, const int32_t* triples, const RefitOut* refit, int optimize, int scale_exp,

@@ -3,10 +3,75 @@
 // between the moments and the plane, or between the peel and the stop rule), saving two launches per round.
 #pragma once
 
+#include <math_constants.h>
+
 #include "pr_kernels.h"
 #include "pr_math.h"
 
 namespace pr {
+
+// PCL SampleConsensusModelPlane::isSampleGood + computeModelCoefficients (sac_model_plane.hpp), FP32,
+// every operation rounded on its own; reductions in Eigen's SSE2 order (e0 + e2) + (e1 + e3).
+__device__ __forceinline__ bool model_from_sample(int4 q0, int4 q1, int4 q2, float4* out) {
+  float p0x = __int_as_float(q0.x), p0y = __int_as_float(q0.y), p0z = __int_as_float(q0.z);
+  float ux = __fsub_rn(__int_as_float(q1.x), p0x), uy = __fsub_rn(__int_as_float(q1.y), p0y),
+        uz = __fsub_rn(__int_as_float(q1.z), p0z);
+  float vx = __fsub_rn(__int_as_float(q2.x), p0x), vy = __fsub_rn(__int_as_float(q2.y), p0y),
+        vz = __fsub_rn(__int_as_float(q2.z), p0z);
+  float r0 = __fdiv_rn(ux, vx), r1 = __fdiv_rn(uy, vy), r2 = __fdiv_rn(uz, vz);
+  bool ok = (r0 != r1) || (r2 != r1);
+  float4 h = make_float4(CUDART_NAN_F, CUDART_NAN_F, CUDART_NAN_F, CUDART_NAN_F);
+  if (ok) {
+    float nx = __fsub_rn(__fmul_rn(uy, vz), __fmul_rn(uz, vy));
+    float ny = __fsub_rn(__fmul_rn(uz, vx), __fmul_rn(ux, vz));
+    float nz = __fsub_rn(__fmul_rn(ux, vy), __fmul_rn(uy, vx));
+    float sq = __fadd_rn(__fadd_rn(__fmul_rn(nx, nx), __fmul_rn(nz, nz)), __fadd_rn(__fmul_rn(ny, ny), 0.0f));
+    float nrm = __fsqrt_rn(sq);
+    nx = __fdiv_rn(nx, nrm);
+    ny = __fdiv_rn(ny, nrm);
+    nz = __fdiv_rn(nz, nrm);
+    float dot = __fadd_rn(__fadd_rn(__fmul_rn(nx, p0x), __fmul_rn(nz, p0z)), __fadd_rn(__fmul_rn(ny, p0y), 0.0f));
+    h = make_float4(nx, ny, nz, __fmul_rn(-1.0f, dot));
+  }
+  *out = h;
+  return ok;
+}
+
+// RandomSampleConsensus::computeModel over the K counts of a score-all round, by one block of kChainBlock threads (all
+// of them must call it).  With probability 1 the loop scores max_iterations + 1 good samples and keeps the first one
+// with the largest count (strict '>' against n_best = -INT_MAX).  A bad sample among the K draws means the loop needs
+// more draws than were scored: the round goes back to the host loop (stop = 2), which replays PCL's redraw rule.
+constexpr int kChainBlock = 1024;
+__device__ __forceinline__ void chain_replay_block(const int32_t* counts, const int32_t* __restrict__ good, int K, RoundState* st,
+                                                   RoundRecord* rec) {
+  __shared__ unsigned long long s_best[kChainBlock / 32];
+  unsigned long long best = 0ull;
+  int all_good = 1;
+  for (int j = threadIdx.x; j < K; j += kChainBlock) {
+    if (!good[j]) all_good = 0;
+    const unsigned long long key = ((unsigned long long)(unsigned)counts[j] << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)j);
+    best = key > best ? key : best;
+  }
+  all_good = __syncthreads_and(all_good);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long other = __shfl_down_sync(0xFFFFFFFFu, best, o);
+    best = other > best ? other : best;
+  }
+  if ((threadIdx.x & 31) == 0) s_best[threadIdx.x >> 5] = best;
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  for (int w = 1; w < kChainBlock / 32; ++w) best = s_best[w] > best ? s_best[w] : best;
+  if (!all_good) {
+    st->stop = 2;
+    rec->stop = 2;
+    __threadfence_system();
+    rec->ran = 1;
+    return;
+  }
+  st->best = (int)(0xFFFFFFFFu - (unsigned)(best & 0xFFFFFFFFull));
+  st->best_count = (int)(best >> 32);
+}
 
 // Refined plane of the round (PCL optimizeModelCoefficients: closed form from the summed moments, pr_math.h) + the
 // round's record.  m: the 16 moments as this thread sees them (already summed over blocks / ranks).

@@ -341,33 +341,7 @@ __global__ void __launch_bounds__(256) gather_samples_kernel(const float* __rest
   }
 }
 
-// PCL SampleConsensusModelPlane::isSampleGood + computeModelCoefficients (sac_model_plane.hpp), FP32,
-// every operation rounded on its own; reductions in Eigen's SSE2 order (e0 + e2) + (e1 + e3).
-__device__ __forceinline__ bool model_from_sample(int4 q0, int4 q1, int4 q2, float4* out) {
-  float p0x = __int_as_float(q0.x), p0y = __int_as_float(q0.y), p0z = __int_as_float(q0.z);
-  float ux = __fsub_rn(__int_as_float(q1.x), p0x), uy = __fsub_rn(__int_as_float(q1.y), p0y),
-        uz = __fsub_rn(__int_as_float(q1.z), p0z);
-  float vx = __fsub_rn(__int_as_float(q2.x), p0x), vy = __fsub_rn(__int_as_float(q2.y), p0y),
-        vz = __fsub_rn(__int_as_float(q2.z), p0z);
-  float r0 = __fdiv_rn(ux, vx), r1 = __fdiv_rn(uy, vy), r2 = __fdiv_rn(uz, vz);
-  bool ok = (r0 != r1) || (r2 != r1);
-  float4 h = make_float4(CUDART_NAN_F, CUDART_NAN_F, CUDART_NAN_F, CUDART_NAN_F);
-  if (ok) {
-    float nx = __fsub_rn(__fmul_rn(uy, vz), __fmul_rn(uz, vy));
-    float ny = __fsub_rn(__fmul_rn(uz, vx), __fmul_rn(ux, vz));
-    float nz = __fsub_rn(__fmul_rn(ux, vy), __fmul_rn(uy, vx));
-    float sq = __fadd_rn(__fadd_rn(__fmul_rn(nx, nx), __fmul_rn(nz, nz)), __fadd_rn(__fmul_rn(ny, ny), 0.0f));
-    float nrm = __fsqrt_rn(sq);
-    nx = __fdiv_rn(nx, nrm);
-    ny = __fdiv_rn(ny, nrm);
-    nz = __fdiv_rn(nz, nrm);
-    float dot = __fadd_rn(__fadd_rn(__fmul_rn(nx, p0x), __fmul_rn(nz, p0z)), __fadd_rn(__fmul_rn(ny, p0y), 0.0f));
-    h = make_float4(nx, ny, nz, __fmul_rn(-1.0f, dot));
-  }
-  *out = h;
-  return ok;
-}
-
+// model_from_sample (PCL isSampleGood + computeModelCoefficients) lives in pr_chain_dev.cuh: the exchange kernels use it too.
 __global__ void __launch_bounds__(128) models_kernel(const int4* __restrict__ sample_pts, int n_models,
                                                      float4* __restrict__ hyps, int32_t* __restrict__ good) {
   int k = blockIdx.x * blockDim.x + threadIdx.x;

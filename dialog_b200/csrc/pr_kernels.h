@@ -205,25 +205,42 @@ struct P2PView {
   int n_ranks;
   int rank;
 };
+// The host-free peel loop lets an exchange kernel also run the small step that consumes its result (same CTA, no extra
+// launch): computeModel's decision after the counts, the closed-form plane after the moments, the stop rule after the
+// totals, the models after the sample points.
+struct P2PTail {
+  enum { kNone = 0, kReplay, kFinish, kAdvance, kModels };
+  int kind = kNone;
+  RoundRecord* rec = nullptr;
+  const int32_t* good = nullptr;      // kReplay
+  const float4* hyps = nullptr;       // kFinish
+  const int32_t* triples = nullptr;   // kFinish
+  int optimize = 0, scale_exp = 0, n_draws = 0;  // kFinish
+  int min_plane = 0;                  // kAdvance
+  float4* hyps_out = nullptr;         // kModels
+  int32_t* good_out = nullptr;        // kModels
+};
 // One single-CTA kernel per exchange: store this rank's contribution into every peer's mailbox slot
 // (slot_off + parity * buffer_bytes + rank * slot_stride), raise flag[rank] = epoch in every peer's flag array (flag_off,
 // kP2PMaxRanks x uint64), wait (bounded; *err = 1 on timeout) for every rank's flag locally, then sum / concatenate in
 // rank order.  The epoch is *epoch_ctr + 1 (device counter, advanced by the kernel); parity = epoch & 1 selects one of
-// the channel's two buffers.  st: the exchange is skipped (no epoch consumed) once st->stop is set.
+// the channel's two buffers.  st: the exchange is skipped (no epoch consumed) once st->stop is set.  wait_ns (optional,
+// 2 x uint64): time spent spinning on the peers' flags and the number of exchanges, accumulated.
 void launch_p2p_allreduce_i32(const P2PView& v, const int32_t* src, size_t n, size_t slot_off, size_t buffer_bytes, size_t slot_stride,
                               size_t flag_off, unsigned long long* epoch_ctr, int32_t* dst, unsigned* err, cudaStream_t s,
-                              const RoundState* st = nullptr);
+                              RoundState* st = nullptr, unsigned long long* wait_ns = nullptr, const P2PTail* tail = nullptr);
 void launch_p2p_allreduce_i64(const P2PView& v, const long long* src, size_t n, size_t slot_off, size_t buffer_bytes, size_t slot_stride,
                               size_t flag_off, unsigned long long* epoch_ctr, long long* dst, unsigned* err, cudaStream_t s,
-                              const RoundState* st = nullptr);
+                              RoundState* st = nullptr, unsigned long long* wait_ns = nullptr, const P2PTail* tail = nullptr);
+// dst must directly follow the n source values in memory (src = dst - n) when the kAdvance tail is used.
 void launch_p2p_allgather_i64(const P2PView& v, const long long* src, size_t n, size_t slot_off, size_t buffer_bytes, size_t slot_stride,
                               size_t flag_off, unsigned long long* epoch_ctr, long long* dst, unsigned* err, cudaStream_t s,
-                              const RoundState* st = nullptr);
+                              RoundState* st = nullptr, unsigned long long* wait_ns = nullptr, const P2PTail* tail = nullptr);
 // K1a fused with its exchange: the owner of sample s writes the point's bits into every rank's sample buffer (sp_off);
 // dst receives all n_samples entries.  st: shard extent (first, n) from the device state.
 void launch_p2p_samples(const P2PView& v, CloudView cloud, long long first, size_t n, const int32_t* triples, int n_samples,
                         size_t sp_off, size_t buffer_bytes, size_t flag_off, unsigned long long* epoch_ctr, int4* dst, unsigned* err,
-                        cudaStream_t s, const RoundState* st = nullptr);
+                        cudaStream_t s, const RoundState* st = nullptr, unsigned long long* wait_ns = nullptr, const P2PTail* tail = nullptr);
 
 // ---- the peel loop without the host (pr_chain.cu): per-round kernels driven by a RoundState in HBM ------------------
 // PCL's index triples for a cloud of st->n_global points: rnd = the first 3 * n_draws values of mt19937(seed) >> 1,

@@ -14,6 +14,8 @@
 // coordinates directly into all peers' sample buffers.
 #include "pr_kernels.h"
 
+#include "pr_chain_dev.cuh"
+
 namespace pr {
 
 __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
@@ -34,9 +36,22 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
 // loads.  One launch instead of a producer + consumer pair or an NCCL collective.
 constexpr int kP2PThreads = 1024;
 
-__device__ __forceinline__ bool p2p_signal_and_wait(const P2PView& v, size_t flag_off, unsigned long long epoch, unsigned* err) {
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
+// wait_ns (optional): [0] += the longest any thread of this exchange spun on a peer's flag (ns), [1] += 1 — what a rank
+// loses per exchange to the slowest peer plus the NVLink round trip (pr_profile.p2p_wait_ms).
+__device__ __forceinline__ bool p2p_signal_and_wait(const P2PView& v, size_t flag_off, unsigned long long epoch, unsigned* err,
+                                                    unsigned long long* wait_ns) {
   __shared__ int s_bad;
-  if (threadIdx.x == 0) s_bad = 0;
+  __shared__ unsigned long long s_wait;
+  if (threadIdx.x == 0) {
+    s_bad = 0;
+    s_wait = 0ull;
+  }
   __threadfence_system();
   __syncthreads();
   if ((int)threadIdx.x < v.n_ranks) {
@@ -44,6 +59,7 @@ __device__ __forceinline__ bool p2p_signal_and_wait(const P2PView& v, size_t fla
     st_release_sys(reinterpret_cast<unsigned long long*>(v.peers[r] + flag_off) + v.rank, epoch);
     const unsigned long long* f = reinterpret_cast<const unsigned long long*>(v.peers[v.rank] + flag_off) + r;
     const long long t0 = clock64();
+    const unsigned long long w0 = global_ns();
     while (ld_acquire_sys(f) < epoch) {
       if (clock64() - t0 > 40000000000ll) {  // ~20 s: a lost peer becomes an error code, not a hung GPU
         atomicExch(err, 1u);
@@ -51,8 +67,13 @@ __device__ __forceinline__ bool p2p_signal_and_wait(const P2PView& v, size_t fla
         break;
       }
     }
+    atomicMax(&s_wait, global_ns() - w0);
   }
   __syncthreads();
+  if (threadIdx.x == 0 && wait_ns != nullptr) {
+    wait_ns[0] += s_wait;
+    wait_ns[1] += 1ull;
+  }
   return s_bad == 0;
 }
 
@@ -72,7 +93,8 @@ __device__ __forceinline__ bool p2p_enter(const RoundState* st, const unsigned l
 template <typename T>
 __global__ void __launch_bounds__(kP2PThreads) p2p_allreduce_kernel(P2PView v, const T* src, size_t n, size_t slot_off, size_t buffer_bytes,
                                                                     size_t slot_stride, size_t flag_off, unsigned long long* epoch_ctr,
-                                                                    T* dst, unsigned* err, const RoundState* st) {
+                                                                    T* dst, unsigned* err, RoundState* st, unsigned long long* wait_ns,
+                                                                    P2PTail tail) {
   unsigned long long epoch;
   if (!p2p_enter(st, epoch_ctr, err, &epoch)) return;
   slot_off += (size_t)(epoch & 1ull) * buffer_bytes;
@@ -80,7 +102,7 @@ __global__ void __launch_bounds__(kP2PThreads) p2p_allreduce_kernel(P2PView v, c
     T* out = reinterpret_cast<T*>(v.peers[r] + slot_off + (size_t)v.rank * slot_stride);
     for (size_t i = threadIdx.x; i < n; i += kP2PThreads) out[i] = src[i];
   }
-  if (!p2p_signal_and_wait(v, flag_off, epoch, err)) return;
+  if (!p2p_signal_and_wait(v, flag_off, epoch, err, wait_ns)) return;
   for (size_t i = threadIdx.x; i < n; i += kP2PThreads) {
     T acc = 0;
     for (int r = 0; r < v.n_ranks; ++r)
@@ -88,6 +110,20 @@ __global__ void __launch_bounds__(kP2PThreads) p2p_allreduce_kernel(P2PView v, c
     dst[i] = acc;
   }
   if (threadIdx.x == 0) *epoch_ctr = epoch;
+  // host-free peel loop: the step that consumes the sums runs in this CTA instead of a launch of its own
+  if (tail.kind == P2PTail::kReplay) {
+    __syncthreads();  // the sums are in dst (global memory, written by this block)
+    chain_replay_block(reinterpret_cast<const int32_t*>(dst), tail.good, (int)n, st, tail.rec);
+  } else if (tail.kind == P2PTail::kFinish) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const RefitOut* ro = reinterpret_cast<const RefitOut*>(dst);
+      long long m[16];
+      for (int i = 0; i < 16; ++i) m[i] = ro->m[i];
+      const float pivot[3] = {ro->pivot[0], ro->pivot[1], ro->pivot[2]};
+      chain_finish(st, tail.hyps, tail.triples, m, pivot, tail.optimize, tail.scale_exp, tail.n_draws, tail.rec);
+    }
+  }
 }
 
 // dst[r * n + i] = rank r's src[i]
@@ -95,7 +131,7 @@ template <typename T>
 __global__ void __launch_bounds__(kP2PThreads) p2p_allgather_kernel(P2PView v, const T* __restrict__ src, size_t n, size_t slot_off,
                                                                     size_t buffer_bytes, size_t slot_stride, size_t flag_off,
                                                                     unsigned long long* epoch_ctr, T* __restrict__ dst, unsigned* err,
-                                                                    const RoundState* st) {
+                                                                    RoundState* st, unsigned long long* wait_ns, P2PTail tail) {
   unsigned long long epoch;
   if (!p2p_enter(st, epoch_ctr, err, &epoch)) return;
   slot_off += (size_t)(epoch & 1ull) * buffer_bytes;
@@ -103,12 +139,16 @@ __global__ void __launch_bounds__(kP2PThreads) p2p_allgather_kernel(P2PView v, c
     T* out = reinterpret_cast<T*>(v.peers[r] + slot_off + (size_t)v.rank * slot_stride);
     for (size_t i = threadIdx.x; i < n; i += kP2PThreads) out[i] = src[i];
   }
-  if (!p2p_signal_and_wait(v, flag_off, epoch, err)) return;
+  if (!p2p_signal_and_wait(v, flag_off, epoch, err, wait_ns)) return;
   for (size_t i = threadIdx.x; i < n * (size_t)v.n_ranks; i += kP2PThreads) {
     const size_t r = i / n, k = i - r * n;
     dst[i] = __ldcg(reinterpret_cast<const T*>(v.peers[v.rank] + slot_off + r * slot_stride) + k);
   }
   if (threadIdx.x == 0) *epoch_ctr = epoch;
+  if (tail.kind == P2PTail::kAdvance) {  // dst - n = this rank's own (remaining, inliers) pair, dst = every rank's
+    __syncthreads();
+    if (threadIdx.x == 0) chain_advance(st, reinterpret_cast<const long long*>(dst) - n, v.n_ranks, v.rank, tail.min_plane, tail.rec);
+  }
 }
 
 // K1a fused with its exchange: the owner of sample s writes the point's bits into every rank's sample buffer; after
@@ -117,7 +157,8 @@ __global__ void __launch_bounds__(kP2PThreads) p2p_samples_kernel(P2PView v, con
                                                                   const float* __restrict__ z, long long first, size_t n,
                                                                   const int32_t* __restrict__ triples, int n_samples, size_t sp_off,
                                                                   size_t buffer_bytes, size_t flag_off, unsigned long long* epoch_ctr,
-                                                                  int4* __restrict__ dst, unsigned* err, const RoundState* st) {
+                                                                  int4* __restrict__ dst, unsigned* err, const RoundState* st,
+                                                                  unsigned long long* wait_ns, P2PTail tail) {
   unsigned long long epoch;
   if (!p2p_enter(st, epoch_ctr, err, &epoch)) return;
   if (st != nullptr) {
@@ -132,32 +173,46 @@ __global__ void __launch_bounds__(kP2PThreads) p2p_samples_kernel(P2PView v, con
       for (int r = 0; r < v.n_ranks; ++r) reinterpret_cast<int4*>(v.peers[r] + sp_off)[s] = val;
     }
   }
-  if (!p2p_signal_and_wait(v, flag_off, epoch, err)) return;
+  if (!p2p_signal_and_wait(v, flag_off, epoch, err, wait_ns)) return;
   const int4* in = reinterpret_cast<const int4*>(v.peers[v.rank] + sp_off);
   for (int s = threadIdx.x; s < n_samples; s += kP2PThreads) dst[s] = __ldcg(in + s);
   if (threadIdx.x == 0) *epoch_ctr = epoch;
+  if (tail.kind == P2PTail::kModels) {  // K1b in the same CTA: the models of the n_samples / 3 gathered triples
+    for (int k = threadIdx.x; k < n_samples / 3; k += kP2PThreads) {
+      float4 h;
+      const bool ok = model_from_sample(__ldcg(in + 3 * k), __ldcg(in + 3 * k + 1), __ldcg(in + 3 * k + 2), &h);
+      tail.hyps_out[k] = h;
+      tail.good_out[k] = ok ? 1 : 0;
+    }
+  }
 }
 
 void launch_p2p_allreduce_i32(const P2PView& v, const int32_t* src, size_t n, size_t slot_off, size_t buffer_bytes, size_t slot_stride,
-                              size_t flag_off, unsigned long long* epoch_ctr, int32_t* dst, unsigned* err, cudaStream_t s, const RoundState* st) {
-  p2p_allreduce_kernel<int32_t><<<1, kP2PThreads, 0, s>>>(v, src, n, slot_off, buffer_bytes, slot_stride, flag_off, epoch_ctr, dst, err, st);
+                              size_t flag_off, unsigned long long* epoch_ctr, int32_t* dst, unsigned* err, cudaStream_t s, RoundState* st,
+                              unsigned long long* wait_ns, const P2PTail* tail) {
+  p2p_allreduce_kernel<int32_t><<<1, kP2PThreads, 0, s>>>(v, src, n, slot_off, buffer_bytes, slot_stride, flag_off, epoch_ctr, dst, err, st,
+                                                          wait_ns, tail ? *tail : P2PTail());
 }
 
 void launch_p2p_allreduce_i64(const P2PView& v, const long long* src, size_t n, size_t slot_off, size_t buffer_bytes, size_t slot_stride,
-                              size_t flag_off, unsigned long long* epoch_ctr, long long* dst, unsigned* err, cudaStream_t s, const RoundState* st) {
-  p2p_allreduce_kernel<long long><<<1, kP2PThreads, 0, s>>>(v, src, n, slot_off, buffer_bytes, slot_stride, flag_off, epoch_ctr, dst, err, st);
+                              size_t flag_off, unsigned long long* epoch_ctr, long long* dst, unsigned* err, cudaStream_t s, RoundState* st,
+                              unsigned long long* wait_ns, const P2PTail* tail) {
+  p2p_allreduce_kernel<long long><<<1, kP2PThreads, 0, s>>>(v, src, n, slot_off, buffer_bytes, slot_stride, flag_off, epoch_ctr, dst, err, st,
+                                                            wait_ns, tail ? *tail : P2PTail());
 }
 
 void launch_p2p_allgather_i64(const P2PView& v, const long long* src, size_t n, size_t slot_off, size_t buffer_bytes, size_t slot_stride,
-                              size_t flag_off, unsigned long long* epoch_ctr, long long* dst, unsigned* err, cudaStream_t s, const RoundState* st) {
-  p2p_allgather_kernel<long long><<<1, kP2PThreads, 0, s>>>(v, src, n, slot_off, buffer_bytes, slot_stride, flag_off, epoch_ctr, dst, err, st);
+                              size_t flag_off, unsigned long long* epoch_ctr, long long* dst, unsigned* err, cudaStream_t s, RoundState* st,
+                              unsigned long long* wait_ns, const P2PTail* tail) {
+  p2p_allgather_kernel<long long><<<1, kP2PThreads, 0, s>>>(v, src, n, slot_off, buffer_bytes, slot_stride, flag_off, epoch_ctr, dst, err, st,
+                                                            wait_ns, tail ? *tail : P2PTail());
 }
 
 void launch_p2p_samples(const P2PView& v, CloudView cloud, long long first, size_t n, const int32_t* triples, int n_samples,
                         size_t sp_off, size_t buffer_bytes, size_t flag_off, unsigned long long* epoch_ctr, int4* dst, unsigned* err,
-                        cudaStream_t s, const RoundState* st) {
+                        cudaStream_t s, const RoundState* st, unsigned long long* wait_ns, const P2PTail* tail) {
   p2p_samples_kernel<<<1, kP2PThreads, 0, s>>>(v, cloud.x, cloud.y, cloud.z, first, n, triples, n_samples, sp_off, buffer_bytes, flag_off,
-                                              epoch_ctr, dst, err, st);
+                                              epoch_ctr, dst, err, st, wait_ns, tail ? *tail : P2PTail());
 }
 
 }  // namespace pr

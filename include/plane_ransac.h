@@ -113,6 +113,11 @@ typedef struct {
   /* peel launches of segment / extract calls (ABI 3): what the compaction kept and what it peeled off */
   long long points_kept;     /* points written to the remaining cloud                           */
   long long points_peeled;   /* inliers written to the index lists                              */
+  /* sharded runs with peer-memory exchanges: per channel (0 sample points, 1 counts, 2 refit moments, 3 remaining
+   * counts) the time this rank's exchange kernels spent spinning on the peers' flags — the slowest rank's lag plus the
+   * NVLink round trip — and the number of exchanges, since the last profile_reset */
+  double p2p_wait_ms[4];
+  long long p2p_exchanges[4];
 } pr_profile;
 
 /* ---- lifetime ---------------------------------------------------------------------------- */
