@@ -16,6 +16,8 @@ DOT_PCL_SSE2 = 0
 DOT_FMA = 1
 SCORER_BRUTE = 0
 SCORER_HIER = 1
+REFIT_FIXED = 0
+REFIT_PCL_FLOAT = 1
 STAGE_REMOVE_NONFINITE = 1
 STAGE_TRANSLATE_CENTROID = 2
 
@@ -45,6 +47,7 @@ class PrParams(C.Structure):
         ("max_planes", C.c_int),
         ("dot_order", C.c_int),
         ("scorer", C.c_int),
+        ("refit_mode", C.c_int),
     ]
 
 

@@ -164,6 +164,7 @@ struct plane_ransac_ctx {
   DevBuf<long long> d_totals;     // [0..2) local totals, [2 .. 2 + 2*ranks) gathered
   PinBuf<long long> h_totals;
   DevBuf<unsigned char> d_scratch;
+  DevBuf<float> d_pcl_sums;  // PR_REFIT_PCL_FLOAT: the nine sequential FP32 sums
   DevBuf<int32_t> d_inl_cur, d_inl_orig;
   PinBuf<float4> h_small;  // raw coefficient read-back
   DevBuf<float4> d_flush;
@@ -385,6 +386,7 @@ int check_params(const pr_params* p) {
   if (p->dot_order != PR_DOT_PCL_SSE2 && p->dot_order != PR_DOT_FMA) return fail(PR_ERR_INVALID, "unknown dot_order");
   if (p->max_planes < 0) return fail(PR_ERR_INVALID, "max_planes must be >= 0");
   if (p->scorer != PR_SCORER_BRUTE && p->scorer != PR_SCORER_HIER) return fail(PR_ERR_INVALID, "unknown scorer");
+  if (p->refit_mode != PR_REFIT_FIXED && p->refit_mode != PR_REFIT_PCL_FLOAT) return fail(PR_ERR_INVALID, "unknown refit_mode");
   return PR_OK;
 }
 
@@ -952,7 +954,34 @@ int segment_core(plane_ransac_ctx* c, const pr_params* prm, pr::CloudView src, s
   for (int i = 0; i < 3; ++i) inf.best_sample[i] = c->h_triples.p[3 * (size_t)best + i];
 
   float refined[4];
-  if (prm->optimize_coefficients) {
+  const bool pcl_float = prm->optimize_coefficients && prm->refit_mode == PR_REFIT_PCL_FLOAT;
+  if (pcl_float) {
+    // PCL 1.8's own arithmetic: selectWithinDistance(raw model) in index order, nine sequential FP32 sums over that
+    // list (one device thread), FP32 eigen33 on the host.  The list is built where the final selection will be written.
+    if (c->comm) return fail(PR_ERR_INVALID, "PR_REFIT_PCL_FLOAT needs the whole cloud on one GPU (a sequential sum has no sharded form)");
+    if (!d_inl_cur) return fail(PR_ERR_INVALID, "PR_REFIT_PCL_FLOAT needs the inlier list buffer");
+    PR_CUDA(cudaMemcpyAsync(c->h_small.p, c->d_hyps.p + best, sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
+    PR_TRY(sync_stream(c));
+    std::memcpy(inf.raw_coeff, c->h_small.p, 4 * sizeof(float));
+    PR_TRY(dev_reserve(c->d_scratch, pr::compact_scratch_bytes(n_local) + 64));
+    PR_TRY(dev_reserve(c->d_pcl_sums, 16));
+    {
+      Span sp(c, KC_REFIT, n_local ? 2 : 1);
+      const pr::Plane4 raw = {inf.raw_coeff[0], inf.raw_coeff[1], inf.raw_coeff[2], inf.raw_coeff[3]};
+      pr::CloudView none;
+      pr::launch_compact(src, n_local, raw, t, prm->dot_order, none, false, d_inl_cur, nullptr, c->d_scratch.p, c->d_totals.p, c->stream);
+      pr::launch_refit_pcl_float(src, d_inl_cur, c->d_totals.p + 1, c->d_pcl_sums.p, c->stream);
+      c->prof.points_refit += (long long)n_local;
+      c->prof.bytes_refit += 12ll * (long long)n_local;
+    }
+    PR_CUDA(cudaGetLastError());
+    float sums[9];
+    PR_CUDA(cudaMemcpyAsync(sums, c->d_pcl_sums.p, sizeof(sums), cudaMemcpyDeviceToHost, c->stream));
+    PR_CUDA(cudaMemcpyAsync(c->h_totals.p, c->d_totals.p, 2 * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
+    PR_TRY(sync_stream(c));
+    std::memcpy(refined, inf.raw_coeff, sizeof(refined));
+    pr::plane_from_pcl_float_sums(sums, c->h_totals.p[1], refined);  // < 4 inliers: keeps the raw model
+  } else if (prm->optimize_coefficients) {
     PR_CUDA(cudaMemsetAsync(c->d_refit.p, 0, sizeof(pr::RefitOut), c->stream));
     {
       Span sp(c, KC_REFIT, 1);
@@ -964,11 +993,13 @@ int segment_core(plane_ransac_ctx* c, const pr_params* prm, pr::CloudView src, s
     PR_TRY(exchange_refit(c));
     PR_CUDA(cudaMemcpyAsync(c->h_refit.p, c->d_refit.p, sizeof(pr::RefitOut), cudaMemcpyDeviceToHost, c->stream));
   }
-  PR_CUDA(cudaMemcpyAsync(c->h_small.p, c->d_hyps.p + best, sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
-  PR_TRY(sync_stream(c));
-  std::memcpy(inf.raw_coeff, c->h_small.p, 4 * sizeof(float));
-  std::memcpy(refined, inf.raw_coeff, sizeof(refined));
-  if (prm->optimize_coefficients) {
+  if (!pcl_float) {
+    PR_CUDA(cudaMemcpyAsync(c->h_small.p, c->d_hyps.p + best, sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
+    PR_TRY(sync_stream(c));
+    std::memcpy(inf.raw_coeff, c->h_small.p, 4 * sizeof(float));
+    std::memcpy(refined, inf.raw_coeff, sizeof(refined));
+  }
+  if (prm->optimize_coefficients && !pcl_float) {
     int64_t m[16];
     for (int i = 0; i < 16; ++i) m[i] = (int64_t)c->h_refit.p->m[i];
     // sharded: every rank wrote the same pivot; the all-reduce summed only m[]
@@ -1070,6 +1101,7 @@ bool chain_eligible(const plane_ransac_ctx* c, const pr_params* prm, long long n
   static const bool enabled = [] { const char* e = getenv("PR_CHAIN"); return !(e && atoi(e) == 0); }();
   if (!enabled || c->round_loop == PR_LOOP_HOST || c->pend.active) return false;
   if (!(prm->probability >= 1.0) || prm->scorer != PR_SCORER_BRUTE) return false;
+  if (prm->optimize_coefficients && prm->refit_mode != PR_REFIT_FIXED) return false;  // the sequential FP32 sums are host-driven
   if (prm->max_iterations < 1 || (long long)prm->max_iterations + 1 > kChainMaxHyps) return false;
   if (c->comm && !c->p2p_on) return false;
   // about (3K)^2 / N of a round's picks collide; beyond what the device replays the round would come straight back
@@ -1429,6 +1461,7 @@ void plane_ransac_default_params(pr_params* p) {
   p->max_planes = 64;
   p->dot_order = PR_DOT_FMA;
   p->scorer = PR_SCORER_BRUTE;
+  p->refit_mode = PR_REFIT_FIXED;
 }
 
 int plane_ransac_create(plane_ransac_ctx** out, int device_id) {
@@ -1481,7 +1514,7 @@ void plane_ransac_destroy(plane_ransac_ctx* c) {
   for (int i = 0; i < 2; ++i) { dev_free(c->work_mem[i]); dev_free(c->work_orig[i]); }
   dev_free(c->aos); dev_free(c->d_bbox); dev_free(c->d_triples); dev_free(c->d_counts); dev_free(c->d_good);
   dev_free(c->d_sample_pts); dev_free(c->d_hyps); dev_free(c->d_refit); dev_free(c->d_totals);
-  dev_free(c->d_scratch); dev_free(c->d_inl_cur); dev_free(c->d_inl_orig); dev_free(c->d_flush); dev_free(c->batch_mem);
+  dev_free(c->d_scratch); dev_free(c->d_pcl_sums); dev_free(c->d_inl_cur); dev_free(c->d_inl_orig); dev_free(c->d_flush); dev_free(c->batch_mem);
   dev_free(c->d_stage_map);
   dev_free(c->d_stage_map_tmp);
   for (int i = 0; i < 3; ++i) dev_free(c->sorted_mem[i]);
@@ -2465,6 +2498,8 @@ int plane_ransac_segment_batch_lists(plane_ransac_ctx* c, const pr_params* prm, 
   if (c->batch_clouds == 0) return fail(PR_ERR_NO_CLOUD, "no batch staged");
   if (!coeffs || !n_inliers) return fail(PR_ERR_INVALID, "null output");
   if (inliers && !offsets) return fail(PR_ERR_INVALID, "inlier lists need the offsets array");
+  if (prm->optimize_coefficients && prm->refit_mode != PR_REFIT_FIXED)
+    return fail(PR_ERR_INVALID, "PR_REFIT_PCL_FLOAT is not available for batches (use plane_ransac_segment_one per cloud)");
   const bool device_loop = c->round_loop != PR_LOOP_HOST && prm->probability >= 1.0 && prm->max_iterations >= 1 && c->batch_n >= 3 &&
                            (double)c->batch_clouds * ((double)prm->max_iterations + 1.0) <= 4.0e8;
   if (device_loop) {

@@ -290,6 +290,99 @@ bool plane_from_moments(const int64_t m[16], const float pivot[3], int scale_exp
   return pm_plane_from_moments(mm, pivot, scale_exp, coeff);
 }
 
+// --- pcl::eigen33 / computeRoots / computeRoots2 in FP32, as PCL 1.8 instantiates them for the plane model ------------
+namespace {
+void roots2f(float b, float c, float roots[3]) {
+  roots[0] = 0.f;
+  float d = (float)(b * b - 4.0 * c);  // PCL writes the literal 4.0: the product is formed in double
+  if (d < 0.0) d = 0.f;
+  const float sd = std::sqrt(d);
+  roots[2] = 0.5f * (b + sd);
+  roots[1] = 0.5f * (b - sd);
+}
+
+void roots3f(const float m[9], float roots[3]) {
+  const float c0 = m[0] * m[4] * m[8] + 2.f * m[1] * m[2] * m[5] - m[0] * m[5] * m[5] - m[4] * m[2] * m[2] - m[8] * m[1] * m[1];
+  const float c1 = m[0] * m[4] - m[1] * m[1] + m[0] * m[8] - m[2] * m[2] + m[4] * m[8] - m[5] * m[5];
+  const float c2 = m[0] + m[4] + m[8];
+  if (std::fabs(c0) < FLT_EPSILON) {
+    roots2f(c2, c1, roots);
+    return;
+  }
+  const float s_inv3 = (float)(1.0 / 3.0);
+  const float s_sqrt3 = std::sqrt(3.0f);
+  const float c2_over_3 = c2 * s_inv3;
+  float a_over_3 = (c1 - c2 * c2_over_3) * s_inv3;
+  if (a_over_3 > 0.f) a_over_3 = 0.f;
+  const float half_b = 0.5f * (c0 + c2_over_3 * (2.f * c2_over_3 * c2_over_3 - c1));
+  float q = half_b * half_b + a_over_3 * a_over_3 * a_over_3;
+  if (q > 0.f) q = 0.f;
+  const float rho = std::sqrt(-a_over_3);
+  const float theta = std::atan2(std::sqrt(-q), half_b) * s_inv3;
+  const float cos_theta = std::cos(theta);
+  const float sin_theta = std::sin(theta);
+  roots[0] = c2_over_3 + 2.f * rho * cos_theta;
+  roots[1] = c2_over_3 - rho * (cos_theta + s_sqrt3 * sin_theta);
+  roots[2] = c2_over_3 - rho * (cos_theta - s_sqrt3 * sin_theta);
+  float tmp;
+  if (roots[0] >= roots[1]) { tmp = roots[0]; roots[0] = roots[1]; roots[1] = tmp; }
+  if (roots[1] >= roots[2]) {
+    tmp = roots[1]; roots[1] = roots[2]; roots[2] = tmp;
+    if (roots[0] >= roots[1]) { tmp = roots[0]; roots[0] = roots[1]; roots[1] = tmp; }
+  }
+  if (roots[0] <= 0) roots2f(c2, c1, roots);
+}
+}  // namespace
+
+bool plane_from_pcl_float_sums(const float sums[9], long long n_inliers, float coeff[4]) {
+  if (n_inliers < 4) return false;  // PCL: "if (inliers.size () <= 3)" -> the input coefficients stand
+  float accu[9];
+  const float cnt = (float)n_inliers;
+  for (int i = 0; i < 9; ++i) accu[i] = sums[i] / cnt;
+  float s[9];
+  s[0] = accu[0] - accu[6] * accu[6];
+  s[1] = accu[1] - accu[6] * accu[7];
+  s[2] = accu[2] - accu[6] * accu[8];
+  s[4] = accu[3] - accu[7] * accu[7];
+  s[5] = accu[4] - accu[7] * accu[8];
+  s[8] = accu[5] - accu[8] * accu[8];
+  s[3] = s[1];
+  s[6] = s[2];
+  s[7] = s[5];
+  float scale = 0.f;
+  for (int i = 0; i < 9; ++i) {
+    const float a = std::fabs(s[i]);
+    if (a > scale) scale = a;
+  }
+  if (scale <= FLT_MIN) scale = 1.f;
+  for (int i = 0; i < 9; ++i) s[i] = s[i] / scale;
+  float ev[3];
+  roots3f(s, ev);
+  s[0] -= ev[0];
+  s[4] -= ev[0];
+  s[8] -= ev[0];
+  const float v1[3] = {s[1] * s[5] - s[2] * s[4], s[2] * s[3] - s[0] * s[5], s[0] * s[4] - s[1] * s[3]};
+  const float v2[3] = {s[1] * s[8] - s[2] * s[7], s[2] * s[6] - s[0] * s[8], s[0] * s[7] - s[1] * s[6]};
+  const float v3[3] = {s[4] * s[8] - s[5] * s[7], s[5] * s[6] - s[3] * s[8], s[3] * s[7] - s[4] * s[6]};
+  const float len1 = v1[0] * v1[0] + v1[1] * v1[1] + v1[2] * v1[2];
+  const float len2 = v2[0] * v2[0] + v2[1] * v2[1] + v2[2] * v2[2];
+  const float len3 = v3[0] * v3[0] + v3[1] * v3[1] + v3[2] * v3[2];
+  const float* best;
+  float len;
+  if (len1 >= len2 && len1 >= len3) { best = v1; len = len1; }
+  else if (len2 >= len1 && len2 >= len3) { best = v2; len = len2; }
+  else { best = v3; len = len3; }
+  const float nrm = std::sqrt(len);
+  const float v[3] = {best[0] / nrm, best[1] / nrm, best[2] / nrm};
+  // Hessian form: d = -(v . centroid), the 4-term dot in Eigen's SSE2 order with a zero fourth coefficient
+  const float dot = (v[0] * accu[6] + v[2] * accu[8]) + (v[1] * accu[7] + 0.0f * 1.0f);
+  coeff[0] = v[0];
+  coeff[1] = v[1];
+  coeff[2] = v[2];
+  coeff[3] = -1.0f * dot;
+  return true;
+}
+
 float threshold_up(double t) {
   float f = (float)t;  // round to nearest
   if ((double)f < t) f = std::nextafterf(f, INFINITY);

@@ -110,6 +110,12 @@ bool centroid_from_sums(const long long sums[4], const float lo[3], int scale_ex
 // untouched) when fewer than 4 points contributed.
 bool plane_from_moments(const int64_t m[16], const float pivot[3], int scale_exp, float coeff[4]);
 
+// PCL 1.8's float path of optimizeModelCoefficients after the nine sequential sums (PR_REFIT_PCL_FLOAT):
+// computeMeanAndCovarianceMatrix's division and covariance, pcl::eigen33 in FP32 (sqrtf / atan2f / cosf / sinf of the
+// platform, as PCL itself calls them), Hessian d.  accu: xx, xy, xz, yy, yz, zz, x, y, z.  Fewer than 4 inliers:
+// coeff keeps the sample's model (false).
+bool plane_from_pcl_float_sums(const float accu[9], long long n_inliers, float coeff[4]);
+
 // Smallest float >= t: the FP32 threshold equivalent to PCL's float-vs-double strict compare.
 float threshold_up(double t);
 

@@ -1246,6 +1246,48 @@ void launch_refit_batch(CloudView clouds, size_t n_per, size_t cloud_stride, int
 }
 
 // ------------------------------------------------------------------------------------------------
+// PCL 1.8's own refit accumulation (PR_REFIT_PCL_FLOAT): computeMeanAndCovarianceMatrix sums nine FP32 accumulators
+// over the inliers sequentially, in index order.  A sequential FP32 sum cannot be split across threads without
+// changing its value, so one thread (lane 0) does all the additions; the other lanes of its warp only fetch the next
+// 32 inliers' coordinates (a coalesced index read + gather) and hand them over by shuffle.  A parity mode, not the fast
+// path: ~20 ms per million inliers.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32) refit_pcl_float_kernel(const float* __restrict__ X, const float* __restrict__ Y, const float* __restrict__ Z,
+                                                             const int32_t* __restrict__ idx, const long long* __restrict__ n_idx_dev,
+                                                             float* __restrict__ out9) {
+  const long long n_idx = *n_idx_dev;
+  const int lane = threadIdx.x;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, a4 = 0.f, a5 = 0.f, a6 = 0.f, a7 = 0.f, a8 = 0.f;
+  for (long long base = 0; base < n_idx; base += 32) {
+    float x = 0.f, y = 0.f, z = 0.f;
+    if (base + lane < n_idx) {
+      const int32_t j = idx[base + lane];
+      x = X[j]; y = Y[j]; z = Z[j];
+    }
+    const int m = (int)(n_idx - base < 32 ? n_idx - base : 32);
+    for (int k = 0; k < m; ++k) {
+      const float px = __shfl_sync(0xFFFFFFFFu, x, k), py = __shfl_sync(0xFFFFFFFFu, y, k), pz = __shfl_sync(0xFFFFFFFFu, z, k);
+      a0 = __fadd_rn(a0, __fmul_rn(px, px));
+      a1 = __fadd_rn(a1, __fmul_rn(px, py));
+      a2 = __fadd_rn(a2, __fmul_rn(px, pz));
+      a3 = __fadd_rn(a3, __fmul_rn(py, py));
+      a4 = __fadd_rn(a4, __fmul_rn(py, pz));
+      a5 = __fadd_rn(a5, __fmul_rn(pz, pz));
+      a6 = __fadd_rn(a6, px);
+      a7 = __fadd_rn(a7, py);
+      a8 = __fadd_rn(a8, pz);
+    }
+  }
+  if (lane == 0) {
+    out9[0] = a0; out9[1] = a1; out9[2] = a2; out9[3] = a3; out9[4] = a4; out9[5] = a5; out9[6] = a6; out9[7] = a7; out9[8] = a8;
+  }
+}
+
+void launch_refit_pcl_float(CloudView cloud, const int32_t* idx, const long long* n_idx_dev, float* out9, cudaStream_t s) {
+  refit_pcl_float_kernel<<<1, 32, 0, s>>>(cloud.x, cloud.y, cloud.z, idx, n_idx_dev, out9);
+}
+
+// ------------------------------------------------------------------------------------------------
 // K5: stable partition with a single-pass decoupled look-back scan.
 // Tile = 2048 points (256 threads x 2 rounds x 4 consecutive points, 128-bit loads).  The scan runs
 // on the number of KEPT points; the inlier rank of a point is its position minus the kept points

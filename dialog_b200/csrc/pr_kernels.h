@@ -133,6 +133,10 @@ void launch_refit(CloudView cloud, size_t n, const float4* hyps, const int4* sam
                   int dot_order, int scale_exp, RefitOut* out, int num_sms, cudaStream_t s, RoundState* st = nullptr,
                   const ChainTail* tail = nullptr);
 
+// PR_REFIT_PCL_FLOAT: out9 = PCL computeMeanAndCovarianceMatrix's nine FP32 sums (xx, xy, xz, yy, yz, zz, x, y, z) over the
+// points idx[0 .. *n_idx_dev) of the cloud, added sequentially in that order by one thread.
+void launch_refit_pcl_float(CloudView cloud, const int32_t* idx, const long long* n_idx_dev, float* out9, cudaStream_t s);
+
 // K3 for a batch: cloud c refits hypothesis c * K + model_idx[c] (skipped when negative) with scale 2^s_c.
 void launch_refit_batch(CloudView clouds, size_t n_per, size_t cloud_stride, int n_clouds, const float4* hyps,
                         const int4* sample_pts, int K, const int32_t* model_idx, float t, int dot_order,

@@ -18,17 +18,18 @@ from dataclasses import dataclass, field
 import numpy as np
 
 from . import _lib
-from ._lib import (DOT_FMA, DOT_PCL_SSE2, SCORER_BRUTE, SCORER_HIER, PlaneRansacError, PrParams, PrProfile,  # noqa: F401
+from ._lib import (DOT_FMA, DOT_PCL_SSE2, REFIT_FIXED, REFIT_PCL_FLOAT, SCORER_BRUTE, SCORER_HIER, PlaneRansacError, PrParams, PrProfile,  # noqa: F401
                    PrSegmentInfo)
 
 
 def make_params(distance_threshold: float = 0.1, max_iterations: int = 50, min_plane_size: int = 500,
                 probability: float = 0.99, optimize_coefficients: bool = True, seed: int = 12345,
-                max_planes: int = 64, dot_order: int = DOT_FMA, scorer: int = 0) -> PrParams:
+                max_planes: int = 64, dot_order: int = DOT_FMA, scorer: int = 0, refit_mode: int = 0) -> PrParams:
     """Defaults: T_dist_point_plane / T_num_of_single_plane from Dialog/config.txt:29,20 and PCL's
     SACSegmentation defaults for the knobs config.txt has no key for."""
     return PrParams(float(distance_threshold), int(max_iterations), int(min_plane_size), float(probability),
-                    int(bool(optimize_coefficients)), int(seed), int(max_planes), int(dot_order), int(scorer))
+                    int(bool(optimize_coefficients)), int(seed), int(max_planes), int(dot_order), int(scorer),
+                    int(refit_mode))
 
 
 def as_cloud(points: np.ndarray) -> np.ndarray:

@@ -122,6 +122,7 @@ class PlaneDetectRansac {
   void setMaxPlanes(int n) { prm_.max_planes = n; }
   void setDotOrder(int order) { prm_.dot_order = order; }
   void setScorer(int scorer) { prm_.scorer = scorer; }
+  void setRefitMode(int mode) { prm_.refit_mode = mode; }  // PR_REFIT_FIXED (default) / PR_REFIT_PCL_FLOAT
   const pr_params& params() const { return prm_; }
 
   // Page-locks storage the caller owns (e.g. pcl::PointCloud::points) in place, so that detect calls on it take the

@@ -63,6 +63,18 @@ enum { PR_DOT_PCL_SSE2 = 0, PR_DOT_FMA = 1 };
  *                    staged cloud and a second compaction per peel round; not used by the batch entry points. */
 enum { PR_SCORER_BRUTE = 0, PR_SCORER_HIER = 1 };
 
+/* How optimizeModelCoefficients (the least-squares refit behind pcl::computePointNormal, Dialog/PlaneDetect.h:1084,
+ * 1130,1386,1485) accumulates the covariance.
+ *   PR_REFIT_FIXED      (default) inlier coordinates quantised to a 2^-30-of-the-extent grid, moments summed as exact
+ *                       integers, pcl::eigen33 in double: independent of any summation order, so 1 thread, 148 SMs and
+ *                       8 GPUs give the same bits.
+ *   PR_REFIT_PCL_FLOAT  PCL 1.8's own arithmetic: nine FP32 accumulators summed sequentially over the inliers in index
+ *                       order (computeMeanAndCovarianceMatrix), pcl::eigen33 in FP32.  One device thread does the sums
+ *                       (about 20 ms per million inliers), the host the 3x3 solve; a parity mode, host-driven rounds, one
+ *                       GPU only (a sequential sum over a sharded cloud would need the points in one place).
+ * The two agree to about 1e-5 relative in the coefficients (tests/test_gpu_parity.py enumerates the inliers that differ). */
+enum { PR_REFIT_FIXED = 0, PR_REFIT_PCL_FLOAT = 1 };
+
 /* pcl::SACSegmentation knobs + the peel stop rule. */
 typedef struct {
   double distance_threshold;  /* setDistanceThreshold(double); inlier iff |n·p + d| <  t (strict) */
@@ -74,6 +86,7 @@ typedef struct {
   int max_planes;             /* bound on planes returned by plane_ransac_extract_planes         */
   int dot_order;              /* PR_DOT_*                                                         */
   int scorer;                 /* PR_SCORER_*: how the inlier counts are computed (same counts either way) */
+  int refit_mode;             /* PR_REFIT_* (ABI 3)                                                */
 } pr_params;
 
 /* What one segment() call decided (mirrors RandomSampleConsensus state; used by parity tests). */

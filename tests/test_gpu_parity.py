@@ -305,6 +305,63 @@ def test_config2_at_its_named_size(O, pr, scene2):
     assert pr.remaining().tobytes() == want.remaining.tobytes()
 
 
+@pytest.mark.parametrize("prob,max_it", [(1.0, 255), (0.99, 50)])
+def test_refit_pcl_float_mode_matches_oracle(O, pr, scene2, scene3, prob, max_it):
+    """PR_REFIT_PCL_FLOAT: PCL 1.8's own refit arithmetic on the product path (nine FP32 sums added sequentially in index
+    order by one device thread, FP32 eigen33) against the oracle's ORC_REFIT_PCL_FLOAT, bit for bit."""
+    import dialog_b200 as D
+    for scene, n, planes in ((scene2, 120_000, 3), (scene3, 200_000, 8)):
+        pts = scene.points(0, n)
+        prm = D.make_params(0.1, max_it, 1500, prob, True, 12345, planes, D.DOT_FMA, D.SCORER_BRUTE, D.REFIT_PCL_FLOAT)
+        pr.set_cloud(pts)
+        ex = pr.extract_planes(prm)
+        want = O.extract_planes(pts, _oparams(O, prm, O.REFIT_PCL_FLOAT))
+        assert len(ex.planes) == len(want.coeffs) >= 3
+        for k, p in enumerate(ex.planes):
+            assert _same_bits(p.coeff, want.coeffs[k]), (k, p.coeff, want.coeffs[k])
+            assert np.array_equal(p.inliers_orig, want.inliers_orig[k])
+        assert pr.remaining().tobytes() == want.remaining.tobytes()
+        coeff, inl, info = pr.segment_one(prm)
+        seg = O.segment(pts, _oparams(O, prm, O.REFIT_PCL_FLOAT))
+        assert _same_bits(coeff, seg.coeff) and np.array_equal(inl, seg.inliers)
+
+
+@pytest.mark.parametrize("cfg", ["configs[1]", "configs[2]"])
+def test_refit_modes_agree_to_1e5_and_differences_are_enumerated(O, pr, scene2, scene3, cfg):
+    """north_star: 'plane coefficients must agree within 1e-5 relative' — here between the canonical order-independent
+    refit and PCL's sequential FP32 one, at the named sizes of BASELINE configs[1] (1M x 1024) and configs[2] (10M x 4096).
+    Round 0 (same cloud, same winning sample in both modes): coefficients within 1e-5 of the plane's scale, and every
+    point that is an inlier in one mode only lies within the band those coefficient differences allow around t."""
+    import dialog_b200 as D
+    if cfg == "configs[1]":
+        pts, K, planes = scene2.points(0, 1_000_000), 1024, 3
+    else:
+        pts, K, planes = scene3.points(0, 10_000_000), 4096, 20
+    pr.set_cloud(pts)
+    fixed = D.make_params(0.1, K - 1, 500, 1.0, True, 12345, planes, D.DOT_FMA)
+    pclf = D.make_params(0.1, K - 1, 500, 1.0, True, 12345, planes, D.DOT_FMA, D.SCORER_BRUTE, D.REFIT_PCL_FLOAT)
+    c0, i0, info0 = pr.segment_one(fixed)
+    c1, i1, info1 = pr.segment_one(pclf)
+    assert list(info0.best_sample) == list(info1.best_sample) and info0.best_count == info1.best_count
+    scale = max(1.0, float(np.abs(c0).max()))
+    diff = np.abs(c0.astype(np.float64) - c1.astype(np.float64))
+    assert diff.max() <= 1e-5 * scale, (c0, c1)
+    only = np.setxor1d(i0, i1)
+    # a point can change sides only if its residual under one plane is within |delta coeff| . (|x|, |y|, |z|, 1) of t
+    r0 = np.abs(O.residuals(pts[only], c0, O.DOT_FMA).astype(np.float64))
+    band = (np.abs(pts[only, :3]).astype(np.float64) * diff[:3]).sum(1) + diff[3] + 1e-6
+    assert (np.abs(r0 - 0.1) <= band).all()
+    print(f"{cfg}: round 0 coefficients differ by {diff.max():.2e}; {only.size} of {i0.size} inliers differ between the refit modes, "
+          f"all within {band.max() if only.size else 0:.2e} of the threshold")
+    # the whole peel: the same number of planes, each canonical plane has a PCL-float twin
+    exf, exp_ = pr.extract_planes(fixed), pr.extract_planes(pclf)
+    assert len(exf.planes) == len(exp_.planes) == planes
+    for p in exf.planes:
+        best = min(exp_.planes, key=lambda q: min(np.abs(q.coeff - p.coeff).max(), np.abs(q.coeff + p.coeff).max()))
+        d = min(np.abs(best.coeff - p.coeff).max(), np.abs(best.coeff + p.coeff).max())
+        assert d <= 2e-3 and abs(best.info.n_inliers - p.info.n_inliers) <= 0.01 * p.info.n_inliers + 50
+
+
 def test_extract_capacity_error(pr, scene2):
     import ctypes as C
     import dialog_b200 as D
