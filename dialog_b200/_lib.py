@@ -32,7 +32,7 @@ SYMBOLS = [
     "plane_ransac_host_alloc", "plane_ransac_host_free", "plane_ransac_host_register", "plane_ransac_host_unregister", "plane_ransac_profile_enable", "plane_ransac_profile_reset", "plane_ransac_profile_get",
     "plane_ransac_timer_start", "plane_ransac_timer_stop", "plane_ransac_measure_ffma_peak", "plane_ransac_measure_copy_bw", "plane_ransac_flush_l2",
     "plane_ransac_host_draw_triples", "plane_ransac_host_draw_triples_parallel", "plane_ransac_host_replay", "plane_ransac_host_shard_range",
-    "plane_ransac_host_plane_from_moments", "plane_ransac_host_rand_edges",
+    "plane_ransac_host_plane_from_moments", "plane_ransac_host_plane_from_pcl_float_sums", "plane_ransac_host_rand_edges",
 ]
 
 
@@ -145,6 +145,7 @@ def load():
     L.plane_ransac_host_replay.argtypes = [vp, vp, C.c_int, C.c_longlong, C.c_int, C.c_double] + [C.POINTER(C.c_int)] * 5
     L.plane_ransac_host_shard_range.argtypes = [C.c_longlong, C.c_int, C.c_int, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]
     L.plane_ransac_host_plane_from_moments.argtypes = [vp, vp, C.c_int, vp]
+    L.plane_ransac_host_plane_from_pcl_float_sums.argtypes = [vp, C.c_longlong, vp]
     L.plane_ransac_host_rand_edges.argtypes = [C.c_uint, C.c_int, vp]
     for name in SYMBOLS:
         fn = getattr(L, name)

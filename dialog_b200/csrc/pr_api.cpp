@@ -2761,6 +2761,11 @@ int plane_ransac_host_shard_range(long long n_points, int n_ranks, int rank, lon
   return PR_OK;
 }
 
+int plane_ransac_host_plane_from_pcl_float_sums(const float sums[9], long long n_inliers, float coeff[4]) {
+  if (!sums || !coeff) return fail(PR_ERR_INVALID, "null argument");
+  return pr::plane_from_pcl_float_sums(sums, n_inliers, coeff) ? PR_OK : fail(PR_ERR_INVALID, "fewer than 4 inliers");
+}
+
 int plane_ransac_host_plane_from_moments(const int64_t m[16], const float pivot[3], int scale_exp, float coeff[4]) {
   if (!m || !pivot || !coeff) return fail(PR_ERR_INVALID, "null argument");
   return pr::plane_from_moments(m, pivot, scale_exp, coeff) ? PR_OK : fail(PR_ERR_INVALID, "fewer than 4 points in the moments");

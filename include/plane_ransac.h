@@ -342,6 +342,10 @@ int plane_ransac_host_shard_range(long long n_points, int n_ranks, int rank, lon
 int plane_ransac_host_plane_from_moments(const int64_t m[16], const float pivot[3], int scale_exp,
                                          float coeff[4]);
 
+/* PR_REFIT_PCL_FLOAT's host half: PCL 1.8 computeMeanAndCovarianceMatrix's division + covariance, pcl::eigen33 in FP32 and
+ * the Hessian d from the nine sequential sums (xx, xy, xz, yy, yz, zz, x, y, z) over n_inliers points. */
+int plane_ransac_host_plane_from_pcl_float_sums(const float sums[9], long long n_inliers, float coeff[4]);
+
 #ifdef __cplusplus
 }
 #endif

@@ -398,6 +398,51 @@ def cluster_filter(cloud, radius, max_small_cluster) -> np.ndarray:
     return keep.astype(bool)
 
 
+def segment_line(cloud, params: Params):
+    """pcl::SACSegmentation with SACMODEL_LINE as Dialog/SimplifyVerticesSize.cpp:64-67 calls it: (ok, coeff[6] = point +
+    direction, inlier indices, trace) through the same sampler and computeModel loop as the plane model."""
+    c = _cloud(cloud)
+    coeff = np.zeros(6, np.float32)
+    inl = np.empty(max(c.shape[0], 1), np.int32)
+    n = C.c_size_t(0)
+    tr = Trace()
+    L = lib()
+    L.orc_segment_line.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(Params), C.c_void_p, C.c_void_p, C.POINTER(C.c_size_t), C.POINTER(Trace)]
+    rc = L.orc_segment_line(_p(c), c.shape[0], C.byref(params), _p(coeff), _p(inl), C.byref(n), C.byref(tr))
+    if rc < 0:
+        raise RuntimeError("orc_segment_line failed")
+    return bool(rc), coeff, inl[: n.value].copy(), tr
+
+
+def draw_sequence_k(n_points: int, n_draws: int, sample_size: int, seed: int = 12345) -> np.ndarray:
+    """drawIndexSample for a model of sample_size points (line: 2), through the oracle's sampler."""
+    L = lib()
+    class Sampler(C.Structure):
+        _fields_ = [("mt", C.c_uint32 * 624), ("idx", C.c_int), ("shuffled", C.c_void_p), ("n", C.c_size_t)]
+    s = Sampler()
+    L.orc_sampler_init.argtypes = [C.c_void_p, C.c_size_t, C.c_uint32]
+    L.orc_sampler_draw_k.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    L.orc_sampler_free.argtypes = [C.c_void_p]
+    if L.orc_sampler_init(C.byref(s), n_points, seed):
+        raise MemoryError
+    out = np.zeros((n_draws, sample_size), np.int32)
+    for k in range(n_draws):
+        L.orc_sampler_draw_k(C.byref(s), sample_size, out[k].ctypes.data_as(C.c_void_p))
+    L.orc_sampler_free(C.byref(s))
+    return out
+
+
+def cluster_filter_reference_bfs(cloud, radius, max_small_cluster, ties_by_index: bool) -> np.ndarray:
+    """clusterFilt restated literally (BFS, first radius-search hit skipped, Dialog/PlaneDetect.h:1598-1634): keep mask."""
+    c = _cloud(cloud)
+    keep = np.ones(c.shape[0], np.uint8)
+    L = lib()
+    L.orc_cluster_filter_reference_bfs.argtypes = [C.c_void_p, C.c_size_t, C.c_double, C.c_int, C.c_int, C.c_void_p]
+    if L.orc_cluster_filter_reference_bfs(_p(c), c.shape[0], float(radius), int(max_small_cluster), int(ties_by_index), _p(keep)) != 0:
+        raise ValueError("bad radius")
+    return keep.astype(bool)
+
+
 # ---- the reference's own source of the same predicate (oracle/build_ref.py) ------------------------------------
 _REF_SO = os.path.join(_HERE, "_ref", "libdialog_ref.so")
 _ref = None

@@ -68,18 +68,19 @@ void orc_sampler_free(orc_sampler* s) {
   s->shuffled = NULL;
 }
 
-void orc_sampler_draw(orc_sampler* s, int32_t idx[3]) {
-  for (size_t i = 0; i < 3; ++i) {
+/* drawIndexSample for a model of sample_size points (plane: 3, line: 2) */
+void orc_sampler_draw_k(orc_sampler* s, int sample_size, int32_t* idx) {
+  for (size_t i = 0; i < (size_t)sample_size; ++i) {
     uint32_t r = orc_mt_next(&s->rng) >> 1; /* rnd() */
     size_t j = i + (size_t)r % (s->n - i);
     int32_t tmp = s->shuffled[i];
     s->shuffled[i] = s->shuffled[j];
     s->shuffled[j] = tmp;
   }
-  idx[0] = s->shuffled[0];
-  idx[1] = s->shuffled[1];
-  idx[2] = s->shuffled[2];
+  for (int i = 0; i < sample_size; ++i) idx[i] = s->shuffled[i];
 }
+
+void orc_sampler_draw(orc_sampler* s, int32_t idx[3]) { orc_sampler_draw_k(s, 3, idx); }
 
 int orc_draw_sequence(size_t n, uint32_t seed, int n_draws, int32_t* triples) {
   if (n < 3) return -1;
@@ -468,15 +469,29 @@ int orc_refit_fixed(const orc_point* cloud, const int32_t* idx, size_t n_idx, co
  * RandomSampleConsensus::computeModel (sample_consensus/impl/ransac.hpp) followed by
  * SACSegmentation::segment (segmentation/impl/sac_segmentation.hpp).
  * ========================================================================================= */
-int orc_segment(const orc_point* cloud, size_t n, const orc_params* prm, int scale_exp_or_min,
-                float coeff[4], int32_t* inliers, size_t* n_inliers, orc_trace* trace) {
-  orc_trace tr;
-  memset(&tr, 0, sizeof(tr));
-  *n_inliers = 0;
-  coeff[0] = coeff[1] = coeff[2] = coeff[3] = 0.0f;
+/* =========================================================================================
+ * RandomSampleConsensus::computeModel (sample_consensus/impl/ransac.hpp) over a model given by its sample size and its
+ * three callbacks — the SAME loop (and the same sampler) serves the plane model of the hot path and the line model of
+ * the reference's only literal SAC call (Dialog/SimplifyVerticesSize.cpp:64-67).
+ * ========================================================================================= */
+typedef struct {
+  int sample_size;
+  int (*is_sample_good)(const orc_point* cloud, const int32_t* idx);
+  int (*compute_model)(const orc_point* cloud, const int32_t* idx, float* coeff);
+  int64_t (*count_within)(const orc_point* cloud, size_t n, const float* coeff, double t, int dot_order);
+  int n_coeff;
+} orc_sac_model;
+
+typedef struct {
+  int iterations, draws, skipped, have_model, n_best;
+  int32_t best_sample[3];
+  float best_coeff[6];
+} orc_sac_result;
+
+static int orc_ransac_compute_model(const orc_point* cloud, size_t n, const orc_params* prm, const orc_sac_model* mdl, orc_sac_result* out) {
+  memset(out, 0, sizeof(*out));
   const double threshold = prm->distance_threshold;
   const int max_iterations = prm->max_iterations;
-
   int iterations = 0;
   int n_best = -INT_MAX;
   double k = 1.0;
@@ -484,40 +499,38 @@ int orc_segment(const orc_point* cloud, size_t n, const orc_params* prm, int sca
   const double one_over_indices = 1.0 / (double)n;
   unsigned skipped = 0;
   const unsigned max_skip = (unsigned)max_iterations * 10u;
-  int have_model = 0;
-  int32_t best_sample[3] = {0, 0, 0};
-  float best_coeff[4] = {0, 0, 0, 0};
   const unsigned max_sample_checks = 1000;
+  const size_t ss = (size_t)mdl->sample_size;
 
   orc_sampler smp;
   smp.shuffled = NULL;
-  if (n >= 3 && orc_sampler_init(&smp, n, prm->seed)) return -1;
+  if (n >= ss && orc_sampler_init(&smp, n, prm->seed)) return -1;
 
   while ((double)iterations < k && skipped < max_skip) {
     /* getSamples: fewer points than the sample size => empty selection, loop ends */
-    int32_t sel[3];
+    int32_t sel[3] = {0, 0, 0};
     int got = 0;
-    if (n >= 3) {
+    if (n >= ss) {
       for (unsigned it = 0; it < max_sample_checks; ++it) {
-        orc_sampler_draw(&smp, sel);
-        ++tr.draws;
-        if (orc_is_sample_good(cloud, sel)) { got = 1; break; }
+        orc_sampler_draw_k(&smp, mdl->sample_size, sel);
+        ++out->draws;
+        if (mdl->is_sample_good(cloud, sel)) { got = 1; break; }
       }
     }
     if (!got) break; /* "No samples could be selected!" */
-    float mc[4];
-    if (!orc_compute_model(cloud, sel, mc)) {
+    float mc[6];
+    if (!mdl->compute_model(cloud, sel, mc)) {
       ++skipped;
       continue;
     }
-    int cnt = (int)orc_count_within(cloud, n, mc, threshold, prm->dot_order);
+    int cnt = (int)mdl->count_within(cloud, n, mc, threshold, prm->dot_order);
     if (cnt > n_best) {
       n_best = cnt;
-      memcpy(best_sample, sel, sizeof(sel));
-      memcpy(best_coeff, mc, sizeof(mc));
-      have_model = 1;
+      memcpy(out->best_sample, sel, sizeof(sel));
+      memcpy(out->best_coeff, mc, (size_t)mdl->n_coeff * sizeof(float));
+      out->have_model = 1;
       double w = (double)n_best * one_over_indices;
-      double p_no_outliers = 1.0 - pow(w, 3.0);
+      double p_no_outliers = 1.0 - pow(w, (double)mdl->sample_size);
       if (p_no_outliers < DBL_EPSILON) p_no_outliers = DBL_EPSILON;             /* (std::max)(eps, p) */
       if (p_no_outliers > 1.0 - DBL_EPSILON) p_no_outliers = 1.0 - DBL_EPSILON; /* (std::min)(1-eps, p) */
       k = log_probability / log(p_no_outliers);
@@ -525,7 +538,36 @@ int orc_segment(const orc_point* cloud, size_t n, const orc_params* prm, int sca
     ++iterations;
     if (iterations > max_iterations) break;
   }
-  if (n >= 3) orc_sampler_free(&smp);
+  if (n >= ss) orc_sampler_free(&smp);
+  out->iterations = iterations;
+  out->skipped = (int)skipped;
+  out->n_best = n_best;
+  return 0;
+}
+
+static int plane_good_cb(const orc_point* cloud, const int32_t* idx) { return orc_is_sample_good(cloud, idx); }
+static int plane_model_cb(const orc_point* cloud, const int32_t* idx, float* coeff) { return orc_compute_model(cloud, idx, coeff); }
+static int64_t plane_count_cb(const orc_point* cloud, size_t n, const float* coeff, double t, int dot_order) {
+  return orc_count_within(cloud, n, coeff, t, dot_order);
+}
+
+int orc_segment(const orc_point* cloud, size_t n, const orc_params* prm, int scale_exp_or_min,
+                float coeff[4], int32_t* inliers, size_t* n_inliers, orc_trace* trace) {
+  orc_trace tr;
+  memset(&tr, 0, sizeof(tr));
+  *n_inliers = 0;
+  coeff[0] = coeff[1] = coeff[2] = coeff[3] = 0.0f;
+  const double threshold = prm->distance_threshold;
+  const orc_sac_model plane = {3, plane_good_cb, plane_model_cb, plane_count_cb, 4};
+  orc_sac_result res;
+  if (orc_ransac_compute_model(cloud, n, prm, &plane, &res)) return -1;
+  const int iterations = res.iterations, have_model = res.have_model, n_best = res.n_best;
+  const unsigned skipped = (unsigned)res.skipped;
+  tr.draws = res.draws;
+  int32_t best_sample[3];
+  float best_coeff[4];
+  memcpy(best_sample, res.best_sample, sizeof(best_sample));
+  memcpy(best_coeff, res.best_coeff, sizeof(best_coeff));
 
   tr.iterations = iterations;
   tr.skipped = (int)skipped;
@@ -778,5 +820,175 @@ int orc_cluster_filter(const orc_point* cloud, size_t n, double radius, int max_
     keep[i] = (finite_pt(&cloud[i]) && size[uf_root(parent, (int32_t)i)] <= max_small_cluster) ? 0 : 1;
   free(parent);
   free(size);
+  return 0;
+}
+
+/* =========================================================================================
+ * SACMODEL_LINE as the reference calls it (Dialog/SimplifyVerticesSize.cpp:64-67,87,122,146):
+ * pcl::SACSegmentation<PointXYZ>, SACMODEL_LINE, SAC_RANSAC, setDistanceThreshold(FLT_MAX), everything else at its
+ * default (max_iterations 50, probability 0.99, optimize_coefficients true), on a few contour vertices.  Restated from
+ * PCL 1.8 sac_model_line.hpp; it runs through orc_ransac_compute_model and orc_sampler above — a second consumer of
+ * the sampler and the loop, with the reference's own call pattern: every point is an inlier of the first good sample,
+ * so w = 1, k collapses and the loop ends after one iteration.
+ *   isSampleGood            all three coordinates of the two points differ (PCL 1.8 joins the tests with &&)
+ *   computeModelCoefficients  (p0, normalised p1 - p0)
+ *   countWithinDistance     |(p0 - p) x dir|^2 < threshold^2, the square taken in double
+ *   optimizeModelCoefficients  <= 2 inliers: unchanged; else point = centroid, direction = principal axis of the
+ *                           covariance.  CHOICE: PCL gets the axis from eigen33(cov, evals) +
+ *                           computeCorrespondingEigenVector in FP32; here a cyclic Jacobi in double — the test asserts
+ *                           agreement with an independent float64 PCA to 1e-5, not bits.
+ * ========================================================================================= */
+static int line_good_cb(const orc_point* cloud, const int32_t* idx) {
+  const orc_point *a = &cloud[idx[0]], *b = &cloud[idx[1]];
+  return (a->x != b->x) && (a->y != b->y) && (a->z != b->z);
+}
+static int line_model_cb(const orc_point* cloud, const int32_t* idx, float* c) {
+  const orc_point *a = &cloud[idx[0]], *b = &cloud[idx[1]];
+  c[0] = a->x; c[1] = a->y; c[2] = a->z;
+  float dx = b->x - a->x, dy = b->y - a->y, dz = b->z - a->z;
+  float nrm = sqrtf(dx * dx + (dy * dy + dz * dz));
+  c[3] = dx / nrm; c[4] = dy / nrm; c[5] = dz / nrm;
+  return 1;
+}
+static int64_t line_count_cb(const orc_point* cloud, size_t n, const float* c, double t, int dot_order) {
+  (void)dot_order;
+  const double sqr_t = t * t;
+  int64_t cnt = 0;
+  for (size_t i = 0; i < n; ++i) {
+    const float vx = c[0] - cloud[i].x, vy = c[1] - cloud[i].y, vz = c[2] - cloud[i].z;
+    const float cx = vy * c[5] - vz * c[4], cy = vz * c[3] - vx * c[5], cz = vx * c[4] - vy * c[3];
+    const float d2 = cx * cx + (cy * cy + cz * cz);
+    if ((double)d2 < sqr_t) ++cnt;
+  }
+  return cnt;
+}
+
+int orc_segment_line(const orc_point* cloud, size_t n, const orc_params* prm, float coeff[6], int32_t* inliers, size_t* n_inliers,
+                     orc_trace* trace) {
+  orc_trace tr;
+  memset(&tr, 0, sizeof(tr));
+  *n_inliers = 0;
+  for (int i = 0; i < 6; ++i) coeff[i] = 0.0f;
+  const orc_sac_model line = {2, line_good_cb, line_model_cb, line_count_cb, 6};
+  orc_sac_result res;
+  if (orc_ransac_compute_model(cloud, n, prm, &line, &res)) return -1;
+  tr.iterations = res.iterations;
+  tr.draws = res.draws;
+  tr.skipped = res.skipped;
+  tr.ok = res.have_model;
+  if (!res.have_model) { if (trace) *trace = tr; return 0; }
+  tr.best_sample[0] = res.best_sample[0];
+  tr.best_sample[1] = res.best_sample[1];
+  tr.best_count = res.n_best;
+  memcpy(tr.raw_coeff, res.best_coeff, 4 * sizeof(float));
+  /* selectWithinDistance */
+  const double sqr_t = prm->distance_threshold * prm->distance_threshold;
+  size_t m = 0;
+  for (size_t i = 0; i < n; ++i) {
+    const float* c = res.best_coeff;
+    const float vx = c[0] - cloud[i].x, vy = c[1] - cloud[i].y, vz = c[2] - cloud[i].z;
+    const float cx = vy * c[5] - vz * c[4], cy = vz * c[3] - vx * c[5], cz = vx * c[4] - vy * c[3];
+    if ((double)(cx * cx + (cy * cy + cz * cz)) < sqr_t) inliers[m++] = (int32_t)i;
+  }
+  memcpy(coeff, res.best_coeff, 6 * sizeof(float));
+  if (prm->optimize_coefficients && m > 2) {
+    double mean[3] = {0, 0, 0};
+    for (size_t k = 0; k < m; ++k) { mean[0] += cloud[inliers[k]].x; mean[1] += cloud[inliers[k]].y; mean[2] += cloud[inliers[k]].z; }
+    for (int a = 0; a < 3; ++a) mean[a] /= (double)m;
+    double A[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+    for (size_t k = 0; k < m; ++k) {
+      const double d[3] = {cloud[inliers[k]].x - mean[0], cloud[inliers[k]].y - mean[1], cloud[inliers[k]].z - mean[2]};
+      for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) A[a][b] += d[a] * d[b];
+    }
+    double V[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+    for (int sweep = 0; sweep < 60; ++sweep) {
+      for (int p = 0; p < 2; ++p) for (int q = p + 1; q < 3; ++q) {
+        if (fabs(A[p][q]) < 1e-300) continue;
+        const double th = 0.5 * atan2(2.0 * A[p][q], A[q][q] - A[p][p]);
+        const double cs = cos(th), sn = sin(th);
+        for (int r = 0; r < 3; ++r) { const double ap = A[r][p], aq = A[r][q]; A[r][p] = cs * ap - sn * aq; A[r][q] = sn * ap + cs * aq; }
+        for (int r = 0; r < 3; ++r) { const double ap = A[p][r], aq = A[q][r]; A[p][r] = cs * ap - sn * aq; A[q][r] = sn * ap + cs * aq; }
+        for (int r = 0; r < 3; ++r) { const double vp = V[r][p], vq = V[r][q]; V[r][p] = cs * vp - sn * vq; V[r][q] = sn * vp + cs * vq; }
+      }
+    }
+    int big = 0;
+    if (A[1][1] > A[big][big]) big = 1;
+    if (A[2][2] > A[big][big]) big = 2;
+    coeff[0] = (float)mean[0]; coeff[1] = (float)mean[1]; coeff[2] = (float)mean[2];
+    coeff[3] = (float)V[0][big]; coeff[4] = (float)V[1][big]; coeff[5] = (float)V[2][big];
+    /* "Refine inliers": selectWithinDistance with the optimised line */
+    m = 0;
+    for (size_t i = 0; i < n; ++i) {
+      const float vx = coeff[0] - cloud[i].x, vy = coeff[1] - cloud[i].y, vz = coeff[2] - cloud[i].z;
+      const float cx = vy * coeff[5] - vz * coeff[4], cy = vz * coeff[3] - vx * coeff[5], cz = vx * coeff[4] - vy * coeff[3];
+      if ((double)(cx * cx + (cy * cy + cz * cz)) < sqr_t) inliers[m++] = (int32_t)i;
+    }
+  }
+  *n_inliers = m;
+  tr.n_inliers = (int)m;
+  if (trace) *trace = tr;
+  return 1;
+}
+
+/* =========================================================================================
+ * clusterFilt as the reference writes it (Dialog/PlaneDetect.h:1598-1634), literally: seeds in index order, BFS over
+ * radius searches whose hits are sorted by distance (pcl::KdTreeFLANN::radiusSearch, sorted results), the FIRST hit of
+ * every search skipped as "the query itself" (for (i = 1; ...), :1623).  FLANN does not define the order of hits at
+ * equal distance; ties_by_index = 1 sorts them by descending index (an exact duplicate with a larger index then comes
+ * before the query and is the one skipped), 0 puts the query first (the skip then always hits the query).  Exists to ENUMERATE
+ * where that skip makes the reference differ from the connected-components definition orc_cluster_filter and the
+ * device use (tests/test_normals.py): only isolated groups of exact duplicates.
+ * ========================================================================================= */
+typedef struct { float d; int32_t i; int self; } orc_hit;
+static int hit_cmp_self_first(const void* a, const void* b) {
+  const orc_hit *x = (const orc_hit*)a, *y = (const orc_hit*)b;
+  if (x->d != y->d) return x->d < y->d ? -1 : 1;
+  if (x->self != y->self) return x->self ? -1 : 1;
+  return (x->i > y->i) - (x->i < y->i);
+}
+static int hit_cmp_by_index(const void* a, const void* b) {
+  const orc_hit *x = (const orc_hit*)a, *y = (const orc_hit*)b;
+  if (x->d != y->d) return x->d < y->d ? -1 : 1;
+  return (y->i > x->i) - (y->i < x->i); /* descending: a copy with a larger index precedes the query */
+}
+
+int orc_cluster_filter_reference_bfs(const orc_point* cloud, size_t n, double radius, int max_small_cluster, int ties_by_index,
+                                     uint8_t* keep) {
+  if (!(radius > 0.0) || !isfinite(radius)) return -1;
+  const float r2 = (float)(radius * radius);
+  uint8_t* processed = (uint8_t*)calloc(n ? n : 1, 1);
+  int32_t* queue = (int32_t*)malloc((n ? n : 1) * sizeof(int32_t));
+  int32_t* members = (int32_t*)malloc((n ? n : 1) * sizeof(int32_t));
+  orc_hit* hits = (orc_hit*)malloc((n ? n : 1) * sizeof(orc_hit));
+  if (!processed || !queue || !members || !hits) { free(processed); free(queue); free(members); free(hits); return -1; }
+  for (size_t i = 0; i < n; ++i) keep[i] = 1;
+  for (size_t seed = 0; seed < n; ++seed) {
+    if (processed[seed] || !finite_pt(&cloud[seed])) continue;
+    size_t qh = 0, qt = 0, nm = 0;
+    queue[qt++] = (int32_t)seed;
+    members[nm++] = (int32_t)seed;
+    while (qh < qt) {
+      const int32_t cur = queue[qh++];
+      processed[cur] = 1;
+      size_t nh = 0;
+      for (size_t j = 0; j < n; ++j) {
+        if (!finite_pt(&cloud[j])) continue;
+        const float dx = cloud[cur].x - cloud[j].x, dy = cloud[cur].y - cloud[j].y, dz = cloud[cur].z - cloud[j].z;
+        const float d = (dx * dx + dy * dy) + dz * dz;
+        if (d < r2) { hits[nh].d = d; hits[nh].i = (int32_t)j; hits[nh].self = (int32_t)j == cur; ++nh; }
+      }
+      qsort(hits, nh, sizeof(orc_hit), ties_by_index ? hit_cmp_by_index : hit_cmp_self_first);
+      for (size_t h = 1; h < nh; ++h) {
+        const int32_t j = hits[h].i;
+        if (processed[j]) continue;
+        queue[qt++] = j;
+        members[nm++] = j;
+        processed[j] = 1;
+      }
+    }
+    if ((long long)nm <= (long long)max_small_cluster)
+      for (size_t k = 0; k < nm; ++k) keep[members[k]] = 0;
+  }
+  free(processed); free(queue); free(members); free(hits);
   return 0;
 }

@@ -84,6 +84,7 @@ typedef struct { orc_mt19937 rng; int32_t* shuffled; size_t n; } orc_sampler;
 int orc_sampler_init(orc_sampler* s, size_t n, uint32_t seed);
 void orc_sampler_free(orc_sampler* s);
 void orc_sampler_draw(orc_sampler* s, int32_t idx[3]);
+void orc_sampler_draw_k(orc_sampler* s, int sample_size, int32_t* idx);
 /* Convenience for tests: the first n_draws raw draws for a cloud of n points. */
 int orc_draw_sequence(size_t n, uint32_t seed, int n_draws, int32_t* triples /* 3*n_draws */);
 
@@ -180,6 +181,15 @@ int orc_segment(const orc_point* cloud, size_t n, const orc_params* prm, int sca
 int orc_extract_planes(const orc_point* cloud, size_t n, const orc_params* prm, float* coeffs,
                        int32_t* inlier_cur, int32_t* inlier_orig, size_t idx_cap, size_t* plane_offsets,
                        int* n_planes, orc_point* remaining, size_t* n_remaining, orc_trace* traces);
+
+/* ---- SACMODEL_LINE exactly as the reference calls it (Dialog/SimplifyVerticesSize.cpp:64-67): same sampler, same
+ * computeModel loop as the plane model; coeff = (point, direction). */
+int orc_segment_line(const orc_point* cloud, size_t n, const orc_params* prm, float coeff[6], int32_t* inliers, size_t* n_inliers,
+                     orc_trace* trace);
+/* ---- clusterFilt restated literally from Dialog/PlaneDetect.h:1598-1634 (BFS, first radius-search hit skipped), to
+ * enumerate where it differs from the connected-components definition. */
+int orc_cluster_filter_reference_bfs(const orc_point* cloud, size_t n, double radius, int max_small_cluster, int ties_by_index,
+                                     uint8_t* keep);
 
 #ifdef __cplusplus
 }

@@ -100,6 +100,24 @@ def test_plane_from_moments_matches_oracle_bitwise(O, scene2):
         assert D.host_plane_from_moments(m2, piv, s).tobytes() == want.tobytes()
 
 
+def test_pcl_float_solve_matches_oracle_bitwise(O, scene2, lib_built):
+    """PR_REFIT_PCL_FLOAT's host half (FP32 eigen33 of the nine sequential sums) against the oracle's ORC_REFIT_PCL_FLOAT;
+    the sums themselves are formed here the way the device thread forms them: one FP32 addition at a time, in index order."""
+    import ctypes as C
+    from dialog_b200 import _lib
+    L = _lib.load()
+    pts = scene2.points(0, 60_000)
+    for patch in scene2.patches:
+        c0 = patch.coeff.astype(np.float32)
+        idx = O.select_within(pts, c0, 0.1, O.DOT_FMA)
+        x, y, z = (pts[idx, a] for a in range(3))
+        terms = [x * x, x * y, x * z, y * y, y * z, z * z, x, y, z]            # float32 products
+        sums = np.array([np.cumsum(t, dtype=np.float32)[-1] for t in terms], np.float32)   # cumsum adds sequentially
+        got = np.zeros(4, np.float32)
+        _lib.check(L.plane_ransac_host_plane_from_pcl_float_sums(sums.ctypes.data_as(C.c_void_p), idx.size, got.ctypes.data_as(C.c_void_p)))
+        assert got.tobytes() == O.refit_pcl_float(pts, idx, c0).tobytes()
+
+
 def test_plane_from_moments_needs_four_points():
     with pytest.raises(D.PlaneRansacError):
         D.host_plane_from_moments(np.zeros(16, np.int64), np.zeros(3, np.float32), 0)

@@ -143,6 +143,41 @@ def test_oracle_cluster_filter_known_answers():
     assert not O.cluster_filter(chain, 0.08, 1).any()
 
 
+def test_cluster_filter_deviation_from_the_reference_is_only_isolated_duplicates():
+    """The reference grows clusters by BFS and skips the first hit of every radius search as "the query itself"
+    (Dialog/PlaneDetect.h:1623, `for (i = 1; ...)`).  FLANN lists hits by distance and leaves the order of equal distances
+    open, so with an exact duplicate in the cloud the skipped hit can be the duplicate instead.  This enumerates where that
+    literal procedure (both tie orders) differs from the connected-components definition the oracle and the device use:
+    nowhere on a cloud without duplicates; with duplicates, only points whose every neighbour is an exact copy of them."""
+    from oracle import oracle as O
+    rng = np.random.default_rng(4)
+    base = np.ones((2500, 4), np.float32)
+    base[:, :3] = rng.random((2500, 3)) * [3.0, 3.0, 0.4]
+    for radius, small in ((0.12, 3), (0.2, 8), (0.08, 1)):
+        want = O.cluster_filter(base, radius, small)
+        for ties in (False, True):
+            assert np.array_equal(O.cluster_filter_reference_bfs(base, radius, small, ties), want)
+    dup = base.copy()
+    far = np.array([[9.0, 9, 9], [12.0, 9, 9], [15.0, 9, 9]], np.float32)
+    dup[10:12, :3] = far[0]                 # an isolated pair of identical points
+    dup[20:23, :3] = far[1]                 # an isolated triple
+    dup[30:32, :3] = dup[500, :3]           # copies of a point in the middle of the slab: they share its neighbours
+    dup[40, :3] = far[2]                    # an isolated single point
+    enumerated = set()
+    for radius, small in ((0.12, 1), (0.12, 2), (0.2, 2)):
+        ours = O.cluster_filter(dup, radius, small)
+        for ties in (False, True):
+            ref = O.cluster_filter_reference_bfs(dup, radius, small, ties)
+            differ = np.nonzero(ref != ours)[0]
+            for i in differ.tolist():
+                d2 = ((dup[:, :3] - dup[i, :3]) ** 2).sum(1)
+                near = np.nonzero(d2 < np.float32(radius * radius))[0]
+                assert (dup[near, :3] == dup[i, :3]).all() and near.size >= 2, i      # only exact copies around it
+                enumerated.add(i)
+    assert enumerated and enumerated <= {10, 11, 20, 21, 22}
+    print(f"clusterFilt: the reference's first-hit skip changes the outcome for points {sorted(enumerated)} only (isolated exact duplicates)")
+
+
 @pytest.mark.gpu
 def test_gpu_cluster_filter_matches_oracle():
     import dialog_b200 as D

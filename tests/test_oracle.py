@@ -247,3 +247,63 @@ def test_double_shadow_reference_threshold_is_degenerate(O, double_shadow):
     seg = O.segment(double_shadow, O.make_params(0.1, 50, 500, 0.99, True, dot_order=O.DOT_PCL_SSE2,
                                                  refit_mode=O.REFIT_PCL_FLOAT))
     assert seg.ok and seg.inliers.size == 991 and seg.trace.iterations == 1
+
+
+def test_line_model_replays_the_reference_sac_call_on_its_saved_contours(O):
+    """The reference's only literal pcl::SACSegmentation call (Dialog/SimplifyVerticesSize.cpp:64-67,87,122,146): SACMODEL_LINE,
+    SAC_RANSAC, setDistanceThreshold(FLT_MAX), defaults otherwise, on a growing run of contour vertices.  Replayed here on
+    the 11 plane borders the reference saved (Dialog/dataForPlane/source_plane_registration.pcd, tests/golden/
+    ref_polygons_golden.npz) through the SAME sampler and computeModel loop the plane path uses — a second, independent
+    consumer of that code with the reference's own call pattern: every vertex is an inlier of the first good 2-point
+    sample, w = 1 makes k collapse, and the loop ends after one iteration."""
+    g = np.load(os.path.join(GOLDEN, "ref_polygons_golden.npz"))
+    verts, sizes = g["vertices"], g["sizes"]
+    flt_max = float(np.finfo(np.float32).max)
+    prm = O.make_params(flt_max, 50, 0, 0.99, True, 12345, 1, O.DOT_FMA, O.REFIT_PCL_FLOAT)
+    start, fits = 0, 0
+    for poly, m in enumerate(sizes.tolist()):
+        contour = verts[start:start + m]
+        start += m
+        for seed in range(0, m, max(1, m // 6)):
+            for grow in (1, 2, 4, 9):                      # prev / seed / next, then the run as constructInitLineSegs grows it
+                idx = [(seed + d) % m for d in range(-grow, grow + 1)]
+                run = np.ones((len(idx), 4), np.float32)
+                run[:, :3] = contour[idx]
+                n = run.shape[0]
+                ok, coeff, inl, tr = O.segment_line(run, prm)
+                # the sampler, restated independently: partial Fisher-Yates with a 2-point sample over mt19937(12345) >> 1
+                raw = O.mt19937_stream(12345, 2 * 1000).astype(np.int64) >> 1
+                sh, draws, pair = list(range(n)), 0, None
+                for k in range(1000):
+                    for i in range(2):
+                        j = i + int(raw[2 * k + i]) % (n - i)
+                        sh[i], sh[j] = sh[j], sh[i]
+                    draws += 1
+                    a, b = run[sh[0], :3], run[sh[1], :3]
+                    if (a != b).all():                     # PCL 1.8 isSampleGood: x, y AND z differ
+                        pair = sh[:2]
+                        break
+                assert ok == (pair is not None)
+                if not ok:
+                    continue
+                assert tr.iterations == 1 and tr.draws == draws and list(tr.best_sample)[:2] == pair
+                assert tr.best_count == n and inl.size == n and (inl == np.arange(n)).all()
+                # optimizeModelCoefficients: point = centroid, direction = principal axis (float64 PCA as the yardstick)
+                p64 = run[:, :3].astype(np.float64)
+                assert np.abs(coeff[:3] - p64.mean(0)).max() <= 1e-6 * max(1.0, np.abs(p64).max())
+                w, v = np.linalg.eigh(np.cov((p64 - p64.mean(0)).T))
+                if w[2] > 1e-9 and w[2] > 4 * w[1]:        # a run that is a line, not a corner: the axis is well defined
+                    assert abs(float(coeff[3:] @ v[:, 2])) >= 1 - 1e-5
+                assert abs(float(np.linalg.norm(coeff[3:])) - 1) <= 1e-6
+                fits += 1
+    assert fits > 200
+    # the k-point sampler against the same Python walk on a larger index set
+    raw = O.mt19937_stream(12345, 2 * 40).astype(np.int64) >> 1
+    sh, exp = list(range(997)), []
+    for k in range(40):
+        for i in range(2):
+            j = i + int(raw[2 * k + i]) % (997 - i)
+            sh[i], sh[j] = sh[j], sh[i]
+        exp.append(sh[:2])
+    assert (O.draw_sequence_k(997, 40, 2) == np.array(exp)).all()
+    assert (O.draw_sequence_k(500, 30, 3) == O.draw_sequence(500, 30)).all()
