@@ -29,7 +29,7 @@ SYMBOLS = [
     "plane_ransac_cloud_size", "plane_ransac_score", "plane_ransac_segment_one", "plane_ransac_extract_planes",
     "plane_ransac_plane_points", "plane_ransac_set_round_loop", "plane_ransac_remaining", "plane_ransac_reabsorb", "plane_ransac_estimate_normals", "plane_ransac_cluster_filter", "plane_ransac_restage_remaining", "plane_ransac_set_cloud_batch", "plane_ransac_segment_batch", "plane_ransac_segment_batch_lists",
     "plane_ransac_comm_unique_id", "plane_ransac_comm_init", "plane_ransac_comm_p2p_enabled", "plane_ransac_shard_info",
-    "plane_ransac_host_alloc", "plane_ransac_host_free", "plane_ransac_host_register", "plane_ransac_host_unregister", "plane_ransac_profile_enable", "plane_ransac_profile_reset", "plane_ransac_profile_get",
+    "plane_ransac_load_pcd", "plane_ransac_host_alloc", "plane_ransac_host_free", "plane_ransac_host_register", "plane_ransac_host_unregister", "plane_ransac_profile_enable", "plane_ransac_profile_reset", "plane_ransac_profile_get",
     "plane_ransac_timer_start", "plane_ransac_timer_stop", "plane_ransac_measure_ffma_peak", "plane_ransac_measure_copy_bw", "plane_ransac_flush_l2",
     "plane_ransac_host_draw_triples", "plane_ransac_host_draw_triples_parallel", "plane_ransac_host_replay", "plane_ransac_host_shard_range",
     "plane_ransac_host_plane_from_moments", "plane_ransac_host_plane_from_pcl_float_sums", "plane_ransac_host_rand_edges",
@@ -128,6 +128,7 @@ def load():
     L.plane_ransac_shard_info.argtypes = [vp] + [C.POINTER(C.c_longlong)] * 4
     L.plane_ransac_host_alloc.argtypes = [sz, C.POINTER(vp)]
     L.plane_ransac_host_free.argtypes = [vp]
+    L.plane_ransac_load_pcd.argtypes = [C.c_char_p, C.POINTER(vp), C.POINTER(sz)]
     L.plane_ransac_host_register.argtypes = [vp, sz]
     L.plane_ransac_host_unregister.argtypes = [vp]
     L.plane_ransac_profile_enable.argtypes = [vp, C.c_int]

@@ -28,7 +28,7 @@ NVCC_FLAGS = [
 CXX_FLAGS = ["-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-Wall", "-Wextra",
              f"-I{CUDA_HOME}/include"]
 
-SOURCES = [("pr_kernels.cu", "nvcc"), ("pr_chain.cu", "nvcc"), ("pr_reabsorb.cu", "nvcc"), ("pr_p2p.cu", "nvcc"), ("pr_normals.cu", "nvcc"), ("pr_host.cpp", "cxx"), ("pr_api.cpp", "cxx")]
+SOURCES = [("pr_kernels.cu", "nvcc"), ("pr_chain.cu", "nvcc"), ("pr_reabsorb.cu", "nvcc"), ("pr_p2p.cu", "nvcc"), ("pr_normals.cu", "nvcc"), ("pr_host.cpp", "cxx"), ("pr_pcd.cpp", "cxx"), ("pr_api.cpp", "cxx")]
 HEADERS = ["pr_kernels.h", "pr_host.hpp", "pr_math.h", "pr_draw.h", os.path.join("..", "..", "include", "plane_ransac.h")]
 
 

@@ -16,6 +16,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -1441,6 +1442,41 @@ int p2p_setup(plane_ransac_ctx* c) {
 
 }  // namespace
 
+namespace pr {
+// Pageable stand-in for plane_ransac_host_alloc where page-locking is impossible (no CUDA device: the PCD reader still
+// works there, e.g. in a conversion tool); remembered so that plane_ransac_host_free releases it the right way.
+static std::mutex g_plain_mu;
+static std::vector<void*> g_plain_allocs;
+void* plain_alloc(size_t bytes) {
+  void* p = std::malloc(bytes ? bytes : 1);
+  if (p) {
+    std::lock_guard<std::mutex> lk(g_plain_mu);
+    g_plain_allocs.push_back(p);
+  }
+  return p;
+}
+bool release_plain_alloc(void* p) {
+  std::lock_guard<std::mutex> lk(g_plain_mu);
+  for (size_t i = 0; i < g_plain_allocs.size(); ++i)
+    if (g_plain_allocs[i] == p) {
+      g_plain_allocs.erase(g_plain_allocs.begin() + (long)i);
+      std::free(p);
+      return true;
+    }
+  return false;
+}
+// error hook for the other translation units of the library (pr_pcd.cpp)
+int pcd_fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_error = buf;
+  return code;
+}
+}  // namespace pr
+
 // =================================================================================================
 // extern "C"
 // =================================================================================================
@@ -2569,6 +2605,7 @@ int plane_ransac_host_alloc(size_t bytes, void** out) {
 }
 
 int plane_ransac_host_free(void* p) {
+  if (p && pr::release_plain_alloc(p)) return PR_OK;  // a reader's buffer on a host without a CUDA device
   if (p && cudaFreeHost(p) != cudaSuccess) {
     cudaGetLastError();
     return fail(PR_ERR_CUDA, "cudaFreeHost failed");

@@ -13,7 +13,7 @@
 //     --bench STEPS          the cloud in a page-locked buffer; STEPS timed detectViews() calls, host cloud in ->
 //                            coefficients + index lists out, wall clock per call
 //
-// .pcd: ASCII PCD v0.7 with x y z as the first three fields (the format of Dialog/double_shadow.pcd);
+// .pcd: PCD v0.7 through plane_ransac_load_pcd (ascii like Dialog/double_shadow.pcd, binary, binary_compressed);
 // .f32: raw little-endian float32 x,y,z triples.
 #include <algorithm>
 #include <chrono>
@@ -22,7 +22,6 @@
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
-#include <sstream>
 #include <string>
 #include <vector>
 
@@ -36,23 +35,17 @@ using plane_detect_ransac::PointXYZ;
 
 static bool load_cloud(const std::string& path, std::vector<PointXYZ>& out) {
   if (path.size() > 4 && path.substr(path.size() - 4) == ".pcd") {
-    std::ifstream f(path);
-    if (!f) return false;
-    std::string line;
-    bool data = false;
-    while (std::getline(f, line)) {
-      if (!data) {
-        if (line.rfind("DATA", 0) == 0) {
-          if (line.find("ascii") == std::string::npos) return false;
-          data = true;
-        }
-        continue;
-      }
-      std::istringstream ss(line);
-      PointXYZ p{0, 0, 0, 1.0f};
-      if (ss >> p.x >> p.y >> p.z) out.push_back(p);
+    // the library's reader (pcl::io::loadPCDFile's formats: ascii, binary, binary_compressed)
+    pr_point* pts = nullptr;
+    size_t n = 0;
+    if (plane_ransac_load_pcd(path.c_str(), &pts, &n) != PR_OK) {
+      std::fprintf(stderr, "%s\n", plane_ransac_last_error());
+      return false;
     }
-    return data;
+    out.resize(n);
+    if (n) std::memcpy(out.data(), pts, n * sizeof(PointXYZ));
+    plane_ransac_host_free(pts);
+    return true;
   }
   std::ifstream f(path, std::ios::binary);
   if (!f) return false;

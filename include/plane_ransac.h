@@ -301,6 +301,14 @@ int plane_ransac_host_free(void* p);
 int plane_ransac_host_register(void* p, size_t bytes);
 int plane_ransac_host_unregister(void* p);
 
+/* ---- cloud reader: pcl::io::loadPCDFile for an XYZ cloud (Dialog/PCLViewer.cpp:80-89) ---------------------------
+ * PCD v0.7, DATA ascii / binary / binary_compressed; x, y, z may sit anywhere in the record and have any numeric
+ * type, other fields are skipped (Dialog/double_shadow.pcd is "x y z rgb", ascii).  *points is a page-locked buffer of
+ * *n_points pcl::PointXYZ-compatible records (w = 1), ready for plane_ransac_set_cloud_async; release it with
+ * plane_ransac_host_free.  Non-finite points are kept (plane_ransac_set_cloud_ex removes them, as the reference's
+ * preProcess does). */
+int plane_ransac_load_pcd(const char* path, pr_point** points, size_t* n_points);
+
 /* ---- measurement ------------------------------------------------------------------------- */
 int plane_ransac_profile_enable(plane_ransac_ctx* ctx, int on);
 int plane_ransac_profile_reset(plane_ransac_ctx* ctx);
