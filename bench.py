@@ -303,6 +303,52 @@ def run_extras(args, pr):
         "nan_normals": int(np.isnan(nrm[:, 0]).sum()),
         "oracle_check": {"points": n_chk, "counts_identical": bool(np.array_equal(sub_c, want_c)), "max_normal_diff": float(dn.max()) if okn.any() else 0.0},
         "note": "includes the 160 MB + 40 MB download of normals and counts to pageable host memory"}
+    # BASELINE configs[3] scale, PCL-default adaptive mode (max_iterations = 50, probability = 0.99), host cloud in ->
+    # coefficients + inlier indices out, against the CPU oracle on the whole 100M-point scene (~100 s of one core)
+    big = storeys_cloud(pts10, 0, 100_000_000)
+    pinb = D.PinnedArray(big.shape, np.float32)
+    pinb.array[:] = big
+    prm = D.make_params(0.1, 50, 500, 0.99, True, 12345, args.planes, D.DOT_FMA)
+    pr.set_cloud_ptr(pinb.ptr, big.shape[0], overlap=True)
+    exb = pr.extract_planes(prm, want_indices=True, copy=False)
+    ms = []
+    for _ in range(2):
+        pr.flush_l2()
+        pr.timer_start()
+        pr.set_cloud_ptr(pinb.ptr, big.shape[0], overlap=True)
+        exb = pr.extract_planes(prm, want_indices=True, copy=False)
+        ms.append(pr.timer_stop())
+    t0 = time.perf_counter()
+    want = O.extract_planes(big, O.make_params(0.1, 50, 500, 0.99, True, 12345, args.planes, O.DOT_FMA, O.REFIT_FIXED))
+    cpu_s = time.perf_counter() - t0
+    same = len(want.coeffs) == len(exb.planes) and all(
+        p.coeff.tobytes() == want.coeffs[k].tobytes() and np.array_equal(p.inliers_orig, want.inliers_orig[k])
+        for k, p in enumerate(exb.planes))
+    out["pcl_default_adaptive_100M_end_to_end"] = {
+        "gpu_ms": sum(ms) / len(ms), "cpu_oracle_s": cpu_s, "cpu_threads": 1, "planes": len(exb.planes),
+        "identical_to_cpu_oracle": bool(same), "speedup": cpu_s / (sum(ms) / len(ms) * 1e-3),
+        "note": "ten 10M-point storeys (the configs[3] scene); 1.6 GB pinned cloud in, coefficients + inlier indices out"}
+    pinb.free()
+    del big, want
+    pr.set_cloud(pts10[:1000])
+    # the drop-in C++ surface end to end at the headline size: examples/plane_detect_demo --bench (PlaneDetectRansac::
+    # detectViews on a page-locked cloud: upload + 20 rounds + index lists back), wall clock per call
+    try:
+        import tempfile
+        from dialog_b200 import build as _b
+        demo = _b.build_demo()
+        with tempfile.TemporaryDirectory() as td:
+            path = os.path.join(td, "cloud.f32")
+            pts10[:, :3].astype("<f4").tofile(path)
+            r = subprocess.run([demo, path, "0.1", str(args.hyps - 1), "500", "--prob", "1.0", "--max-planes", str(args.planes), "--bench", "5"],
+                               capture_output=True, text=True, timeout=600)
+        f = r.stdout.split()
+        out["cpp_shim_end_to_end"] = {"ms_per_step": float(f[f.index("e2e_ms_per_step") + 1]), "planes": int(f[f.index("planes") + 1]),
+                                      "inliers": int(f[f.index("inliers") + 1]),
+                                      "what": "examples/plane_detect_demo --bench 5: PlaneDetectRansac::detectViews (include/PlaneDetectRansac.h) on a "
+                                              "page-locked 10M-point cloud, same parameters as the headline; compare with e2e.ms_per_step"}
+    except Exception as e:  # noqa: BLE001
+        out["cpp_shim_end_to_end"] = {"error": str(e)}
     # configs[4]: batch of 32K-point clouds, one plane each, 256 hypotheses per cloud (slice of the 4096 clouds)
     nc = args.batch_clouds
     clouds = np.stack([synth.tile_scene(cid).points(0, 32768) for cid in range(nc)])
