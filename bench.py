@@ -127,9 +127,9 @@ class ClockSampler:
 
 
 def ncu_traffic():
-    """DRAM bytes per launch of the scoring kernel from the committed ncu capture (profiles/r01_traffic.json)."""
+    """DRAM bytes per launch of the scoring kernel from the committed ncu capture (profiles/r02_traffic.json)."""
     try:
-        return json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        return json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
     except Exception:
         return None
 

@@ -51,9 +51,11 @@ def summarize_rep(rep, out):
                 if k in hdr:
                     i = hdr.index(k)
                     f.write(f"{k:86s} {r[i]:>18s} {units[i]}\n")
-            rd = float(r[hdr.index('dram__bytes_read.sum')]); wr = float(r[hdr.index('dram__bytes_write.sum')])
-            u = units[hdr.index('dram__bytes_read.sum')]
-            f.write(f"{'traffic = dram read + write':86s} {rd + wr:18.3f} {u}\n")
+            mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+            ir, iw = hdr.index('dram__bytes_read.sum'), hdr.index('dram__bytes_write.sum')
+            rd = float(r[ir].replace(",", "")) * mult.get(units[ir], 1.0)
+            wr = float(r[iw].replace(",", "")) * mult.get(units[iw], 1.0)
+            f.write(f"{'traffic = dram read + write':86s} {(rd + wr) / 1e6:18.3f} Mbyte\n")
 
 
 def summarize_launches(path, out):
