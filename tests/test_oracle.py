@@ -296,7 +296,8 @@ def test_line_model_replays_the_reference_sac_call_on_its_saved_contours(O):
                     assert abs(float(coeff[3:] @ v[:, 2])) >= 1 - 1e-5
                 assert abs(float(np.linalg.norm(coeff[3:])) - 1) <= 1e-6
                 fits += 1
-    assert fits > 200
+    assert fits > 200, fits
+    print(f'line-model fits replayed: {fits}')
     # the k-point sampler against the same Python walk on a larger index set
     raw = O.mt19937_stream(12345, 2 * 40).astype(np.int64) >> 1
     sh, exp = list(range(997)), []

@@ -238,6 +238,96 @@ float time_ms(F f, int reps = 5) {
   return best;
 }
 
+
+// MODE 9: the FFMA2 chain of hypothesis j + 1 interleaved one-to-one with the FSET / IADD3 of hypothesis j, the order
+// pinned with asm volatile (ptxas otherwise groups the FFMA2s first and leaves runs of ALU instructions at the end).
+__device__ __forceinline__ unsigned long long pk(float2 v) { return ((unsigned long long)__float_as_uint(v.y) << 32) | __float_as_uint(v.x); }
+__device__ __forceinline__ unsigned long long ffma2v(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long d;
+  asm volatile("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ unsigned fsetv(unsigned bits, float t) {
+  float f;
+  asm volatile("set.lt.f32.f32 %0, %1, %2;" : "=f"(f) : "f"(fabsf(__uint_as_float(bits))), "f"(t));
+  return __float_as_uint(f);
+}
+__device__ __forceinline__ unsigned iadd3v(unsigned a, unsigned b, unsigned c) {
+  unsigned d;
+  asm volatile("{.reg .u32 t; add.u32 t, %1, %2; add.u32 %0, t, %3;}" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+template <int H>
+__global__ void __launch_bounds__(256, 2) k_score_il(const float4* __restrict__ hyps, int* __restrict__ out, int iters, float t) {
+  __shared__ __align__(16) float sx[TP];
+  __shared__ __align__(16) float sy[TP];
+  __shared__ __align__(16) float sz[TP];
+  for (int i = threadIdx.x; i < TP; i += blockDim.x) {
+    sx[i] = (i * 37 % 101) * 0.03f; sy[i] = (i * 11 % 97) * 0.031f; sz[i] = (i * 7 % 89) * 0.029f;
+  }
+  __syncthreads();
+  unsigned long long A[H], B[H], C[H], D[H];
+  int cnt[H];
+  unsigned acc[H];
+#pragma unroll
+  for (int j = 0; j < H; ++j) {
+    float4 h = hyps[(blockIdx.x * blockDim.x + threadIdx.x) * H + j];
+    A[j] = pk(make_float2(h.x, h.x)); B[j] = pk(make_float2(h.y, h.y)); C[j] = pk(make_float2(h.z, h.z)); D[j] = pk(make_float2(h.w, h.w));
+    cnt[j] = 0; acc[j] = 0;
+  }
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll 1
+    for (int pb = 0; pb < TP; pb += 4 * 64) {
+#pragma unroll
+      for (int j = 0; j < H; ++j) { cnt[j] += ((acc[j] >> 23) * 383u) & 511u; acc[j] = 0; }
+      unsigned long long p0 = 0x7FC000007FC00000ull, p1 = p0;  // residual pairs of the previous hypothesis (NaN: never counted)
+#pragma unroll 4
+      for (int p = pb; p < pb + 4 * 64; p += 4) {
+        const float4 X = *reinterpret_cast<const float4*>(&sx[p]);
+        const float4 Y = *reinterpret_cast<const float4*>(&sy[p]);
+        const float4 Z = *reinterpret_cast<const float4*>(&sz[p]);
+        const unsigned long long X0 = pk(make_float2(X.x, X.y)), X1 = pk(make_float2(X.z, X.w));
+        const unsigned long long Y0 = pk(make_float2(Y.x, Y.y)), Y1 = pk(make_float2(Y.z, Y.w));
+        const unsigned long long Z0 = pk(make_float2(Z.x, Z.y)), Z1 = pk(make_float2(Z.z, Z.w));
+#pragma unroll
+        for (int j = 0; j < H; ++j) {
+          const int q = (j + H - 1) % H;  // the hypothesis whose residuals are compared now
+          unsigned f0 = 0, f1 = 0, f2 = 0, f3 = 0;
+          unsigned long long r0 = ffma2v(C[j], Z0, D[j]);
+          f0 = fsetv((unsigned)p0, t);
+          unsigned long long r1 = ffma2v(C[j], Z1, D[j]);
+          f1 = fsetv((unsigned)(p0 >> 32), t);
+          r0 = ffma2v(B[j], Y0, r0);
+          f2 = fsetv((unsigned)p1, t);
+          r1 = ffma2v(B[j], Y1, r1);
+          f3 = fsetv((unsigned)(p1 >> 32), t);
+          r0 = ffma2v(A[j], X0, r0);
+          acc[q] = iadd3v(acc[q], f0, f1);
+          r1 = ffma2v(A[j], X1, r1);
+          acc[q] = iadd3v(acc[q], f2, f3);
+          p0 = r0; p1 = r1;
+        }
+      }
+      {  // drain: the last hypothesis of the last step
+        const unsigned f0 = fsetv((unsigned)p0, t), f1 = fsetv((unsigned)(p0 >> 32), t), f2 = fsetv((unsigned)p1, t), f3 = fsetv((unsigned)(p1 >> 32), t);
+        acc[H - 1] = iadd3v(acc[H - 1], f0, f1);
+        acc[H - 1] = iadd3v(acc[H - 1], f2, f3);
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < H; ++j) out[(blockIdx.x * blockDim.x + threadIdx.x) * H + j] = cnt[j] + (int)(((acc[j] >> 23) * 383u) & 511u);
+}
+template <int H>
+void run_score_il(const char* name, int nsm, float4* dh, int* dout, double peak_tf) {
+  int grid = nsm * 2, iters = 64;
+  float ms = time_ms([&] { k_score_il<H><<<grid, 256>>>(dh, dout, iters, 0.1f); });
+  CK(cudaGetLastError());
+  double pairs = (double)grid * 256 * H * (double)TP * iters;
+  double tf = pairs * 6 / (ms * 1e-3) / 1e12;
+  printf("%-34s H=%d  %8.3f ms  %8.3f Tpairs/s  %7.2f TFLOP/s-equiv  %5.1f%% of ffma peak\n", name, H, ms, pairs / (ms * 1e-3) / 1e12, tf, 100 * tf / peak_tf);
+}
+
 template <int H, int MODE>
 void run_score(const char* name, int nsm, float4* dh, int* dout, double peak_tf) {
   int grid = nsm * 2, iters = 64;
@@ -294,6 +384,15 @@ int main() {
   run_score<4, 7>("FFMA2 + FSET.BF + IADD3 2-in mod512", nsm, dh, dcnt, best_tf);
   run_score<8, 8>("FFMA + FSET.BF + IADD3 2-in mod512", nsm, dh, dcnt, best_tf);
   run_score<4, 8>("FFMA + FSET.BF + IADD3 2-in mod512", nsm, dh, dcnt, best_tf);
+  run_score_il<8>("FFMA2/FSET/IADD3 interleaved 1:1 (asm volatile)", nsm, dh, dcnt, best_tf);
+  {
+    std::vector<int> a(16), b(16);
+    run_score<8, 7>("  (check) mod512 reference", nsm, dh, dcnt, best_tf);
+    CK(cudaMemcpy(a.data(), dcnt, 64, cudaMemcpyDeviceToHost));
+    run_score_il<8>("  (check) interleaved", nsm, dh, dcnt, best_tf);
+    CK(cudaMemcpy(b.data(), dcnt, 64, cudaMemcpyDeviceToHost));
+    printf("interleaved counts %s the reference variant (%d %d %d vs %d %d %d)\n", a == b ? "equal" : "DIFFER FROM", a[0], a[1], a[2], b[0], b[1], b[2]);
+  }
   run_score<8, 6>("FFMA2 + FSET mask, IADD3 2-in", nsm, dh, dcnt, best_tf);
   run_score<4, 6>("FFMA2 + FSET mask, IADD3 2-in", nsm, dh, dcnt, best_tf);
   std::vector<int> hc(16); CK(cudaMemcpy(hc.data(), dcnt, 64, cudaMemcpyDeviceToHost));
