@@ -739,6 +739,29 @@ def main():
     pr2.close()
     pr.set_cloud_ptr(pinned.data_ptr(), count)
 
+    # ---- the PCL-faithful dot order (Eigen's SSE2 reduction: 3 FMUL + 3 FADD, separately rounded) on the same workload ----
+    sse2 = None
+    if args.scorer == "brute":
+        prm_s = D.make_params(0.1, args.hyps - 1, 500, 1.0, True, 12345, args.planes, D.DOT_PCL_SSE2)
+        for _ in range(2):
+            exs = pr.extract_planes(prm_s, want_indices=False)
+        pr.profile_enable(True)
+        pr.profile_reset()
+        sse2_ms = []
+        for _ in range(min(args.steps, 3)):
+            pr.flush_l2()
+            barrier()
+            pr.timer_start()
+            exs = pr.extract_planes(prm_s, want_indices=False)
+            sse2_ms.append(pr.timer_stop())
+        ps = pr.profile()
+        pr.profile_enable(False)
+        sse2 = {"ms_per_step": sum(sse2_ms) / len(sse2_ms), "planes": len(exs.planes),
+                "score_tflops": 6.0 * ps.pairs_scored / (ps.ms_score * 1e-3) / 1e12 if ps.ms_score > 0 else None,
+                "note": "PR_DOT_PCL_SSE2: (a*x + c*z) + (b*y + d) with separately rounded products, the order PCL 1.8 / MSVC v140 "
+                        "evaluates; 6 FP32 operations per point-hypothesis issue as 6 scalar instructions (ptxas fuses packed mul+add "
+                        "into FFMA2, which would change the bits), against 1.5 FFMA2 for the FMA order; this rank's figure"}
+
     # ---- same workload through the opt-in hierarchical (bounding-box culled) scorer: identical planes ----
     hier_ms = []
     hier_same = None
@@ -828,6 +851,9 @@ def main():
                           "as kernels; the host reads one record per round",
             "clocks": clock_info,
         }
+        if sse2:
+            sse2["frac_of_fp32_peak"] = sse2["score_tflops"] / peak_tf if sse2["score_tflops"] else None
+            line["pcl_sse2_dot_order"] = sse2
         if waits:
             line["exchange_wait_ms_per_step_by_rank"] = {
                 "channels": ["sample points", "counts", "refit moments", "remaining counts"],

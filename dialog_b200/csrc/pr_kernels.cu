@@ -1032,11 +1032,8 @@ static void launch_score_hier_t(dim3 grid, const float* SX, const float* SY, con
                                 size_t n_blocks, int n_tiles, int tiles_per_cta, const float4* hyps, const float2* aux,
                                 int K, float t, int32_t* counts, cudaStream_t s) {
   const size_t smem = 3 * kTilePoints * sizeof(float) + kHierMaxK * sizeof(int) + 32 * (CH + 32) * sizeof(unsigned short) + 33 * sizeof(int);
-  static bool configured = false;
-  if (!configured) {
-    cudaFuncSetAttribute(score_hier_kernel<DOT, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    configured = true;
-  }
+  // function attributes are per device (a process may hold contexts on several): set on every launch, it is cheap
+  if (cudaFuncSetAttribute(score_hier_kernel<DOT, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return;
   score_hier_kernel<DOT, CH><<<grid, 256, smem, s>>>(SX, SY, SZ, bounds, n_blocks, n_tiles, tiles_per_cta, hyps, aux, K, t, counts);
 }
 

@@ -6,7 +6,18 @@
  * tests or golden vectors for it.  Each function restates the published PCL 1.8 behaviour of the
  * source file it names (restated from the PCL 1.8 sources, not copied from /root/reference, which
  * does not contain them).  Known places where PCL's result depends on its build and this file had
- * to pick one behaviour are marked "CHOICE".
+ * to pick one behaviour are marked "CHOICE".  All of them, in one place:
+ *   - rnd() == rng() >> 1: boost::uniform_int<>(0, INT_MAX) over mt19937.  Holds for Boost >= 1.47 (the
+ *     generate_uniform_int algorithm: engine range 2^32 - 1 over target range 2^31 - 1 gives bucket_size 2 and never
+ *     rejects); Boost is not vendored with the reference, PCL 1.8.x binaries for MSVC v140 shipped with Boost 1.6x.
+ *   - Eigen >= 3.3: Vector::normalize() and "accu /= n" DIVIDE (Eigen 3.2 multiplied by the reciprocal).
+ *   - Eigen's 4-wide FP32 reductions run in SSE2 order (e0 + e2) + (e1 + e3) (MSVC v140 x64, no AVX): the plane dot
+ *     product of countWithinDistance (ORC_DOT_PCL_SSE2), the squared norm and d of computeModelCoefficients, the
+ *     Hessian d of optimizeModelCoefficients.  ORC_DOT_FMA is this backend's own faster order, also implemented.
+ *   - no FP contraction on the reference toolchain (MSVC v140 /fp:precise): every '*' and '+' rounds separately.
+ *   - the line model's optimised axis (SACMODEL_LINE, only used to replay the reference's own SAC call) comes from a
+ *     double-precision Jacobi instead of PCL's FP32 eigen33 + computeCorrespondingEigenVector.
+ *   - the libm behind eigen33's atan2 / cos / sin is this platform's (glibc), not MSVC's CRT.
  *
  * Build: gcc -O2 -ffp-contract=off -mfma -fopenmp -fPIC -shared  (see oracle/Makefile).
  * -ffp-contract=off keeps every '*' and '+' separately rounded (MSVC v140 / SSE2 code generation);
