@@ -122,6 +122,14 @@ __global__ void __launch_bounds__(kResolveThreads) draw_resolve_kernel(RoundStat
     for (uint32_t k = 0; k < 4; ++k) s_pre[4 * i + k] = s >= k ? v[s - k] : 0;
   }
   __syncthreads();
+  SmemFetch fetch{s_sorted, s_pre};
+  // common case: the listed ops only interact inside their position groups -> one thread per entry (pr_draw.h)
+  int ok = 1;
+  for (uint32_t i = threadIdx.x; i < n_c; i += kResolveThreads) ok = ok && draw_independent_ok(s_sorted, (int)i, fetch);
+  if (__syncthreads_and(ok)) {
+    for (uint32_t i = threadIdx.x; i < n_c; i += kResolveThreads) v[s_sorted[i]] = draw_resolve_independent(s_sorted, (int)i, fetch);
+    return;
+  }
   if (threadIdx.x != 0) return;
   if (s_distinct > kDrawMaxCollisions) {
     st->stop = 2;
@@ -130,7 +138,6 @@ __global__ void __launch_bounds__(kResolveThreads) draw_resolve_kernel(RoundStat
     rec->ran = 1;
     return;
   }
-  SmemFetch fetch{s_sorted, s_pre};
   draw_resolve(s_sorted, (int)n_c, v, fetch, s_keys, s_vals, (uint32_t)(kResolveMapSlots - 1));
 }
 

@@ -94,6 +94,31 @@ PR_HD void draw_resolve(const uint32_t* ops_sorted, int n_ops, int32_t* v, Fetch
   }
 }
 
+// The common case needs no sequential replay at all.  If no listed op lies in the head (b < 3) and no two distinct listed
+// ops are within 3 of each other, the listed ops only interact inside the group that shares a position q: the first op
+// of a group reads q itself, every later one reads what its predecessor s' in the group left there, which is the
+// content of head position a' = s' % 3 just before s', i.e. v[s' - 3] (s' - 3 is not a listed op, so that value is its
+// b), or a' itself for s' < 3.  draw_independent_ok tests the condition for entry i, draw_resolve_independent gives
+// entry i's value; both are evaluated by one thread per entry.
+template <class Fetch>
+PR_HD bool draw_independent_ok(const uint32_t* ops_sorted, int i, Fetch fetch) {
+  const uint32_t s = ops_sorted[i];
+  if ((uint32_t)fetch(i, s) < 3u) return false;
+  return i == 0 || s == ops_sorted[i - 1] || s - ops_sorted[i - 1] > 3u;
+}
+
+template <class Fetch>
+PR_HD int32_t draw_resolve_independent(const uint32_t* ops_sorted, int i, Fetch fetch) {
+  const uint32_t s = ops_sorted[i];
+  const uint32_t q = (uint32_t)fetch(i, s);
+  for (int j = i - 1; j >= 0; --j) {
+    const uint32_t sp = ops_sorted[j];
+    if (sp == s || (uint32_t)fetch(j, sp) != q) continue;  // a duplicate entry of this op / another group
+    return sp >= 3u ? fetch(j, sp - 3u) : (int32_t)(sp % 3u);
+  }
+  return (int32_t)q;
+}
+
 // Parallel phase, one call per op: v[s] = b_s; ops in the head and ops whose position another op also picked are
 // appended to coll (the first op of a position is appended by whoever finds it there; duplicates are fine).  The
 // counter keeps counting past coll_cap so that the overflow is visible.  A: atomics policy (device / host emulation).

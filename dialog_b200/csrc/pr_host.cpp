@@ -192,6 +192,15 @@ bool draw_triples_parallel(size_t n_points, uint32_t seed, int n_draws, int32_t*
   while (map_cap < 2 * distinct) map_cap <<= 1;
   std::vector<uint32_t> mk(map_cap, kDrawNoOp);
   std::vector<int32_t> mv(map_cap, 0);
+  // the kernel's two paths: independent groups resolved one entry per thread when that is exact, else the sequential replay
+  const std::vector<int32_t> before(triples, triples + n_ops);  // v as the parallel phase left it (the kernel prefetches it)
+  auto fetch = [&before](int, uint32_t idx) { return before[idx]; };
+  bool independent = true;
+  for (size_t i = 0; i < distinct; ++i) independent = independent && draw_independent_ok(coll.data(), (int)i, fetch);
+  if (independent) {
+    for (size_t i = 0; i < distinct; ++i) triples[coll[i]] = draw_resolve_independent(coll.data(), (int)i, fetch);
+    return true;
+  }
   draw_resolve(coll.data(), (int)distinct, triples, [triples](int, uint32_t idx) { return triples[idx]; }, mk.data(), mv.data(), map_cap - 1);
   return true;
 }
