@@ -236,8 +236,6 @@ struct plane_ransac_ctx {
   uint32_t rnd_seed = 0;
   size_t rnd_count = 0;
   DevBuf<unsigned long long> d_draw_table;
-  uint32_t draw_epoch = 0;   // epoch tag of the sampler's table slots (round_head_kernel); 0: table not initialised
-  size_t draw_epoch_slots = 0;
   DevBuf<uint32_t> d_draw_coll;  // kDrawCollCap entries + the counter
 
   // chunked upload queued by plane_ransac_set_cloud_async: copies run on copy_stream, chunk k is complete at ev[k];
@@ -1175,16 +1173,8 @@ int run_chain(plane_ransac_ctx* c, const pr_params* prm, PeelCursor& cur, float*
       if (pr::round_head_supported(K)) {
         // one single-CTA launch: accumulators cleared, triples drawn, (one GPU) sample points gathered and models formed
         Span sp(c, KC_MODELS, sharded ? 2 : 1);
-        if (c->draw_epoch == 0 || c->draw_epoch >= 65535u || c->draw_epoch_slots != slots) {
-          // epoch-tagged slots: the table is zeroed once (and when the 16-bit epoch wraps), never per round
-          PR_CUDA(cudaMemsetAsync(c->d_draw_table.p, 0, slots * sizeof(unsigned long long), c->stream));
-          c->draw_epoch = 0;
-          c->draw_epoch_slots = slots;
-        }
-        ++c->draw_epoch;
         pr::launch_round_head(c->d_rnd.p, K, rs, c->d_triples.p, rec, sharded ? nullptr : &src, c->d_sample_pts.p, c->d_hyps.p, c->d_good.p,
-                              c->d_counts.p, c->d_refit.p, c->d_scratch.p, scratch_bytes, c->d_chain_tickets.p, c->d_draw_table.p, slots,
-                              c->draw_epoch, c->stream);
+                              c->d_counts.p, c->d_refit.p, c->d_scratch.p, scratch_bytes, c->d_chain_tickets.p, c->stream);
         if (sharded) {
           pr::P2PTail tm;
           tm.kind = pr::P2PTail::kModels;
@@ -1194,7 +1184,6 @@ int run_chain(plane_ransac_ctx* c, const pr_params* prm, PeelCursor& cur, float*
         }
       } else {
         Span sp(c, KC_MODELS, 4);
-        c->draw_epoch = 0;  // this path fills the table with its own empty marker: the epoch-tagged user starts over
         pr::launch_round_prep(rs, c->d_draw_table.p, slots, coll_count, c->d_counts.p, K, c->d_refit.p, c->d_scratch.p, scratch_bytes,
                               c->d_chain_tickets.p, c->num_sms, c->stream);
         pr::launch_draw(c->d_rnd.p, K, rs, c->d_triples.p, c->d_draw_table.p, slots, c->d_draw_coll.p, coll_count, rec, c->stream);

@@ -141,22 +141,16 @@ __global__ void __launch_bounds__(kResolveThreads) draw_resolve_kernel(RoundStat
   draw_resolve(s_sorted, (int)n_c, v, fetch, s_keys, s_vals, (uint32_t)(kResolveMapSlots - 1));
 }
 
-// ---- the head of a round in ONE launch (K <= 4096): clear the round's accumulators, draw PCL's triples and, on one GPU,
-// gather the sample points and form the models.  One CTA; replaces round_prep + draw_scatter + draw_resolve +
-// gather_models (four launches and their gaps, ~40 us per round).
-// The sampler's hash table stays in global memory: shared-memory compare-and-swap (32- or 64-bit) measured ~25 cycles
-// per lane per SM on B200 (160 us for the 12288 inserts of a round), while L2 atomics pipeline.  Slots are tagged with a
-// 16-bit epoch (one per launched round) so the table is never cleared: slot = position << 33 | op << 16 | epoch; a
-// slot whose epoch is not the current one is free.  Every thread first loads the home slots of all its (<= 12) ops,
-// then issues their first compare-and-swaps back to back, and only then walks on with the few that met another key.
+// ---- the head of a round in ONE launch (K <= 4096): clear the round's accumulators, draw PCL's triples (the sampler's
+// hash table lives in shared memory: no global table to clear, shared-memory atomics), and on one GPU gather the sample
+// points and form the models.  One CTA; replaces round_prep + draw_scatter + draw_resolve + gather_models (four launches
+// and their gaps: ~40 us -> ~12 us per round, which is what the small configurations are made of).
 constexpr int kHeadThreads = 1024;
 constexpr int kHeadMaxDraws = 4096;
 constexpr int kHeadOpsPerThread = 3 * kHeadMaxDraws / kHeadThreads;  // 12
-constexpr size_t kHeadSmemBytes = (size_t)kDrawCollCap * (4 + 16 + 4) + (size_t)kResolveMapSlots * 8;
-
-__device__ __forceinline__ unsigned long long head_slot(uint32_t q, uint32_t s, uint32_t epoch) {
-  return ((unsigned long long)q << 33) | ((unsigned long long)s << 16) | (unsigned long long)epoch;
-}
+constexpr int kHeadTableSlots = 32768;  // 32-bit slots (the position alone): load factor <= 0.375
+constexpr size_t kHeadTableBytes = (size_t)kHeadTableSlots * 4, kHeadFlagBytes = kHeadTableSlots / 8;
+constexpr size_t kHeadSmemBytes = kHeadTableBytes + kHeadFlagBytes + (size_t)kDrawCollCap * (4 + 16 + 4);
 
 __global__ void __launch_bounds__(kHeadThreads) round_head_kernel(const uint32_t* __restrict__ rnd, int n_draws, RoundState* st,
                                                                   int32_t* v, RoundRecord* rec, const float* __restrict__ X,
@@ -164,14 +158,17 @@ __global__ void __launch_bounds__(kHeadThreads) round_head_kernel(const uint32_t
                                                                   int4* __restrict__ sample_pts, float4* __restrict__ hyps,
                                                                   int32_t* __restrict__ good, int32_t* __restrict__ counts,
                                                                   RefitOut* __restrict__ refit, unsigned long long* __restrict__ scratch,
-                                                                  size_t scratch_words, unsigned* __restrict__ tickets,
-                                                                  unsigned long long* table, uint32_t table_mask, uint32_t epoch) {
+                                                                  size_t scratch_words, unsigned* __restrict__ tickets) {
+  // Shared-memory 64-bit compare-and-swap runs at about one lane per 8 cycles per SM (measured: 170 us for the 12288
+  // inserts of a round), so the table holds the 32-bit position alone: the op that claims a slot remembers the slot,
+  // every later op with the same position lists itself and raises the slot's flag, and after a barrier the claimers
+  // whose flag is up list themselves too.
   extern __shared__ __align__(16) unsigned char s_raw[];
-  uint32_t* s_sorted = reinterpret_cast<uint32_t*>(s_raw);
-  int32_t* s_pre = reinterpret_cast<int32_t*>(s_raw + (size_t)kDrawCollCap * 4);
-  uint32_t* s_coll = reinterpret_cast<uint32_t*>(s_raw + (size_t)kDrawCollCap * 20);
-  uint32_t* m_keys = reinterpret_cast<uint32_t*>(s_raw + (size_t)kDrawCollCap * 24);
-  int32_t* m_vals = reinterpret_cast<int32_t*>(m_keys + kResolveMapSlots);
+  uint32_t* s_table = reinterpret_cast<uint32_t*>(s_raw);
+  uint32_t* s_flags = reinterpret_cast<uint32_t*>(s_raw + kHeadTableBytes);
+  uint32_t* s_sorted = reinterpret_cast<uint32_t*>(s_raw + kHeadTableBytes + kHeadFlagBytes);
+  int32_t* s_pre = reinterpret_cast<int32_t*>(s_raw + kHeadTableBytes + kHeadFlagBytes + (size_t)kDrawCollCap * 4);
+  uint32_t* s_coll = reinterpret_cast<uint32_t*>(s_raw + kHeadTableBytes + kHeadFlagBytes + (size_t)kDrawCollCap * 20);
   __shared__ uint32_t s_count;
   __shared__ int s_distinct;
   if (st->stop) return;
@@ -197,6 +194,8 @@ __global__ void __launch_bounds__(kHeadThreads) round_head_kernel(const uint32_t
     }
     return;
   }
+  for (int i = tid; i < kHeadTableSlots; i += kHeadThreads) s_table[i] = kDrawNoOp;
+  for (int i = tid; i < kHeadTableSlots / 32; i += kHeadThreads) s_flags[i] = 0u;
   if (tid == 0) {
     s_count = 0u;
     s_distinct = 0;
@@ -204,56 +203,43 @@ __global__ void __launch_bounds__(kHeadThreads) round_head_kernel(const uint32_t
   __syncthreads();
   const uint32_t n_points = (uint32_t)st->n_global;
   const int n_ops = 3 * n_draws;
-  uint32_t q[kHeadOpsPerThread], h[kHeadOpsPerThread];
-  unsigned long long seen[kHeadOpsPerThread];
-  // phase A: positions, v = b, the home slot of every op (independent loads, all in flight together)
+  uint32_t claimed[kHeadOpsPerThread];  // slot this thread's it-th op claimed, kDrawNoOp if none
 #pragma unroll
   for (int it = 0; it < kHeadOpsPerThread; ++it) {
+    claimed[it] = kDrawNoOp;
     const int s = tid + it * kHeadThreads;
-    q[it] = kDrawNoOp;
-    h[it] = 0;
-    seen[it] = 0ull;
-    if (s < n_ops) {
-      q[it] = draw_position((uint32_t)s, rnd[s], n_points);
-      v[s] = (int32_t)q[it];
-      if (q[it] >= 3u) {
-        h[it] = draw_hash(q[it]) & table_mask;
-        seen[it] = *reinterpret_cast<volatile unsigned long long*>(&table[h[it]]);
-      }
-    }
-  }
-  // phase B: claim (compare-and-swap against the stale value seen) or meet the same position; a few walk on
-#pragma unroll
-  for (int it = 0; it < kHeadOpsPerThread; ++it) {
-    const int s = tid + it * kHeadThreads;
-    if (q[it] == kDrawNoOp) continue;
-    uint32_t first_other = kDrawNoOp;
-    bool list_me = q[it] < 3u;
+    if (s >= n_ops) continue;
+    const uint32_t q = draw_position((uint32_t)s, rnd[s], n_points);
+    v[s] = (int32_t)q;
+    bool list_me = q < 3u;
     if (!list_me) {
-      const unsigned long long mine = head_slot(q[it], (uint32_t)s, epoch);
-      unsigned long long cur = seen[it];
-      uint32_t hh = h[it];
+      uint32_t h = draw_hash(q) & (uint32_t)(kHeadTableSlots - 1);
       for (;;) {
-        if ((uint32_t)(cur & 0xFFFFull) != epoch) {  // free (left over from an earlier round)
-          const unsigned long long old = atomicCAS(&table[hh], cur, mine);
-          if (old == cur) break;                      // claimed
-          cur = old;                                  // somebody was faster: look at what is there now
-          continue;
-        }
-        if ((uint32_t)(cur >> 33) == q[it]) {         // same position: both ops are listed
-          list_me = true;
-          first_other = (uint32_t)(cur >> 16) & 0x1FFFFu;
+        const uint32_t old = atomicCAS(&s_table[h], kDrawNoOp, q);
+        if (old == kDrawNoOp) {
+          claimed[it] = h;
           break;
         }
-        hh = (hh + 1) & table_mask;
-        cur = *reinterpret_cast<volatile unsigned long long*>(&table[hh]);
+        if (old == q) {
+          list_me = true;
+          atomicOr(&s_flags[h >> 5], 1u << (h & 31u));
+          break;
+        }
+        h = (h + 1) & (uint32_t)(kHeadTableSlots - 1);
       }
     }
     if (list_me) {
-      const uint32_t n_new = first_other != kDrawNoOp ? 2u : 1u;
-      const uint32_t at = atomicAdd(&s_count, n_new);
+      const uint32_t at = atomicAdd(&s_count, 1u);
       if (at < (uint32_t)kDrawCollCap) s_coll[at] = (uint32_t)s;
-      if (n_new == 2u && at + 1 < (uint32_t)kDrawCollCap) s_coll[at + 1] = first_other;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int it = 0; it < kHeadOpsPerThread; ++it) {
+    const uint32_t h = claimed[it];
+    if (h != kDrawNoOp && ((s_flags[h >> 5] >> (h & 31u)) & 1u)) {
+      const uint32_t at = atomicAdd(&s_count, 1u);
+      if (at < (uint32_t)kDrawCollCap) s_coll[at] = (uint32_t)(tid + it * kHeadThreads);
     }
   }
   __syncthreads();  // v[] (global, written by this block) and the collision list are complete
@@ -300,6 +286,9 @@ __global__ void __launch_bounds__(kHeadThreads) round_head_kernel(const uint32_t
         }
         return;
       }
+      // the sequential replay; its position map reuses the (now idle) table
+      uint32_t* m_keys = reinterpret_cast<uint32_t*>(s_table);
+      int32_t* m_vals = reinterpret_cast<int32_t*>(m_keys + kResolveMapSlots);
       for (int i = tid; i < kResolveMapSlots; i += kHeadThreads) m_keys[i] = kDrawNoOp;
       __syncthreads();
       if (tid == 0) draw_resolve(s_sorted, (int)n_c, v, fetch, m_keys, m_vals, (uint32_t)(kResolveMapSlots - 1));
@@ -309,17 +298,17 @@ __global__ void __launch_bounds__(kHeadThreads) round_head_kernel(const uint32_t
   if (X == nullptr) return;  // sharded: the sample-point exchange gathers and forms the models
   const long long n_local = st->n_local;
   for (int k = tid; k < n_draws; k += kHeadThreads) {
-    int4 qq[3];
+    int4 q[3];
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
       const long long j = (long long)v[3 * k + i];
-      qq[i] = make_int4(0, 0, 0, 0);
-      if (j >= 0 && j < n_local) qq[i] = make_int4(__float_as_int(X[j]), __float_as_int(Y[j]), __float_as_int(Z[j]), 0x3F800000);
-      sample_pts[3 * k + i] = qq[i];
+      q[i] = make_int4(0, 0, 0, 0);
+      if (j >= 0 && j < n_local) q[i] = make_int4(__float_as_int(X[j]), __float_as_int(Y[j]), __float_as_int(Z[j]), 0x3F800000);
+      sample_pts[3 * k + i] = q[i];
     }
-    float4 hm;
-    const bool okm = model_from_sample(qq[0], qq[1], qq[2], &hm);
-    hyps[k] = hm;
+    float4 h;
+    const bool okm = model_from_sample(q[0], q[1], q[2], &h);
+    hyps[k] = h;
     good[k] = okm ? 1 : 0;
   }
 }
@@ -328,12 +317,12 @@ bool round_head_supported(int n_draws) { return n_draws <= kHeadMaxDraws; }
 
 void launch_round_head(const uint32_t* rnd, int n_draws, RoundState* st, int32_t* triples, RoundRecord* rec, const CloudView* cloud,
                        int4* sample_pts, float4* hyps, int32_t* good, int32_t* counts, RefitOut* refit, void* scratch, size_t scratch_bytes,
-                       unsigned* tickets, unsigned long long* table, size_t table_slots, uint32_t epoch, cudaStream_t s) {
+                       unsigned* tickets, cudaStream_t s) {
   cudaFuncSetAttribute(round_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHeadSmemBytes);  // per device, cheap
   round_head_kernel<<<1, kHeadThreads, kHeadSmemBytes, s>>>(rnd, n_draws, st, triples, rec, cloud ? cloud->x : nullptr,
                                                             cloud ? cloud->y : nullptr, cloud ? cloud->z : nullptr, sample_pts, hyps, good,
                                                             counts, refit, reinterpret_cast<unsigned long long*>(scratch), scratch_bytes / 8,
-                                                            tickets, table, (uint32_t)(table_slots - 1), epoch);
+                                                            tickets);
 }
 
 // ---- computeModel's decision over the K counts (pr_chain_dev.cuh chain_replay_block) as its own kernel (one GPU) ------
