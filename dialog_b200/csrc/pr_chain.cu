@@ -147,10 +147,8 @@ __global__ void __launch_bounds__(kResolveThreads) draw_resolve_kernel(RoundStat
 // and their gaps: ~40 us -> ~12 us per round, which is what the small configurations are made of).
 constexpr int kHeadThreads = 1024;
 constexpr int kHeadMaxDraws = 4096;
-constexpr int kHeadOpsPerThread = 3 * kHeadMaxDraws / kHeadThreads;  // 12
-constexpr int kHeadTableSlots = 32768;  // 32-bit slots (the position alone): load factor <= 0.375
-constexpr size_t kHeadTableBytes = (size_t)kHeadTableSlots * 4, kHeadFlagBytes = kHeadTableSlots / 8;
-constexpr size_t kHeadSmemBytes = kHeadTableBytes + kHeadFlagBytes + (size_t)kDrawCollCap * (4 + 16 + 4);
+constexpr int kHeadTableSlots = 16384;  // >= 4/3 of 3 * kHeadMaxDraws
+constexpr size_t kHeadSmemBytes = (size_t)kHeadTableSlots * 8 + (size_t)kDrawCollCap * (4 + 16 + 4);
 
 __global__ void __launch_bounds__(kHeadThreads) round_head_kernel(const uint32_t* __restrict__ rnd, int n_draws, RoundState* st,
                                                                   int32_t* v, RoundRecord* rec, const float* __restrict__ X,
@@ -159,16 +157,11 @@ __global__ void __launch_bounds__(kHeadThreads) round_head_kernel(const uint32_t
                                                                   int32_t* __restrict__ good, int32_t* __restrict__ counts,
                                                                   RefitOut* __restrict__ refit, unsigned long long* __restrict__ scratch,
                                                                   size_t scratch_words, unsigned* __restrict__ tickets) {
-  // Shared-memory 64-bit compare-and-swap runs at about one lane per 8 cycles per SM (measured: 170 us for the 12288
-  // inserts of a round), so the table holds the 32-bit position alone: the op that claims a slot remembers the slot,
-  // every later op with the same position lists itself and raises the slot's flag, and after a barrier the claimers
-  // whose flag is up list themselves too.
   extern __shared__ __align__(16) unsigned char s_raw[];
-  uint32_t* s_table = reinterpret_cast<uint32_t*>(s_raw);
-  uint32_t* s_flags = reinterpret_cast<uint32_t*>(s_raw + kHeadTableBytes);
-  uint32_t* s_sorted = reinterpret_cast<uint32_t*>(s_raw + kHeadTableBytes + kHeadFlagBytes);
-  int32_t* s_pre = reinterpret_cast<int32_t*>(s_raw + kHeadTableBytes + kHeadFlagBytes + (size_t)kDrawCollCap * 4);
-  uint32_t* s_coll = reinterpret_cast<uint32_t*>(s_raw + kHeadTableBytes + kHeadFlagBytes + (size_t)kDrawCollCap * 20);
+  unsigned long long* s_table = reinterpret_cast<unsigned long long*>(s_raw);
+  uint32_t* s_sorted = reinterpret_cast<uint32_t*>(s_raw + (size_t)kHeadTableSlots * 8);
+  int32_t* s_pre = reinterpret_cast<int32_t*>(s_raw + (size_t)kHeadTableSlots * 8 + (size_t)kDrawCollCap * 4);
+  uint32_t* s_coll = reinterpret_cast<uint32_t*>(s_raw + (size_t)kHeadTableSlots * 8 + (size_t)kDrawCollCap * 20);
   __shared__ uint32_t s_count;
   __shared__ int s_distinct;
   if (st->stop) return;
@@ -194,8 +187,7 @@ __global__ void __launch_bounds__(kHeadThreads) round_head_kernel(const uint32_t
     }
     return;
   }
-  for (int i = tid; i < kHeadTableSlots; i += kHeadThreads) s_table[i] = kDrawNoOp;
-  for (int i = tid; i < kHeadTableSlots / 32; i += kHeadThreads) s_flags[i] = 0u;
+  for (int i = tid; i < kHeadTableSlots; i += kHeadThreads) s_table[i] = kDrawEmptySlot;
   if (tid == 0) {
     s_count = 0u;
     s_distinct = 0;
@@ -203,45 +195,8 @@ __global__ void __launch_bounds__(kHeadThreads) round_head_kernel(const uint32_t
   __syncthreads();
   const uint32_t n_points = (uint32_t)st->n_global;
   const int n_ops = 3 * n_draws;
-  uint32_t claimed[kHeadOpsPerThread];  // slot this thread's it-th op claimed, kDrawNoOp if none
-#pragma unroll
-  for (int it = 0; it < kHeadOpsPerThread; ++it) {
-    claimed[it] = kDrawNoOp;
-    const int s = tid + it * kHeadThreads;
-    if (s >= n_ops) continue;
-    const uint32_t q = draw_position((uint32_t)s, rnd[s], n_points);
-    v[s] = (int32_t)q;
-    bool list_me = q < 3u;
-    if (!list_me) {
-      uint32_t h = draw_hash(q) & (uint32_t)(kHeadTableSlots - 1);
-      for (;;) {
-        const uint32_t old = atomicCAS(&s_table[h], kDrawNoOp, q);
-        if (old == kDrawNoOp) {
-          claimed[it] = h;
-          break;
-        }
-        if (old == q) {
-          list_me = true;
-          atomicOr(&s_flags[h >> 5], 1u << (h & 31u));
-          break;
-        }
-        h = (h + 1) & (uint32_t)(kHeadTableSlots - 1);
-      }
-    }
-    if (list_me) {
-      const uint32_t at = atomicAdd(&s_count, 1u);
-      if (at < (uint32_t)kDrawCollCap) s_coll[at] = (uint32_t)s;
-    }
-  }
-  __syncthreads();
-#pragma unroll
-  for (int it = 0; it < kHeadOpsPerThread; ++it) {
-    const uint32_t h = claimed[it];
-    if (h != kDrawNoOp && ((s_flags[h >> 5] >> (h & 31u)) & 1u)) {
-      const uint32_t at = atomicAdd(&s_count, 1u);
-      if (at < (uint32_t)kDrawCollCap) s_coll[at] = (uint32_t)(tid + it * kHeadThreads);
-    }
-  }
+  for (int s = tid; s < n_ops; s += kHeadThreads)
+    draw_scatter<DevAtomics>((uint32_t)s, rnd[s], n_points, v, s_table, (uint32_t)(kHeadTableSlots - 1), s_coll, &s_count, (uint32_t)kDrawCollCap);
   __syncthreads();  // v[] (global, written by this block) and the collision list are complete
   const uint32_t n_c = s_count;
   if (n_c > (uint32_t)kDrawCollCap) {  // crowded round: the sequential host sampler takes it
