@@ -1170,19 +1170,7 @@ int run_chain(plane_ransac_ctx* c, const pr_params* prm, PeelCursor& cur, float*
       dst_of[r] = dst;
       pr::RoundRecord* rec = c->h_recs.p + r;  // mapped host memory (unified addressing)
       uint32_t* coll_count = c->d_draw_coll.p + pr::kDrawCollCap;
-      if (pr::round_head_supported(K)) {
-        // one single-CTA launch: accumulators cleared, triples drawn, (one GPU) sample points gathered and models formed
-        Span sp(c, KC_MODELS, sharded ? 2 : 1);
-        pr::launch_round_head(c->d_rnd.p, K, rs, c->d_triples.p, rec, sharded ? nullptr : &src, c->d_sample_pts.p, c->d_hyps.p, c->d_good.p,
-                              c->d_counts.p, c->d_refit.p, c->d_scratch.p, scratch_bytes, c->d_chain_tickets.p, c->stream);
-        if (sharded) {
-          pr::P2PTail tm;
-          tm.kind = pr::P2PTail::kModels;
-          tm.hyps_out = c->d_hyps.p;
-          tm.good_out = c->d_good.p;
-          PR_TRY(exchange_samples(c, src, 0, 0, c->d_triples.p, 3 * K, c->d_sample_pts.p, rs, &tm));
-        }
-      } else {
+      {
         Span sp(c, KC_MODELS, 4);
         pr::launch_round_prep(rs, c->d_draw_table.p, slots, coll_count, c->d_counts.p, K, c->d_refit.p, c->d_scratch.p, scratch_bytes,
                               c->d_chain_tickets.p, c->num_sms, c->stream);

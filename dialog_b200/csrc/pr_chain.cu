@@ -141,145 +141,6 @@ __global__ void __launch_bounds__(kResolveThreads) draw_resolve_kernel(RoundStat
   draw_resolve(s_sorted, (int)n_c, v, fetch, s_keys, s_vals, (uint32_t)(kResolveMapSlots - 1));
 }
 
-// ---- the head of a round in ONE launch (K <= 4096): clear the round's accumulators, draw PCL's triples (the sampler's
-// hash table lives in shared memory: no global table to clear, shared-memory atomics), and on one GPU gather the sample
-// points and form the models.  One CTA; replaces round_prep + draw_scatter + draw_resolve + gather_models (four launches
-// and their gaps: ~40 us -> ~12 us per round, which is what the small configurations are made of).
-constexpr int kHeadThreads = 1024;
-constexpr int kHeadMaxDraws = 4096;
-constexpr int kHeadTableSlots = 16384;  // >= 4/3 of 3 * kHeadMaxDraws
-constexpr size_t kHeadSmemBytes = (size_t)kHeadTableSlots * 8 + (size_t)kDrawCollCap * (4 + 16 + 4);
-
-__global__ void __launch_bounds__(kHeadThreads) round_head_kernel(const uint32_t* __restrict__ rnd, int n_draws, RoundState* st,
-                                                                  int32_t* v, RoundRecord* rec, const float* __restrict__ X,
-                                                                  const float* __restrict__ Y, const float* __restrict__ Z,
-                                                                  int4* __restrict__ sample_pts, float4* __restrict__ hyps,
-                                                                  int32_t* __restrict__ good, int32_t* __restrict__ counts,
-                                                                  RefitOut* __restrict__ refit, unsigned long long* __restrict__ scratch,
-                                                                  size_t scratch_words, unsigned* __restrict__ tickets) {
-  extern __shared__ __align__(16) unsigned char s_raw[];
-  unsigned long long* s_table = reinterpret_cast<unsigned long long*>(s_raw);
-  uint32_t* s_sorted = reinterpret_cast<uint32_t*>(s_raw + (size_t)kHeadTableSlots * 8);
-  int32_t* s_pre = reinterpret_cast<int32_t*>(s_raw + (size_t)kHeadTableSlots * 8 + (size_t)kDrawCollCap * 4);
-  uint32_t* s_coll = reinterpret_cast<uint32_t*>(s_raw + (size_t)kHeadTableSlots * 8 + (size_t)kDrawCollCap * 20);
-  __shared__ uint32_t s_count;
-  __shared__ int s_distinct;
-  if (st->stop) return;
-  const int tid = threadIdx.x;
-  // everything this round accumulates into
-  for (size_t i = tid; i < scratch_words; i += kHeadThreads) scratch[i] = 0ull;
-  for (int i = tid; i < n_draws; i += kHeadThreads) counts[i] = 0;
-  if (tid < (int)(sizeof(RefitOut) / sizeof(long long))) reinterpret_cast<long long*>(refit)[tid] = 0;
-  if (tid == 0) tickets[0] = 0u;
-  if (st->n_global < 3) {  // getSamples: "Can not select 0 unique points out of N": segment() returns no model
-    if (tid == 0) {
-      st->stop = 1;
-      st->best = -1;
-      rec->stop = 1;
-      rec->n_cloud = st->n_global;
-      rec->n_local = st->n_local;
-      rec->n_rem_local = st->n_local;
-      rec->n_rem_global = st->n_global;
-      rec->first_after = st->first;
-      rec->inl_off = st->inl_off;
-      __threadfence_system();
-      rec->ran = 1;
-    }
-    return;
-  }
-  for (int i = tid; i < kHeadTableSlots; i += kHeadThreads) s_table[i] = kDrawEmptySlot;
-  if (tid == 0) {
-    s_count = 0u;
-    s_distinct = 0;
-  }
-  __syncthreads();
-  const uint32_t n_points = (uint32_t)st->n_global;
-  const int n_ops = 3 * n_draws;
-  for (int s = tid; s < n_ops; s += kHeadThreads)
-    draw_scatter<DevAtomics>((uint32_t)s, rnd[s], n_points, v, s_table, (uint32_t)(kHeadTableSlots - 1), s_coll, &s_count, (uint32_t)kDrawCollCap);
-  __syncthreads();  // v[] (global, written by this block) and the collision list are complete
-  const uint32_t n_c = s_count;
-  if (n_c > (uint32_t)kDrawCollCap) {  // crowded round: the sequential host sampler takes it
-    if (tid == 0) {
-      st->stop = 2;
-      rec->stop = 2;
-      __threadfence_system();
-      rec->ran = 1;
-    }
-    return;
-  }
-  if (n_c > 0) {
-    for (uint32_t i = tid; i < n_c; i += kHeadThreads) {
-      const uint32_t mine = s_coll[i];
-      uint32_t rank = 0;
-      for (uint32_t j = 0; j < n_c; ++j) {
-        const uint32_t o = s_coll[j];
-        rank += (o < mine || (o == mine && j < i)) ? 1u : 0u;
-      }
-      s_sorted[rank] = mine;
-    }
-    __syncthreads();
-    for (uint32_t i = tid; i < n_c; i += kHeadThreads) {
-      const uint32_t s = s_sorted[i];
-      if (i == 0 || s != s_sorted[i - 1]) atomicAdd(&s_distinct, 1);
-#pragma unroll
-      for (uint32_t k = 0; k < 4; ++k) s_pre[4 * i + k] = s >= k ? v[s - k] : 0;
-    }
-    __syncthreads();
-    SmemFetch fetch{s_sorted, s_pre};
-    int ok = 1;
-    for (uint32_t i = tid; i < n_c; i += kHeadThreads) ok = ok && draw_independent_ok(s_sorted, (int)i, fetch);
-    if (__syncthreads_and(ok)) {
-      for (uint32_t i = tid; i < n_c; i += kHeadThreads) v[s_sorted[i]] = draw_resolve_independent(s_sorted, (int)i, fetch);
-    } else {
-      if (s_distinct > kDrawMaxCollisions) {
-        if (tid == 0) {
-          st->stop = 2;
-          rec->stop = 2;
-          __threadfence_system();
-          rec->ran = 1;
-        }
-        return;
-      }
-      // the sequential replay; its position map reuses the (now idle) table
-      uint32_t* m_keys = reinterpret_cast<uint32_t*>(s_table);
-      int32_t* m_vals = reinterpret_cast<int32_t*>(m_keys + kResolveMapSlots);
-      for (int i = tid; i < kResolveMapSlots; i += kHeadThreads) m_keys[i] = kDrawNoOp;
-      __syncthreads();
-      if (tid == 0) draw_resolve(s_sorted, (int)n_c, v, fetch, m_keys, m_vals, (uint32_t)(kResolveMapSlots - 1));
-    }
-    __syncthreads();  // the resolved v[] is visible to the whole block
-  }
-  if (X == nullptr) return;  // sharded: the sample-point exchange gathers and forms the models
-  const long long n_local = st->n_local;
-  for (int k = tid; k < n_draws; k += kHeadThreads) {
-    int4 q[3];
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-      const long long j = (long long)v[3 * k + i];
-      q[i] = make_int4(0, 0, 0, 0);
-      if (j >= 0 && j < n_local) q[i] = make_int4(__float_as_int(X[j]), __float_as_int(Y[j]), __float_as_int(Z[j]), 0x3F800000);
-      sample_pts[3 * k + i] = q[i];
-    }
-    float4 h;
-    const bool okm = model_from_sample(q[0], q[1], q[2], &h);
-    hyps[k] = h;
-    good[k] = okm ? 1 : 0;
-  }
-}
-
-bool round_head_supported(int n_draws) { return n_draws <= kHeadMaxDraws; }
-
-void launch_round_head(const uint32_t* rnd, int n_draws, RoundState* st, int32_t* triples, RoundRecord* rec, const CloudView* cloud,
-                       int4* sample_pts, float4* hyps, int32_t* good, int32_t* counts, RefitOut* refit, void* scratch, size_t scratch_bytes,
-                       unsigned* tickets, cudaStream_t s) {
-  cudaFuncSetAttribute(round_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHeadSmemBytes);  // per device, cheap
-  round_head_kernel<<<1, kHeadThreads, kHeadSmemBytes, s>>>(rnd, n_draws, st, triples, rec, cloud ? cloud->x : nullptr,
-                                                            cloud ? cloud->y : nullptr, cloud ? cloud->z : nullptr, sample_pts, hyps, good,
-                                                            counts, refit, reinterpret_cast<unsigned long long*>(scratch), scratch_bytes / 8,
-                                                            tickets);
-}
-
 // ---- computeModel's decision over the K counts (pr_chain_dev.cuh chain_replay_block) as its own kernel (one GPU) ------
 __global__ void __launch_bounds__(kChainBlock) replay_kernel(const int32_t* __restrict__ counts, const int32_t* __restrict__ good, int K,
                                                              RoundState* st, RoundRecord* rec) {

@@ -257,12 +257,6 @@ void launch_round_prep(const RoundState* st, unsigned long long* table, size_t t
                        RefitOut* refit, void* scratch, size_t scratch_bytes, unsigned* tickets, int num_sms, cudaStream_t s);
 void launch_draw(const uint32_t* rnd, int n_draws, RoundState* st, int32_t* triples, unsigned long long* table, size_t table_slots,
                  uint32_t* coll, uint32_t* coll_count, RoundRecord* rec, cudaStream_t s);
-// The head of a round in one single-CTA launch (n_draws <= 4096): clears the round's accumulators, draws the triples
-// (hash table in shared memory) and, when cloud != nullptr (one GPU), gathers the sample points and forms the models.
-bool round_head_supported(int n_draws);
-void launch_round_head(const uint32_t* rnd, int n_draws, RoundState* st, int32_t* triples, RoundRecord* rec, const CloudView* cloud,
-                       int4* sample_pts, float4* hyps, int32_t* good, int32_t* counts, RefitOut* refit, void* scratch, size_t scratch_bytes,
-                       unsigned* tickets, cudaStream_t s);
 // computeModel's decision over K counts (score-all mode): st->best / best_count, or st->stop = 2 when a bad sample means
 // PCL would draw beyond the K scored hypotheses.
 void launch_replay(const int32_t* counts, const int32_t* good, int K, RoundState* st, RoundRecord* rec, cudaStream_t s);
