@@ -229,7 +229,8 @@ def _same_extraction(a, b):
 
 @pytest.mark.parametrize("scene,n,max_it,min_plane,max_planes,opt,order", [
     ("s2", 150_000, 255, 5000, 8, True, 1), ("s2", 150_000, 255, 5000, 2, True, 0), ("s3", 250_000, 511, 500, 20, True, 1),
-    ("s3", 90_000, 99, 500, 30, False, 1), ("s2", 40_000, 31, 10**9, 4, True, 1), ("s3", 1_200_000, 1023, 500, 12, True, 1)])
+    ("s3", 90_000, 99, 500, 30, False, 1), ("s2", 40_000, 31, 10**9, 4, True, 1), ("s3", 1_200_000, 1023, 500, 12, True, 1),
+    ("s3", 1_500_000, 8191, 500, 5, True, 1)])
 def test_device_round_loop_equals_host_loop(O, pr, scene2, scene3, scene, n, max_it, min_plane, max_planes, opt, order):
     """Score-all mode: whole rounds queued on the device (PCL's triples, computeModel's decision, the closed-form refit
     and the stop rule as kernels on a device-resident state) against the same rounds driven by the host."""
