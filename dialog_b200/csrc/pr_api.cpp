@@ -236,6 +236,8 @@ struct plane_ransac_ctx {
   uint32_t rnd_seed = 0;
   size_t rnd_count = 0;
   DevBuf<unsigned long long> d_draw_table;
+  uint32_t draw_epoch = 0;      // epoch tag of the sampler's table slots; 0: table not initialised
+  size_t draw_epoch_slots = 0;
   DevBuf<uint32_t> d_draw_coll;  // kDrawCollCap entries + the counter
 
   // chunked upload queued by plane_ransac_set_cloud_async: copies run on copy_stream, chunk k is complete at ev[k];
@@ -1171,10 +1173,17 @@ int run_chain(plane_ransac_ctx* c, const pr_params* prm, PeelCursor& cur, float*
       pr::RoundRecord* rec = c->h_recs.p + r;  // mapped host memory (unified addressing)
       uint32_t* coll_count = c->d_draw_coll.p + pr::kDrawCollCap;
       {
-        Span sp(c, KC_MODELS, 4);
-        pr::launch_round_prep(rs, c->d_draw_table.p, slots, coll_count, c->d_counts.p, K, c->d_refit.p, c->d_scratch.p, scratch_bytes,
-                              c->d_chain_tickets.p, c->num_sms, c->stream);
-        pr::launch_draw(c->d_rnd.p, K, rs, c->d_triples.p, c->d_draw_table.p, slots, c->d_draw_coll.p, coll_count, rec, c->stream);
+        Span sp(c, KC_MODELS, 3);
+        if (c->draw_epoch == 0 || c->draw_epoch >= 65535u || c->draw_epoch_slots != slots) {
+          // epoch-tagged slots: the sampler's table is zeroed once (and when the 16-bit epoch wraps), never per round
+          PR_CUDA(cudaMemsetAsync(c->d_draw_table.p, 0, slots * sizeof(unsigned long long), c->stream));
+          PR_CUDA(cudaMemsetAsync(coll_count, 0, sizeof(uint32_t), c->stream));
+          c->draw_epoch = 0;
+          c->draw_epoch_slots = slots;
+        }
+        ++c->draw_epoch;
+        pr::launch_draw(c->d_rnd.p, K, rs, c->d_triples.p, c->d_draw_table.p, slots, c->draw_epoch, c->d_draw_coll.p, coll_count, rec,
+                        c->d_counts.p, c->d_refit.p, c->d_scratch.p, scratch_bytes, c->d_chain_tickets.p, c->stream);
         if (sharded) {  // (chain_eligible: sharded implies peer-memory exchanges, which run the consuming step themselves)
           pr::P2PTail tm;
           tm.kind = pr::P2PTail::kModels;

@@ -23,35 +23,31 @@ struct DevAtomics {
   static __device__ __forceinline__ unsigned long long cas(unsigned long long* p, unsigned long long expect, unsigned long long v) {
     return atomicCAS(p, expect, v);
   }
+  static __device__ __forceinline__ unsigned long long load(const unsigned long long* p) {
+    return *reinterpret_cast<const volatile unsigned long long*>(p);
+  }
   static __device__ __forceinline__ uint32_t add(uint32_t* p, uint32_t v) { return atomicAdd(p, v); }
 };
 }  // namespace
 
-// ---- sampler, parallel phase: one thread per op ------------------------------------------------------------------------
+// ---- sampler, parallel phase: one thread per op; the same launch clears everything the round accumulates into (none of
+// which it reads itself) ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) draw_scatter_kernel(const uint32_t* __restrict__ rnd, int n_ops, const RoundState* __restrict__ st,
                                                            int32_t* __restrict__ v, unsigned long long* table, uint32_t table_mask,
-                                                           uint32_t* coll, uint32_t* coll_count) {
-  if (st->stop || st->n_global < 3) return;
-  const uint32_t n_points = (uint32_t)st->n_global;
-  for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n_ops; s += gridDim.x * blockDim.x)
-    draw_scatter<DevAtomics>((uint32_t)s, rnd[s], n_points, v, table, table_mask, coll, coll_count, (uint32_t)kDrawCollCap);
-}
-
-// ---- round preparation: every buffer the round's kernels accumulate into, cleared by one launch ------------------------
-__global__ void __launch_bounds__(256) round_prep_kernel(const RoundState* __restrict__ st, unsigned long long* __restrict__ table, size_t table_slots,
-                                                         uint32_t* __restrict__ coll_count, int32_t* __restrict__ counts, int K,
-                                                         RefitOut* __restrict__ refit, unsigned long long* __restrict__ scratch,
-                                                         size_t scratch_words, unsigned* __restrict__ tickets) {
+                                                           uint32_t epoch, uint32_t* coll, uint32_t* coll_count,
+                                                           int32_t* __restrict__ counts, int K, RefitOut* __restrict__ refit,
+                                                           unsigned long long* __restrict__ scratch, size_t scratch_words,
+                                                           unsigned* __restrict__ tickets) {
   if (st->stop) return;
   const size_t stride = (size_t)gridDim.x * blockDim.x, i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  for (size_t i = i0; i < table_slots; i += stride) table[i] = kDrawEmptySlot;
   for (size_t i = i0; i < scratch_words; i += stride) scratch[i] = 0ull;
   for (size_t i = i0; i < (size_t)K; i += stride) counts[i] = 0;
   if (i0 < sizeof(RefitOut) / sizeof(long long)) reinterpret_cast<long long*>(refit)[i0] = 0;
-  if (i0 == 0) {
-    *coll_count = 0u;
-    tickets[0] = 0u;
-  }
+  if (i0 == 0) tickets[0] = 0u;
+  if (st->n_global < 3) return;
+  const uint32_t n_points = (uint32_t)st->n_global;
+  for (int s = (int)i0; s < n_ops; s += (int)stride)
+    draw_scatter<DevAtomics>((uint32_t)s, rnd[s], n_points, v, table, table_mask, epoch, coll, coll_count, (uint32_t)kDrawCollCap);
 }
 
 // ---- sampler, sequential phase: the colliding ops, sorted by op index, replayed by one thread ------------------------------
@@ -68,7 +64,7 @@ struct SmemFetch {
 };
 
 __global__ void __launch_bounds__(kResolveThreads) draw_resolve_kernel(RoundState* st, int32_t* v, const uint32_t* __restrict__ coll,
-                                                                       const uint32_t* __restrict__ coll_count, RoundRecord* rec) {
+                                                                       uint32_t* coll_count, RoundRecord* rec) {
   extern __shared__ __align__(16) unsigned char s_raw[];
   uint32_t* s_sorted = reinterpret_cast<uint32_t*>(s_raw);
   int32_t* s_pre = reinterpret_cast<int32_t*>(s_raw + (size_t)kDrawCollCap * 4);
@@ -93,6 +89,8 @@ __global__ void __launch_bounds__(kResolveThreads) draw_resolve_kernel(RoundStat
     return;
   }
   const uint32_t n_c = *coll_count;
+  __syncthreads();
+  if (threadIdx.x == 0) *coll_count = 0u;  // ready for the next round's scatter (the host zeroes it before the first)
   if (n_c > (uint32_t)kDrawCollCap) {  // crowded round: the sequential host sampler takes it
     if (threadIdx.x == 0) {
       st->stop = 2;
@@ -165,18 +163,14 @@ __global__ void advance_kernel(RoundState* st, const long long* __restrict__ tot
   chain_advance(st, totals, n_ranks, rank, min_plane, rec);
 }
 
-void launch_round_prep(const RoundState* st, unsigned long long* table, size_t table_slots, uint32_t* coll_count, int32_t* counts, int K,
-                       RefitOut* refit, void* scratch, size_t scratch_bytes, unsigned* tickets, int num_sms, cudaStream_t s) {
-  round_prep_kernel<<<num_sms * 2, 256, 0, s>>>(st, table, table_slots, coll_count, counts, K, refit,
-                                               reinterpret_cast<unsigned long long*>(scratch), scratch_bytes / 8, tickets);
-}
-
 void launch_draw(const uint32_t* rnd, int n_draws, RoundState* st, int32_t* triples, unsigned long long* table, size_t table_slots,
-                 uint32_t* coll, uint32_t* coll_count, RoundRecord* rec, cudaStream_t s) {
+                 uint32_t epoch, uint32_t* coll, uint32_t* coll_count, RoundRecord* rec, int32_t* counts, RefitOut* refit, void* scratch,
+                 size_t scratch_bytes, unsigned* tickets, cudaStream_t s) {
   const int n_ops = 3 * n_draws;
   int blocks = (n_ops + 255) / 256;
   if (blocks > 148 * 4) blocks = 148 * 4;
-  draw_scatter_kernel<<<blocks, 256, 0, s>>>(rnd, n_ops, st, triples, table, (uint32_t)(table_slots - 1), coll, coll_count);
+  draw_scatter_kernel<<<blocks, 256, 0, s>>>(rnd, n_ops, st, triples, table, (uint32_t)(table_slots - 1), epoch, coll, coll_count, counts,
+                                             n_draws, refit, reinterpret_cast<unsigned long long*>(scratch), scratch_bytes / 8, tickets);
   cudaFuncSetAttribute(draw_resolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kResolveSmemBytes);  // per device: cheap, unconditional
   draw_resolve_kernel<<<1, kResolveThreads, kResolveSmemBytes, s>>>(st, triples, coll, coll_count, rec);
 }

@@ -21,7 +21,6 @@
 namespace pr {
 
 constexpr uint32_t kDrawNoOp = 0xFFFFFFFFu;
-constexpr uint64_t kDrawEmptySlot = ~0ull;
 // Collected ops the sequential replay accepts (more: the round falls back to the host sampler).
 constexpr int kDrawMaxCollisions = 2048;
 // Capacity of the collected list (an op can be listed more than once).
@@ -122,25 +121,37 @@ PR_HD int32_t draw_resolve_independent(const uint32_t* ops_sorted, int i, Fetch 
 // Parallel phase, one call per op: v[s] = b_s; ops in the head and ops whose position another op also picked are
 // appended to coll (the first op of a position is appended by whoever finds it there; duplicates are fine).  The
 // counter keeps counting past coll_cap so that the overflow is visible.  A: atomics policy (device / host emulation).
+// The table is never cleared between rounds: a slot is position << 33 | op << 16 | epoch and counts as free unless its
+// epoch is the current one (epochs run 1 .. 65535; the owner zeroes the table once and whenever the epoch wraps).
+PR_HD unsigned long long draw_slot(uint32_t q, uint32_t s, uint32_t epoch) {
+  return ((unsigned long long)q << 33) | ((unsigned long long)s << 16) | (unsigned long long)epoch;
+}
+
 template <class A>
 PR_HD void draw_scatter(uint32_t s, uint32_t rnd, uint32_t n_points, int32_t* v, unsigned long long* table, uint32_t table_mask,
-                        uint32_t* coll, uint32_t* coll_count, uint32_t coll_cap) {
+                        uint32_t epoch, uint32_t* coll, uint32_t* coll_count, uint32_t coll_cap) {
   const uint32_t q = draw_position(s, rnd, n_points);
   v[s] = (int32_t)q;
   uint32_t first_other = kDrawNoOp;
   bool collide = q < 3u;
   if (!collide) {
-    const unsigned long long mine = ((unsigned long long)q << 32) | s;
+    const unsigned long long mine = draw_slot(q, s, epoch);
     uint32_t h = draw_hash(q) & table_mask;
+    unsigned long long cur = A::load(&table[h]);
     for (;;) {
-      const unsigned long long old = A::cas(&table[h], kDrawEmptySlot, mine);
-      if (old == kDrawEmptySlot) break;
-      if ((uint32_t)(old >> 32) == q) {
+      if ((uint32_t)(cur & 0xFFFFull) != epoch) {  // free: left over from an earlier round
+        const unsigned long long old = A::cas(&table[h], cur, mine);
+        if (old == cur) break;                      // claimed
+        cur = old;                                  // somebody was faster: look at what is there now
+        continue;
+      }
+      if ((uint32_t)(cur >> 33) == q) {
         collide = true;
-        first_other = (uint32_t)old;
+        first_other = (uint32_t)(cur >> 16) & 0x1FFFFu;
         break;
       }
       h = (h + 1) & table_mask;
+      cur = A::load(&table[h]);
     }
   }
   if (collide) {

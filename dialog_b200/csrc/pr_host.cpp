@@ -161,6 +161,7 @@ struct HostAtomics {
     if (old == expect) *p = v;
     return old;
   }
+  static unsigned long long load(const unsigned long long* p) { return *p; }
   static uint32_t add(uint32_t* p, uint32_t v) {
     const uint32_t old = *p;
     *p += v;
@@ -176,13 +177,13 @@ bool draw_triples_parallel(size_t n_points, uint32_t seed, int n_draws, int32_t*
   fill_rnd_stream(seed, n_ops, rnd.data());
   size_t cap = 1024;
   while (cap < 4 * n_ops) cap <<= 1;
-  std::vector<unsigned long long> table(cap, kDrawEmptySlot);
+  std::vector<unsigned long long> table(cap, 0ull);  // epoch 0 = never used
   std::vector<uint32_t> coll(kDrawCollCap);
   uint32_t n_coll = 0;
   // the device runs the ops in any order: emulate the reverse one, so that the op that owns a table slot is never
   // the earliest op of its position
   for (size_t k = n_ops; k-- > 0;)
-    draw_scatter<HostAtomics>((uint32_t)k, rnd[k], (uint32_t)n_points, triples, table.data(), (uint32_t)(cap - 1), coll.data(), &n_coll,
+    draw_scatter<HostAtomics>((uint32_t)k, rnd[k], (uint32_t)n_points, triples, table.data(), (uint32_t)(cap - 1), 1u, coll.data(), &n_coll,
                               (uint32_t)coll.size());
   if (n_coll > (uint32_t)coll.size()) return false;
   std::sort(coll.begin(), coll.begin() + n_coll);

@@ -248,15 +248,16 @@ void launch_p2p_samples(const P2PView& v, CloudView cloud, long long first, size
 
 // ---- the peel loop without the host (pr_chain.cu): per-round kernels driven by a RoundState in HBM ------------------
 // PCL's index triples for a cloud of st->n_global points: rnd = the first 3 * n_draws values of mt19937(seed) >> 1,
-// table = draw_table_slots(n_draws) uint64 of scratch, coll = kDrawCollCap uint32 + coll_count.  Sets st->stop = 2 when
-// the round has to go back to the sequential host sampler, 1 when the cloud has fewer than 3 points.
+// table = draw_table_slots(n_draws) uint64 slots tagged with a 16-bit epoch (never cleared between rounds: pass a new
+// epoch in 1 .. 65535 per call and zero the table once / when the epoch wraps), coll = kDrawCollCap uint32 + coll_count
+// (zeroed by the caller before the first round, by the resolve kernel afterwards).  The scatter launch also clears what
+// the round accumulates into: the K counts, the refit moments, the compaction descriptors (scratch) and the
+// blocks-done ticket.  Sets st->stop = 2 when the round has to go back to the sequential host sampler, 1 when the cloud
+// has fewer than 3 points.
 size_t draw_table_slots(int n_draws);
-// One launch clears everything a round accumulates into: the sampler's table and collision count, the K counts, the
-// refit moments, the compaction descriptors (scratch) and the blocks-done ticket.
-void launch_round_prep(const RoundState* st, unsigned long long* table, size_t table_slots, uint32_t* coll_count, int32_t* counts, int K,
-                       RefitOut* refit, void* scratch, size_t scratch_bytes, unsigned* tickets, int num_sms, cudaStream_t s);
 void launch_draw(const uint32_t* rnd, int n_draws, RoundState* st, int32_t* triples, unsigned long long* table, size_t table_slots,
-                 uint32_t* coll, uint32_t* coll_count, RoundRecord* rec, cudaStream_t s);
+                 uint32_t epoch, uint32_t* coll, uint32_t* coll_count, RoundRecord* rec, int32_t* counts, RefitOut* refit, void* scratch,
+                 size_t scratch_bytes, unsigned* tickets, cudaStream_t s);
 // computeModel's decision over K counts (score-all mode): st->best / best_count, or st->stop = 2 when a bad sample means
 // PCL would draw beyond the K scored hypotheses.
 void launch_replay(const int32_t* counts, const int32_t* good, int K, RoundState* st, RoundRecord* rec, cudaStream_t s);
