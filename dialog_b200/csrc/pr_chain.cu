@@ -5,8 +5,8 @@
 //   draw_scatter / draw_resolve   PCL's index triples for the round's cloud size (pr_draw.h)
 //   gather + models + score       K1, K2 (pr_kernels.cu), sized from RoundState on the device
 //   replay_kernel                 RandomSampleConsensus::computeModel's decision over the K counts
-//   refit + finish_kernel         K3 moments -> pcl::eigen33 closed form (pr_math.h) -> refined plane
-//   compact + advance_kernel      K5 peel, minimum-plane-size rule, sizes of the next round
+//   refit (+ chain_finish)        K3 moments; its last block solves pcl::eigen33's closed form (pr_math.h) -> refined plane
+//   compact (+ chain_advance)     K5 peel; its last tile applies the minimum-plane-size rule and sets the next round's sizes
 // so the host queues whole rounds ahead and only reads the per-round records (pr_api.cpp run_chain).
 #include "pr_kernels.h"
 
@@ -146,8 +146,9 @@ __global__ void __launch_bounds__(kChainBlock) replay_kernel(const int32_t* __re
   chain_replay_block(counts, good, K, st, rec);
 }
 
-// ---- refined plane + stop rule as their own kernels (sharded clouds: an exchange sits between them and K3 / K5; on one
-// GPU they run in the last block of refit_kernel / compact_kernel instead) ---------------------------------------------
+// ---- refined plane as its own kernel (rounds without a refit pass: optimize_coefficients off; with the refit it runs in
+// the last block of refit_kernel on one GPU, inside the moments exchange when sharded; the stop rule likewise runs in
+// the last tile of compact_kernel / inside the totals exchange) ---------------------------------------------------------
 __global__ void finish_kernel(RoundState* st, const float4* __restrict__ hyps, const int32_t* __restrict__ triples,
                               const RefitOut* __restrict__ refit, int optimize, int scale_exp, int n_draws, RoundRecord* rec) {
   if (threadIdx.x != 0 || st->stop) return;
@@ -155,12 +156,6 @@ __global__ void finish_kernel(RoundState* st, const float4* __restrict__ hyps, c
   for (int i = 0; i < 16; ++i) m[i] = refit->m[i];
   const float pivot[3] = {refit->pivot[0], refit->pivot[1], refit->pivot[2]};
   chain_finish(st, hyps, triples, m, pivot, optimize, scale_exp, n_draws, rec);
-}
-
-__global__ void advance_kernel(RoundState* st, const long long* __restrict__ totals, int n_ranks, int rank, int min_plane,
-                               RoundRecord* rec) {
-  if (threadIdx.x != 0 || st->stop) return;
-  chain_advance(st, totals, n_ranks, rank, min_plane, rec);
 }
 
 void launch_draw(const uint32_t* rnd, int n_draws, RoundState* st, int32_t* triples, unsigned long long* table, size_t table_slots,
@@ -188,10 +183,6 @@ void launch_replay(const int32_t* counts, const int32_t* good, int K, RoundState
 void launch_finish(RoundState* st, const float4* hyps, const int32_t* triples, const RefitOut* refit, int optimize, int scale_exp,
                    int n_draws, RoundRecord* rec, cudaStream_t s) {
   finish_kernel<<<1, 32, 0, s>>>(st, hyps, triples, refit, optimize, scale_exp, n_draws, rec);
-}
-
-void launch_advance(RoundState* st, const long long* totals, int n_ranks, int rank, int min_plane, RoundRecord* rec, cudaStream_t s) {
-  advance_kernel<<<1, 32, 0, s>>>(st, totals, n_ranks, rank, min_plane, rec);
 }
 
 }  // namespace pr

@@ -264,8 +264,6 @@ void launch_replay(const int32_t* counts, const int32_t* good, int K, RoundState
 // st->plane = refined coefficients (closed form from the summed moments, pr_math.h) or the raw model; fills the record.
 void launch_finish(RoundState* st, const float4* hyps, const int32_t* triples, const RefitOut* refit, int optimize, int scale_exp,
                    int n_draws, RoundRecord* rec, cudaStream_t s);
-// Minimum-plane-size rule on the global inlier count; on acceptance the state moves to the remaining cloud.
-void launch_advance(RoundState* st, const long long* totals, int n_ranks, int rank, int min_plane, RoundRecord* rec, cudaStream_t s);
 
 // ---- batch of small clouds without the host in the loop (score-all mode; pr_chain.cu) ----------------------------------
 // best[c] = computeModel's winner among cloud c's K draws (-1 + *any_bad when a degenerate sample needs PCL's redraw).
