@@ -658,15 +658,13 @@ static void launch_score_h(const float* X, const float* Y, const float* Z, size_
     gx = (total_items + items_per_cta - 1) / items_per_cta;
   }
   dim3 grid(gx, n_chunks);
-  static const int unroll = [] { const char* e = getenv("PR_SCORE_UNROLL"); return e ? atoi(e) : 16; }();  // tuning knob (H = 8, FMA order): % of FP32 peak at N = 10M, K = 4096: 59.2 (2), 60.3 (8), 61.0 (16), 50.9 (32: instruction cache)
+  // loop unroll of the H = 8 / FMA-order kernel: % of FP32 peak at N = 10M, K = 4096 measured on B200: 59.2 (2), 60.3 (8),
+  // 61.0 (16), 50.9 (32: the body no longer fits the instruction cache) — profiles/r02_score_unroll.txt
 #define PR_SCORE(HH, D, U)                                                                                                   \
   score_kernel<HH, D, U><<<grid, kScoreThreads, 0, s>>>(X, Y, Z, cloud_stride, tiles_per_cloud, total_items, items_per_cta, \
                                                         pts_per_cta, n_padded, hyps, K, k_begin, k_end, t, counts, warps_h, st)
   if (dot_order == 1) {
-    if (H == 8 && unroll == 4) PR_SCORE(8, 1, 4);
-    else if (H == 8 && unroll == 8) PR_SCORE(8, 1, 8);
-    else if (H == 8 && unroll == 16) PR_SCORE(8, 1, 16);
-    else if (H == 8 && unroll == 32) PR_SCORE(8, 1, 32);
+    if (H == 8) PR_SCORE(8, 1, 16);
     else PR_SCORE(H, 1, 2);
   } else {
     PR_SCORE(H, 0, 2);
