@@ -38,6 +38,7 @@ __global__ void __launch_bounds__(256) draw_scatter_kernel(const uint32_t* __res
                                                            int32_t* __restrict__ counts, int K, RefitOut* __restrict__ refit,
                                                            unsigned long long* __restrict__ scratch, size_t scratch_words,
                                                            unsigned* __restrict__ tickets) {
+  pdl_wait();
   if (st->stop) return;
   const size_t stride = (size_t)gridDim.x * blockDim.x, i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   for (size_t i = i0; i < scratch_words; i += stride) scratch[i] = 0ull;
@@ -71,6 +72,7 @@ __global__ void __launch_bounds__(kResolveThreads) draw_resolve_kernel(RoundStat
   uint32_t* s_keys = reinterpret_cast<uint32_t*>(s_raw + (size_t)kDrawCollCap * 20);
   int32_t* s_vals = reinterpret_cast<int32_t*>(s_raw + (size_t)kDrawCollCap * 20 + (size_t)kResolveMapSlots * 4);
   __shared__ int s_distinct;
+  pdl_wait();
   if (st->stop) return;
   if (st->n_global < 3) {  // getSamples: "Can not select 0 unique points out of N": segment() returns no model
     if (threadIdx.x == 0) {
@@ -142,6 +144,7 @@ __global__ void __launch_bounds__(kResolveThreads) draw_resolve_kernel(RoundStat
 // ---- computeModel's decision over the K counts (pr_chain_dev.cuh chain_replay_block) as its own kernel (one GPU) ------
 __global__ void __launch_bounds__(kChainBlock) replay_kernel(const int32_t* __restrict__ counts, const int32_t* __restrict__ good, int K,
                                                              RoundState* st, RoundRecord* rec) {
+  pdl_wait();
   if (st->stop) return;
   chain_replay_block(counts, good, K, st, rec);
 }
@@ -151,6 +154,7 @@ __global__ void __launch_bounds__(kChainBlock) replay_kernel(const int32_t* __re
 // the last tile of compact_kernel / inside the totals exchange) ---------------------------------------------------------
 __global__ void finish_kernel(RoundState* st, const float4* __restrict__ hyps, const int32_t* __restrict__ triples,
                               const RefitOut* __restrict__ refit, int optimize, int scale_exp, int n_draws, RoundRecord* rec) {
+  pdl_wait();
   if (threadIdx.x != 0 || st->stop) return;
   long long m[16];
   for (int i = 0; i < 16; ++i) m[i] = refit->m[i];
@@ -164,10 +168,10 @@ void launch_draw(const uint32_t* rnd, int n_draws, RoundState* st, int32_t* trip
   const int n_ops = 3 * n_draws;
   int blocks = (n_ops + 255) / 256;
   if (blocks > 148 * 4) blocks = 148 * 4;
-  draw_scatter_kernel<<<blocks, 256, 0, s>>>(rnd, n_ops, st, triples, table, (uint32_t)(table_slots - 1), epoch, coll, coll_count, counts,
-                                             n_draws, refit, reinterpret_cast<unsigned long long*>(scratch), scratch_bytes / 8, tickets);
+  launch_chained(draw_scatter_kernel, dim3(blocks), dim3(256), 0, s, rnd, n_ops, st, triples, table, (uint32_t)(table_slots - 1), epoch, coll,
+                 coll_count, counts, n_draws, refit, reinterpret_cast<unsigned long long*>(scratch), scratch_bytes / 8, tickets);
   cudaFuncSetAttribute(draw_resolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kResolveSmemBytes);  // per device: cheap, unconditional
-  draw_resolve_kernel<<<1, kResolveThreads, kResolveSmemBytes, s>>>(st, triples, coll, coll_count, rec);
+  launch_chained(draw_resolve_kernel, dim3(1), dim3(kResolveThreads), kResolveSmemBytes, s, st, triples, coll, coll_count, rec);
 }
 
 size_t draw_table_slots(int n_draws) {
@@ -177,12 +181,12 @@ size_t draw_table_slots(int n_draws) {
 }
 
 void launch_replay(const int32_t* counts, const int32_t* good, int K, RoundState* st, RoundRecord* rec, cudaStream_t s) {
-  replay_kernel<<<1, kChainBlock, 0, s>>>(counts, good, K, st, rec);
+  launch_chained(replay_kernel, dim3(1), dim3(kChainBlock), 0, s, counts, good, K, st, rec);
 }
 
 void launch_finish(RoundState* st, const float4* hyps, const int32_t* triples, const RefitOut* refit, int optimize, int scale_exp,
                    int n_draws, RoundRecord* rec, cudaStream_t s) {
-  finish_kernel<<<1, 32, 0, s>>>(st, hyps, triples, refit, optimize, scale_exp, n_draws, rec);
+  launch_chained(finish_kernel, dim3(1), dim3(32), 0, s, st, hyps, triples, refit, optimize, scale_exp, n_draws, rec);
 }
 
 }  // namespace pr

@@ -5,10 +5,45 @@
 
 #include <math_constants.h>
 
+#include <cstdlib>
+#include <tuple>
+#include <utility>
+
 #include "pr_kernels.h"
 #include "pr_math.h"
 
 namespace pr {
+
+// ---- programmatic dependent launch for the kernels of a queued round -----------------------------------------------------
+// Every kernel of the host-free loop depends on the one before it, so the ~2-3 us it takes to set up and schedule a grid
+// would sit exposed between any two of them (about nine per round).  Launched with the programmatic-stream-serialization
+// attribute, a kernel's grid is set up while its predecessor drains; the kernel then waits at griddepcontrol.wait (first
+// statement) until the predecessor has completed and its writes are visible.  PR_PDL=0 launches them plainly.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <typename... P, size_t... I>
+inline cudaError_t launch_chained_impl(void (*kernel)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, std::tuple<P...>& params,
+                                       std::index_sequence<I...>) {
+  static const bool pdl = [] { const char* e = getenv("PR_PDL"); return !(e && atoi(e) == 0); }();
+  void* ptrs[] = {static_cast<void*>(&std::get<I>(params))...};
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelExC(&cfg, reinterpret_cast<const void*>(kernel), ptrs);
+}
+
+template <typename... P, typename... A>
+inline cudaError_t launch_chained(void (*kernel)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, A... args) {
+  std::tuple<P...> params(static_cast<P>(args)...);  // the kernel's own parameter types
+  return launch_chained_impl(kernel, grid, block, smem, s, params, std::index_sequence_for<P...>{});
+}
 
 // PCL SampleConsensusModelPlane::isSampleGood + computeModelCoefficients (sac_model_plane.hpp), FP32,
 // every operation rounded on its own; reductions in Eigen's SSE2 order (e0 + e2) + (e1 + e3).

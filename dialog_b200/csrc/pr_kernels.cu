@@ -358,6 +358,7 @@ __global__ void __launch_bounds__(128) gather_models_kernel(const float* __restr
                                                             const float* __restrict__ z, const int32_t* __restrict__ triples,
                                                             int n_models, int4* __restrict__ sample_pts, float4* __restrict__ hyps,
                                                             int32_t* __restrict__ good, const RoundState* __restrict__ st) {
+  pdl_wait();
   if (st->stop) return;
   const long long n = st->n_local;
   int k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -379,7 +380,8 @@ __global__ void __launch_bounds__(128) gather_models_kernel(const float* __restr
 void launch_gather_models(CloudView cloud, const int32_t* triples, int n_models, int4* sample_pts, float4* hyps, int32_t* good,
                           const RoundState* st, cudaStream_t s) {
   if (n_models <= 0) return;
-  gather_models_kernel<<<(n_models + 127) / 128, 128, 0, s>>>(cloud.x, cloud.y, cloud.z, triples, n_models, sample_pts, hyps, good, st);
+  launch_chained(gather_models_kernel, dim3((n_models + 127) / 128), dim3(128), 0, s, cloud.x, cloud.y, cloud.z, triples, n_models, sample_pts,
+                 hyps, good, st);
 }
 
 void launch_gather_samples(CloudView cloud, long long first, size_t n, const int32_t* triples, int n_samples,
@@ -470,6 +472,7 @@ __global__ void __launch_bounds__(kScoreThreads, H <= 4 ? 4 : 2)
   // hypotheses [k_begin, k_end) of the K per cloud are scored by this launch
   if (st != nullptr) {
     // peel loop without the host (range mode): the even split of launch_score_h, from the cloud size on the device
+    pdl_wait();
     if (st->stop) return;
     const long long unit = 128ll * (kScoreWarps / warps_h);
     n_padded = (st->n_local + unit - 1) / unit * unit;
@@ -660,9 +663,15 @@ static void launch_score_h(const float* X, const float* Y, const float* Z, size_
   dim3 grid(gx, n_chunks);
   // loop unroll of the H = 8 / FMA-order kernel: % of FP32 peak at N = 10M, K = 4096 measured on B200: 59.2 (2), 60.3 (8),
   // 61.0 (16), 50.9 (32: the body no longer fits the instruction cache) — profiles/r02_score_unroll.txt
-#define PR_SCORE(HH, D, U)                                                                                                   \
-  score_kernel<HH, D, U><<<grid, kScoreThreads, 0, s>>>(X, Y, Z, cloud_stride, tiles_per_cloud, total_items, items_per_cta, \
-                                                        pts_per_cta, n_padded, hyps, K, k_begin, k_end, t, counts, warps_h, st)
+#define PR_SCORE(HH, D, U)                                                                                                    \
+  do {                                                                                                                        \
+    if (st != nullptr)                                                                                                        \
+      launch_chained(score_kernel<HH, D, U>, grid, dim3(kScoreThreads), 0, s, X, Y, Z, cloud_stride, tiles_per_cloud, total_items,      \
+                     items_per_cta, pts_per_cta, n_padded, hyps, K, k_begin, k_end, t, counts, warps_h, st);                  \
+    else                                                                                                                      \
+      score_kernel<HH, D, U><<<grid, kScoreThreads, 0, s>>>(X, Y, Z, cloud_stride, tiles_per_cloud, total_items, items_per_cta, \
+                                                            pts_per_cta, n_padded, hyps, K, k_begin, k_end, t, counts, warps_h, st); \
+  } while (0)
   if (dot_order == 1) {
     if (H == 8) PR_SCORE(8, 1, 16);
     else PR_SCORE(H, 1, 2);
@@ -1099,6 +1108,7 @@ __global__ void __launch_bounds__(256, 4) refit_kernel(const float* __restrict__
                                                        size_t cloud_stride, int K, const int32_t* __restrict__ model_idx_arr,
                                                        const double* __restrict__ scale_arr, RoundState* st, ChainTail tail) {
   if (st != nullptr) {  // peel loop without the host: size and winning draw of this round live on the device
+    pdl_wait();
     if (st->stop || st->best < 0) return;
     n = (size_t)st->n_local;
     model_index = st->best;
@@ -1219,7 +1229,14 @@ void launch_refit(CloudView cloud, size_t n, const float4* hyps, const int4* sam
   // one wave exactly: 4 resident CTAs per SM (launch bounds), grid-stride over the cloud
   if (blocks > (size_t)num_sms * 4) blocks = (size_t)num_sms * 4;
   if (blocks < 1) blocks = 1;
-  if (dot_order == 1)
+  if (st != nullptr) {
+    if (dot_order == 1)
+      launch_chained(refit_kernel<1>, dim3((unsigned)blocks), dim3(256), 0, s, cloud.x, cloud.y, cloud.z, n, hyps, sample_pts, model_index, t, scale, out,
+                     (size_t)0, 0, (const int32_t*)nullptr, (const double*)nullptr, st, tl);
+    else
+      launch_chained(refit_kernel<0>, dim3((unsigned)blocks), dim3(256), 0, s, cloud.x, cloud.y, cloud.z, n, hyps, sample_pts, model_index, t, scale, out,
+                     (size_t)0, 0, (const int32_t*)nullptr, (const double*)nullptr, st, tl);
+  } else if (dot_order == 1)
     refit_kernel<1><<<(unsigned)blocks, 256, 0, s>>>(cloud.x, cloud.y, cloud.z, n, hyps, sample_pts, model_index, t, scale, out, 0, 0, nullptr, nullptr, st, tl);
   else
     refit_kernel<0><<<(unsigned)blocks, 256, 0, s>>>(cloud.x, cloud.y, cloud.z, n, hyps, sample_pts, model_index, t, scale, out, 0, 0, nullptr, nullptr, st, tl);
@@ -1320,6 +1337,7 @@ __global__ void __launch_bounds__(kCompactThreads, 5)
   if (st != nullptr) {
     // peel loop without the host: size, plane and list offset of this round live on the device; the grid was sized
     // for an upper bound of n
+    pdl_wait();
     if (st->stop) return;
     n = (size_t)st->n_local;
     pl.a = st->plane[0]; pl.b = st->plane[1]; pl.c = st->plane[2]; pl.d = st->plane[3];
@@ -1548,10 +1566,16 @@ void launch_compact(CloudView src, size_t n, Plane4 plane, float t, int dot_orde
   if (tail) tl = *tail;
   unsigned long long* tile_state = reinterpret_cast<unsigned long long*>(scratch);
   unsigned* ticket = reinterpret_cast<unsigned*>(tile_state + (n + kCompactTile - 1) / kCompactTile);
-#define PR_COMPACT(D, W)                                                                                              \
-  compact_kernel<D, W><<<n_tiles, kCompactThreads, 0, s>>>(src.x, src.y, src.z, src.orig, n, plane, t, dst.x, dst.y,  \
-                                                           dst.z, dst.orig, dst.cap, inl_cur, inl_orig, tile_state,   \
-                                                           ticket, totals, flags, st, tl)
+#define PR_COMPACT(D, W)                                                                                                       \
+  do {                                                                                                                         \
+    if (st != nullptr)                                                                                                         \
+      launch_chained(compact_kernel<D, W>, dim3(n_tiles), dim3(kCompactThreads), 0, s, src.x, src.y, src.z, src.orig, n, plane, t, dst.x, \
+                     dst.y, dst.z, dst.orig, dst.cap, inl_cur, inl_orig, tile_state, ticket, totals, flags, st, tl);           \
+    else                                                                                                                       \
+      compact_kernel<D, W><<<n_tiles, kCompactThreads, 0, s>>>(src.x, src.y, src.z, src.orig, n, plane, t, dst.x, dst.y, dst.z, \
+                                                               dst.orig, dst.cap, inl_cur, inl_orig, tile_state, ticket,       \
+                                                               totals, flags, st, tl);                                         \
+  } while (0)
   if (dot_order == 3) {
     PR_COMPACT(3, true);
   } else if (dot_order == 2) {
