@@ -187,6 +187,10 @@ struct plane_ransac_ctx {
   DevBuf<float4> d_batch_raw;
   DevBuf<unsigned long long> d_batch_offs;
   DevBuf<int> d_batch_flag;
+  DevBuf<uint32_t> d_batch_out;    // flag | best | best count | final count | raw | refined, read back in one copy
+  PinBuf<uint32_t> h_batch_out;
+  DevBuf<int32_t> d_batch_tri;
+  size_t batch_tri_dev_valid = 0;  // number of triple entries of batch_tri that are on the device
   std::vector<int32_t> batch_tri;  // the K triples every cloud of the batch draws (same size, same seed)
   size_t batch_tri_n = 0;
   unsigned batch_tri_seed = 0;
@@ -670,9 +674,7 @@ inline size_t p2p_flag_off(int ch) { return (size_t)ch * pr::kP2PMaxRanks * size
 
 // K1a + its exchange: sample points of `n_samples` indices into dsp on every rank.  st: the shard extent comes from the
 // device-resident round state and the exchange is skipped once the peel loop has stopped (run_chain); tail: the small
-// step that consumes the result, run by the exchange kernel itself (peer-memory mode only — check with p2p_takes_tail).
-bool p2p_takes_tail(const plane_ransac_ctx* c, size_t n_hyps) { return c->p2p_on && n_hyps <= kP2PMaxHyps; }
-
+// step that consumes the result, run by the exchange kernel itself (peer-memory mode only: run_chain requires it).
 int exchange_samples(plane_ransac_ctx* c, pr::CloudView src, long long first, size_t n_local, const int32_t* dt, int n_samples,
                      int4* dsp, pr::RoundState* st = nullptr, const pr::P2PTail* tail = nullptr) {
   if (c->p2p_on && (size_t)n_samples <= 3 * kP2PMaxHyps) {
@@ -1574,6 +1576,7 @@ void plane_ransac_destroy(plane_ransac_ctx* c) {
   dev_free(c->d_batch_hyps); dev_free(c->d_batch_pts); dev_free(c->d_batch_cnt);
   dev_free(c->d_batch_best); dev_free(c->d_batch_bestcnt); dev_free(c->d_batch_sexp); dev_free(c->d_batch_lists);
   dev_free(c->d_batch_raw); dev_free(c->d_batch_offs); dev_free(c->d_batch_flag);
+  dev_free(c->d_batch_out); pin_free(c->h_batch_out); dev_free(c->d_batch_tri);
   pin_free(c->h_triples); pin_free(c->h_counts); pin_free(c->h_good); pin_free(c->h_refit); pin_free(c->h_sample_pts);
   for (cudaEvent_t e : c->pend.ev) cudaEventDestroy(e);
   pin_free(c->h_totals); pin_free(c->h_small);
@@ -2231,10 +2234,11 @@ int plane_ransac_set_cloud_batch(plane_ransac_ctx* c, const pr_point* pts, size_
 
 namespace {
 
-// Every cloud's ascending inlier list for the planes in d_batch_hyps (clouds with ok[c] < 0 have none): offsets, then
-// the lists themselves into the caller's buffer.
-int batch_lists_out(plane_ransac_ctx* c, const pr_params* prm, const int32_t* d_ok, const int32_t* d_cnt, int32_t* inliers, size_t cap,
-                    size_t* offsets) {
+// Every cloud's ascending inlier list for d_planes (clouds with ok[c] < 0 have none), in two halves so that a caller can
+// put its own read-backs between them under one synchronisation: queue the offsets + list kernels and the offsets'
+// read-back; then, once the stream has been synchronised, check the capacity and fetch the lists.
+int batch_lists_queue(plane_ransac_ctx* c, const pr_params* prm, const float4* d_planes, const int32_t* d_ok, const int32_t* d_cnt,
+                      int32_t* inliers, size_t cap, size_t* offsets) {
   const size_t C = c->batch_clouds, n = c->batch_n;
   if (!offsets) return PR_OK;
   const float t = pr::threshold_up(prm->distance_threshold);
@@ -2243,14 +2247,18 @@ int batch_lists_out(plane_ransac_ctx* c, const pr_params* prm, const int32_t* d_
   if (dev_cap) PR_TRY(dev_reserve(c->d_batch_lists, dev_cap));
   {
     Span sp(c, KC_COMPACT, dev_cap ? 2 : 1);
-    pr::launch_batch_lists(c->batch_view, n, c->batch_stride, (int)C, c->d_batch_hyps.p, d_ok, t, prm->dot_order, d_cnt, c->d_batch_offs.p, dev_cap,
+    pr::launch_batch_lists(c->batch_view, n, c->batch_stride, (int)C, d_planes, d_ok, t, prm->dot_order, d_cnt, c->d_batch_offs.p, dev_cap,
                            dev_cap ? c->d_batch_lists.p : nullptr, c->stream);
   }
   PR_CUDA(cudaGetLastError());
   static_assert(sizeof(size_t) == sizeof(unsigned long long), "size_t is 64 bits");
   PR_CUDA(cudaMemcpyAsync(offsets, c->d_batch_offs.p, (C + 1) * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
-  PR_TRY(sync_stream(c));
-  const size_t total = offsets[C];
+  return PR_OK;
+}
+
+int batch_lists_fetch(plane_ransac_ctx* c, int32_t* inliers, size_t cap, const size_t* offsets) {
+  if (!offsets) return PR_OK;
+  const size_t total = offsets[c->batch_clouds];
   if (inliers && total > cap) return fail(PR_ERR_CAPACITY, "inlier buffer holds %zu entries, the batch has %zu inliers", cap, total);
   if (inliers && total) {
     PR_CUDA(cudaMemcpyAsync(inliers, c->d_batch_lists.p, total * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
@@ -2277,63 +2285,73 @@ int segment_batch_device(plane_ransac_ctx* c, const pr_params* prm, float* coeff
     for (int j = 0; j < K; ++j) sampler.draw(c->batch_tri.data() + 3 * j);
     c->batch_tri_n = n;
     c->batch_tri_seed = prm->seed;
+    c->batch_tri_dev_valid = 0;
   }
   PR_TRY(reserve_draws(c, CK, false));
-  PR_TRY(dev_reserve(c->d_batch_best, C));
-  PR_TRY(dev_reserve(c->d_batch_bestcnt, C));
-  PR_TRY(dev_reserve(c->d_batch_flag, 1));
+  // every per-cloud result in ONE device block (a single read-back): flag | raw | refined | best | best count | final count
+  const size_t words = 4 + 8 * C + 3 * C;  // 32-bit words; the float4 parts stay 16-byte aligned
+  PR_TRY(dev_reserve(c->d_batch_out, words));
+  PR_TRY(pin_reserve(c->h_batch_out, words));
+  int* d_flag = reinterpret_cast<int*>(c->d_batch_out.p);
+  float4* d_raw = reinterpret_cast<float4*>(c->d_batch_out.p + 4);
+  float4* d_refined = d_raw + C;
+  int32_t* d_best = reinterpret_cast<int32_t*>(d_refined + C);
+  int32_t* d_bestcnt = d_best + C;
+  int32_t* d_cnt = prm->optimize_coefficients ? d_bestcnt + C : d_bestcnt;  // without the refit the raw model's count is final
   PR_TRY(dev_reserve(c->d_batch_refit, C));
-  PR_TRY(dev_reserve(c->d_batch_raw, C));
   PR_TRY(dev_reserve(c->d_batch_hyps, C));
-  PR_TRY(dev_reserve(c->d_batch_cnt, 2 * C));
-  std::memcpy(c->h_triples.p, c->batch_tri.data(), 3 * (size_t)K * sizeof(int32_t));
-  PR_CUDA(cudaMemcpyAsync(c->d_triples.p, c->h_triples.p, 3 * (size_t)K * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+  if (c->batch_tri_dev_valid != 3 * (size_t)K) {  // the triples only change with (n, seed, K): uploaded once
+    std::memcpy(c->h_triples.p, c->batch_tri.data(), 3 * (size_t)K * sizeof(int32_t));
+    PR_TRY(dev_reserve(c->d_batch_tri, 3 * (size_t)K));
+    PR_CUDA(cudaMemcpyAsync(c->d_batch_tri.p, c->h_triples.p, 3 * (size_t)K * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+    PR_CUDA(cudaStreamSynchronize(c->stream));
+    c->batch_tri_dev_valid = 3 * (size_t)K;
+  }
+  // One dependent chain of launches (each set up while its predecessor drains: pr_chain_dev.cuh), no memsets between
+  // them: the models launch clears the counts and the flag, the decision launch clears the moments.
   {
     Span sp(c, KC_MODELS, 2);
-    pr::launch_gather_samples(c->batch_view, 0, n, c->d_triples.p, 3 * K, c->d_sample_pts.p, (int)C, stride, c->stream);
-    pr::launch_models(c->d_sample_pts.p, (int)CK, c->d_hyps.p, c->d_good.p, c->stream);
+    pr::launch_gather_samples(c->batch_view, 0, n, c->d_batch_tri.p, 3 * K, c->d_sample_pts.p, (int)C, stride, c->stream);
+    pr::launch_models(c->d_sample_pts.p, (int)CK, c->d_hyps.p, c->d_good.p, c->stream, c->d_counts.p, d_flag, true);
   }
-  PR_CUDA(cudaMemsetAsync(c->d_counts.p, 0, CK * sizeof(int32_t), c->stream));
   {
     Span sp(c, KC_SCORE, 0);
-    c->prof.launches_score += pr::launch_score(c->batch_view, n, (int)C, stride, c->d_hyps.p, K, t, prm->dot_order, c->d_counts.p, c->num_sms, c->stream);
+    c->prof.launches_score += pr::launch_score(c->batch_view, n, (int)C, stride, c->d_hyps.p, K, t, prm->dot_order, c->d_counts.p, c->num_sms, c->stream,
+                                               nullptr, true);
     c->prof.pairs_scored += (long long)n * (long long)CK;
   }
-  PR_CUDA(cudaMemsetAsync(c->d_batch_flag.p, 0, sizeof(int), c->stream));
   {
     Span sp(c, KC_OTHER, 1);
-    pr::launch_batch_replay(c->d_counts.p, c->d_good.p, K, (int)C, c->d_batch_best.p, c->d_batch_bestcnt.p, c->d_batch_flag.p, c->stream);
+    pr::launch_batch_replay(c->d_counts.p, c->d_good.p, K, (int)C, d_best, d_bestcnt, d_flag,
+                            prm->optimize_coefficients ? c->d_batch_refit.p : nullptr, c->stream);
   }
   if (prm->optimize_coefficients) {
-    PR_CUDA(cudaMemsetAsync(c->d_batch_refit.p, 0, C * sizeof(pr::RefitOut), c->stream));
     Span sp(c, KC_REFIT, 1);
-    pr::launch_refit_batch(c->batch_view, n, stride, (int)C, c->d_hyps.p, c->d_sample_pts.p, K, c->d_batch_best.p, t, prm->dot_order,
-                           c->d_batch_scale.p, c->d_batch_refit.p, c->stream);
+    pr::launch_refit_batch(c->batch_view, n, stride, (int)C, c->d_hyps.p, c->d_sample_pts.p, K, d_best, t, prm->dot_order,
+                           c->d_batch_scale.p, c->d_batch_refit.p, c->stream, true);
     c->prof.points_refit += (long long)(n * C);
     c->prof.bytes_refit += 12ll * (long long)(n * C);
   }
   {
     Span sp(c, KC_OTHER, 1);
-    pr::launch_batch_finish(c->d_hyps.p, K, c->d_batch_best.p, c->d_batch_refit.p, c->d_batch_sexp.p, prm->optimize_coefficients ? 1 : 0,
-                            (int)C, c->d_batch_raw.p, c->d_batch_hyps.p, c->stream);
+    pr::launch_batch_finish(c->d_hyps.p, K, d_best, c->d_batch_refit.p, c->d_batch_sexp.p, prm->optimize_coefficients ? 1 : 0,
+                            (int)C, d_raw, d_refined, c->stream);
   }
-  const int32_t* d_final = c->d_batch_bestcnt.p;  // without the refit the raw model's count is the final one
   if (prm->optimize_coefficients) {
     Span sp(c, KC_COMPACT, 1);
-    pr::launch_batch_count(c->batch_view, n, stride, (int)C, c->d_batch_hyps.p, c->d_batch_best.p, t, prm->dot_order, c->d_batch_cnt.p, c->stream);
-    d_final = c->d_batch_cnt.p;
+    pr::launch_batch_count(c->batch_view, n, stride, (int)C, d_refined, d_best, t, prm->dot_order, d_cnt, c->stream);
   }
   PR_CUDA(cudaGetLastError());
-  std::vector<int32_t> best(C), best_cnt(C), final_cnt(C);
-  std::vector<float4> raw(C), refined(C);
-  int flag = 0;
-  PR_CUDA(cudaMemcpyAsync(&flag, c->d_batch_flag.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-  PR_CUDA(cudaMemcpyAsync(best.data(), c->d_batch_best.p, C * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
-  PR_CUDA(cudaMemcpyAsync(best_cnt.data(), c->d_batch_bestcnt.p, C * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
-  PR_CUDA(cudaMemcpyAsync(final_cnt.data(), d_final, C * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
-  PR_CUDA(cudaMemcpyAsync(raw.data(), c->d_batch_raw.p, C * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
-  PR_CUDA(cudaMemcpyAsync(refined.data(), c->d_batch_hyps.p, C * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
+  // the lists are queued before anything is read back (a batch that has to be redone wastes them, nothing else)
+  PR_TRY(batch_lists_queue(c, prm, d_refined, d_best, d_cnt, inliers, cap, offsets));
+  PR_CUDA(cudaMemcpyAsync(c->h_batch_out.p, c->d_batch_out.p, words * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
   PR_TRY(sync_stream(c));
+  const int flag = *reinterpret_cast<const int*>(c->h_batch_out.p);
+  const float4* raw = reinterpret_cast<const float4*>(c->h_batch_out.p + 4);
+  const float4* refined = raw + C;
+  const int32_t* best = reinterpret_cast<const int32_t*>(refined + C);
+  const int32_t* best_cnt = best + C;
+  const int32_t* final_cnt = prm->optimize_coefficients ? best_cnt + C : best_cnt;
   if (flag) {
     *fell_back = true;
     return PR_OK;
@@ -2356,7 +2374,7 @@ int segment_batch_device(plane_ransac_ctx* c, const pr_params* prm, float* coeff
       infos[i] = inf;
     }
   }
-  return batch_lists_out(c, prm, c->d_batch_best.p, d_final, inliers, cap, offsets);
+  return batch_lists_fetch(c, inliers, cap, offsets);
 }
 
 int segment_batch_host(plane_ransac_ctx* c, const pr_params* prm, float* coeffs, int32_t* n_inliers, int32_t* inliers, size_t cap,
@@ -2528,7 +2546,9 @@ int segment_batch_host(plane_ransac_ctx* c, const pr_params* prm, float* coeffs,
   PR_CUDA(cudaMemcpyAsync(c->d_batch_hyps.p, refined.data(), C * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
   PR_CUDA(cudaMemcpyAsync(c->d_batch_idx.p, model_idx.data(), C * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
   PR_CUDA(cudaMemcpyAsync(c->d_batch_cnt.p, n_inliers, C * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
-  return batch_lists_out(c, prm, c->d_batch_idx.p, c->d_batch_cnt.p, inliers, cap, offsets);
+  PR_TRY(batch_lists_queue(c, prm, c->d_batch_hyps.p, c->d_batch_idx.p, c->d_batch_cnt.p, inliers, cap, offsets));
+  PR_TRY(sync_stream(c));
+  return batch_lists_fetch(c, inliers, cap, offsets);
 }
 
 }  // namespace

@@ -201,9 +201,13 @@ namespace pr {
 // computeModel over the K counts of every cloud: best[c] = first draw with the largest count, or -1 and *any_bad = 1 when
 // a degenerate sample among the K draws means PCL would have drawn further (the host-driven path then redoes the batch).
 __global__ void __launch_bounds__(128) batch_replay_kernel(const int32_t* __restrict__ counts, const int32_t* __restrict__ good, int K,
-                                                           int32_t* __restrict__ best, int32_t* __restrict__ best_count, int* any_bad) {
+                                                           int32_t* __restrict__ best, int32_t* __restrict__ best_count, int* any_bad,
+                                                           RefitOut* __restrict__ refit_to_clear) {
   __shared__ unsigned long long s_best[4];
+  pdl_wait();
   const size_t c = blockIdx.x;
+  if (refit_to_clear != nullptr && threadIdx.x < sizeof(RefitOut) / sizeof(long long))
+    reinterpret_cast<long long*>(refit_to_clear + c)[threadIdx.x] = 0;  // the refit pass that follows accumulates into it
   unsigned long long b = 0ull;
   int all_good = 1;
   for (int j = threadIdx.x; j < K; j += 128) {
@@ -235,6 +239,7 @@ __global__ void __launch_bounds__(128) batch_replay_kernel(const int32_t* __rest
 __global__ void __launch_bounds__(64) batch_finish_kernel(const float4* __restrict__ hyps, int K, const int32_t* __restrict__ best,
                                                           const RefitOut* __restrict__ refit, const int32_t* __restrict__ scale_exp,
                                                           int optimize, int n_clouds, float4* __restrict__ raw, float4* __restrict__ refined) {
+  pdl_wait();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= n_clouds) return;
   const int b = best[c];
@@ -260,6 +265,7 @@ __global__ void __launch_bounds__(1024) batch_offsets_kernel(const int32_t* __re
   __shared__ unsigned long long s_warp[32];
   __shared__ unsigned long long s_carry;
   if (threadIdx.x == 0) s_carry = 0ull;
+  pdl_wait();
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int base = 0; base < n_clouds; base += 1024) {
@@ -292,6 +298,7 @@ __global__ void __launch_bounds__(256) batch_lists_kernel(const float* __restric
                                                           const unsigned long long* __restrict__ offs, size_t cap, int32_t* __restrict__ out) {
   __shared__ int s_warp[8];
   __shared__ int s_base;
+  pdl_wait();
   const size_t c = blockIdx.x;
   if (best[c] < 0) return;
   const float4 pl = planes[c];
@@ -350,6 +357,7 @@ __global__ void __launch_bounds__(256) batch_count_kernel(const float* __restric
                                                           size_t n_per, size_t stride, const float4* __restrict__ planes,
                                                           const int32_t* __restrict__ best, float t, int32_t* __restrict__ cnt) {
   __shared__ int s_warp[8];
+  pdl_wait();
   const size_t c = blockIdx.x;
   if (best[c] < 0) {
     if (threadIdx.x == 0) cnt[c] = 0;
@@ -385,28 +393,28 @@ __global__ void __launch_bounds__(256) batch_count_kernel(const float* __restric
 
 void launch_batch_count(CloudView clouds, size_t n_per, size_t stride, int n_clouds, const float4* planes, const int32_t* best, float t,
                         int dot_order, int32_t* cnt, cudaStream_t s) {
-  if (dot_order == 1) batch_count_kernel<1><<<n_clouds, 256, 0, s>>>(clouds.x, clouds.y, clouds.z, n_per, stride, planes, best, t, cnt);
-  else batch_count_kernel<0><<<n_clouds, 256, 0, s>>>(clouds.x, clouds.y, clouds.z, n_per, stride, planes, best, t, cnt);
+  if (dot_order == 1) launch_chained(batch_count_kernel<1>, dim3(n_clouds), dim3(256), 0, s, clouds.x, clouds.y, clouds.z, n_per, stride, planes, best, t, cnt);
+  else launch_chained(batch_count_kernel<0>, dim3(n_clouds), dim3(256), 0, s, clouds.x, clouds.y, clouds.z, n_per, stride, planes, best, t, cnt);
 }
 
 void launch_batch_replay(const int32_t* counts, const int32_t* good, int K, int n_clouds, int32_t* best, int32_t* best_count, int* any_bad,
-                         cudaStream_t s) {
-  batch_replay_kernel<<<n_clouds, 128, 0, s>>>(counts, good, K, best, best_count, any_bad);
+                         RefitOut* refit_to_clear, cudaStream_t s) {
+  launch_chained(batch_replay_kernel, dim3(n_clouds), dim3(128), 0, s, counts, good, K, best, best_count, any_bad, refit_to_clear);
 }
 
 void launch_batch_finish(const float4* hyps, int K, const int32_t* best, const RefitOut* refit, const int32_t* scale_exp, int optimize,
                          int n_clouds, float4* raw, float4* refined, cudaStream_t s) {
-  batch_finish_kernel<<<(n_clouds + 63) / 64, 64, 0, s>>>(hyps, K, best, refit, scale_exp, optimize, n_clouds, raw, refined);
+  launch_chained(batch_finish_kernel, dim3((n_clouds + 63) / 64), dim3(64), 0, s, hyps, K, best, refit, scale_exp, optimize, n_clouds, raw, refined);
 }
 
 void launch_batch_lists(CloudView clouds, size_t n_per, size_t stride, int n_clouds, const float4* planes, const int32_t* best, float t,
                         int dot_order, const int32_t* cnt, unsigned long long* offs, size_t cap, int32_t* out, cudaStream_t s) {
-  batch_offsets_kernel<<<1, 1024, 0, s>>>(cnt, n_clouds, offs);
+  launch_chained(batch_offsets_kernel, dim3(1), dim3(1024), 0, s, cnt, n_clouds, offs);
   if (out == nullptr) return;
   if (dot_order == 1)
-    batch_lists_kernel<1><<<n_clouds, 256, 0, s>>>(clouds.x, clouds.y, clouds.z, n_per, stride, planes, best, t, offs, cap, out);
+    launch_chained(batch_lists_kernel<1>, dim3(n_clouds), dim3(256), 0, s, clouds.x, clouds.y, clouds.z, n_per, stride, planes, best, t, offs, cap, out);
   else
-    batch_lists_kernel<0><<<n_clouds, 256, 0, s>>>(clouds.x, clouds.y, clouds.z, n_per, stride, planes, best, t, offs, cap, out);
+    launch_chained(batch_lists_kernel<0>, dim3(n_clouds), dim3(256), 0, s, clouds.x, clouds.y, clouds.z, n_per, stride, planes, best, t, offs, cap, out);
 }
 
 }  // namespace pr

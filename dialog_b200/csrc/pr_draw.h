@@ -56,7 +56,9 @@ PR_HD void draw_resolve(const uint32_t* ops_sorted, int n_ops, int32_t* v, Fetch
     // content of head position p just before op s: the later of the last op that had p as its first operand (every
     // third op; it left its v there) and the last recorded swap of another head position with p
     int32_t head[3];
+#if defined(__CUDACC__)
 #pragma unroll
+#endif
     for (uint32_t p = 0; p < 3u; ++p) {
       const uint32_t d = (s % 3u + 3u - p) % 3u;
       const long long ua = (long long)s - (d == 0 ? 3 : (long long)d);  // negative: no such op yet
@@ -65,7 +67,9 @@ PR_HD void draw_resolve(const uint32_t* ops_sorted, int n_ops, int32_t* v, Fetch
         val = hw_val[p];
       } else if (ua >= 0) {
         val = fetch(i, (uint32_t)ua);
+#if defined(__CUDACC__)
 #pragma unroll
+#endif
         for (int k = 0; k < 3; ++k)
           if (done_s[k] == ua) val = done_v[k];
       }

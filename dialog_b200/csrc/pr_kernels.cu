@@ -322,6 +322,7 @@ __global__ void __launch_bounds__(256) gather_samples_kernel(const float* __rest
                                                              const int32_t* __restrict__ triples, int n_samples,
                                                              int4* __restrict__ out, int n_clouds, size_t cloud_stride,
                                                              bool per_cloud_triples, const RoundState* __restrict__ st) {
+  pdl_wait();  // returns at once unless launched as a programmatic dependent (batch path)
   if (st != nullptr) {  // peel loop without the host: this round's shard extent lives on the device
     if (st->stop) return;
     first = st->first;
@@ -343,9 +344,13 @@ __global__ void __launch_bounds__(256) gather_samples_kernel(const float* __rest
 
 // model_from_sample (PCL isSampleGood + computeModelCoefficients) lives in pr_chain_dev.cuh: the exchange kernels use it too.
 __global__ void __launch_bounds__(128) models_kernel(const int4* __restrict__ sample_pts, int n_models,
-                                                     float4* __restrict__ hyps, int32_t* __restrict__ good) {
+                                                     float4* __restrict__ hyps, int32_t* __restrict__ good,
+                                                     int32_t* __restrict__ counts_to_clear, int* __restrict__ flag_to_clear) {
+  pdl_wait();
   int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k == 0 && flag_to_clear != nullptr) *flag_to_clear = 0;
   if (k >= n_models) return;
+  if (counts_to_clear != nullptr) counts_to_clear[k] = 0;  // the scoring launch that follows accumulates into it
   float4 h;
   const bool ok = model_from_sample(sample_pts[3 * k], sample_pts[3 * k + 1], sample_pts[3 * k + 2], &h);
   hyps[k] = h;
@@ -392,12 +397,17 @@ void launch_gather_samples(CloudView cloud, long long first, size_t n, const int
   long long blocks = (total + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
   gather_samples_kernel<<<(unsigned)blocks, 256, 0, s>>>(cloud.x, cloud.y, cloud.z, first, n, triples, n_samples,
-                                                         sample_pts, n_clouds, cloud_stride, per_cloud_triples, st);
+                                                         sample_pts, n_clouds, cloud_stride, per_cloud_triples, st);  // first of its sequence: plain
 }
 
-void launch_models(const int4* sample_pts, int n_models_total, float4* hyps, int32_t* good, cudaStream_t s) {
+void launch_models(const int4* sample_pts, int n_models_total, float4* hyps, int32_t* good, cudaStream_t s, int32_t* counts_to_clear,
+                   int* flag_to_clear, bool chained) {
   if (n_models_total <= 0) return;
-  models_kernel<<<(n_models_total + 127) / 128, 128, 0, s>>>(sample_pts, n_models_total, hyps, good);
+  if (chained)
+    launch_chained(models_kernel, dim3((n_models_total + 127) / 128), dim3(128), 0, s, sample_pts, n_models_total, hyps, good, counts_to_clear,
+                   flag_to_clear);
+  else
+    models_kernel<<<(n_models_total + 127) / 128, 128, 0, s>>>(sample_pts, n_models_total, hyps, good, counts_to_clear, flag_to_clear);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -470,9 +480,9 @@ __global__ void __launch_bounds__(kScoreThreads, H <= 4 ? 4 : 2)
                  long long n_padded, const float4* __restrict__ hyps, int K, int k_begin, int k_end, float t,
                  int32_t* __restrict__ counts, int warps_h, const RoundState* __restrict__ st) {
   // hypotheses [k_begin, k_end) of the K per cloud are scored by this launch
+  pdl_wait();  // returns at once unless launched as a programmatic dependent (queued rounds, batch path)
   if (st != nullptr) {
     // peel loop without the host (range mode): the even split of launch_score_h, from the cloud size on the device
-    pdl_wait();
     if (st->stop) return;
     const long long unit = 128ll * (kScoreWarps / warps_h);
     n_padded = (st->n_local + unit - 1) / unit * unit;
@@ -637,7 +647,7 @@ __global__ void __launch_bounds__(kScoreThreads, H <= 4 ? 4 : 2)
 template <int H>
 static void launch_score_h(const float* X, const float* Y, const float* Z, size_t n_per_cloud, size_t cloud_stride,
                            int n_clouds, const float4* hyps, int K, int k_begin, int k_end, int warps_h, float t,
-                           int dot_order, int32_t* counts, int num_sms, cudaStream_t s, bool range_mode, const RoundState* st) {
+                           int dot_order, int32_t* counts, int num_sms, cudaStream_t s, bool range_mode, const RoundState* st, bool chained) {
   const int chunk = 32 * H * warps_h;
   const int n_chunks = (k_end - k_begin + chunk - 1) / chunk;
   int slots = ((H <= 4 ? 4 : 2) * num_sms) / n_chunks;
@@ -665,7 +675,7 @@ static void launch_score_h(const float* X, const float* Y, const float* Z, size_
   // 61.0 (16), 50.9 (32: the body no longer fits the instruction cache) — profiles/r02_score_unroll.txt
 #define PR_SCORE(HH, D, U)                                                                                                    \
   do {                                                                                                                        \
-    if (st != nullptr)                                                                                                        \
+    if (st != nullptr || chained)                                                                                             \
       launch_chained(score_kernel<HH, D, U>, grid, dim3(kScoreThreads), 0, s, X, Y, Z, cloud_stride, tiles_per_cloud, total_items,      \
                      items_per_cta, pts_per_cta, n_padded, hyps, K, k_begin, k_end, t, counts, warps_h, st);                  \
     else                                                                                                                      \
@@ -682,7 +692,7 @@ static void launch_score_h(const float* X, const float* Y, const float* Z, size_
 }
 
 int launch_score(CloudView cloud, size_t n_per_cloud, int n_clouds, size_t cloud_stride, const float4* hyps, int K,
-                 float t, int dot_order, int32_t* counts, int num_sms, cudaStream_t s, const RoundState* st) {
+                 float t, int dot_order, int32_t* counts, int num_sms, cudaStream_t s, const RoundState* st, bool chained) {
   if (K <= 0 || n_per_cloud == 0 || n_clouds <= 0) return 0;
   static const int forced_h = [] { const char* e = getenv("PR_SCORE_H"); return e ? atoi(e) : 0; }();  // tuning knob
   static const int geom = [] { const char* e = getenv("PR_SCORE_GEOM"); return e ? atoi(e) : 1; }();   // 0: round-1 whole-tile split
@@ -724,10 +734,10 @@ int launch_score(CloudView cloud, size_t n_per_cloud, int n_clouds, size_t cloud
     if (forced_h == 4 && H > 4) { warps_h = warps_h * H / 4 > kScoreWarps ? kScoreWarps : warps_h * H / 4; H = 4; }
     const float* X = cloud.x; const float* Y = cloud.y; const float* Z = cloud.z;
     switch (H) {
-      case 1: launch_score_h<1>(X, Y, Z, n_per_cloud, cloud_stride, n_clouds, hyps, K, k, k + take, warps_h, t, dot_order, counts, num_sms, s, range_mode, st); break;
-      case 2: launch_score_h<2>(X, Y, Z, n_per_cloud, cloud_stride, n_clouds, hyps, K, k, k + take, warps_h, t, dot_order, counts, num_sms, s, range_mode, st); break;
-      case 4: launch_score_h<4>(X, Y, Z, n_per_cloud, cloud_stride, n_clouds, hyps, K, k, k + take, warps_h, t, dot_order, counts, num_sms, s, range_mode, st); break;
-      default: launch_score_h<8>(X, Y, Z, n_per_cloud, cloud_stride, n_clouds, hyps, K, k, k + take, warps_h, t, dot_order, counts, num_sms, s, range_mode, st); break;
+      case 1: launch_score_h<1>(X, Y, Z, n_per_cloud, cloud_stride, n_clouds, hyps, K, k, k + take, warps_h, t, dot_order, counts, num_sms, s, range_mode, st, chained); break;
+      case 2: launch_score_h<2>(X, Y, Z, n_per_cloud, cloud_stride, n_clouds, hyps, K, k, k + take, warps_h, t, dot_order, counts, num_sms, s, range_mode, st, chained); break;
+      case 4: launch_score_h<4>(X, Y, Z, n_per_cloud, cloud_stride, n_clouds, hyps, K, k, k + take, warps_h, t, dot_order, counts, num_sms, s, range_mode, st, chained); break;
+      default: launch_score_h<8>(X, Y, Z, n_per_cloud, cloud_stride, n_clouds, hyps, K, k, k + take, warps_h, t, dot_order, counts, num_sms, s, range_mode, st, chained); break;
     }
     k += take;
     ++launches;
@@ -1107,8 +1117,8 @@ __global__ void __launch_bounds__(256, 4) refit_kernel(const float* __restrict__
                                                        int model_index, float t, double scale, RefitOut* __restrict__ out,
                                                        size_t cloud_stride, int K, const int32_t* __restrict__ model_idx_arr,
                                                        const double* __restrict__ scale_arr, RoundState* st, ChainTail tail) {
+  pdl_wait();  // returns at once unless launched as a programmatic dependent (queued rounds, batch path)
   if (st != nullptr) {  // peel loop without the host: size and winning draw of this round live on the device
-    pdl_wait();
     if (st->stop || st->best < 0) return;
     n = (size_t)st->n_local;
     model_index = st->best;
@@ -1244,14 +1254,21 @@ void launch_refit(CloudView cloud, size_t n, const float4* hyps, const int4* sam
 
 void launch_refit_batch(CloudView clouds, size_t n_per, size_t cloud_stride, int n_clouds, const float4* hyps,
                         const int4* sample_pts, int K, const int32_t* model_idx, float t, int dot_order,
-                        const double* scales, RefitOut* outs, cudaStream_t s) {
+                        const double* scales, RefitOut* outs, cudaStream_t s, bool chained) {
   if (n_clouds <= 0) return;
   size_t nvec = (n_per + 3) / 4;
   unsigned bx = (unsigned)((nvec + 255) / 256);
   if (bx > 8) bx = 8;
   if (bx < 1) bx = 1;
   dim3 grid(bx, (unsigned)n_clouds);
-  if (dot_order == 1)
+  if (chained) {
+    if (dot_order == 1)
+      launch_chained(refit_kernel<1>, grid, dim3(256), 0, s, clouds.x, clouds.y, clouds.z, n_per, hyps, sample_pts, 0, t, 1.0, outs, cloud_stride, K,
+                     model_idx, scales, (RoundState*)nullptr, ChainTail());
+    else
+      launch_chained(refit_kernel<0>, grid, dim3(256), 0, s, clouds.x, clouds.y, clouds.z, n_per, hyps, sample_pts, 0, t, 1.0, outs, cloud_stride, K,
+                     model_idx, scales, (RoundState*)nullptr, ChainTail());
+  } else if (dot_order == 1)
     refit_kernel<1><<<grid, 256, 0, s>>>(clouds.x, clouds.y, clouds.z, n_per, hyps, sample_pts, 0, t, 1.0, outs, cloud_stride, K, model_idx, scales, nullptr, ChainTail());
   else
     refit_kernel<0><<<grid, 256, 0, s>>>(clouds.x, clouds.y, clouds.z, n_per, hyps, sample_pts, 0, t, 1.0, outs, cloud_stride, K, model_idx, scales, nullptr, ChainTail());

@@ -108,14 +108,18 @@ void launch_gather_samples(CloudView cloud, long long first, size_t n, const int
 void launch_gather_models(CloudView cloud, const int32_t* triples, int n_models, int4* sample_pts, float4* hyps, int32_t* good,
                           const RoundState* st, cudaStream_t s);
 // K1b: plane through each sample triple, PCL op order, no contraction; NaN plane + good = 0 when degenerate.
-void launch_models(const int4* sample_pts, int n_models_total, float4* hyps, int32_t* good, cudaStream_t s);
+// counts_to_clear / flag_to_clear (optional): zeroed on the way (one entry per model / one int), so that the scoring launch
+// that follows needs no separate memset; chained: launched as a programmatic dependent of the kernel before it.
+void launch_models(const int4* sample_pts, int n_models_total, float4* hyps, int32_t* good, cudaStream_t s,
+                   int32_t* counts_to_clear = nullptr, int* flag_to_clear = nullptr, bool chained = false);
 
 // K2: counts[c * K + k] += |{ i in cloud c : |hyp[c*K+k] . (p_i, 1)| < t }|.  counts must be zeroed.
 // Returns the number of kernel launches it made (K is cut into launches that fill their lane slots).
 // st (single cloud only): the cloud size is st->n_local, read on the device (n_per_cloud is then only an upper bound), and
 // the launch does nothing once st->stop is set.
 int launch_score(CloudView cloud, size_t n_per_cloud, int n_clouds, size_t cloud_stride, const float4* hyps,
-                 int K, float t, int dot_order, int32_t* counts, int num_sms, cudaStream_t s, const RoundState* st = nullptr);
+                 int K, float t, int dot_order, int32_t* counts, int num_sms, cudaStream_t s, const RoundState* st = nullptr,
+                 bool chained = false);
 
 // Hierarchical scorer: Morton-sorted copy of a cloud, per-32-point-block boxes, culled scoring with counts
 // identical to launch_score.  keys / vals: 2*n uint32 each; temp: sort_temp_bytes(n); bounds: 2 float4 per block.
@@ -140,7 +144,7 @@ void launch_refit_pcl_float(CloudView cloud, const int32_t* idx, const long long
 // K3 for a batch: cloud c refits hypothesis c * K + model_idx[c] (skipped when negative) with scale 2^s_c.
 void launch_refit_batch(CloudView clouds, size_t n_per, size_t cloud_stride, int n_clouds, const float4* hyps,
                         const int4* sample_pts, int K, const int32_t* model_idx, float t, int dot_order,
-                        const double* scales, RefitOut* outs, cudaStream_t s);
+                        const double* scales, RefitOut* outs, cudaStream_t s, bool chained = false);
 
 // K5: stable partition by the inlier predicate of `plane`: remaining points -> dst (NaN re-padded),
 // inlier positions -> inl_cur, their original indices -> inl_orig.  totals[0] = remaining, totals[1] = inliers.
@@ -267,8 +271,9 @@ void launch_finish(RoundState* st, const float4* hyps, const int32_t* triples, c
 
 // ---- batch of small clouds without the host in the loop (score-all mode; pr_chain.cu) ----------------------------------
 // best[c] = computeModel's winner among cloud c's K draws (-1 + *any_bad when a degenerate sample needs PCL's redraw).
+// refit_to_clear (optional): cloud c's moments are zeroed on the way (the refit pass accumulates into them).
 void launch_batch_replay(const int32_t* counts, const int32_t* good, int K, int n_clouds, int32_t* best, int32_t* best_count, int* any_bad,
-                         cudaStream_t s);
+                         RefitOut* refit_to_clear, cudaStream_t s);
 // raw[c] = hyps[c * K + best[c]]; refined[c] = closed-form plane from refit[c] on the 2^-scale_exp[c] grid (or raw[c]).
 void launch_batch_finish(const float4* hyps, int K, const int32_t* best, const RefitOut* refit, const int32_t* scale_exp, int optimize,
                          int n_clouds, float4* raw, float4* refined, cudaStream_t s);

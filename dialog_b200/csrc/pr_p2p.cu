@@ -83,6 +83,7 @@ __device__ __forceinline__ bool p2p_signal_and_wait(const P2PView& v, size_t fla
 // rank), without consuming an epoch, so two exchanges that use the same buffer always have a completed one between them.
 __device__ __forceinline__ bool p2p_enter(const RoundState* st, const unsigned long long* epoch_ctr, const unsigned* err,
                                           unsigned long long* epoch) {
+  if (st != nullptr) pdl_wait();  // queued rounds launch their kernels with programmatic dependent launch (pr_chain_dev.cuh)
   if (st != nullptr && st->stop) return false;
   if (*reinterpret_cast<const volatile unsigned*>(err)) return false;  // an earlier exchange timed out: do not wait 20 s again
   *epoch = *epoch_ctr + 1ull;
@@ -190,29 +191,45 @@ __global__ void __launch_bounds__(kP2PThreads) p2p_samples_kernel(P2PView v, con
 void launch_p2p_allreduce_i32(const P2PView& v, const int32_t* src, size_t n, size_t slot_off, size_t buffer_bytes, size_t slot_stride,
                               size_t flag_off, unsigned long long* epoch_ctr, int32_t* dst, unsigned* err, cudaStream_t s, RoundState* st,
                               unsigned long long* wait_ns, const P2PTail* tail) {
-  p2p_allreduce_kernel<int32_t><<<1, kP2PThreads, 0, s>>>(v, src, n, slot_off, buffer_bytes, slot_stride, flag_off, epoch_ctr, dst, err, st,
-                                                          wait_ns, tail ? *tail : P2PTail());
+  if (st != nullptr)
+    launch_chained(p2p_allreduce_kernel<int32_t>, dim3(1), dim3(kP2PThreads), 0, s, v, src, n, slot_off, buffer_bytes, slot_stride, flag_off, epoch_ctr,
+                   dst, err, st, wait_ns, tail ? *tail : P2PTail());
+  else
+    p2p_allreduce_kernel<int32_t><<<1, kP2PThreads, 0, s>>>(v, src, n, slot_off, buffer_bytes, slot_stride, flag_off, epoch_ctr, dst, err, st,
+                                                            wait_ns, tail ? *tail : P2PTail());
 }
 
 void launch_p2p_allreduce_i64(const P2PView& v, const long long* src, size_t n, size_t slot_off, size_t buffer_bytes, size_t slot_stride,
                               size_t flag_off, unsigned long long* epoch_ctr, long long* dst, unsigned* err, cudaStream_t s, RoundState* st,
                               unsigned long long* wait_ns, const P2PTail* tail) {
-  p2p_allreduce_kernel<long long><<<1, kP2PThreads, 0, s>>>(v, src, n, slot_off, buffer_bytes, slot_stride, flag_off, epoch_ctr, dst, err, st,
-                                                            wait_ns, tail ? *tail : P2PTail());
+  if (st != nullptr)
+    launch_chained(p2p_allreduce_kernel<long long>, dim3(1), dim3(kP2PThreads), 0, s, v, src, n, slot_off, buffer_bytes, slot_stride, flag_off,
+                   epoch_ctr, dst, err, st, wait_ns, tail ? *tail : P2PTail());
+  else
+    p2p_allreduce_kernel<long long><<<1, kP2PThreads, 0, s>>>(v, src, n, slot_off, buffer_bytes, slot_stride, flag_off, epoch_ctr, dst, err, st,
+                                                              wait_ns, tail ? *tail : P2PTail());
 }
 
 void launch_p2p_allgather_i64(const P2PView& v, const long long* src, size_t n, size_t slot_off, size_t buffer_bytes, size_t slot_stride,
                               size_t flag_off, unsigned long long* epoch_ctr, long long* dst, unsigned* err, cudaStream_t s, RoundState* st,
                               unsigned long long* wait_ns, const P2PTail* tail) {
-  p2p_allgather_kernel<long long><<<1, kP2PThreads, 0, s>>>(v, src, n, slot_off, buffer_bytes, slot_stride, flag_off, epoch_ctr, dst, err, st,
-                                                            wait_ns, tail ? *tail : P2PTail());
+  if (st != nullptr)
+    launch_chained(p2p_allgather_kernel<long long>, dim3(1), dim3(kP2PThreads), 0, s, v, src, n, slot_off, buffer_bytes, slot_stride, flag_off,
+                   epoch_ctr, dst, err, st, wait_ns, tail ? *tail : P2PTail());
+  else
+    p2p_allgather_kernel<long long><<<1, kP2PThreads, 0, s>>>(v, src, n, slot_off, buffer_bytes, slot_stride, flag_off, epoch_ctr, dst, err, st,
+                                                              wait_ns, tail ? *tail : P2PTail());
 }
 
 void launch_p2p_samples(const P2PView& v, CloudView cloud, long long first, size_t n, const int32_t* triples, int n_samples,
                         size_t sp_off, size_t buffer_bytes, size_t flag_off, unsigned long long* epoch_ctr, int4* dst, unsigned* err,
                         cudaStream_t s, const RoundState* st, unsigned long long* wait_ns, const P2PTail* tail) {
-  p2p_samples_kernel<<<1, kP2PThreads, 0, s>>>(v, cloud.x, cloud.y, cloud.z, first, n, triples, n_samples, sp_off, buffer_bytes, flag_off,
-                                              epoch_ctr, dst, err, st, wait_ns, tail ? *tail : P2PTail());
+  if (st != nullptr)
+    launch_chained(p2p_samples_kernel, dim3(1), dim3(kP2PThreads), 0, s, v, cloud.x, cloud.y, cloud.z, first, n, triples, n_samples, sp_off,
+                   buffer_bytes, flag_off, epoch_ctr, dst, err, st, wait_ns, tail ? *tail : P2PTail());
+  else
+    p2p_samples_kernel<<<1, kP2PThreads, 0, s>>>(v, cloud.x, cloud.y, cloud.z, first, n, triples, n_samples, sp_off, buffer_bytes, flag_off,
+                                                epoch_ctr, dst, err, st, wait_ns, tail ? *tail : P2PTail());
 }
 
 }  // namespace pr
