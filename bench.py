@@ -52,6 +52,8 @@ def parse_args():
     ap.add_argument("--planes", type=int, default=20)
     ap.add_argument("--cpu-sample-hyps", type=int, default=512)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--timeline-out", default=None,
+                    help="write every rank's per-round kernel stamps of the last timed step (device-resident loop) to this JSON file")
     ap.add_argument("--scorer", default="brute", choices=["brute", "hier"],
                     help="brute = the FP32-FMA-bound kernel the roofline is reported for (default); hier = same counts "
                          "through the bounding-box culled scorer")
@@ -668,7 +670,9 @@ def main():
     peak_tf = pr.measure_ffma_peak()
     for _ in range(args.warmup):
         ex = pr.extract_planes(prm, want_indices=False)
-    pr.profile_enable(True)
+    # No events between the kernels of the timed steps (an event between two kernels of a round would keep the second
+    # from being set up while the first drains): the kernels of the device-resident loop stamp %globaltimer themselves
+    # (pr_profile.loop_ms), which is where the roofline's kernel time comes from.
     pr.profile_reset()
     clocks = ClockSampler(local_rank)
     barrier()
@@ -682,11 +686,25 @@ def main():
         ex = pr.extract_planes(prm, want_indices=False)
         step_ms.append(pr.timer_stop())
     barrier()
-    prof = pr.profile()
-    pr.profile_enable(False)
+    prof_t = pr.profile()
+    timeline = pr.round_timeline()
     pairs_step = pairs_of(ex)
     n_planes = len(ex.planes)
     total_ms = sum(step_ms)
+    # the same steps once more with CUDA events around every kernel class (outside the timed region: the events cost
+    # about 1 ms per step): per-class kernel times, HBM rooflines, exchange waits
+    pr.profile_enable(True)
+    pr.profile_reset()
+    ev_ms = []
+    for _ in range(args.steps):
+        pr.flush_l2()
+        barrier()
+        pr.timer_start()
+        pr.extract_planes(prm, want_indices=False)
+        ev_ms.append(pr.timer_stop())
+    barrier()
+    prof = pr.profile()
+    pr.profile_enable(False)
 
     # ---- end-to-end arm: host cloud in, coefficients + inlier index lists out, every step ----
     for _ in range(min(args.warmup, 2)):
@@ -782,6 +800,22 @@ def main():
             for a, b in zip(exh.planes, ex.planes))
     hier_total_ms = sum(hier_ms)
 
+    # ---- per-round, per-rank timeline of the last timed step (the ranks' clocks are not synchronised with each other: each
+    #      rank's stamps are relative to its own first one) ----
+    if args.timeline_out:
+        rel = [[int(v) - int(timeline[0][0]) if v else None for v in row] for row in timeline.tolist()] if len(timeline) else []
+        per_rank = [rel]
+        if world > 1:
+            per_rank = [None] * world
+            dist.all_gather_object(per_rank, rel)
+        if rank == 0:
+            with open(args.timeline_out, "w") as f:
+                json.dump({"n_gpus": world, "points_per_gpu": count, "hypotheses_per_round": args.hyps,
+                           "stages": list(D.LOOP_STAGE_NAMES) + ["record_written"],
+                           "unit": "ns since the rank's own first stamp (the GPUs' %globaltimer values are not aligned with each "
+                                   "other); null: the round has no such stage",
+                           "ranks": per_rank}, f)
+
     # ---- per-rank time spent inside the exchange kernels waiting for the peers (lag of the slowest rank + NVLink round trip) ----
     waits = None
     if world > 1:
@@ -805,10 +839,18 @@ def main():
         e2e_value = pairs_step / (e2e_total_ms / args.steps * 1e-3)
         peaks = measured_peaks()
         hbm_peak = peaks["hbm_gbs"] if peaks else 6650.0
-        score_tf = 6.0 * prof.pairs_scored / (prof.ms_score * 1e-3) / 1e12 if prof.ms_score > 0 else None
-        launches = (prof.launches_stage + prof.launches_models + prof.launches_score + prof.launches_refit +
-                    prof.launches_compact + prof.launches_other)
+        # scoring time inside the timed region: device stamps (start of K2 to start of the kernel after it) when the
+        # rounds ran in the device-resident loop, else the event pass
+        loop_ms = list(prof_t.loop_ms)
+        stamped = prof_t.loop_rounds > 0 and loop_ms[3] > 0
+        score_ms_timed = loop_ms[3] if stamped else prof.ms_score
+        score_pairs = prof_t.pairs_scored if stamped else prof.pairs_scored
+        score_tf = 6.0 * score_pairs / (score_ms_timed * 1e-3) / 1e12 if score_ms_timed > 0 else None
+        score_tf_events = 6.0 * prof.pairs_scored / (prof.ms_score * 1e-3) / 1e12 if prof.ms_score > 0 else None
+        launches = (prof_t.launches_stage + prof_t.launches_models + prof_t.launches_score + prof_t.launches_refit +
+                    prof_t.launches_compact + prof_t.launches_other)
         kernel_ms = prof.ms_models + prof.ms_score + prof.ms_refit + prof.ms_compact
+        ev_ms_per_step = sum(ev_ms) / len(ev_ms)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -838,15 +880,35 @@ def main():
                 "peak_source": "FFMA2-only kernel timed live on this GPU (MEASURED_PEAKS.json has no FP32 figure; "
                                "nominal 148 SM x 128 lanes x 2 x 1.965 GHz = 74.4)",
                 "algorithmic": "6 FLOP (3 FMA) per point-hypothesis x points x hypotheses per launch",
-                "ms_in_timed_region": prof.ms_score, "share_of_kernel_time": prof.ms_score / kernel_ms if kernel_ms else None},
+                "ms_in_timed_region": score_ms_timed,
+                "timing": ("%globaltimer stamps taken by the kernels themselves inside the timed region: start of the scoring "
+                           "launch to start of the kernel that follows it (the kernel plus one hand-over), summed over the "
+                           "rounds of the timed steps") if stamped else "CUDA events around the scoring launches (event pass)",
+                "share_of_step": score_ms_timed / total_ms if total_ms else None,
+                "frac_cuda_events": (score_tf_events / peak_tf) if score_tf_events and peak_tf else None,
+                "frac_cuda_events_note": "the same launches timed with CUDA events on the launching stream in the event pass "
+                                         "(same steps run again outside the timed region)",
+                "share_of_kernel_time": prof.ms_score / kernel_ms if kernel_ms else None},
             "roofline_hbm": dict(hbm_block(prof, hbm_peak),
                                  peak_source="MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
                                  note="averages over the 20 shrinking rounds of the 10M-point extraction (the later rounds are "
                                       "launch-latency bound); single_launch_100M below is the kernel at the north-star scene size"),
+            "device_loop_ms_per_step": dict(
+                {nm: loop_ms[i] / args.steps for i, nm in enumerate(D.LOOP_STAGE_NAMES)},
+                rounds_per_step=prof_t.loop_rounds / args.steps,
+                rounds_total=sum(loop_ms) / args.steps,
+                step_minus_rounds=ms_per_step - sum(loop_ms) / args.steps,
+                note="timed region, this rank: %globaltimer at the start of each kernel of a round (after its predecessor "
+                     "completed) and when the round's record was written; a stage is its kernel plus the hand-over to the "
+                     "next one, so the stages add up to the rounds' device time and step_minus_rounds is what the host "
+                     "adds (first launch, last record, the final sync)") if stamped else None,
             "kernel_ms_per_step": {"models_draw": prof.ms_models / args.steps, "score": prof.ms_score / args.steps,
                                    "refit": prof.ms_refit / args.steps, "compact": prof.ms_compact / args.steps,
                                    "other": prof.ms_other / args.steps,
-                                   "step_minus_kernels": ms_per_step - (kernel_ms + prof.ms_other) / args.steps},
+                                   "event_pass_ms_per_step": ev_ms_per_step,
+                                   "step_minus_kernels": ev_ms_per_step - (kernel_ms + prof.ms_other) / args.steps,
+                                   "note": "event pass (outside the timed region): CUDA events around every kernel class; "
+                                           "step_minus_kernels is against that pass's own step time"},
             "round_loop": "device-resident (PR_LOOP_AUTO): draws, computeModel's decision, closed-form refit and the stop rule run "
                           "as kernels; the host reads one record per round",
             "clocks": clock_info,

@@ -29,7 +29,7 @@ SYMBOLS = [
     "plane_ransac_cloud_size", "plane_ransac_score", "plane_ransac_segment_one", "plane_ransac_extract_planes",
     "plane_ransac_plane_points", "plane_ransac_set_round_loop", "plane_ransac_remaining", "plane_ransac_reabsorb", "plane_ransac_estimate_normals", "plane_ransac_cluster_filter", "plane_ransac_restage_remaining", "plane_ransac_set_cloud_batch", "plane_ransac_segment_batch", "plane_ransac_segment_batch_lists",
     "plane_ransac_comm_unique_id", "plane_ransac_comm_init", "plane_ransac_comm_p2p_enabled", "plane_ransac_shard_info",
-    "plane_ransac_load_pcd", "plane_ransac_host_alloc", "plane_ransac_host_free", "plane_ransac_host_register", "plane_ransac_host_unregister", "plane_ransac_profile_enable", "plane_ransac_profile_reset", "plane_ransac_profile_get",
+    "plane_ransac_load_pcd", "plane_ransac_host_alloc", "plane_ransac_host_free", "plane_ransac_host_register", "plane_ransac_host_unregister", "plane_ransac_profile_enable", "plane_ransac_profile_reset", "plane_ransac_profile_get", "plane_ransac_round_timeline",
     "plane_ransac_timer_start", "plane_ransac_timer_stop", "plane_ransac_measure_ffma_peak", "plane_ransac_measure_copy_bw", "plane_ransac_flush_l2",
     "plane_ransac_host_draw_triples", "plane_ransac_host_draw_triples_parallel", "plane_ransac_host_replay", "plane_ransac_host_shard_range",
     "plane_ransac_host_plane_from_moments", "plane_ransac_host_plane_from_pcl_float_sums", "plane_ransac_host_rand_edges",
@@ -68,6 +68,10 @@ class PrSegmentInfo(C.Structure):
     ]
 
 
+LOOP_STAGES = 9  # PR_LOOP_STAGES
+LOOP_STAGE_NAMES = ("draw", "draw_resolve", "models", "score", "decide", "refit", "finish", "peel", "advance")
+
+
 class PrProfile(C.Structure):
     _fields_ = [(n, C.c_double) for n in ("ms_stage", "ms_models", "ms_score", "ms_refit", "ms_compact", "ms_other")] + \
                [(n, C.c_longlong) for n in ("launches_stage", "launches_models", "launches_score", "launches_refit",
@@ -75,7 +79,8 @@ class PrProfile(C.Structure):
                                             "points_compact", "bytes_compact", "bytes_refit")] + \
                [(n, C.c_double) for n in ("host_ms_sampling", "host_ms_replay", "host_ms_wait", "host_ms_total")] + \
                [(n, C.c_longlong) for n in ("points_kept", "points_peeled")] + \
-               [("p2p_wait_ms", C.c_double * 4), ("p2p_exchanges", C.c_longlong * 4)]
+               [("p2p_wait_ms", C.c_double * 4), ("p2p_exchanges", C.c_longlong * 4)] + \
+               [("loop_ms", C.c_double * LOOP_STAGES), ("loop_rounds", C.c_longlong)]
 
 
 class PlaneRansacError(RuntimeError):
@@ -134,6 +139,7 @@ def load():
     L.plane_ransac_profile_enable.argtypes = [vp, C.c_int]
     L.plane_ransac_profile_reset.argtypes = [vp]
     L.plane_ransac_profile_get.argtypes = [vp, C.POINTER(PrProfile)]
+    L.plane_ransac_round_timeline.argtypes = [vp, vp, sz, C.POINTER(sz)]
     L.plane_ransac_timer_start.argtypes = [vp]
     L.plane_ransac_timer_stop.argtypes = [vp, C.POINTER(C.c_double)]
     L.plane_ransac_measure_ffma_peak.argtypes = [vp, C.POINTER(C.c_double)]

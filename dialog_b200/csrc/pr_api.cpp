@@ -192,6 +192,7 @@ struct plane_ransac_ctx {
   DevBuf<int32_t> d_batch_tri;
   size_t batch_tri_dev_valid = 0;  // number of triple entries of batch_tri that are on the device
   std::vector<int32_t> batch_tri;  // the K triples every cloud of the batch draws (same size, same seed)
+  std::vector<unsigned long long> timeline;  // last extract call: kStampSlots stamps per device-loop round
   size_t batch_tri_n = 0;
   unsigned batch_tri_seed = 0;
 
@@ -1297,6 +1298,18 @@ int run_chain(plane_ransac_ctx* c, const pr_params* prm, PeelCursor& cur, float*
       c->prof.points_peeled += rec.n_inl_local;
     }
     if (infos) infos[cur.planes] = inf;
+    if (rec.t[pr::kStampEnd] != 0ull) {
+      // kernel-to-kernel times of the round from the device's own stamps (stages a round does not have stay 0)
+      static_assert(pr::kStampEnd == PR_LOOP_STAGES, "pr_profile.loop_ms has one entry per stage");
+      unsigned long long next = rec.t[pr::kStampEnd];
+      for (int i = pr::kStampEnd - 1; i >= 0; --i) {
+        if (rec.t[i] == 0ull) continue;
+        if (next > rec.t[i]) c->prof.loop_ms[i] += (double)(next - rec.t[i]) * 1e-6;
+        next = rec.t[i];
+      }
+      ++c->prof.loop_rounds;
+      c->timeline.insert(c->timeline.end(), rec.t, rec.t + pr::kStampSlots);
+    }
     if (!rec.accepted) {
       stop_seen = true;
       *stopped = true;
@@ -1827,6 +1840,7 @@ int plane_ransac_extract_planes(plane_ransac_ctx* c, const pr_params* prm, float
   };
   int handed_back = 0;
   bool finished = false;
+  c->timeline.clear();
   while (!finished && cur.planes < prm->max_planes) {
     if (chain_eligible(c, prm, cur.n_global) && handed_back < 2) {
       bool stopped = false, back = false;
@@ -2689,6 +2703,14 @@ int plane_ransac_profile_get(plane_ransac_ctx* c, pr_profile* out) {
       out->p2p_exchanges[ch] = (long long)w[2 * ch + 1];
     }
   }
+  return PR_OK;
+}
+
+int plane_ransac_round_timeline(plane_ransac_ctx* c, unsigned long long* stamps, size_t cap_rounds, size_t* n_rounds) {
+  PR_TRY(check_ctx(c));
+  const size_t rounds = c->timeline.size() / pr::kStampSlots;
+  if (n_rounds) *n_rounds = rounds;
+  if (stamps) std::memcpy(stamps, c->timeline.data(), std::min(rounds, cap_rounds) * pr::kStampSlots * sizeof(unsigned long long));
   return PR_OK;
 }
 

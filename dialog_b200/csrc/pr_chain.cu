@@ -40,6 +40,7 @@ __global__ void __launch_bounds__(256) draw_scatter_kernel(const uint32_t* __res
                                                            unsigned* __restrict__ tickets) {
   pdl_wait();
   if (st->stop) return;
+  chain_stamp(st, kStampDraw);
   const size_t stride = (size_t)gridDim.x * blockDim.x, i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   for (size_t i = i0; i < scratch_words; i += stride) scratch[i] = 0ull;
   for (size_t i = i0; i < (size_t)K; i += stride) counts[i] = 0;
@@ -74,6 +75,7 @@ __global__ void __launch_bounds__(kResolveThreads) draw_resolve_kernel(RoundStat
   __shared__ int s_distinct;
   pdl_wait();
   if (st->stop) return;
+  chain_stamp(st, kStampResolve);
   if (st->n_global < 3) {  // getSamples: "Can not select 0 unique points out of N": segment() returns no model
     if (threadIdx.x == 0) {
       st->stop = 1;
@@ -146,6 +148,7 @@ __global__ void __launch_bounds__(kChainBlock) replay_kernel(const int32_t* __re
                                                              RoundState* st, RoundRecord* rec) {
   pdl_wait();
   if (st->stop) return;
+  chain_stamp(st, kStampDecide);
   chain_replay_block(counts, good, K, st, rec);
 }
 
@@ -156,6 +159,7 @@ __global__ void finish_kernel(RoundState* st, const float4* __restrict__ hyps, c
                               const RefitOut* __restrict__ refit, int optimize, int scale_exp, int n_draws, RoundRecord* rec) {
   pdl_wait();
   if (threadIdx.x != 0 || st->stop) return;
+  chain_stamp(st, kStampFinish);
   long long m[16];
   for (int i = 0; i < 16; ++i) m[i] = refit->m[i];
   const float pivot[3] = {refit->pivot[0], refit->pivot[1], refit->pivot[2]};

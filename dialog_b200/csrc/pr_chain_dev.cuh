@@ -21,6 +21,16 @@ namespace pr {
 // statement) until the predecessor has completed and its writes are visible.  PR_PDL=0 launches them plainly.
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
+__device__ __forceinline__ unsigned long long chain_now() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// call right after pdl_wait(): the predecessor of this kernel has just completed
+__device__ __forceinline__ void chain_stamp(const RoundState* st, int slot) {
+  if (st != nullptr && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0) const_cast<RoundState*>(st)->t[slot] = chain_now();
+}
+
 template <typename... P, size_t... I>
 inline cudaError_t launch_chained_impl(void (*kernel)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, std::tuple<P...>& params,
                                        std::index_sequence<I...>) {
@@ -163,6 +173,11 @@ __device__ __forceinline__ void chain_advance(RoundState* st, const long long* t
     st->stop = 1;
   }
   rec->stop = st->stop;
+  for (int i = 0; i < kStampEnd; ++i) {
+    rec->t[i] = st->t[i];
+    st->t[i] = 0ull;
+  }
+  rec->t[kStampEnd] = chain_now();
   __threadfence_system();  // the record may live in mapped host memory: everything above lands before `ran`
   rec->ran = 1;
 }

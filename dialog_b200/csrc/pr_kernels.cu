@@ -365,6 +365,7 @@ __global__ void __launch_bounds__(128) gather_models_kernel(const float* __restr
                                                             int32_t* __restrict__ good, const RoundState* __restrict__ st) {
   pdl_wait();
   if (st->stop) return;
+  chain_stamp(st, kStampModels);
   const long long n = st->n_local;
   int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n_models) return;
@@ -484,6 +485,7 @@ __global__ void __launch_bounds__(kScoreThreads, H <= 4 ? 4 : 2)
   if (st != nullptr) {
     // peel loop without the host (range mode): the even split of launch_score_h, from the cloud size on the device
     if (st->stop) return;
+    if (k_begin == 0) chain_stamp(st, kStampScore);
     const long long unit = 128ll * (kScoreWarps / warps_h);
     n_padded = (st->n_local + unit - 1) / unit * unit;
     long long per = (n_padded + gridDim.x - 1) / gridDim.x;
@@ -1120,6 +1122,7 @@ __global__ void __launch_bounds__(256, 4) refit_kernel(const float* __restrict__
   pdl_wait();  // returns at once unless launched as a programmatic dependent (queued rounds, batch path)
   if (st != nullptr) {  // peel loop without the host: size and winning draw of this round live on the device
     if (st->stop || st->best < 0) return;
+    chain_stamp(st, kStampRefit);
     n = (size_t)st->n_local;
     model_index = st->best;
   }
@@ -1356,6 +1359,7 @@ __global__ void __launch_bounds__(kCompactThreads, 5)
     // for an upper bound of n
     pdl_wait();
     if (st->stop) return;
+    chain_stamp(st, kStampPeel);
     n = (size_t)st->n_local;
     pl.a = st->plane[0]; pl.b = st->plane[1]; pl.c = st->plane[2]; pl.d = st->plane[3];
     if (inl_cur) inl_cur += st->inl_off;

@@ -37,6 +37,22 @@ struct RefitOut {
 
 // ---- device-resident state of the peel loop (score-all mode): every kernel of a round reads its sizes, the winning
 // draw and the refined plane from here, so a whole extraction is queued without the host in the loop (pr_chain.cu).
+// Every kernel of a queued round notes %globaltimer once its predecessor has completed (thread 0 of block 0, right after
+// griddepcontrol.wait); the stop rule copies the stamps into the round's record with the time it ran itself.  The
+// difference of two consecutive stamps is a kernel plus the hand-over to the next one; no events, nothing on the host.
+enum {
+  kStampDraw = 0,   // sampler, parallel phase (also clears the round's accumulators)
+  kStampResolve,    // sampler, collision replay
+  kStampModels,     // sample points (+ their exchange) and computeModelCoefficients
+  kStampScore,      // K2
+  kStampDecide,     // (count exchange +) computeModel's decision
+  kStampRefit,      // K3
+  kStampFinish,     // closed-form plane as its own step: moment exchange, or rounds without the refit pass
+  kStampPeel,       // K5
+  kStampAdvance,    // remaining-count exchange + stop rule as its own step (sharded)
+  kStampEnd,        // the round's record was written
+  kStampSlots
+};
 struct RoundState {
   long long n_local;    // points of this rank's current cloud
   long long n_global;   // ... of all ranks
@@ -48,6 +64,7 @@ struct RoundState {
   int best_count;       // its inlier count
   float plane[4];       // coefficients of the round's final selection
   int pad[4];
+  unsigned long long t[kStampSlots];  // %globaltimer when each kernel of the round in flight started (kStamp*)
 };
 // What one round decided; the host reads record r once round r has run (pr_segment_info + the peel bookkeeping).
 struct RoundRecord {
@@ -65,6 +82,7 @@ struct RoundRecord {
   long long n_inl_global, n_rem_global;
   long long first_after;                  // this rank's first global index in the remaining cloud
   long long inl_off;                      // where this round's inlier lists start (this rank)
+  unsigned long long t[kStampSlots];      // RoundState::t of the round, t[kStampEnd]: when the record was written
 };
 
 // On one GPU the last block of K3 / K5 also runs the step that follows it in the host-free loop (closed-form plane /

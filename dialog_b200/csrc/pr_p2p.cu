@@ -82,9 +82,12 @@ __device__ __forceinline__ bool p2p_signal_and_wait(const P2PView& v, size_t fla
 // A kernel queued by the host-free peel loop returns at once when the loop has stopped (st->stop, the same on every
 // rank), without consuming an epoch, so two exchanges that use the same buffer always have a completed one between them.
 __device__ __forceinline__ bool p2p_enter(const RoundState* st, const unsigned long long* epoch_ctr, const unsigned* err,
-                                          unsigned long long* epoch) {
+                                          unsigned long long* epoch, int tail_kind) {
   if (st != nullptr) pdl_wait();  // queued rounds launch their kernels with programmatic dependent launch (pr_chain_dev.cuh)
   if (st != nullptr && st->stop) return false;
+  if (tail_kind != P2PTail::kNone)
+    chain_stamp(st, tail_kind == P2PTail::kModels ? kStampModels : tail_kind == P2PTail::kReplay ? kStampDecide
+                    : tail_kind == P2PTail::kFinish ? kStampFinish : kStampAdvance);
   if (*reinterpret_cast<const volatile unsigned*>(err)) return false;  // an earlier exchange timed out: do not wait 20 s again
   *epoch = *epoch_ctr + 1ull;
   return true;
@@ -97,7 +100,7 @@ __global__ void __launch_bounds__(kP2PThreads) p2p_allreduce_kernel(P2PView v, c
                                                                     T* dst, unsigned* err, RoundState* st, unsigned long long* wait_ns,
                                                                     P2PTail tail) {
   unsigned long long epoch;
-  if (!p2p_enter(st, epoch_ctr, err, &epoch)) return;
+  if (!p2p_enter(st, epoch_ctr, err, &epoch, tail.kind)) return;
   slot_off += (size_t)(epoch & 1ull) * buffer_bytes;
   for (int r = 0; r < v.n_ranks; ++r) {
     T* out = reinterpret_cast<T*>(v.peers[r] + slot_off + (size_t)v.rank * slot_stride);
@@ -134,7 +137,7 @@ __global__ void __launch_bounds__(kP2PThreads) p2p_allgather_kernel(P2PView v, c
                                                                     unsigned long long* epoch_ctr, T* __restrict__ dst, unsigned* err,
                                                                     RoundState* st, unsigned long long* wait_ns, P2PTail tail) {
   unsigned long long epoch;
-  if (!p2p_enter(st, epoch_ctr, err, &epoch)) return;
+  if (!p2p_enter(st, epoch_ctr, err, &epoch, tail.kind)) return;
   slot_off += (size_t)(epoch & 1ull) * buffer_bytes;
   for (int r = 0; r < v.n_ranks; ++r) {
     T* out = reinterpret_cast<T*>(v.peers[r] + slot_off + (size_t)v.rank * slot_stride);
@@ -161,7 +164,7 @@ __global__ void __launch_bounds__(kP2PThreads) p2p_samples_kernel(P2PView v, con
                                                                   int4* __restrict__ dst, unsigned* err, const RoundState* st,
                                                                   unsigned long long* wait_ns, P2PTail tail) {
   unsigned long long epoch;
-  if (!p2p_enter(st, epoch_ctr, err, &epoch)) return;
+  if (!p2p_enter(st, epoch_ctr, err, &epoch, tail.kind)) return;
   if (st != nullptr) {
     first = st->first;
     n = (size_t)st->n_local;

@@ -19,7 +19,7 @@ import numpy as np
 
 from . import _lib
 from ._lib import (DOT_FMA, DOT_PCL_SSE2, REFIT_FIXED, REFIT_PCL_FLOAT, SCORER_BRUTE, SCORER_HIER, PlaneRansacError, PrParams, PrProfile,  # noqa: F401
-                   PrSegmentInfo)
+                   PrSegmentInfo, LOOP_STAGE_NAMES)
 
 
 def make_params(distance_threshold: float = 0.1, max_iterations: int = 50, min_plane_size: int = 500,
@@ -369,6 +369,15 @@ class PlaneRansac:
         p = PrProfile()
         _lib.check(self._L.plane_ransac_profile_get(self._h, C.byref(p)))
         return p
+
+    def round_timeline(self) -> np.ndarray:
+        """(rounds, LOOP_STAGES + 1) uint64 %globaltimer stamps of the last extract_planes call's device-loop rounds."""
+        n = C.c_size_t(0)
+        _lib.check(self._L.plane_ransac_round_timeline(self._h, None, 0, C.byref(n)))
+        out = np.zeros((n.value, _lib.LOOP_STAGES + 1), dtype=np.uint64)
+        if n.value:
+            _lib.check(self._L.plane_ransac_round_timeline(self._h, out.ctypes.data, n.value, C.byref(n)))
+        return out
 
     def timer_start(self):
         _lib.check(self._L.plane_ransac_timer_start(self._h))

@@ -105,6 +105,7 @@ typedef struct {
   long long n_cloud;    /* points in the cloud of this round (global when sharded)              */
 } pr_segment_info;
 
+#define PR_LOOP_STAGES 9
 /* Device time per kernel class, accumulated while profiling is enabled (CUDA events on the
  * context's stream), and launch counts since the last plane_ransac_profile_reset. */
 typedef struct {
@@ -131,6 +132,14 @@ typedef struct {
    * NVLink round trip — and the number of exchanges, since the last profile_reset */
   double p2p_wait_ms[4];
   long long p2p_exchanges[4];
+  /* device-resident round loop: time from the start of one kernel of a round to the start of the next (the kernel plus
+   * the hand-over), from %globaltimer stamps the kernels take themselves — no events, always accumulated, also while
+   * profiling is off.  [0] sampler, parallel phase  [1] sampler, collision replay  [2] sample points (+ exchange) and
+   * models  [3] scoring  [4] (count exchange +) computeModel's decision  [5] refit moments  [6] closed-form plane as its
+   * own step (moment exchange / no refit pass)  [7] peel  [8] remaining-count exchange + stop rule (sharded).  Their
+   * sum is the device time of loop_rounds rounds. */
+  double loop_ms[PR_LOOP_STAGES];
+  long long loop_rounds;
 } pr_profile;
 
 /* ---- lifetime ---------------------------------------------------------------------------- */
@@ -313,6 +322,10 @@ int plane_ransac_load_pcd(const char* path, pr_point** points, size_t* n_points)
 int plane_ransac_profile_enable(plane_ransac_ctx* ctx, int on);
 int plane_ransac_profile_reset(plane_ransac_ctx* ctx);
 int plane_ransac_profile_get(plane_ransac_ctx* ctx, pr_profile* out);
+/* Rounds the last plane_ransac_extract_planes call ran in the device-resident loop, in order: PR_LOOP_STAGES + 1
+ * %globaltimer values (ns) per round — when each stage of pr_profile.loop_ms started (0: the round has no such stage) and
+ * when the round's record was written.  stamps may be NULL (count only); at most cap_rounds rounds are copied. */
+int plane_ransac_round_timeline(plane_ransac_ctx* ctx, unsigned long long* stamps, size_t cap_rounds, size_t* n_rounds);
 /* Device-side stopwatch: CUDA events recorded on the context's stream (the stream every kernel and
  * copy of this library is issued on).  stop synchronises and returns the elapsed milliseconds. */
 int plane_ransac_timer_start(plane_ransac_ctx* ctx);
