@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(kResolveThreads) draw_resolve_kernel(RoundStat
   }
   __syncthreads();
   SmemFetch fetch{s_sorted, s_pre};
-  // common case: the listed ops only interact inside their position groups -> one thread per entry (pr_draw.h)
+  // common case: no listed op swaps inside the head -> every entry follows its own dependency chain, one thread each (pr_draw.h)
   int ok = 1;
   for (uint32_t i = threadIdx.x; i < n_c; i += kResolveThreads) ok = ok && draw_independent_ok(s_sorted, (int)i, fetch);
   if (__syncthreads_and(ok)) {

@@ -97,29 +97,41 @@ PR_HD void draw_resolve(const uint32_t* ops_sorted, int n_ops, int32_t* v, Fetch
   }
 }
 
-// The common case needs no sequential replay at all.  If no listed op lies in the head (b < 3) and no two distinct listed
-// ops are within 3 of each other, the listed ops only interact inside the group that shares a position q: the first op
-// of a group reads q itself, every later one reads what its predecessor s' in the group left there, which is the
-// content of head position a' = s' % 3 just before s', i.e. v[s' - 3] (s' - 3 is not a listed op, so that value is its
-// b), or a' itself for s' < 3.  draw_independent_ok tests the condition for entry i, draw_resolve_independent gives
-// entry i's value; both are evaluated by one thread per entry.
+// The common case needs no sequential replay at all.  While no listed op lies in the head (b < 3) the head position
+// a = s % 3 is only ever touched by the ops s, s - 3, s - 6, ..., so op s finds there what op s - 3 left: v[s - 3] (or a
+// itself for s < 3) — and leaves it in position b_s.  Hence the first op of a position group reads q itself and every
+// later one reads what its predecessor s' in the group left there: the FINAL value of op s' - 3.  That op is either not
+// listed (its value is its b) or listed, and then the same rule gives its value: a chain of strictly decreasing op
+// indices that only reads the values the parallel phase wrote, so every entry is evaluated by its own thread.
+// draw_independent_ok tests the condition for entry i, draw_resolve_independent gives entry i's value.
 template <class Fetch>
 PR_HD bool draw_independent_ok(const uint32_t* ops_sorted, int i, Fetch fetch) {
-  const uint32_t s = ops_sorted[i];
-  if ((uint32_t)fetch(i, s) < 3u) return false;
-  return i == 0 || s == ops_sorted[i - 1] || s - ops_sorted[i - 1] > 3u;
+  return (uint32_t)fetch(i, ops_sorted[i]) >= 3u;
 }
 
 template <class Fetch>
 PR_HD int32_t draw_resolve_independent(const uint32_t* ops_sorted, int i, Fetch fetch) {
-  const uint32_t s = ops_sorted[i];
-  const uint32_t q = (uint32_t)fetch(i, s);
-  for (int j = i - 1; j >= 0; --j) {
+  for (;;) {
+    const uint32_t s = ops_sorted[i];
+    const uint32_t q = (uint32_t)fetch(i, s);
+    int j = i - 1;
+    for (; j >= 0; --j) {
+      const uint32_t sp = ops_sorted[j];
+      if (sp != s && (uint32_t)fetch(j, sp) == q) break;  // (sp == s: a duplicate entry of this op)
+    }
+    if (j < 0) return (int32_t)q;
     const uint32_t sp = ops_sorted[j];
-    if (sp == s || (uint32_t)fetch(j, sp) != q) continue;  // a duplicate entry of this op / another group
-    return sp >= 3u ? fetch(j, sp - 3u) : (int32_t)(sp % 3u);
+    if (sp < 3u) return (int32_t)(sp % 3u);
+    const uint32_t u = sp - 3u;
+    int lo = 0, hi = j;  // first entry >= u among the entries before j
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (ops_sorted[mid] < u) lo = mid + 1;
+      else hi = mid;
+    }
+    if (lo >= j || ops_sorted[lo] != u) return fetch(j, u);  // not listed: its b
+    i = lo;
   }
-  return (int32_t)q;
 }
 
 // Parallel phase, one call per op: v[s] = b_s; ops in the head and ops whose position another op also picked are

@@ -256,6 +256,40 @@ def test_device_round_loop_equals_host_loop(O, pr, scene2, scene3, scene, n, max
         assert rem_dev.tobytes() == want.remaining.tobytes()
 
 
+def test_device_round_loop_timeline(pr, scene3):
+    """The kernels of a queued round stamp %globaltimer themselves: one row per round that ran, stages in launch order,
+    and pr_profile.loop_ms adds up to the rounds' device time — with the event profiler off."""
+    import dialog_b200 as D
+    pts = scene3.points(0, 400_000)
+    for opt in (True, False):
+        prm = D.make_params(0.1, 511, 500, 1.0, opt, 12345, 6, D.DOT_FMA)
+        pr.set_cloud(pts)
+        pr.profile_reset()
+        ex = pr.extract_planes(prm, want_indices=False)
+        tl = pr.round_timeline().astype(np.int64)
+        prof = pr.profile()
+        assert tl.shape == (len(ex.infos), D.plane_detect._lib.LOOP_STAGES + 1) and prof.loop_rounds == len(ex.infos)
+        names = list(D.LOOP_STAGE_NAMES)
+        has = ["draw", "draw_resolve", "models", "score", "decide"] + (["refit"] if opt else ["finish"]) + ["peel"]
+        total = 0
+        for r, row in enumerate(tl):
+            used = [row[names.index(nm)] for nm in has] + [row[-1]]
+            assert all(v > 0 for v in used) and all(b >= a for a, b in zip(used, used[1:])), (r, row)
+            assert all(row[i] == 0 for i, nm in enumerate(names) if nm not in has)
+            if r:
+                assert row[0] >= tl[r - 1][-1]      # rounds follow each other
+            total += int(row[-1] - row[0])
+        assert abs(sum(prof.loop_ms) - total * 1e-6) < 1e-6
+        assert prof.loop_ms[names.index("score")] > 0.3 * sum(prof.loop_ms)   # K2 dominates a round
+    pr.set_round_loop(host=True)
+    try:
+        pr.set_cloud(pts)
+        pr.extract_planes(prm, want_indices=False)
+        assert pr.round_timeline().shape[0] == 0    # host-driven rounds have no stamps
+    finally:
+        pr.set_round_loop(host=False)
+
+
 def test_device_round_loop_hands_rounds_back(O, pr, scene2):
     """Rounds the device cannot decide alone go back to the host-driven loop and give PCL's answer: duplicated points make
     degenerate samples (PCL redraws them, so more than max_iterations + 1 draws are consumed), and a small cloud with many
