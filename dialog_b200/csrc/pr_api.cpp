@@ -250,8 +250,9 @@ struct plane_ransac_ctx {
   struct PendingUpload {
     bool active = false;
     const pr_point* host = nullptr;
-    size_t n = 0, chunk = 0;
+    size_t n = 0;
     int n_chunks = 0, next = 0;
+    std::vector<size_t> off;  // chunk k = points [off[k], off[k + 1]), boundaries on whole tiles
     std::vector<cudaEvent_t> ev;
   } pend;
   PinBuf<int4> h_sample_pts;
@@ -574,8 +575,8 @@ int stage_from_device(plane_ransac_ctx* c, const float4* d_aos, size_t n, unsign
 // Stage chunk k of a queued upload on the main stream once its copy has landed.
 int stage_pending_chunk(plane_ransac_ctx* c, int k, pr::CloudView* view, size_t* n_chunk) {
   auto& u = c->pend;
-  const size_t off = (size_t)k * u.chunk;
-  const size_t cnt = std::min(u.chunk, u.n - off);
+  const size_t off = u.off[k];
+  const size_t cnt = u.off[k + 1] - off;
   const bool last = k == u.n_chunks - 1;
   pr::CloudView v = c->staged;
   v.x += off; v.y += off; v.z += off;
@@ -1634,9 +1635,38 @@ int plane_ransac_set_cloud_async(plane_ransac_ctx* c, const pr_point* pts, size_
   c->last_coeffs.clear();
   c->sorted_staged_valid = false;
   auto& u = c->pend;
-  u.n_chunks = 8;
-  u.chunk = ((n + u.n_chunks - 1) / u.n_chunks + pr::kTilePoints - 1) / pr::kTilePoints * pr::kTilePoints;
-  u.n_chunks = (int)((n + u.chunk - 1) / u.chunk);
+  // Chunk sizes grow, then shrink.  The first scoring launch can start once the first chunk has landed, so that one is
+  // small.  While scoring a chunk takes longer than copying it (one GPU: ~5.4 ms against ~3 ms for 10M points x 4096
+  // hypotheses) the device never waits for the copy again and larger chunks score more efficiently; when the copy is
+  // the slower one (eight ranks sharing the host's memory system) the call ends one chunk's scoring after the copy, so
+  // the last chunks are small again.  PR_UPLOAD_WEIGHTS=1,1,1,1,1,1,1,1 gives round 1's eight equal chunks.
+  static const std::vector<int> weights = [] {
+    std::vector<int> w;
+    if (const char* e = getenv("PR_UPLOAD_WEIGHTS")) {
+      for (const char* p = e; *p;) {
+        char* end = nullptr;
+        const long v = strtol(p, &end, 10);
+        if (end == p) break;
+        if (v > 0) w.push_back((int)v);
+        p = *end ? end + 1 : end;
+      }
+    }
+    if (w.empty()) w = {1, 2, 3, 4, 3, 2, 1};
+    return w;
+  }();
+  {
+    long long wsum = 0;
+    for (int w : weights) wsum += w;
+    const size_t tiles = (n + pr::kTilePoints - 1) / pr::kTilePoints;
+    u.off.assign(1, 0);
+    long long acc = 0;
+    for (size_t k = 0; k < weights.size(); ++k) {
+      acc += weights[k];
+      const size_t end = k + 1 == weights.size() ? n : std::min(n, (size_t)((double)tiles * (double)acc / (double)wsum) * (size_t)pr::kTilePoints);
+      if (end > u.off.back()) u.off.push_back(end);
+    }
+    u.n_chunks = (int)u.off.size() - 1;
+  }
   while ((int)u.ev.size() < u.n_chunks) {
     cudaEvent_t e = nullptr;
     PR_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -1645,7 +1675,7 @@ int plane_ransac_set_cloud_async(plane_ransac_ctx* c, const pr_point* pts, size_
   pr::launch_bbox_init(c->d_bbox.p, c->stream);
   c->prof.launches_stage += 1;
   for (int k = 0; k < u.n_chunks; ++k) {
-    const size_t off = (size_t)k * u.chunk, cnt = std::min(u.chunk, n - off);
+    const size_t off = u.off[k], cnt = u.off[k + 1] - off;
     PR_CUDA(cudaMemcpyAsync(c->aos.p + off, pts + off, cnt * sizeof(pr_point), cudaMemcpyHostToDevice, c->copy_stream));
     PR_CUDA(cudaEventRecord(u.ev[k], c->copy_stream));
   }

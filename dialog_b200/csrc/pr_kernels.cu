@@ -122,13 +122,28 @@ __global__ void __launch_bounds__(256) stage_kernel(const float4* __restrict__ a
       z[i] = CUDART_NAN_F;
     }
   }
+  // one atomic per block and bound: atomics on the same six words serialise in L2 (a few ns each), which at one per
+  // warp cost more than moving the chunk itself
+  __shared__ uint32_t s_key[6][8];
 #pragma unroll
   for (int a = 0; a < 3; ++a) {
     uint32_t l = __reduce_min_sync(0xFFFFFFFFu, lo[a]);
     uint32_t h = __reduce_max_sync(0xFFFFFFFFu, hi[a]);
     if ((threadIdx.x & 31) == 0) {
-      if (l != 0xFFFFFFFFu) atomicMin(&bbox[a], l);
-      if (h != 0u) atomicMax(&bbox[3 + a], h);
+      s_key[a][threadIdx.x >> 5] = l;
+      s_key[3 + a][threadIdx.x >> 5] = h;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 6) {
+    const bool is_min = threadIdx.x < 3;
+    uint32_t k = s_key[threadIdx.x][0];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) k = is_min ? min(k, s_key[threadIdx.x][w]) : max(k, s_key[threadIdx.x][w]);
+    if (is_min) {
+      if (k != 0xFFFFFFFFu) atomicMin(&bbox[threadIdx.x], k);
+    } else if (k != 0u) {
+      atomicMax(&bbox[threadIdx.x], k);
     }
   }
 }
@@ -257,7 +272,7 @@ void launch_translate(CloudView c, size_t n, const float centroid[3], int num_sm
 
 void launch_stage(const float4* aos, size_t n, CloudView dst, uint32_t* bbox, cudaStream_t s) {
   size_t blocks = (dst.cap + 255) / 256;
-  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (blocks > 148 * 8) blocks = 148 * 8;  // one resident wave
   stage_kernel<<<(unsigned)blocks, 256, 0, s>>>(aos, n, dst.x, dst.y, dst.z, dst.cap, bbox);
 }
 

@@ -238,9 +238,10 @@ class PlaneRansac:
         self._batch = n_clouds
         self._batch_n = n_per_cloud
 
-    def segment_batch(self, params: PrParams, want_infos: bool = True, want_lists: bool = False):
+    def segment_batch(self, params: PrParams, want_infos: bool = True, want_lists: bool = False, lists_buf: np.ndarray = None):
         """One segment() per cloud: (coeffs (n_clouds,4), n_inliers (n_clouds,), infos) and, with want_lists, a fourth
-        item: the list of per-cloud ascending inlier index arrays (views into one buffer)."""
+        item: the list of per-cloud ascending inlier index arrays (views into one buffer).  lists_buf: the caller's int32
+        buffer for the lists (a PinnedArray's .array makes the read-back a single DMA; too small: PlaneRansacError -4)."""
         nc = self._batch
         coeffs = np.zeros((nc, 4), np.float32)
         cnt = np.zeros(nc, np.int32)
@@ -250,6 +251,13 @@ class PlaneRansac:
                                                           cnt.ctypes.data_as(C.c_void_p), infos))
             return coeffs, cnt, infos
         offs = np.zeros(nc + 1, np.uintp)
+        if lists_buf is not None:
+            buf = lists_buf.reshape(-1)
+            assert buf.dtype == np.int32 and buf.flags["C_CONTIGUOUS"]
+            _lib.check(self._L.plane_ransac_segment_batch_lists(self._h, C.byref(params), coeffs.ctypes.data_as(C.c_void_p),
+                                                                cnt.ctypes.data_as(C.c_void_p), buf.ctypes.data_as(C.c_void_p), buf.size,
+                                                                offs.ctypes.data_as(C.c_void_p), infos))
+            return coeffs, cnt, infos, [buf[int(offs[k]): int(offs[k + 1])] for k in range(nc)]
         cap = max(1, self._batch_n * nc // 2)
         for _ in range(2):
             buf = np.empty(cap, np.int32)

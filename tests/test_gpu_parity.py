@@ -606,6 +606,15 @@ def test_segment_batch_matches_per_cloud_oracle(O, pr, n_clouds, n_per, max_it, 
     coeffs, cnt, infos, lists = pr.segment_batch(prm, want_lists=True)
     c2, n2, _ = pr.segment_batch(prm)                   # counts-only entry point: same planes
     assert _same_bits(c2, coeffs) and (n2 == cnt).all()
+    pin = D.PinnedArray((int(cnt.sum()) + 7,), np.int32)  # the caller's page-locked list buffer: same lists; too small: -4
+    c4, n4, _, l4 = pr.segment_batch(prm, want_lists=True, lists_buf=pin.array)
+    assert _same_bits(c4, coeffs) and all(np.array_equal(a, b) for a, b in zip(l4, lists))
+    if cnt.sum() > 8:
+        with pytest.raises(D.PlaneRansacError) as err:
+            pr.segment_batch(prm, want_lists=True, lists_buf=pin.array[: int(cnt.sum()) - 1])
+        assert err.value.code == -4
+    del l4
+    pin.free()
     pr.set_round_loop(host=True)                        # the host-driven path gives the same batch
     try:
         c3, n3, i3, l3 = pr.segment_batch(prm, want_lists=True)
