@@ -170,18 +170,38 @@ __global__ void __launch_bounds__(kP2PThreads) p2p_samples_kernel(P2PView v, con
     n = (size_t)st->n_local;
   }
   sp_off += (size_t)(epoch & 1ull) * buffer_bytes;
-  for (int s = threadIdx.x; s < n_samples; s += kP2PThreads) {
-    const long long local = (long long)triples[s] - first;
-    if (local >= 0 && local < (long long)n) {
-      const int4 val = make_int4(__float_as_int(x[local]), __float_as_int(y[local]), __float_as_int(z[local]), 0x3F800000);
-      for (int r = 0; r < v.n_ranks; ++r) reinterpret_cast<int4*>(v.peers[r] + sp_off)[s] = val;
+  // four samples per thread and pass, so that the index loads, then the 12 gathers, are in flight together (one CTA:
+  // a dependent load chain per sample would cost ~1 us each)
+  for (int base = threadIdx.x; base < n_samples; base += 4 * kP2PThreads) {
+    long long local[4];
+    float px[4], py[4], pz[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int s = base + j * kP2PThreads;
+      local[j] = s < n_samples ? (long long)triples[s] - first : -1ll;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const bool mine = local[j] >= 0 && local[j] < (long long)n;
+      px[j] = mine ? x[local[j]] : 0.0f;
+      py[j] = mine ? y[local[j]] : 0.0f;
+      pz[j] = mine ? z[local[j]] : 0.0f;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (local[j] >= 0 && local[j] < (long long)n) {
+        const int4 val = make_int4(__float_as_int(px[j]), __float_as_int(py[j]), __float_as_int(pz[j]), 0x3F800000);
+        for (int r = 0; r < v.n_ranks; ++r) reinterpret_cast<int4*>(v.peers[r] + sp_off)[base + j * kP2PThreads] = val;
+      }
     }
   }
   if (!p2p_signal_and_wait(v, flag_off, epoch, err, wait_ns)) return;
   const int4* in = reinterpret_cast<const int4*>(v.peers[v.rank] + sp_off);
+#pragma unroll 4
   for (int s = threadIdx.x; s < n_samples; s += kP2PThreads) dst[s] = __ldcg(in + s);
   if (threadIdx.x == 0) *epoch_ctr = epoch;
   if (tail.kind == P2PTail::kModels) {  // K1b in the same CTA: the models of the n_samples / 3 gathered triples
+#pragma unroll 2
     for (int k = threadIdx.x; k < n_samples / 3; k += kP2PThreads) {
       float4 h;
       const bool ok = model_from_sample(__ldcg(in + 3 * k), __ldcg(in + 3 * k + 1), __ldcg(in + 3 * k + 2), &h);
