@@ -68,7 +68,7 @@ def parse_args():
     ap.add_argument("--config4-points", type=int, default=100_000_000)
     ap.add_argument("--no-config5", action="store_true",
                     help="skip BASELINE configs[4]: 512 x N clouds of 32K points (the full 4096-cloud batch at N = 8), sharded "
-                         "by cloud id over the N ranks")
+                         "by cloud id over the N ranks; also skips the configs[1] block (1M points, rank 0)")
     ap.add_argument("--config5-clouds-per-gpu", type=int, default=512)
     return ap.parse_args()
 
@@ -548,15 +548,22 @@ def run_config5(args, torch, dist, D, local_rank, world, rank, peak_tf):
     pr.set_cloud_batch_ptr(pinned.data_ptr(), len(ids), n_per)
     for _ in range(3):
         coeffs, cnt, _ = pr.segment_batch(prm, want_infos=False)
-    pr.profile_enable(True)
-    pr.profile_reset()
     ms, e2e = [], []
-    for _ in range(5):
+    for _ in range(5):      # timed without events between the launches (they chain with programmatic dependent launch)
         pr.flush_l2()
         barrier()
         pr.timer_start()
         coeffs, cnt, _ = pr.segment_batch(prm, want_infos=False)
         ms.append(pr.timer_stop())
+    pr.profile_enable(True)
+    pr.profile_reset()
+    ev = []
+    for _ in range(5):      # the same batches with CUDA events around every kernel class, for the breakdown
+        pr.flush_l2()
+        barrier()
+        pr.timer_start()
+        pr.segment_batch(prm, want_infos=False)
+        ev.append(pr.timer_stop())
     prof = pr.profile()
     pr.profile_enable(False)
     # host tiles in -> coefficients, counts and every cloud's inlier index list out (page-locked buffers both ways)
@@ -592,11 +599,42 @@ def run_config5(args, torch, dist, D, local_rank, world, rank, peak_tf):
             "frac_of_fp32_peak_whole_call": 6.0 * pairs / (ms_b * 1e-3) / 1e12 / (peak_tf * world),
             "score_kernel_frac_of_fp32_peak": score_tf / peak_tf if score_tf else None,
             "kernel_ms": {"gather_models": prof.ms_models / 5, "score": prof.ms_score / 5, "refit": prof.ms_refit / 5,
-                          "final_count": prof.ms_compact / 5, "other": prof.ms_other / 5},
+                          "final_count": prof.ms_compact / 5, "other": prof.ms_other / 5,
+                          "event_pass_ms_per_batch": sum(ev) / len(ev),
+                          "note": "separate pass with CUDA events around every kernel class (about 0.07 ms slower per batch)"},
             "e2e_ms_per_batch": ms_e, "e2e_clouds_per_s": total / (ms_e * 1e-3),
             "e2e_note": "pinned host tiles in (%d MB per GPU), coefficients + counts + every cloud's inlier index list out into "
                         "a page-locked buffer; 2 warm-up batches, 3 timed" % (len(ids) * n_per * 16 // 2**20),
             "mean_inliers": float(res[:, 4].mean().item()), "clouds_with_plane": int((res[:, 4] >= 500).sum().item())}
+
+
+def run_config2(D, local_rank, peak_tf):
+    """BASELINE configs[1]: 1M points, 3 planes + 1 % noise + 30 % outliers, 1024 hypotheses per round, one GPU (rank 0)."""
+    from dialog_b200 import synth
+    pts = synth.three_planes_scene().points(0, 1_000_000)
+    pr = D.PlaneRansac(local_rank)
+    pr.set_cloud(pts)
+    prm = D.make_params(0.1, 1023, 500, 1.0, True, 12345, 3, D.DOT_FMA)
+    for _ in range(3):
+        pr.extract_planes(prm, want_indices=False)
+    pr.profile_reset()
+    ms = []
+    for _ in range(5):
+        pr.flush_l2()
+        pr.timer_start()
+        ex = pr.extract_planes(prm, want_indices=False)
+        ms.append(pr.timer_stop())
+    prof = pr.profile()
+    pr.close()
+    pairs = sum(int(i.n_cloud) * int(i.n_scored) for i in ex.infos)
+    step = sum(ms) / len(ms)
+    loop = list(prof.loop_ms)
+    return {"points": 1_000_000, "planes": len(ex.planes), "hypotheses_per_round": 1024, "ms_per_extraction": step,
+            "point_hypotheses_per_s": pairs / (step * 1e-3),
+            "frac_of_fp32_peak_whole_call": 6.0 * pairs / (step * 1e-3) / 1e12 / peak_tf,
+            "score_kernel_frac_of_fp32_peak": 6.0 * prof.pairs_scored / (loop[3] * 1e-3) / 1e12 / peak_tf if loop[3] > 0 else None,
+            "device_loop_ms": dict({nm: loop[i] / len(ms) for i, nm in enumerate(D.LOOP_STAGE_NAMES) if loop[i] > 0},
+                                   rounds=prof.loop_rounds / len(ms), step_minus_rounds=step - sum(loop) / len(ms))}
 
 
 def hbm_block(prof, hbm_peak):
@@ -945,6 +983,7 @@ def main():
     if not args.no_config5:
         c5 = run_config5(args, torch, dist, D, local_rank, world, rank, peak_tf)
     if rank == 0:
+        line["config2_1M"] = run_config2(D, local_rank, peak_tf) if not args.no_config5 else None
         line["config5_batch"] = c5
         if c4 and "single_launch" in c4:
             # the HBM kernels at the north star's scene size, one launch each, timed alone; the figures in roofline_hbm
