@@ -681,7 +681,8 @@ int exchange_samples(plane_ransac_ctx* c, pr::CloudView src, long long first, si
                      int4* dsp, pr::RoundState* st = nullptr, const pr::P2PTail* tail = nullptr) {
   if (c->p2p_on && (size_t)n_samples <= 3 * kP2PMaxHyps) {
     pr::launch_p2p_samples(c->p2p_view, src, first, n_local, dt, n_samples, kP2POffSamples, kP2PSamplesBytes, p2p_flag_off(P2P_SAMPLES),
-                           c->d_p2p_epoch.p + P2P_SAMPLES, dsp, c->d_p2p_aux.p + 4, c->stream, st, c->d_p2p_wait.p + 2 * P2P_SAMPLES, tail);
+                           c->d_p2p_epoch.p + P2P_SAMPLES, dsp, c->d_p2p_aux.p + 4, c->stream, st, c->d_p2p_wait.p + 2 * P2P_SAMPLES, tail,
+                           reinterpret_cast<unsigned*>(c->d_p2p_epoch.p + 4));
     return PR_OK;
   }
   pr::launch_gather_samples(src, first, n_local, dt, n_samples, dsp, 1, 0, c->stream, false, st);
@@ -694,7 +695,8 @@ int exchange_counts(plane_ransac_ctx* c, int32_t* dc, size_t n, pr::RoundState* 
   if (!c->comm) return PR_OK;
   if (c->p2p_on && n <= kP2PMaxHyps) {
     pr::launch_p2p_allreduce_i32(c->p2p_view, dc, n, kP2POffCounts, pr::kP2PMaxRanks * kP2PCountsSlot, kP2PCountsSlot, p2p_flag_off(P2P_COUNTS),
-                                 c->d_p2p_epoch.p + P2P_COUNTS, dc, c->d_p2p_aux.p + 4, c->stream, st, c->d_p2p_wait.p + 2 * P2P_COUNTS, tail);
+                                 c->d_p2p_epoch.p + P2P_COUNTS, dc, c->d_p2p_aux.p + 4, c->stream, st, c->d_p2p_wait.p + 2 * P2P_COUNTS, tail,
+                                 reinterpret_cast<unsigned*>(c->d_p2p_epoch.p + 4) + 2);
     return PR_OK;
   }
   PR_NCCL(g_nccl.AllReduce(dc, dc, n, ncclInt32, ncclSum, c->comm, c->stream));
@@ -1456,9 +1458,9 @@ int p2p_setup(plane_ransac_ctx* c) {
   if (rc != PR_OK) ok = 0;
   c->p2p_on = ok != 0;
   if (rc == PR_OK) {
-    PR_TRY(dev_reserve(c->d_p2p_epoch, 4));
+    PR_TRY(dev_reserve(c->d_p2p_epoch, 8));  // 4 epochs, then the tickets of the multi-block exchanges (2 x uint32 each)
     PR_TRY(dev_reserve(c->d_p2p_wait, 8));
-    PR_CUDA(cudaMemsetAsync(c->d_p2p_epoch.p, 0, 4 * sizeof(unsigned long long), c->stream));
+    PR_CUDA(cudaMemsetAsync(c->d_p2p_epoch.p, 0, 8 * sizeof(unsigned long long), c->stream));
     PR_CUDA(cudaMemsetAsync(c->d_p2p_wait.p, 0, 8 * sizeof(unsigned long long), c->stream));
     PR_CUDA(cudaStreamSynchronize(c->stream));
   }

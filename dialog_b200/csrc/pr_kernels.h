@@ -254,7 +254,8 @@ struct P2PTail {
 // 2 x uint64): time spent spinning on the peers' flags and the number of exchanges, accumulated.
 void launch_p2p_allreduce_i32(const P2PView& v, const int32_t* src, size_t n, size_t slot_off, size_t buffer_bytes, size_t slot_stride,
                               size_t flag_off, unsigned long long* epoch_ctr, int32_t* dst, unsigned* err, cudaStream_t s,
-                              RoundState* st = nullptr, unsigned long long* wait_ns = nullptr, const P2PTail* tail = nullptr);
+                              RoundState* st = nullptr, unsigned long long* wait_ns = nullptr, const P2PTail* tail = nullptr,
+                              unsigned* tickets = nullptr);
 void launch_p2p_allreduce_i64(const P2PView& v, const long long* src, size_t n, size_t slot_off, size_t buffer_bytes, size_t slot_stride,
                               size_t flag_off, unsigned long long* epoch_ctr, long long* dst, unsigned* err, cudaStream_t s,
                               RoundState* st = nullptr, unsigned long long* wait_ns = nullptr, const P2PTail* tail = nullptr);
@@ -266,7 +267,10 @@ void launch_p2p_allgather_i64(const P2PView& v, const long long* src, size_t n, 
 // dst receives all n_samples entries.  st: shard extent (first, n) from the device state.
 void launch_p2p_samples(const P2PView& v, CloudView cloud, long long first, size_t n, const int32_t* triples, int n_samples,
                         size_t sp_off, size_t buffer_bytes, size_t flag_off, unsigned long long* epoch_ctr, int4* dst, unsigned* err,
-                        cudaStream_t s, const RoundState* st = nullptr, unsigned long long* wait_ns = nullptr, const P2PTail* tail = nullptr);
+                        cudaStream_t s, const RoundState* st = nullptr, unsigned long long* wait_ns = nullptr, const P2PTail* tail = nullptr,
+                        unsigned* tickets = nullptr);
+// tickets (sample points and counts only): two zero-initialised counters per channel; given them, the exchange runs
+// over several blocks (pr_p2p.cu), which leave them zero again.
 
 // ---- the peel loop without the host (pr_chain.cu): per-round kernels driven by a RoundState in HBM ------------------
 // PCL's index triples for a cloud of st->n_global points: rnd = the first 3 * n_draws values of mt19937(seed) >> 1,

@@ -14,6 +14,9 @@
 // coordinates directly into all peers' sample buffers.
 #include "pr_kernels.h"
 
+#include <algorithm>
+#include <cstdlib>
+
 #include "pr_chain_dev.cuh"
 
 namespace pr {
@@ -44,19 +47,21 @@ __device__ __forceinline__ unsigned long long global_ns() {
 
 // wait_ns (optional): [0] += the longest any thread of this exchange spun on a peer's flag (ns), [1] += 1 — what a rank
 // loses per exchange to the slowest peer plus the NVLink round trip (pr_profile.p2p_wait_ms).
+// signal: whether this block raises the rank's flags (one block does: the only one, or the last of several to have its
+// stores out); every block waits for all ranks' flags.
 __device__ __forceinline__ bool p2p_signal_and_wait(const P2PView& v, size_t flag_off, unsigned long long epoch, unsigned* err,
-                                                    unsigned long long* wait_ns) {
+                                                    unsigned long long* wait_ns, bool signal = true, bool fence = true) {
   __shared__ int s_bad;
   __shared__ unsigned long long s_wait;
   if (threadIdx.x == 0) {
     s_bad = 0;
     s_wait = 0ull;
   }
-  __threadfence_system();
+  if (fence) __threadfence_system();  // (a system-scope fence behind remote stores costs 2-3 us: exactly one per exchange)
   __syncthreads();
   if ((int)threadIdx.x < v.n_ranks) {
     const int r = threadIdx.x;
-    st_release_sys(reinterpret_cast<unsigned long long*>(v.peers[r] + flag_off) + v.rank, epoch);
+    if (signal) st_release_sys(reinterpret_cast<unsigned long long*>(v.peers[r] + flag_off) + v.rank, epoch);
     const unsigned long long* f = reinterpret_cast<const unsigned long long*>(v.peers[v.rank] + flag_off) + r;
     const long long t0 = clock64();
     const unsigned long long w0 = global_ns();
@@ -211,9 +216,134 @@ __global__ void __launch_bounds__(kP2PThreads) p2p_samples_kernel(P2PView v, con
   }
 }
 
+// ---- the two larger exchanges (sample points, counts) over several blocks ---------------------------------------------
+// One SM keeps too few remote stores in flight: 196 KB of sample points through a single block take ~20 us.  With G
+// blocks every block stores its slice, fences at system scope and takes a ticket; the block that takes the last ticket
+// knows all of this rank's stores are out and raises the flags; all G blocks then wait for every rank's flag and consume
+// their slice.  A second ticket finds the block that finishes last: it advances the channel's epoch (no block can get
+// there before every block of this rank has read the epoch on entry: the flags it waits for include this rank's own),
+// resets both tickets and runs the consuming step.  G <= 16 blocks on an otherwise idle GPU are co-resident, so the
+// waiting blocks cannot starve the one that signals.
+// remote: the block's stores went to peers (system-scope fence before the ticket); otherwise to local memory only.
+__device__ __forceinline__ bool p2p_block_is_last(unsigned* ticket, bool remote) {
+  __shared__ int s_last;
+  if (remote) __threadfence_system();
+  else __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(ticket, 1u) == gridDim.x - 1 ? 1 : 0;
+  __syncthreads();
+  if (s_last) __threadfence();  // the other blocks' tickets, and with them their stores, are ordered before what follows
+  return s_last != 0;
+}
+
+constexpr int kP2PMcThreads = 256;
+constexpr int kP2PSampleBlocks = 16;
+
+__global__ void __launch_bounds__(kP2PMcThreads) p2p_samples_mc_kernel(P2PView v, const float* __restrict__ x, const float* __restrict__ y,
+                                                                       const float* __restrict__ z, long long first, size_t n,
+                                                                       const int32_t* __restrict__ triples, int n_samples, size_t sp_off,
+                                                                       size_t buffer_bytes, size_t flag_off, unsigned long long* epoch_ctr,
+                                                                       int4* __restrict__ dst, unsigned* err, const RoundState* st,
+                                                                       unsigned long long* wait_ns, P2PTail tail, unsigned* tickets) {
+  unsigned long long epoch;
+  if (!p2p_enter(st, epoch_ctr, err, &epoch, tail.kind)) return;
+  if (st != nullptr) {
+    first = st->first;
+    n = (size_t)st->n_local;
+  }
+  sp_off += (size_t)(epoch & 1ull) * buffer_bytes;
+  const int gtid = blockIdx.x * kP2PMcThreads + threadIdx.x, gstride = gridDim.x * kP2PMcThreads;
+  for (int base = gtid; base < n_samples; base += 4 * gstride) {
+    long long local[4];
+    float px[4], py[4], pz[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int s = base + j * gstride;
+      local[j] = s < n_samples ? (long long)triples[s] - first : -1ll;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const bool mine = local[j] >= 0 && local[j] < (long long)n;
+      px[j] = mine ? x[local[j]] : 0.0f;
+      py[j] = mine ? y[local[j]] : 0.0f;
+      pz[j] = mine ? z[local[j]] : 0.0f;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (local[j] >= 0 && local[j] < (long long)n) {
+        const int4 val = make_int4(__float_as_int(px[j]), __float_as_int(py[j]), __float_as_int(pz[j]), 0x3F800000);
+        for (int r = 0; r < v.n_ranks; ++r) reinterpret_cast<int4*>(v.peers[r] + sp_off)[base + j * gstride] = val;
+      }
+    }
+  }
+  const bool signal = p2p_block_is_last(&tickets[0], true);
+  if (!p2p_signal_and_wait(v, flag_off, epoch, err, blockIdx.x == 0 ? wait_ns : nullptr, signal, false)) return;
+  const int4* in = reinterpret_cast<const int4*>(v.peers[v.rank] + sp_off);
+#pragma unroll 4
+  for (int s = gtid; s < n_samples; s += gstride) dst[s] = __ldcg(in + s);
+  if (tail.kind == P2PTail::kModels) {  // K1b: this block's share of the n_samples / 3 models
+    for (int k = gtid; k < n_samples / 3; k += gstride) {
+      float4 h;
+      const bool ok = model_from_sample(__ldcg(in + 3 * k), __ldcg(in + 3 * k + 1), __ldcg(in + 3 * k + 2), &h);
+      tail.hyps_out[k] = h;
+      tail.good_out[k] = ok ? 1 : 0;
+    }
+  }
+  if (p2p_block_is_last(&tickets[1], false) && threadIdx.x == 0) {
+    *epoch_ctr = epoch;
+    tickets[0] = 0u;
+    tickets[1] = 0u;
+  }
+}
+
+// counts: dst[i] = sum over ranks of src[i], G blocks of kP2PThreads; the block that finishes last runs computeModel's
+// decision over the complete sums (tail.kind == kReplay).
+__global__ void __launch_bounds__(kP2PThreads) p2p_allreduce_i32_mc_kernel(P2PView v, const int32_t* src, size_t n, size_t slot_off,
+                                                                           size_t buffer_bytes, size_t slot_stride, size_t flag_off,
+                                                                           unsigned long long* epoch_ctr, int32_t* dst, unsigned* err,
+                                                                           RoundState* st, unsigned long long* wait_ns, P2PTail tail,
+                                                                           unsigned* tickets) {
+  unsigned long long epoch;
+  if (!p2p_enter(st, epoch_ctr, err, &epoch, tail.kind)) return;
+  slot_off += (size_t)(epoch & 1ull) * buffer_bytes;
+  const size_t gtid = (size_t)blockIdx.x * kP2PThreads + threadIdx.x, gstride = (size_t)gridDim.x * kP2PThreads;
+  for (size_t i = gtid; i < n; i += gstride) {
+    const int32_t mine = src[i];
+    for (int r = 0; r < v.n_ranks; ++r)
+      reinterpret_cast<int32_t*>(v.peers[r] + slot_off + (size_t)v.rank * slot_stride)[i] = mine;
+  }
+  const bool signal = p2p_block_is_last(&tickets[0], true);
+  if (!p2p_signal_and_wait(v, flag_off, epoch, err, blockIdx.x == 0 ? wait_ns : nullptr, signal, false)) return;
+  for (size_t i = gtid; i < n; i += gstride) {  // the same slice this block read from src above: in place is fine
+    int32_t acc = 0;
+    for (int r = 0; r < v.n_ranks; ++r)
+      acc += __ldcg(reinterpret_cast<const int32_t*>(v.peers[v.rank] + slot_off + (size_t)r * slot_stride) + i);
+    dst[i] = acc;
+  }
+  if (!p2p_block_is_last(&tickets[1], false)) return;
+  if (threadIdx.x == 0) {
+    *epoch_ctr = epoch;
+    tickets[0] = 0u;
+    tickets[1] = 0u;
+  }
+  if (tail.kind == P2PTail::kReplay)  // every block's sums are in dst and visible (fence + ticket)
+    chain_replay_block(reinterpret_cast<const int32_t*>(dst), tail.good, (int)n, st, tail.rec);
+}
+
 void launch_p2p_allreduce_i32(const P2PView& v, const int32_t* src, size_t n, size_t slot_off, size_t buffer_bytes, size_t slot_stride,
                               size_t flag_off, unsigned long long* epoch_ctr, int32_t* dst, unsigned* err, cudaStream_t s, RoundState* st,
-                              unsigned long long* wait_ns, const P2PTail* tail) {
+                              unsigned long long* wait_ns, const P2PTail* tail, unsigned* tickets) {
+  static const bool mc = [] { const char* e = getenv("PR_P2P_MC"); return !(e && atoi(e) == 0); }();
+  const unsigned blocks = (unsigned)std::min<size_t>(8, (n + kP2PThreads - 1) / kP2PThreads);
+  if (mc && tickets != nullptr && blocks > 1) {
+    if (st != nullptr)
+      launch_chained(p2p_allreduce_i32_mc_kernel, dim3(blocks), dim3(kP2PThreads), 0, s, v, src, n, slot_off, buffer_bytes, slot_stride, flag_off,
+                     epoch_ctr, dst, err, st, wait_ns, tail ? *tail : P2PTail(), tickets);
+    else
+      p2p_allreduce_i32_mc_kernel<<<blocks, kP2PThreads, 0, s>>>(v, src, n, slot_off, buffer_bytes, slot_stride, flag_off, epoch_ctr, dst, err, st,
+                                                                 wait_ns, tail ? *tail : P2PTail(), tickets);
+    return;
+  }
   if (st != nullptr)
     launch_chained(p2p_allreduce_kernel<int32_t>, dim3(1), dim3(kP2PThreads), 0, s, v, src, n, slot_off, buffer_bytes, slot_stride, flag_off, epoch_ctr,
                    dst, err, st, wait_ns, tail ? *tail : P2PTail());
@@ -246,7 +376,18 @@ void launch_p2p_allgather_i64(const P2PView& v, const long long* src, size_t n, 
 
 void launch_p2p_samples(const P2PView& v, CloudView cloud, long long first, size_t n, const int32_t* triples, int n_samples,
                         size_t sp_off, size_t buffer_bytes, size_t flag_off, unsigned long long* epoch_ctr, int4* dst, unsigned* err,
-                        cudaStream_t s, const RoundState* st, unsigned long long* wait_ns, const P2PTail* tail) {
+                        cudaStream_t s, const RoundState* st, unsigned long long* wait_ns, const P2PTail* tail, unsigned* tickets) {
+  static const bool mc = [] { const char* e = getenv("PR_P2P_MC"); return !(e && atoi(e) == 0); }();
+  if (mc && tickets != nullptr && n_samples > 4 * kP2PMcThreads) {
+    const unsigned blocks = (unsigned)std::min(kP2PSampleBlocks, (n_samples + 4 * kP2PMcThreads - 1) / (4 * kP2PMcThreads));
+    if (st != nullptr)
+      launch_chained(p2p_samples_mc_kernel, dim3(blocks), dim3(kP2PMcThreads), 0, s, v, cloud.x, cloud.y, cloud.z, first, n, triples, n_samples,
+                     sp_off, buffer_bytes, flag_off, epoch_ctr, dst, err, st, wait_ns, tail ? *tail : P2PTail(), tickets);
+    else
+      p2p_samples_mc_kernel<<<blocks, kP2PMcThreads, 0, s>>>(v, cloud.x, cloud.y, cloud.z, first, n, triples, n_samples, sp_off, buffer_bytes,
+                                                             flag_off, epoch_ctr, dst, err, st, wait_ns, tail ? *tail : P2PTail(), tickets);
+    return;
+  }
   if (st != nullptr)
     launch_chained(p2p_samples_kernel, dim3(1), dim3(kP2PThreads), 0, s, v, cloud.x, cloud.y, cloud.z, first, n, triples, n_samples, sp_off,
                    buffer_bytes, flag_off, epoch_ctr, dst, err, st, wait_ns, tail ? *tail : P2PTail());
