@@ -192,6 +192,7 @@ struct plane_ransac_ctx {
   DevBuf<int32_t> d_batch_tri;
   size_t batch_tri_dev_valid = 0;  // number of triple entries of batch_tri that are on the device
   std::vector<int32_t> batch_tri;  // the K triples every cloud of the batch draws (same size, same seed)
+  std::vector<cudaEvent_t> head_ev;  // per queued round: its head (draws, sample exchange, models) is done
   std::vector<unsigned long long> timeline;  // last extract call: kStampSlots stamps per device-loop round
   size_t batch_tri_n = 0;
   unsigned batch_tri_seed = 0;
@@ -1138,6 +1139,16 @@ int run_chain(plane_ransac_ctx* c, const pr_params* prm, PeelCursor& cur, float*
     PR_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     c->round_ev.push_back(e);
   }
+  // Sharded runs that return index lists: a plane's lists must not travel while the next round's head runs its
+  // exchanges — a system-scope fence issued while a device-to-host DMA saturates PCIe waits tens of microseconds — so
+  // the copy of plane r starts once round r + 1 has reached its scoring launch (head_ev) and is over long before that
+  // launch ends.
+  const bool stagger_lists = sharded && lists.wanted() && lists.overlap;
+  while (stagger_lists && (int)c->head_ev.size() < max_rounds) {
+    cudaEvent_t e = nullptr;
+    PR_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    c->head_ev.push_back(e);
+  }
   const size_t slots = pr::draw_table_slots(K);
   PR_TRY(dev_reserve(c->d_draw_table, slots));
   PR_TRY(dev_reserve(c->d_draw_coll, (size_t)pr::kDrawCollCap + 4));
@@ -1200,6 +1211,7 @@ int run_chain(plane_ransac_ctx* c, const pr_params* prm, PeelCursor& cur, float*
           pr::launch_gather_models(src, c->d_triples.p, K, c->d_sample_pts.p, c->d_hyps.p, c->d_good.p, rs, c->stream);
         }
       }
+      if (stagger_lists) PR_CUDA(cudaEventRecord(c->head_ev[r], c->stream));
       {
         Span sp(c, KC_SCORE, 0);
         c->prof.launches_score += pr::launch_score(src, n_bound, 1, 0, c->d_hyps.p, K, t, prm->dot_order, c->d_counts.p, c->num_sms, c->stream, rs);
@@ -1323,7 +1335,7 @@ int run_chain(plane_ransac_ctx* c, const pr_params* prm, PeelCursor& cur, float*
     cur.off = begin + (size_t)rec.n_inl_local;
     plane_offsets[cur.planes + 1] = cur.off;
     ++cur.planes;
-    PR_TRY(lists.on_plane(c, begin, cur.off, c->round_ev[r]));
+    PR_TRY(lists.on_plane(c, begin, cur.off, stagger_lists && r + 1 < launched ? c->head_ev[r + 1] : c->round_ev[r]));
     cur.src = dst_of[r];
     cur.n_local = (size_t)rec.n_rem_local;
     cur.n_global = rec.n_rem_global;
@@ -1572,6 +1584,7 @@ void plane_ransac_destroy(plane_ransac_ctx* c) {
   dev_free(c->d_state); pin_free(c->h_state); pin_free(c->h_recs); dev_free(c->d_chain_tickets);
   dev_free(c->d_rnd); dev_free(c->d_draw_table); dev_free(c->d_draw_coll);
   for (cudaEvent_t e : c->round_ev) cudaEventDestroy(e);
+  for (cudaEvent_t e : c->head_ev) cudaEventDestroy(e);
   if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
   dev_free(c->staged_mem);
   for (int i = 0; i < 2; ++i) { dev_free(c->work_mem[i]); dev_free(c->work_orig[i]); }
