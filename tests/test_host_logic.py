@@ -41,6 +41,18 @@ def test_parallel_sampler_hands_crowded_rounds_back():
         assert got is None or (got == D.host_draw_triples(n, k)).all()
 
 
+def test_parallel_sampler_dependency_chains_random_seeds():
+    """Rounds the size the bench runs (tens to hundreds of colliding picks among 3K ops, the listed ops often next to each
+    other in time): without a swap inside the head every listed op is resolved by following its own dependency chain; with
+    one, by the sequential replay.  Both must give PCL's triples for every seed."""
+    rng = np.random.default_rng(11)
+    for n, k, reps in ((1_000_000, 4096, 40), (300_000, 2048, 40), (2_000_000, 8192, 15), (100_000, 1000, 60), (50_000, 512, 60)):
+        for _ in range(reps):
+            seed = int(rng.integers(1, 2**31 - 1))
+            got = D.host_draw_triples_parallel(n, k, seed=seed)
+            assert got is not None and (got == D.host_draw_triples(n, k, seed=seed)).all(), (n, k, seed)
+
+
 def test_sampler_rejects_tiny_clouds():
     with pytest.raises(D.PlaneRansacError):
         D.host_draw_triples(2, 1)
