@@ -2369,9 +2369,9 @@ int segment_batch_device(plane_ransac_ctx* c, const pr_params* prm, float* coeff
   // One dependent chain of launches (each set up while its predecessor drains: pr_chain_dev.cuh), no memsets between
   // them: the models launch clears the counts and the flag, the decision launch clears the moments.
   {
-    Span sp(c, KC_MODELS, 2);
-    pr::launch_gather_samples(c->batch_view, 0, n, c->d_batch_tri.p, 3 * K, c->d_sample_pts.p, (int)C, stride, c->stream);
-    pr::launch_models(c->d_sample_pts.p, (int)CK, c->d_hyps.p, c->d_good.p, c->stream, c->d_counts.p, d_flag, true);
+    Span sp(c, KC_MODELS, 1);
+    pr::launch_batch_gather_models(c->batch_view, n, stride, (int)C, c->d_batch_tri.p, K, c->d_sample_pts.p, c->d_hyps.p, c->d_good.p,
+                                   c->d_counts.p, d_flag, c->stream);
   }
   {
     Span sp(c, KC_SCORE, 0);

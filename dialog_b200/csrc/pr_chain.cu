@@ -401,6 +401,44 @@ void launch_batch_count(CloudView clouds, size_t n_per, size_t stride, int n_clo
   else launch_chained(batch_count_kernel<0>, dim3(n_clouds), dim3(256), 0, s, clouds.x, clouds.y, clouds.z, n_per, stride, planes, best, t, cnt);
 }
 
+// K1a + K1b for a batch of equal-sized clouds that all draw the same K triples: thread (k, cloud) gathers its three sample
+// points (kept: the refit takes its pivot from there), forms the model, and clears the count the scoring launch
+// accumulates into; thread (0, 0) clears the batch's bad-sample flag.
+__global__ void __launch_bounds__(128) batch_gather_models_kernel(const float* __restrict__ X, const float* __restrict__ Y,
+                                                                  const float* __restrict__ Z, size_t n_per, size_t stride,
+                                                                  const int32_t* __restrict__ triples, int K, int4* __restrict__ sample_pts,
+                                                                  float4* __restrict__ hyps, int32_t* __restrict__ good,
+                                                                  int32_t* __restrict__ counts, int* __restrict__ flag) {
+  pdl_wait();
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t c = blockIdx.y;
+  if (k == 0 && c == 0) *flag = 0;
+  if (k >= K) return;
+  const size_t o = c * (size_t)K + (size_t)k;
+  int4 q[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const long long j = (long long)triples[3 * k + i];
+    q[i] = make_int4(0, 0, 0, 0);
+    if (j >= 0 && j < (long long)n_per) {
+      const size_t p = c * stride + (size_t)j;
+      q[i] = make_int4(__float_as_int(X[p]), __float_as_int(Y[p]), __float_as_int(Z[p]), 0x3F800000);
+    }
+    sample_pts[3 * o + i] = q[i];
+  }
+  float4 h;
+  const bool ok = model_from_sample(q[0], q[1], q[2], &h);
+  hyps[o] = h;
+  good[o] = ok ? 1 : 0;
+  counts[o] = 0;
+}
+
+void launch_batch_gather_models(CloudView clouds, size_t n_per, size_t stride, int n_clouds, const int32_t* triples, int K, int4* sample_pts,
+                                float4* hyps, int32_t* good, int32_t* counts, int* flag, cudaStream_t s) {
+  launch_chained(batch_gather_models_kernel, dim3((K + 127) / 128, n_clouds), dim3(128), 0, s, clouds.x, clouds.y, clouds.z, n_per, stride, triples, K,
+                 sample_pts, hyps, good, counts, flag);
+}
+
 void launch_batch_replay(const int32_t* counts, const int32_t* good, int K, int n_clouds, int32_t* best, int32_t* best_count, int* any_bad,
                          RefitOut* refit_to_clear, cudaStream_t s) {
   launch_chained(batch_replay_kernel, dim3(n_clouds), dim3(128), 0, s, counts, good, K, best, best_count, any_bad, refit_to_clear);

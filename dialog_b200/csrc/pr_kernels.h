@@ -292,6 +292,9 @@ void launch_finish(RoundState* st, const float4* hyps, const int32_t* triples, c
                    int n_draws, RoundRecord* rec, cudaStream_t s);
 
 // ---- batch of small clouds without the host in the loop (score-all mode; pr_chain.cu) ----------------------------------
+// K1 for a batch whose clouds all draw the same K triples: sample points + models per (cloud, draw); clears counts and flag.
+void launch_batch_gather_models(CloudView clouds, size_t n_per, size_t stride, int n_clouds, const int32_t* triples, int K, int4* sample_pts,
+                                float4* hyps, int32_t* good, int32_t* counts, int* flag, cudaStream_t s);
 // best[c] = computeModel's winner among cloud c's K draws (-1 + *any_bad when a degenerate sample needs PCL's redraw).
 // refit_to_clear (optional): cloud c's moments are zeroed on the way (the refit pass accumulates into them).
 void launch_batch_replay(const int32_t* counts, const int32_t* good, int K, int n_clouds, int32_t* best, int32_t* best_count, int* any_bad,
