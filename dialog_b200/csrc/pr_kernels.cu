@@ -554,21 +554,40 @@ __global__ void __launch_bounds__(kScoreThreads, H <= 4 ? 4 : 2)
   int cnt[H];
   unsigned acc[H];
   int cur_cloud = -1;
+  // item mode: (cloud, tile) of the item being scored and of the one the ring is refilled with, advanced step by step
+  // (a division per tile is ~1 % of a warp's work on a 128-point share)
+  int it_c = 0, it_t = 0, nx_c = 0, nx_t = 0;
+  if (pts_per_cta == 0) {
+    it_c = w.item_begin / tiles_per_cloud;
+    it_t = w.item_begin - it_c * tiles_per_cloud;
+    const int nx = w.item_begin + kScoreStages;
+    nx_c = nx / tiles_per_cloud;
+    nx_t = nx - nx_c * tiles_per_cloud;
+  }
+  int pending = 0;  // 128-point chunks accumulated in the packed counters since the last fold (at most 3)
 
   for (int it = 0; it < n_items; ++it) {
     const int s = it % kScoreStages;
     int c, len;
     size_t off;
-    score_tile_of(w, it, tiles_per_cloud, cloud_stride, pts_per_cta, &c, &off, &len);
+    if (pts_per_cta == 0) {
+      c = it_c;
+      off = (size_t)it_c * cloud_stride + (size_t)it_t * kTilePoints;
+      len = kTilePoints;
+    } else {
+      score_tile_of(w, it, tiles_per_cloud, cloud_stride, pts_per_cta, &c, &off, &len);
+    }
     const int pts_per_warp = len / warps_p;  // a multiple of 128: len is a multiple of 128 * warps_p
     const int p_begin = wp * pts_per_warp;
     if (c != cur_cloud) {
       if (cur_cloud >= 0) {
 #pragma unroll
         for (int j = 0; j < H; ++j) {
+          cnt[j] += (int)(((acc[j] >> 23) * 383u) & 511u);
           const int k = k0 + j * k_stride;
           if (k < k_end && cnt[j] != 0) atomicAdd(&counts[(size_t)cur_cloud * K + k], cnt[j]);
         }
+        pending = 0;
       }
 #pragma unroll
       for (int j = 0; j < H; ++j) {
@@ -588,8 +607,8 @@ __global__ void __launch_bounds__(kScoreThreads, H <= 4 ? 4 : 2)
     const float* sz = sx + 2 * kTilePoints;
 
     // 128-point chunks (32 steps of 4 points): compile-time trip count; the packed counters hold up to 511 increments,
-    // so they are folded into the plain counters every third chunk (384 increments) and at the end of the tile
-    int pending = 0;
+    // so they are folded into the plain counters every third chunk (384 increments), across tiles, and before the
+    // counts leave the registers
     for (int p = 0; p < pts_per_warp; p += 4 * kScoreStepsPerFlush) {
       // software pipeline: the points of step q + 1 are loaded while step q computes (the load issued by
       // the last step of a tile reads 16 bytes past its plane: the next plane, or the stage's tail pad)
@@ -628,10 +647,8 @@ __global__ void __launch_bounds__(kScoreThreads, H <= 4 ? 4 : 2)
         }
       }
     }
-#pragma unroll
-    for (int j = 0; j < H; ++j) {
-      cnt[j] += (int)(((acc[j] >> 23) * 383u) & 511u);
-      acc[j] = 0u;
+    if (pts_per_cta == 0) {
+      if (++it_t == tiles_per_cloud) { it_t = 0; ++it_c; }
     }
 
     // release the stage; the last warp to finish refills it (no thread ever spins on an empty slot)
@@ -647,14 +664,23 @@ __global__ void __launch_bounds__(kScoreThreads, H <= 4 ? 4 : 2)
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           int c_, len_;
           size_t off_;
-          score_tile_of(w, next, tiles_per_cloud, cloud_stride, pts_per_cta, &c_, &off_, &len_);
+          if (pts_per_cta == 0) {
+            off_ = (size_t)nx_c * cloud_stride + (size_t)nx_t * kTilePoints;
+            len_ = kTilePoints;
+          } else {
+            score_tile_of(w, next, tiles_per_cloud, cloud_stride, pts_per_cta, &c_, &off_, &len_);
+          }
           score_issue_tile(X, Y, Z, off_, len_, &s_pts[s][0], &s_full[s]);
         }
       }
     }
+    if (pts_per_cta == 0) {
+      if (++nx_t == tiles_per_cloud) { nx_t = 0; ++nx_c; }
+    }
   }
 #pragma unroll
   for (int j = 0; j < H; ++j) {
+    cnt[j] += (int)(((acc[j] >> 23) * 383u) & 511u);
     const int k = k0 + j * k_stride;
     if (k < k_end && cnt[j] != 0) atomicAdd(&counts[(size_t)cur_cloud * K + k], cnt[j]);
   }

@@ -1,4 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "batch" 2>&1 | tail -2
+timeout 2400 python -m pytest tests -m gpu -x -q > gpurun_out/r02o_pytest.log 2>&1; echo "pytest exit $?" >> gpurun_out/r02o_pytest.log; tail -4 gpurun_out/r02o_pytest.log
 timeout 200 python ubench/batch_rate.py 2>&1 | tail -1
+timeout 600 python ubench/host_overhead.py 2>&1 | grep "no events"
+timeout 900 python ubench/stress_loops.py 2>&1 | tail -1
