@@ -183,10 +183,8 @@ struct plane_ransac_ctx {
   DevBuf<int4> d_batch_pts;
   DevBuf<int32_t> d_batch_cnt;
   // device-driven batch path: per-cloud winner, raw model, list offsets, the lists; grid exponents uploaded at staging
-  DevBuf<int32_t> d_batch_best, d_batch_bestcnt, d_batch_sexp, d_batch_lists;
-  DevBuf<float4> d_batch_raw;
+  DevBuf<int32_t> d_batch_sexp, d_batch_lists;
   DevBuf<unsigned long long> d_batch_offs;
-  DevBuf<int> d_batch_flag;
   DevBuf<uint32_t> d_batch_out;    // flag | best | best count | final count | raw | refined, read back in one copy
   PinBuf<uint32_t> h_batch_out;
   DevBuf<int32_t> d_batch_tri;
@@ -1603,8 +1601,8 @@ void plane_ransac_destroy(plane_ransac_ctx* c) {
   dev_free(c->d_nrm_temp);
   dev_free(c->d_batch_bbox); dev_free(c->d_batch_idx); dev_free(c->d_batch_scale); dev_free(c->d_batch_refit);
   dev_free(c->d_batch_hyps); dev_free(c->d_batch_pts); dev_free(c->d_batch_cnt);
-  dev_free(c->d_batch_best); dev_free(c->d_batch_bestcnt); dev_free(c->d_batch_sexp); dev_free(c->d_batch_lists);
-  dev_free(c->d_batch_raw); dev_free(c->d_batch_offs); dev_free(c->d_batch_flag);
+  dev_free(c->d_batch_sexp); dev_free(c->d_batch_lists);
+  dev_free(c->d_batch_offs);
   dev_free(c->d_batch_out); pin_free(c->h_batch_out); dev_free(c->d_batch_tri);
   pin_free(c->h_triples); pin_free(c->h_counts); pin_free(c->h_good); pin_free(c->h_refit); pin_free(c->h_sample_pts);
   for (cudaEvent_t e : c->pend.ev) cudaEventDestroy(e);
@@ -2358,7 +2356,6 @@ int segment_batch_device(plane_ransac_ctx* c, const pr_params* prm, float* coeff
   int32_t* d_bestcnt = d_best + C;
   int32_t* d_cnt = prm->optimize_coefficients ? d_bestcnt + C : d_bestcnt;  // without the refit the raw model's count is final
   PR_TRY(dev_reserve(c->d_batch_refit, C));
-  PR_TRY(dev_reserve(c->d_batch_hyps, C));
   if (c->batch_tri_dev_valid != 3 * (size_t)K) {  // the triples only change with (n, seed, K): uploaded once
     std::memcpy(c->h_triples.p, c->batch_tri.data(), 3 * (size_t)K * sizeof(int32_t));
     PR_TRY(dev_reserve(c->d_batch_tri, 3 * (size_t)K));

@@ -337,7 +337,6 @@ __global__ void __launch_bounds__(256) gather_samples_kernel(const float* __rest
                                                              const int32_t* __restrict__ triples, int n_samples,
                                                              int4* __restrict__ out, int n_clouds, size_t cloud_stride,
                                                              bool per_cloud_triples, const RoundState* __restrict__ st) {
-  pdl_wait();  // returns at once unless launched as a programmatic dependent (batch path)
   if (st != nullptr) {  // peel loop without the host: this round's shard extent lives on the device
     if (st->stop) return;
     first = st->first;
@@ -359,13 +358,9 @@ __global__ void __launch_bounds__(256) gather_samples_kernel(const float* __rest
 
 // model_from_sample (PCL isSampleGood + computeModelCoefficients) lives in pr_chain_dev.cuh: the exchange kernels use it too.
 __global__ void __launch_bounds__(128) models_kernel(const int4* __restrict__ sample_pts, int n_models,
-                                                     float4* __restrict__ hyps, int32_t* __restrict__ good,
-                                                     int32_t* __restrict__ counts_to_clear, int* __restrict__ flag_to_clear) {
-  pdl_wait();
+                                                     float4* __restrict__ hyps, int32_t* __restrict__ good) {
   int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k == 0 && flag_to_clear != nullptr) *flag_to_clear = 0;
   if (k >= n_models) return;
-  if (counts_to_clear != nullptr) counts_to_clear[k] = 0;  // the scoring launch that follows accumulates into it
   float4 h;
   const bool ok = model_from_sample(sample_pts[3 * k], sample_pts[3 * k + 1], sample_pts[3 * k + 2], &h);
   hyps[k] = h;
@@ -416,14 +411,9 @@ void launch_gather_samples(CloudView cloud, long long first, size_t n, const int
                                                          sample_pts, n_clouds, cloud_stride, per_cloud_triples, st);  // first of its sequence: plain
 }
 
-void launch_models(const int4* sample_pts, int n_models_total, float4* hyps, int32_t* good, cudaStream_t s, int32_t* counts_to_clear,
-                   int* flag_to_clear, bool chained) {
+void launch_models(const int4* sample_pts, int n_models_total, float4* hyps, int32_t* good, cudaStream_t s) {
   if (n_models_total <= 0) return;
-  if (chained)
-    launch_chained(models_kernel, dim3((n_models_total + 127) / 128), dim3(128), 0, s, sample_pts, n_models_total, hyps, good, counts_to_clear,
-                   flag_to_clear);
-  else
-    models_kernel<<<(n_models_total + 127) / 128, 128, 0, s>>>(sample_pts, n_models_total, hyps, good, counts_to_clear, flag_to_clear);
+  models_kernel<<<(n_models_total + 127) / 128, 128, 0, s>>>(sample_pts, n_models_total, hyps, good);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -126,10 +126,7 @@ void launch_gather_samples(CloudView cloud, long long first, size_t n, const int
 void launch_gather_models(CloudView cloud, const int32_t* triples, int n_models, int4* sample_pts, float4* hyps, int32_t* good,
                           const RoundState* st, cudaStream_t s);
 // K1b: plane through each sample triple, PCL op order, no contraction; NaN plane + good = 0 when degenerate.
-// counts_to_clear / flag_to_clear (optional): zeroed on the way (one entry per model / one int), so that the scoring launch
-// that follows needs no separate memset; chained: launched as a programmatic dependent of the kernel before it.
-void launch_models(const int4* sample_pts, int n_models_total, float4* hyps, int32_t* good, cudaStream_t s,
-                   int32_t* counts_to_clear = nullptr, int* flag_to_clear = nullptr, bool chained = false);
+void launch_models(const int4* sample_pts, int n_models_total, float4* hyps, int32_t* good, cudaStream_t s);
 
 // K2: counts[c * K + k] += |{ i in cloud c : |hyp[c*K+k] . (p_i, 1)| < t }|.  counts must be zeroed.
 // Returns the number of kernel launches it made (K is cut into launches that fill their lane slots).
